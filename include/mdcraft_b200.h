@@ -1,0 +1,213 @@
+/*
+ * mdcraft_b200.h — C ABI of libmdcraft_b200.so
+ *
+ * B200-native (sm_100a) replacement for the per-frame arithmetic of
+ * MDCraft's `mdcraft.analysis.structure` S(q) and g(r) path.  The two pure
+ * functions below the reference's analysis classes are the cut:
+ *
+ *   delta_fourier_transform_sum(qs f64[Nq,3], rs f64[N,3]) -> c128[Nq]
+ *       /root/reference/src/mdcraft/analysis/structure.py:1240-1280
+ *   radial_histogram(pos_a, pos_b, n_bins, range_, dimensions, exclusion) -> intp[B]
+ *       /root/reference/src/mdcraft/analysis/structure.py:34-131
+ *
+ * plus the per-frame accumulation the classes wrap around them
+ * (StructureFactor._single_frame structure.py:1940-1991,
+ *  RadialDistributionFunction._single_frame structure.py:868-920), which is
+ * exposed as "plans" so that frame blocks can be pushed without a host round
+ * trip per frame.
+ *
+ * Conventions
+ *   - plain C: opaque handles, pointers and sizes; no torch / C++ types.
+ *   - every entry returns int: 0 = MDC_OK, negative = error; mdc_last_error()
+ *     returns a thread-local message.  No C++ exception crosses the ABI.
+ *   - "pos" arrays are float32 AoS (F, N, 3), exactly what MDAnalysis'
+ *     AtomGroup.positions yields per frame; `on_device` != 0 means the pointer
+ *     is a CUDA device pointer on the plan's device, else host memory (pinned
+ *     memory makes the copy asynchronous).
+ *   - a context owns two CUDA streams (copies + layout kernels / analysis
+ *     kernels) shared by its plans; a context and its plans are single-threaded.
+ *     Buffers passed to *_push may be reused once the call returns (the library
+ *     stages them before returning); the analysis kernels keep running
+ *     asynchronously until *_read / mdc_synchronize.
+ *   - the library owns all device memory for the lifetime of the plan; the
+ *     *_accum_ptr calls expose the on-device accumulators so a caller can hand
+ *     them to NCCL (frame-sharded multi-GPU runs all-reduce them once).
+ */
+#ifndef MDCRAFT_B200_H
+#define MDCRAFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDC_OK                 0
+#define MDC_ERR_INVALID       -1   /* bad argument */
+#define MDC_ERR_CUDA          -2   /* CUDA runtime error (message has details) */
+#define MDC_ERR_NOMEM         -3
+#define MDC_ERR_UNSUPPORTED   -4   /* e.g. triclinic box */
+
+#define MDC_PRECISION_FP32     0   /* phases exact (fixed point / FP64), sin/cos on the SFU, FP32 partial sums */
+#define MDC_PRECISION_FP64     1   /* everything FP64 (reference arithmetic) */
+
+/* S(q) kernel selection for reciprocal-lattice plans in FP32 precision. */
+#define MDC_SQ_ALGO_AUTO       0
+#define MDC_SQ_ALGO_DIRECT     1   /* one sincos per (q, particle) term on the SFU */
+#define MDC_SQ_ALGO_POLY       2   /* same terms, sincos as FP32-pipe polynomial */
+#define MDC_SQ_ALGO_FACTORED   3   /* per-axis phasor tables + complex products (FP32 pipe) */
+
+typedef struct mdc_ctx      mdc_ctx;
+typedef struct mdc_sq_plan  mdc_sq_plan;
+typedef struct mdc_rdf_plan mdc_rdf_plan;
+
+/* ---- library / context ------------------------------------------------- */
+
+int          mdc_version(void);
+const char  *mdc_last_error(void);
+
+/* Binds a context to CUDA device `device` (creates nothing on other devices). */
+int  mdc_create(int device, mdc_ctx **out);
+int  mdc_destroy(mdc_ctx *ctx);
+int  mdc_device_info(mdc_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
+                     int *sm_clock_khz, int64_t *global_mem_bytes);
+/* Blocks until all work queued by plans of this context has finished. */
+int  mdc_synchronize(mdc_ctx *ctx);
+
+/* ---- S(q): StructureFactor ---------------------------------------------- */
+
+/*
+ * Creates an S(q) plan.
+ *
+ * Wavevectors = [reciprocal-lattice part] ++ [explicit part], in that order
+ * (the order the reference stacks them, structure.py:1837-1872):
+ *   lattice part (n_points > 0): q = 2*pi*(a/L0[0], b/L0[1], c/L0[2]),
+ *     a,b,c in [0, n_points), flat order b*n^2 + a*n + c (np.meshgrid 'xy'),
+ *     filtered by |q| <= q_max when q_max >= 0 (structure.py:1883-1887).  The
+ *     grid is generated on the device with the reference's FP64 operation
+ *     order; nothing of size Nq is uploaded.
+ *   explicit part (n_explicit > 0): q_explicit f64 (n_explicit, 3), used as is
+ *     (user `wavevectors=` or the off-lattice `n_surfaces` points); the caller
+ *     applies q_max to these.
+ *
+ * Groups: positions pushed later hold the groups concatenated in order;
+ *   group g has group_sizes[g] particles (the reference's _slices,
+ *   structure.py:1889-1899).
+ * Pairs: n_pairs x 2 group indices (j, k); (-1, -1) means "all particles as
+ *   one group" (mode=None).  j == k accumulates |rho_j|^2, j != k accumulates
+ *   2 Re(rho_j conj(rho_k))  (structure.py:1953-1970).
+ */
+int  mdc_sq_plan_create(mdc_ctx *ctx,
+                        int n_points, const double L0[3], double q_max,
+                        const double *q_explicit, int64_t n_explicit,
+                        int n_groups, const int64_t *group_sizes,
+                        int n_pairs, const int *pairs,
+                        int precision, int algo,
+                        mdc_sq_plan **out);
+int  mdc_sq_plan_destroy(mdc_sq_plan *plan);
+
+/* Number of wavevectors kept (lattice after q_max + explicit). */
+int64_t mdc_sq_num_wavevectors(mdc_sq_plan *plan);
+/* Copies the device-built wavevectors, f64 (Nq, 3), to host memory. */
+int  mdc_sq_wavevectors(mdc_sq_plan *plan, double *q_out);
+
+/*
+ * Accumulates n_frames frames:  ssf[p, :] += per-frame pair products.
+ * pos: f32 (n_frames, N, 3) with N = sum(group_sizes).  Asynchronous with
+ * respect to the device; synchronous with respect to the host buffer.
+ */
+int  mdc_sq_push(mdc_sq_plan *plan, const float *pos, int n_frames, int on_device);
+
+/* Un-normalised sums f64 (n_pairs, Nq) and the number of frames pushed. */
+int  mdc_sq_read(mdc_sq_plan *plan, double *ssf_out, int64_t *n_frames_out);
+int  mdc_sq_reset(mdc_sq_plan *plan);
+/* Device pointer / element count of the f64 accumulator (for NCCL). */
+int  mdc_sq_accum_ptr(mdc_sq_plan *plan, void **dev_ptr, int64_t *n_elems);
+/* Overrides the frame counter (after an external all-reduce). */
+int  mdc_sq_set_frames(mdc_sq_plan *plan, int64_t n_frames);
+
+/*
+ * One-shot functional seam: rho[i] = sum_j exp(i q_i . r_j)
+ * (structure.py:1240-1280).  qs f64 (nq,3), rs f64 (n,3) host arrays,
+ * rho_out f64 (nq, 2) interleaved (re, im) == complex128.
+ */
+int  mdc_delta_fourier_transform_sum(mdc_ctx *ctx, const double *qs, int64_t nq,
+                                     const double *rs, int64_t n,
+                                     int precision, double *rho_out);
+
+/* ---- g(r): RadialDistributionFunction ------------------------------------ */
+
+/*
+ * Creates a g(r) plan for ordered pairs (i in a, j in b).
+ *   n_bins, r0, r1 : histogram of distances with r0 - DBL_EPSILON < d <= r1,
+ *                    bins as numba_histogram (algorithm/accelerated.py:46-81).
+ *   same_group     : b is a (group_b=None in the reference); pos_b is ignored.
+ *   excl0, excl1   : drop pairs with i / excl0 == j / excl1 (structure.py:119);
+ *                    excl0 <= 0 means no exclusion.
+ * Counts are exact integers, independent of launch geometry.
+ */
+int  mdc_rdf_plan_create(mdc_ctx *ctx, int n_bins, double r0, double r1,
+                         int64_t n_a, int64_t n_b, int same_group,
+                         int64_t excl0, int64_t excl1,
+                         mdc_rdf_plan **out);
+int  mdc_rdf_plan_destroy(mdc_rdf_plan *plan);
+
+/*
+ * Accumulates n_frames frames.  pos_a f32 (n_frames, n_a, 3); pos_b f32
+ * (n_frames, n_b, 3) or NULL when same_group; box f32 (n_frames, 6)
+ * [lx, ly, lz, alpha, beta, gamma] (host memory always).  Only orthorhombic
+ * boxes (90/90/90) are supported: MDC_ERR_UNSUPPORTED otherwise.
+ */
+int  mdc_rdf_push(mdc_rdf_plan *plan, const float *pos_a, const float *pos_b,
+                  const float *box, int n_frames, int on_device);
+
+int  mdc_rdf_read(mdc_rdf_plan *plan, int64_t *counts_out, int64_t *n_frames_out);
+int  mdc_rdf_reset(mdc_rdf_plan *plan);
+int  mdc_rdf_accum_ptr(mdc_rdf_plan *plan, void **dev_ptr, int64_t *n_elems);
+
+/*
+ * One-shot functional seam (structure.py:34-131): counts_out i64 (n_bins).
+ * exclusion as above.  Host arrays.
+ */
+int  mdc_radial_histogram(mdc_ctx *ctx, const float *pos_a, int64_t n_a,
+                          const float *pos_b, int64_t n_b, const float box[6],
+                          int n_bins, double r0, double r1,
+                          int64_t excl0, int64_t excl1, int64_t *counts_out);
+
+/* ---- timing (CUDA events on the context's compute stream) ---------------- */
+
+/*
+ * All plans of a context queue their kernels on the context's compute stream.
+ * mdc_mark(ctx, 0 / 1) records a start / stop event there; mdc_elapsed_ms waits
+ * for the stop event and returns the device time between the two.
+ */
+int  mdc_mark(mdc_ctx *ctx, int which);
+int  mdc_elapsed_ms(mdc_ctx *ctx, float *ms);
+
+/* Milliseconds the device spent in the DOMINANT kernels of the last *_push call
+ * (the density kernels for S(q), the pair kernel for g(r); first 8 frame blocks of
+ * the push), and how many kernels of any kind that call launched. */
+int  mdc_sq_last_push_stats(mdc_sq_plan *plan, float *kernel_ms, int *n_launches);
+int  mdc_rdf_last_push_stats(mdc_rdf_plan *plan, float *kernel_ms, int *n_launches);
+
+/* ---- on-box probes (recorded next to MEASURED_PEAKS.json by bench.py) ---- */
+
+/*
+ * Issue-rate microbenchmarks.  which: 0 = FFMA, 1 = MUFU.SIN+MUFU.COS pairs,
+ * 2 = DFMA, 3 = F2F.F64.F32, 4 = shared-memory atomics (spread addresses),
+ * 5 = IMAD.  Returns operations per second over the whole GPU.
+ */
+int  mdc_probe_rate(mdc_ctx *ctx, int which, double *ops_per_s);
+
+/*
+ * Accuracy of the SFU sincos pipeline used by the DIRECT S(q) kernel over all
+ * 2^23 phases: out[0..1] = mean error of (cos, sin) (the DC bias a coherent sum
+ * over N particles multiplies by N), out[2] = rms error, out[3] = max |error|.
+ * variant selects the kernel's phase-to-argument mapping.
+ */
+int  mdc_probe_sincos(mdc_ctx *ctx, int variant, double out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDCRAFT_B200_H */

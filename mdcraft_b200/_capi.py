@@ -1,0 +1,395 @@
+"""
+ctypes binding of ``libmdcraft_b200.so`` (``include/mdcraft_b200.h``).
+
+This is the only door between the Python host code and the CUDA kernels.  There
+is no CPU fallback: if the library is missing, or no sm_100 device is present,
+every entry point raises :class:`MdcError`.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import build as _build
+
+MDC_OK = 0
+MDC_ERR_INVALID = -1
+MDC_ERR_CUDA = -2
+MDC_ERR_NOMEM = -3
+MDC_ERR_UNSUPPORTED = -4
+
+PRECISION_FP32 = 0
+PRECISION_FP64 = 1
+PRECISIONS = {"fp32": PRECISION_FP32, "fp64": PRECISION_FP64}
+
+SQ_ALGO_AUTO = 0
+SQ_ALGO_DIRECT = 1
+SQ_ALGOS = {"auto": SQ_ALGO_AUTO, "direct": SQ_ALGO_DIRECT}
+
+PROBES = {
+    "ffma": 0, "mufu_sincos_pairs": 1, "dfma": 2, "f2f_f64_f32": 3, "atoms_spread": 4, "imad": 5,
+    "ffma2": 6, "alu": 7, "i2f": 8, "atoms_hist": 9, "atoms_hist_base": 10,
+}
+
+
+class MdcError(RuntimeError):
+    """An error reported by libmdcraft_b200 (``code`` is the C return value)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libmdcraft_b200 error {code}: {message}")
+        self.code = code
+
+
+_dp = POINTER(c_double)
+_fp = POINTER(c_float)
+_lp = POINTER(c_int64)
+_ip = POINTER(c_int)
+
+#: every symbol declared in include/mdcraft_b200.h: name -> (restype, argtypes)
+SIGNATURES = {
+    "mdc_version": (c_int, []),
+    "mdc_last_error": (c_char_p, []),
+    "mdc_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "mdc_destroy": (c_int, [c_void_p]),
+    "mdc_device_info": (c_int, [c_void_p, _ip, _ip, _ip, _ip, _lp]),
+    "mdc_synchronize": (c_int, [c_void_p]),
+    "mdc_mark": (c_int, [c_void_p, c_int]),
+    "mdc_elapsed_ms": (c_int, [c_void_p, _fp]),
+    "mdc_sq_plan_create": (
+        c_int,
+        [c_void_p, c_int, _dp, c_double, _dp, c_int64, c_int, _lp, c_int, _ip, c_int, c_int, POINTER(c_void_p)],
+    ),
+    "mdc_sq_plan_destroy": (c_int, [c_void_p]),
+    "mdc_sq_num_wavevectors": (c_int64, [c_void_p]),
+    "mdc_sq_wavevectors": (c_int, [c_void_p, _dp]),
+    "mdc_sq_push": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "mdc_sq_read": (c_int, [c_void_p, _dp, _lp]),
+    "mdc_sq_reset": (c_int, [c_void_p]),
+    "mdc_sq_accum_ptr": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
+    "mdc_sq_set_frames": (c_int, [c_void_p, c_int64]),
+    "mdc_delta_fourier_transform_sum": (c_int, [c_void_p, _dp, c_int64, _dp, c_int64, c_int, _dp]),
+    "mdc_rdf_plan_create": (
+        c_int,
+        [c_void_p, c_int, c_double, c_double, c_int64, c_int64, c_int, c_int64, c_int64, POINTER(c_void_p)],
+    ),
+    "mdc_rdf_plan_destroy": (c_int, [c_void_p]),
+    "mdc_rdf_push": (c_int, [c_void_p, c_void_p, c_void_p, _fp, c_int, c_int]),
+    "mdc_rdf_read": (c_int, [c_void_p, _lp, _lp]),
+    "mdc_rdf_reset": (c_int, [c_void_p]),
+    "mdc_rdf_accum_ptr": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
+    "mdc_radial_histogram": (
+        c_int,
+        [c_void_p, _fp, c_int64, _fp, c_int64, _fp, c_int, c_double, c_double, c_int64, c_int64, _lp],
+    ),
+    "mdc_sq_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
+    "mdc_rdf_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
+    "mdc_probe_rate": (c_int, [c_void_p, c_int, _dp]),
+    "mdc_probe_sincos": (c_int, [c_void_p, c_int, _dp]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def header_path() -> str:
+    return os.path.join(os.path.dirname(_build.HERE), "include", "mdcraft_b200.h")
+
+
+def declared_symbols() -> list:
+    """Function names declared in ``include/mdcraft_b200.h``."""
+    with open(header_path()) as fh:
+        text = fh.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdc_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib() -> ctypes.CDLL:
+    """Loads (building it in-tree if the sources are newer) the CUDA library."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PATH
+        if _build.is_stale():
+            try:
+                path = _build.build()
+            except Exception as err:  # no nvcc on the box: use what travelled with the snapshot
+                if not os.path.exists(path):
+                    raise MdcError(
+                        MDC_ERR_UNSUPPORTED,
+                        f"{path} is missing and cannot be built ({err}); there is no CPU fallback",
+                    ) from err
+        L = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(code: int) -> None:
+    if code != MDC_OK:
+        raise MdcError(code, (lib().mdc_last_error() or b"").decode("utf-8", "replace"))
+
+
+def _as(a: np.ndarray, ptr):
+    return a.ctypes.data_as(ptr)
+
+
+def _buffer(x, dtype=np.float32):
+    """
+    ``(address, on_device, keepalive)`` for a NumPy array (host) or any object
+    with ``__cuda_array_interface__`` / a CUDA ``torch.Tensor`` (device).
+    """
+    if hasattr(x, "__cuda_array_interface__") and not isinstance(x, np.ndarray):
+        cai = x.__cuda_array_interface__
+        if np.dtype(cai["typestr"]) != np.dtype(dtype):
+            raise TypeError(f"device buffer must be {np.dtype(dtype)}")
+        if cai.get("strides") is not None:
+            raise ValueError("device buffer must be C-contiguous")
+        return c_void_p(cai["data"][0]), 1, x
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return c_void_p(a.ctypes.data), 0, a
+
+
+class Context:
+    """One CUDA device (``mdc_create``)."""
+
+    def __init__(self, device: int = 0):
+        self._h = c_void_p()
+        self.device = int(device)
+        _check(lib().mdc_create(self.device, byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().mdc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        sm, ma, mi, khz = c_int(), c_int(), c_int(), c_int()
+        mem = c_int64()
+        _check(lib().mdc_device_info(self._h, byref(sm), byref(ma), byref(mi), byref(khz), byref(mem)))
+        return {
+            "sm_count": sm.value, "cc": (ma.value, mi.value), "sm_clock_khz": khz.value,
+            "global_mem_bytes": mem.value,
+        }
+
+    def synchronize(self) -> None:
+        _check(lib().mdc_synchronize(self._h))
+
+    def mark(self, which: int) -> None:
+        """Records the start (0) / stop (1) event on the compute stream shared by this context's plans."""
+        _check(lib().mdc_mark(self._h, int(which)))
+
+    def elapsed_ms(self) -> float:
+        ms = c_float()
+        _check(lib().mdc_elapsed_ms(self._h, byref(ms)))
+        return ms.value
+
+    def probe_rate(self, which) -> float:
+        out = c_double()
+        _check(lib().mdc_probe_rate(self._h, PROBES[which] if isinstance(which, str) else int(which), byref(out)))
+        return out.value
+
+    def probe_sincos(self, variant: int = 0) -> dict:
+        out = (c_double * 4)()
+        _check(lib().mdc_probe_sincos(self._h, int(variant), out))
+        return {"mean_cos_err": out[0], "mean_sin_err": out[1], "rms_err": out[2], "max_err": out[3]}
+
+    # -- one-shot functional seams ------------------------------------------
+    def delta_fourier_transform_sum(self, qs, rs, precision: str = "fp32") -> np.ndarray:
+        """``structure.py:1240-1280``: ``F[i] = sum_j exp(1j q_i . r_j)`` (complex128)."""
+        qs = np.ascontiguousarray(qs, dtype=np.float64).reshape(-1, 3)
+        rs = np.ascontiguousarray(rs, dtype=np.float64).reshape(-1, 3)
+        out = np.empty((qs.shape[0], 2), dtype=np.float64)
+        _check(lib().mdc_delta_fourier_transform_sum(
+            self._h, _as(qs, _dp), qs.shape[0], _as(rs, _dp), rs.shape[0], PRECISIONS[precision], _as(out, _dp)))
+        return out.view(np.complex128).reshape(-1)
+
+    def radial_histogram(self, pos_a, pos_b, n_bins, range_, dimensions, exclusion=None) -> np.ndarray:
+        """``structure.py:34-131``: ordered-pair distance histogram (int64)."""
+        a = np.ascontiguousarray(np.atleast_2d(pos_a), dtype=np.float32)
+        same = pos_b is None or pos_b is pos_a
+        b = a if same else np.ascontiguousarray(np.atleast_2d(pos_b), dtype=np.float32)
+        box = np.ascontiguousarray(dimensions, dtype=np.float32)
+        if box.shape[0] == 3:
+            box = np.concatenate((box, np.full(3, 90, np.float32)))
+        ex0, ex1 = (0, 0) if exclusion is None else (int(exclusion[0]), int(exclusion[1]))
+        out = np.zeros(int(n_bins), dtype=np.int64)
+        _check(lib().mdc_radial_histogram(
+            self._h, _as(a, _fp), a.shape[0], _as(a if same else b, _fp), b.shape[0], _as(box, _fp), int(n_bins),
+            float(range_[0]), float(range_[1]), ex0, ex1, _as(out, _lp)))
+        return out
+
+
+class _DeviceArray:
+    """Exposes a library-owned accumulator through ``__cuda_array_interface__`` (for NCCL via torch)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str, owner):
+        self.__cuda_array_interface__ = {
+            "shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None,
+        }
+        self._owner = owner
+
+
+class SqPlan:
+    """``mdc_sq_plan``: accumulates S(q) pair sums over pushed frame blocks."""
+
+    def __init__(
+        self,
+        ctx: Context,
+        group_sizes: Sequence[int],
+        pairs: Sequence[Sequence[Optional[int]]],
+        *,
+        n_points: int = 0,
+        L0: Optional[Sequence[float]] = None,
+        q_max: Optional[float] = None,
+        wavevectors: Optional[np.ndarray] = None,
+        precision: str = "fp32",
+        algo: str = "auto",
+    ):
+        self.ctx = ctx
+        self._h = c_void_p()
+        gs = np.ascontiguousarray(group_sizes, dtype=np.int64)
+        pr = np.ascontiguousarray(
+            [(-1, -1) if p[0] is None else (int(p[0]), int(p[1])) for p in pairs], dtype=np.int32
+        ).reshape(-1, 2)
+        L = np.zeros(3) if L0 is None else np.ascontiguousarray(L0, dtype=np.float64)
+        if wavevectors is not None:
+            wv = np.ascontiguousarray(wavevectors, dtype=np.float64).reshape(-1, 3)
+            n_exp, wv_p = wv.shape[0], _as(wv, _dp)
+        else:
+            wv, n_exp, wv_p = None, 0, None
+        _check(lib().mdc_sq_plan_create(
+            ctx._h, int(n_points), _as(L, _dp), -1.0 if q_max is None else float(q_max), wv_p, n_exp,
+            gs.shape[0], _as(gs, _lp), pr.shape[0], _as(pr, _ip), PRECISIONS[precision], SQ_ALGOS[algo],
+            byref(self._h)))
+        self.n_particles = int(gs.sum())
+        self.n_pairs = pr.shape[0]
+        self.n_wavevectors = int(lib().mdc_sq_num_wavevectors(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().mdc_sq_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def wavevectors(self) -> np.ndarray:
+        out = np.empty((self.n_wavevectors, 3), dtype=np.float64)
+        _check(lib().mdc_sq_wavevectors(self._h, _as(out, _dp)))
+        return out
+
+    def push(self, pos, n_frames: Optional[int] = None) -> None:
+        """``pos``: float32 ``(F, N, 3)`` (or ``(N, 3)``), host array or device buffer."""
+        ptr, on_dev, keep = _buffer(pos)
+        shape = keep.shape if hasattr(keep, "shape") else None
+        if n_frames is None:
+            n_frames = 1 if len(shape) == 2 else int(shape[0])
+        n_el = int(np.prod(shape))
+        if n_el != n_frames * self.n_particles * 3:
+            raise ValueError(f"positions have {n_el} elements, expected {n_frames} x {self.n_particles} x 3")
+        _check(lib().mdc_sq_push(self._h, ptr, int(n_frames), on_dev))
+
+    def read(self):
+        """Un-normalised sums ``(n_pairs, Nq)`` and the number of frames accumulated."""
+        out = np.empty((self.n_pairs, self.n_wavevectors), dtype=np.float64)
+        nf = c_int64()
+        _check(lib().mdc_sq_read(self._h, _as(out, _dp), byref(nf)))
+        return out, nf.value
+
+    def reset(self) -> None:
+        _check(lib().mdc_sq_reset(self._h))
+
+    def set_frames(self, n: int) -> None:
+        _check(lib().mdc_sq_set_frames(self._h, int(n)))
+
+    def accumulator(self) -> _DeviceArray:
+        p, n = c_void_p(), c_int64()
+        _check(lib().mdc_sq_accum_ptr(self._h, byref(p), byref(n)))
+        return _DeviceArray(p.value, n.value, "<f8", self)
+
+    def last_push_stats(self):
+        ms, nl = c_float(), c_int()
+        _check(lib().mdc_sq_last_push_stats(self._h, byref(ms), byref(nl)))
+        return ms.value, nl.value
+
+
+class RdfPlan:
+    """``mdc_rdf_plan``: accumulates the ordered-pair distance histogram over pushed frame blocks."""
+
+    def __init__(self, ctx: Context, n_bins: int, range_, n_a: int, n_b: Optional[int] = None, exclusion=None):
+        self.ctx = ctx
+        self._h = c_void_p()
+        self.same = n_b is None
+        ex0, ex1 = (0, 0) if exclusion is None else (int(exclusion[0]), int(exclusion[1]))
+        _check(lib().mdc_rdf_plan_create(
+            ctx._h, int(n_bins), float(range_[0]), float(range_[1]), int(n_a), int(n_a if n_b is None else n_b),
+            1 if self.same else 0, ex0, ex1, byref(self._h)))
+        self.n_bins, self.n_a, self.n_b = int(n_bins), int(n_a), int(n_a if n_b is None else n_b)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().mdc_rdf_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push(self, pos_a, pos_b, box, n_frames: Optional[int] = None) -> None:
+        """``pos_*``: float32 ``(F, n, 3)`` host or device; ``box``: float32 ``(F, 6)`` or ``(6,)`` host."""
+        pa, dev_a, ka = _buffer(pos_a)
+        if n_frames is None:
+            n_frames = 1 if len(ka.shape) == 2 else int(ka.shape[0])
+        if int(np.prod(ka.shape)) != n_frames * self.n_a * 3:
+            raise ValueError("pos_a has the wrong number of elements")
+        if self.same:
+            pb, kb = None, None
+        else:
+            pb, dev_b, kb = _buffer(pos_b)
+            if dev_b != dev_a:
+                raise ValueError("pos_a and pos_b must both be host or both be device buffers")
+            if int(np.prod(kb.shape)) != n_frames * self.n_b * 3:
+                raise ValueError("pos_b has the wrong number of elements")
+        bx = np.ascontiguousarray(box, dtype=np.float32)
+        if bx.ndim == 1:
+            bx = np.ascontiguousarray(np.broadcast_to(bx, (n_frames, bx.shape[0])))
+        if bx.shape != (n_frames, 6):
+            raise ValueError("box must be (n_frames, 6)")
+        _check(lib().mdc_rdf_push(self._h, pa, pb, _as(bx, _fp), int(n_frames), dev_a))
+
+    def read(self):
+        out = np.empty(self.n_bins, dtype=np.int64)
+        nf = c_int64()
+        _check(lib().mdc_rdf_read(self._h, _as(out, _lp), byref(nf)))
+        return out, nf.value
+
+    def reset(self) -> None:
+        _check(lib().mdc_rdf_reset(self._h))
+
+    def accumulator(self) -> _DeviceArray:
+        p, n = c_void_p(), c_int64()
+        _check(lib().mdc_rdf_accum_ptr(self._h, byref(p), byref(n)))
+        return _DeviceArray(p.value, n.value, "<i8", self)
+
+    def last_push_stats(self):
+        ms, nl = c_float(), c_int()
+        _check(lib().mdc_rdf_last_push_stats(self._h, byref(ms), byref(nl)))
+        return ms.value, nl.value

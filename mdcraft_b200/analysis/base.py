@@ -1,0 +1,159 @@
+"""
+Analysis base classes
+=====================
+
+Drop-in surface of ``/root/reference/src/mdcraft/analysis/base.py`` for the
+S(q) / g(r) path: ``Hash`` (:68), ``SerialAnalysisBase`` (:106, ``run`` +
+``save``), ``NumbaAnalysisBase`` (:209, ``run(..., n_threads=)``) and
+``DynamicAnalysisBase`` (:521, the serial/parallel switch).
+
+The reference's process-pool frame farm (``ParallelAnalysisBase.run``,
+base.py:308-518) is *not* reproduced: on this path frames are processed in
+blocks on the GPU and, across GPUs, one contiguous frame block per rank with a
+single all-reduce (see :mod:`mdcraft_b200.distributed`).  ``parallel``,
+``n_jobs``, ``module`` ... are accepted and ignored so existing call sites keep
+working.
+
+When MDAnalysis is importable the classes derive from its real
+``AnalysisBase``; otherwise from a protocol-compatible stand-in
+(``_setup_frames`` -> ``_prepare`` -> per-frame ``_single_frame`` ->
+``_conclude``).
+"""
+
+from __future__ import annotations
+
+from typing import TextIO, Union
+
+import numpy as np
+
+try:  # pragma: no cover - MDAnalysis is absent in the build image
+    from MDAnalysis.analysis.base import AnalysisBase as _MDAAnalysisBase
+    from MDAnalysis.analysis.base import Results as _MDAResults
+
+    FOUND_MDANALYSIS = True
+except ImportError:
+    _MDAAnalysisBase = None
+    _MDAResults = None
+    FOUND_MDANALYSIS = False
+
+
+class Hash(dict):
+    """``dict`` with attribute access (base.py:68-103)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.__dict__ = self
+
+
+if FOUND_MDANALYSIS:  # pragma: no cover
+    Results = _MDAResults
+    AnalysisBase = _MDAAnalysisBase
+else:
+
+    class Results(dict):
+        """Attribute-accessible result container (``MDAnalysis.analysis.base.Results``)."""
+
+        def __getattr__(self, key):
+            try:
+                return self[key]
+            except KeyError as err:
+                raise AttributeError(f"'Results' object has no attribute '{key}'") from err
+
+        def __setattr__(self, key, value):
+            self[key] = value
+
+        def __delattr__(self, key):
+            try:
+                del self[key]
+            except KeyError as err:
+                raise AttributeError(f"'Results' object has no attribute '{key}'") from err
+
+    class AnalysisBase:
+        """Protocol-compatible stand-in for ``MDAnalysis.analysis.base.AnalysisBase``."""
+
+        def __init__(self, trajectory, verbose: bool = False, **kwargs):
+            self._trajectory = trajectory
+            self._verbose = verbose
+            self.results = Results()
+
+        def _setup_frames(self, trajectory, start=None, stop=None, step=None, frames=None):
+            self._trajectory = trajectory
+            if frames is not None:
+                if not all(opt is None for opt in (start, stop, step)):
+                    raise ValueError("start/stop/step cannot be combined with frames")
+                self._sliced_trajectory = trajectory[frames]
+            else:
+                start, stop, step = trajectory.check_slice_indices(start, stop, step)
+                self._sliced_trajectory = trajectory[start:stop:step]
+            self.start, self.stop, self.step = start, stop, step
+            self.n_frames = len(self._sliced_trajectory)
+            self.frames = np.zeros(self.n_frames, dtype=int)
+            self.times = np.zeros(self.n_frames)
+
+        def _prepare(self):
+            pass
+
+        def _single_frame(self):
+            raise NotImplementedError("Only implemented in child classes")
+
+        def _conclude(self):
+            pass
+
+        def run(self, start=None, stop=None, step=None, frames=None, verbose=None, **kwargs):
+            self._setup_frames(self._trajectory, start=start, stop=stop, step=step, frames=frames)
+            self._prepare()
+            for i, ts in enumerate(self._sliced_trajectory):
+                self._frame_index = i
+                self._ts = ts
+                self.frames[i] = ts.frame
+                self.times[i] = ts.time
+                self._single_frame()
+            self._conclude()
+            return self
+
+
+class SerialAnalysisBase(AnalysisBase):
+    """base.py:106-206."""
+
+    def __init__(self, trajectory, verbose: bool = False, **kwargs):
+        super().__init__(trajectory, verbose, **kwargs)
+
+    def run(self, start=None, stop=None, step=None, frames=None, verbose=None, **kwargs):
+        return super().run(start, stop, step, frames, verbose, **kwargs)
+
+    def save(self, file: Union[str, TextIO], archive: bool = True, compress: bool = True, **kwargs) -> None:
+        """Saves ``results`` in NumPy format (base.py:167-206)."""
+        if archive and compress:
+            np.savez_compressed(file, **self.results, **kwargs)
+        elif archive:
+            np.savez(file, **self.results, **kwargs)
+        else:
+            for data in self.results:
+                np.save(f"{file}_{data}", self.results[data], **kwargs)
+
+
+class NumbaAnalysisBase(SerialAnalysisBase):
+    """base.py:209-278.  ``n_threads`` only ever sized Numba's pool; ignored on the GPU."""
+
+    def run(self, start=None, stop=None, step=None, frames=None, verbose=None, *, n_threads=None, **kwargs):
+        return super().run(start=start, stop=stop, step=step, frames=frames, verbose=verbose, **kwargs)
+
+
+class DynamicAnalysisBase(SerialAnalysisBase):
+    """
+    base.py:521-602.  The reference switches between the serial loop and the
+    process farm on ``parallel``; here both run the same GPU frame-block path,
+    and the farm's keyword arguments (``n_jobs``, ``module``, ``block``,
+    ``method``) are accepted and dropped.
+    """
+
+    _FARM_KWARGS = ("n_jobs", "module", "block", "method")
+
+    def __init__(self, trajectory, parallel: bool = False, verbose: bool = False, **kwargs):
+        super().__init__(trajectory, verbose, **kwargs)
+        self._parallel = parallel
+
+    def run(self, start=None, stop=None, step=None, frames=None, verbose=None, **kwargs):
+        for k in self._FARM_KWARGS:
+            kwargs.pop(k, None)
+        return super().run(start, stop, step, frames, verbose, **kwargs)

@@ -1,0 +1,859 @@
+// sq.cu — S(q): StructureFactor per-frame arithmetic on sm_100a.
+//
+// Replaces (all paths relative to /root/reference/src/mdcraft/):
+//   analysis/structure.py:1822-1887  wavevector grid       -> lat_row_counts / lat_fill (device)
+//   analysis/structure.py:1240-1280  delta_fourier_transform_sum
+//   algorithm/accelerated.py:84-113  numba_dot             -> sq_lattice_direct / sq_explicit_* kernels
+//   analysis/structure.py:1940-1970  _single_frame (exp)   -> sq_pair_accum
+//
+// Data layout in HBM, per frame block of F frames (one plan, two slots):
+//   raw   f32 (F, N, 3)        as pushed (AoS, what AtomGroup.positions yields)
+//   fix   u32 (F, 3, N)        SoA, position / L0 as a 32-bit binary fraction of the box   [lattice, FP32 mode]
+//   posd  f64 (F, 3, N)        SoA, exact widening of the float32 coordinates             [explicit q / FP64 mode]
+//   part  f64x2 (F, n_sets, P, Nq)  per-particle-chunk partial densities (fixed-order reduce => bit-reproducible)
+//   ssf   f64 (n_pairs, Nq)    accumulator over all frames pushed
+//
+// Roofline: one (wavevector, particle) term costs two MUFU ops
+// (sin, cos); 16 MUFU lanes per SM per clock => 8 terms/clk/SM.  HBM traffic is
+// 12 B per particle per frame and irrelevant.
+#include "common.cuh"
+#include "sq_math.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+using namespace mdc;
+
+namespace {
+
+constexpr int SQ_Q = 8;          // consecutive c (z index) values per thread in the lattice kernel
+constexpr int SQ_THREADS = 128;
+constexpr int SQ_TILE = 512;     // particles staged in shared memory per inner pass (FP32 partial-sum run)
+constexpr double TWO_PI = 6.283185307179586;  // == 2 * np.pi
+
+// ------------------------------------------------------------------------------------------
+// wavevector grid (structure.py:1837-1841, 1874-1887)
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ double grid_value(int i, double L) { return __ddiv_rn(__dmul_rn(TWO_PI, (double)i), L); }
+
+__device__ __forceinline__ double norm3(double x, double y, double z)
+{
+    // np.linalg.norm(axis=1): sqrt(((x*x + y*y) + z*z)), no FMA
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+}
+
+// row r = b * n + a  (np.meshgrid 'xy' indexing: flat index b*n^2 + a*n + c, q = (g[a], g[b], g[c]))
+__global__ void lat_row_counts(int n, double Lx, double Ly, double Lz, double q_max, int *cnt)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n * n) return;
+    const int a = r % n, b = r / n;
+    const double qx = grid_value(a, Lx), qy = grid_value(b, Ly);
+    int k = 0;
+    if (q_max < 0) {
+        k = n;
+    } else {
+        // |q| is non-decreasing in c, so the kept c form a prefix
+        for (int c = 0; c < n; ++c) {
+            if (norm3(qx, qy, grid_value(c, Lz)) <= q_max) ++k;
+            else break;
+        }
+    }
+    cnt[r] = k;
+}
+
+// items: {a | b << 16, c0 | count << 16, first wavevector index (low 32), (high 32)}
+__global__ void lat_fill(int n, double Lx, double Ly, double Lz, const int *cnt, const int64_t *q_off,
+                         const int64_t *item_off, double *q, uint4 *items)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n * n) return;
+    const int a = r % n, b = r / n;
+    const double qx = grid_value(a, Lx), qy = grid_value(b, Ly);
+    const int k = cnt[r];
+    const int64_t q0 = q_off[r];
+    for (int c = 0; c < k; ++c) {
+        q[3 * (q0 + c) + 0] = qx;
+        q[3 * (q0 + c) + 1] = qy;
+        q[3 * (q0 + c) + 2] = grid_value(c, Lz);
+    }
+    int64_t it = item_off[r];
+    for (int c0 = 0; c0 < k; c0 += SQ_Q, ++it) {
+        const int m = min(SQ_Q, k - c0);
+        const int64_t qi = q0 + c0;
+        items[it] = make_uint4((unsigned)a | ((unsigned)b << 16), (unsigned)c0 | ((unsigned)m << 16),
+                               (unsigned)(qi & 0xffffffffll), (unsigned)(qi >> 32));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// layout kernels
+// ------------------------------------------------------------------------------------------
+
+// raw f32 (F, N, 3) -> fix u32 (F, 3, N): frac(x / L0) * 2^32, rounded to nearest (wraps mod 2^32)
+__global__ void prep_fix(const float *__restrict__ raw, int64_t N, int64_t total, double iLx, double iLy,
+                         double iLz, uint32_t *__restrict__ fix)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t f = i / N, j = i - f * N;
+    const float *p = raw + 3 * i;
+    const double inv[3] = {iLx, iLy, iLz};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double s = (double)p[k] * inv[k];
+        s -= floor(s);
+        fix[(f * 3 + k) * N + j] = (uint32_t)(unsigned long long)(s * 4294967296.0 + 0.5);
+    }
+}
+
+// raw f32 (F, N, 3) -> posd f64 (F, 3, N)
+__global__ void prep_f64(const float *__restrict__ raw, int64_t N, int64_t total, double *__restrict__ posd)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t f = i / N, j = i - f * N;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) posd[(f * 3 + k) * N + j] = (double)raw[3 * i + k];
+}
+
+// f64 (N, 3) -> f64 (3, N)
+__global__ void transpose_f64(const double *__restrict__ rs, int64_t N, double *__restrict__ posd)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) posd[k * N + i] = rs[3 * i + k];
+}
+
+// ------------------------------------------------------------------------------------------
+// density kernels: part[((f * n_sets + s) * P + p) * nq + q] = sum over the particle chunk
+// ------------------------------------------------------------------------------------------
+
+struct Chunk {
+    int64_t lo, hi;
+};
+
+__device__ __forceinline__ Chunk chunk_range(int2 set, int p, int P)
+{
+    const int64_t lo = set.x, len = (int64_t)set.y - set.x;
+    Chunk c;
+    c.lo = lo + len * p / P;
+    c.hi = lo + len * (p + 1) / P;
+    return c;
+}
+
+// DIRECT, reciprocal lattice, FP32 + SFU.  One thread = SQ_Q consecutive c of one (a, b) row;
+// particles are broadcast from shared memory.  Phase arithmetic is exact (integers mod 2^32).
+__global__ void __launch_bounds__(SQ_THREADS)
+sq_lattice_direct(const uint4 *__restrict__ items, int64_t n_items, const uint32_t *__restrict__ fix,
+                  int64_t N, const int2 *__restrict__ sets, int n_sets, int P, int64_t nq,
+                  double2 *__restrict__ part)
+{
+    __shared__ uint4 sm[SQ_TILE];
+    const int64_t it = (int64_t)blockIdx.x * SQ_THREADS + threadIdx.x;
+    const bool valid = it < n_items;
+    const uint4 item = items[valid ? it : n_items - 1];
+    const uint32_t a = item.x & 0xffffu, b = item.x >> 16, c0 = item.y & 0xffffu;
+    const int cnt = (int)(item.y >> 16);
+    const int p = blockIdx.y;
+    const int f = blockIdx.z / n_sets, s = blockIdx.z - f * n_sets;
+    const Chunk ch = chunk_range(sets[s], p, P);
+    const uint32_t *fx = fix + ((int64_t)f * 3 + 0) * N;
+    const uint32_t *fy = fix + ((int64_t)f * 3 + 1) * N;
+    const uint32_t *fz = fix + ((int64_t)f * 3 + 2) * N;
+
+    double dre[SQ_Q], dim[SQ_Q];
+#pragma unroll
+    for (int k = 0; k < SQ_Q; ++k) dre[k] = dim[k] = 0.0;
+
+    for (int64_t t0 = ch.lo; t0 < ch.hi; t0 += SQ_TILE) {
+        const int n = (int)min((int64_t)SQ_TILE, ch.hi - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += SQ_THREADS)
+            sm[i] = make_uint4(fx[t0 + i], fy[t0 + i], fz[t0 + i], 0u);
+        __syncthreads();
+
+        float re[SQ_Q], im[SQ_Q];
+#pragma unroll
+        for (int k = 0; k < SQ_Q; ++k) re[k] = im[k] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < n; ++j) {
+            const uint4 r = sm[j];
+            uint32_t ph = a * r.x + b * r.y + c0 * r.z;
+#pragma unroll
+            for (int k = 0; k < SQ_Q; ++k) {
+                float sn, cs;
+                sincos_phase(ph, sn, cs);
+                re[k] += cs;
+                im[k] += sn;
+                ph += r.z;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SQ_Q; ++k) {
+            dre[k] += (double)re[k];
+            dim[k] += (double)im[k];
+        }
+    }
+    if (valid) {
+        const int64_t q0 = (int64_t)item.z | ((int64_t)item.w << 32);
+        double2 *out = part + ((int64_t)blockIdx.z * P + p) * nq + q0;
+#pragma unroll
+        for (int k = 0; k < SQ_Q; ++k)
+            if (k < cnt) out[k] = make_double2(dre[k], dim[k]);
+    }
+}
+
+// Arbitrary wavevectors, FP32 + SFU.  The phase is formed in FP64 (3 DFMA-class ops), and the
+// magic add  t + 1.5 * 2^20  leaves frac(t) * 2^32 in the low word: the same exact 32-bit phase
+// the lattice kernel uses, with no conversion instruction.
+constexpr int SQX_TILE = 256;
+__global__ void __launch_bounds__(SQ_THREADS)
+sq_explicit_f32(const double *__restrict__ q, int64_t q_first, int64_t n_q, const double *__restrict__ posd,
+                int64_t N, const int2 *__restrict__ sets, int n_sets, int P, int64_t nq,
+                double2 *__restrict__ part)
+{
+    __shared__ double sx[SQX_TILE], sy[SQX_TILE], sz[SQX_TILE];
+    const int64_t iq = (int64_t)blockIdx.x * SQ_THREADS + threadIdx.x;
+    const bool valid = iq < n_q;
+    const int64_t qi = q_first + (valid ? iq : n_q - 1);
+    const double inv2pi = 0.15915494309189535;
+    const double qx = q[3 * qi] * inv2pi, qy = q[3 * qi + 1] * inv2pi, qz = q[3 * qi + 2] * inv2pi;
+    const int p = blockIdx.y;
+    const int f = blockIdx.z / n_sets, s = blockIdx.z - f * n_sets;
+    const Chunk ch = chunk_range(sets[s], p, P);
+    const double *px = posd + ((int64_t)f * 3 + 0) * N;
+    const double *py = posd + ((int64_t)f * 3 + 1) * N;
+    const double *pz = posd + ((int64_t)f * 3 + 2) * N;
+    double dre = 0.0, dim = 0.0;
+    for (int64_t t0 = ch.lo; t0 < ch.hi; t0 += SQX_TILE) {
+        const int n = (int)min((int64_t)SQX_TILE, ch.hi - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += SQ_THREADS) {
+            sx[i] = px[t0 + i];
+            sy[i] = py[t0 + i];
+            sz[i] = pz[t0 + i];
+        }
+        __syncthreads();
+        float re = 0.f, im = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            const double t = fma(qz, sz[j], fma(qy, sy[j], qx * sx[j]));   // turns
+            const uint32_t ph = (uint32_t)__double2loint(t + 1572864.0);    // frac(t) * 2^32
+            float sn, cs;
+            sincos_phase(ph, sn, cs);
+            re += cs;
+            im += sn;
+        }
+        dre += (double)re;
+        dim += (double)im;
+    }
+    if (valid) part[((int64_t)blockIdx.z * P + p) * nq + qi] = make_double2(dre, dim);
+}
+
+// Arbitrary wavevectors, FP64 throughout: the reference's arithmetic (numba_dot + exp(1j x) in
+// complex128), for MDC_PRECISION_FP64.
+__global__ void __launch_bounds__(SQ_THREADS)
+sq_explicit_f64(const double *__restrict__ q, int64_t q_first, int64_t n_q, const double *__restrict__ posd,
+                int64_t N, const int2 *__restrict__ sets, int n_sets, int P, int64_t nq,
+                double2 *__restrict__ part)
+{
+    __shared__ double sx[SQX_TILE], sy[SQX_TILE], sz[SQX_TILE];
+    const int64_t iq = (int64_t)blockIdx.x * SQ_THREADS + threadIdx.x;
+    const bool valid = iq < n_q;
+    const int64_t qi = q_first + (valid ? iq : n_q - 1);
+    const double qx = q[3 * qi], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
+    const int p = blockIdx.y;
+    const int f = blockIdx.z / n_sets, s = blockIdx.z - f * n_sets;
+    const Chunk ch = chunk_range(sets[s], p, P);
+    const double *px = posd + ((int64_t)f * 3 + 0) * N;
+    const double *py = posd + ((int64_t)f * 3 + 1) * N;
+    const double *pz = posd + ((int64_t)f * 3 + 2) * N;
+    double dre = 0.0, dim = 0.0;
+    for (int64_t t0 = ch.lo; t0 < ch.hi; t0 += SQX_TILE) {
+        const int n = (int)min((int64_t)SQX_TILE, ch.hi - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += SQ_THREADS) {
+            sx[i] = px[t0 + i];
+            sy[i] = py[t0 + i];
+            sz[i] = pz[t0 + i];
+        }
+        __syncthreads();
+        for (int j = 0; j < n; ++j) {
+            // accelerated.py:113  a[0]*b[0] + a[1]*b[1] + a[2]*b[2]
+            const double x = __dadd_rn(__dadd_rn(__dmul_rn(qx, sx[j]), __dmul_rn(qy, sy[j])), __dmul_rn(qz, sz[j]));
+            double sn, cs;
+            sincos(x, &sn, &cs);
+            dre += cs;
+            dim += sn;
+        }
+    }
+    if (valid) part[((int64_t)blockIdx.z * P + p) * nq + qi] = make_double2(dre, dim);
+}
+
+// rho[f, s, q] = sum_p part[f, s, p, q] (fixed order) - N_s * dc ;  ssf[pair, q] += products over frames.
+// dc = (mean cos error, mean sin error) of the SFU pipeline over all phases: the zeroth Fourier
+// coefficient of its error function is the only part a sum over N particles multiplies by N, so it is
+// measured once per plan (probe_sincos_kernel) and removed analytically.  Zero in FP64 mode.
+__global__ void sq_pair_accum(double2 *__restrict__ part, int F, int n_sets, int P, int64_t nq,
+                              const int2 *__restrict__ sets, const int2 *__restrict__ pairs, int n_pairs,
+                              double dc_cos, double dc_sin, double *__restrict__ ssf)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    for (int fs = 0; fs < F * n_sets; ++fs) {
+        double2 *base = part + (int64_t)fs * P * nq + q;
+        double re = 0.0, im = 0.0;
+        for (int p = 0; p < P; ++p) {
+            const double2 v = base[(int64_t)p * nq];
+            re += v.x;
+            im += v.y;
+        }
+        const int2 set = sets[fs % n_sets];
+        const double n = (double)(set.y - set.x);
+        base[0] = make_double2(re - n * dc_cos, im - n * dc_sin);
+    }
+    for (int pr = 0; pr < n_pairs; ++pr) {
+        const int2 jk = pairs[pr];
+        double acc = 0.0;
+        for (int f = 0; f < F; ++f) {
+            const double2 rj = part[((int64_t)f * n_sets + jk.x) * P * nq + q];
+            if (jk.x == jk.y) {
+                acc += rj.x * rj.x + rj.y * rj.y;   // (rho * conj(rho)).real
+            } else {
+                const double2 rk = part[((int64_t)f * n_sets + jk.y) * P * nq + q];
+                acc += 2.0 * (rj.x * rk.x + rj.y * rk.y);   // 2 * (rho_j * conj(rho_k)).real
+            }
+        }
+        ssf[(int64_t)pr * nq + q] += acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// accuracy probe of sincos_phase over all 2^23 distinct phases
+// ------------------------------------------------------------------------------------------
+__global__ void probe_sincos_kernel(int variant, double *acc /* [sum ec, sum es, sum e^2, max|e| bits] */)
+{
+    __shared__ double sh[4][256];
+    double sc = 0, ss = 0, s2 = 0, mx = 0;
+    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < (1u << 23); m += gridDim.x * blockDim.x) {
+        float sn, cs;
+        if (variant == 0) {
+            sincos_phase(m << 9, sn, cs);
+        } else {
+            // single-constant variant, for the record: x = t * float(2 pi)
+            const float t = __uint_as_float(0x3f800000u | m);
+            const float x = t * 6.2831854820251465f;
+            asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(x));
+            asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(x));
+        }
+        double rs, rc;
+        sincospi((double)m * (2.0 / 8388608.0), &rs, &rc);
+        const double ec = (double)cs - rc, es = (double)sn - rs;
+        sc += ec;
+        ss += es;
+        s2 += ec * ec + es * es;
+        mx = fmax(mx, fmax(fabs(ec), fabs(es)));
+    }
+    sh[0][threadIdx.x] = sc;
+    sh[1][threadIdx.x] = ss;
+    sh[2][threadIdx.x] = s2;
+    sh[3][threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+            sh[2][threadIdx.x] += sh[2][threadIdx.x + o];
+            sh[3][threadIdx.x] = fmax(sh[3][threadIdx.x], sh[3][threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(&acc[0], sh[0][0]);
+        atomicAdd(&acc[1], sh[1][0]);
+        atomicAdd(&acc[2], sh[2][0]);
+        // max of non-negative doubles == max of their bit patterns
+        atomicMax((unsigned long long *)&acc[3], (unsigned long long)__double_as_longlong(sh[3][0]));
+    }
+}
+
+int run_probe_sincos(int variant, double out[4])
+{
+    DevBuf<double> acc;
+    MDC_CHECK(acc.alloc(4));
+    MDC_CUDA(cudaMemset(acc.p, 0, 4 * sizeof(double)));
+    probe_sincos_kernel<<<1024, 256>>>(variant, acc.p);
+    MDC_CUDA(cudaGetLastError());
+    double h[4];
+    MDC_CUDA(cudaMemcpy(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost));
+    acc.release();
+    const double n = 8388608.0;
+    out[0] = h[0] / n;
+    out[1] = h[1] / n;
+    out[2] = sqrt(h[2] / (2 * n));
+    out[3] = h[3];
+    return MDC_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+
+struct mdc_sq_plan {
+    mdc_ctx *ctx = nullptr;
+    int n_points = 0;
+    double L0[3] = {0, 0, 0};
+    int64_t n_lat = 0, n_exp = 0, nq = 0, n_items = 0;
+    int64_t N = 0;
+    int n_sets = 0, n_pairs = 0;
+    int precision = 0, algo = 0;
+    bool lattice_fast = false;   // lattice part runs through sq_lattice_direct
+    double dc[2] = {0, 0};
+    DevBuf<double> q, ssf, posd[2];
+    DevBuf<uint4> items;
+    DevBuf<double2> part;
+    DevBuf<float> raw[2];
+    DevBuf<uint32_t> fix[2];
+    DevBuf<int2> d_sets, d_pairs;
+    std::vector<int2> sets;
+    Streams st;
+    int fblk = 0, P = 1;
+    int64_t n_frames = 0;
+    float last_ms = 0.f;
+    int last_launches = 0;
+};
+
+namespace {
+
+void plan_free(mdc_sq_plan *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaDeviceSynchronize();
+    p->q.release();
+    p->ssf.release();
+    p->items.release();
+    p->part.release();
+    p->d_sets.release();
+    p->d_pairs.release();
+    for (int i = 0; i < 2; ++i) {
+        p->posd[i].release();
+        p->raw[i].release();
+        p->fix[i].release();
+    }
+    p->st.destroy();
+    delete p;
+}
+
+}  // namespace
+
+extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3], double q_max,
+                                  const double *q_explicit, int64_t n_explicit, int n_groups,
+                                  const int64_t *group_sizes, int n_pairs, const int *pairs, int precision,
+                                  int algo, mdc_sq_plan **out)
+{
+    if (!ctx || !out) return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: NULL argument");
+    *out = nullptr;
+    if (n_points < 0 || n_points > 65535) return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: n_points out of range");
+    if (n_points > 0 && (!L0 || !(L0[0] > 0) || !(L0[1] > 0) || !(L0[2] > 0)))
+        return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: lattice plans need positive L0");
+    if (n_explicit < 0 || (n_explicit > 0 && !q_explicit))
+        return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: bad explicit wavevectors");
+    if (n_points == 0 && n_explicit == 0) return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: no wavevectors");
+    if (n_groups < 1 || !group_sizes) return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: need at least one group");
+    if (n_pairs < 1 || !pairs) return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: need at least one pair");
+    if (precision != MDC_PRECISION_FP32 && precision != MDC_PRECISION_FP64)
+        return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: unknown precision");
+    if (algo != MDC_SQ_ALGO_AUTO && algo != MDC_SQ_ALGO_DIRECT)
+        return fail(MDC_ERR_UNSUPPORTED, "mdc_sq_plan_create: only the DIRECT algorithm is implemented");
+    MDC_CUDA(cudaSetDevice(ctx->device));
+
+    mdc_sq_plan *p = new mdc_sq_plan();
+    p->ctx = ctx;
+    p->n_points = n_points;
+    p->precision = precision;
+    p->algo = MDC_SQ_ALGO_DIRECT;
+    p->n_exp = n_explicit;
+    if (n_points > 0) memcpy(p->L0, L0, sizeof(p->L0));
+
+    // density sets: one per group referenced by a pair, plus "all particles" for (-1, -1)
+    std::vector<int64_t> off(n_groups + 1, 0);
+    for (int g = 0; g < n_groups; ++g) {
+        if (group_sizes[g] < 0) {
+            delete p;
+            return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: negative group size");
+        }
+        off[g + 1] = off[g] + group_sizes[g];
+    }
+    p->N = off[n_groups];
+    if (p->N <= 0 || p->N > 2147483647ll) {
+        delete p;
+        return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: total particle count must be in [1, 2^31)");
+    }
+    std::vector<int> set_of(n_groups + 1, -1);
+    std::vector<int2> hp(n_pairs);
+    for (int i = 0; i < n_pairs; ++i) {
+        int jk[2] = {pairs[2 * i], pairs[2 * i + 1]};
+        for (int t = 0; t < 2; ++t) {
+            int g = jk[t] < 0 ? n_groups : jk[t];
+            if (g > n_groups) {
+                delete p;
+                return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: pair index out of range");
+            }
+            if (set_of[g] < 0) {
+                set_of[g] = (int)p->sets.size();
+                p->sets.push_back(g == n_groups ? make_int2(0, (int)p->N) : make_int2((int)off[g], (int)off[g + 1]));
+            }
+            jk[t] = set_of[g];
+        }
+        hp[i] = make_int2(jk[0], jk[1]);
+    }
+    p->n_sets = (int)p->sets.size();
+    p->n_pairs = n_pairs;
+
+    int rc = p->st.init(ctx);
+    if (rc != MDC_OK) {
+        plan_free(p);
+        return rc;
+    }
+
+#define PLAN_TRY(expr)              \
+    do {                            \
+        int _r = (expr);            \
+        if (_r != MDC_OK) {         \
+            plan_free(p);           \
+            return _r;              \
+        }                           \
+    } while (0)
+#define PLAN_CUDA(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            plan_free(p);                                                                    \
+            return fail(MDC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+        }                                                                                    \
+    } while (0)
+
+    // grid build, pass 1: kept wavevectors per (a, b) row on the device; prefix sums over the
+    // n^2 rows on the host (nothing of size Nq crosses the bus)
+    const int rows = n_points * n_points;
+    DevBuf<int> cnt;
+    std::vector<int64_t> hq(rows), hi(rows);
+    if (n_points > 0) {
+        PLAN_TRY(cnt.alloc(rows));
+        lat_row_counts<<<(rows + 255) / 256, 256>>>(n_points, p->L0[0], p->L0[1], p->L0[2], q_max, cnt.p);
+        PLAN_CUDA(cudaGetLastError());
+        std::vector<int> h(rows);
+        PLAN_CUDA(cudaMemcpy(h.data(), cnt.p, rows * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < rows; ++r) {
+            hq[r] = p->n_lat;
+            hi[r] = p->n_items;
+            p->n_lat += h[r];
+            p->n_items += (h[r] + SQ_Q - 1) / SQ_Q;
+        }
+    }
+    p->nq = p->n_lat + p->n_exp;
+    if (p->nq == 0) {
+        cnt.release();
+        plan_free(p);
+        return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: q_max removes every wavevector");
+    }
+    p->lattice_fast = (precision == MDC_PRECISION_FP32) && p->n_lat > 0;
+
+    PLAN_TRY(p->q.alloc((size_t)p->nq * 3));
+    PLAN_TRY(p->ssf.alloc((size_t)p->nq * n_pairs));
+    PLAN_CUDA(cudaMemset(p->ssf.p, 0, (size_t)p->nq * n_pairs * sizeof(double)));
+    PLAN_TRY(p->d_sets.alloc(p->n_sets));
+    PLAN_TRY(p->d_pairs.alloc(n_pairs));
+    PLAN_CUDA(cudaMemcpy(p->d_sets.p, p->sets.data(), p->n_sets * sizeof(int2), cudaMemcpyHostToDevice));
+    PLAN_CUDA(cudaMemcpy(p->d_pairs.p, hp.data(), n_pairs * sizeof(int2), cudaMemcpyHostToDevice));
+
+    if (p->n_lat > 0) {
+        // pass 2: wavevectors (reference FP64 operation order) and the lattice kernel's work items
+        DevBuf<int64_t> qo, io;
+        PLAN_TRY(qo.alloc(rows));
+        PLAN_TRY(io.alloc(rows));
+        PLAN_CUDA(cudaMemcpy(qo.p, hq.data(), rows * sizeof(int64_t), cudaMemcpyHostToDevice));
+        PLAN_CUDA(cudaMemcpy(io.p, hi.data(), rows * sizeof(int64_t), cudaMemcpyHostToDevice));
+        PLAN_TRY(p->items.alloc((size_t)p->n_items));
+        lat_fill<<<(rows + 255) / 256, 256>>>(n_points, p->L0[0], p->L0[1], p->L0[2], cnt.p, qo.p, io.p, p->q.p,
+                                              p->items.p);
+        PLAN_CUDA(cudaGetLastError());
+        PLAN_CUDA(cudaDeviceSynchronize());
+        qo.release();
+        io.release();
+    }
+    cnt.release();
+    if (p->n_exp > 0)
+        PLAN_CUDA(cudaMemcpy(p->q.p + 3 * p->n_lat, q_explicit, (size_t)p->n_exp * 3 * sizeof(double),
+                             cudaMemcpyHostToDevice));
+
+    if (precision == MDC_PRECISION_FP32) {
+        double pr[4];
+        PLAN_TRY(run_probe_sincos(0, pr));
+        p->dc[0] = pr[0];
+        p->dc[1] = pr[1];
+    }
+#undef PLAN_TRY
+#undef PLAN_CUDA
+    *out = p;
+    return MDC_OK;
+}
+
+extern "C" int mdc_sq_plan_destroy(mdc_sq_plan *plan)
+{
+    plan_free(plan);
+    return MDC_OK;
+}
+
+extern "C" int64_t mdc_sq_num_wavevectors(mdc_sq_plan *plan) { return plan ? plan->nq : -1; }
+
+extern "C" int mdc_sq_wavevectors(mdc_sq_plan *plan, double *q_out)
+{
+    if (!plan || !q_out) return fail(MDC_ERR_INVALID, "mdc_sq_wavevectors: NULL argument");
+    MDC_CUDA(cudaSetDevice(plan->ctx->device));
+    MDC_CUDA(cudaMemcpy(q_out, plan->q.p, (size_t)plan->nq * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return MDC_OK;
+}
+
+namespace {
+
+// frames per block and particle chunks per set, sized so that the grid fills the GPU several times
+// over and the partial-density buffer stays within budget
+int configure(mdc_sq_plan *p, int n_frames_hint)
+{
+    if (p->fblk > 0) return MDC_OK;
+    const int64_t budget = (int64_t)1 << 31;   // bytes for `part`
+    const int64_t per_frame_min = (int64_t)p->n_sets * p->nq * sizeof(double2);
+    if (per_frame_min > budget * 8)
+        return fail(MDC_ERR_NOMEM, "mdc_sq_push: wavevector grid too large for the partial-density buffer");
+    const int64_t blocks_q = ceil_div(p->lattice_fast ? p->n_items : 0, SQ_THREADS) +
+                             ceil_div(p->lattice_fast ? p->n_exp : p->nq, SQ_THREADS);
+    int fblk = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_frames_hint, 32), budget / per_frame_min));
+    const int64_t want = (int64_t)p->ctx->sm_count * 32;
+    int64_t min_len = p->N;
+    for (auto &s : p->sets) min_len = std::min<int64_t>(min_len, std::max(1, s.y - s.x));
+    int64_t P = ceil_div(want, blocks_q * fblk * p->n_sets);
+    P = std::min<int64_t>(P, std::max<int64_t>(1, min_len / (2 * SQ_TILE)));
+    P = std::min<int64_t>(P, std::max<int64_t>(1, budget / (per_frame_min * fblk)));
+    P = std::max<int64_t>(1, std::min<int64_t>(P, 65535));
+    p->fblk = fblk;
+    p->P = (int)P;
+    MDC_CHECK(p->part.alloc((size_t)fblk * p->n_sets * P * p->nq));
+    for (int i = 0; i < 2; ++i) {
+        MDC_CHECK(p->raw[i].alloc((size_t)fblk * p->N * 3));
+        if (p->lattice_fast) MDC_CHECK(p->fix[i].alloc((size_t)fblk * p->N * 3));
+        if (!p->lattice_fast || p->n_exp > 0) MDC_CHECK(p->posd[i].alloc((size_t)fblk * p->N * 3));
+    }
+    return MDC_OK;
+}
+
+int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launches)
+{
+    cudaStream_t sc = p->st.copy, sk = p->st.compute;
+    const int64_t total = (int64_t)F * p->N;
+    const int pb = (int)ceil_div(total, 256);
+    if (p->lattice_fast) {
+        prep_fix<<<pb, 256, 0, sc>>>(raw, p->N, total, 1.0 / p->L0[0], 1.0 / p->L0[1], 1.0 / p->L0[2], p->fix[slot].p);
+        ++*launches;
+    }
+    if (!p->lattice_fast || p->n_exp > 0) {
+        prep_f64<<<pb, 256, 0, sc>>>(raw, p->N, total, p->posd[slot].p);
+        ++*launches;
+    }
+    MDC_CUDA(cudaGetLastError());
+    MDC_CUDA(cudaEventRecord(p->st.staged[slot], sc));
+    MDC_CUDA(cudaStreamWaitEvent(sk, p->st.staged[slot], 0));
+    const int ti = p->st.n_timed < 8 ? p->st.n_timed : -1;
+    if (ti >= 0) MDC_CUDA(cudaEventRecord(p->st.k0[ti], sk));
+    const unsigned gz = (unsigned)(F * p->n_sets);
+    if (p->lattice_fast) {
+        dim3 g((unsigned)ceil_div(p->n_items, SQ_THREADS), (unsigned)p->P, gz);
+        sq_lattice_direct<<<g, SQ_THREADS, 0, sk>>>(p->items.p, p->n_items, p->fix[slot].p, p->N, p->d_sets.p,
+                                                   p->n_sets, p->P, p->nq, p->part.p);
+        ++*launches;
+        if (p->n_exp > 0) {
+            dim3 ge((unsigned)ceil_div(p->n_exp, SQ_THREADS), (unsigned)p->P, gz);
+            sq_explicit_f32<<<ge, SQ_THREADS, 0, sk>>>(p->q.p, p->n_lat, p->n_exp, p->posd[slot].p, p->N,
+                                                      p->d_sets.p, p->n_sets, p->P, p->nq, p->part.p);
+            ++*launches;
+        }
+    } else {
+        dim3 g((unsigned)ceil_div(p->nq, SQ_THREADS), (unsigned)p->P, gz);
+        if (p->precision == MDC_PRECISION_FP64)
+            sq_explicit_f64<<<g, SQ_THREADS, 0, sk>>>(p->q.p, 0, p->nq, p->posd[slot].p, p->N, p->d_sets.p,
+                                                      p->n_sets, p->P, p->nq, p->part.p);
+        else
+            sq_explicit_f32<<<g, SQ_THREADS, 0, sk>>>(p->q.p, 0, p->nq, p->posd[slot].p, p->N, p->d_sets.p,
+                                                      p->n_sets, p->P, p->nq, p->part.p);
+        ++*launches;
+    }
+    if (ti >= 0) {
+        MDC_CUDA(cudaEventRecord(p->st.k1[ti], sk));
+        p->st.n_timed = ti + 1;
+    }
+    sq_pair_accum<<<(unsigned)ceil_div(p->nq, 256), 256, 0, sk>>>(p->part.p, F, p->n_sets, p->P, p->nq, p->d_sets.p,
+                                                                 p->d_pairs.p, p->n_pairs, p->dc[0], p->dc[1],
+                                                                 p->ssf.p);
+    ++*launches;
+    MDC_CUDA(cudaGetLastError());
+    MDC_CUDA(cudaEventRecord(p->st.consumed[slot], sk));
+    p->st.used[slot] = true;
+    return MDC_OK;
+}
+
+}  // namespace
+
+extern "C" int mdc_sq_push(mdc_sq_plan *p, const float *pos, int n_frames, int on_device)
+{
+    if (!p || !pos) return fail(MDC_ERR_INVALID, "mdc_sq_push: NULL argument");
+    if (n_frames <= 0) return MDC_OK;
+    MDC_CUDA(cudaSetDevice(p->ctx->device));
+    MDC_CHECK(configure(p, n_frames));
+    p->st.n_timed = 0;
+    int launches = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += p->fblk) {
+        const int F = std::min(p->fblk, n_frames - f0);
+        const int slot = p->st.next;
+        p->st.next ^= 1;
+        // the slot's layout buffers (and `part`, shared by both slots through stream order on
+        // `compute`) may still be read by the kernels of two blocks ago
+        if (p->st.used[slot]) MDC_CUDA(cudaStreamWaitEvent(p->st.copy, p->st.consumed[slot], 0));
+        const float *src = pos + (size_t)f0 * p->N * 3;
+        const float *raw = src;
+        if (!on_device) {
+            MDC_CUDA(cudaMemcpyAsync(p->raw[slot].p, src, (size_t)F * p->N * 3 * sizeof(float),
+                                     cudaMemcpyHostToDevice, p->st.copy));
+            raw = p->raw[slot].p;
+        }
+        MDC_CHECK(launch_block(p, raw, F, slot, &launches));
+    }
+    // the caller may reuse `pos` on return: wait for the copies / layout kernels (not the analysis kernels)
+    MDC_CUDA(cudaStreamSynchronize(p->st.copy));
+    p->n_frames += n_frames;
+    p->last_launches = launches;
+    return MDC_OK;
+}
+
+extern "C" int mdc_sq_read(mdc_sq_plan *p, double *ssf_out, int64_t *n_frames_out)
+{
+    if (!p) return fail(MDC_ERR_INVALID, "mdc_sq_read: NULL plan");
+    MDC_CUDA(cudaSetDevice(p->ctx->device));
+    MDC_CUDA(cudaStreamSynchronize(p->st.compute));
+    if (ssf_out)
+        MDC_CUDA(cudaMemcpy(ssf_out, p->ssf.p, (size_t)p->nq * p->n_pairs * sizeof(double), cudaMemcpyDeviceToHost));
+    if (n_frames_out) *n_frames_out = p->n_frames;
+    return MDC_OK;
+}
+
+extern "C" int mdc_sq_reset(mdc_sq_plan *p)
+{
+    if (!p) return fail(MDC_ERR_INVALID, "mdc_sq_reset: NULL plan");
+    MDC_CUDA(cudaSetDevice(p->ctx->device));
+    MDC_CUDA(cudaStreamSynchronize(p->st.compute));
+    MDC_CUDA(cudaMemset(p->ssf.p, 0, (size_t)p->nq * p->n_pairs * sizeof(double)));
+    p->n_frames = 0;
+    return MDC_OK;
+}
+
+extern "C" int mdc_sq_accum_ptr(mdc_sq_plan *p, void **dev_ptr, int64_t *n_elems)
+{
+    if (!p || !dev_ptr || !n_elems) return fail(MDC_ERR_INVALID, "mdc_sq_accum_ptr: NULL argument");
+    MDC_CUDA(cudaSetDevice(p->ctx->device));
+    MDC_CUDA(cudaStreamSynchronize(p->st.compute));
+    *dev_ptr = p->ssf.p;
+    *n_elems = p->nq * p->n_pairs;
+    return MDC_OK;
+}
+
+extern "C" int mdc_sq_set_frames(mdc_sq_plan *p, int64_t n_frames)
+{
+    if (!p || n_frames < 0) return fail(MDC_ERR_INVALID, "mdc_sq_set_frames: bad argument");
+    p->n_frames = n_frames;
+    return MDC_OK;
+}
+
+extern "C" int mdc_sq_last_push_stats(mdc_sq_plan *p, float *kernel_ms, int *n_launches)
+{
+    if (!p) return fail(MDC_ERR_INVALID, "mdc_sq_last_push_stats: NULL plan");
+    MDC_CUDA(cudaSetDevice(p->ctx->device));
+    if (kernel_ms) MDC_CHECK(p->st.kernel_ms(kernel_ms));
+    if (n_launches) *n_launches = p->last_launches;
+    return MDC_OK;
+}
+
+extern "C" int mdc_delta_fourier_transform_sum(mdc_ctx *ctx, const double *qs, int64_t nq, const double *rs,
+                                               int64_t n, int precision, double *rho_out)
+{
+    if (!ctx || !qs || !rs || !rho_out) return fail(MDC_ERR_INVALID, "mdc_delta_fourier_transform_sum: NULL argument");
+    if (nq <= 0 || n <= 0 || n > 2147483647ll) return fail(MDC_ERR_INVALID, "mdc_delta_fourier_transform_sum: bad sizes");
+    MDC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<double> dq, drs, dpos;
+    DevBuf<double2> part;
+    DevBuf<int2> dset;
+    int rc = MDC_OK;
+    const int64_t blocks_q = ceil_div(nq, SQ_THREADS);
+    int64_t P = std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)ctx->sm_count * 16, blocks_q), n / SQX_TILE));
+    P = std::min<int64_t>(P, 1024);
+    std::vector<double2> h;
+    double dc[2] = {0, 0};
+    do {
+        if ((rc = dq.alloc((size_t)nq * 3)) || (rc = drs.alloc((size_t)n * 3)) || (rc = dpos.alloc((size_t)n * 3)) ||
+            (rc = part.alloc((size_t)P * nq)) || (rc = dset.alloc(1)))
+            break;
+        const int2 set = make_int2(0, (int)n);
+        cudaMemcpy(dq.p, qs, (size_t)nq * 3 * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(drs.p, rs, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(dset.p, &set, sizeof(set), cudaMemcpyHostToDevice);
+        transpose_f64<<<(unsigned)ceil_div(n, 256), 256>>>(drs.p, n, dpos.p);
+        dim3 g((unsigned)blocks_q, (unsigned)P, 1);
+        if (precision == MDC_PRECISION_FP64) {
+            sq_explicit_f64<<<g, SQ_THREADS>>>(dq.p, 0, nq, dpos.p, n, dset.p, 1, (int)P, nq, part.p);
+        } else {
+            double pr[4];
+            if ((rc = run_probe_sincos(0, pr))) break;
+            dc[0] = pr[0];
+            dc[1] = pr[1];
+            sq_explicit_f32<<<g, SQ_THREADS>>>(dq.p, 0, nq, dpos.p, n, dset.p, 1, (int)P, nq, part.p);
+        }
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            rc = fail(MDC_ERR_CUDA, std::string("mdc_delta_fourier_transform_sum: ") + cudaGetErrorString(e));
+            break;
+        }
+        h.resize((size_t)P * nq);
+        e = cudaMemcpy(h.data(), part.p, h.size() * sizeof(double2), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            rc = fail(MDC_ERR_CUDA, std::string("mdc_delta_fourier_transform_sum: ") + cudaGetErrorString(e));
+            break;
+        }
+        for (int64_t i = 0; i < nq; ++i) {
+            double re = 0, im = 0;
+            for (int64_t pp = 0; pp < P; ++pp) {
+                re += h[pp * nq + i].x;
+                im += h[pp * nq + i].y;
+            }
+            rho_out[2 * i] = re - (double)n * dc[0];
+            rho_out[2 * i + 1] = im - (double)n * dc[1];
+        }
+    } while (0);
+    dq.release();
+    drs.release();
+    dpos.release();
+    part.release();
+    dset.release();
+    return rc;
+}
+
+extern "C" int mdc_probe_sincos(mdc_ctx *ctx, int variant, double out[4])
+{
+    if (!ctx || !out) return fail(MDC_ERR_INVALID, "mdc_probe_sincos: NULL argument");
+    MDC_CUDA(cudaSetDevice(ctx->device));
+    return run_probe_sincos(variant, out);
+}

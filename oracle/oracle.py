@@ -1,0 +1,396 @@
+"""
+CPU oracle for the S(q) / g(r) hot path — TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
+/ ``--impl reference`` legs may import this module.  Nothing under
+``mdcraft_b200/`` does; the product path fails loudly without its CUDA library.
+
+It wraps ``oracle/oracle.c`` (the arithmetic, see that file's header for what
+is pinned against the reference and what is "parity unpinned") and restates
+the class-level bookkeeping of the reference in NumPy:
+
+* ``structure_factor``  ~ ``StructureFactor.__init__/_prepare/_single_frame/
+  _conclude``  (``/root/reference/src/mdcraft/analysis/structure.py:1822-2017``)
+* ``rdf``               ~ ``RadialDistributionFunction._prepare/_single_frame/
+  _conclude``  (``structure.py:849-1010``)
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from itertools import combinations_with_replacement
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle.c with the committed Makefile (gcc, OpenMP, no FMA contraction)."""
+    src = os.path.join(_HERE, "oracle.c")
+    if (
+        force
+        or not os.path.exists(_LIB_PATH)
+        or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+    ):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        c_dp = ctypes.POINTER(ctypes.c_double)
+        c_fp = ctypes.POINTER(ctypes.c_float)
+        c_lp = ctypes.POINTER(ctypes.c_int64)
+        c_ip = ctypes.POINTER(ctypes.c_int)
+        L.orc_delta_fourier_transform_sum.argtypes = [c_dp, ctypes.c_int64, c_dp, ctypes.c_int64, c_dp]
+        L.orc_sq_single_frame.argtypes = [c_dp, ctypes.c_int64, c_dp, c_lp, ctypes.c_int, c_ip, ctypes.c_int, c_dp]
+        L.orc_histogram_bin_edges.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int, c_dp]
+        L.orc_histogram.argtypes = [c_dp, ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_double, c_lp]
+        L.orc_pair_distance.argtypes = [c_fp, c_fp, c_fp]
+        L.orc_pair_distance.restype = ctypes.c_double
+        L.orc_radial_histogram.argtypes = [
+            c_fp, ctypes.c_int64, c_fp, ctypes.c_int64, c_fp, ctypes.c_int,
+            ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_int64, c_lp,
+        ]
+        L.orc_num_threads.restype = ctypes.c_int
+        L.orc_set_num_threads.argtypes = [ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _lp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))
+
+
+# ----------------------------------------------------------------------------
+# S(q)
+# ----------------------------------------------------------------------------
+
+
+def delta_fourier_transform_sum(qs: np.ndarray, rs: np.ndarray) -> np.ndarray:
+    """``structure.py:1240-1280``: ``F[i] = sum_j exp(1j q_i . r_j)`` (complex128)."""
+    qs = np.ascontiguousarray(qs, dtype=np.float64)
+    rs = np.ascontiguousarray(rs, dtype=np.float64)
+    out = np.empty((qs.shape[0], 2), dtype=np.float64)
+    lib().orc_delta_fourier_transform_sum(_dp(qs), qs.shape[0], _dp(rs), rs.shape[0], _dp(out))
+    return out.view(np.complex128).reshape(-1)
+
+
+def wavevector_grid(
+    dimensions: Sequence[float],
+    n_points: int = 32,
+    q_max: Optional[float] = None,
+    n_surfaces: Optional[int] = None,
+    n_surface_points: int = 8,
+):
+    """
+    ``structure.py:1822-1887``: first-octant reciprocal-lattice grid (+ optional
+    off-lattice surface points, cubic boxes only) and the ``q_max`` filter.
+    Returns ``(wavevectors (Nq,3), wavenumbers (Nq,))``.
+    """
+    dimensions = np.asarray(dimensions)
+    if len(dimensions) != 3:
+        raise ValueError("'dimensions' must have length 3.")
+    if np.allclose(dimensions, dimensions[0]):
+        grid = 2 * np.pi * np.arange(n_points) / dimensions[0]
+        wavevectors = np.stack(np.meshgrid(grid, grid, grid), -1).reshape(-1, 3)
+        if n_surfaces:
+            n_theta, n_phi = _closest_factors(n_surface_points)
+            theta = np.linspace(
+                np.pi / (2 * n_theta + 4), np.pi / 2 - np.pi / (2 * n_theta + 4), n_theta
+            )
+            phi = np.linspace(
+                np.pi / (2 * n_phi + 4), np.pi / 2 - np.pi / (2 * n_phi + 4), n_phi
+            )
+            extra = np.einsum(
+                "o,tpd->otpd",
+                grid[1 : n_surfaces + 1],
+                np.stack(
+                    (
+                        np.sin(theta) * np.cos(phi)[:, None],
+                        np.sin(theta) * np.sin(phi)[:, None],
+                        np.tile(np.cos(theta)[None, :], (n_phi, 1)),
+                    ),
+                    axis=-1,
+                ),
+            ).reshape((n_surfaces * n_surface_points, 3))
+            wavevectors = np.vstack((wavevectors, extra))
+    else:
+        wavevectors = np.stack(
+            np.meshgrid(*[2 * np.pi * np.arange(n_points) / L for L in dimensions]),
+            axis=-1,
+        ).reshape(-1, 3)
+    wavenumbers = np.linalg.norm(wavevectors, axis=1)
+    if q_max is not None:
+        keep = wavenumbers <= q_max
+        wavevectors = wavevectors[keep]
+        wavenumbers = wavenumbers[keep]
+    return wavevectors, wavenumbers
+
+
+def _closest_factors(value: int):
+    """
+    ``algorithm/utility.py:16-75`` get_closest_factors(value, 2, reverse=True):
+    the reference's greedy assignment of prime factors (largest first), which
+    is not always the closest pair (72 -> (12, 6)).
+    """
+    n_factors = 2
+    rt = value ** (1 / n_factors)
+    rt_int = int(np.round(rt))
+    if np.isclose(rt, rt_int):
+        return rt_int, rt_int
+    primes, v, p = [], int(value), 2
+    while p * p <= v:
+        while v % p == 0:
+            primes.append(p)
+            v //= p
+        p += 1
+    if v > 1:
+        primes.append(v)
+    i = 0
+    factors = [1] * n_factors
+    for j, f in enumerate(primes[::-1]):
+        while True:
+            if i < n_factors:
+                m = factors[i] * f
+                if m <= rt_int or (j < n_factors and factors[i] == 1):
+                    factors[i] = m
+                    break
+                i += 1
+            else:
+                factors[int(np.argmin(factors))] *= f
+                break
+    hi, lo = sorted(factors)[::-1]
+    return hi, lo
+
+
+def sq_pairs(n_groups: int, mode: Optional[str]):
+    """``structure.py:1917-1921``."""
+    if mode == "partial":
+        return tuple(combinations_with_replacement(range(n_groups), 2))
+    if mode == "pair":
+        return ((0, n_groups - 1),)
+    return ((None, None),)
+
+
+def sq_accumulate(
+    frames: Iterable[np.ndarray],
+    group_sizes: Sequence[int],
+    wavevectors: np.ndarray,
+    pairs,
+) -> tuple:
+    """
+    Per-frame accumulation (``structure.py:1940-1970``).  ``frames`` yields the
+    concatenated float32 ``(N, 3)`` positions of all groups (group order).
+    Returns ``(ssf_sum (n_pairs, Nq), n_frames)`` — un-normalised.
+    """
+    wavevectors = np.ascontiguousarray(wavevectors, dtype=np.float64)
+    offsets = np.concatenate(([0], np.cumsum(group_sizes))).astype(np.int64)
+    pr = np.array(
+        [(-1, -1) if p[0] is None else p for p in pairs], dtype=np.int32
+    ).reshape(-1, 2)
+    ssf = np.zeros((len(pairs), wavevectors.shape[0]))
+    n_frames = 0
+    for pos in frames:
+        pos64 = np.ascontiguousarray(pos, dtype=np.float64)  # structure.py:1943 (f32 -> f64)
+        lib().orc_sq_single_frame(
+            _dp(wavevectors), wavevectors.shape[0], _dp(pos64), _lp(offsets),
+            len(group_sizes), _ip(pr), len(pairs), _dp(ssf),
+        )
+        n_frames += 1
+    return ssf, n_frames
+
+
+def sq_conclude(ssf_sum, n_frames, n_total, wavenumbers, unique=True, sort=True):
+    """``structure.py:1993-2017`` verbatim semantics (the O(N_unique x Nq) isclose loop)."""
+    ssf = ssf_sum / (n_frames * n_total)
+    wn = np.unique(wavenumbers.round(11)) if unique else wavenumbers
+    if unique:
+        ssf = np.hstack(
+            [ssf[:, np.isclose(q, wavenumbers)].mean(axis=1, keepdims=True) for q in wn]
+        )
+    if sort:
+        order = np.argsort(wn)
+        wn = wn[order]
+        ssf = ssf[:, order]
+    return wn, ssf
+
+
+def structure_factor(
+    frames: Iterable[np.ndarray],
+    group_sizes: Sequence[int],
+    dimensions: Sequence[float],
+    *,
+    mode: Optional[str] = None,
+    n_points: int = 32,
+    q_max: Optional[float] = None,
+    n_surfaces: Optional[int] = None,
+    n_surface_points: int = 8,
+    wavevectors: Optional[np.ndarray] = None,
+    sort: bool = True,
+    unique: bool = True,
+) -> dict:
+    """Whole-class restatement; returns the reference's ``results`` keys."""
+    if wavevectors is not None:
+        wv = np.asarray(wavevectors, dtype=np.float64)
+        wn = np.linalg.norm(wv, axis=1)
+        if q_max is not None:
+            keep = wn <= q_max
+            wv, wn = wv[keep], wn[keep]
+    else:
+        wv, wn = wavevector_grid(dimensions, n_points, q_max, n_surfaces, n_surface_points)
+    pairs = sq_pairs(len(group_sizes), mode)
+    ssf_sum, n_frames = sq_accumulate(frames, group_sizes, wv, pairs)
+    wn_out, ssf = sq_conclude(ssf_sum, n_frames, int(np.sum(group_sizes)), wn, unique, sort)
+    return {"pairs": pairs, "ssf": ssf, "wavenumbers": wn_out, "wavevectors": wv, "ssf_sum": ssf_sum, "n_frames": n_frames}
+
+
+# ----------------------------------------------------------------------------
+# g(r)
+# ----------------------------------------------------------------------------
+
+
+def histogram_bin_edges(range_, n_bins: int) -> np.ndarray:
+    """``accelerated.py:13-43``."""
+    edges = np.empty(n_bins + 1)
+    lib().orc_histogram_bin_edges(float(min(range_)), float(max(range_)), int(n_bins), _dp(edges))
+    return edges
+
+
+def histogram(x: np.ndarray, n_bins: int, bin_edges: np.ndarray) -> np.ndarray:
+    """``accelerated.py:46-81`` (LLVM-lowered arithmetic, see oracle.c)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    h = np.zeros(n_bins, dtype=np.int64)
+    lib().orc_histogram(_dp(x), x.shape[0], int(n_bins), float(bin_edges[0]), float(bin_edges[-1]), _lp(h))
+    return h
+
+
+def pair_distance(a, b, box) -> float:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    box = np.ascontiguousarray(box, dtype=np.float32)
+    return float(lib().orc_pair_distance(_fp(a), _fp(b), _fp(box)))
+
+
+def radial_histogram(
+    positions_a, positions_b, n_bins, range_, dimensions, *, exclusion=None
+) -> np.ndarray:
+    """``structure.py:34-131`` with a streamed brute-force ``capped_distance``."""
+    a = np.ascontiguousarray(np.atleast_2d(positions_a), dtype=np.float32)
+    b = np.ascontiguousarray(np.atleast_2d(positions_b), dtype=np.float32)
+    box = np.ascontiguousarray(dimensions, dtype=np.float32)
+    if box.shape[0] >= 6 and not np.all(box[3:6] == 90):
+        raise NotImplementedError("oracle restates the orthorhombic distance routine only")
+    h = np.zeros(n_bins, dtype=np.int64)
+    ex0, ex1 = (0, 0) if exclusion is None else (int(exclusion[0]), int(exclusion[1]))
+    lib().orc_radial_histogram(
+        _fp(a), a.shape[0], _fp(b), b.shape[0], _fp(box), int(n_bins),
+        float(range_[0]), float(range_[1]), ex0, ex1, _lp(h),
+    )
+    return h
+
+
+def capped_distance(reference, configuration, max_cutoff, min_cutoff=None, box=None):
+    """
+    Materialising restatement of ``MDAnalysis.lib.distances.capped_distance``
+    (brute-force method) for SMALL inputs — used only as the stub behind the
+    reference's real ``radial_histogram`` when generating golden vectors.
+    Vectorised NumPy with the same op order as ``oracle.c:orc_pair_r2``.
+    """
+    a = np.atleast_2d(np.asarray(reference, dtype=np.float32))
+    b = np.atleast_2d(np.asarray(configuration, dtype=np.float32))
+    box = np.asarray(box, dtype=np.float32)
+    inv = (1.0 / box[:3].astype(np.float64)).astype(np.float32)
+    r2 = np.zeros((a.shape[0], b.shape[0]))
+    for k in range(3):
+        dx = (b[None, :, k] - a[:, None, k]).astype(np.float64)  # float32 subtract, widened
+        if box[k] > np.finfo(np.float32).eps:
+            s = np.float64(inv[k]) * dx
+            # C round(): half away from zero
+            rs = np.where(s >= 0, np.floor(s + 0.5), np.ceil(s - 0.5))
+            dx = np.float64(box[k]) * (s - rs)
+        sq = dx * dx
+        r2 = sq if k == 0 else r2 + sq
+    d = np.sqrt(r2)
+    mask = d <= max_cutoff
+    if min_cutoff is not None:
+        mask &= d > min_cutoff
+    pairs = np.argwhere(mask)
+    return pairs.astype(np.intp), d[mask]
+
+
+def rdf(
+    frames_a: Iterable[np.ndarray],
+    frames_b: Optional[Iterable[np.ndarray]],
+    dims_per_frame: Iterable[np.ndarray],
+    n_bins: int,
+    range_,
+    *,
+    exclusion=None,
+    norm: Optional[str] = "rdf",
+    drop_axis: Optional[int] = None,
+) -> dict:
+    """Whole-class restatement of the serial RDF path (``structure.py:849-1010``)."""
+    edges = histogram_bin_edges(np.asarray(range_, dtype=float), n_bins)
+    bins = (edges[:-1] + edges[1:]) / 2
+    counts = np.zeros(n_bins, dtype=np.int64)
+    vol = 0.0
+    n_frames = 0
+    fb = frames_a if frames_b is None else frames_b
+    n_a = n_b = None
+    for pa, pb, dims in zip(frames_a, fb, dims_per_frame):
+        pa = np.array(pa, dtype=np.float32)
+        pb = pa if frames_b is None else np.array(pb, dtype=np.float32)
+        dims = np.array(dims, dtype=np.float32)
+        n_a, n_b = pa.shape[0], pb.shape[0]
+        if drop_axis is None:
+            vol += float(dims[0]) * float(dims[1]) * float(dims[2])
+        else:
+            pa[:, drop_axis] = 0
+            pb[:, drop_axis] = 0
+            dims[drop_axis] = dims[:3].max()
+            vol += np.delete(dims[:3], drop_axis).prod()
+        counts += radial_histogram(pa, pb, n_bins, range_, dims, exclusion=exclusion)
+        n_frames += 1
+    nrm = n_frames
+    if norm is not None:
+        if drop_axis is None:
+            nrm = nrm * 4 * np.pi * np.diff(edges**3) / 3
+        else:
+            nrm = nrm * np.pi * np.diff(edges**2)
+        if norm == "rdf":
+            n2 = n_b - (exclusion[1] if exclusion else 0)
+            nrm = nrm * (n_a * n2 * n_frames / vol)
+    return {
+        "bin_edges": edges, "bins": bins, "counts": counts, "rdf": counts / nrm,
+        "n_frames": n_frames, "volume": vol,
+    }

@@ -1,0 +1,160 @@
+"""
+Loads the REAL reference modules from ``/root/reference`` in the build
+container — TEST INFRASTRUCTURE ONLY (golden-vector generation and oracle
+pinning).  ``/root/reference`` does not exist on the GPU box, so nothing that
+runs there may call :func:`load`; use :func:`available` to gate.
+
+Recipe: MDAnalysis and pint are not installed, so stub modules
+are registered in ``sys.modules`` and the heavy package ``__init__`` files are
+bypassed by pre-creating empty package objects whose ``__path__`` points into
+the reference tree.  ``mdcraft.analysis.structure`` then imports unmodified and
+its real ``StructureFactor`` / ``RadialDistributionFunction`` classes run on the
+in-memory Universe from ``mdcraft_b200.synthetic``.  The only non-reference
+arithmetic behind them is the ``capped_distance`` stub (``oracle.capped_distance``).
+"""
+
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+REF_SRC = "/root/reference/src"
+_loaded = None
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_SRC, "mdcraft", "analysis"))
+
+
+class _Unit:
+    """Just enough of a pint unit for ``results.units`` (never used numerically)."""
+
+    def __init__(self, name="dimensionless"):
+        self.name = name
+
+    def __pow__(self, p):
+        return _Unit(f"({self.name})**{p}")
+
+    def __mul__(self, o):
+        return _Unit(f"{self.name}*{getattr(o, 'name', o)}")
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return _Unit(f"{self.name}/{getattr(o, 'name', o)}")
+
+    def __repr__(self):
+        return f"<unit {self.name}>"
+
+
+class _UnitRegistry:
+    def __init__(self, *a, **k):
+        pass
+
+    def __getattr__(self, name):
+        return _Unit(name)
+
+
+class _AnalysisBase:
+    """
+    The run protocol of ``MDAnalysis.analysis.base.AnalysisBase`` [RECALL],
+    consistent with how the reference re-implements it (base.py:386-389, 517).
+    """
+
+    def __init__(self, trajectory, verbose=False, **kwargs):
+        from mdcraft_b200.analysis.base import Results
+
+        self._trajectory = trajectory
+        self._verbose = verbose
+        self.results = Results()
+
+    def _setup_frames(self, trajectory, start=None, stop=None, step=None, frames=None):
+        import numpy as np
+
+        self._trajectory = trajectory
+        if frames is not None:
+            self._sliced_trajectory = trajectory[frames]
+        else:
+            start, stop, step = trajectory.check_slice_indices(start, stop, step)
+            self._sliced_trajectory = trajectory[start:stop:step]
+        self.start, self.stop, self.step = start, stop, step
+        self.n_frames = len(self._sliced_trajectory)
+        self.frames = np.zeros(self.n_frames, dtype=int)
+        self.times = np.zeros(self.n_frames)
+
+    def _prepare(self):
+        pass
+
+    def _conclude(self):
+        pass
+
+    def run(self, start=None, stop=None, step=None, frames=None, verbose=None, **kwargs):
+        self._setup_frames(self._trajectory, start=start, stop=stop, step=step, frames=frames)
+        self._prepare()
+        for i, ts in enumerate(self._sliced_trajectory):
+            self._frame_index = i
+            self._ts = ts
+            self.frames[i] = ts.frame
+            self.times[i] = ts.time
+            self._single_frame()
+        self._conclude()
+        return self
+
+
+def load():
+    """Returns ``(structure_module, accelerated_module)`` of the real reference."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not available():
+        raise RuntimeError("/root/reference is not present (GPU box?)")
+    sys.dont_write_bytecode = True  # the reference tree is read-only
+
+    from mdcraft_b200 import synthetic
+    from . import oracle
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    if "MDAnalysis" not in sys.modules:
+        mda = mod("MDAnalysis", AtomGroup=synthetic.AtomGroup, Universe=synthetic.Universe)
+        mda.__path__ = []
+        lib = mod("MDAnalysis.lib")
+        lib.__path__ = []
+        dist = mod(
+            "MDAnalysis.lib.distances",
+            capped_distance=oracle.capped_distance,
+            minimize_vectors=lambda v, box: v,
+        )
+        ana = mod("MDAnalysis.analysis")
+        ana.__path__ = []
+        base = mod("MDAnalysis.analysis.base", AnalysisBase=_AnalysisBase)
+        coords = mod("MDAnalysis.coordinates")
+        coords.__path__ = []
+        cbase = mod("MDAnalysis.coordinates.base", ReaderBase=object)
+        mda.lib, lib.distances = lib, dist
+        mda.analysis, ana.base = ana, base
+        mda.coordinates, coords.base = coords, cbase
+    if "pint" not in sys.modules:
+        mod("pint", Quantity=type("Quantity", (), {}), UnitRegistry=_UnitRegistry)
+
+    pkg = mod(
+        "mdcraft", FOUND_OPENMM=False, Q_=sys.modules["pint"].Quantity,
+        ureg=_UnitRegistry(), VERSION="reference",
+    )
+    pkg.__path__ = [os.path.join(REF_SRC, "mdcraft")]
+    for sub in ("algorithm", "analysis"):
+        m = mod(f"mdcraft.{sub}")
+        m.__path__ = [os.path.join(REF_SRC, "mdcraft", sub)]
+        setattr(pkg, sub, m)
+
+    accelerated = importlib.import_module("mdcraft.algorithm.accelerated")
+    sys.modules["mdcraft.algorithm"].accelerated = accelerated
+    structure = importlib.import_module("mdcraft.analysis.structure")
+    _loaded = (structure, accelerated)
+    return _loaded

@@ -1,0 +1,189 @@
+"""
+Generates the golden fixtures in this directory by running the REAL reference
+(`/root/reference/src/mdcraft/analysis/structure.py` and
+`algorithm/accelerated.py`, unmodified) in the build container.
+
+    python tests/golden/make_golden.py
+
+The reference cannot be imported normally here (MDAnalysis, pint, matplotlib ...
+are not installed), so `oracle/ref_loader.py` registers stub modules and drives
+the real `StructureFactor` / `RadialDistributionFunction` classes on the
+in-memory Universe of `mdcraft_b200.synthetic`.  S(q) outputs are 100 % reference
+arithmetic.  For g(r) the only non-reference code on the path is the
+`capped_distance` stub (`oracle.capped_distance`, a NumPy restatement of
+MDAnalysis' brute-force orthorhombic routine); binning, exclusion, accumulation
+and normalisation are the reference's.
+
+Every fixture stores its inputs (positions, boxes, arguments) next to the
+reference outputs, so the tests never need `/root/reference`.
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from mdcraft_b200 import synthetic  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+
+def universe_from(pos, dims, resindices=None):
+    traj = synthetic.MemoryTrajectory(np.asarray(pos, np.float32), np.asarray(dims, np.float32))
+    return synthetic.Universe(traj, resindices=resindices)
+
+
+def lj_frames(n, n_frames, rho, seed0, scale=None):
+    L = synthetic.cubic_box_length(n, rho)
+    pos = np.stack([synthetic.lj_like_frame(n, L, seed0 + i) for i in range(n_frames)])
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    if scale is not None:
+        scale = np.asarray(scale, np.float32)
+        pos = (pos * scale).astype(np.float32)
+        dims[:3] = dims[:3] * scale
+        pos = np.where(pos >= dims[:3], np.float32(0), pos).astype(np.float32)
+    return pos, dims
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def main():
+    st, acc = ref_loader.load()
+    rng = np.random.default_rng(20261019)
+
+    # ------------------------------------------------------------------ S(q)
+    # (a) C1: total S(q), default 32^3 grid, N = 1000, 3 frames
+    pos, dims = lj_frames(1000, 3, 0.8, 1000)
+    u = universe_from(pos, dims)
+    r = st.StructureFactor(u.atoms, parallel=True, verbose=False).run()
+    save("sq_total_c1.npz", pos=pos, dims=dims, ssf=r.results.ssf, wavenumbers=r.results.wavenumbers,
+         n_points=32)
+
+    # (b) partial S(q), two groups, q_max filter, off-lattice surfaces
+    pos, dims = lj_frames(600, 3, 0.8, 1100)
+    u = universe_from(pos, dims)
+    ga, gb = u.select(0, 250), u.select(250, 600)
+    r = st.StructureFactor([ga, gb], mode="partial", n_points=14, q_max=6.0, n_surfaces=2, n_surface_points=6,
+                           verbose=False).run()
+    save("sq_partial_surfaces.npz", pos=pos, dims=dims, sizes=np.array([250, 350]), ssf=r.results.ssf,
+         wavenumbers=r.results.wavenumbers, pairs=np.array(r.results.pairs), n_points=14, q_max=6.0,
+         n_surfaces=2, n_surface_points=6, wavevectors=r._wavevectors)
+
+    # (c) pair mode, orthorhombic box, unsorted / non-unique output, trig form
+    pos, dims = lj_frames(512, 2, 0.8, 1200, scale=(1.0, 1.25, 0.8))
+    u = universe_from(pos, dims)
+    ga, gb = u.select(0, 200), u.select(200, 512)
+    r = st.StructureFactor([ga, gb], mode="pair", n_points=7, sort=False, unique=False, verbose=False).run()
+    r2 = st.StructureFactor([ga, gb], mode="pair", n_points=7, form="trig", verbose=False).run()
+    save("sq_pair_ortho.npz", pos=pos, dims=dims, sizes=np.array([200, 312]), ssf=r.results.ssf,
+         wavenumbers=r.results.wavenumbers, ssf_trig_unique=r2.results.ssf, wavenumbers_unique=r2.results.wavenumbers,
+         n_points=7, wavevectors=r._wavevectors)
+
+    # (d) explicit wavevectors
+    pos, dims = lj_frames(300, 2, 0.8, 1300)
+    u = universe_from(pos, dims)
+    wv = rng.normal(size=(97, 3)) * 2.5
+    r = st.StructureFactor(u.atoms, wavevectors=wv, sort=False, unique=False, verbose=False).run()
+    save("sq_explicit.npz", pos=pos, dims=dims, wavevectors=wv, ssf=r.results.ssf, wavenumbers=r.results.wavenumbers)
+
+    # (e) the functional seam: delta_fourier_transform_sum
+    import numba
+
+    dfts = numba.njit(st.delta_fourier_transform_sum, fastmath=True)
+    qs = rng.normal(size=(64, 3)) * 3.0
+    rs = rng.random((777, 3)) * 9.0
+    save("sq_dfts.npz", qs=qs, rs=rs, rho=dfts(qs, rs))
+
+    # ------------------------------------------------------------------ g(r)
+    # (f) C1: self-RDF, 200 bins to L/2, with and without exclusion=(1, 1)
+    pos, dims = lj_frames(1000, 4, 0.8, 1000)
+    u = universe_from(pos, dims)
+    half = float(dims[0]) / 2
+    r = st.RadialDistributionFunction(u.atoms, n_bins=200, range_=(0.0, half), verbose=False).run()
+    rx = st.RadialDistributionFunction(u.atoms, n_bins=200, range_=(0.0, half), exclusion=(1, 1), verbose=False).run()
+    save("rdf_self_c1.npz", pos=pos, dims=dims, range_=np.array([0.0, half]), n_bins=200,
+         counts=r.results.counts, rdf=r.results.rdf, bins=r.results.bins, bin_edges=r.results.bin_edges,
+         counts_excl=rx.results.counts, rdf_excl=rx.results.rdf)
+
+    # (g) cross-RDF, r0 > 0, block exclusion (4, 10), default 201 bins; norm variants
+    pos, dims = lj_frames(700, 3, 0.8, 1400)
+    u = universe_from(pos, dims)
+    ga, gb = u.select(0, 200), u.select(200, 700)
+    out = {}
+    for norm in ("rdf", "density", None):
+        r = st.RadialDistributionFunction(ga, gb, n_bins=201, range_=(0.35, 4.1), exclusion=(4, 10), norm=norm,
+                                          verbose=False).run()
+        out[f"rdf_{norm}"] = r.results.rdf
+        out["counts"] = r.results.counts
+        out["bin_edges"] = r.results.bin_edges
+    save("rdf_cross_excl.npz", pos=pos, dims=dims, sizes=np.array([200, 500]), range_=np.array([0.35, 4.1]),
+         n_bins=201, exclusion=np.array([4, 10]), **out)
+
+    # (h) NPT (box changes every frame), orthorhombic, drop_axis
+    n, F = 400, 4
+    boxes = np.stack([np.array([7.5 + 0.3 * i, 8.0 - 0.2 * i, 9.0 + 0.1 * i, 90, 90, 90], np.float32) for i in range(F)])
+    pos = np.stack([(np.random.default_rng(1500 + i).random((n, 3)) * boxes[i, :3]).astype(np.float32) for i in range(F)])
+    u = universe_from(pos, boxes)
+    r = st.RadialDistributionFunction(u.atoms, n_bins=64, range_=(0.0, 3.5), verbose=False).run()
+    rd = st.RadialDistributionFunction(u.atoms, n_bins=64, range_=(0.0, 3.5), drop_axis=2, verbose=False).run()
+    save("rdf_npt_dropaxis.npz", pos=pos, dims=boxes, range_=np.array([0.0, 3.5]), n_bins=64,
+         counts=r.results.counts, rdf=r.results.rdf, counts_drop=rd.results.counts, rdf_drop=rd.results.rdf)
+
+    # (i) the functional seam, as the reference's own test uses it
+    #     (tests/test_analysis_structure.py:21-46): neighbours at known radii around the box centre
+    L = 20.0
+    origin = np.full(3, L / 2, np.float32)
+    norm_ = rng.random(1000) * (L / 2)
+    v = rng.normal(size=(1000, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    neighbors = (origin + norm_[:, None] * v).astype(np.float32)
+    box = np.array([L, L, L, 90, 90, 90], np.float32)
+    h = st.radial_histogram(origin, neighbors, n_bins=10, range_=(0, 11), dimensions=box)
+    save("rdf_radial_histogram.npz", origin=origin, neighbors=neighbors, dims=box, counts=h)
+
+    # (j) the bin formula itself: numba_histogram on length-1 arrays (scalar loop) for random values and
+    #     for values within a few ulps of every edge, plus numba_histogram_bin_edges
+    cases = [(0.0, 5.386094808578491, 50), (0.0, 15.0, 201), (0.3, 7.7, 200), (1.0, 11.0, 10), (0.25, 9.3, 1000),
+             (0.0, 17.09976, 200)]
+    hist = {}
+    for c, (r0, r1, n) in enumerate(cases):
+        edges = acc.numba_histogram_bin_edges(np.asarray((r0, r1), dtype=float), n)
+        vals = list(rng.uniform(r0 - 0.05, r1 + 0.05, 300))
+        for e in edges[:: max(1, n // 40)]:
+            x = e
+            for _ in range(3):
+                vals.append(x)
+                x = np.nextafter(x, np.inf)
+            x = e
+            for _ in range(3):
+                x = np.nextafter(x, -np.inf)
+                vals.append(x)
+        vals += [r1, np.nextafter(r1, -np.inf), np.nextafter(r1, np.inf), r0, r0 - 1e-17, r0 - 2.3e-16]
+        vals = np.array(vals)
+        bins = np.empty(vals.shape[0], dtype=np.int64)
+        for i, x in enumerate(vals):
+            nz = np.nonzero(acc.numba_histogram(np.array([x]), n, edges))[0]
+            bins[i] = nz[0] if len(nz) else -1
+        hist[f"case{c}_args"] = np.array([r0, r1, n])
+        hist[f"case{c}_edges"] = edges
+        hist[f"case{c}_values"] = vals
+        hist[f"case{c}_bins"] = bins
+    # the reference's position dependence at a bin edge (see oracle.c): np.full(L, just-below-edge)
+    edges = acc.numba_histogram_bin_edges(np.asarray((0.0, 15.0), dtype=float), 201)
+    below = np.nextafter(edges[50], -np.inf)
+    hist["position_dependence"] = np.array(
+        [[L_, *acc.numba_histogram(np.full(L_, below), 201, edges)[49:51]] for L_ in (1, 2, 3, 4, 8)]
+    )
+    save("histogram_pins.npz", n_cases=len(cases), **hist)
+
+
+if __name__ == "__main__":
+    main()

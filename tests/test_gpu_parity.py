@@ -1,0 +1,307 @@
+"""
+GPU: the CUDA path (through the C ABI and through the drop-in classes) against
+the golden vectors of the real reference and against the CPU oracle.
+
+Bars: g(r) counts bit-exact; S(q) within 1e-5 relative of the
+reference in FP32 mode (plus the reference's own atol=1e-6 where S is tiny),
+1e-10 in FP64 mode.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import golden, universe_from
+
+pytestmark = pytest.mark.gpu
+
+SQ_RTOL_FP32, SQ_ATOL = 1e-5, 1e-6
+
+
+def _sq_close(got, want, precision):
+    if precision == "fp64":
+        np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
+    else:
+        np.testing.assert_allclose(got, want, rtol=SQ_RTOL_FP32, atol=SQ_ATOL)
+
+
+# --------------------------------------------------------------------------- C ABI
+
+
+def test_device_is_b200_class(ctx):
+    info = ctx.info()
+    assert info["cc"][0] >= 10 and info["sm_count"] > 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_dfts_seam(ctx, precision):
+    g = golden("sq_dfts.npz")
+    rho = ctx.delta_fourier_transform_sum(g["qs"], g["rs"], precision)
+    tol = 1e-9 if precision == "fp64" else 2e-3   # |rho| ~ sqrt(777); FP32 mode: absolute error ~1e-4
+    np.testing.assert_allclose(rho, g["rho"], rtol=0, atol=tol)
+
+
+def test_radial_histogram_seam(ctx):
+    g = golden("rdf_radial_histogram.npz")
+    h = ctx.radial_histogram(g["origin"], g["neighbors"], 10, (0, 11), g["dims"])
+    np.testing.assert_array_equal(h, g["counts"])
+
+
+def test_wavevector_grid_built_on_device(ctx):
+    from mdcraft_b200 import _capi
+    from oracle import oracle
+
+    for dims, n_points, q_max in (((10.77, 10.77, 10.77), 32, None), ((10.77, 10.77, 10.77), 36, 20.0),
+                                  ((8.0, 10.0, 6.5), 9, 5.0), ((50.0, 50.0, 50.0), 20, 1.0)):
+        L0 = np.array(dims, np.float32).astype(np.float64)
+        wv, _ = oracle.wavevector_grid(L0, n_points, q_max)
+        plan = _capi.SqPlan(ctx, [10], [(None, None)], n_points=n_points, L0=L0, q_max=q_max)
+        assert plan.n_wavevectors == wv.shape[0]
+        np.testing.assert_array_equal(plan.wavevectors(), wv)
+        plan.close()
+
+
+def test_plan_errors(ctx):
+    from mdcraft_b200 import _capi
+
+    with pytest.raises(_capi.MdcError):
+        _capi.RdfPlan(ctx, 0, (0.0, 1.0), 10)
+    with pytest.raises(_capi.MdcError):
+        _capi.RdfPlan(ctx, 10, (2.0, 1.0), 10)
+    with pytest.raises(_capi.MdcError):
+        _capi.SqPlan(ctx, [10], [(None, None)], n_points=0)
+    plan = _capi.RdfPlan(ctx, 10, (0.0, 1.0), 10)
+    with pytest.raises(_capi.MdcError, match="orthorhombic"):
+        plan.push(np.zeros((1, 10, 3), np.float32), None, np.array([[5, 5, 5, 90, 60, 90]], np.float32))
+    with pytest.raises(ValueError):
+        plan.push(np.zeros((1, 11, 3), np.float32), None, np.array([[5, 5, 5, 90, 90, 90]], np.float32))
+    plan.close()
+
+
+def test_histogram_bins_through_the_kernel(ctx):
+    """Every pinned (value -> bin) of the reference's numba_histogram, pushed through the pair kernel
+    as a two-particle system whose separation is exactly that value."""
+    g = golden("histogram_pins.npz")
+    box = np.array([1e4, 1e4, 1e4, 90, 90, 90], np.float32)
+    checked = 0
+    for c in range(int(g["n_cases"])):
+        r0, r1, n = g[f"case{c}_args"]
+        n = int(n)
+        for x, want in zip(g[f"case{c}_values"], g[f"case{c}_bins"]):
+            xf = np.float32(x)
+            if float(xf) != x or x < 0:     # only separations a float32 coordinate can realise exactly
+                continue
+            a = np.zeros((1, 3), np.float32)
+            b = np.array([[xf, 0, 0]], np.float32)
+            h = ctx.radial_histogram(a, b, n, (r0, r1), box)
+            nz = np.nonzero(h)[0]
+            assert (nz[0] if len(nz) else -1) == want, (c, x)
+            checked += 1
+    assert checked > 10
+
+
+# --------------------------------------------------------------------------- g(r) class
+
+
+def _rdf(*args, **kw):
+    from mdcraft_b200.analysis.structure import RadialDistributionFunction
+
+    return RadialDistributionFunction(*args, verbose=False, **kw).run()
+
+
+def test_rdf_self_c1_golden():
+    g = golden("rdf_self_c1.npz")
+    u = universe_from(g["pos"], g["dims"])
+    r = _rdf(u.atoms, n_bins=int(g["n_bins"]), range_=tuple(g["range_"]), frame_block=3)
+    assert r.results.counts.dtype == np.int64
+    np.testing.assert_array_equal(r.results.counts, g["counts"])
+    np.testing.assert_array_equal(r.results.bin_edges, g["bin_edges"])
+    np.testing.assert_array_equal(r.results.bins, g["bins"])
+    np.testing.assert_allclose(r.results.rdf, g["rdf"], rtol=1e-12)
+    rx = _rdf(u.atoms, n_bins=int(g["n_bins"]), range_=tuple(g["range_"]), exclusion=(1, 1))
+    np.testing.assert_array_equal(rx.results.counts, g["counts_excl"])
+    np.testing.assert_allclose(rx.results.rdf, g["rdf_excl"], rtol=1e-12)
+    # passing the same group twice is the same thing (structure.py:805)
+    r2 = _rdf(u.atoms, u.atoms, n_bins=int(g["n_bins"]), range_=tuple(g["range_"]))
+    np.testing.assert_array_equal(r2.results.counts, g["counts"])
+    # run(start, stop, step)
+    r3 = _rdf(u.atoms, n_bins=int(g["n_bins"]), range_=tuple(g["range_"]))
+    r3.run(start=1, stop=4, step=2)
+    from oracle import oracle
+
+    want = oracle.rdf([g["pos"][1], g["pos"][3]], None, [g["dims"]] * 2, int(g["n_bins"]), tuple(g["range_"]))
+    np.testing.assert_array_equal(r3.results.counts, want["counts"])
+    np.testing.assert_allclose(r3.results.rdf, want["rdf"], rtol=1e-12)
+
+
+def test_rdf_cross_exclusion_norms_golden():
+    g = golden("rdf_cross_excl.npz")
+    u = universe_from(g["pos"], g["dims"])
+    na = int(g["sizes"][0])
+    ga, gb = u.select(0, na), u.select(na, g["pos"].shape[1])
+    for norm in ("rdf", "density", None):
+        r = _rdf(ga, gb, n_bins=int(g["n_bins"]), range_=tuple(g["range_"]), exclusion=tuple(int(e) for e in g["exclusion"]),
+                 norm=norm)
+        np.testing.assert_array_equal(r.results.counts, g["counts"])
+        np.testing.assert_allclose(r.results.rdf, g[f"rdf_{norm}"], rtol=1e-12)
+    # asymmetric block exclusion on ONE group takes the ordered-pair path
+    from oracle import oracle
+
+    want = oracle.rdf(list(g["pos"]), None, [g["dims"]] * len(g["pos"]), 50, (0.0, 4.0), exclusion=(4, 10))
+    r = _rdf(u.atoms, n_bins=50, range_=(0.0, 4.0), exclusion=(4, 10))
+    np.testing.assert_array_equal(r.results.counts, want["counts"])
+
+
+def test_rdf_npt_and_drop_axis_golden():
+    g = golden("rdf_npt_dropaxis.npz")
+    u = universe_from(g["pos"], g["dims"])
+    r = _rdf(u.atoms, n_bins=int(g["n_bins"]), range_=tuple(g["range_"]), frame_block=2)
+    np.testing.assert_array_equal(r.results.counts, g["counts"])
+    np.testing.assert_allclose(r.results.rdf, g["rdf"], rtol=1e-12)
+    rd = _rdf(u.atoms, n_bins=int(g["n_bins"]), range_=tuple(g["range_"]), drop_axis="z")
+    np.testing.assert_array_equal(rd.results.counts, g["counts_drop"])
+    np.testing.assert_allclose(rd.results.rdf, g["rdf_drop"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,n_bins,frac", [(1, 8, 0.5), (2, 8, 0.5), (511, 33, 0.5), (512, 200, 0.5), (513, 200, 0.37),
+                                           (1025, 1000, 0.5), (3000, 200, 0.5), (2049, 4096, 0.45)])
+def test_rdf_ragged_sizes_vs_oracle(n, n_bins, frac):
+    """Tile-edge sizes (tiles are 512 x 512), tiny systems, many bins."""
+    from oracle import oracle
+
+    rng = np.random.default_rng(n)
+    L = np.float32(max(2.0, (n / 0.8) ** (1 / 3)))
+    pos = (rng.random((2, n, 3)) * L).astype(np.float32)
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    rng_ = (0.0, float(L) * frac)
+    want = oracle.rdf(list(pos), None, [dims] * 2, n_bins, rng_)
+    u = universe_from(pos, dims)
+    r = _rdf(u.atoms, n_bins=n_bins, range_=rng_)
+    np.testing.assert_array_equal(r.results.counts, want["counts"])
+    if n > 2:
+        na = n // 3
+        want = oracle.rdf(list(pos[:, :na]), list(pos[:, na:]), [dims] * 2, n_bins, rng_)
+        r = _rdf(u.select(0, na), u.select(na, n), n_bins=n_bins, range_=rng_)
+        np.testing.assert_array_equal(r.results.counts, want["counts"])
+
+
+def test_rdf_adversarial_edge_distances():
+    """Particles on a lattice whose spacings fall exactly on bin edges, coincident particles,
+    separations of exactly L/2 (minimum-image ties) and unwrapped coordinates."""
+    from oracle import oracle
+
+    L = np.float32(16.0)
+    g1 = np.arange(0, 16, 0.5, dtype=np.float32)
+    lattice = np.stack(np.meshgrid(g1[::2], g1[::4], g1[::8], indexing="ij"), -1).reshape(-1, 3)
+    extra = np.array([[0, 0, 0], [0, 0, 0], [8, 0, 0], [8, 8, 8], [-3.5, 20.25, 33.0], [15.999999, 0, 0]], np.float32)
+    pos = np.concatenate([lattice, extra])[None]
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    for n_bins, rng_ in ((16, (0.0, 8.0)), (64, (0.0, 8.0)), (200, (0.0, 8.0)), (10, (1.0, 6.0)), (7, (0.5, 7.5))):
+        want = oracle.rdf(list(pos), None, [dims], n_bins, rng_)
+        u = universe_from(pos, dims)
+        r = _rdf(u.atoms, n_bins=n_bins, range_=rng_)
+        np.testing.assert_array_equal(r.results.counts, want["counts"])
+
+
+def test_rdf_post_processing_runs():
+    g = golden("rdf_self_c1.npz")
+    u = universe_from(g["pos"], g["dims"])
+    r = _rdf(u.atoms, n_bins=int(g["n_bins"]), range_=tuple(g["range_"]), exclusion=(1, 1))
+    r.calculate_coordination_numbers(0.8, threshold=0.01)
+    assert r.results.coordination_numbers.shape == (2,)
+    r.calculate_pmf(300.0)
+    assert r.results.pmf.shape == r.results.rdf.shape
+    r.calculate_structure_factor(0.8, n_q=32)
+    assert r.results.ssf.shape == (32,)
+
+
+# --------------------------------------------------------------------------- S(q) class
+
+
+def _sq(*args, **kw):
+    from mdcraft_b200.analysis.structure import StructureFactor
+
+    return StructureFactor(*args, verbose=False, **kw).run()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_sq_total_c1_golden(precision):
+    g = golden("sq_total_c1.npz")
+    u = universe_from(g["pos"], g["dims"])
+    r = _sq(u.atoms, precision=precision, frame_block=2)
+    assert r.results.pairs == ((None, None),)
+    np.testing.assert_array_equal(r.results.wavenumbers, g["wavenumbers"])
+    _sq_close(r.results.ssf, g["ssf"], precision)
+    if precision == "fp32":
+        # ensemble-level statement of the FP32 bar: relative error of every shell with S > 0.01
+        m = g["ssf"] > 1e-2
+        assert np.max(np.abs(r.results.ssf[m] / g["ssf"][m] - 1)) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_sq_partial_surfaces_golden(precision):
+    g = golden("sq_partial_surfaces.npz")
+    u = universe_from(g["pos"], g["dims"])
+    na = int(g["sizes"][0])
+    kw = dict(n_points=int(g["n_points"]), q_max=float(g["q_max"]), n_surfaces=int(g["n_surfaces"]),
+              n_surface_points=int(g["n_surface_points"]), precision=precision)
+    r = _sq([u.select(0, na), u.select(na, g["pos"].shape[1])], mode="partial", **kw)
+    assert r.results.pairs == tuple(map(tuple, g["pairs"]))
+    np.testing.assert_array_equal(r._wavevectors, g["wavevectors"])
+    np.testing.assert_array_equal(r.results.wavenumbers, g["wavenumbers"])
+    _sq_close(r.results.ssf, g["ssf"], precision)
+    # sum rule: sum of the partials equals the total S(q) of the same run
+    tot = _sq(u.atoms, **kw)
+    np.testing.assert_allclose(r.results.ssf.sum(axis=0), tot.results.ssf[0], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_sq_pair_ortho_golden(precision):
+    g = golden("sq_pair_ortho.npz")
+    u = universe_from(g["pos"], g["dims"])
+    na = int(g["sizes"][0])
+    groups = [u.select(0, na), u.select(na, g["pos"].shape[1])]
+    r = _sq(groups, mode="pair", n_points=int(g["n_points"]), sort=False, unique=False, precision=precision)
+    assert r.results.pairs == ((0, 1),)
+    np.testing.assert_array_equal(r._wavevectors, g["wavevectors"])
+    _sq_close(r.results.ssf, g["ssf"], precision)
+    r2 = _sq(groups, mode="pair", n_points=int(g["n_points"]), form="trig", precision=precision)
+    np.testing.assert_array_equal(r2.results.wavenumbers, g["wavenumbers_unique"])
+    _sq_close(r2.results.ssf, g["ssf_trig_unique"], precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_sq_explicit_golden(precision):
+    g = golden("sq_explicit.npz")
+    u = universe_from(g["pos"], g["dims"])
+    r = _sq(u.atoms, wavevectors=g["wavevectors"], sort=False, unique=False, precision=precision)
+    np.testing.assert_array_equal(r.results.wavenumbers, g["wavenumbers"])
+    _sq_close(r.results.ssf, g["ssf"], precision)
+
+
+def test_sq_fp32_is_reproducible_and_frame_block_invariant():
+    g = golden("sq_total_c1.npz")
+    u = universe_from(g["pos"], g["dims"])
+    a = _sq(u.atoms, n_points=16, frame_block=1).results.ssf
+    b = _sq(u.atoms, n_points=16, frame_block=1).results.ssf
+    np.testing.assert_array_equal(a, b)
+    c = _sq(u.atoms, n_points=16, frame_block=3).results.ssf
+    np.testing.assert_allclose(a, c, rtol=1e-12)
+
+
+def test_sq_large_n_accuracy_vs_oracle():
+    """The coherent-error budget (SURVEY.md §7 hard part 2) at N = 50,000: one frame, a few hundred
+    wavevectors of the default grid against the FP64 oracle."""
+    from mdcraft_b200 import synthetic
+    from oracle import oracle
+
+    n = 50_000
+    L = synthetic.cubic_box_length(n, 0.8)
+    pos = synthetic.lj_like_frame(n, L, 7)[None]
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    want = oracle.structure_factor(list(pos), [n], dims[:3], n_points=7, sort=False, unique=False)
+    u = universe_from(pos, dims)
+    r = _sq(u.atoms, n_points=7, sort=False, unique=False)
+    s, s0 = r.results.ssf[0], want["ssf"][0]
+    np.testing.assert_allclose(s, s0, rtol=1e-5, atol=1e-6)
+    m = s0 > 0.05
+    assert np.max(np.abs(s[m] / s0[m] - 1)) < 1e-5

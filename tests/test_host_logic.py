@@ -1,0 +1,173 @@
+"""CPU: host-side logic of the drop-in classes, the C-ABI surface and the no-fallback rule."""
+
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden, universe_from
+from mdcraft_b200 import _capi, algorithm, build, distributed
+from mdcraft_b200.analysis import structure
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    declared = _capi.declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/mdcraft_b200.h but not exported"
+    # and the binding covers exactly the header
+    assert sorted(_capi.SIGNATURES) == declared
+    assert _capi.lib().mdc_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_capi.MdcError) as err:
+        _capi.Context(0)
+    assert "no CPU fallback" in str(err.value) or "CUDA" in str(err.value)
+    g = golden("rdf_self_c1.npz")
+    u = universe_from(g["pos"], g["dims"])
+    with pytest.raises(_capi.MdcError):
+        structure.RadialDistributionFunction(u.atoms, n_bins=10, range_=(0.0, 3.0), verbose=False).run()
+    with pytest.raises(_capi.MdcError):
+        structure.StructureFactor(u.atoms, n_points=4, verbose=False)
+    # nothing under mdcraft_b200/ may import the oracle
+    root = os.path.dirname(os.path.abspath(build.__file__))
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_constructor_validation_matches_reference_messages():
+    g = golden("rdf_self_c1.npz")
+    u = universe_from(g["pos"][:1], g["dims"])
+    a = u.atoms
+    with pytest.raises(ValueError, match="Invalid grouping 'molecules'"):
+        structure.RadialDistributionFunction(a, groupings="molecules")
+    with pytest.raises(ValueError, match="must be a string or an array with length 2"):
+        structure.RadialDistributionFunction(a, groupings=("atoms",))
+    with pytest.raises(ValueError, match="Invalid axis in 'drop_axis'"):
+        structure.RadialDistributionFunction(a, drop_axis=3)
+    assert structure.RadialDistributionFunction(a, drop_axis="z")._drop_axis == 2
+    with pytest.raises(ValueError, match="Invalid grouping 'segments'"):
+        structure.StructureFactor(a, groupings="segments")
+    with pytest.raises(ValueError, match="exactly one or two atom groups"):
+        structure.StructureFactor([u.select(0, 10), u.select(10, 20), u.select(20, 30)], mode="pair")
+    with pytest.raises(ValueError, match="must contain all atoms"):
+        structure.StructureFactor(u.select(0, 10))
+    with pytest.raises(ValueError, match="'dimensions' must have length 3"):
+        structure.StructureFactor(a, dimensions=[1.0, 2.0])
+    u2 = universe_from(g["pos"][:1], None)
+    with pytest.raises(ValueError, match="does not contain system dimension"):
+        structure.RadialDistributionFunction(u2.atoms)
+    with pytest.raises(ValueError, match="System dimensions were not found"):
+        structure.StructureFactor(u2.atoms)
+
+
+def test_bin_edges_match_reference():
+    g = golden("histogram_pins.npz")
+    for c in range(int(g["n_cases"])):
+        r0, r1, n = g[f"case{c}_args"]
+        np.testing.assert_array_equal(algorithm.histogram_bin_edges((r0, r1), int(n)), g[f"case{c}_edges"])
+
+
+def test_get_closest_factors():
+    assert tuple(algorithm.get_closest_factors(8, 2, reverse=True)) == (4, 2)
+    assert tuple(algorithm.get_closest_factors(6, 2, reverse=True)) == (3, 2)
+    assert tuple(algorithm.get_closest_factors(16, 2)) == (4, 4)
+    assert tuple(algorithm.get_closest_factors(72, 2, reverse=True)) == (12, 6)
+    assert tuple(algorithm.get_closest_factors(7, 2, reverse=True)) == (7, 1)
+    for v in (6, 8, 12, 30, 72, 97, 128):
+        assert int(np.prod(algorithm.get_closest_factors(v, 2))) == v
+        assert int(np.prod(algorithm.get_closest_factors(v, 3))) == v
+
+
+def test_strip_unit_plain_values():
+    assert algorithm.strip_unit(2.5, "Å") == (2.5, "Å")
+    assert algorithm.strip_unit([1, 2, 3], "Å")[0] == [1, 2, 3]
+    assert algorithm.is_unitless(300.0)
+    assert algorithm.strip_unit("12.5", "K")[0] == 12.5
+
+
+def test_combine_equal_wavenumbers_is_the_reference_loop():
+    rng = np.random.default_rng(3)
+    for n_points, L in ((12, 10.77), (24, 50.0)):
+        grid = 2 * np.pi * np.arange(n_points) / L
+        wv = np.stack(np.meshgrid(grid, grid, grid), -1).reshape(-1, 3)
+        wn = np.linalg.norm(wv, axis=1)
+        ssf = rng.random((3, wn.shape[0]))
+        uq = np.unique(wn.round(11))
+        want = np.hstack([ssf[:, np.isclose(q, wn)].mean(axis=1, keepdims=True) for q in uq])
+        got = structure.combine_equal_wavenumbers(ssf, wn, uq)
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+    # overlapping isclose windows (large |n|): membership must still be identical
+    wn = np.sort(np.concatenate([1000.0 + np.arange(50) * 4e-3, [1000.1 + 1e-9, 1000.1 - 1e-9]]))
+    uq = np.unique(wn.round(11))
+    ssf = rng.random((2, wn.shape[0]))
+    want = np.hstack([ssf[:, np.isclose(q, wn)].mean(axis=1, keepdims=True) for q in uq])
+    np.testing.assert_allclose(structure.combine_equal_wavenumbers(ssf, wn, uq), want, rtol=1e-13, atol=0)
+
+
+def test_frame_block_partition():
+    for n in (0, 1, 7, 8, 100, 1001):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [distributed.frame_block(n, r, world) for r in range(world)]
+            covered = [i for lo, hi in blocks for i in range(lo, hi)]
+            assert covered == list(range(n))
+            assert max(hi - lo for lo, hi in blocks) <= -(-n // world) if n else True
+    for start, stop, step in ((None, None, None), (3, 97, 4), (10, 11, 1), (5, 5, 1), (0, 100, 7)):
+        want = list(range(*slice(start, stop, step).indices(100)))
+        for world in (1, 2, 4, 8):
+            got = []
+            for r in range(world):
+                s0, s1, st = distributed.shard_slice(100, start, stop, step, rank=r, world=world)
+                got += list(range(s0, s1, st))
+            assert got == want
+
+
+def test_post_processing_functions():
+    # analytic check used by the reference's own test (tests/test_analysis_structure.py:48-59):
+    # the radial Fourier transform of exp(-alpha r) / r is 4 pi / (alpha^2 + q^2)
+    alpha = 3.0
+    r = np.linspace(1e-8, 20, 20001)
+    q = np.linspace(0.5, 5, 10)
+    f = np.exp(-alpha * r) / r
+    np.testing.assert_allclose(structure.radial_fourier_transform(r, f, q), 4 * np.pi / (alpha**2 + q**2), atol=4e-5)
+    # coordination number of an ideal gas shell: no minima -> nan + warning
+    with pytest.warns(UserWarning):
+        cn = structure.calculate_coordination_numbers(np.linspace(0.1, 5, 50), np.ones(50), 0.8)
+    assert np.isnan(cn).all()
+    bins = np.linspace(0.05, 6, 120)
+    rdf = 1 + np.cos(2 * np.pi * bins / 2.0) * np.exp(-bins / 3) * (bins > 0.8)
+    rdf[bins <= 0.8] = 0.0
+    cn = structure.calculate_coordination_numbers(bins, rdf, 0.8, threshold=0.05)
+    assert np.isfinite(cn[0]) and cn[0] > 0
+    qq, s = structure.calculate_structure_factor(bins, rdf, True, 0.8, n_q=16)
+    assert qq.shape == s.shape == (16,)
+    with pytest.raises(ValueError):
+        structure.calculate_structure_factor(bins, rdf, False, 0.8, 0.5, 0.5, formalism="nope")
+
+
+def test_synthetic_universe_protocol():
+    from mdcraft_b200 import synthetic
+
+    u = synthetic.make_config("C1", n_frames=5)
+    assert u.atoms.n_atoms == 1000 and len(u.trajectory) == 5
+    p0 = u.trajectory[0].positions.copy()
+    assert p0.dtype == np.float32 and p0.shape == (1000, 3)
+    L = u.dimensions[0]
+    assert (p0 >= 0).all() and (p0 < L).all()
+    sl = u.trajectory[1:5:2]
+    assert [ts.frame for ts in sl] == [1, 3]
+    assert u.trajectory.check_slice_indices(None, None, None) == (0, 5, 1)
+    np.testing.assert_array_equal(u.trajectory[0].positions, p0)   # deterministic seeds
