@@ -136,10 +136,10 @@ def cpu_baseline(seconds_target=10.0):
     cores = oracle.num_threads()
     Ls = synthetic.cubic_box_length(N_PART, SQ["rho"])
     pos_s = synthetic.lj_like_frame(N_PART, Ls, SQ["seed0"]).astype(np.float64)
-    wv, _ = oracle.wavevector_grid(np.full(3, float(Ls)), 24, SQ["q_max"])
+    wv, _ = oracle.wavevector_grid(np.full(3, float(Ls)), 64, SQ["q_max"])
     nq_full = 2_140_871
-    nq = 2048 * cores
-    wv = wv[-nq:]
+    wv = wv[-min(2048 * cores, len(wv)):]
+    nq = len(wv)
     oracle.delta_fourier_transform_sum(wv[:cores], pos_s[:1000])   # warm the thread pool
     t0 = time.perf_counter()
     oracle.delta_fourier_transform_sum(wv, pos_s)
@@ -212,7 +212,8 @@ def run_native(args, rank, world):
     Lg = float(box_g[0])
 
     rdf = _capi.RdfPlan(ctx, GR["n_bins"], (0.0, Lg / 2), N_PART, None, (1, 1))
-    sqp = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=SQ["n_points"], L0=[Ls] * 3, q_max=SQ["q_max"])
+    sqp = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=SQ["n_points"], L0=[Ls] * 3, q_max=SQ["q_max"],
+                       algo=args.sq_algo)
     nq = sqp.n_wavevectors
     gr_dev = torch.from_numpy(gr_host).cuda()
     sq_dev = torch.from_numpy(sq_host).cuda()
@@ -286,8 +287,17 @@ def run_native(args, rank, world):
     if rank == 0:
         terms = float(nq) * N_PART * F * args.steps           # per rank
         achieved = terms / (sq_ms * 1e-3)
-        peak = ctx.probe_rate("mufu_sincos_pairs")            # measured on this box, this run
         sm = ctx.info()["sm_count"]
+        if args.sq_algo == "direct":
+            kernel, bound = "sq_lattice_direct", "sfu"
+            peak = ctx.probe_rate("mufu_sincos_pairs")        # measured on this box, this run
+            peak_src = f"measured in this run: MUFU.SIN+MUFU.COS pairs/s (mdc_probe_rate); nominal {sm} SMs x 8 pairs/clk"
+            algorithmic = "2 SFU ops + ~10 FP32/INT issue slots per term"
+        else:
+            kernel, bound = "sq_lattice_factored", "fp32"
+            peak = ctx.probe_rate("ffma") / 4.0               # 4 FP32 FMAs (2 packed FFMA2) per term
+            peak_src = f"measured in this run: FFMA/s / 4 (mdc_probe_rate); nominal {sm} SMs x 128 FMA/clk / 4"
+            algorithmic = "one complex FMA = 4 FP32 FMAs (2 x fma.rn.f32x2) per term; 56 table phasors per 4096 terms"
         pairs = 0.5 * N_PART * (N_PART - 1) * F * args.steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -299,12 +309,11 @@ def run_native(args, rank, world):
                     "d2h_bytes_per_step": int(GR["n_bins"] * 8 + nq * 8)},
             "gpu_launches": launches,
             "roofline": {
-                "bound": "sfu", "kernel": "sq_lattice_direct", "achieved": achieved / 1e9, "peak": peak / 1e9,
+                "bound": bound, "kernel": kernel, "achieved": achieved / 1e9, "peak": peak / 1e9,
                 "unit": "G(q,particle) terms/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": "measured in this run: MUFU.SIN+MUFU.COS pairs/s (mdc_probe_rate); "
-                               f"nominal {sm} SMs x 8 pairs/clk",
-                "algorithmic": "2 SFU ops + ~9 FP32/INT issue slots per term; 12 B of positions per particle per frame",
+                "peak_source": peak_src, "algorithmic": algorithmic,
             },
+            "sq_algo": args.sq_algo,
             "sq_frames_per_s": F * args.steps / (sq_ms * 1e-3),
             "gr_frames_per_s": F * args.steps / (gr_ms * 1e-3),
             "gr_pairs_per_s": pairs / (gr_ms * 1e-3),
@@ -325,6 +334,8 @@ def main():
     ap.add_argument("--frames", type=int, default=2, help="frames per step per GPU")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sq-algo", default="auto", choices=["auto", "direct", "factored"],
+                    help="S(q) lattice kernel: factored (default) or the SFU-bound direct one")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

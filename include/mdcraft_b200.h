@@ -52,10 +52,9 @@ extern "C" {
 #define MDC_PRECISION_FP64     1   /* everything FP64 (reference arithmetic) */
 
 /* S(q) kernel selection for reciprocal-lattice plans in FP32 precision. */
-#define MDC_SQ_ALGO_AUTO       0
-#define MDC_SQ_ALGO_DIRECT     1   /* one sincos per (q, particle) term on the SFU */
-#define MDC_SQ_ALGO_POLY       2   /* same terms, sincos as FP32-pipe polynomial */
-#define MDC_SQ_ALGO_FACTORED   3   /* per-axis phasor tables + complex products (FP32 pipe) */
+#define MDC_SQ_ALGO_AUTO       0   /* FACTORED for the lattice part, DIRECT arithmetic for explicit wavevectors */
+#define MDC_SQ_ALGO_DIRECT     1   /* one fused sin/cos per (q, particle) term on the SFU (2 MUFU ops per term) */
+#define MDC_SQ_ALGO_FACTORED   3   /* per-axis unit-phasor tables + one complex FMA per term (4 FP32 FMAs per term) */
 
 typedef struct mdc_ctx      mdc_ctx;
 typedef struct mdc_sq_plan  mdc_sq_plan;

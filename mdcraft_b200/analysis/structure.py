@@ -25,9 +25,12 @@ Extra keyword arguments (all optional, defaults reproduce the reference):
 ``device`` (CUDA ordinal), ``frame_block`` (frames per upload), ``distributed``
 (all-reduce the accumulators across ``torch.distributed`` ranks in
 ``_conclude``; see :mod:`mdcraft_b200.distributed`) and, for S(q),
-``precision`` (``"fp32"``: exact integer/FP64 phases + SFU sin/cos + FP32 partial
-sums, within 1e-5 of the reference; ``"fp64"``: the reference's arithmetic,
-within 1e-10).
+``precision`` (``"fp32"``: exact integer phases, FP32 arithmetic, FP64 sums,
+within 1e-5 of the reference; ``"fp64"``: the reference's arithmetic, within
+1e-10) and ``algorithm`` (FP32 lattice grids only: ``"direct"`` evaluates one
+fused sin/cos per (wavevector, particle) term on the SFU, ``"factored"`` builds
+per-axis unit-phasor tables and spends one complex FMA per term; ``"auto"`` =
+factored).
 """
 
 from __future__ import annotations
@@ -529,6 +532,7 @@ class StructureFactor(NumbaAnalysisBase):
         parallel: bool = False,
         verbose: bool = True,
         precision: str = "fp32",
+        algorithm: str = "auto",
         device: int = 0,
         frame_block: int = 8,
         distributed: bool = False,
@@ -566,6 +570,8 @@ class StructureFactor(NumbaAnalysisBase):
             raise ValueError("Invalid form. Valid values: 'exp', 'trig'.")
         if precision not in _capi.PRECISIONS:
             raise ValueError("Invalid precision. Valid values: 'fp32', 'fp64'.")
+        if algorithm not in _capi.SQ_ALGOS:
+            raise ValueError("Invalid algorithm. Valid values: 'auto', 'direct', 'factored'.")
 
         # structure.py:1822-1887: the grid is fixed at construction from the current frame's box
         self._explicit = None
@@ -625,6 +631,7 @@ class StructureFactor(NumbaAnalysisBase):
         self._unique = unique
         self._verbose = verbose
         self._precision = precision
+        self._algorithm = algorithm
         self._device = int(device)
         self._frame_block = max(1, int(frame_block))
         self._distributed = bool(distributed)
@@ -645,7 +652,7 @@ class StructureFactor(NumbaAnalysisBase):
         explicit = self._explicit if self._explicit is not None and len(self._explicit) else None
         self._plan = _capi.SqPlan(
             _context(self._device), self._Ns, self._pairs(), n_points=n_points, L0=L0, q_max=self._q_max,
-            wavevectors=explicit, precision=self._precision,
+            wavevectors=explicit, precision=self._precision, algo=self._algorithm,
         )
         # the grid is built on the device; the host only needs it for |q| bookkeeping
         self._wavevectors = self._plan.wavevectors()

@@ -20,19 +20,15 @@
 #include "common.cuh"
 
 #include <float.h>
+#include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 using namespace mdc;
 
 namespace {
-
-constexpr int RDF_THREADS = 256;
-constexpr int RDF_IPT = 2;                       // i-particles per thread
-constexpr int RDF_TI = RDF_THREADS * RDF_IPT;    // i-tile
-constexpr int RDF_TJ = 512;                      // j-tile staged in shared memory
-constexpr int RDF_FLUSH_ITEMS = 4096;            // u32 privatised counters: 4096 * 512 * 512 < 2^31
 
 struct FrameBox {
     double box[3];
@@ -106,28 +102,96 @@ Thresholds make_thresholds(int B, double r0, double r1)
 // device
 // ------------------------------------------------------------------------------------------
 
-// raw f32 (F, N, 3) -> soa f32 (F, 3, N)
-__global__ void rdf_prep_soa(const float *__restrict__ raw, int64_t N, int64_t total, float *__restrict__ soa)
+// Per-frame constants of the filter kernel (written by rdf_frame_params).
+struct FrameFast {
+    float ax, ay, az;   // (float)(int32)(u_j - u_i) * a_k  =  separation along k in units of one bin width
+    float c0;           // v = |separation| + c0 = bin coordinate - 0.5   (c0 = -r0 * S - 0.5)
+    float thr;          // 0.5 - margin: a pair is decided in FP32 iff |v - rint(v)| <= thr
+    int cubic;          // ax == ay == az
+    int usable;         // 0: this frame must take the exact kernel's arithmetic for every pair
+    int pad;
+};
+
+// raw f32 (F, N, 3) -> soa f32 (F, 3, N); also fix u32 (F, 3, N) = frac(x / L) * 2^32 and the per-frame
+// max |coordinate| (float bits, atomicMax) that bounds the float32 subtraction error of the reference.
+__global__ void rdf_prep(const float *__restrict__ raw, int64_t N, int64_t total, const FrameBox *__restrict__ boxes,
+                         float *__restrict__ soa, uint32_t *__restrict__ fix, unsigned *__restrict__ absmax)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int64_t f = i / N, j = i - f * N;
+    float m = 0.f;
+    int64_t f = 0;
+    if (i < total) {
+        f = i / N;
+        const int64_t j = i - f * N;
+        const FrameBox fb = boxes[f];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) soa[(f * 3 + k) * N + j] = raw[3 * i + k];
+        for (int k = 0; k < 3; ++k) {
+            const float x = raw[3 * i + k];
+            soa[(f * 3 + k) * N + j] = x;
+            double s = fb.pbc[k] ? (double)x / fb.box[k] : 0.0;
+            s -= floor(s);
+            fix[(f * 3 + k) * N + j] = (uint32_t)(unsigned long long)(s * 4294967296.0 + 0.5);
+            m = fmaxf(m, fabsf(x));
+        }
+    }
+    // one atomic per warp (lanes of a warp may straddle two frames: fall back to per-lane atomics then)
+    const int64_t f0 = __shfl_sync(0xffffffffu, f, 0);
+    const bool same = __all_sync(0xffffffffu, (i >= total) || f == f0);
+    if (same) {
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&absmax[f0], __float_as_uint(m));
+    } else if (i < total && m > 0.f) {
+        atomicMax(&absmax[f], __float_as_uint(m));
+    }
+}
+
+// One thread per frame: turns the box, the plan's range and the coordinate bound into the filter's
+// constants.  The margin bounds |v_filter - v_reference| ("g(r) filter error budget"):
+//   reference vs true separation: float32 subtraction (<= 2^-24 * 2M per axis) and the (box * inv_box)
+//     factor (<= 2^-24 * 2M per axis), M = max |coordinate|;
+//   fixed point vs true separation: 2^-32 * L per axis;
+//   FP32 evaluation (I2F, squares, sum, MUFU.SQRT, FMA): <= 3.5e-7 relative + one ulp of v.
+__global__ void rdf_frame_params(const FrameBox *__restrict__ boxes, const unsigned *__restrict__ absmax_a,
+                                 const unsigned *__restrict__ absmax_b, int F, int n_bins, double r0, double r1,
+                                 FrameFast *__restrict__ out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const FrameBox fb = boxes[f];
+    const double S = (double)n_bins / (r1 - r0);
+    const double M = fmax((double)__uint_as_float(absmax_a[f]), (double)__uint_as_float(absmax_b[f]));
+    const double Lmax = fmax(fb.box[0], fmax(fb.box[1], fb.box[2]));
+    FrameFast p;
+    p.ax = (float)(fb.box[0] * S / 4294967296.0);
+    p.ay = (float)(fb.box[1] * S / 4294967296.0);
+    p.az = (float)(fb.box[2] * S / 4294967296.0);
+    p.c0 = (float)(-r0 * S - 0.5);
+    const double e_abs = 1.7320508 * (2.0 * M / 4194304.0 + Lmax / 2147483648.0);
+    const double vmax = (double)n_bins + 2.0 + fabs(r0 * S);
+    const double margin = 1.25 * (S * e_abs + 4.7e-7 * vmax) + 1e-6;
+    p.thr = (float)fmax(0.5 - margin, -1.0);
+    p.cubic = (p.ax == p.ay && p.ay == p.az) ? 1 : 0;
+    // the magic-number rounding below needs |v| < 2^22; all three axes must be periodic
+    const double v_far = 0.5 * sqrt(fb.box[0] * fb.box[0] + fb.box[1] * fb.box[1] + fb.box[2] * fb.box[2]) * S + fabs(r0 * S) + 1.0;
+    p.usable = (fb.pbc[0] && fb.pbc[1] && fb.pbc[2] && v_far < 4.0e6 && margin < 0.5) ? 1 : 0;
+    p.pad = 0;
+    out[f] = p;
 }
 
 struct RdfArgs {
-    const float *a, *b;       // SoA (F, 3, Na), (F, 3, Nb); b == a for a self-RDF
-    const FrameBox *boxes;    // (F)
-    const double *T;          // (B + 1)
+    const float *a, *b;        // SoA f32 (F, 3, Na), (F, 3, Nb); b == a for a self-RDF
+    const uint32_t *ua, *ub;   // SoA u32 fixed-point fractions, same shapes
+    const FrameBox *boxes;     // (F)
+    const FrameFast *fast;     // (F)
+    const double *T;           // (B + 1)
     unsigned long long *counts;
     double e_lo, e_hi;
-    float r0f, scalef;        // candidate bin = (sqrt(r2) - r0) * B / (r1 - r0) in FP32
+    float r0f, scalef;         // candidate bin = (sqrt(r2) - r0) * B / (r1 - r0) in FP32
     int64_t na, nb;
-    int64_t ex0, ex1;         // ex0 <= 0: no exclusion
+    int64_t ex0, ex1;          // ex0 <= 0: no exclusion
     int n_bins, n_copies;
-    int F, nti, ntj;          // tiles
-    int sym;                  // 1: self-RDF over unordered pairs (each counted twice)
+    int F, nti, ntj;           // tiles
+    int sym;                   // 1: self-RDF over unordered pairs (each counted twice)
     int64_t items_per_frame;
 };
 
@@ -144,6 +208,39 @@ __device__ __forceinline__ double min_image_sq(float dxf, double inv, double box
     return __dmul_rn(dx, dx);
 }
 
+// The reference's r^2 for one pair, bit for bit (calc_distances.h arithmetic, see file header).
+__device__ __forceinline__ double exact_r2(float xi, float yi, float zi, float xj, float yj, float zj,
+                                           const FrameBox &fb)
+{
+    double r2 = min_image_sq(xj - xi, fb.inv[0], fb.box[0], fb.pbc[0]);
+    r2 = __dadd_rn(r2, min_image_sq(yj - yi, fb.inv[1], fb.box[1], fb.pbc[1]));
+    r2 = __dadd_rn(r2, min_image_sq(zj - zi, fb.inv[2], fb.box[2], fb.pbc[2]));
+    return r2;
+}
+
+// Exact bin of an exact r^2 (-1: not counted), by comparison with the precomputed thresholds.
+__device__ __forceinline__ int exact_bin(double r2, const RdfArgs &A, const double *sT)
+{
+    if (!(r2 >= sT[0]) || !(r2 < A.e_hi)) return -1;
+    if (r2 < sT[A.n_bins]) {
+        const float d = sqrtf((float)r2);
+        int k = (int)((d - A.r0f) * A.scalef);
+        k = max(0, min(A.n_bins - 1, k));
+        while (r2 < sT[k]) --k;
+        while (r2 >= sT[k + 1]) ++k;
+        return k;
+    }
+    return (r2 >= A.e_lo) ? A.n_bins - 1 : -1;
+}
+
+// ---- exact kernel: FP64 for every pair (frames the filter cannot take: non-periodic axes, huge v) ----
+
+constexpr int RDF_THREADS = 256;
+constexpr int RDF_IPT = 2;                       // i-particles per thread
+constexpr int RDF_TI = RDF_THREADS * RDF_IPT;    // i-tile
+constexpr int RDF_TJ = 512;                      // j-tile staged in shared memory
+constexpr int RDF_FLUSH_ITEMS = 4096;            // u32 privatised counters: 4096 * 512 * 512 < 2^31
+
 template <bool CHECK>
 __device__ __forceinline__ void tile_pairs(const RdfArgs &A, const float4 *__restrict__ sj, int nj, int64_t j0,
                                            const float (&xi)[RDF_IPT], const float (&yi)[RDF_IPT],
@@ -151,36 +248,60 @@ __device__ __forceinline__ void tile_pairs(const RdfArgs &A, const float4 *__res
                                            const int64_t (&ig)[RDF_IPT], const FrameBox &fb, const double *sT,
                                            unsigned *hist, bool diag)
 {
-    const double T0 = sT[0], TB = sT[A.n_bins];
     for (int j = 0; j < nj; ++j) {
         const float4 pj = sj[j];
         const int bj = __float_as_int(pj.w);
 #pragma unroll
         for (int u = 0; u < RDF_IPT; ++u) {
-            double r2 = min_image_sq(pj.x - xi[u], fb.inv[0], fb.box[0], fb.pbc[0]);
-            r2 = __dadd_rn(r2, min_image_sq(pj.y - yi[u], fb.inv[1], fb.box[1], fb.pbc[1]));
-            r2 = __dadd_rn(r2, min_image_sq(pj.z - zi[u], fb.inv[2], fb.box[2], fb.pbc[2]));
-            bool ok = (r2 >= T0) && (r2 < A.e_hi) && (bi[u] != bj);
+            const double r2 = exact_r2(xi[u], yi[u], zi[u], pj.x, pj.y, pj.z, fb);
+            bool ok = bi[u] != bj;
             if (CHECK) ok = ok && (ig[u] < A.na) && (!diag || (j0 + j) > ig[u]);
             if (ok) {
-                int k;
-                if (r2 < TB) {
-                    const float d = sqrtf((float)r2);
-                    k = (int)((d - A.r0f) * A.scalef);
-                    k = max(0, min(A.n_bins - 1, k));
-                    while (r2 < sT[k]) --k;
-                    while (r2 >= sT[k + 1]) ++k;
-                } else {
-                    k = (r2 >= A.e_lo) ? A.n_bins - 1 : -1;
-                }
+                const int k = exact_bin(r2, A, sT);
                 if (k >= 0) atomicAdd(&hist[k], 1u);
             }
         }
     }
 }
 
+// decodes a work item into (frame, I, J); false if the item is a duplicate to skip
+__device__ __forceinline__ bool decode_item(const RdfArgs &A, int64_t item, int &f, int &I, int &J, bool &diag)
+{
+    f = (int)(item / A.items_per_frame);
+    const int64_t w = item - (int64_t)f * A.items_per_frame;
+    diag = false;
+    if (A.sym) {
+        // unordered tile pairs: J = (I + off) mod nt, off in [0, nt/2]; for even nt the
+        // off == nt/2 column would visit each pair twice, keep the lower half
+        const int nt = A.nti, half = nt / 2 + 1;
+        I = (int)(w / half);
+        const int off = (int)(w - (int64_t)I * half);
+        J = I + off;
+        if (J >= nt) J -= nt;
+        diag = off == 0;
+        if (((nt & 1) == 0) && (off == nt / 2) && (I >= nt / 2)) return false;
+    } else {
+        I = (int)(w / A.ntj);
+        J = (int)(w - (int64_t)I * A.ntj);
+    }
+    return true;
+}
+
+__device__ __forceinline__ void flush_hist(unsigned *sh, int B, int n_copies, unsigned long long weight,
+                                           unsigned long long *counts, bool clear)
+{
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        unsigned long long s = 0;
+        for (int c = 0; c < n_copies; ++c) {
+            s += sh[c * B + i];
+            if (clear) sh[c * B + i] = 0u;
+        }
+        if (s) atomicAdd(&counts[i], s * weight);
+    }
+}
+
 __global__ void __launch_bounds__(RDF_THREADS)
-rdf_pairs_kernel(RdfArgs A)
+rdf_pairs_exact(RdfArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sj = reinterpret_cast<float4 *>(smem_raw);
@@ -195,25 +316,9 @@ rdf_pairs_kernel(RdfArgs A)
     int since_flush = 0;
 
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
-        const int f = (int)(item / A.items_per_frame);
-        const int64_t w = item - (int64_t)f * A.items_per_frame;
-        int I, J;
-        bool diag = false, skip = false;
-        if (A.sym) {
-            // unordered tile pairs: J = (I + off) mod nt, off in [0, nt/2]; for even nt the
-            // off == nt/2 column would visit each pair twice, keep the lower half
-            const int nt = A.nti, half = nt / 2 + 1;
-            I = (int)(w / half);
-            const int off = (int)(w - (int64_t)I * half);
-            J = I + off;
-            if (J >= nt) J -= nt;
-            diag = off == 0;
-            skip = ((nt & 1) == 0) && (off == nt / 2) && (I >= nt / 2);
-        } else {
-            I = (int)(w / A.ntj);
-            J = (int)(w - (int64_t)I * A.ntj);
-        }
-        if (skip) continue;
+        int f, I, J;
+        bool diag;
+        if (!decode_item(A, item, f, I, J, diag)) continue;
         const FrameBox fb = A.boxes[f];
         const float *ax = A.a + ((int64_t)f * 3) * A.na, *ay = ax + A.na, *az = ay + A.na;
         const float *bx = A.b + ((int64_t)f * 3) * A.nb, *by = bx + A.nb, *bz = by + A.nb;
@@ -247,23 +352,177 @@ rdf_pairs_kernel(RdfArgs A)
 
         if (++since_flush >= RDF_FLUSH_ITEMS) {
             __syncthreads();
-            for (int i = threadIdx.x; i < B; i += RDF_THREADS) {
-                unsigned long long s = 0;
-                for (int c = 0; c < A.n_copies; ++c) {
-                    s += sh[c * B + i];
-                    sh[c * B + i] = 0u;
-                }
-                if (s) atomicAdd(&A.counts[i], s * weight);
-            }
+            flush_hist(sh, B, A.n_copies, weight, A.counts, true);
             since_flush = 0;
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < B; i += RDF_THREADS) {
-        unsigned long long s = 0;
-        for (int c = 0; c < A.n_copies; ++c) s += sh[c * B + i];
-        if (s) atomicAdd(&A.counts[i], s * weight);
+    flush_hist(sh, B, A.n_copies, weight, A.counts, false);
+}
+
+// ---- filter kernel: integer minimum image + FP32 bin proposal, FP64 only for undecided pairs ----
+//
+// Positions are 32-bit binary fractions of the box, so u_j - u_i wraps to the minimum image for
+// free.  The FP32 bin coordinate v differs from the reference's by at most `margin` (FrameFast);
+// a pair whose v is further than that from a bin edge is binned at once (shared-memory atomic),
+// the rest (~1e-3 of the pairs) are queued and resolved with the exact arithmetic after the tile,
+// so the counts are exactly those of the exact kernel.
+
+constexpr int RF_THREADS = 256;
+constexpr int RF_IPT = 4;
+constexpr int RF_TI = RF_THREADS * RF_IPT;   // 1024
+constexpr int RF_TJ = 1024;
+constexpr int RF_QCAP = 4096;                // undecided pairs per tile before falling back to in-line resolution
+constexpr int RF_FLUSH_ITEMS = 1024;         // 1024 * 1024 * 1024 pairs < 2^31
+constexpr float RF_MAGIC = 12582912.0f;      // 1.5 * 2^23: adding it rounds to the nearest integer
+constexpr int RF_MAGIC_BITS = 0x4B400000;
+
+struct FastShared {
+    uint4 sj[RF_TJ];            // {ux, uy, uz, exclusion block of j}
+    unsigned queue[RF_QCAP];    // i_local | j_local << 16
+    unsigned qcount;
+};
+
+// cold path, kept out of line so that the filter loop stays small enough for the instruction cache
+__device__ __noinline__ void resolve_exact(const RdfArgs &A, const FrameBox &fb, int f, int64_t ig, int64_t jg,
+                                           const double *sT, unsigned *hist)
+{
+    const float *ax = A.a + ((int64_t)f * 3) * A.na, *bx = A.b + ((int64_t)f * 3) * A.nb;
+    const double r2 = exact_r2(ax[ig], ax[A.na + ig], ax[2 * A.na + ig], bx[jg], bx[A.nb + jg], bx[2 * A.nb + jg], fb);
+    const int k = exact_bin(r2, A, sT);
+    if (k >= 0) atomicAdd(&hist[k], 1u);
+}
+
+// cold path of the filter loop: park an undecided pair for the post-tile FP64 pass
+__device__ __noinline__ void park_pair(FastShared *S, unsigned packed, const RdfArgs &A, const FrameBox &fb, int f,
+                                       int64_t ig, int64_t jg, const double *sT, unsigned *hist)
+{
+    const unsigned slot = atomicAdd(&S->qcount, 1u);
+    if (slot < RF_QCAP) S->queue[slot] = packed;
+    else resolve_exact(A, fb, f, ig, jg, sT, hist);   // queue full (pathological inputs): resolve in line
+}
+
+template <bool CHECK, bool CUBIC, bool EXCL>
+__device__ __forceinline__ void tile_pairs_fast(const RdfArgs &A, FastShared *S, int nj, int64_t i0, int64_t j0,
+                                                const uint32_t (&ux)[RF_IPT], const uint32_t (&uy)[RF_IPT],
+                                                const uint32_t (&uz)[RF_IPT], const int (&bi)[RF_IPT],
+                                                const FrameFast &ff, const FrameBox &fb, int f, const double *sT,
+                                                unsigned *hist, bool diag)
+{
+    const unsigned B = (unsigned)A.n_bins;
+    // frames whose margin is too wide for the filter (usable == 0) send every pair to the FP64 pass
+    const float thr = ff.usable ? ff.thr : -1.f;
+    const int k_lo = ff.usable ? -1 : INT_MIN, k_hi = ff.usable ? (int)B : INT_MAX;
+    const unsigned hist_addr = (unsigned)__cvta_generic_to_shared(hist);
+#pragma unroll 2
+    for (int j = 0; j < nj; ++j) {
+        const uint4 pj = S->sj[j];
+#pragma unroll
+        for (int u = 0; u < RF_IPT; ++u) {
+            const float tx = (float)(int)(pj.x - ux[u]);
+            const float ty = (float)(int)(pj.y - uy[u]);
+            const float tz = (float)(int)(pj.z - uz[u]);
+            float v, d;
+            if (CUBIC) {
+                const float t2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
+                v = fmaf(d, ff.ax, ff.c0);
+            } else {
+                const float ex = tx * ff.ax, ey = ty * ff.ay, ez = tz * ff.az;
+                const float t2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
+                v = d + ff.c0;
+            }
+            const float w = v + RF_MAGIC;
+            const int k = __float_as_int(w) - RF_MAGIC_BITS;     // rint(v): the bin, if v is clear of an edge
+            const bool clear = fabsf(v - (w - RF_MAGIC)) <= thr;
+            bool ok = true;
+            if (EXCL) ok = bi[u] != (int)pj.w;
+            if (CHECK) {
+                const int64_t ig = i0 + threadIdx.x + u * RF_THREADS;
+                ok = ok && (ig < A.na) && (!diag || (j0 + j) > ig);
+            }
+            if (ok && clear && (unsigned)k < B)
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + 4u * (unsigned)k) : "memory");
+            if (ok && !clear && k >= k_lo && k <= k_hi)
+                park_pair(S, (unsigned)(threadIdx.x + u * RF_THREADS) | ((unsigned)j << 16), A, fb, f,
+                          i0 + threadIdx.x + u * RF_THREADS, j0 + j, sT, hist);
+        }
     }
+}
+
+__global__ void __launch_bounds__(RF_THREADS)
+rdf_pairs_fast(RdfArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FastShared *S = reinterpret_cast<FastShared *>(smem_raw);
+    double *sT = reinterpret_cast<double *>(smem_raw + ((sizeof(FastShared) + 15) & ~size_t(15)));
+    unsigned *sh = reinterpret_cast<unsigned *>(sT + (A.n_bins + 1));
+    const int B = A.n_bins;
+    for (int i = threadIdx.x; i <= B; i += RF_THREADS) sT[i] = A.T[i];
+    for (int i = threadIdx.x; i < B * A.n_copies; i += RF_THREADS) sh[i] = 0u;
+    if (threadIdx.x == 0) S->qcount = 0u;
+    unsigned *hist = sh + ((threadIdx.x >> 5) & (A.n_copies - 1)) * B;
+    const unsigned long long weight = A.sym ? 2ull : 1ull;
+    const int64_t total = A.items_per_frame * A.F;
+    int since_flush = 0;
+
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        int f, I, J;
+        bool diag;
+        if (!decode_item(A, item, f, I, J, diag)) continue;
+        const FrameFast ff = A.fast[f];
+        const FrameBox fb = A.boxes[f];
+        const uint32_t *ax = A.ua + ((int64_t)f * 3) * A.na, *ay = ax + A.na, *az = ay + A.na;
+        const uint32_t *bx = A.ub + ((int64_t)f * 3) * A.nb, *by = bx + A.nb, *bz = by + A.nb;
+        const int64_t i0 = (int64_t)I * RF_TI, j0 = (int64_t)J * RF_TJ;
+
+        uint32_t ux[RF_IPT], uy[RF_IPT], uz[RF_IPT];
+        int bi[RF_IPT];
+#pragma unroll
+        for (int u = 0; u < RF_IPT; ++u) {
+            const int64_t ii = min(i0 + threadIdx.x + u * RF_THREADS, A.na - 1);
+            ux[u] = ax[ii];
+            uy[u] = ay[ii];
+            uz[u] = az[ii];
+            bi[u] = A.ex0 > 0 ? (int)(ii / A.ex0) : -1;
+        }
+        const int nj = (int)min((int64_t)RF_TJ, A.nb - j0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < nj; j += RF_THREADS) {
+            const int64_t jj = j0 + j;
+            const int bj = A.ex0 > 0 ? (int)(jj / A.ex1) : -2;
+            S->sj[j] = make_uint4(bx[jj], by[jj], bz[jj], (unsigned)bj);
+        }
+        __syncthreads();
+        const bool check = diag || (i0 + RF_TI > A.na);
+        const bool excl = A.ex0 > 0;
+#define RF_CALL(C, Q, E) tile_pairs_fast<C, Q, E>(A, S, nj, i0, j0, ux, uy, uz, bi, ff, fb, f, sT, hist, diag)
+        if (check) {
+            if (ff.cubic) { if (excl) RF_CALL(true, true, true); else RF_CALL(true, true, false); }
+            else          { if (excl) RF_CALL(true, false, true); else RF_CALL(true, false, false); }
+        } else {
+            if (ff.cubic) { if (excl) RF_CALL(false, true, true); else RF_CALL(false, true, false); }
+            else          { if (excl) RF_CALL(false, false, true); else RF_CALL(false, false, false); }
+        }
+#undef RF_CALL
+        // resolve the undecided pairs of this tile with the reference's FP64 arithmetic
+        __syncthreads();
+        const unsigned nq = min(S->qcount, (unsigned)RF_QCAP);
+        for (unsigned e = threadIdx.x; e < nq; e += RF_THREADS) {
+            const unsigned q = S->queue[e];
+            resolve_exact(A, fb, f, i0 + (q & 0xffffu), j0 + (q >> 16), sT, hist);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) S->qcount = 0u;
+
+        if (++since_flush >= RF_FLUSH_ITEMS) {
+            flush_hist(sh, B, A.n_copies, weight, A.counts, true);
+            since_flush = 0;
+        }
+    }
+    __syncthreads();
+    flush_hist(sh, B, A.n_copies, weight, A.counts, false);
 }
 
 __global__ void rdf_add_const(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
@@ -276,19 +535,24 @@ __global__ void rdf_add_const(unsigned long long *p, unsigned long long v) { ato
 
 struct mdc_rdf_plan {
     mdc_ctx *ctx = nullptr;
-    int n_bins = 0, n_copies = 1;
+    int n_bins = 0, n_copies = 1, n_copies_fast = 1;
     double r0 = 0, r1 = 0;
     int64_t na = 0, nb = 0, ex0 = 0, ex1 = 0;
     bool same = false, sym = false;
     int self_bin = -1;          // bin receiving the i == j pairs of a symmetric self-RDF (-1: none)
+    int force_exact = 0;        // testing / diagnostics: MDC_RDF_EXACT=1 in the environment
+    int occ_fast = 1, occ_exact = 1;   // resident blocks per SM (persistent grids)
     Thresholds th;
     DevBuf<double> T;
     DevBuf<unsigned long long> counts;
     DevBuf<float> raw_a[2], raw_b[2], soa_a[2], soa_b[2];
+    DevBuf<uint32_t> fix_a[2], fix_b[2];
+    DevBuf<unsigned> absmax[2];        // (2, F): group a, group b
     DevBuf<FrameBox> boxes[2];
+    DevBuf<FrameFast> fast[2];
     Streams st;
     int fblk = 0;
-    size_t smem = 0;
+    size_t smem = 0, smem_fast = 0;
     int64_t n_frames = 0;
     int last_launches = 0;
 };
@@ -307,7 +571,11 @@ void rdf_free(mdc_rdf_plan *p)
         p->raw_b[i].release();
         p->soa_a[i].release();
         p->soa_b[i].release();
+        p->fix_a[i].release();
+        p->fix_b[i].release();
+        p->absmax[i].release();
         p->boxes[i].release();
+        p->fast[i].release();
     }
     p->st.destroy();
     delete p;
@@ -322,11 +590,15 @@ int rdf_configure(mdc_rdf_plan *p, int n_frames_hint)
     for (int i = 0; i < 2; ++i) {
         MDC_CHECK(p->raw_a[i].alloc((size_t)fblk * p->na * 3));
         MDC_CHECK(p->soa_a[i].alloc((size_t)fblk * p->na * 3));
+        MDC_CHECK(p->fix_a[i].alloc((size_t)fblk * p->na * 3));
         if (!p->same) {
             MDC_CHECK(p->raw_b[i].alloc((size_t)fblk * p->nb * 3));
             MDC_CHECK(p->soa_b[i].alloc((size_t)fblk * p->nb * 3));
+            MDC_CHECK(p->fix_b[i].alloc((size_t)fblk * p->nb * 3));
         }
+        MDC_CHECK(p->absmax[i].alloc((size_t)2 * fblk));
         MDC_CHECK(p->boxes[i].alloc(fblk));
+        MDC_CHECK(p->fast[i].alloc(fblk));
     }
     return MDC_OK;
 }
@@ -395,6 +667,13 @@ extern "C" int mdc_rdf_plan_create(mdc_ctx *ctx, int n_bins, double r0, double r
     }
     p->n_copies = copies;
     p->smem = fixed + (size_t)copies * n_bins * 4;
+    const size_t fixed_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + sizeof(double) * (n_bins + 1);
+    int copies_fast = RF_THREADS / 32;
+    while (copies_fast > 1 && fixed_fast + (size_t)copies_fast * n_bins * 4 > budget) copies_fast >>= 1;
+    p->n_copies_fast = copies_fast;
+    p->smem_fast = fixed_fast + (size_t)copies_fast * n_bins * 4;   // > budget: the filter kernel is not used
+    const char *env = getenv("MDC_RDF_EXACT");
+    p->force_exact = (env && env[0] == '1') || p->smem_fast > budget;
 
     int rc = p->st.init(ctx);
     if (rc == MDC_OK) rc = p->T.alloc(n_bins + 1);
@@ -406,11 +685,19 @@ extern "C" int mdc_rdf_plan_create(mdc_ctx *ctx, int n_bins, double r0, double r
     cudaError_t e = cudaMemcpy(p->T.p, p->th.T.data(), (n_bins + 1) * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(p->counts.p, 0, n_bins * sizeof(unsigned long long));
     if (e == cudaSuccess && p->smem > 48 * 1024)
-        e = cudaFuncSetAttribute(rdf_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+        e = cudaFuncSetAttribute(rdf_pairs_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e == cudaSuccess && !p->force_exact && p->smem_fast > 48 * 1024)
+        e = cudaFuncSetAttribute(rdf_pairs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fast);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->occ_exact, rdf_pairs_exact, RDF_THREADS, p->smem);
+    if (e == cudaSuccess && !p->force_exact)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->occ_fast, rdf_pairs_fast, RF_THREADS, p->smem_fast);
     if (e != cudaSuccess) {
         rdf_free(p);
         return fail(MDC_ERR_CUDA, std::string("mdc_rdf_plan_create: ") + cudaGetErrorString(e));
     }
+    p->occ_exact = std::max(1, p->occ_exact);
+    p->occ_fast = std::max(1, p->occ_fast);
     *out = p;
     return MDC_OK;
 }
@@ -450,19 +737,39 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
             }
         }
         MDC_CUDA(cudaMemcpyAsync(p->boxes[slot].p, hb.data() + f0, F * sizeof(FrameBox), cudaMemcpyHostToDevice, sc));
-        rdf_prep_soa<<<(unsigned)ceil_div((int64_t)F * p->na, 256), 256, 0, sc>>>(ra, p->na, (int64_t)F * p->na, p->soa_a[slot].p);
+        MDC_CUDA(cudaMemsetAsync(p->absmax[slot].p, 0, 2 * (size_t)p->fblk * sizeof(unsigned), sc));
+        rdf_prep<<<(unsigned)ceil_div((int64_t)F * p->na, 256), 256, 0, sc>>>(
+            ra, p->na, (int64_t)F * p->na, p->boxes[slot].p, p->soa_a[slot].p, p->fix_a[slot].p, p->absmax[slot].p);
         ++launches;
         if (rb) {
-            rdf_prep_soa<<<(unsigned)ceil_div((int64_t)F * p->nb, 256), 256, 0, sc>>>(rb, p->nb, (int64_t)F * p->nb, p->soa_b[slot].p);
+            rdf_prep<<<(unsigned)ceil_div((int64_t)F * p->nb, 256), 256, 0, sc>>>(
+                rb, p->nb, (int64_t)F * p->nb, p->boxes[slot].p, p->soa_b[slot].p, p->fix_b[slot].p,
+                p->absmax[slot].p + p->fblk);
             ++launches;
         }
+        rdf_frame_params<<<(unsigned)ceil_div(F, 64), 64, 0, sc>>>(
+            p->boxes[slot].p, p->absmax[slot].p, p->absmax[slot].p + (rb ? p->fblk : 0), F, p->n_bins, p->r0, p->r1,
+            p->fast[slot].p);
+        ++launches;
         MDC_CUDA(cudaGetLastError());
         MDC_CUDA(cudaEventRecord(p->st.staged[slot], sc));
         MDC_CUDA(cudaStreamWaitEvent(sk, p->st.staged[slot], 0));
+        // the filter kernel needs three periodic axes and a bin coordinate below 2^22 in every frame
+        bool fast = !p->force_exact;
+        for (int f = 0; f < F && fast; ++f) {
+            const FrameBox &fb = hb[f0 + f];
+            const double S = (double)p->n_bins / (p->r1 - p->r0);
+            const double v_far = 0.5 * sqrt(fb.box[0] * fb.box[0] + fb.box[1] * fb.box[1] + fb.box[2] * fb.box[2]) * S +
+                                 fabs(p->r0 * S) + 1.0;
+            fast = fb.pbc[0] && fb.pbc[1] && fb.pbc[2] && v_far < 4.0e6;
+        }
         RdfArgs A;
         A.a = p->soa_a[slot].p;
         A.b = p->same ? p->soa_a[slot].p : p->soa_b[slot].p;
+        A.ua = p->fix_a[slot].p;
+        A.ub = p->same ? p->fix_a[slot].p : p->fix_b[slot].p;
         A.boxes = p->boxes[slot].p;
+        A.fast = p->fast[slot].p;
         A.T = p->T.p;
         A.counts = p->counts.p;
         A.e_lo = p->th.e_lo;
@@ -474,17 +781,22 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         A.ex0 = p->ex0;
         A.ex1 = p->ex1;
         A.n_bins = p->n_bins;
-        A.n_copies = p->n_copies;
+        A.n_copies = fast ? p->n_copies_fast : p->n_copies;
         A.F = F;
-        A.nti = (int)ceil_div(p->na, RDF_TI);
-        A.ntj = (int)ceil_div(p->nb, RDF_TJ);
+        A.nti = (int)ceil_div(p->na, fast ? RF_TI : RDF_TI);
+        A.ntj = (int)ceil_div(p->nb, fast ? RF_TJ : RDF_TJ);
         A.sym = p->sym ? 1 : 0;
         A.items_per_frame = p->sym ? (int64_t)A.nti * (A.nti / 2 + 1) : (int64_t)A.nti * A.ntj;
         const int64_t total = A.items_per_frame * F;
-        const int grid = (int)std::min<int64_t>(total, (int64_t)p->ctx->sm_count * 8);
         const int ti = p->st.n_timed < 8 ? p->st.n_timed : -1;
         if (ti >= 0) MDC_CUDA(cudaEventRecord(p->st.k0[ti], sk));
-        rdf_pairs_kernel<<<grid, RDF_THREADS, p->smem, sk>>>(A);
+        if (fast) {
+            const int grid = (int)std::min<int64_t>(total, (int64_t)p->ctx->sm_count * p->occ_fast);
+            rdf_pairs_fast<<<grid, RF_THREADS, p->smem_fast, sk>>>(A);
+        } else {
+            const int grid = (int)std::min<int64_t>(total, (int64_t)p->ctx->sm_count * p->occ_exact);
+            rdf_pairs_exact<<<grid, RDF_THREADS, p->smem, sk>>>(A);
+        }
         ++launches;
         if (ti >= 0) {
             MDC_CUDA(cudaEventRecord(p->st.k1[ti], sk));

@@ -29,7 +29,7 @@ namespace {
 
 constexpr int SQ_Q = 8;          // consecutive c (z index) values per thread in the lattice kernel
 constexpr int SQ_THREADS = 128;
-constexpr int SQ_TILE = 512;     // particles staged in shared memory per inner pass (FP32 partial-sum run)
+constexpr int SQ_TILE = 256;     // particles staged in shared memory per inner pass (one exact integer partial sum)
 constexpr double TWO_PI = 6.283185307179586;  // == 2 * np.pi
 
 // ------------------------------------------------------------------------------------------
@@ -176,9 +176,13 @@ sq_lattice_direct(const uint4 *__restrict__ items, int64_t n_items, const uint32
             sm[i] = make_uint4(fx[t0 + i], fy[t0 + i], fz[t0 + i], 0u);
         __syncthreads();
 
-        float re[SQ_Q], im[SQ_Q];
+        // Partial sums are accumulated EXACTLY: adding 3.0f snaps a term in [-1, 1] onto the 2^-22 grid of
+        // the binade [2, 4] (one rounding, +-2^-23, unbiased), after which the float's bit pattern is an
+        // integer count of grid steps that an integer add accumulates without error.  A plain FP32 running
+        // sum would lose ~eps * |partial sum| per add, which for N = 1e5 exceeds the SFU's own error.
+        int re[SQ_Q], im[SQ_Q];
 #pragma unroll
-        for (int k = 0; k < SQ_Q; ++k) re[k] = im[k] = 0.f;
+        for (int k = 0; k < SQ_Q; ++k) re[k] = im[k] = 0;
 #pragma unroll 2
         for (int j = 0; j < n; ++j) {
             const uint4 r = sm[j];
@@ -187,15 +191,15 @@ sq_lattice_direct(const uint4 *__restrict__ items, int64_t n_items, const uint32
             for (int k = 0; k < SQ_Q; ++k) {
                 float sn, cs;
                 sincos_phase(ph, sn, cs);
-                re[k] += cs;
-                im[k] += sn;
+                re[k] += __float_as_int(cs + 3.0f) - 0x40400000;
+                im[k] += __float_as_int(sn + 3.0f) - 0x40400000;
                 ph += r.z;
             }
         }
 #pragma unroll
         for (int k = 0; k < SQ_Q; ++k) {
-            dre[k] += (double)re[k];
-            dim[k] += (double)im[k];
+            dre[k] += (double)re[k] * (1.0 / 4194304.0);
+            dim[k] += (double)im[k] * (1.0 / 4194304.0);
         }
     }
     if (valid) {
@@ -238,18 +242,18 @@ sq_explicit_f32(const double *__restrict__ q, int64_t q_first, int64_t n_q, cons
             sz[i] = pz[t0 + i];
         }
         __syncthreads();
-        float re = 0.f, im = 0.f;
+        int re = 0, im = 0;   // exact integer partial sums on the 2^-22 grid (see sq_lattice_direct)
 #pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const double t = fma(qz, sz[j], fma(qy, sy[j], qx * sx[j]));   // turns
             const uint32_t ph = (uint32_t)__double2loint(t + 1572864.0);    // frac(t) * 2^32
             float sn, cs;
             sincos_phase(ph, sn, cs);
-            re += cs;
-            im += sn;
+            re += __float_as_int(cs + 3.0f) - 0x40400000;
+            im += __float_as_int(sn + 3.0f) - 0x40400000;
         }
-        dre += (double)re;
-        dim += (double)im;
+        dre += (double)re * (1.0 / 4194304.0);
+        dim += (double)im * (1.0 / 4194304.0);
     }
     if (valid) part[((int64_t)blockIdx.z * P + p) * nq + qi] = make_double2(dre, dim);
 }
@@ -294,16 +298,176 @@ sq_explicit_f64(const double *__restrict__ q, int64_t q_first, int64_t n_q, cons
     if (valid) part[((int64_t)blockIdx.z * P + p) * nq + qi] = make_double2(dre, dim);
 }
 
+// ------------------------------------------------------------------------------------------
+// FACTORED, reciprocal lattice, FP32 pipe.  On the lattice
+//     exp(i q.r) = X_j[a] * Y_j[b] * Z_j[c],     X_j[a] = exp(2 pi i a s_xj)  etc.,
+// so a block that owns a patch of 32 a x 16 b x 8 c wavevectors needs only 56 unit phasors per particle
+// for its 4096 terms.  The phasor tables are built once per frame from the exact integer phase with an
+// FP64 sincospi (rounded once to FP32, no SFU error), streamed through shared memory, and every term is
+// one complex multiply-accumulate = two packed fma.rn.f32x2:
+//     acc(re, im) += (zr, zr) * (wr, wi) + (-zi, zi) * (wi, wr),       W = X[a] * Y[b].
+// FP32 running sums are folded into FP64 every FC_RUN particles, so the accumulation error stays below
+// the rounding of the terms themselves.  Cost: 4 FP32 FMAs per term instead of 2 SFU ops.
+// ------------------------------------------------------------------------------------------
+
+constexpr int FC_PA = 32, FC_PB = 16, FC_CQ = 8;   // patch: a x b x c wavevector indices per block
+constexpr int FC_THREADS = (FC_PA / 2) * FC_PB;    // thread = 2 adjacent a, 1 b, FC_CQ c
+constexpr int FC_T = 32;                           // particles per shared-memory tile
+constexpr int FC_RUN = 8;                          // particles per FP32 run before folding into FP64
+constexpr int FC_ROW = FC_PA * 8 + FC_PB * 8 + FC_CQ * 16;   // bytes of one particle's phasors in a tile (512)
+
+// tables: X float2 (F*N, nxp), Y float2 (F*N, nyp), Z float4 {zr, zr, -zi, zi} (F*N, nzp)
+__global__ void sq_prep_tables(const uint32_t *__restrict__ fix, int64_t N, int64_t total, int n_points, int nxp,
+                               int nyp, int nzp, float2 *__restrict__ tx, float2 *__restrict__ ty,
+                               float4 *__restrict__ tz)
+{
+    const int64_t pj = blockIdx.x;   // frame * N + particle
+    if (pj >= total) return;
+    const int64_t f = pj / N, j = pj - f * N;
+    const uint32_t s[3] = {fix[(f * 3 + 0) * N + j], fix[(f * 3 + 1) * N + j], fix[(f * 3 + 2) * N + j]};
+    const int n_all = nxp + nyp + nzp;
+    for (int e = threadIdx.x; e < n_all; e += blockDim.x) {
+        int axis, idx;
+        if (e < nxp) { axis = 0; idx = e; }
+        else if (e < nxp + nyp) { axis = 1; idx = e - nxp; }
+        else { axis = 2; idx = e - nxp - nyp; }
+        float re = 0.f, im = 0.f;
+        if (idx < n_points) {
+            const uint32_t ph = (uint32_t)idx * s[axis];          // exact phase, in 2^-32 turns
+            double sn, cs;
+            sincospi((double)ph * (2.0 / 4294967296.0), &sn, &cs);
+            re = (float)cs;
+            im = (float)sn;
+        }
+        if (axis == 0) tx[pj * nxp + idx] = make_float2(re, im);
+        else if (axis == 1) ty[pj * nyp + idx] = make_float2(re, im);
+        else tz[pj * nzp + idx] = make_float4(re, re, -im, im);
+    }
+}
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+
+__device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long a, unsigned long long b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+__global__ void __launch_bounds__(FC_THREADS, 2)
+sq_lattice_factored(const uint4 *__restrict__ patches, const float2 *__restrict__ tabx,
+                    const float2 *__restrict__ taby, const float4 *__restrict__ tabz, int nxp, int nyp, int nzp,
+                    int64_t N, const int2 *__restrict__ sets, int n_sets, int P, int n_points,
+                    const int *__restrict__ row_cnt, const int64_t *__restrict__ row_qoff, int64_t nq,
+                    double2 *__restrict__ part)
+{
+    __shared__ __align__(16) unsigned char tile[FC_T * FC_ROW];
+    const uint4 patch = patches[blockIdx.x];
+    const int a0 = (int)patch.x, b0 = (int)patch.y, c0 = (int)patch.z;
+    const int p = blockIdx.y;
+    const int f = blockIdx.z / n_sets, s = blockIdx.z - f * n_sets;
+    const Chunk ch = chunk_range(sets[s], p, P);
+    const int tx = threadIdx.x & (FC_PA / 2 - 1), ty = threadIdx.x / (FC_PA / 2);
+
+    // tile loader: 16-byte pieces; a particle's 512-byte row = 16 X pieces, 8 Y pieces, 8 Z pieces
+    constexpr int PIECES = FC_T * FC_ROW / 16 / FC_THREADS;   // per thread
+    uint4 stage[PIECES];
+    auto fetch = [&](int64_t t0) {
+#pragma unroll
+        for (int r = 0; r < PIECES; ++r) {
+            const int piece = threadIdx.x + r * FC_THREADS;
+            const int jj = piece >> 5, w = piece & 31;
+            const int64_t j = t0 + jj;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (j < ch.hi) {
+                const int64_t pj = (int64_t)f * N + j;
+                if (w < 16) v = *reinterpret_cast<const uint4 *>(tabx + pj * nxp + a0 + 2 * w);
+                else if (w < 24) v = *reinterpret_cast<const uint4 *>(taby + pj * nyp + b0 + 2 * (w - 16));
+                else v = *reinterpret_cast<const uint4 *>(tabz + pj * nzp + c0 + (w - 24));
+            }
+            stage[r] = v;
+        }
+    };
+    auto commit = [&]() {
+#pragma unroll
+        for (int r = 0; r < PIECES; ++r)
+            *reinterpret_cast<uint4 *>(tile + (size_t)(threadIdx.x + r * FC_THREADS) * 16) = stage[r];
+    };
+
+    double dre[2][FC_CQ], dim[2][FC_CQ];
+#pragma unroll
+    for (int c = 0; c < FC_CQ; ++c) dre[0][c] = dre[1][c] = dim[0][c] = dim[1][c] = 0.0;
+
+    if (ch.lo < ch.hi) fetch(ch.lo);
+    for (int64_t t0 = ch.lo; t0 < ch.hi; t0 += FC_T) {
+        __syncthreads();
+        commit();
+        __syncthreads();
+        if (t0 + FC_T < ch.hi) fetch(t0 + FC_T);   // next tile's loads fly during this tile's math
+#pragma unroll 1
+        for (int r0 = 0; r0 < FC_T; r0 += FC_RUN) {
+            unsigned long long acc[2][FC_CQ];
+#pragma unroll
+            for (int c = 0; c < FC_CQ; ++c) acc[0][c] = acc[1][c] = 0ull;
+#pragma unroll
+            for (int jj = r0; jj < r0 + FC_RUN; ++jj) {
+                const unsigned char *row = tile + jj * FC_ROW;
+                const float4 x = *reinterpret_cast<const float4 *>(row + tx * 16);
+                const float2 y = *reinterpret_cast<const float2 *>(row + FC_PA * 8 + ty * 8);
+                const float w0r = fmaf(-x.y, y.y, x.x * y.x), w0i = fmaf(x.y, y.x, x.x * y.y);
+                const float w1r = fmaf(-x.w, y.y, x.z * y.x), w1i = fmaf(x.w, y.x, x.z * y.y);
+                const unsigned long long wd0 = pack2(w0r, w0i), ws0 = pack2(w0i, w0r);
+                const unsigned long long wd1 = pack2(w1r, w1i), ws1 = pack2(w1i, w1r);
+#pragma unroll
+                for (int c = 0; c < FC_CQ; ++c) {
+                    const ulonglong2 z = *reinterpret_cast<const ulonglong2 *>(row + FC_PA * 8 + FC_PB * 8 + c * 16);
+                    fma2(acc[0][c], z.x, wd0);
+                    fma2(acc[1][c], z.x, wd1);
+                    fma2(acc[0][c], z.y, ws0);
+                    fma2(acc[1][c], z.y, ws1);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < FC_CQ; ++c) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float lo, hi;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[h][c]));
+                    dre[h][c] += (double)lo;
+                    dim[h][c] += (double)hi;
+                }
+            }
+        }
+    }
+    const int b = b0 + ty;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int a = a0 + 2 * tx + h;
+        if (a < n_points && b < n_points) {
+            const int row = b * n_points + a;
+            const int cnt = row_cnt[row];
+            double2 *out = part + ((int64_t)blockIdx.z * P + p) * nq + row_qoff[row];
+#pragma unroll
+            for (int c = 0; c < FC_CQ; ++c)
+                if (c0 + c < cnt) out[c0 + c] = make_double2(dre[h][c], dim[h][c]);
+        }
+    }
+}
+
 // rho[f, s, q] = sum_p part[f, s, p, q] (fixed order) - N_s * dc ;  ssf[pair, q] += products over frames.
 // dc = (mean cos error, mean sin error) of the SFU pipeline over all phases: the zeroth Fourier
 // coefficient of its error function is the only part a sum over N particles multiplies by N, so it is
 // measured once per plan (probe_sincos_kernel) and removed analytically.  Zero in FP64 mode.
 __global__ void sq_pair_accum(double2 *__restrict__ part, int F, int n_sets, int P, int64_t nq,
                               const int2 *__restrict__ sets, const int2 *__restrict__ pairs, int n_pairs,
-                              double dc_cos, double dc_sin, double *__restrict__ ssf)
+                              double dc_cos, double dc_sin, int64_t dc_first, double *__restrict__ ssf)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
+    if (q < dc_first) dc_cos = dc_sin = 0.0;   // wavevectors evaluated without the SFU
     for (int fs = 0; fs < F * n_sets; ++fs) {
         double2 *base = part + (int64_t)fs * P * nq + q;
         double re = 0.0, im = 0.0;
@@ -413,10 +577,17 @@ struct mdc_sq_plan {
     int64_t N = 0;
     int n_sets = 0, n_pairs = 0;
     int precision = 0, algo = 0;
-    bool lattice_fast = false;   // lattice part runs through sq_lattice_direct
+    bool lattice_fast = false;   // lattice part runs through an FP32 lattice kernel (direct or factored)
+    bool factored = false;       // ... the factored one
     double dc[2] = {0, 0};
     DevBuf<double> q, ssf, posd[2];
-    DevBuf<uint4> items;
+    DevBuf<uint4> items, patches;
+    DevBuf<int> row_cnt;
+    DevBuf<int64_t> row_qoff;
+    DevBuf<float2> tabx[2], taby[2];
+    DevBuf<float4> tabz[2];
+    int64_t n_patches = 0;
+    int nxp = 0, nyp = 0, nzp = 0;
     DevBuf<double2> part;
     DevBuf<float> raw[2];
     DevBuf<uint32_t> fix[2];
@@ -439,6 +610,9 @@ void plan_free(mdc_sq_plan *p)
     p->q.release();
     p->ssf.release();
     p->items.release();
+    p->patches.release();
+    p->row_cnt.release();
+    p->row_qoff.release();
     p->part.release();
     p->d_sets.release();
     p->d_pairs.release();
@@ -446,6 +620,9 @@ void plan_free(mdc_sq_plan *p)
         p->posd[i].release();
         p->raw[i].release();
         p->fix[i].release();
+        p->tabx[i].release();
+        p->taby[i].release();
+        p->tabz[i].release();
     }
     p->st.destroy();
     delete p;
@@ -470,15 +647,15 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
     if (n_pairs < 1 || !pairs) return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: need at least one pair");
     if (precision != MDC_PRECISION_FP32 && precision != MDC_PRECISION_FP64)
         return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: unknown precision");
-    if (algo != MDC_SQ_ALGO_AUTO && algo != MDC_SQ_ALGO_DIRECT)
-        return fail(MDC_ERR_UNSUPPORTED, "mdc_sq_plan_create: only the DIRECT algorithm is implemented");
+    if (algo != MDC_SQ_ALGO_AUTO && algo != MDC_SQ_ALGO_DIRECT && algo != MDC_SQ_ALGO_FACTORED)
+        return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: unknown algorithm");
     MDC_CUDA(cudaSetDevice(ctx->device));
 
     mdc_sq_plan *p = new mdc_sq_plan();
     p->ctx = ctx;
     p->n_points = n_points;
     p->precision = precision;
-    p->algo = MDC_SQ_ALGO_DIRECT;
+    p->algo = algo;
     p->n_exp = n_explicit;
     if (n_points > 0) memcpy(p->L0, L0, sizeof(p->L0));
 
@@ -543,13 +720,13 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
     // grid build, pass 1: kept wavevectors per (a, b) row on the device; prefix sums over the
     // n^2 rows on the host (nothing of size Nq crosses the bus)
     const int rows = n_points * n_points;
-    DevBuf<int> cnt;
+    DevBuf<int> &cnt = p->row_cnt;
     std::vector<int64_t> hq(rows), hi(rows);
+    std::vector<int> h(rows);
     if (n_points > 0) {
         PLAN_TRY(cnt.alloc(rows));
         lat_row_counts<<<(rows + 255) / 256, 256>>>(n_points, p->L0[0], p->L0[1], p->L0[2], q_max, cnt.p);
         PLAN_CUDA(cudaGetLastError());
-        std::vector<int> h(rows);
         PLAN_CUDA(cudaMemcpy(h.data(), cnt.p, rows * sizeof(int), cudaMemcpyDeviceToHost));
         for (int r = 0; r < rows; ++r) {
             hq[r] = p->n_lat;
@@ -560,11 +737,11 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
     }
     p->nq = p->n_lat + p->n_exp;
     if (p->nq == 0) {
-        cnt.release();
         plan_free(p);
         return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: q_max removes every wavevector");
     }
     p->lattice_fast = (precision == MDC_PRECISION_FP32) && p->n_lat > 0;
+    p->factored = p->lattice_fast && algo != MDC_SQ_ALGO_DIRECT;
 
     PLAN_TRY(p->q.alloc((size_t)p->nq * 3));
     PLAN_TRY(p->ssf.alloc((size_t)p->nq * n_pairs));
@@ -576,7 +753,8 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
 
     if (p->n_lat > 0) {
         // pass 2: wavevectors (reference FP64 operation order) and the lattice kernel's work items
-        DevBuf<int64_t> qo, io;
+        DevBuf<int64_t> &qo = p->row_qoff;
+        DevBuf<int64_t> io;
         PLAN_TRY(qo.alloc(rows));
         PLAN_TRY(io.alloc(rows));
         PLAN_CUDA(cudaMemcpy(qo.p, hq.data(), rows * sizeof(int64_t), cudaMemcpyHostToDevice));
@@ -586,10 +764,31 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
                                               p->items.p);
         PLAN_CUDA(cudaGetLastError());
         PLAN_CUDA(cudaDeviceSynchronize());
-        qo.release();
         io.release();
+        if (!p->factored) {
+            cnt.release();
+            qo.release();
+        } else {
+            // patches of FC_PA x FC_PB x FC_CQ wavevector indices that contain at least one kept wavevector
+            p->items.release();
+            const int n = n_points;
+            std::vector<uint4> hp;
+            for (int c0 = 0; c0 < n; c0 += FC_CQ)
+                for (int b0 = 0; b0 < n; b0 += FC_PB)
+                    for (int a0 = 0; a0 < n; a0 += FC_PA) {
+                        bool any = false;
+                        for (int b = b0; b < std::min(n, b0 + FC_PB) && !any; ++b)
+                            for (int a = a0; a < std::min(n, a0 + FC_PA) && !any; ++a) any = h[b * n + a] > c0;
+                        if (any) hp.push_back(make_uint4((unsigned)a0, (unsigned)b0, (unsigned)c0, 0u));
+                    }
+            p->n_patches = (int64_t)hp.size();
+            PLAN_TRY(p->patches.alloc(hp.size()));
+            PLAN_CUDA(cudaMemcpy(p->patches.p, hp.data(), hp.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+            p->nxp = (int)ceil_div(n, FC_PA) * FC_PA;
+            p->nyp = (int)ceil_div(n, FC_PB) * FC_PB;
+            p->nzp = (int)ceil_div(n, FC_CQ) * FC_CQ;
+        }
     }
-    cnt.release();
     if (p->n_exp > 0)
         PLAN_CUDA(cudaMemcpy(p->q.p + 3 * p->n_lat, q_explicit, (size_t)p->n_exp * 3 * sizeof(double),
                              cudaMemcpyHostToDevice));
@@ -633,9 +832,13 @@ int configure(mdc_sq_plan *p, int n_frames_hint)
     const int64_t per_frame_min = (int64_t)p->n_sets * p->nq * sizeof(double2);
     if (per_frame_min > budget * 8)
         return fail(MDC_ERR_NOMEM, "mdc_sq_push: wavevector grid too large for the partial-density buffer");
-    const int64_t blocks_q = ceil_div(p->lattice_fast ? p->n_items : 0, SQ_THREADS) +
+    const int64_t blocks_q = (p->factored ? p->n_patches : ceil_div(p->lattice_fast ? p->n_items : 0, SQ_THREADS)) +
                              ceil_div(p->lattice_fast ? p->n_exp : p->nq, SQ_THREADS);
     int fblk = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_frames_hint, 32), budget / per_frame_min));
+    if (p->factored) {
+        const int64_t tab_frame = p->N * ((int64_t)p->nxp * 8 + (int64_t)p->nyp * 8 + (int64_t)p->nzp * 16);
+        fblk = (int)std::max<int64_t>(1, std::min<int64_t>(fblk, ((int64_t)3 << 30) / tab_frame));
+    }
     const int64_t want = (int64_t)p->ctx->sm_count * 32;
     int64_t min_len = p->N;
     for (auto &s : p->sets) min_len = std::min<int64_t>(min_len, std::max(1, s.y - s.x));
@@ -649,6 +852,11 @@ int configure(mdc_sq_plan *p, int n_frames_hint)
     for (int i = 0; i < 2; ++i) {
         MDC_CHECK(p->raw[i].alloc((size_t)fblk * p->N * 3));
         if (p->lattice_fast) MDC_CHECK(p->fix[i].alloc((size_t)fblk * p->N * 3));
+        if (p->factored) {
+            MDC_CHECK(p->tabx[i].alloc((size_t)fblk * p->N * p->nxp));
+            MDC_CHECK(p->taby[i].alloc((size_t)fblk * p->N * p->nyp));
+            MDC_CHECK(p->tabz[i].alloc((size_t)fblk * p->N * p->nzp));
+        }
         if (!p->lattice_fast || p->n_exp > 0) MDC_CHECK(p->posd[i].alloc((size_t)fblk * p->N * 3));
     }
     return MDC_OK;
@@ -663,6 +871,11 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
         prep_fix<<<pb, 256, 0, sc>>>(raw, p->N, total, 1.0 / p->L0[0], 1.0 / p->L0[1], 1.0 / p->L0[2], p->fix[slot].p);
         ++*launches;
     }
+    if (p->factored) {
+        sq_prep_tables<<<(unsigned)total, 128, 0, sc>>>(p->fix[slot].p, p->N, total, p->n_points, p->nxp, p->nyp,
+                                                       p->nzp, p->tabx[slot].p, p->taby[slot].p, p->tabz[slot].p);
+        ++*launches;
+    }
     if (!p->lattice_fast || p->n_exp > 0) {
         prep_f64<<<pb, 256, 0, sc>>>(raw, p->N, total, p->posd[slot].p);
         ++*launches;
@@ -674,9 +887,17 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
     if (ti >= 0) MDC_CUDA(cudaEventRecord(p->st.k0[ti], sk));
     const unsigned gz = (unsigned)(F * p->n_sets);
     if (p->lattice_fast) {
-        dim3 g((unsigned)ceil_div(p->n_items, SQ_THREADS), (unsigned)p->P, gz);
-        sq_lattice_direct<<<g, SQ_THREADS, 0, sk>>>(p->items.p, p->n_items, p->fix[slot].p, p->N, p->d_sets.p,
-                                                   p->n_sets, p->P, p->nq, p->part.p);
+        if (p->factored) {
+            dim3 g((unsigned)p->n_patches, (unsigned)p->P, gz);
+            sq_lattice_factored<<<g, FC_THREADS, 0, sk>>>(p->patches.p, p->tabx[slot].p, p->taby[slot].p,
+                                                         p->tabz[slot].p, p->nxp, p->nyp, p->nzp, p->N, p->d_sets.p,
+                                                         p->n_sets, p->P, p->n_points, p->row_cnt.p, p->row_qoff.p,
+                                                         p->nq, p->part.p);
+        } else {
+            dim3 g((unsigned)ceil_div(p->n_items, SQ_THREADS), (unsigned)p->P, gz);
+            sq_lattice_direct<<<g, SQ_THREADS, 0, sk>>>(p->items.p, p->n_items, p->fix[slot].p, p->N, p->d_sets.p,
+                                                       p->n_sets, p->P, p->nq, p->part.p);
+        }
         ++*launches;
         if (p->n_exp > 0) {
             dim3 ge((unsigned)ceil_div(p->n_exp, SQ_THREADS), (unsigned)p->P, gz);
@@ -700,7 +921,7 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
     }
     sq_pair_accum<<<(unsigned)ceil_div(p->nq, 256), 256, 0, sk>>>(p->part.p, F, p->n_sets, p->P, p->nq, p->d_sets.p,
                                                                  p->d_pairs.p, p->n_pairs, p->dc[0], p->dc[1],
-                                                                 p->ssf.p);
+                                                                 p->factored ? p->n_lat : 0, p->ssf.p);
     ++*launches;
     MDC_CUDA(cudaGetLastError());
     MDC_CUDA(cudaEventRecord(p->st.consumed[slot], sk));
