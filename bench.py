@@ -175,6 +175,10 @@ def run_reference(args, rank):
     GPU box and needs MDAnalysis), all host threads, each step a bounded sample of the workload."""
     if rank != 0:
         return
+    from oracle import oracle
+
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it is allowed to
+    oracle.set_num_threads(len(os.sched_getaffinity(0)))
     vals = []
     for i in range(args.warmup + args.steps):
         cb = cpu_baseline()

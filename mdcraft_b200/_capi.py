@@ -35,7 +35,7 @@ SQ_ALGOS = {"auto": SQ_ALGO_AUTO, "direct": SQ_ALGO_DIRECT, "factored": SQ_ALGO_
 
 PROBES = {
     "ffma": 0, "mufu_sincos_pairs": 1, "dfma": 2, "f2f_f64_f32": 3, "atoms_spread": 4, "imad": 5,
-    "ffma2": 6, "alu": 7, "i2f": 8, "atoms_hist": 9, "atoms_hist_base": 10,
+    "ffma2": 6, "alu": 7, "i2f": 8, "atoms_hist": 9, "atoms_hist_base": 10, "ffma2_scalar": 11,
 }
 
 
@@ -113,8 +113,8 @@ def lib() -> ctypes.CDLL:
     """Loads (building it in-tree if the sources are newer) the CUDA library."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
-        if _build.is_stale():
+        path = os.environ.get("MDCRAFT_B200_LIB") or _build.LIB_PATH   # override: kernel experiments only
+        if path == _build.LIB_PATH and _build.is_stale():
             try:
                 path = _build.build()
             except Exception as err:  # no nvcc on the box: use what travelled with the snapshot

@@ -163,6 +163,37 @@ __global__ void probe_ffma2(float2 *out, float a, float b)
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// packed FMA with the operand forms of sq_lattice_factored: scalar (broadcast) x register pair
+__global__ void probe_ffma2_scalar(float2 *out, float a, float b)
+{
+    unsigned long long x[8], W, V;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(W) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(V) : "f"(-b), "f"(a));
+    float s0 = a * 0.5f, s1 = b * 0.25f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float v = threadIdx.x + k;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(x[k]) : "f"(v));
+    }
+    for (int i = 0; i < PROBE_ITER; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            unsigned long long S;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(S) : "f"((k & 1) ? s0 : s1));
+            asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(x[k]) : "l"(S), "l"((k & 2) ? W : V));
+        }
+    }
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[k]));
+        acc.x += lo;
+        acc.y += hi;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 __global__ void probe_mufu(float *out, float a)
 {
     float x0 = threadIdx.x * 1e-3f, x1 = x0 + .1f, x2 = x0 + .2f, x3 = x0 + .3f;
@@ -380,6 +411,9 @@ extern "C" int mdc_probe_rate(mdc_ctx *ctx, int which, double *ops_per_s)
         break;
     case 10:  // address generation alone (subtract from 9)
         rc = time_probe(ctx, [&](int b) { probe_atoms_hist_base<<<b, PROBE_THREADS>>>((unsigned *)o, 12345u); }, per8, ops_per_s);
+        break;
+    case 11:  // packed FMA, scalar x pair operands
+        rc = time_probe(ctx, [&](int b) { probe_ffma2_scalar<<<b, PROBE_THREADS>>>((float2 *)o, 1.0001f, 0.5f); }, per8, ops_per_s);
         break;
     default:
         rc = fail(MDC_ERR_INVALID, "mdc_probe_rate: unknown probe");

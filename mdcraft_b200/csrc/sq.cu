@@ -313,13 +313,20 @@ sq_explicit_f64(const double *__restrict__ q, int64_t q_first, int64_t n_q, cons
 constexpr int FC_PA = 32, FC_PB = 16, FC_CQ = 8;   // patch: a x b x c wavevector indices per block
 constexpr int FC_THREADS = (FC_PA / 2) * FC_PB;    // thread = 2 adjacent a, 1 b, FC_CQ c
 constexpr int FC_T = 32;                           // particles per shared-memory tile
-constexpr int FC_RUN = 8;                          // particles per FP32 run before folding into FP64
-constexpr int FC_ROW = FC_PA * 8 + FC_PB * 8 + FC_CQ * 16;   // bytes of one particle's phasors in a tile (512)
+#ifndef MDC_FC_RUN
+#define MDC_FC_RUN 8
+#endif
+constexpr int FC_RUN = MDC_FC_RUN;                 // particles per first-level FP32 run
+#ifndef MDC_FC_FOLD
+#define MDC_FC_FOLD 8
+#endif
+constexpr int FC_FOLD = MDC_FC_FOLD;               // first-level runs per second-level FP32 sum before folding into FP64
+constexpr size_t FC_SMEM = sizeof(float2) * 2 * FC_T * (FC_PA + 2 * FC_PB + FC_CQ) + sizeof(double2) * 2 * FC_CQ * FC_THREADS;
 
-// tables: X float2 (F*N, nxp), Y float2 (F*N, nyp), Z float4 {zr, zr, -zi, zi} (F*N, nzp)
+// tables: X float2 (F*N, nxp), Y float4 {yr, yi, -yi, yr} (F*N, nyp), Z float2 (F*N, nzp)
 __global__ void sq_prep_tables(const uint32_t *__restrict__ fix, int64_t N, int64_t total, int n_points, int nxp,
-                               int nyp, int nzp, float2 *__restrict__ tx, float2 *__restrict__ ty,
-                               float4 *__restrict__ tz)
+                               int nyp, int nzp, float2 *__restrict__ tx, float4 *__restrict__ ty,
+                               float2 *__restrict__ tz)
 {
     const int64_t pj = blockIdx.x;   // frame * N + particle
     if (pj >= total) return;
@@ -340,8 +347,8 @@ __global__ void sq_prep_tables(const uint32_t *__restrict__ fix, int64_t N, int6
             im = (float)sn;
         }
         if (axis == 0) tx[pj * nxp + idx] = make_float2(re, im);
-        else if (axis == 1) ty[pj * nyp + idx] = make_float2(re, im);
-        else tz[pj * nzp + idx] = make_float4(re, re, -im, im);
+        else if (axis == 1) ty[pj * nyp + idx] = make_float4(re, im, -im, re);
+        else tz[pj * nzp + idx] = make_float2(re, im);
     }
 }
 
@@ -359,12 +366,21 @@ __device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long
 
 __global__ void __launch_bounds__(FC_THREADS, 2)
 sq_lattice_factored(const uint4 *__restrict__ patches, const float2 *__restrict__ tabx,
-                    const float2 *__restrict__ taby, const float4 *__restrict__ tabz, int nxp, int nyp, int nzp,
+                    const float4 *__restrict__ taby, const float2 *__restrict__ tabz, int nxp, int nyp, int nzp,
                     int64_t N, const int2 *__restrict__ sets, int n_sets, int P, int n_points,
                     const int *__restrict__ row_cnt, const int64_t *__restrict__ row_qoff, int64_t nq,
                     double2 *__restrict__ part)
 {
-    __shared__ __align__(16) unsigned char tile[FC_T * FC_ROW];
+    // shared-memory tiles (double buffered, filled with cp.async): X [FC_T][FC_PA], Y [FC_T][FC_PB],
+    // Z [FC_T][FC_CQ] unit phasors (float2 = re, im); and this block's FP64 accumulators
+    extern __shared__ __align__(16) unsigned char fc_smem[];
+    typedef float2 (*TileX)[FC_T][FC_PA];
+    typedef float4 (*TileY)[FC_T][FC_PB];
+    typedef float2 (*TileZ)[FC_T][FC_CQ];
+    TileX sX = reinterpret_cast<TileX>(fc_smem);
+    TileY sY = reinterpret_cast<TileY>(fc_smem + sizeof(float2) * 2 * FC_T * FC_PA);
+    TileZ sZ = reinterpret_cast<TileZ>(fc_smem + sizeof(float2) * 2 * FC_T * (FC_PA + 2 * FC_PB));
+    double2 *sD = reinterpret_cast<double2 *>(fc_smem + sizeof(float2) * 2 * FC_T * (FC_PA + 2 * FC_PB + FC_CQ));
     const uint4 patch = patches[blockIdx.x];
     const int a0 = (int)patch.x, b0 = (int)patch.y, c0 = (int)patch.z;
     const int p = blockIdx.y;
@@ -372,41 +388,71 @@ sq_lattice_factored(const uint4 *__restrict__ patches, const float2 *__restrict_
     const Chunk ch = chunk_range(sets[s], p, P);
     const int tx = threadIdx.x & (FC_PA / 2 - 1), ty = threadIdx.x / (FC_PA / 2);
 
-    // tile loader: 16-byte pieces; a particle's 512-byte row = 16 X pieces, 8 Y pieces, 8 Z pieces
-    constexpr int PIECES = FC_T * FC_ROW / 16 / FC_THREADS;   // per thread
-    uint4 stage[PIECES];
-    auto fetch = [&](int64_t t0) {
-#pragma unroll
-        for (int r = 0; r < PIECES; ++r) {
-            const int piece = threadIdx.x + r * FC_THREADS;
-            const int jj = piece >> 5, w = piece & 31;
-            const int64_t j = t0 + jj;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (j < ch.hi) {
-                const int64_t pj = (int64_t)f * N + j;
-                if (w < 16) v = *reinterpret_cast<const uint4 *>(tabx + pj * nxp + a0 + 2 * w);
-                else if (w < 24) v = *reinterpret_cast<const uint4 *>(taby + pj * nyp + b0 + 2 * (w - 16));
-                else v = *reinterpret_cast<const uint4 *>(tabz + pj * nzp + c0 + (w - 24));
-            }
-            stage[r] = v;
+    // tile loader, 16-byte pieces: X = FC_T * 16 pieces (two per thread), Y = FC_T * 16 (two per thread),
+    // Z = FC_T * 4 (threads 0..127).  Particles past the end of the chunk are zero-filled (src-size 0).
+    static_assert(FC_THREADS == 256 && FC_T == 32 && FC_PA == 32 && FC_PB == 16 && FC_CQ == 8, "loader layout");
+    auto cp16 = [](void *dst, const void *src, bool valid) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+        const int n = valid ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+    };
+    auto fetch = [&](int64_t t0, int buf) {
+        const int64_t base = (int64_t)f * N;
+        {
+            const int jj = threadIdx.x >> 4, w = threadIdx.x & 15;
+            const int64_t j = t0 + jj, j2 = j + 16;
+            cp16(&sX[buf][jj][2 * w], tabx + (base + min(j, ch.hi - 1)) * nxp + a0 + 2 * w, j < ch.hi);
+            cp16(&sX[buf][jj + 16][2 * w], tabx + (base + min(j2, ch.hi - 1)) * nxp + a0 + 2 * w, j2 < ch.hi);
         }
-    };
-    auto commit = [&]() {
-#pragma unroll
-        for (int r = 0; r < PIECES; ++r)
-            *reinterpret_cast<uint4 *>(tile + (size_t)(threadIdx.x + r * FC_THREADS) * 16) = stage[r];
+        {
+            const int jj = threadIdx.x >> 4, w = threadIdx.x & 15;
+            const int64_t j = t0 + jj, j2 = j + 16;
+            cp16(&sY[buf][jj][w], taby + (base + min(j, ch.hi - 1)) * nyp + b0 + w, j < ch.hi);
+            cp16(&sY[buf][jj + 16][w], taby + (base + min(j2, ch.hi - 1)) * nyp + b0 + w, j2 < ch.hi);
+        }
+        if (threadIdx.x < 128) {
+            const int jj = threadIdx.x >> 2, w = threadIdx.x & 3;
+            const int64_t j = t0 + jj;
+            cp16(&sZ[buf][jj][2 * w], tabz + (base + min(j, ch.hi - 1)) * nzp + c0 + 2 * w, j < ch.hi);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    double dre[2][FC_CQ], dim[2][FC_CQ];
+    // Three accumulation levels keep the rounding of the sums below that of the terms:
+    //   acc1 (FP32, registers): FC_RUN = 8 particles;  acc2 (FP32, registers): FC_FOLD runs;
+    //   sD (FP64, shared memory, [accumulator][thread]): everything else.
 #pragma unroll
-    for (int c = 0; c < FC_CQ; ++c) dre[0][c] = dre[1][c] = dim[0][c] = dim[1][c] = 0.0;
+    for (int k = 0; k < 2 * FC_CQ; ++k) sD[k * FC_THREADS + threadIdx.x] = make_double2(0.0, 0.0);
+    unsigned long long acc2[2][FC_CQ];
+#pragma unroll
+    for (int c = 0; c < FC_CQ; ++c) acc2[0][c] = acc2[1][c] = 0ull;
+    auto fold = [&]() {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < FC_CQ; ++c) {
+                float lo, hi;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc2[h][c]));
+                double2 d = sD[(h * FC_CQ + c) * FC_THREADS + threadIdx.x];
+                d.x += (double)lo;
+                d.y += (double)hi;
+                sD[(h * FC_CQ + c) * FC_THREADS + threadIdx.x] = d;
+                acc2[h][c] = 0ull;
+            }
+    };
 
-    if (ch.lo < ch.hi) fetch(ch.lo);
-    for (int64_t t0 = ch.lo; t0 < ch.hi; t0 += FC_T) {
-        __syncthreads();
-        commit();
-        __syncthreads();
-        if (t0 + FC_T < ch.hi) fetch(t0 + FC_T);   // next tile's loads fly during this tile's math
+    int buf = 0, runs = 0;
+    if (ch.lo < ch.hi) fetch(ch.lo, 0);
+    for (int64_t t0 = ch.lo; t0 < ch.hi; t0 += FC_T, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                      // tile `buf` landed; everyone is done with `buf ^ 1`
+        if (t0 + FC_T < ch.hi) fetch(t0 + FC_T, buf ^ 1);     // next tile's copies fly during this tile's math
+        // software pipeline: the phasors of particle jj + 1 are loaded while particle jj is consumed
+        float4 x = *reinterpret_cast<const float4 *>(&sX[buf][0][2 * tx]);
+        float4 y = sY[buf][0][ty];
+        float4 z[FC_CQ / 2];
+#pragma unroll
+        for (int c = 0; c < FC_CQ / 2; ++c) z[c] = *reinterpret_cast<const float4 *>(&sZ[buf][0][2 * c]);
 #pragma unroll 1
         for (int r0 = 0; r0 < FC_T; r0 += FC_RUN) {
             unsigned long long acc[2][FC_CQ];
@@ -414,34 +460,63 @@ sq_lattice_factored(const uint4 *__restrict__ patches, const float2 *__restrict_
             for (int c = 0; c < FC_CQ; ++c) acc[0][c] = acc[1][c] = 0ull;
 #pragma unroll
             for (int jj = r0; jj < r0 + FC_RUN; ++jj) {
-                const unsigned char *row = tile + jj * FC_ROW;
-                const float4 x = *reinterpret_cast<const float4 *>(row + tx * 16);
-                const float2 y = *reinterpret_cast<const float2 *>(row + FC_PA * 8 + ty * 8);
-                const float w0r = fmaf(-x.y, y.y, x.x * y.x), w0i = fmaf(x.y, y.x, x.x * y.y);
-                const float w1r = fmaf(-x.w, y.y, x.z * y.x), w1i = fmaf(x.w, y.x, x.z * y.y);
-                const unsigned long long wd0 = pack2(w0r, w0i), ws0 = pack2(w0i, w0r);
-                const unsigned long long wd1 = pack2(w1r, w1i), ws1 = pack2(w1i, w1r);
+                const int jn = (jj + 1) & (FC_T - 1);          // the last particle re-reads row 0 (unused)
+                const float4 xn = *reinterpret_cast<const float4 *>(&sX[buf][jn][2 * tx]);
+                const float4 yn = sY[buf][jn][ty];
+                // With Yp = (yr, yi) and Yq = (-yi, yr) from the table:
+                //   W = X * Y       = x.re * Yp + x.im * Yq        V = (-wi, wr) = x.re * Yq - x.im * Yp
+                //   acc(re, im)    += zr * W + zi * V              (two packed FMAs per term)
+                // Every FFMA2 operand is a scalar (broadcast by the instruction) or a register pair that a
+                // packed instruction or a 128-bit load produced: no register shuffling.
+                const unsigned long long yp = pack2(y.x, y.y), yq = pack2(y.z, y.w);
+                unsigned long long w0, w1, v0, v1;
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(w0) : "l"(pack2(x.x, x.x)), "l"(yp));
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(w1) : "l"(pack2(x.z, x.z)), "l"(yp));
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(v0) : "l"(pack2(x.x, x.x)), "l"(yq));
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(v1) : "l"(pack2(x.z, x.z)), "l"(yq));
+                fma2(w0, pack2(x.y, x.y), yq);
+                fma2(w1, pack2(x.w, x.w), yq);
+                fma2(v0, pack2(-x.y, -x.y), yp);
+                fma2(v1, pack2(-x.w, -x.w), yp);
 #pragma unroll
-                for (int c = 0; c < FC_CQ; ++c) {
-                    const ulonglong2 z = *reinterpret_cast<const ulonglong2 *>(row + FC_PA * 8 + FC_PB * 8 + c * 16);
-                    fma2(acc[0][c], z.x, wd0);
-                    fma2(acc[1][c], z.x, wd1);
-                    fma2(acc[0][c], z.y, ws0);
-                    fma2(acc[1][c], z.y, ws1);
+                for (int c = 0; c < FC_CQ; c += 2) {
+                    const float4 zz = z[c / 2];
+                    z[c / 2] = *reinterpret_cast<const float4 *>(&sZ[buf][jn][c]);
+                    const unsigned long long zr0 = pack2(zz.x, zz.x), zi0 = pack2(zz.y, zz.y);
+                    const unsigned long long zr1 = pack2(zz.z, zz.z), zi1 = pack2(zz.w, zz.w);
+                    fma2(acc[0][c], zr0, w0);
+                    fma2(acc[1][c], zr0, w1);
+                    fma2(acc[0][c + 1], zr1, w0);
+                    fma2(acc[1][c + 1], zr1, w1);
+                    fma2(acc[0][c], zi0, v0);
+                    fma2(acc[1][c], zi0, v1);
+                    fma2(acc[0][c + 1], zi1, v0);
+                    fma2(acc[1][c + 1], zi1, v1);
                 }
+                x = xn;
+                y = yn;
             }
 #pragma unroll
             for (int c = 0; c < FC_CQ; ++c) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float lo, hi;
-                    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[h][c]));
-                    dre[h][c] += (double)lo;
-                    dim[h][c] += (double)hi;
-                }
+                asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc2[0][c]) : "l"(acc[0][c]));
+                asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc2[1][c]) : "l"(acc[1][c]));
+            }
+            if (++runs == FC_FOLD) {
+                fold();
+                runs = 0;
             }
         }
     }
+    fold();
+    double dre[2][FC_CQ], dim[2][FC_CQ];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < FC_CQ; ++c) {
+            const double2 d = sD[(h * FC_CQ + c) * FC_THREADS + threadIdx.x];
+            dre[h][c] = d.x;
+            dim[h][c] = d.y;
+        }
     const int b = b0 + ty;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -584,8 +659,9 @@ struct mdc_sq_plan {
     DevBuf<uint4> items, patches;
     DevBuf<int> row_cnt;
     DevBuf<int64_t> row_qoff;
-    DevBuf<float2> tabx[2], taby[2];
-    DevBuf<float4> tabz[2];
+    DevBuf<float2> tabx[2], tabz[2];
+    DevBuf<float4> taby[2];
+
     int64_t n_patches = 0;
     int nxp = 0, nyp = 0, nzp = 0;
     DevBuf<double2> part;
@@ -784,6 +860,7 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
             p->n_patches = (int64_t)hp.size();
             PLAN_TRY(p->patches.alloc(hp.size()));
             PLAN_CUDA(cudaMemcpy(p->patches.p, hp.data(), hp.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+            PLAN_CUDA(cudaFuncSetAttribute(sq_lattice_factored, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC_SMEM));
             p->nxp = (int)ceil_div(n, FC_PA) * FC_PA;
             p->nyp = (int)ceil_div(n, FC_PB) * FC_PB;
             p->nzp = (int)ceil_div(n, FC_CQ) * FC_CQ;
@@ -836,7 +913,7 @@ int configure(mdc_sq_plan *p, int n_frames_hint)
                              ceil_div(p->lattice_fast ? p->n_exp : p->nq, SQ_THREADS);
     int fblk = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_frames_hint, 32), budget / per_frame_min));
     if (p->factored) {
-        const int64_t tab_frame = p->N * ((int64_t)p->nxp * 8 + (int64_t)p->nyp * 8 + (int64_t)p->nzp * 16);
+        const int64_t tab_frame = p->N * ((int64_t)p->nxp * 8 + (int64_t)p->nyp * 16 + (int64_t)p->nzp * 8);
         fblk = (int)std::max<int64_t>(1, std::min<int64_t>(fblk, ((int64_t)3 << 30) / tab_frame));
     }
     const int64_t want = (int64_t)p->ctx->sm_count * 32;
@@ -889,7 +966,7 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
     if (p->lattice_fast) {
         if (p->factored) {
             dim3 g((unsigned)p->n_patches, (unsigned)p->P, gz);
-            sq_lattice_factored<<<g, FC_THREADS, 0, sk>>>(p->patches.p, p->tabx[slot].p, p->taby[slot].p,
+            sq_lattice_factored<<<g, FC_THREADS, FC_SMEM, sk>>>(p->patches.p, p->tabx[slot].p, p->taby[slot].p,
                                                          p->tabz[slot].p, p->nxp, p->nyp, p->nzp, p->N, p->d_sets.p,
                                                          p->n_sets, p->P, p->n_points, p->row_cnt.p, p->row_qoff.p,
                                                          p->nq, p->part.p);
