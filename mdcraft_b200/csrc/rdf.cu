@@ -377,81 +377,157 @@ constexpr int RF_FLUSH_ITEMS = 1024;         // 1024 * 1024 * 1024 pairs < 2^31
 constexpr float RF_MAGIC = 12582912.0f;      // 1.5 * 2^23: adding it rounds to the nearest integer
 constexpr int RF_MAGIC_BITS = 0x4B400000;
 
+struct TileCtx;
 struct FastShared {
     uint4 sj[RF_TJ];            // {ux, uy, uz, exclusion block of j}
     unsigned queue[RF_QCAP];    // i_local | j_local << 16
     unsigned qcount;
+    unsigned pad[3];
+    unsigned char ctx[320];     // TileCtx of the tile in flight (cold passes read it from here)
 };
 
-// cold path, kept out of line so that the filter loop stays small enough for the instruction cache
-__device__ __noinline__ void resolve_exact(const RdfArgs &A, const FrameBox &fb, int f, int64_t ig, int64_t jg,
-                                           const double *sT, unsigned *hist)
+// The filter's FP32 bin coordinate of one pair: v = bin coordinate - 0.5 (so that rint(v) is the bin).
+template <bool CUBIC>
+__device__ __forceinline__ float filter_v(uint32_t ujx, uint32_t ujy, uint32_t ujz, uint32_t uix, uint32_t uiy,
+                                          uint32_t uiz, const FrameFast &ff)
 {
-    const float *ax = A.a + ((int64_t)f * 3) * A.na, *bx = A.b + ((int64_t)f * 3) * A.nb;
-    const double r2 = exact_r2(ax[ig], ax[A.na + ig], ax[2 * A.na + ig], bx[jg], bx[A.nb + jg], bx[2 * A.nb + jg], fb);
-    const int k = exact_bin(r2, A, sT);
-    if (k >= 0) atomicAdd(&hist[k], 1u);
-}
-
-// cold path of the filter loop: park an undecided pair for the post-tile FP64 pass
-__device__ __noinline__ void park_pair(FastShared *S, unsigned packed, const RdfArgs &A, const FrameBox &fb, int f,
-                                       int64_t ig, int64_t jg, const double *sT, unsigned *hist)
-{
-    const unsigned slot = atomicAdd(&S->qcount, 1u);
-    if (slot < RF_QCAP) S->queue[slot] = packed;
-    else resolve_exact(A, fb, f, ig, jg, sT, hist);   // queue full (pathological inputs): resolve in line
-}
-
-template <bool CHECK, bool CUBIC, bool EXCL>
-__device__ __forceinline__ void tile_pairs_fast(const RdfArgs &A, FastShared *S, int nj, int64_t i0, int64_t j0,
-                                                const uint32_t (&ux)[RF_IPT], const uint32_t (&uy)[RF_IPT],
-                                                const uint32_t (&uz)[RF_IPT], const int (&bi)[RF_IPT],
-                                                const FrameFast &ff, const FrameBox &fb, int f, const double *sT,
-                                                unsigned *hist, bool diag)
-{
-    const unsigned B = (unsigned)A.n_bins;
-    // frames whose margin is too wide for the filter (usable == 0) send every pair to the FP64 pass
-    const float thr = ff.usable ? ff.thr : -1.f;
-    const int k_lo = ff.usable ? -1 : INT_MIN, k_hi = ff.usable ? (int)B : INT_MAX;
-    const unsigned hist_addr = (unsigned)__cvta_generic_to_shared(hist);
-#pragma unroll 2
-    for (int j = 0; j < nj; ++j) {
-        const uint4 pj = S->sj[j];
-#pragma unroll
-        for (int u = 0; u < RF_IPT; ++u) {
-            const float tx = (float)(int)(pj.x - ux[u]);
-            const float ty = (float)(int)(pj.y - uy[u]);
-            const float tz = (float)(int)(pj.z - uz[u]);
-            float v, d;
-            if (CUBIC) {
-                const float t2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
-                v = fmaf(d, ff.ax, ff.c0);
-            } else {
-                const float ex = tx * ff.ax, ey = ty * ff.ay, ez = tz * ff.az;
-                const float t2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
-                v = d + ff.c0;
-            }
-            const float w = v + RF_MAGIC;
-            const int k = __float_as_int(w) - RF_MAGIC_BITS;     // rint(v): the bin, if v is clear of an edge
-            const bool clear = fabsf(v - (w - RF_MAGIC)) <= thr;
-            bool ok = true;
-            if (EXCL) ok = bi[u] != (int)pj.w;
-            if (CHECK) {
-                const int64_t ig = i0 + threadIdx.x + u * RF_THREADS;
-                ok = ok && (ig < A.na) && (!diag || (j0 + j) > ig);
-            }
-            if (ok && clear && (unsigned)k < B)
-                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + 4u * (unsigned)k) : "memory");
-            if (ok && !clear && k >= k_lo && k <= k_hi)
-                park_pair(S, (unsigned)(threadIdx.x + u * RF_THREADS) | ((unsigned)j << 16), A, fb, f,
-                          i0 + threadIdx.x + u * RF_THREADS, j0 + j, sT, hist);
-        }
+    const float tx = (float)(int)(ujx - uix);
+    const float ty = (float)(int)(ujy - uiy);
+    const float tz = (float)(int)(ujz - uiz);
+    float d;
+    if (CUBIC) {
+        const float t2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
+        return fmaf(d, ff.ax, ff.c0);
+    } else {
+        const float ex = tx * ff.ax, ey = ty * ff.ay, ez = tz * ff.az;
+        const float t2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
+        return d + ff.c0;
     }
 }
 
-__global__ void __launch_bounds__(RF_THREADS)
+struct TileCtx {            // everything the cold passes need (kept in shared memory, one per block)
+    RdfArgs A;
+    FrameFast ff;
+    FrameBox fb;
+    int64_t i0, j0;
+    int f, diag;
+    float thr;
+    int k_lo, k_hi;
+};
+
+__device__ __forceinline__ bool pair_allowed(const TileCtx &T, int64_t ig, int64_t jg)
+{
+    if (ig >= T.A.na) return false;
+    if (T.diag && jg <= ig) return false;
+    // particle counts are below 2^31 (plan creation), so 32-bit division is exact; block sizes are clamped
+    if (T.A.ex0 > 0) {
+        const unsigned e0 = (unsigned)min(T.A.ex0, (int64_t)0x7fffffff), e1 = (unsigned)min(T.A.ex1, (int64_t)0x7fffffff);
+        if ((unsigned)ig / e0 == (unsigned)jg / e1) return false;
+    }
+    return true;
+}
+
+// cold: the reference's exact FP64 result for a pair the filter could not decide
+__device__ __noinline__ void resolve_pair(const TileCtx *Tp, int il, int jl, const double *sT, unsigned *hist)
+{
+    const TileCtx &T = *Tp;
+    const int64_t ig = T.i0 + il, jg = T.j0 + jl;
+    const float *ax = T.A.a + ((int64_t)T.f * 3) * T.A.na, *bx = T.A.b + ((int64_t)T.f * 3) * T.A.nb;
+    const double r2 = exact_r2(ax[ig], ax[T.A.na + ig], ax[2 * T.A.na + ig], bx[jg], bx[T.A.nb + jg],
+                               bx[2 * T.A.nb + jg], T.fb);
+    const int k = exact_bin(r2, T.A, sT);
+    if (k >= 0) atomicAdd(&hist[k], 1u);
+}
+
+// cold: the pairs (this thread's particle u, row jl) with bit u set in `mask` are undecided; park them
+__device__ __noinline__ void park_row(const TileCtx *Tp, unsigned *queue, unsigned *qcount, int jl, unsigned mask,
+                                      const double *sT, unsigned *hist)
+{
+    for (int u = 0; u < RF_IPT; ++u) {
+        if (!((mask >> u) & 1u)) continue;
+        const int il = threadIdx.x + u * RF_THREADS;
+        const unsigned slot = atomicAdd(qcount, 1u);
+        if (slot < RF_QCAP) queue[slot] = (unsigned)il | ((unsigned)jl << 16);
+        else resolve_pair(Tp, il, jl, sT, hist);   // queue full (pathological inputs): resolve in line
+    }
+}
+
+// One pair of the hot loop after v is known: bins it if v is clear of every bin edge, otherwise reports it
+// undecided.  Written in PTX so that the shared-memory increment is predicated instead of branched around.
+//   w = v + MAGIC;  k = bits(w) - bits(MAGIC) = rint(v);  undecided = |v - (w - MAGIC)| > thr
+//   if (ok && !undecided && k < B)  hist[k] += 1;      returns ok && undecided && -1 <= k <= B  ? bit : 0
+template <unsigned BIT>
+__device__ __forceinline__ unsigned bin_or_flag(float v, float thr, unsigned B, unsigned k_span, unsigned hist_addr,
+                                                unsigned ok, unsigned one)
+{
+    unsigned und;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q, r;\n\t"
+        ".reg .f32 w, kf, df;\n\t"
+        ".reg .u32 k, ad;\n\t"
+        "add.f32 w, %1, 0f4B400000;\n\t"
+        "sub.f32 kf, w, 0f4B400000;\n\t"
+        "sub.f32 df, %1, kf;\n\t"
+        "abs.f32 df, df;\n\t"
+        "mov.b32 k, w;\n\t"
+        "sub.u32 k, k, 0x4B400000;\n\t"
+        "setp.gt.f32 q, df, %2;\n\t"
+        "setp.ne.u32 r, %5, 0;\n\t"
+        "setp.lt.and.u32 p, k, %3, r;\n\t"
+        "and.pred p, p, !q;\n\t"
+        "shl.b32 ad, k, 2;\n\t"
+        "add.u32 ad, ad, %4;\n\t"
+        "@p red.shared.add.u32 [ad], %6;\n\t"
+        "add.u32 k, k, 1;\n\t"                 // -1 <= k <= B  <=>  (unsigned)(k + 1) <= B + 1
+        "setp.le.and.u32 p, k, %7, r;\n\t"
+        "and.pred p, p, q;\n\t"
+        "selp.u32 %0, %8, 0, p;\n\t"
+        "}"
+        : "=r"(und)
+        : "f"(v), "f"(thr), "r"(B), "r"(hist_addr), "r"(ok), "r"(one), "r"(k_span), "n"(BIT)
+        : "memory");
+    return und;
+}
+
+template <bool CHECK, bool CUBIC, bool EXCL>
+__device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, const uint32_t (&ux)[RF_IPT],
+                                                const uint32_t (&uy)[RF_IPT], const uint32_t (&uz)[RF_IPT],
+                                                const int (&bi)[RF_IPT], const FrameFast &ff, float thr, unsigned B,
+                                                unsigned k_span, int64_t na, int64_t i0, int64_t j0, bool diag, const double *sT,
+                                                unsigned *hist)
+{
+    const unsigned hist_addr = (unsigned)__cvta_generic_to_shared(hist);
+    // an increment the compiler cannot see through: a literal 1 makes ptxas emit ATOMS.POPC.INC inside a
+    // branch instead of a predicated ATOMS.ADD
+    const unsigned one = (unsigned)Tp->A.sym | 1u;
+#pragma unroll 2
+    for (int j = 0; j < nj; ++j) {
+        const uint4 pj = S->sj[j];
+        static_assert(RF_IPT == 4, "the undecided-pair mask is built for four particles per thread");
+        float v[RF_IPT];
+        unsigned ok[RF_IPT];
+#pragma unroll
+        for (int u = 0; u < RF_IPT; ++u) {
+            v[u] = filter_v<CUBIC>(pj.x, pj.y, pj.z, ux[u], uy[u], uz[u], ff);
+            ok[u] = 1u;
+            if (EXCL) ok[u] = bi[u] != (int)pj.w;
+            if (CHECK) {
+                const int64_t ig = i0 + threadIdx.x + u * RF_THREADS;
+                ok[u] = ok[u] && (ig < na) && (!diag || (j0 + j) > ig);
+            }
+        }
+        const unsigned und = bin_or_flag<1u>(v[0], thr, B, k_span, hist_addr, ok[0], one) |
+                             bin_or_flag<2u>(v[1], thr, B, k_span, hist_addr, ok[1], one) |
+                             bin_or_flag<4u>(v[2], thr, B, k_span, hist_addr, ok[2], one) |
+                             bin_or_flag<8u>(v[3], thr, B, k_span, hist_addr, ok[3], one);
+        if (und) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
+    }
+}
+
+__global__ void __launch_bounds__(RF_THREADS, 3)
 rdf_pairs_fast(RdfArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -495,9 +571,29 @@ rdf_pairs_fast(RdfArgs A)
             S->sj[j] = make_uint4(bx[jj], by[jj], bz[jj], (unsigned)bj);
         }
         __syncthreads();
+        static_assert(sizeof(TileCtx) <= sizeof(S->ctx), "TileCtx must fit its shared-memory slot");
+        TileCtx *Tp = reinterpret_cast<TileCtx *>(S->ctx);
+        // frames whose margin is too wide for the filter (usable == 0) send every pair to the FP64 pass
+        const float thr = ff.usable ? ff.thr : -1.f;
+        if (threadIdx.x == 0) {
+            Tp->A = A;
+            Tp->ff = ff;
+            Tp->fb = fb;
+            Tp->i0 = i0;
+            Tp->j0 = j0;
+            Tp->f = f;
+            Tp->diag = diag ? 1 : 0;
+            Tp->thr = thr;
+            Tp->k_lo = ff.usable ? -1 : INT_MIN;
+            Tp->k_hi = ff.usable ? B : INT_MAX;
+        }
+        __syncthreads();
         const bool check = diag || (i0 + RF_TI > A.na);
         const bool excl = A.ex0 > 0;
-#define RF_CALL(C, Q, E) tile_pairs_fast<C, Q, E>(A, S, nj, i0, j0, ux, uy, uz, bi, ff, fb, f, sT, hist, diag)
+        // undecided pairs are parked when -1 <= k <= B; unusable frames park every pair
+        const unsigned k_span = ff.usable ? (unsigned)B + 1u : 0xffffffffu;
+#define RF_CALL(C, Q, E) \
+    tile_pairs_fast<C, Q, E>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, k_span, A.na, i0, j0, diag, sT, hist)
         if (check) {
             if (ff.cubic) { if (excl) RF_CALL(true, true, true); else RF_CALL(true, true, false); }
             else          { if (excl) RF_CALL(true, false, true); else RF_CALL(true, false, false); }
@@ -511,7 +607,7 @@ rdf_pairs_fast(RdfArgs A)
         const unsigned nq = min(S->qcount, (unsigned)RF_QCAP);
         for (unsigned e = threadIdx.x; e < nq; e += RF_THREADS) {
             const unsigned q = S->queue[e];
-            resolve_exact(A, fb, f, i0 + (q & 0xffffu), j0 + (q >> 16), sT, hist);
+            resolve_pair(Tp, (int)(q & 0xffffu), (int)(q >> 16), sT, hist);
         }
         __syncthreads();
         if (threadIdx.x == 0) S->qcount = 0u;
