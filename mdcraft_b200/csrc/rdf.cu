@@ -383,6 +383,7 @@ struct FastShared {
     unsigned queue[RF_QCAP];    // i_local | j_local << 16
     unsigned qcount;
     unsigned pad[3];
+    unsigned trash[RF_THREADS]; // per-thread dummy target of the branch-free histogram increment
     unsigned char ctx[320];     // TileCtx of the tile in flight (cold passes read it from here)
 };
 
@@ -455,40 +456,64 @@ __device__ __noinline__ void park_row(const TileCtx *Tp, unsigned *queue, unsign
 }
 
 // One pair of the hot loop after v is known: bins it if v is clear of every bin edge, otherwise reports it
-// undecided.  Written in PTX so that the shared-memory increment is predicated instead of branched around.
+// undecided.  Written in PTX to keep it branch free: a pair that is not to be counted increments a per-thread
+// dummy word instead of being branched around.
 //   w = v + MAGIC;  k = bits(w) - bits(MAGIC) = rint(v);  undecided = |v - (w - MAGIC)| > thr
-//   if (ok && !undecided && k < B)  hist[k] += 1;      returns ok && undecided && -1 <= k <= B  ? bit : 0
-template <unsigned BIT>
-__device__ __forceinline__ unsigned bin_or_flag(float v, float thr, unsigned B, unsigned k_span, unsigned hist_addr,
+//   hist[(ok && !undecided && k < B) ? k : dummy] += 1;        returns (ok && undecided) ? BIT : 0
+template <unsigned BIT, bool HAS_OK>
+__device__ __forceinline__ unsigned bin_or_flag(float v, float thr, unsigned B, unsigned hist_addr, unsigned trash_addr,
                                                 unsigned ok, unsigned one)
 {
     unsigned und;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, q, r;\n\t"
-        ".reg .f32 w, kf, df;\n\t"
-        ".reg .u32 k, ad;\n\t"
-        "add.f32 w, %1, 0f4B400000;\n\t"
-        "sub.f32 kf, w, 0f4B400000;\n\t"
-        "sub.f32 df, %1, kf;\n\t"
-        "abs.f32 df, df;\n\t"
-        "mov.b32 k, w;\n\t"
-        "sub.u32 k, k, 0x4B400000;\n\t"
-        "setp.gt.f32 q, df, %2;\n\t"
-        "setp.ne.u32 r, %5, 0;\n\t"
-        "setp.lt.and.u32 p, k, %3, r;\n\t"
-        "and.pred p, p, !q;\n\t"
-        "shl.b32 ad, k, 2;\n\t"
-        "add.u32 ad, ad, %4;\n\t"
-        "@p red.shared.add.u32 [ad], %6;\n\t"
-        "add.u32 k, k, 1;\n\t"                 // -1 <= k <= B  <=>  (unsigned)(k + 1) <= B + 1
-        "setp.le.and.u32 p, k, %7, r;\n\t"
-        "and.pred p, p, q;\n\t"
-        "selp.u32 %0, %8, 0, p;\n\t"
-        "}"
-        : "=r"(und)
-        : "f"(v), "f"(thr), "r"(B), "r"(hist_addr), "r"(ok), "r"(one), "r"(k_span), "n"(BIT)
-        : "memory");
+    if (HAS_OK) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, q, r;\n\t"
+            ".reg .f32 w, kf, df;\n\t"
+            ".reg .u32 k, ad;\n\t"
+            "add.f32 w, %1, 0f4B400000;\n\t"
+            "sub.f32 kf, w, 0f4B400000;\n\t"
+            "sub.f32 df, %1, kf;\n\t"
+            "abs.f32 df, df;\n\t"
+            "mov.b32 k, w;\n\t"
+            "sub.u32 k, k, 0x4B400000;\n\t"
+            "setp.ne.u32 r, %6, 0;\n\t"
+            "setp.gt.and.f32 q, df, %2, r;\n\t"
+            "setp.lt.and.u32 p, k, %3, r;\n\t"
+            "and.pred p, p, !q;\n\t"
+            "shl.b32 ad, k, 2;\n\t"
+            "add.u32 ad, ad, %4;\n\t"
+            "selp.u32 ad, ad, %5, p;\n\t"
+            "red.shared.add.u32 [ad], %7;\n\t"
+            "selp.u32 %0, %8, 0, q;\n\t"
+            "}"
+            : "=r"(und)
+            : "f"(v), "f"(thr), "r"(B), "r"(hist_addr), "r"(trash_addr), "r"(ok), "r"(one), "n"(BIT)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, q;\n\t"
+            ".reg .f32 w, kf, df;\n\t"
+            ".reg .u32 k, ad;\n\t"
+            "add.f32 w, %1, 0f4B400000;\n\t"
+            "sub.f32 kf, w, 0f4B400000;\n\t"
+            "sub.f32 df, %1, kf;\n\t"
+            "abs.f32 df, df;\n\t"
+            "mov.b32 k, w;\n\t"
+            "sub.u32 k, k, 0x4B400000;\n\t"
+            "setp.gt.f32 q, df, %2;\n\t"
+            "setp.lt.and.u32 p, k, %3, !q;\n\t"
+            "shl.b32 ad, k, 2;\n\t"
+            "add.u32 ad, ad, %4;\n\t"
+            "selp.u32 ad, ad, %5, p;\n\t"
+            "red.shared.add.u32 [ad], %6;\n\t"
+            "selp.u32 %0, %7, 0, q;\n\t"
+            "}"
+            : "=r"(und)
+            : "f"(v), "f"(thr), "r"(B), "r"(hist_addr), "r"(trash_addr), "r"(one), "n"(BIT)
+            : "memory");
+    }
     return und;
 }
 
@@ -496,13 +521,14 @@ template <bool CHECK, bool CUBIC, bool EXCL>
 __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, const uint32_t (&ux)[RF_IPT],
                                                 const uint32_t (&uy)[RF_IPT], const uint32_t (&uz)[RF_IPT],
                                                 const int (&bi)[RF_IPT], const FrameFast &ff, float thr, unsigned B,
-                                                unsigned k_span, int64_t na, int64_t i0, int64_t j0, bool diag, const double *sT,
+                                                int64_t na, int64_t i0, int64_t j0, bool diag, const double *sT,
                                                 unsigned *hist)
 {
     const unsigned hist_addr = (unsigned)__cvta_generic_to_shared(hist);
-    // an increment the compiler cannot see through: a literal 1 makes ptxas emit ATOMS.POPC.INC inside a
-    // branch instead of a predicated ATOMS.ADD
+    const unsigned trash_addr = (unsigned)__cvta_generic_to_shared(&S->trash[threadIdx.x]);
+    // an increment the compiler cannot see through (a literal 1 becomes ATOMS.POPC.INC inside a branch)
     const unsigned one = (unsigned)Tp->A.sym | 1u;
+    constexpr bool HAS_OK = CHECK || EXCL;
 #pragma unroll 2
     for (int j = 0; j < nj; ++j) {
         const uint4 pj = S->sj[j];
@@ -519,10 +545,10 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                 ok[u] = ok[u] && (ig < na) && (!diag || (j0 + j) > ig);
             }
         }
-        const unsigned und = bin_or_flag<1u>(v[0], thr, B, k_span, hist_addr, ok[0], one) |
-                             bin_or_flag<2u>(v[1], thr, B, k_span, hist_addr, ok[1], one) |
-                             bin_or_flag<4u>(v[2], thr, B, k_span, hist_addr, ok[2], one) |
-                             bin_or_flag<8u>(v[3], thr, B, k_span, hist_addr, ok[3], one);
+        const unsigned und = bin_or_flag<1u, HAS_OK>(v[0], thr, B, hist_addr, trash_addr, ok[0], one) |
+                             bin_or_flag<2u, HAS_OK>(v[1], thr, B, hist_addr, trash_addr, ok[1], one) |
+                             bin_or_flag<4u, HAS_OK>(v[2], thr, B, hist_addr, trash_addr, ok[2], one) |
+                             bin_or_flag<8u, HAS_OK>(v[3], thr, B, hist_addr, trash_addr, ok[3], one);
         if (und) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
     }
 }
@@ -589,11 +615,15 @@ rdf_pairs_fast(RdfArgs A)
         }
         __syncthreads();
         const bool check = diag || (i0 + RF_TI > A.na);
-        const bool excl = A.ex0 > 0;
-        // undecided pairs are parked when -1 <= k <= B; unusable frames park every pair
-        const unsigned k_span = ff.usable ? (unsigned)B + 1u : 0xffffffffu;
+        // the block exclusion i / ex0 == j / ex1 can only bite where the two tiles' block ranges overlap
+        bool excl = false;
+        if (A.ex0 > 0) {
+            const int64_t ilo = i0 / A.ex0, ihi = min(i0 + RF_TI - 1, A.na - 1) / A.ex0;
+            const int64_t jlo = j0 / A.ex1, jhi = (j0 + nj - 1) / A.ex1;
+            excl = ilo <= jhi && jlo <= ihi;
+        }
 #define RF_CALL(C, Q, E) \
-    tile_pairs_fast<C, Q, E>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, k_span, A.na, i0, j0, diag, sT, hist)
+    tile_pairs_fast<C, Q, E>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist)
         if (check) {
             if (ff.cubic) { if (excl) RF_CALL(true, true, true); else RF_CALL(true, true, false); }
             else          { if (excl) RF_CALL(true, false, true); else RF_CALL(true, false, false); }
