@@ -1,0 +1,155 @@
+"""
+GPU: the BASELINE.json configurations at FULL size (C2-C5), checked through size-independent
+properties and through oracle slices that the CPU finishes in seconds:
+
+* g(r): the filter kernel against the all-FP64 kernel (bit-exact), a 512-particle slab of i against all j against
+  the CPU oracle (bit-exact), evenness / self-pair / exclusion identities, the ideal-gas in-range fraction;
+* S(q): FP32 (factored and direct) against the FP64-mode kernel on the whole grid under the error model, the
+  FP64-mode kernel against the CPU oracle on a random subset of wavevectors, the partial sum rule.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(name, n=None, frame=0):
+    from mdcraft_b200 import synthetic
+
+    n0, _, rho, kind, seed0 = synthetic.CONFIGS[name]
+    n = n or n0
+    L = synthetic.cubic_box_length(n, rho)
+    fn = synthetic.lj_like_frame if kind == "lj" else synthetic.uniform_frame
+    return fn(n, L, seed0 + frame), np.array([L, L, L, 90, 90, 90], np.float32)
+
+
+def _rdf_counts(ctx, pos_a, pos_b, box, n_bins, rng, exclusion=None, exact=False):
+    from mdcraft_b200 import _capi
+
+    old = os.environ.get("MDC_RDF_EXACT")
+    os.environ["MDC_RDF_EXACT"] = "1" if exact else "0"
+    try:
+        plan = _capi.RdfPlan(ctx, n_bins, rng, len(pos_a), None if pos_b is None else len(pos_b), exclusion)
+    finally:
+        if old is None:
+            del os.environ["MDC_RDF_EXACT"]
+        else:
+            os.environ["MDC_RDF_EXACT"] = old
+    plan.push(pos_a[None], None if pos_b is None else pos_b[None], box, n_frames=1)
+    counts, nf = plan.read()
+    assert nf == 1
+    plan.close()
+    return counts
+
+
+def test_c2_rdf_full_size(ctx):
+    """C2: g(r) on 100,000 uniform particles, 200 bins to L/2."""
+    from oracle import oracle
+
+    pos, box = _frame("C2")
+    n, L = len(pos), float(box[0])
+    rng = (0.0, L / 2)
+    fast = _rdf_counts(ctx, pos, None, box, 200, rng)
+    # identities: N self pairs in bin 0, every other contribution comes in (i, j) / (j, i) twins
+    assert fast[0] >= n and ((fast - np.eye(1, 200, 0, dtype=np.int64)[0] * n) % 2 == 0).all()
+    excl = _rdf_counts(ctx, pos, None, box, 200, rng, exclusion=(1, 1))
+    np.testing.assert_array_equal(excl, fast - np.eye(1, 200, 0, dtype=np.int64)[0] * n)
+    # ideal gas: the fraction of ordered pairs within L/2 is pi/6, to ~1/sqrt(pairs)
+    assert abs(excl.sum() / (n * (n - 1.0)) - np.pi / 6) < 2e-4
+    # a slab of i against all j, bit-exact against the CPU restatement of the reference
+    slab = _rdf_counts(ctx, pos[:512], pos, box, 200, rng)
+    np.testing.assert_array_equal(slab, oracle.radial_histogram(pos[:512], pos, 200, rng, box))
+    # the FP32 filter changes nothing: all-FP64 kernel, same counts (20 % of the particles keeps this quick)
+    sub = pos[:20_000]
+    np.testing.assert_array_equal(_rdf_counts(ctx, sub, None, box, 200, rng),
+                                  _rdf_counts(ctx, sub, None, box, 200, rng, exact=True))
+
+
+def test_c4_binary_electrolyte_partials(ctx):
+    """C4: 100k cations + 100k anions: ++, +-, -- g(r) and the partial S(q) sum rule."""
+    from mdcraft_b200 import _capi
+
+    pos, box = _frame("C4")
+    n, L = len(pos), float(box[0])
+    half = n // 2
+    rng = (0.0, L / 2)
+    pp = _rdf_counts(ctx, pos[:half], None, box, 200, rng, exclusion=(1, 1))
+    mm = _rdf_counts(ctx, pos[half:], None, box, 200, rng, exclusion=(1, 1))
+    pm = _rdf_counts(ctx, pos[:half], pos[half:], box, 200, rng)
+    mp = _rdf_counts(ctx, pos[half:], pos[:half], box, 200, rng)
+    allp = _rdf_counts(ctx, pos, None, box, 200, rng, exclusion=(1, 1))
+    np.testing.assert_array_equal(pm, mp)                       # float32 subtraction is antisymmetric
+    np.testing.assert_array_equal(pp + mm + pm + mp, allp)      # the four blocks tile the full pair matrix
+
+    plan = _capi.SqPlan(ctx, [half, half], [(0, 0), (0, 1), (1, 1)], n_points=32, L0=[L] * 3)
+    tot = _capi.SqPlan(ctx, [n], [(None, None)], n_points=32, L0=[L] * 3)
+    plan.push(pos[None])
+    tot.push(pos[None])
+    part, _ = plan.read()
+    s, _ = tot.read()
+    part /= n
+    s /= n
+    # sum rule (structure.py:1554-1560); both sides carry kappa ~ 1e-7 per term
+    tol = 1e-5 * s[0] + 3e-6 * (np.sqrt(part[0]) + np.sqrt(part[2])) + 1e-9
+    assert (np.abs(part.sum(axis=0) - s[0]) <= tol).all()
+    plan.close()
+    tot.close()
+
+
+@pytest.mark.parametrize("algo,kappa", [("factored", 1e-7), ("direct", 5e-7)])
+def test_c3_sq_full_size(ctx, algo, kappa):
+    """C3: S(q) on 100,000 particles, default 32^3 grid: FP32 kernels against the FP64-mode kernel."""
+    from mdcraft_b200 import _capi
+    from oracle import oracle
+
+    pos, box = _frame("C3")
+    n, L = len(pos), float(box[0])
+    ref = _capi.SqPlan(ctx, [n], [(None, None)], n_points=32, L0=[L] * 3, precision="fp64")
+    ref.push(pos[None])
+    s64, _ = ref.read()
+    s64 = s64[0] / n
+    if algo == "factored":   # pin the FP64-mode kernel itself on a random slice of the grid
+        wv = ref.wavevectors()
+        idx = np.random.default_rng(0).choice(len(wv), 256, replace=False)
+        rho = oracle.delta_fourier_transform_sum(wv[idx], pos.astype(np.float64))
+        np.testing.assert_allclose(s64[idx], np.abs(rho) ** 2 / n, rtol=1e-10, atol=1e-12)
+    ref.close()
+    plan = _capi.SqPlan(ctx, [n], [(None, None)], n_points=32, L0=[L] * 3, algo=algo)
+    plan.push(pos[None])
+    s32, _ = plan.read()
+    s32 = s32[0] / n
+    plan.close()
+    tol = 1e-5 * s64 + 2 * 5 * kappa * np.sqrt(s64) + 1e-12
+    assert (np.abs(s32 - s64) <= tol).all(), float(np.max(np.abs(s32 - s64) / tol))
+    big = s64 > (0.01 if algo == "factored" else 0.25)
+    assert np.max(np.abs(s32[big] / s64[big] - 1)) < 1e-5
+
+
+def test_c5_million_particles(ctx):
+    """C5: 1,000,000 particles: one frame of g(r) (1e12 ordered pairs) and S(q)."""
+    from mdcraft_b200 import _capi
+    from oracle import oracle
+
+    pos, box = _frame("C5")
+    n, L = len(pos), float(box[0])
+    rng = (0.0, L / 2)
+    counts = _rdf_counts(ctx, pos, None, box, 200, rng, exclusion=(1, 1))
+    assert (counts % 2 == 0).all()
+    assert abs(counts.sum() / (n * (n - 1.0)) - np.pi / 6) < 2e-5
+    slab = _rdf_counts(ctx, pos[:64], pos, box, 200, rng)
+    np.testing.assert_array_equal(slab, oracle.radial_histogram(pos[:64], pos, 200, rng, box))
+
+    plan = _capi.SqPlan(ctx, [n], [(None, None)], n_points=32, L0=[L] * 3)
+    plan.push(pos[None])
+    s32, _ = plan.read()
+    s32 = s32[0] / n
+    wv = plan.wavevectors()
+    plan.close()
+    idx = np.random.default_rng(1).choice(len(wv), 96, replace=False)
+    rho = oracle.delta_fourier_transform_sum(wv[idx], pos.astype(np.float64))
+    want = np.abs(rho) ** 2 / n
+    tol = 1e-5 * want + 2 * 5 * 1e-7 * np.sqrt(want) + 1e-12
+    assert (np.abs(s32[idx] - want) <= tol).all()
