@@ -281,6 +281,19 @@ def run_native(args, rank, world):
     value = total_frames / (dev_ms * 1e-3)
     e2e = total_frames / (e2e_ms * 1e-3)
 
+    # secondary figure: the reference's DEFAULT grid (n_points = 32, Nq = 32,768) on the same frames, device resident
+    sqd = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=32, L0=[Ls] * 3, algo=args.sq_algo)
+    rep = 16
+    for _ in range(3):
+        sqd.push(sq_dev, n_frames=F)
+    ctx.synchronize()
+    ctx.mark(0)
+    for _ in range(rep):
+        sqd.push(sq_dev, n_frames=F)
+    ctx.mark(1)
+    sq_default_fps = F * rep / (ctx.elapsed_ms() * 1e-3)
+    sqd.close()
+
     # the once-per-run exchange step: all-reduce of the accumulators over NVLink (outside the timed steps)
     if world > 1:
         from mdcraft_b200 import distributed as mdist
@@ -319,6 +332,7 @@ def run_native(args, rank, world):
             },
             "sq_algo": args.sq_algo,
             "sq_frames_per_s": F * args.steps / (sq_ms * 1e-3),
+            "sq_default_grid_frames_per_s": sq_default_fps,
             "gr_frames_per_s": F * args.steps / (gr_ms * 1e-3),
             "gr_pairs_per_s": pairs / (gr_ms * 1e-3),
             "wall_s": wall,

@@ -374,8 +374,7 @@ constexpr int RF_TI = RF_THREADS * RF_IPT;   // 1024
 constexpr int RF_TJ = 1024;
 constexpr int RF_QCAP = 4096;                // undecided pairs per tile before falling back to in-line resolution
 constexpr int RF_FLUSH_ITEMS = 1024;         // 1024 * 1024 * 1024 pairs < 2^31
-constexpr float RF_MAGIC = 12582912.0f;      // 1.5 * 2^23: adding it rounds to the nearest integer
-constexpr int RF_MAGIC_BITS = 0x4B400000;
+// the filter rounds with the magic number 1.5 * 2^23 = 12582912.0f = 0x4B400000 (bin_or_flag)
 
 struct TileCtx;
 struct FastShared {
@@ -415,20 +414,7 @@ struct TileCtx {            // everything the cold passes need (kept in shared m
     int64_t i0, j0;
     int f, diag;
     float thr;
-    int k_lo, k_hi;
 };
-
-__device__ __forceinline__ bool pair_allowed(const TileCtx &T, int64_t ig, int64_t jg)
-{
-    if (ig >= T.A.na) return false;
-    if (T.diag && jg <= ig) return false;
-    // particle counts are below 2^31 (plan creation), so 32-bit division is exact; block sizes are clamped
-    if (T.A.ex0 > 0) {
-        const unsigned e0 = (unsigned)min(T.A.ex0, (int64_t)0x7fffffff), e1 = (unsigned)min(T.A.ex1, (int64_t)0x7fffffff);
-        if ((unsigned)ig / e0 == (unsigned)jg / e1) return false;
-    }
-    return true;
-}
 
 // cold: the reference's exact FP64 result for a pair the filter could not decide
 __device__ __noinline__ void resolve_pair(const TileCtx *Tp, int il, int jl, const double *sT, unsigned *hist)
@@ -610,8 +596,6 @@ rdf_pairs_fast(RdfArgs A)
             Tp->f = f;
             Tp->diag = diag ? 1 : 0;
             Tp->thr = thr;
-            Tp->k_lo = ff.usable ? -1 : INT_MIN;
-            Tp->k_hi = ff.usable ? B : INT_MAX;
         }
         __syncthreads();
         const bool check = diag || (i0 + RF_TI > A.na);
