@@ -318,8 +318,8 @@ class RadialDistributionFunction(DynamicAnalysisBase):
         self.results.counts = np.zeros(self._n_bins, dtype=np.int64)
         self.results.units = Hash({"bins": _ANGSTROM, "edges": _ANGSTROM})
 
-        self._same = self._groups[0] is self._groups[1] or (
-            self._groups[0] == self._groups[1] and self._groupings[0] == self._groupings[1]
+        self._same = self._groupings[0] == self._groupings[1] and (
+            self._groups[0] is self._groups[1] or bool(self._groups[0] == self._groups[1])
         )
         n_a = _entity_count(self._groups[0], self._groupings[0])
         n_b = _entity_count(self._groups[1], self._groupings[1])

@@ -310,8 +310,9 @@ sq_explicit_f64(const double *__restrict__ q, int64_t q_first, int64_t n_q, cons
 // the rounding of the terms themselves.  Cost: 4 FP32 FMAs per term instead of 2 SFU ops.
 // ------------------------------------------------------------------------------------------
 
-constexpr int FC_PA = 32, FC_PB = 16, FC_CQ = 8;   // patch: a x b x c wavevector indices per block
-constexpr int FC_THREADS = (FC_PA / 2) * FC_PB;    // thread = 2 adjacent a, 1 b, FC_CQ c
+constexpr int FC_PA = 32, FC_CQ = 8;                // a block covers one 32-wide a column and 8 c
+constexpr int FC_YB = 24;                          // ... and up to 24 consecutive b rows, from which it takes
+constexpr int FC_THREADS = 256;                    // up to 256 (a pair, b) work items: thread = 2 adjacent a, 1 b, FC_CQ c
 constexpr int FC_T = 32;                           // particles per shared-memory tile
 #ifndef MDC_FC_RUN
 #define MDC_FC_RUN 8
@@ -321,7 +322,7 @@ constexpr int FC_RUN = MDC_FC_RUN;                 // particles per first-level 
 #define MDC_FC_FOLD 8
 #endif
 constexpr int FC_FOLD = MDC_FC_FOLD;               // first-level runs per second-level FP32 sum before folding into FP64
-constexpr size_t FC_SMEM = sizeof(float2) * 2 * FC_T * (FC_PA + 2 * FC_PB + FC_CQ) + sizeof(double2) * 2 * FC_CQ * FC_THREADS;
+constexpr size_t FC_SMEM = sizeof(float2) * 2 * FC_T * (FC_PA + 2 * FC_YB + FC_CQ) + sizeof(double2) * 2 * FC_CQ * FC_THREADS;
 
 // tables: X float2 (F*N, nxp), Y float4 {yr, yi, -yi, yr} (F*N, nyp), Z float2 (F*N, nzp)
 __global__ void sq_prep_tables(const uint32_t *__restrict__ fix, int64_t N, int64_t total, int n_points, int nxp,
@@ -365,32 +366,39 @@ __device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long
 }
 
 __global__ void __launch_bounds__(FC_THREADS, 2)
-sq_lattice_factored(const uint4 *__restrict__ patches, const float2 *__restrict__ tabx,
+sq_lattice_factored(const uint4 *__restrict__ patches, const unsigned short *__restrict__ entries,
+                    const float2 *__restrict__ tabx,
                     const float4 *__restrict__ taby, const float2 *__restrict__ tabz, int nxp, int nyp, int nzp,
                     int64_t N, const int2 *__restrict__ sets, int n_sets, int P, int n_points,
                     const int *__restrict__ row_cnt, const int64_t *__restrict__ row_qoff, int64_t nq,
                     double2 *__restrict__ part)
 {
-    // shared-memory tiles (double buffered, filled with cp.async): X [FC_T][FC_PA], Y [FC_T][FC_PB],
+    // shared-memory tiles (double buffered, filled with cp.async): X [FC_T][FC_PA], Y [FC_T][FC_YB],
     // Z [FC_T][FC_CQ] unit phasors (float2 = re, im); and this block's FP64 accumulators
     extern __shared__ __align__(16) unsigned char fc_smem[];
     typedef float2 (*TileX)[FC_T][FC_PA];
-    typedef float4 (*TileY)[FC_T][FC_PB];
+    typedef float4 (*TileY)[FC_T][FC_YB];
     typedef float2 (*TileZ)[FC_T][FC_CQ];
     TileX sX = reinterpret_cast<TileX>(fc_smem);
     TileY sY = reinterpret_cast<TileY>(fc_smem + sizeof(float2) * 2 * FC_T * FC_PA);
-    TileZ sZ = reinterpret_cast<TileZ>(fc_smem + sizeof(float2) * 2 * FC_T * (FC_PA + 2 * FC_PB));
-    double2 *sD = reinterpret_cast<double2 *>(fc_smem + sizeof(float2) * 2 * FC_T * (FC_PA + 2 * FC_PB + FC_CQ));
+    TileZ sZ = reinterpret_cast<TileZ>(fc_smem + sizeof(float2) * 2 * FC_T * (FC_PA + 2 * FC_YB));
+    double2 *sD = reinterpret_cast<double2 *>(fc_smem + sizeof(float2) * 2 * FC_T * (FC_PA + 2 * FC_YB + FC_CQ));
     const uint4 patch = patches[blockIdx.x];
-    const int a0 = (int)patch.x, b0 = (int)patch.y, c0 = (int)patch.z;
+    // block = {a0 | b0 << 16, c0 | n_items << 16, first entry}; entry = (a pair index in the column) | (b - b0) << 8.
+    // Work items are the (a pair, b) rows that still hold kept wavevectors at c0, packed densely, so that blocks
+    // on the rim of the q_max sphere are as full as those inside it.
+    const int a0 = (int)(patch.x & 0xffffu), b0 = (int)(patch.x >> 16), c0 = (int)(patch.y & 0xffffu);
+    const int n_work = (int)(patch.y >> 16);
+    const bool active = (int)threadIdx.x < n_work;
+    const unsigned entry = entries[patch.z + (active ? threadIdx.x : 0)];
+    const int tx = (int)(entry & 0xffu), ty = (int)(entry >> 8);
     const int p = blockIdx.y;
     const int f = blockIdx.z / n_sets, s = blockIdx.z - f * n_sets;
     const Chunk ch = chunk_range(sets[s], p, P);
-    const int tx = threadIdx.x & (FC_PA / 2 - 1), ty = threadIdx.x / (FC_PA / 2);
 
-    // tile loader, 16-byte pieces: X = FC_T * 16 pieces (two per thread), Y = FC_T * 16 (two per thread),
+    // tile loader, 16-byte pieces: X = FC_T * 16 pieces (two per thread), Y = FC_T * 24 (three per thread),
     // Z = FC_T * 4 (threads 0..127).  Particles past the end of the chunk are zero-filled (src-size 0).
-    static_assert(FC_THREADS == 256 && FC_T == 32 && FC_PA == 32 && FC_PB == 16 && FC_CQ == 8, "loader layout");
+    static_assert(FC_THREADS == 256 && FC_T == 32 && FC_PA == 32 && FC_YB == 24 && FC_CQ == 8, "loader layout");
     auto cp16 = [](void *dst, const void *src, bool valid) {
         const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
         const int n = valid ? 16 : 0;
@@ -404,11 +412,11 @@ sq_lattice_factored(const uint4 *__restrict__ patches, const float2 *__restrict_
             cp16(&sX[buf][jj][2 * w], tabx + (base + min(j, ch.hi - 1)) * nxp + a0 + 2 * w, j < ch.hi);
             cp16(&sX[buf][jj + 16][2 * w], tabx + (base + min(j2, ch.hi - 1)) * nxp + a0 + 2 * w, j2 < ch.hi);
         }
-        {
-            const int jj = threadIdx.x >> 4, w = threadIdx.x & 15;
-            const int64_t j = t0 + jj, j2 = j + 16;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int piece = threadIdx.x + r * FC_THREADS, jj = piece / FC_YB, w = piece - jj * FC_YB;
+            const int64_t j = t0 + jj;
             cp16(&sY[buf][jj][w], taby + (base + min(j, ch.hi - 1)) * nyp + b0 + w, j < ch.hi);
-            cp16(&sY[buf][jj + 16][w], taby + (base + min(j2, ch.hi - 1)) * nyp + b0 + w, j2 < ch.hi);
         }
         if (threadIdx.x < 128) {
             const int jj = threadIdx.x >> 2, w = threadIdx.x & 3;
@@ -521,7 +529,7 @@ sq_lattice_factored(const uint4 *__restrict__ patches, const float2 *__restrict_
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int a = a0 + 2 * tx + h;
-        if (a < n_points && b < n_points) {
+        if (active && a < n_points && b < n_points) {
             const int row = b * n_points + a;
             const int cnt = row_cnt[row];
             double2 *out = part + ((int64_t)blockIdx.z * P + p) * nq + row_qoff[row];
@@ -657,6 +665,7 @@ struct mdc_sq_plan {
     double dc[2] = {0, 0};
     DevBuf<double> q, ssf, posd[2];
     DevBuf<uint4> items, patches;
+    DevBuf<unsigned short> entries;
     DevBuf<int> row_cnt;
     DevBuf<int64_t> row_qoff;
     DevBuf<float2> tabx[2], tabz[2];
@@ -687,6 +696,7 @@ void plan_free(mdc_sq_plan *p)
     p->ssf.release();
     p->items.release();
     p->patches.release();
+    p->entries.release();
     p->row_cnt.release();
     p->row_qoff.release();
     p->part.release();
@@ -845,24 +855,50 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
             cnt.release();
             qo.release();
         } else {
-            // patches of FC_PA x FC_PB x FC_CQ wavevector indices that contain at least one kept wavevector
+            // work blocks: for every c chunk and every 32-wide a column, runs of at most FC_YB consecutive b rows
+            // whose (a pair, b) items with kept wavevectors at c0 are packed, up to FC_THREADS per block
             p->items.release();
             const int n = n_points;
             std::vector<uint4> hp;
+            std::vector<unsigned short> he;
             for (int c0 = 0; c0 < n; c0 += FC_CQ)
-                for (int b0 = 0; b0 < n; b0 += FC_PB)
-                    for (int a0 = 0; a0 < n; a0 += FC_PA) {
-                        bool any = false;
-                        for (int b = b0; b < std::min(n, b0 + FC_PB) && !any; ++b)
-                            for (int a = a0; a < std::min(n, a0 + FC_PA) && !any; ++a) any = h[b * n + a] > c0;
-                        if (any) hp.push_back(make_uint4((unsigned)a0, (unsigned)b0, (unsigned)c0, 0u));
+                for (int a0 = 0; a0 < n; a0 += FC_PA) {
+                    int b = 0;
+                    while (b < n) {
+                        const int b_start = b;
+                        const size_t off = he.size();
+                        int count = 0;
+                        while (b < n && b - b_start < FC_YB) {
+                            int m = 0;
+                            for (int ap = 0; ap < FC_PA / 2; ++ap) {
+                                const int a = a0 + 2 * ap;
+                                if (a < n && h[b * n + a] > c0) ++m;
+                            }
+                            if (count + m > FC_THREADS) break;
+                            for (int ap = 0; ap < FC_PA / 2; ++ap) {
+                                const int a = a0 + 2 * ap;
+                                if (a < n && h[b * n + a] > c0) he.push_back((unsigned short)(ap | ((b - b_start) << 8)));
+                            }
+                            count += m;
+                            ++b;
+                            if (m == 0 && count == 0) break;   // nothing kept in this row: start the next block after it
+                        }
+                        if (count > 0)
+                            hp.push_back(make_uint4((unsigned)a0 | ((unsigned)b_start << 16),
+                                                    (unsigned)c0 | ((unsigned)count << 16), (unsigned)off, 0u));
+                        else
+                            he.resize(off);
                     }
+                }
+            if (he.empty()) he.push_back(0);
             p->n_patches = (int64_t)hp.size();
             PLAN_TRY(p->patches.alloc(hp.size()));
             PLAN_CUDA(cudaMemcpy(p->patches.p, hp.data(), hp.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+            PLAN_TRY(p->entries.alloc(he.size()));
+            PLAN_CUDA(cudaMemcpy(p->entries.p, he.data(), he.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
             PLAN_CUDA(cudaFuncSetAttribute(sq_lattice_factored, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC_SMEM));
             p->nxp = (int)ceil_div(n, FC_PA) * FC_PA;
-            p->nyp = (int)ceil_div(n, FC_PB) * FC_PB;
+            p->nyp = (int)ceil_div(n, 8) * 8 + FC_YB;   // a block's Y slice may run past the last row: zero phasors
             p->nzp = (int)ceil_div(n, FC_CQ) * FC_CQ;
         }
     }
@@ -966,7 +1002,7 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
     if (p->lattice_fast) {
         if (p->factored) {
             dim3 g((unsigned)p->n_patches, (unsigned)p->P, gz);
-            sq_lattice_factored<<<g, FC_THREADS, FC_SMEM, sk>>>(p->patches.p, p->tabx[slot].p, p->taby[slot].p,
+            sq_lattice_factored<<<g, FC_THREADS, FC_SMEM, sk>>>(p->patches.p, p->entries.p, p->tabx[slot].p, p->taby[slot].p,
                                                          p->tabz[slot].p, p->nxp, p->nyp, p->nzp, p->N, p->d_sets.p,
                                                          p->n_sets, p->P, p->n_points, p->row_cnt.p, p->row_qoff.p,
                                                          p->nq, p->part.p);

@@ -266,6 +266,28 @@ class AtomGroup:
     def n_segments(self) -> int:
         return int(np.unique(self.universe._segindices[self.indices]).size)
 
+    def _split(self, labels: np.ndarray):
+        """Sub-groups of this group sharing a residue / segment index, in index order."""
+        mine = labels[self.indices]
+        out = []
+        for lab in np.unique(mine):
+            g = AtomGroup(self.universe, self.indices[mine == lab])
+            g.atoms = g   # MDAnalysis' Residue / Segment expose their atoms as ``.atoms``
+            out.append(g)
+        return out
+
+    @property
+    def residues(self):
+        return self._split(self.universe._resindices)
+
+    @property
+    def segments(self):
+        return self._split(self.universe._segindices)
+
+    def center_of_mass(self) -> np.ndarray:
+        m = self.masses
+        return (m[:, None] * self.positions.astype(np.float64)).sum(axis=0) / m.sum()
+
     def __len__(self) -> int:
         return self.n_atoms
 

@@ -222,6 +222,41 @@ def test_rdf_adversarial_edge_distances():
         np.testing.assert_array_equal(r.results.counts, want["counts"])
 
 
+def test_rdf_and_sq_residue_groupings(tmp_path):
+    """groupings="residues": centres of mass are formed on the host (algorithm.center_of_mass) and take the
+    same GPU path; results.save() round-trips."""
+    from mdcraft_b200 import algorithm, synthetic
+    from oracle import oracle
+
+    rng = np.random.default_rng(21)
+    n_res, per, L = 300, 3, 12.0
+    centers = rng.random((2, n_res, 1, 3)) * L
+    pos = (centers + rng.normal(scale=0.3, size=(2, n_res, per, 3))).reshape(2, -1, 3).astype(np.float32)
+    masses = np.tile([16.0, 1.0, 1.0], n_res)
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    traj = synthetic.MemoryTrajectory(pos, dims)
+    u = synthetic.Universe(traj, resindices=np.repeat(np.arange(n_res), per), masses=masses)
+    coms = []
+    for i in range(2):
+        u.trajectory[i]
+        coms.append(algorithm.center_of_mass(u.atoms, "residues").astype(np.float32))
+    want = oracle.rdf(coms, None, [dims] * 2, 60, (0.0, 6.0))
+    r = _rdf(u.atoms, n_bins=60, range_=(0.0, 6.0), groupings="residues")
+    np.testing.assert_array_equal(r.results.counts, want["counts"])
+    np.testing.assert_allclose(r.results.rdf, want["rdf"], rtol=1e-12)
+    r.save(str(tmp_path / "rdf"))
+    saved = np.load(str(tmp_path / "rdf.npz"), allow_pickle=True)
+    np.testing.assert_array_equal(saved["counts"], r.results.counts)
+    # atoms of one group against residues of the same group: two different entity sets
+    want2 = oracle.rdf([p for p in pos], coms, [dims] * 2, 40, (0.0, 5.0))
+    r2 = _rdf(u.atoms, u.atoms, n_bins=40, range_=(0.0, 5.0), groupings=("atoms", "residues"))
+    np.testing.assert_array_equal(r2.results.counts, want2["counts"])
+    s = _sq(u.atoms, "residues", mode="pair", n_points=6)
+    ws = oracle.structure_factor(coms, [n_res], dims[:3], mode="pair", n_points=6)
+    np.testing.assert_array_equal(s.results.wavenumbers, ws["wavenumbers"])
+    np.testing.assert_allclose(s.results.ssf, ws["ssf"], rtol=1e-5, atol=1e-6)
+
+
 def test_rdf_post_processing_runs():
     g = golden("rdf_self_c1.npz")
     u = universe_from(g["pos"], g["dims"])

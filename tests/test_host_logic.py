@@ -171,3 +171,29 @@ def test_synthetic_universe_protocol():
     assert [ts.frame for ts in sl] == [1, 3]
     assert u.trajectory.check_slice_indices(None, None, None) == (0, 5, 1)
     np.testing.assert_array_equal(u.trajectory[0].positions, p0)   # deterministic seeds
+
+
+def test_center_of_mass_groupings():
+    """`center_of_mass(group, grouping)` as the classes call it when groupings != "atoms"
+    (reference: algorithm/molecule.py:16-441, einsum at :428)."""
+    from mdcraft_b200 import synthetic
+
+    rng = np.random.default_rng(11)
+    n_res, per = 50, 4
+    pos = rng.random((2, n_res * per, 3)).astype(np.float32) * 9
+    masses = rng.random(n_res * per) + 0.5
+    traj = synthetic.MemoryTrajectory(pos, np.array([9, 9, 9, 90, 90, 90], np.float32))
+    u = synthetic.Universe(traj, resindices=np.repeat(np.arange(n_res), per), masses=masses)
+    com = algorithm.center_of_mass(u.atoms, "residues")
+    assert com.shape == (n_res, 3)
+    want = (masses[:, None] * pos[0]).reshape(n_res, per, 3).sum(1) / masses.reshape(n_res, per).sum(1)[:, None]
+    np.testing.assert_allclose(com, want, rtol=1e-12)
+    # ragged residues take the per-group path
+    res = np.concatenate([np.repeat(np.arange(10), 3), np.repeat(np.arange(10, 10 + 34), 5)])
+    u2 = synthetic.Universe(traj, resindices=res, masses=masses)
+    com2 = algorithm.center_of_mass(u2.atoms, "residues")
+    assert com2.shape == (44, 3)
+    np.testing.assert_allclose(com2[0], (masses[:3, None] * pos[0, :3]).sum(0) / masses[:3].sum(), rtol=1e-12)
+    np.testing.assert_allclose(algorithm.center_of_mass(u.atoms), (masses[:, None] * pos[0]).sum(0) / masses.sum(), rtol=1e-12)
+    with pytest.raises(ValueError, match="Invalid grouping"):
+        algorithm.center_of_mass(u.atoms, "molecules")
