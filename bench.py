@@ -294,6 +294,26 @@ def run_native(args, rank, world):
     sq_default_fps = F * rep / (ctx.elapsed_ms() * 1e-3)
     sqd.close()
 
+    # secondary figure: the contract kernel of BASELINE.json's north_star (one fused sin/cos per term on the SFU)
+    # on the same full grid, against the SFU issue-rate roofline
+    direct = None
+    if args.sq_algo != "direct" and rank == 0:
+        sqx = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=SQ["n_points"], L0=[Ls] * 3, q_max=SQ["q_max"],
+                           algo="direct")
+        sqx.push(sq_dev[:1], n_frames=1)
+        ctx.synchronize()
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        sqx.push(sq_dev[:1], n_frames=1)
+        ctx.synchronize()
+        ms, _ = sqx.last_push_stats()
+        ach = float(nq) * N_PART / (ms * 1e-3)
+        pk = ctx.probe_rate("mufu_sincos_pairs")
+        direct = {"bound": "sfu", "kernel": "sq_lattice_direct", "achieved": ach / 1e9, "peak": pk / 1e9,
+                  "unit": "G(q,particle) terms/s", "frac": ach / pk, "frames_per_s": 1e3 / ms,
+                  "peak_source": "measured in this run: MUFU.SIN+MUFU.COS pairs/s (mdc_probe_rate)"}
+        sqx.close()
+
     # the once-per-run exchange step: all-reduce of the accumulators over NVLink (outside the timed steps)
     if world > 1:
         from mdcraft_b200 import distributed as mdist
@@ -305,6 +325,8 @@ def run_native(args, rank, world):
         terms = float(nq) * N_PART * F * args.steps           # per rank
         achieved = terms / (sq_ms * 1e-3)
         sm = ctx.info()["sm_count"]
+        # DRAM bytes per launch of the dominant kernel from one `ncu --set full` capture (profiles/*_r01.txt)
+        traffic = 5.8e7 if args.sq_algo == "direct" else 6.8e8
         if args.sq_algo == "direct":
             kernel, bound = "sq_lattice_direct", "sfu"
             peak = ctx.probe_rate("mufu_sincos_pairs")        # measured on this box, this run
@@ -313,7 +335,8 @@ def run_native(args, rank, world):
         else:
             kernel, bound = "sq_lattice_factored", "fp32"
             peak = ctx.probe_rate("ffma") / 4.0               # 4 FP32 FMAs (2 packed FFMA2) per term
-            peak_src = f"measured in this run: FFMA/s / 4 (mdc_probe_rate); nominal {sm} SMs x 128 FMA/clk / 4"
+            peak_src = (f"measured in this run: FFMA/s / 4 (mdc_probe_rate); nominal {sm} SMs x 128 FMA/clk / 4; "
+                        f"FFMA2 in this kernel's operand pattern sustains {ctx.probe_rate('ffma2_loop') / 2e9:.0f} G terms/s")
             algorithmic = "one complex FMA = 4 FP32 FMAs (2 x fma.rn.f32x2) per term; 56 table phasors per 4096 terms"
         pairs = 0.5 * N_PART * (N_PART - 1) * F * args.steps
         line = {
@@ -327,10 +350,11 @@ def run_native(args, rank, world):
             "gpu_launches": launches,
             "roofline": {
                 "bound": bound, "kernel": kernel, "achieved": achieved / 1e9, "peak": peak / 1e9,
-                "unit": "G(q,particle) terms/s", "frac": achieved / peak, "traffic": None,
+                "unit": "G(q,particle) terms/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic": algorithmic,
             },
             "sq_algo": args.sq_algo,
+            "roofline_sfu_direct": direct,
             "sq_frames_per_s": F * args.steps / (sq_ms * 1e-3),
             "sq_default_grid_frames_per_s": sq_default_fps,
             "gr_frames_per_s": F * args.steps / (gr_ms * 1e-3),

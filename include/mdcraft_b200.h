@@ -196,8 +196,9 @@ int  mdc_rdf_last_push_stats(mdc_rdf_plan *plan, float *kernel_ms, int *n_launch
  * 2 = DFMA, 3 = F2F.F64.F32, 4 = shared-memory atomics (spread addresses),
  * 5 = IMAD, 6 = FFMA2 (packed, 2 FMAs each), 7 = ALU (LOP3 + IADD3), 8 = I2F,
  * 9 / 10 = histogram-like shared atomics with / without the atomic,
- * 11 = FFMA2 with scalar x pair operands.  Returns operations per second over
- * the whole GPU.
+ * 11 = FFMA2 with scalar x pair operands, 12 / 13 = FFMA2 in the operand pattern of
+ * the factored S(q) loop (kernel order / grouped by pair operand).  Returns
+ * operations per second over the whole GPU.
  */
 int  mdc_probe_rate(mdc_ctx *ctx, int which, double *ops_per_s);
 

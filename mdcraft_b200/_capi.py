@@ -35,7 +35,7 @@ SQ_ALGOS = {"auto": SQ_ALGO_AUTO, "direct": SQ_ALGO_DIRECT, "factored": SQ_ALGO_
 
 PROBES = {
     "ffma": 0, "mufu_sincos_pairs": 1, "dfma": 2, "f2f_f64_f32": 3, "atoms_spread": 4, "imad": 5,
-    "ffma2": 6, "alu": 7, "i2f": 8, "atoms_hist": 9, "atoms_hist_base": 10, "ffma2_scalar": 11,
+    "ffma2": 6, "alu": 7, "i2f": 8, "atoms_hist": 9, "atoms_hist_base": 10, "ffma2_scalar": 11, "ffma2_loop": 12, "ffma2_loop_grouped": 13,
 }
 
 

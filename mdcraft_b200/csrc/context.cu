@@ -194,6 +194,69 @@ __global__ void probe_ffma2_scalar(float2 *out, float a, float b)
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// packed FMAs in the exact operand pattern of sq_lattice_factored's inner loop: 16 accumulator pairs,
+// 4 register-pair operands (W0, W1, V0, V1) and 16 scalar operands per "particle"; ORDER selects the
+// instruction order (0: as in the kernel, 1: grouped by pair operand)
+template <int ORDER>
+__global__ void probe_ffma2_loop(float2 *out, float a, float b)
+{
+    unsigned long long acc[2][8], w[2], v[2];
+    float z[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) z[k] = a * (k + 1) + threadIdx.x * 1e-6f;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(w[0]) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(w[1]) : "f"(b), "f"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v[0]) : "f"(-b), "f"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v[1]) : "f"(-a), "f"(b));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[0][k] = acc[1][k] = 0ull;
+    for (int i = 0; i < PROBE_ITER / 4; ++i) {
+        if (ORDER == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                unsigned long long zr0, zi0, zr1, zi1;
+                asm("mov.b64 %0, {%1, %1};" : "=l"(zr0) : "f"(z[2 * c]));
+                asm("mov.b64 %0, {%1, %1};" : "=l"(zi0) : "f"(z[2 * c + 1]));
+                asm("mov.b64 %0, {%1, %1};" : "=l"(zr1) : "f"(z[2 * c + 2]));
+                asm("mov.b64 %0, {%1, %1};" : "=l"(zi1) : "f"(z[2 * c + 3]));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[0][c]) : "l"(zr0), "l"(w[0]));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[1][c]) : "l"(zr0), "l"(w[1]));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[0][c + 1]) : "l"(zr1), "l"(w[0]));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[1][c + 1]) : "l"(zr1), "l"(w[1]));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[0][c]) : "l"(zi0), "l"(v[0]));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[1][c]) : "l"(zi0), "l"(v[1]));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[0][c + 1]) : "l"(zi1), "l"(v[0]));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[1][c + 1]) : "l"(zi1), "l"(v[1]));
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    unsigned long long zr;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(zr) : "f"(z[2 * c]));
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[h][c]) : "l"(zr), "l"(w[h]));
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    unsigned long long zi;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(zi) : "f"(z[2 * c + 1]));
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[h][c]) : "l"(zi), "l"(v[h]));
+                }
+            }
+        }
+    }
+    float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[0][k] ^ acc[1][k]));
+        r.x += lo;
+        r.y += hi;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 __global__ void probe_mufu(float *out, float a)
 {
     float x0 = threadIdx.x * 1e-3f, x1 = x0 + .1f, x2 = x0 + .2f, x3 = x0 + .3f;
@@ -414,6 +477,12 @@ extern "C" int mdc_probe_rate(mdc_ctx *ctx, int which, double *ops_per_s)
         break;
     case 11:  // packed FMA, scalar x pair operands
         rc = time_probe(ctx, [&](int b) { probe_ffma2_scalar<<<b, PROBE_THREADS>>>((float2 *)o, 1.0001f, 0.5f); }, per8, ops_per_s);
+        break;
+    case 12:  // packed FMAs, kernel operand pattern and order
+        rc = time_probe(ctx, [&](int b) { probe_ffma2_loop<0><<<b, PROBE_THREADS>>>((float2 *)o, 1.0001f, 0.5f); }, per8, ops_per_s);
+        break;
+    case 13:  // packed FMAs, kernel operand pattern, grouped by pair operand
+        rc = time_probe(ctx, [&](int b) { probe_ffma2_loop<1><<<b, PROBE_THREADS>>>((float2 *)o, 1.0001f, 0.5f); }, per8, ops_per_s);
         break;
     default:
         rc = fail(MDC_ERR_INVALID, "mdc_probe_rate: unknown probe");
