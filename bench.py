@@ -355,6 +355,16 @@ def run_native(args, rank, world):
             },
             "sq_algo": args.sq_algo,
             "roofline_sfu_direct": direct,
+            # g(r): the filter kernel issues ~24 instructions per pair-distance (SASS count, profiles/rdf_fast_r01.txt);
+            # its ceiling is the issue rate, 4 schedulers x 32 lanes per SM per clock
+            "roofline_gr": {
+                "bound": "issue", "kernel": "rdf_pairs_fast", "achieved": pairs / (gr_ms * 1e-3) / 1e9,
+                "peak": sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 24.0 / 1e9, "unit": "G pair-distances/s",
+                "frac": pairs / (gr_ms * 1e-3) / (sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 24.0),
+                "traffic": 3.1e6,
+                "algorithmic": "24 issue slots + 1 SFU op (sqrt) + 0.52 shared-memory atomics per pair; "
+                               "24 B of positions per particle per frame (f32 + u32 fixed point)",
+            },
             "sq_frames_per_s": F * args.steps / (sq_ms * 1e-3),
             "sq_default_grid_frames_per_s": sq_default_fps,
             "gr_frames_per_s": F * args.steps / (gr_ms * 1e-3),

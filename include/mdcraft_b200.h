@@ -134,6 +134,31 @@ int  mdc_delta_fourier_transform_sum(mdc_ctx *ctx, const double *qs, int64_t nq,
                                      const double *rs, int64_t n,
                                      int precision, double *rho_out);
 
+/* ---- F(q, t): IntermediateScatteringFunction ------------------------------- */
+
+/*
+ * Coherent and (optionally) incoherent intermediate scattering functions,
+ * structure.py:2198-2835.  Same wavevector / group / pair
+ * arguments as mdc_sq_plan_create; the handle IS an mdc_sq_plan (wavevector
+ * queries work on it).  Frames must be pushed in time order:
+ *   cisf[lag, p, q] += Re(rho_j(t - lag) conj rho_k(t)) (+ j <-> k for cross pairs)
+ *   iisf[lag, g, q] += Re sum_i exp(i q . (r_i(t) - r_i(t - lag)))   for pairs (g, g)
+ * over a ring of the last n_lags frames kept on the device.  iisf has one row per
+ * group (one row when pairs = {(-1, -1)}).  Frames are not independent, so this
+ * plan does not shard across GPUs.
+ */
+int  mdc_isf_plan_create(mdc_ctx *ctx,
+                         int n_points, const double L0[3], double q_max,
+                         const double *q_explicit, int64_t n_explicit,
+                         int n_groups, const int64_t *group_sizes,
+                         int n_pairs, const int *pairs,
+                         int n_lags, int incoherent,
+                         int precision, int algo,
+                         mdc_sq_plan **out);
+int  mdc_isf_push(mdc_sq_plan *plan, const float *pos, int n_frames, int on_device);
+/* Un-normalised sums: cisf f64 (n_lags, n_pairs, Nq); iisf f64 (n_lags, n_rows, Nq) or NULL. */
+int  mdc_isf_read(mdc_sq_plan *plan, double *cisf_out, double *iisf_out, int64_t *n_frames_out);
+
 /* ---- g(r): RadialDistributionFunction ------------------------------------ */
 
 /*

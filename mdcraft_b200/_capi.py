@@ -75,6 +75,13 @@ SIGNATURES = {
     "mdc_sq_accum_ptr": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
     "mdc_sq_set_frames": (c_int, [c_void_p, c_int64]),
     "mdc_delta_fourier_transform_sum": (c_int, [c_void_p, _dp, c_int64, _dp, c_int64, c_int, _dp]),
+    "mdc_isf_plan_create": (
+        c_int,
+        [c_void_p, c_int, _dp, c_double, _dp, c_int64, c_int, _lp, c_int, _ip, c_int, c_int, c_int, c_int,
+         POINTER(c_void_p)],
+    ),
+    "mdc_isf_push": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "mdc_isf_read": (c_int, [c_void_p, _dp, _dp, _lp]),
     "mdc_rdf_plan_create": (
         c_int,
         [c_void_p, c_int, c_double, c_double, c_int64, c_int64, c_int, c_int64, c_int64, POINTER(c_void_p)],
@@ -328,6 +335,65 @@ class SqPlan:
         ms, nl = c_float(), c_int()
         _check(lib().mdc_sq_last_push_stats(self._h, byref(ms), byref(nl)))
         return ms.value, nl.value
+
+
+class IsfPlan(SqPlan):
+    """``mdc_isf_plan_create``: coherent / incoherent intermediate scattering functions over a ring of lags."""
+
+    def __init__(
+        self,
+        ctx: Context,
+        group_sizes: Sequence[int],
+        pairs: Sequence[Sequence[Optional[int]]],
+        n_lags: int,
+        *,
+        incoherent: bool = False,
+        n_points: int = 0,
+        L0: Optional[Sequence[float]] = None,
+        q_max: Optional[float] = None,
+        wavevectors: Optional[np.ndarray] = None,
+        precision: str = "fp32",
+        algo: str = "auto",
+    ):
+        self.ctx = ctx
+        self._h = c_void_p()
+        gs = np.ascontiguousarray(group_sizes, dtype=np.int64)
+        pr = np.ascontiguousarray(
+            [(-1, -1) if p[0] is None else (int(p[0]), int(p[1])) for p in pairs], dtype=np.int32
+        ).reshape(-1, 2)
+        L = np.zeros(3) if L0 is None else np.ascontiguousarray(L0, dtype=np.float64)
+        if wavevectors is not None:
+            wv = np.ascontiguousarray(wavevectors, dtype=np.float64).reshape(-1, 3)
+            n_exp, wv_p = wv.shape[0], _as(wv, _dp)
+        else:
+            n_exp, wv_p = 0, None
+        _check(lib().mdc_isf_plan_create(
+            ctx._h, int(n_points), _as(L, _dp), -1.0 if q_max is None else float(q_max), wv_p, n_exp,
+            gs.shape[0], _as(gs, _lp), pr.shape[0], _as(pr, _ip), int(n_lags), 1 if incoherent else 0,
+            PRECISIONS[precision], SQ_ALGOS[algo], byref(self._h)))
+        self.n_particles = int(gs.sum())
+        self.n_pairs = pr.shape[0]
+        self.n_lags = int(n_lags)
+        self.incoherent = bool(incoherent)
+        self.n_rows = 1 if pr[0, 0] < 0 else gs.shape[0]
+        self.n_wavevectors = int(lib().mdc_sq_num_wavevectors(self._h))
+
+    def push(self, pos, n_frames: Optional[int] = None) -> None:
+        """Frames must arrive in time order."""
+        ptr, on_dev, keep = _buffer(pos)
+        if n_frames is None:
+            n_frames = 1 if len(keep.shape) == 2 else int(keep.shape[0])
+        if int(np.prod(keep.shape)) != n_frames * self.n_particles * 3:
+            raise ValueError("positions have the wrong number of elements")
+        _check(lib().mdc_isf_push(self._h, ptr, int(n_frames), on_dev))
+
+    def read(self):
+        """Un-normalised ``cisf (n_lags, n_pairs, Nq)``, ``iisf (n_lags, n_rows, Nq)`` or ``None``, frames."""
+        cisf = np.empty((self.n_lags, self.n_pairs, self.n_wavevectors), dtype=np.float64)
+        iisf = np.empty((self.n_lags, self.n_rows, self.n_wavevectors), dtype=np.float64) if self.incoherent else None
+        nf = c_int64()
+        _check(lib().mdc_isf_read(self._h, _as(cisf, _dp), None if iisf is None else _as(iisf, _dp), byref(nf)))
+        return cisf, iisf, nf.value
 
 
 class RdfPlan:

@@ -8,6 +8,7 @@ B200-native drop-ins for the two per-frame structure analyses of
 
 * :class:`RadialDistributionFunction` — ``structure.py:491-1201``
 * :class:`StructureFactor` — ``structure.py:1510-2017``
+* :class:`IntermediateScatteringFunction` — ``structure.py:2198-2835`` ("next" rank 1)
 
 and the two pure functions below them, :func:`radial_histogram`
 (``structure.py:34-131``) and :func:`delta_fourier_transform_sum`
@@ -702,4 +703,114 @@ class StructureFactor(NumbaAnalysisBase):
             order = np.argsort(self.results.wavenumbers)
             self.results.wavenumbers = self.results.wavenumbers[order]
             self.results.ssf = self.results.ssf[:, order]
+        self._stage = None
+
+
+def _combine_last_axis(values: np.ndarray, wavenumbers: np.ndarray, unique_q: np.ndarray) -> np.ndarray:
+    """``combine_equal_wavenumbers`` over the last axis of a ``(lags, rows, Nq)`` array."""
+    shape = values.shape
+    flat = combine_equal_wavenumbers(values.reshape(-1, shape[-1]), wavenumbers, unique_q)
+    return flat.reshape(shape[:-1] + (unique_q.shape[0],))
+
+
+class IntermediateScatteringFunction(StructureFactor):
+    r"""
+    Coherent and incoherent intermediate scattering functions :math:`F(q, t)` and :math:`F_s(q, t)`, drop-in for
+    ``mdcraft.analysis.structure.IntermediateScatteringFunction`` (``structure.py:2198-2835``).
+
+    ``results``: ``pairs``, ``times (n_lags,)``, ``wavenumbers``, ``cisf (n_lags, n_pairs, N_unique or Nq)`` and, with
+    ``incoherent=True``, ``iisf (n_lags, n_groups, ...)``; ``units``.
+
+    The reference keeps a sliding window of the last ``n_lags`` frames because storing every ``exp(i q . r)`` is
+    prohibitive (``structure.py:2679-2685``); here the window (densities and, for the self part, positions) lives
+    on the device.  Frames are not independent, so this analysis does not shard across GPUs.
+    """
+
+    def __init__(
+        self,
+        groups,
+        groupings: Union[str, tuple] = "atoms",
+        *,
+        mode: str = None,
+        form: str = "exp",
+        dimensions=None,
+        dt=None,
+        n_points: int = 32,
+        n_surfaces: int = None,
+        n_surface_points: int = 8,
+        q_max=None,
+        wavevectors: np.ndarray = None,
+        sort: bool = True,
+        unique: bool = True,
+        n_lags: int = None,
+        incoherent: bool = False,
+        parallel: bool = False,
+        verbose: bool = True,
+        **kwargs,
+    ) -> None:
+        self._isf_n_lags = n_lags
+        self._incoherent = incoherent
+        super().__init__(
+            groups, groupings, mode=mode, form=form, dimensions=dimensions, n_points=n_points, n_surfaces=n_surfaces,
+            n_surface_points=n_surface_points, q_max=q_max, wavevectors=wavevectors, sort=sort, unique=unique,
+            parallel=parallel, verbose=verbose, **kwargs,
+        )
+        self._dt = strip_unit(dt, "ps")[0] or self._trajectory.dt
+        self._n_lags = n_lags
+
+    def _make_plan(self) -> None:
+        # the ISF plan needs n_lags, which is only final in _prepare; until then a plain S(q) plan supplies the grid
+        super()._make_plan()
+
+    def _prepare(self) -> None:
+        self._n_lags = int(min(self._isf_n_lags or np.inf, self.n_frames))
+        if hasattr(self._sliced_trajectory, "frames"):
+            dfs = np.diff(self._sliced_trajectory.frames)
+            if (df := dfs[0]) <= 0 or not np.allclose(dfs, df):
+                raise ValueError("The selected frames must be evenly spaced and proceed forward in time.")
+        elif (df := self.step) <= 0:
+            raise ValueError("The analysis must proceed forward in time.")
+
+        self.results.pairs = self._pairs()
+        if self._plan is not None:
+            self._plan.close()
+        n_points, L0 = self._lattice if self._lattice is not None else (0, None)
+        explicit = self._explicit if self._explicit is not None and len(self._explicit) else None
+        self._plan = _capi.IsfPlan(
+            _context(self._device), self._Ns, self.results.pairs, self._n_lags, incoherent=self._incoherent,
+            n_points=n_points, L0=L0, q_max=self._q_max, wavevectors=explicit, precision=self._precision,
+            algo=self._algorithm,
+        )
+        self._stage = _FrameBlock(self._frame_block, self._N)
+        self._frames_seen = 0
+        self.results.times = df * self._dt * np.arange(self._n_lags)
+        self.results.wavenumbers = np.unique(self._wavenumbers.round(11)) if self._unique else self._wavenumbers
+        self.results.units = Hash({
+            "times": _ureg.picosecond if _ureg is not None else "picosecond",
+            "wavenumbers": _ANGSTROM**-1 if _ureg is not None else "1 / angstrom",
+        })
+
+    def _conclude(self) -> None:
+        if self._distributed:
+            raise ValueError("IntermediateScatteringFunction frames are not independent: it cannot be frame-sharded.")
+        self._flush()
+        cisf, iisf, _ = self._plan.read()
+        # structure.py:2790-2828
+        norm = self._N * np.arange(self.n_frames, self.n_frames - self._n_lags, -1)[:, None, None]
+        cisf /= norm
+        if self._incoherent:
+            iisf /= norm
+        if self._unique:
+            cisf = _combine_last_axis(cisf, self._wavenumbers, self.results.wavenumbers)
+            if self._incoherent:
+                iisf = _combine_last_axis(iisf, self._wavenumbers, self.results.wavenumbers)
+        if self._sort:
+            order = np.argsort(self.results.wavenumbers)
+            self.results.wavenumbers = self.results.wavenumbers[order]
+            cisf = cisf[:, :, order]
+            if self._incoherent:
+                iisf = iisf[:, :, order]
+        self.results.cisf = cisf
+        if self._incoherent:
+            self.results.iisf = iisf
         self._stage = None

@@ -580,6 +580,103 @@ __global__ void sq_pair_accum(double2 *__restrict__ part, int F, int n_sets, int
 }
 
 // ------------------------------------------------------------------------------------------
+// intermediate scattering function (structure.py:2198-2835): a ring of the last n_lags densities and,
+// for the self part, of the last n_lags position sets
+// ------------------------------------------------------------------------------------------
+
+// rho[(f * n_sets + s) * nq + q] = sum_p part[f, s, p, q] - N_s * dc   (same reduction as sq_pair_accum)
+__global__ void sq_reduce_rho(const double2 *__restrict__ part, int F, int n_sets, int P, int64_t nq,
+                              const int2 *__restrict__ sets, double dc_cos, double dc_sin, int64_t dc_first,
+                              double2 *__restrict__ rho)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    if (q < dc_first) dc_cos = dc_sin = 0.0;
+    for (int fs = 0; fs < F * n_sets; ++fs) {
+        const double2 *base = part + (int64_t)fs * P * nq + q;
+        double re = 0.0, im = 0.0;
+        for (int p = 0; p < P; ++p) {
+            const double2 v = base[(int64_t)p * nq];
+            re += v.x;
+            im += v.y;
+        }
+        const int2 set = sets[fs % n_sets];
+        const double n = (double)(set.y - set.x);
+        rho[(int64_t)fs * nq + q] = make_double2(re - n * dc_cos, im - n * dc_sin);
+    }
+}
+
+// cisf[lag, pair, q] += Re(rho_j(t - lag) conj rho_k(t)) (+ the j <-> k term for cross pairs), structure.py:2694-2731
+__global__ void isf_coherent(const double2 *__restrict__ ring, int n_lags, int n_sets, int64_t nq, int cur,
+                             int n_valid, const int2 *__restrict__ pairs, int n_pairs, double *__restrict__ cisf)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const double2 *now = ring + (int64_t)cur * n_sets * nq + q;
+    for (int lag = 0; lag < n_valid; ++lag) {
+        int s = cur - lag;
+        if (s < 0) s += n_lags;
+        const double2 *then = ring + (int64_t)s * n_sets * nq + q;
+        for (int pr = 0; pr < n_pairs; ++pr) {
+            const int2 jk = pairs[pr];
+            const double2 aj = then[(int64_t)jk.x * nq], bk = now[(int64_t)jk.y * nq];
+            double v = aj.x * bk.x + aj.y * bk.y;
+            if (jk.x != jk.y) {
+                const double2 ak = then[(int64_t)jk.y * nq], bj = now[(int64_t)jk.x * nq];
+                v += ak.x * bj.x + ak.y * bj.y;
+            }
+            cisf[((int64_t)lag * n_pairs + pr) * nq + q] += v;
+        }
+    }
+}
+
+// displacement "positions" for L consecutive lags: r(t) - r(t - lag).  On the lattice the difference of the
+// 32-bit box fractions (mod 2^32) is exact and wrapping is irrelevant because q is commensurate with the box.
+__global__ void isf_disp_fix(const uint32_t *__restrict__ ring, int n_lags, int64_t N3, int cur, int lag0, int L,
+                             uint32_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N3 * L) return;
+    const int l = (int)(i / N3);
+    const int64_t j = i - (int64_t)l * N3;
+    int s = cur - (lag0 + l);
+    if (s < 0) s += n_lags;
+    out[i] = ring[(int64_t)cur * N3 + j] - ring[(int64_t)s * N3 + j];
+}
+
+__global__ void isf_disp_f64(const double *__restrict__ ring, int n_lags, int64_t N3, int cur, int lag0, int L,
+                             double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N3 * L) return;
+    const int l = (int)(i / N3);
+    const int64_t j = i - (int64_t)l * N3;
+    int s = cur - (lag0 + l);
+    if (s < 0) s += n_lags;
+    out[i] = ring[(int64_t)cur * N3 + j] - ring[(int64_t)s * N3 + j];
+}
+
+// iisf[lag0 + l, slot(s), q] += Re sum_j exp(i q . (r_j(t) - r_j(t - lag)))   (structure.py:2699-2725)
+__global__ void isf_incoherent_accum(const double2 *__restrict__ part, int L, int n_sets, int P, int64_t nq,
+                                     const int2 *__restrict__ sets, const int *__restrict__ inc_slot, int n_inc,
+                                     int lag0, double dc_cos, int64_t dc_first, double *__restrict__ iisf)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    if (q < dc_first) dc_cos = 0.0;
+    for (int l = 0; l < L; ++l)
+        for (int s = 0; s < n_sets; ++s) {
+            const int slot = inc_slot[s];
+            if (slot < 0) continue;
+            const double2 *base = part + ((int64_t)l * n_sets + s) * P * nq + q;
+            double re = 0.0;
+            for (int p = 0; p < P; ++p) re += base[(int64_t)p * nq].x;
+            const int2 set = sets[s];
+            iisf[((int64_t)(lag0 + l) * n_inc + slot) * nq + q] += re - (double)(set.y - set.x) * dc_cos;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
 // accuracy probe of sincos_phase over all 2^23 distinct phases
 // ------------------------------------------------------------------------------------------
 __global__ void probe_sincos_kernel(int variant, double *acc /* [sum ec, sum es, sum e^2, max|e| bits] */)
@@ -673,6 +770,18 @@ struct mdc_sq_plan {
 
     int64_t n_patches = 0;
     int nxp = 0, nyp = 0, nzp = 0;
+    // intermediate scattering function (mdc_isf_*)
+    bool isf = false, incoherent = false;
+    int n_lags = 0, n_inc = 0;
+    DevBuf<double2> rho_ring;                  // (n_lags, n_sets, nq)
+    DevBuf<uint32_t> fix_ring, dfix;           // (n_lags, 3, N), (fblk, 3, N)
+    DevBuf<double> posd_ring, dposd;           // same shapes, explicit wavevectors / FP64 mode
+    DevBuf<float2> dtabx, dtabz;
+    DevBuf<float4> dtaby;
+    DevBuf<double> cisf, iisf;                 // (n_lags, n_pairs, nq), (n_lags, n_inc, nq)
+    DevBuf<int> inc_slot;                      // set -> row of iisf (-1: none)
+    std::vector<int2> pair_sets;
+    int64_t isf_in_push = 0;                   // frames of the current push already processed
     DevBuf<double2> part;
     DevBuf<float> raw[2];
     DevBuf<uint32_t> fix[2];
@@ -697,6 +806,17 @@ void plan_free(mdc_sq_plan *p)
     p->items.release();
     p->patches.release();
     p->entries.release();
+    p->rho_ring.release();
+    p->fix_ring.release();
+    p->dfix.release();
+    p->posd_ring.release();
+    p->dposd.release();
+    p->dtabx.release();
+    p->dtaby.release();
+    p->dtabz.release();
+    p->cisf.release();
+    p->iisf.release();
+    p->inc_slot.release();
     p->row_cnt.release();
     p->row_qoff.release();
     p->part.release();
@@ -779,6 +899,7 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
     }
     p->n_sets = (int)p->sets.size();
     p->n_pairs = n_pairs;
+    p->pair_sets = hp;
 
     int rc = p->st.init(ctx);
     if (rc != MDC_OK) {
@@ -975,6 +1096,107 @@ int configure(mdc_sq_plan *p, int n_frames_hint)
     return MDC_OK;
 }
 
+struct DensityIn {
+    const uint32_t *fix;
+    const float2 *tabx;
+    const float4 *taby;
+    const float2 *tabz;
+    const double *posd;
+};
+
+// density kernels of F frames (or pseudo-frames) into p->part, on the compute stream
+void launch_density(mdc_sq_plan *p, const DensityIn &in, int F, int *launches)
+{
+    cudaStream_t sk = p->st.compute;
+    const unsigned gz = (unsigned)(F * p->n_sets);
+    if (p->lattice_fast) {
+        if (p->factored) {
+            dim3 g((unsigned)p->n_patches, (unsigned)p->P, gz);
+            sq_lattice_factored<<<g, FC_THREADS, FC_SMEM, sk>>>(p->patches.p, p->entries.p, in.tabx, in.taby, in.tabz,
+                                                               p->nxp, p->nyp, p->nzp, p->N, p->d_sets.p, p->n_sets,
+                                                               p->P, p->n_points, p->row_cnt.p, p->row_qoff.p, p->nq,
+                                                               p->part.p);
+        } else {
+            dim3 g((unsigned)ceil_div(p->n_items, SQ_THREADS), (unsigned)p->P, gz);
+            sq_lattice_direct<<<g, SQ_THREADS, 0, sk>>>(p->items.p, p->n_items, in.fix, p->N, p->d_sets.p, p->n_sets,
+                                                       p->P, p->nq, p->part.p);
+        }
+        ++*launches;
+        if (p->n_exp > 0) {
+            dim3 ge((unsigned)ceil_div(p->n_exp, SQ_THREADS), (unsigned)p->P, gz);
+            sq_explicit_f32<<<ge, SQ_THREADS, 0, sk>>>(p->q.p, p->n_lat, p->n_exp, in.posd, p->N, p->d_sets.p,
+                                                      p->n_sets, p->P, p->nq, p->part.p);
+            ++*launches;
+        }
+    } else {
+        dim3 g((unsigned)ceil_div(p->nq, SQ_THREADS), (unsigned)p->P, gz);
+        if (p->precision == MDC_PRECISION_FP64)
+            sq_explicit_f64<<<g, SQ_THREADS, 0, sk>>>(p->q.p, 0, p->nq, in.posd, p->N, p->d_sets.p, p->n_sets, p->P,
+                                                      p->nq, p->part.p);
+        else
+            sq_explicit_f32<<<g, SQ_THREADS, 0, sk>>>(p->q.p, 0, p->nq, in.posd, p->N, p->d_sets.p, p->n_sets, p->P,
+                                                      p->nq, p->part.p);
+        ++*launches;
+    }
+}
+
+// the ISF tail of one frame whose partial densities sit in p->part (F == 1): structure.py:2668-2731
+int isf_frame(mdc_sq_plan *p, int slot, int *launches)
+{
+    cudaStream_t sk = p->st.compute;
+    const int64_t t = p->n_frames + p->isf_in_push;   // index of this frame in the run
+    const int cur = (int)(t % p->n_lags);
+    const int n_valid = (int)std::min<int64_t>(p->n_lags, t + 1);
+    const unsigned qb = (unsigned)ceil_div(p->nq, 256);
+    const int64_t dc_first = p->factored ? p->n_lat : 0;
+    sq_reduce_rho<<<qb, 256, 0, sk>>>(p->part.p, 1, p->n_sets, p->P, p->nq, p->d_sets.p, p->dc[0], p->dc[1], dc_first,
+                                     p->rho_ring.p + (size_t)cur * p->n_sets * p->nq);
+    isf_coherent<<<qb, 256, 0, sk>>>(p->rho_ring.p, p->n_lags, p->n_sets, p->nq, cur, n_valid, p->d_pairs.p, p->n_pairs,
+                                    p->cisf.p);
+    *launches += 2;
+    if (p->incoherent) {
+        const int64_t N3 = 3 * p->N;
+        const bool need_posd = !p->lattice_fast || p->n_exp > 0;
+        if (p->lattice_fast)
+            MDC_CUDA(cudaMemcpyAsync(p->fix_ring.p + (size_t)cur * N3, p->fix[slot].p, N3 * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToDevice, sk));
+        if (need_posd)
+            MDC_CUDA(cudaMemcpyAsync(p->posd_ring.p + (size_t)cur * N3, p->posd[slot].p, N3 * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, sk));
+        for (int lag0 = 0; lag0 < n_valid; lag0 += p->fblk) {
+            const int L = std::min(p->fblk, n_valid - lag0);
+            const unsigned db = (unsigned)ceil_div(N3 * L, 256);
+            DensityIn in = {nullptr, nullptr, nullptr, nullptr, nullptr};
+            if (p->lattice_fast) {
+                isf_disp_fix<<<db, 256, 0, sk>>>(p->fix_ring.p, p->n_lags, N3, cur, lag0, L, p->dfix.p);
+                ++*launches;
+                in.fix = p->dfix.p;
+                if (p->factored) {
+                    sq_prep_tables<<<(unsigned)(L * p->N), 128, 0, sk>>>(p->dfix.p, p->N, (int64_t)L * p->N, p->n_points,
+                                                                        p->nxp, p->nyp, p->nzp, p->dtabx.p, p->dtaby.p,
+                                                                        p->dtabz.p);
+                    ++*launches;
+                    in.tabx = p->dtabx.p;
+                    in.taby = p->dtaby.p;
+                    in.tabz = p->dtabz.p;
+                }
+            }
+            if (need_posd) {
+                isf_disp_f64<<<db, 256, 0, sk>>>(p->posd_ring.p, p->n_lags, N3, cur, lag0, L, p->dposd.p);
+                ++*launches;
+                in.posd = p->dposd.p;
+            }
+            launch_density(p, in, L, launches);
+            isf_incoherent_accum<<<qb, 256, 0, sk>>>(p->part.p, L, p->n_sets, p->P, p->nq, p->d_sets.p, p->inc_slot.p,
+                                                    p->n_inc, lag0, p->dc[0], dc_first, p->iisf.p);
+            ++*launches;
+        }
+    }
+    MDC_CUDA(cudaGetLastError());
+    ++p->isf_in_push;
+    return MDC_OK;
+}
+
 int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launches)
 {
     cudaStream_t sc = p->st.copy, sk = p->st.compute;
@@ -998,44 +1220,25 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
     MDC_CUDA(cudaStreamWaitEvent(sk, p->st.staged[slot], 0));
     const int ti = p->st.n_timed < 8 ? p->st.n_timed : -1;
     if (ti >= 0) MDC_CUDA(cudaEventRecord(p->st.k0[ti], sk));
-    const unsigned gz = (unsigned)(F * p->n_sets);
-    if (p->lattice_fast) {
-        if (p->factored) {
-            dim3 g((unsigned)p->n_patches, (unsigned)p->P, gz);
-            sq_lattice_factored<<<g, FC_THREADS, FC_SMEM, sk>>>(p->patches.p, p->entries.p, p->tabx[slot].p, p->taby[slot].p,
-                                                         p->tabz[slot].p, p->nxp, p->nyp, p->nzp, p->N, p->d_sets.p,
-                                                         p->n_sets, p->P, p->n_points, p->row_cnt.p, p->row_qoff.p,
-                                                         p->nq, p->part.p);
-        } else {
-            dim3 g((unsigned)ceil_div(p->n_items, SQ_THREADS), (unsigned)p->P, gz);
-            sq_lattice_direct<<<g, SQ_THREADS, 0, sk>>>(p->items.p, p->n_items, p->fix[slot].p, p->N, p->d_sets.p,
-                                                       p->n_sets, p->P, p->nq, p->part.p);
-        }
-        ++*launches;
-        if (p->n_exp > 0) {
-            dim3 ge((unsigned)ceil_div(p->n_exp, SQ_THREADS), (unsigned)p->P, gz);
-            sq_explicit_f32<<<ge, SQ_THREADS, 0, sk>>>(p->q.p, p->n_lat, p->n_exp, p->posd[slot].p, p->N,
-                                                      p->d_sets.p, p->n_sets, p->P, p->nq, p->part.p);
-            ++*launches;
-        }
-    } else {
-        dim3 g((unsigned)ceil_div(p->nq, SQ_THREADS), (unsigned)p->P, gz);
-        if (p->precision == MDC_PRECISION_FP64)
-            sq_explicit_f64<<<g, SQ_THREADS, 0, sk>>>(p->q.p, 0, p->nq, p->posd[slot].p, p->N, p->d_sets.p,
-                                                      p->n_sets, p->P, p->nq, p->part.p);
-        else
-            sq_explicit_f32<<<g, SQ_THREADS, 0, sk>>>(p->q.p, 0, p->nq, p->posd[slot].p, p->N, p->d_sets.p,
-                                                      p->n_sets, p->P, p->nq, p->part.p);
-        ++*launches;
-    }
+    DensityIn in;
+    in.fix = p->fix[slot].p;
+    in.tabx = p->tabx[slot].p;
+    in.taby = p->taby[slot].p;
+    in.tabz = p->tabz[slot].p;
+    in.posd = p->posd[slot].p;
+    launch_density(p, in, F, launches);
     if (ti >= 0) {
         MDC_CUDA(cudaEventRecord(p->st.k1[ti], sk));
         p->st.n_timed = ti + 1;
     }
-    sq_pair_accum<<<(unsigned)ceil_div(p->nq, 256), 256, 0, sk>>>(p->part.p, F, p->n_sets, p->P, p->nq, p->d_sets.p,
-                                                                 p->d_pairs.p, p->n_pairs, p->dc[0], p->dc[1],
-                                                                 p->factored ? p->n_lat : 0, p->ssf.p);
-    ++*launches;
+    if (p->isf) {
+        MDC_CHECK(isf_frame(p, slot, launches));   // F == 1
+    } else {
+        sq_pair_accum<<<(unsigned)ceil_div(p->nq, 256), 256, 0, sk>>>(p->part.p, F, p->n_sets, p->P, p->nq,
+                                                                     p->d_sets.p, p->d_pairs.p, p->n_pairs, p->dc[0],
+                                                                     p->dc[1], p->factored ? p->n_lat : 0, p->ssf.p);
+        ++*launches;
+    }
     MDC_CUDA(cudaGetLastError());
     MDC_CUDA(cudaEventRecord(p->st.consumed[slot], sk));
     p->st.used[slot] = true;
@@ -1049,11 +1252,13 @@ extern "C" int mdc_sq_push(mdc_sq_plan *p, const float *pos, int n_frames, int o
     if (!p || !pos) return fail(MDC_ERR_INVALID, "mdc_sq_push: NULL argument");
     if (n_frames <= 0) return MDC_OK;
     MDC_CUDA(cudaSetDevice(p->ctx->device));
-    MDC_CHECK(configure(p, n_frames));
+    MDC_CHECK(configure(p, p->isf ? std::min(p->n_lags, 8) : n_frames));
     p->st.n_timed = 0;
+    p->isf_in_push = 0;
     int launches = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += p->fblk) {
-        const int F = std::min(p->fblk, n_frames - f0);
+    const int step = p->isf ? 1 : p->fblk;   // ISF frames are consumed one at a time, in time order
+    for (int f0 = 0; f0 < n_frames; f0 += step) {
+        const int F = std::min(step, n_frames - f0);
         const int slot = p->st.next;
         p->st.next ^= 1;
         // the slot's layout buffers (and `part`, shared by both slots through stream order on
@@ -1092,6 +1297,10 @@ extern "C" int mdc_sq_reset(mdc_sq_plan *p)
     MDC_CUDA(cudaSetDevice(p->ctx->device));
     MDC_CUDA(cudaStreamSynchronize(p->st.compute));
     MDC_CUDA(cudaMemset(p->ssf.p, 0, (size_t)p->nq * p->n_pairs * sizeof(double)));
+    if (p->isf) {
+        MDC_CUDA(cudaMemset(p->cisf.p, 0, (size_t)p->n_lags * p->n_pairs * p->nq * sizeof(double)));
+        if (p->incoherent) MDC_CUDA(cudaMemset(p->iisf.p, 0, (size_t)p->n_lags * p->n_inc * p->nq * sizeof(double)));
+    }
     p->n_frames = 0;
     return MDC_OK;
 }
@@ -1119,6 +1328,80 @@ extern "C" int mdc_sq_last_push_stats(mdc_sq_plan *p, float *kernel_ms, int *n_l
     MDC_CUDA(cudaSetDevice(p->ctx->device));
     if (kernel_ms) MDC_CHECK(p->st.kernel_ms(kernel_ms));
     if (n_launches) *n_launches = p->last_launches;
+    return MDC_OK;
+}
+
+// ---- intermediate scattering function ------------------------------------------------------
+
+extern "C" int mdc_isf_plan_create(mdc_ctx *ctx, int n_points, const double L0[3], double q_max,
+                                   const double *q_explicit, int64_t n_explicit, int n_groups,
+                                   const int64_t *group_sizes, int n_pairs, const int *pairs, int n_lags,
+                                   int incoherent, int precision, int algo, mdc_sq_plan **out)
+{
+    if (n_lags < 1) return fail(MDC_ERR_INVALID, "mdc_isf_plan_create: n_lags must be positive");
+    MDC_CHECK(mdc_sq_plan_create(ctx, n_points, L0, q_max, q_explicit, n_explicit, n_groups, group_sizes, n_pairs,
+                                 pairs, precision, algo, out));
+    mdc_sq_plan *p = *out;
+    *out = nullptr;
+    p->isf = true;
+    p->n_lags = n_lags;
+    p->incoherent = incoherent != 0;
+    // rows of iisf: one per group (mode None: one); a set contributes only if a pair (j, j) references it
+    const bool total = pairs[0] < 0;
+    p->n_inc = total ? 1 : n_groups;
+    std::vector<int> slot(p->n_sets, -1);
+    for (int i = 0; i < n_pairs; ++i)
+        if (pairs[2 * i] == pairs[2 * i + 1]) slot[p->pair_sets[i].x] = total ? 0 : pairs[2 * i];
+    int rc = configure(p, std::min(n_lags, 8));
+    const size_t N3 = (size_t)3 * p->N;
+    if (rc == MDC_OK) rc = p->rho_ring.alloc((size_t)n_lags * p->n_sets * p->nq);
+    if (rc == MDC_OK) rc = p->cisf.alloc((size_t)n_lags * n_pairs * p->nq);
+    if (rc == MDC_OK) rc = p->inc_slot.alloc(p->n_sets);
+    if (rc == MDC_OK && p->incoherent) {
+        rc = p->iisf.alloc((size_t)n_lags * p->n_inc * p->nq);
+        const bool need_posd = !p->lattice_fast || p->n_exp > 0;
+        if (rc == MDC_OK && p->lattice_fast) rc = p->fix_ring.alloc((size_t)n_lags * N3);
+        if (rc == MDC_OK && p->lattice_fast) rc = p->dfix.alloc((size_t)p->fblk * N3);
+        if (rc == MDC_OK && need_posd) rc = p->posd_ring.alloc((size_t)n_lags * N3);
+        if (rc == MDC_OK && need_posd) rc = p->dposd.alloc((size_t)p->fblk * N3);
+        if (rc == MDC_OK && p->factored) rc = p->dtabx.alloc((size_t)p->fblk * p->N * p->nxp);
+        if (rc == MDC_OK && p->factored) rc = p->dtaby.alloc((size_t)p->fblk * p->N * p->nyp);
+        if (rc == MDC_OK && p->factored) rc = p->dtabz.alloc((size_t)p->fblk * p->N * p->nzp);
+    }
+    cudaError_t e = cudaSuccess;
+    if (rc == MDC_OK) e = cudaMemcpy(p->inc_slot.p, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (rc == MDC_OK && e == cudaSuccess) e = cudaMemset(p->cisf.p, 0, (size_t)n_lags * n_pairs * p->nq * sizeof(double));
+    if (rc == MDC_OK && e == cudaSuccess && p->incoherent)
+        e = cudaMemset(p->iisf.p, 0, (size_t)n_lags * p->n_inc * p->nq * sizeof(double));
+    if (rc == MDC_OK && e != cudaSuccess) rc = fail(MDC_ERR_CUDA, std::string("mdc_isf_plan_create: ") + cudaGetErrorString(e));
+    if (rc != MDC_OK) {
+        plan_free(p);
+        return rc;
+    }
+    *out = p;
+    return MDC_OK;
+}
+
+extern "C" int mdc_isf_push(mdc_sq_plan *p, const float *pos, int n_frames, int on_device)
+{
+    if (!p || !p->isf) return fail(MDC_ERR_INVALID, "mdc_isf_push: not an ISF plan");
+    return mdc_sq_push(p, pos, n_frames, on_device);
+}
+
+extern "C" int mdc_isf_read(mdc_sq_plan *p, double *cisf_out, double *iisf_out, int64_t *n_frames_out)
+{
+    if (!p || !p->isf) return fail(MDC_ERR_INVALID, "mdc_isf_read: not an ISF plan");
+    MDC_CUDA(cudaSetDevice(p->ctx->device));
+    MDC_CUDA(cudaStreamSynchronize(p->st.compute));
+    if (cisf_out)
+        MDC_CUDA(cudaMemcpy(cisf_out, p->cisf.p, (size_t)p->n_lags * p->n_pairs * p->nq * sizeof(double),
+                            cudaMemcpyDeviceToHost));
+    if (iisf_out) {
+        if (!p->incoherent) return fail(MDC_ERR_INVALID, "mdc_isf_read: plan was created without the incoherent part");
+        MDC_CUDA(cudaMemcpy(iisf_out, p->iisf.p, (size_t)p->n_lags * p->n_inc * p->nq * sizeof(double),
+                            cudaMemcpyDeviceToHost));
+    }
+    if (n_frames_out) *n_frames_out = p->n_frames;
     return MDC_OK;
 }
 

@@ -274,6 +274,72 @@ def structure_factor(
     return {"pairs": pairs, "ssf": ssf, "wavenumbers": wn_out, "wavevectors": wv, "ssf_sum": ssf_sum, "n_frames": n_frames}
 
 
+def isf(
+    frames: Sequence[np.ndarray],
+    group_sizes: Sequence[int],
+    dimensions: Sequence[float],
+    *,
+    mode: Optional[str] = None,
+    n_points: int = 32,
+    q_max: Optional[float] = None,
+    wavevectors: Optional[np.ndarray] = None,
+    n_lags: Optional[int] = None,
+    incoherent: bool = False,
+    sort: bool = True,
+    unique: bool = True,
+) -> dict:
+    """
+    ``IntermediateScatteringFunction`` restated (``structure.py:2603-2828``, form="exp"): a sliding window of the
+    last ``n_lags`` frames; ``cisf[lag] += Re(rho(t - lag) conj rho(t))``, ``iisf[lag] += Re sum exp(iq.(r(t) - r(t - lag)))``.
+    """
+    frames = [np.asarray(f, dtype=np.float64) for f in frames]
+    n_frames = len(frames)
+    if wavevectors is not None:
+        wv = np.asarray(wavevectors, dtype=np.float64)
+        wn = np.linalg.norm(wv, axis=1)
+        if q_max is not None:
+            keep = wn <= q_max
+            wv, wn = wv[keep], wn[keep]
+    else:
+        wv, wn = wavevector_grid(dimensions, n_points, q_max)
+    pairs = sq_pairs(len(group_sizes), mode)
+    n_lags = int(min(n_lags or np.inf, n_frames))
+    offsets = np.concatenate(([0], np.cumsum(group_sizes))).astype(int)
+    groups = [slice(0, offsets[-1])] if mode is None else [slice(offsets[i], offsets[i + 1]) for i in range(len(group_sizes))]
+    rho = [[delta_fourier_transform_sum(wv, f[g]) for g in groups] for f in frames]
+    cisf = np.zeros((n_lags, len(pairs), wv.shape[0]))
+    iisf = np.zeros((n_lags, len(groups), wv.shape[0])) if incoherent else None
+    for t in range(n_frames):
+        for lag in range(min(n_lags, t + 1)):
+            s = t - lag
+            for i, (j, k) in enumerate(pairs):
+                j = 0 if j is None else j
+                k = 0 if k is None else k
+                if j == k:
+                    cisf[lag, i] += (rho[s][j] * rho[t][j].conj()).real
+                    if incoherent:
+                        iisf[lag, j] += delta_fourier_transform_sum(wv, frames[t][groups[j]] - frames[s][groups[j]]).real
+                else:
+                    cisf[lag, i] += (rho[s][j] * rho[t][k].conj()).real + (rho[s][k] * rho[t][j].conj()).real
+    n_total = int(np.sum(group_sizes))
+    norm = n_total * np.arange(n_frames, n_frames - n_lags, -1)[:, None, None]
+    cisf /= norm
+    if incoherent:
+        iisf /= norm
+    wn_out = np.unique(wn.round(11)) if unique else wn
+    if unique:
+        cisf = np.stack([cisf[:, :, np.isclose(q, wn)].mean(axis=2) for q in wn_out], axis=-1)
+        if incoherent:
+            iisf = np.stack([iisf[:, :, np.isclose(q, wn)].mean(axis=2) for q in wn_out], axis=-1)
+    if sort:
+        order = np.argsort(wn_out)
+        wn_out = wn_out[order]
+        cisf = cisf[:, :, order]
+        if incoherent:
+            iisf = iisf[:, :, order]
+    return {"pairs": pairs, "cisf": cisf, "iisf": iisf, "wavenumbers": wn_out, "n_lags": n_lags}
+
+
 # ----------------------------------------------------------------------------
 # g(r)
 # ----------------------------------------------------------------------------

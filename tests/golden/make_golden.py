@@ -102,6 +102,21 @@ def main():
     rs = rng.random((777, 3)) * 9.0
     save("sq_dfts.npz", qs=qs, rs=rs, rho=dfts(qs, rs))
 
+    # (e2) intermediate scattering functions: total with the self part, and partial
+    n, F = 250, 7
+    L = synthetic.cubic_box_length(n, 0.8)
+    base = synthetic.lj_like_frame(n, L, 1600).astype(np.float64)
+    walk = np.cumsum(np.random.default_rng(1601).normal(scale=0.08, size=(F, n, 3)), axis=0)
+    pos = np.mod(base[None] + walk, float(L)).astype(np.float32)
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    u = universe_from(pos, dims)
+    r = st.IntermediateScatteringFunction(u.atoms, n_points=6, n_lags=4, incoherent=True, verbose=False).run()
+    r2 = st.IntermediateScatteringFunction([u.select(0, 100), u.select(100, n)], mode="partial", n_points=5, n_lags=3,
+                                           incoherent=True, sort=False, unique=False, verbose=False).run()
+    save("isf_small.npz", pos=pos, dims=dims, cisf=r.results.cisf, iisf=r.results.iisf, times=r.results.times,
+         wavenumbers=r.results.wavenumbers, sizes=np.array([100, 150]), cisf_partial=r2.results.cisf,
+         iisf_partial=r2.results.iisf, pairs_partial=np.array(r2.results.pairs))
+
     # ------------------------------------------------------------------ g(r)
     # (f) C1: self-RDF, 200 bins to L/2, with and without exclusion=(1, 1)
     pos, dims = lj_frames(1000, 4, 0.8, 1000)

@@ -387,3 +387,51 @@ def test_sq_large_n_accuracy_vs_oracle(algorithm):
     np.testing.assert_allclose(s, s0, rtol=1e-5, atol=1e-6)
     m = s0 > (0.01 if algorithm == "factored" else 0.25)
     assert np.max(np.abs(s[m] / s0[m] - 1)) < 1e-5
+
+
+# --------------------------------------------------------------------------- F(q, t) class
+
+
+@pytest.mark.parametrize("precision,algorithm", PRECISION_ALGO)
+def test_isf_golden(precision, algorithm):
+    from mdcraft_b200.analysis.structure import IntermediateScatteringFunction
+
+    g = golden("isf_small.npz")
+    u = universe_from(g["pos"], g["dims"])
+    n = g["pos"].shape[1]
+    r = IntermediateScatteringFunction(u.atoms, n_points=6, n_lags=4, incoherent=True, verbose=False,
+                                       precision=precision, algorithm=algorithm, frame_block=3).run()
+    np.testing.assert_array_equal(r.results.wavenumbers, g["wavenumbers"])
+    np.testing.assert_allclose(r.results.times, g["times"])
+    tol = dict(rtol=1e-10, atol=1e-12) if precision == "fp64" else dict(rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(r.results.cisf, g["cisf"], **tol)
+    np.testing.assert_allclose(r.results.iisf, g["iisf"], **tol)
+    na = int(g["sizes"][0])
+    r2 = IntermediateScatteringFunction([u.select(0, na), u.select(na, n)], mode="partial", n_points=5, n_lags=3,
+                                        incoherent=True, sort=False, unique=False, verbose=False,
+                                        precision=precision, algorithm=algorithm).run()
+    assert r2.results.pairs == tuple(map(tuple, g["pairs_partial"]))
+    np.testing.assert_allclose(r2.results.cisf, g["cisf_partial"], **tol)
+    np.testing.assert_allclose(r2.results.iisf, g["iisf_partial"], **tol)
+
+
+def test_isf_explicit_wavevectors_and_defaults_vs_oracle():
+    from mdcraft_b200.analysis.structure import IntermediateScatteringFunction
+    from oracle import oracle
+
+    g = golden("isf_small.npz")
+    u = universe_from(g["pos"], g["dims"])
+    n = g["pos"].shape[1]
+    wv = np.random.default_rng(8).normal(size=(40, 3)) * 2.0
+    want = oracle.isf(list(g["pos"]), [n], g["dims"][:3], wavevectors=wv, incoherent=True, sort=False, unique=False)
+    r = IntermediateScatteringFunction(u.atoms, wavevectors=wv, incoherent=True, sort=False, unique=False,
+                                       verbose=False).run()      # n_lags defaults to every frame
+    assert r.results.cisf.shape == want["cisf"].shape == (7, 1, 40)
+    np.testing.assert_allclose(r.results.cisf, want["cisf"], rtol=1e-5, atol=5e-6)
+    np.testing.assert_allclose(r.results.iisf, want["iisf"], rtol=1e-5, atol=5e-6)
+    # coherent only, pair mode (cross term only), run(start, stop, step)
+    want = oracle.isf(list(g["pos"][1:7:2]), [100, 150], g["dims"][:3], mode="pair", n_points=5, n_lags=2)
+    r = IntermediateScatteringFunction([u.select(0, 100), u.select(100, n)], mode="pair", n_points=5, n_lags=2,
+                                       verbose=False).run(start=1, stop=7, step=2)
+    np.testing.assert_allclose(r.results.cisf, want["cisf"], rtol=1e-5, atol=2e-6)
+    assert "iisf" not in r.results

@@ -62,6 +62,26 @@ def test_sq_explicit_wavevectors():
     np.testing.assert_allclose(out["ssf"], g["ssf"], rtol=1e-10, atol=1e-12)
 
 
+def test_isf_against_reference_class():
+    """IntermediateScatteringFunction (structure.py:2198-2835): total with the self part, and partial."""
+    g = golden("isf_small.npz")
+    frames = list(g["pos"])
+    n = g["pos"].shape[1]
+    out = oracle.isf(frames, [n], g["dims"][:3], n_points=6, n_lags=4, incoherent=True)
+    np.testing.assert_array_equal(out["wavenumbers"], g["wavenumbers"])
+    np.testing.assert_allclose(out["cisf"], g["cisf"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(out["iisf"], g["iisf"], rtol=1e-9, atol=1e-11)
+    # lag 0 of the self part is exactly 1 (every particle against itself), and cisf[0] is S(q)
+    np.testing.assert_allclose(out["iisf"][0], 1.0, rtol=1e-12)
+    sq = oracle.structure_factor(frames, [n], g["dims"][:3], n_points=6)
+    np.testing.assert_allclose(out["cisf"][0, 0], sq["ssf"][0], rtol=1e-9, atol=1e-11)
+    part = oracle.isf(frames, list(g["sizes"]), g["dims"][:3], mode="partial", n_points=5, n_lags=3, incoherent=True,
+                      sort=False, unique=False)
+    assert part["pairs"] == tuple(map(tuple, g["pairs_partial"]))
+    np.testing.assert_allclose(part["cisf"], g["cisf_partial"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(part["iisf"], g["iisf_partial"], rtol=1e-9, atol=1e-11)
+
+
 def test_histogram_formula_and_edges():
     g = golden("histogram_pins.npz")
     for c in range(int(g["n_cases"])):
