@@ -134,6 +134,22 @@ int  mdc_delta_fourier_transform_sum(mdc_ctx *ctx, const double *qs, int64_t nq,
                                      const double *rs, int64_t n,
                                      int precision, double *rho_out);
 
+/* ---- single-chain structure factor ---------------------------------------- */
+
+/*
+ * polymer.py:1054-1445: positions pushed later hold n_chains
+ * chains of n_monomers consecutive particles; the plan accumulates
+ *   scsf[q] += sum over chains of |rho_chain(q)|^2
+ * into ONE row (mdc_sq_read returns f64 (1, Nq)).  Push / read / wavevector queries /
+ * accumulator access are the mdc_sq_* calls.
+ */
+int  mdc_scsf_plan_create(mdc_ctx *ctx,
+                          int n_points, const double L0[3], double q_max,
+                          const double *q_explicit, int64_t n_explicit,
+                          int64_t n_chains, int64_t n_monomers,
+                          int precision, int algo,
+                          mdc_sq_plan **out);
+
 /* ---- F(q, t): IntermediateScatteringFunction ------------------------------- */
 
 /*

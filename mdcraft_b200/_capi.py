@@ -75,6 +75,10 @@ SIGNATURES = {
     "mdc_sq_accum_ptr": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
     "mdc_sq_set_frames": (c_int, [c_void_p, c_int64]),
     "mdc_delta_fourier_transform_sum": (c_int, [c_void_p, _dp, c_int64, _dp, c_int64, c_int, _dp]),
+    "mdc_scsf_plan_create": (
+        c_int,
+        [c_void_p, c_int, _dp, c_double, _dp, c_int64, c_int64, c_int64, c_int, c_int, POINTER(c_void_p)],
+    ),
     "mdc_isf_plan_create": (
         c_int,
         [c_void_p, c_int, _dp, c_double, _dp, c_int64, c_int, _lp, c_int, _ip, c_int, c_int, c_int, c_int,
@@ -335,6 +339,28 @@ class SqPlan:
         ms, nl = c_float(), c_int()
         _check(lib().mdc_sq_last_push_stats(self._h, byref(ms), byref(nl)))
         return ms.value, nl.value
+
+
+class ScsfPlan(SqPlan):
+    """``mdc_scsf_plan_create``: sum over chains of ``|rho_chain|^2`` in one accumulator row."""
+
+    def __init__(self, ctx: Context, n_chains: int, n_monomers: int, *, n_points: int = 0,
+                 L0: Optional[Sequence[float]] = None, q_max: Optional[float] = None,
+                 wavevectors: Optional[np.ndarray] = None, precision: str = "fp32", algo: str = "auto"):
+        self.ctx = ctx
+        self._h = c_void_p()
+        L = np.zeros(3) if L0 is None else np.ascontiguousarray(L0, dtype=np.float64)
+        if wavevectors is not None:
+            wv = np.ascontiguousarray(wavevectors, dtype=np.float64).reshape(-1, 3)
+            n_exp, wv_p = wv.shape[0], _as(wv, _dp)
+        else:
+            n_exp, wv_p = 0, None
+        _check(lib().mdc_scsf_plan_create(
+            ctx._h, int(n_points), _as(L, _dp), -1.0 if q_max is None else float(q_max), wv_p, n_exp,
+            int(n_chains), int(n_monomers), PRECISIONS[precision], SQ_ALGOS[algo], byref(self._h)))
+        self.n_particles = int(n_chains) * int(n_monomers)
+        self.n_pairs = 1   # one accumulator row
+        self.n_wavevectors = int(lib().mdc_sq_num_wavevectors(self._h))
 
 
 class IsfPlan(SqPlan):

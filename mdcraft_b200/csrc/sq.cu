@@ -546,11 +546,13 @@ sq_lattice_factored(const uint4 *__restrict__ patches, const unsigned short *__r
 // measured once per plan (probe_sincos_kernel) and removed analytically.  Zero in FP64 mode.
 __global__ void sq_pair_accum(double2 *__restrict__ part, int F, int n_sets, int P, int64_t nq,
                               const int2 *__restrict__ sets, const int2 *__restrict__ pairs, int n_pairs,
-                              double dc_cos, double dc_sin, int64_t dc_first, double *__restrict__ ssf)
+                              double dc_cos, double dc_sin, int64_t dc_first, int sum_pairs,
+                              double *__restrict__ ssf)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     if (q < dc_first) dc_cos = dc_sin = 0.0;   // wavevectors evaluated without the SFU
+    double total = 0.0;
     for (int fs = 0; fs < F * n_sets; ++fs) {
         double2 *base = part + (int64_t)fs * P * nq + q;
         double re = 0.0, im = 0.0;
@@ -575,8 +577,10 @@ __global__ void sq_pair_accum(double2 *__restrict__ part, int F, int n_sets, int
                 acc += 2.0 * (rj.x * rk.x + rj.y * rk.y);   // 2 * (rho_j * conj(rho_k)).real
             }
         }
-        ssf[(int64_t)pr * nq + q] += acc;
+        if (sum_pairs) total += acc;
+        else ssf[(int64_t)pr * nq + q] += acc;
     }
+    if (sum_pairs) ssf[q] += total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -782,6 +786,8 @@ struct mdc_sq_plan {
     DevBuf<int> inc_slot;                      // set -> row of iisf (-1: none)
     std::vector<int2> pair_sets;
     int64_t isf_in_push = 0;                   // frames of the current push already processed
+    bool sum_pairs = false;                    // all pairs accumulate into row 0 (single-chain structure factor)
+    int n_rows = 0;                            // rows of ssf: n_pairs, or 1
     DevBuf<double2> part;
     DevBuf<float> raw[2];
     DevBuf<uint32_t> fix[2];
@@ -836,10 +842,10 @@ void plan_free(mdc_sq_plan *p)
 
 }  // namespace
 
-extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3], double q_max,
-                                  const double *q_explicit, int64_t n_explicit, int n_groups,
-                                  const int64_t *group_sizes, int n_pairs, const int *pairs, int precision,
-                                  int algo, mdc_sq_plan **out)
+static int sq_plan_create_impl(mdc_ctx *ctx, int n_points, const double L0[3], double q_max,
+                               const double *q_explicit, int64_t n_explicit, int n_groups,
+                               const int64_t *group_sizes, int n_pairs, const int *pairs, int precision, int algo,
+                               bool sum_pairs, mdc_sq_plan **out)
 {
     if (!ctx || !out) return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: NULL argument");
     *out = nullptr;
@@ -900,6 +906,12 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
     p->n_sets = (int)p->sets.size();
     p->n_pairs = n_pairs;
     p->pair_sets = hp;
+    p->sum_pairs = sum_pairs;
+    p->n_rows = sum_pairs ? 1 : n_pairs;
+    if (p->n_sets > 65535) {
+        delete p;
+        return fail(MDC_ERR_UNSUPPORTED, "mdc_sq_plan_create: more than 65535 distinct groups");
+    }
 
     int rc = p->st.init(ctx);
     if (rc != MDC_OK) {
@@ -951,8 +963,8 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
     p->factored = p->lattice_fast && algo != MDC_SQ_ALGO_DIRECT;
 
     PLAN_TRY(p->q.alloc((size_t)p->nq * 3));
-    PLAN_TRY(p->ssf.alloc((size_t)p->nq * n_pairs));
-    PLAN_CUDA(cudaMemset(p->ssf.p, 0, (size_t)p->nq * n_pairs * sizeof(double)));
+    PLAN_TRY(p->ssf.alloc((size_t)p->nq * p->n_rows));
+    PLAN_CUDA(cudaMemset(p->ssf.p, 0, (size_t)p->nq * p->n_rows * sizeof(double)));
     PLAN_TRY(p->d_sets.alloc(p->n_sets));
     PLAN_TRY(p->d_pairs.alloc(n_pairs));
     PLAN_CUDA(cudaMemcpy(p->d_sets.p, p->sets.data(), p->n_sets * sizeof(int2), cudaMemcpyHostToDevice));
@@ -1039,6 +1051,30 @@ extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3]
     return MDC_OK;
 }
 
+extern "C" int mdc_sq_plan_create(mdc_ctx *ctx, int n_points, const double L0[3], double q_max,
+                                  const double *q_explicit, int64_t n_explicit, int n_groups,
+                                  const int64_t *group_sizes, int n_pairs, const int *pairs, int precision,
+                                  int algo, mdc_sq_plan **out)
+{
+    return sq_plan_create_impl(ctx, n_points, L0, q_max, q_explicit, n_explicit, n_groups, group_sizes, n_pairs, pairs,
+                               precision, algo, false, out);
+}
+
+// Single-chain structure factor (polymer.py:1054-1445): sum over chains of |rho_chain|^2.  Every chain is a group
+// of n_monomers consecutive particles; the n_chains self pairs accumulate into ONE row.
+extern "C" int mdc_scsf_plan_create(mdc_ctx *ctx, int n_points, const double L0[3], double q_max,
+                                    const double *q_explicit, int64_t n_explicit, int64_t n_chains,
+                                    int64_t n_monomers, int precision, int algo, mdc_sq_plan **out)
+{
+    if (n_chains < 1 || n_monomers < 1 || n_chains > 65535)
+        return fail(MDC_ERR_INVALID, "mdc_scsf_plan_create: need 1 <= n_chains <= 65535 and n_monomers >= 1");
+    std::vector<int64_t> sizes((size_t)n_chains, n_monomers);
+    std::vector<int> pairs((size_t)2 * n_chains);
+    for (int64_t c = 0; c < n_chains; ++c) pairs[2 * c] = pairs[2 * c + 1] = (int)c;
+    return sq_plan_create_impl(ctx, n_points, L0, q_max, q_explicit, n_explicit, (int)n_chains, sizes.data(),
+                               (int)n_chains, pairs.data(), precision, algo, true, out);
+}
+
 extern "C" int mdc_sq_plan_destroy(mdc_sq_plan *plan)
 {
     plan_free(plan);
@@ -1073,6 +1109,7 @@ int configure(mdc_sq_plan *p, int n_frames_hint)
         const int64_t tab_frame = p->N * ((int64_t)p->nxp * 8 + (int64_t)p->nyp * 16 + (int64_t)p->nzp * 8);
         fblk = (int)std::max<int64_t>(1, std::min<int64_t>(fblk, ((int64_t)3 << 30) / tab_frame));
     }
+    fblk = (int)std::max<int64_t>(1, std::min<int64_t>(fblk, 65535 / p->n_sets));   // gridDim.z = frames x sets
     const int64_t want = (int64_t)p->ctx->sm_count * 32;
     int64_t min_len = p->N;
     for (auto &s : p->sets) min_len = std::min<int64_t>(min_len, std::max(1, s.y - s.x));
@@ -1236,7 +1273,7 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
     } else {
         sq_pair_accum<<<(unsigned)ceil_div(p->nq, 256), 256, 0, sk>>>(p->part.p, F, p->n_sets, p->P, p->nq,
                                                                      p->d_sets.p, p->d_pairs.p, p->n_pairs, p->dc[0],
-                                                                     p->dc[1], p->factored ? p->n_lat : 0, p->ssf.p);
+                                                                     p->dc[1], p->factored ? p->n_lat : 0, p->sum_pairs ? 1 : 0, p->ssf.p);
         ++*launches;
     }
     MDC_CUDA(cudaGetLastError());
@@ -1286,7 +1323,7 @@ extern "C" int mdc_sq_read(mdc_sq_plan *p, double *ssf_out, int64_t *n_frames_ou
     MDC_CUDA(cudaSetDevice(p->ctx->device));
     MDC_CUDA(cudaStreamSynchronize(p->st.compute));
     if (ssf_out)
-        MDC_CUDA(cudaMemcpy(ssf_out, p->ssf.p, (size_t)p->nq * p->n_pairs * sizeof(double), cudaMemcpyDeviceToHost));
+        MDC_CUDA(cudaMemcpy(ssf_out, p->ssf.p, (size_t)p->nq * p->n_rows * sizeof(double), cudaMemcpyDeviceToHost));
     if (n_frames_out) *n_frames_out = p->n_frames;
     return MDC_OK;
 }
@@ -1296,7 +1333,7 @@ extern "C" int mdc_sq_reset(mdc_sq_plan *p)
     if (!p) return fail(MDC_ERR_INVALID, "mdc_sq_reset: NULL plan");
     MDC_CUDA(cudaSetDevice(p->ctx->device));
     MDC_CUDA(cudaStreamSynchronize(p->st.compute));
-    MDC_CUDA(cudaMemset(p->ssf.p, 0, (size_t)p->nq * p->n_pairs * sizeof(double)));
+    MDC_CUDA(cudaMemset(p->ssf.p, 0, (size_t)p->nq * p->n_rows * sizeof(double)));
     if (p->isf) {
         MDC_CUDA(cudaMemset(p->cisf.p, 0, (size_t)p->n_lags * p->n_pairs * p->nq * sizeof(double)));
         if (p->incoherent) MDC_CUDA(cudaMemset(p->iisf.p, 0, (size_t)p->n_lags * p->n_inc * p->nq * sizeof(double)));
@@ -1311,7 +1348,7 @@ extern "C" int mdc_sq_accum_ptr(mdc_sq_plan *p, void **dev_ptr, int64_t *n_elems
     MDC_CUDA(cudaSetDevice(p->ctx->device));
     MDC_CUDA(cudaStreamSynchronize(p->st.compute));
     *dev_ptr = p->ssf.p;
-    *n_elems = p->nq * p->n_pairs;
+    *n_elems = p->nq * p->n_rows;
     return MDC_OK;
 }
 

@@ -232,6 +232,18 @@ class Universe:
         return AtomGroup(self, np.arange(lo, hi))
 
 
+class _GroupList(list):
+    """``ResidueGroup`` / ``SegmentGroup`` stand-in: a list of sub-groups that knows its length by both names."""
+
+    @property
+    def n_residues(self) -> int:
+        return len(self)
+
+    @property
+    def n_segments(self) -> int:
+        return len(self)
+
+
 class AtomGroup:
     """Minimal stand-in for ``MDAnalysis.AtomGroup`` (index list into a Universe)."""
 
@@ -269,7 +281,7 @@ class AtomGroup:
     def _split(self, labels: np.ndarray):
         """Sub-groups of this group sharing a residue / segment index, in index order."""
         mine = labels[self.indices]
-        out = []
+        out = _GroupList()
         for lab in np.unique(mine):
             g = AtomGroup(self.universe, self.indices[mine == lab])
             g.atoms = g   # MDAnalysis' Residue / Segment expose their atoms as ``.atoms``

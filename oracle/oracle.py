@@ -274,6 +274,38 @@ def structure_factor(
     return {"pairs": pairs, "ssf": ssf, "wavenumbers": wn_out, "wavevectors": wv, "ssf_sum": ssf_sum, "n_frames": n_frames}
 
 
+def scsf(frames: Iterable[np.ndarray], n_chains: int, n_monomers: int, dimensions, *, n_points: int = 32,
+         q_max: Optional[float] = None, wavevectors: Optional[np.ndarray] = None, sort: bool = True,
+         unique: bool = True) -> dict:
+    """``SingleChainStructureFactor`` for one group (``polymer.py:1382-1445``, form="exp")."""
+    if wavevectors is not None:
+        wv = np.asarray(wavevectors, dtype=np.float64)
+        wn = np.linalg.norm(wv, axis=1)
+        if q_max is not None:
+            keep = wn <= q_max
+            wv, wn = wv[keep], wn[keep]
+    else:
+        wv, wn = wavevector_grid(dimensions, n_points, q_max)
+    acc = np.zeros((1, wv.shape[0]))
+    n_frames = 0
+    for pos in frames:
+        chains = np.asarray(pos, dtype=np.float64).reshape(n_chains, n_monomers, 3)
+        for chain in chains:
+            rho = delta_fourier_transform_sum(wv, chain)
+            acc[0] += (rho * rho.conj()).real
+        n_frames += 1
+    acc /= n_chains * n_monomers * n_frames
+    wn_out = np.unique(wn.round(11))
+    if unique:
+        acc = np.hstack([acc[:, np.isclose(q, wn)].mean(axis=1, keepdims=True) for q in wn_out])
+    else:
+        wn_out = wn
+    if sort and unique:
+        order = np.argsort(wn_out)
+        wn_out, acc = wn_out[order], acc[:, order]
+    return {"scsf": acc, "wavenumbers": wn_out}
+
+
 def isf(
     frames: Sequence[np.ndarray],
     group_sizes: Sequence[int],

@@ -158,3 +158,19 @@ def load():
     structure = importlib.import_module("mdcraft.analysis.structure")
     _loaded = (structure, accelerated)
     return _loaded
+
+
+def load_polymer():
+    """The real ``mdcraft.analysis.polymer`` (for ``SingleChainStructureFactor`` golden vectors)."""
+    load()
+    if "MDAnalysis.lib.log" not in sys.modules:
+        log = types.ModuleType("MDAnalysis.lib.log")
+        log.ProgressBar = lambda it, *a, **k: it
+        sys.modules["MDAnalysis.lib.log"] = log
+        sys.modules["MDAnalysis.lib"].log = log
+    if "mdcraft.fit" not in sys.modules:
+        fit = types.ModuleType("mdcraft.fit")
+        fit.__path__ = [os.path.join(REF_SRC, "mdcraft", "fit")]
+        sys.modules["mdcraft.fit"] = fit
+        sys.modules["mdcraft"].fit = fit
+    return importlib.import_module("mdcraft.analysis.polymer")

@@ -117,6 +117,20 @@ def main():
          wavenumbers=r.results.wavenumbers, sizes=np.array([100, 150]), cisf_partial=r2.results.cisf,
          iisf_partial=r2.results.iisf, pairs_partial=np.array(r2.results.pairs))
 
+    # (e3) single-chain structure factor: 12 chains of 20 monomers (random walks)
+    pol = ref_loader.load_polymer()
+    M, N, F = 12, 20, 3
+    L = 14.0
+    steps = np.random.default_rng(1700).normal(scale=0.6, size=(F, M, N, 3))
+    starts = np.random.default_rng(1701).random((F, M, 1, 3)) * L
+    pos = np.mod(starts + np.cumsum(steps, axis=2), L).reshape(F, M * N, 3).astype(np.float32)
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    u = universe_from(pos, dims)
+    r = pol.SingleChainStructureFactor(u.atoms, n_chains=np.array([M]), n_monomers=np.array([N]), n_points=9,
+                                       verbose=False).run()
+    save("scsf_small.npz", pos=pos, dims=dims, n_chains=M, n_monomers=N, n_points=9, scsf=r.results.scsf,
+         wavenumbers=r.results.wavenumbers)
+
     # ------------------------------------------------------------------ g(r)
     # (f) C1: self-RDF, 200 bins to L/2, with and without exclusion=(1, 1)
     pos, dims = lj_frames(1000, 4, 0.8, 1000)

@@ -435,3 +435,31 @@ def test_isf_explicit_wavevectors_and_defaults_vs_oracle():
                                        verbose=False).run(start=1, stop=7, step=2)
     np.testing.assert_allclose(r.results.cisf, want["cisf"], rtol=1e-5, atol=2e-6)
     assert "iisf" not in r.results
+
+
+# --------------------------------------------------------------------------- single-chain S(q) (§8f rank 2)
+
+
+@pytest.mark.parametrize("precision,algorithm", PRECISION_ALGO)
+def test_scsf_golden(precision, algorithm):
+    from mdcraft_b200 import synthetic
+    from mdcraft_b200.analysis.polymer import SingleChainStructureFactor
+    from oracle import oracle
+
+    g = golden("scsf_small.npz")
+    M, N = int(g["n_chains"]), int(g["n_monomers"])
+    traj = synthetic.MemoryTrajectory(g["pos"], g["dims"])
+    u = synthetic.Universe(traj, segindices=np.repeat(np.arange(M), N))
+    tol = dict(rtol=1e-10, atol=1e-12) if precision == "fp64" else dict(rtol=1e-5, atol=1e-6)
+    r = SingleChainStructureFactor(u.atoms, n_chains=M, n_monomers=N, n_points=int(g["n_points"]), verbose=False,
+                                   precision=precision, algorithm=algorithm, frame_block=2).run()
+    np.testing.assert_array_equal(r.results.wavenumbers, g["wavenumbers"])
+    np.testing.assert_allclose(r.results.scsf, g["scsf"], **tol)
+    # chain structure from the topology (segments = chains), two groups, q_max
+    r2 = SingleChainStructureFactor([u.select(0, 4 * N), u.select(4 * N, M * N)], n_points=int(g["n_points"]),
+                                    q_max=3.0, verbose=False, precision=precision, algorithm=algorithm).run()
+    assert list(r2._n_chains) == [4, M - 4] and list(r2._n_monomers) == [N, N]
+    for ig, (lo, hi, m) in enumerate(((0, 4 * N, 4), (4 * N, M * N, M - 4))):
+        want = oracle.scsf([p[lo:hi] for p in g["pos"]], m, N, g["dims"][:3], n_points=int(g["n_points"]), q_max=3.0)
+        np.testing.assert_array_equal(r2.results.wavenumbers, want["wavenumbers"])
+        np.testing.assert_allclose(r2.results.scsf[ig], want["scsf"][0], **tol)

@@ -82,6 +82,15 @@ def test_isf_against_reference_class():
     np.testing.assert_allclose(part["iisf"], g["iisf_partial"], rtol=1e-9, atol=1e-11)
 
 
+def test_scsf_against_reference_class():
+    """polymer.SingleChainStructureFactor (polymer.py:1054-1445), one group."""
+    g = golden("scsf_small.npz")
+    out = oracle.scsf(list(g["pos"]), int(g["n_chains"]), int(g["n_monomers"]), g["dims"][:3], n_points=int(g["n_points"]))
+    np.testing.assert_array_equal(out["wavenumbers"], g["wavenumbers"])
+    np.testing.assert_allclose(out["scsf"], g["scsf"], rtol=1e-10, atol=1e-12)
+    assert out["scsf"][0, 0] == pytest.approx(int(g["n_monomers"]))   # q = 0: N monomers scatter coherently
+
+
 def test_histogram_formula_and_edges():
     g = golden("histogram_pins.npz")
     for c in range(int(g["n_cases"])):
