@@ -209,6 +209,8 @@ def run_native(args, rank, world):
     if world > 1:
         import torch.distributed as dist
 
+        # NCCL's banner ("NCCL version ...") goes to stdout by default; stdout carries the ONE JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = _capi.Context(local)
     F = args.frames
