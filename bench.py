@@ -170,7 +170,7 @@ def cpu_baseline(seconds_target=10.0):
     }
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit=print):
     """--impl reference: the reference's CPU path (oracle port; /root/reference does not exist on the
     GPU box and needs MDAnalysis), all host threads, each step a bounded sample of the workload."""
     if rank != 0:
@@ -193,13 +193,13 @@ def run_reference(args, rank):
         "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------- native arm
 
 
-def run_native(args, rank, world):
+def run_native(args, rank, world, emit=print):
     import torch
 
     from mdcraft_b200 import _capi
@@ -209,8 +209,6 @@ def run_native(args, rank, world):
     if world > 1:
         import torch.distributed as dist
 
-        # NCCL's banner ("NCCL version ...") goes to stdout by default; stdout carries the ONE JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = _capi.Context(local)
     F = args.frames
@@ -375,7 +373,7 @@ def run_native(args, rank, world):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -393,10 +391,24 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
-    if args.impl == "reference":
-        run_reference(args, rank)
-    else:
-        run_native(args, rank, world)
+    # stdout carries the ONE JSON line and nothing else: while the run is in progress, file descriptor 1 points at
+    # stderr, so that banners written by native libraries (e.g. "NCCL version ...") cannot precede the line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    emit = lines.append
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, emit)
+        else:
+            run_native(args, rank, world, emit)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    for line in lines:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":
