@@ -52,9 +52,12 @@ extern "C" {
 #define MDC_PRECISION_FP64     1   /* everything FP64 (reference arithmetic) */
 
 /* S(q) kernel selection for reciprocal-lattice plans in FP32 precision. */
-#define MDC_SQ_ALGO_AUTO       0   /* FACTORED for the lattice part, DIRECT arithmetic for explicit wavevectors */
+#define MDC_SQ_ALGO_AUTO       0   /* FACTORED or NUFFT for the lattice part, DIRECT arithmetic for explicit wavevectors */
 #define MDC_SQ_ALGO_DIRECT     1   /* one fused sin/cos per (q, particle) term on the SFU (2 MUFU ops per term) */
 #define MDC_SQ_ALGO_FACTORED   3   /* per-axis unit-phasor tables + one complex FMA per term (4 FP32 FMAs per term) */
+#define MDC_SQ_ALGO_NUFFT      4   /* gridding type-1 NUFFT in FP64: O(N w^3 + nf^3 log nf) instead of O(Nq N);
+                                      relative l2 error 1e-9 (FP32 precision) / 1e-13 (FP64 precision); also valid
+                                      with MDC_PRECISION_FP64.  AUTO picks it when its cost model says it is faster. */
 
 typedef struct mdc_ctx      mdc_ctx;
 typedef struct mdc_sq_plan  mdc_sq_plan;

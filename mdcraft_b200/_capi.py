@@ -31,7 +31,8 @@ PRECISIONS = {"fp32": PRECISION_FP32, "fp64": PRECISION_FP64}
 SQ_ALGO_AUTO = 0
 SQ_ALGO_DIRECT = 1
 SQ_ALGO_FACTORED = 3
-SQ_ALGOS = {"auto": SQ_ALGO_AUTO, "direct": SQ_ALGO_DIRECT, "factored": SQ_ALGO_FACTORED}
+SQ_ALGO_NUFFT = 4
+SQ_ALGOS = {"auto": SQ_ALGO_AUTO, "direct": SQ_ALGO_DIRECT, "factored": SQ_ALGO_FACTORED, "nufft": SQ_ALGO_NUFFT}
 
 PROBES = {
     "ffma": 0, "mufu_sincos_pairs": 1, "dfma": 2, "f2f_f64_f32": 3, "atoms_spread": 4, "imad": 5,

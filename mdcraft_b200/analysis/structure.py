@@ -28,10 +28,13 @@ Extra keyword arguments (all optional, defaults reproduce the reference):
 ``_conclude``; see :mod:`mdcraft_b200.distributed`) and, for S(q),
 ``precision`` (``"fp32"``: exact integer phases, FP32 arithmetic, FP64 sums,
 within 1e-5 of the reference; ``"fp64"``: the reference's arithmetic, within
-1e-10) and ``algorithm`` (FP32 lattice grids only: ``"direct"`` evaluates one
-fused sin/cos per (wavevector, particle) term on the SFU, ``"factored"`` builds
-per-axis unit-phasor tables and spends one complex FMA per term; ``"auto"`` =
-factored).
+1e-10) and ``algorithm`` (lattice grids: ``"direct"`` evaluates one fused
+sin/cos per (wavevector, particle) term on the SFU, ``"factored"`` builds
+per-axis unit-phasor tables and spends one complex FMA per term, ``"nufft"``
+spreads the particles onto a fine grid and takes pruned FP64 FFTs, which costs
+O(N w^3 + nf^3 log nf) instead of O(Nq N) and is accurate to 1e-9 (1e-13 with
+``precision="fp64"``); ``"auto"`` = whichever of factored / nufft the cost
+model of the plan says is faster).
 """
 
 from __future__ import annotations
@@ -572,7 +575,7 @@ class StructureFactor(NumbaAnalysisBase):
         if precision not in _capi.PRECISIONS:
             raise ValueError("Invalid precision. Valid values: 'fp32', 'fp64'.")
         if algorithm not in _capi.SQ_ALGOS:
-            raise ValueError("Invalid algorithm. Valid values: 'auto', 'direct', 'factored'.")
+            raise ValueError("Invalid algorithm. Valid values: 'auto', 'direct', 'factored', 'nufft'.")
 
         # structure.py:1822-1887: the grid is fixed at construction from the current frame's box
         self._explicit = None

@@ -18,6 +18,7 @@
 // 12 B per particle per frame and irrelevant.
 #include "common.cuh"
 #include "sq_math.cuh"
+#include "sq_nufft.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -31,6 +32,9 @@ constexpr int SQ_Q = 8;          // consecutive c (z index) values per thread in
 constexpr int SQ_THREADS = 128;
 constexpr int SQ_TILE = 256;     // particles staged in shared memory per inner pass (one exact integer partial sum)
 constexpr double TWO_PI = 6.283185307179586;  // == 2 * np.pi
+#ifndef MDC_NUFFT_SPREAD_RATE
+#define MDC_NUFFT_SPREAD_RATE 1.0e11   // fine-grid points spread per second (complex FP64 reductions), see DESIGN.md
+#endif
 
 // ------------------------------------------------------------------------------------------
 // wavevector grid (structure.py:1837-1841, 1874-1887)
@@ -546,17 +550,18 @@ sq_lattice_factored(const uint4 *__restrict__ patches, const unsigned short *__r
 // measured once per plan (probe_sincos_kernel) and removed analytically.  Zero in FP64 mode.
 __global__ void sq_pair_accum(double2 *__restrict__ part, int F, int n_sets, int P, int64_t nq,
                               const int2 *__restrict__ sets, const int2 *__restrict__ pairs, int n_pairs,
-                              double dc_cos, double dc_sin, int64_t dc_first, int sum_pairs,
+                              double dc_cos, double dc_sin, int64_t dc_first, int64_t p1_below, int sum_pairs,
                               double *__restrict__ ssf)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     if (q < dc_first) dc_cos = dc_sin = 0.0;   // wavevectors evaluated without the SFU
+    const int Pq = q < p1_below ? 1 : P;       // ... and as ONE partial (NUFFT): only chunk 0 is written
     double total = 0.0;
     for (int fs = 0; fs < F * n_sets; ++fs) {
         double2 *base = part + (int64_t)fs * P * nq + q;
         double re = 0.0, im = 0.0;
-        for (int p = 0; p < P; ++p) {
+        for (int p = 0; p < Pq; ++p) {
             const double2 v = base[(int64_t)p * nq];
             re += v.x;
             im += v.y;
@@ -591,15 +596,16 @@ __global__ void sq_pair_accum(double2 *__restrict__ part, int F, int n_sets, int
 // rho[(f * n_sets + s) * nq + q] = sum_p part[f, s, p, q] - N_s * dc   (same reduction as sq_pair_accum)
 __global__ void sq_reduce_rho(const double2 *__restrict__ part, int F, int n_sets, int P, int64_t nq,
                               const int2 *__restrict__ sets, double dc_cos, double dc_sin, int64_t dc_first,
-                              double2 *__restrict__ rho)
+                              int64_t p1_below, double2 *__restrict__ rho)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     if (q < dc_first) dc_cos = dc_sin = 0.0;
+    const int Pq = q < p1_below ? 1 : P;
     for (int fs = 0; fs < F * n_sets; ++fs) {
         const double2 *base = part + (int64_t)fs * P * nq + q;
         double re = 0.0, im = 0.0;
-        for (int p = 0; p < P; ++p) {
+        for (int p = 0; p < Pq; ++p) {
             const double2 v = base[(int64_t)p * nq];
             re += v.x;
             im += v.y;
@@ -663,18 +669,20 @@ __global__ void isf_disp_f64(const double *__restrict__ ring, int n_lags, int64_
 // iisf[lag0 + l, slot(s), q] += Re sum_j exp(i q . (r_j(t) - r_j(t - lag)))   (structure.py:2699-2725)
 __global__ void isf_incoherent_accum(const double2 *__restrict__ part, int L, int n_sets, int P, int64_t nq,
                                      const int2 *__restrict__ sets, const int *__restrict__ inc_slot, int n_inc,
-                                     int lag0, double dc_cos, int64_t dc_first, double *__restrict__ iisf)
+                                     int lag0, double dc_cos, int64_t dc_first, int64_t p1_below,
+                                     double *__restrict__ iisf)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     if (q < dc_first) dc_cos = 0.0;
+    const int Pq = q < p1_below ? 1 : P;
     for (int l = 0; l < L; ++l)
         for (int s = 0; s < n_sets; ++s) {
             const int slot = inc_slot[s];
             if (slot < 0) continue;
             const double2 *base = part + ((int64_t)l * n_sets + s) * P * nq + q;
             double re = 0.0;
-            for (int p = 0; p < P; ++p) re += base[(int64_t)p * nq].x;
+            for (int p = 0; p < Pq; ++p) re += base[(int64_t)p * nq].x;
             const int2 set = sets[s];
             iisf[((int64_t)(lag0 + l) * n_inc + slot) * nq + q] += re - (double)(set.y - set.x) * dc_cos;
         }
@@ -763,6 +771,8 @@ struct mdc_sq_plan {
     int precision = 0, algo = 0;
     bool lattice_fast = false;   // lattice part runs through an FP32 lattice kernel (direct or factored)
     bool factored = false;       // ... the factored one
+    bool nufft_on = false;       // lattice part runs through the gridding NUFFT (sq_nufft.cu), either precision
+    Nufft nufft;
     double dc[2] = {0, 0};
     DevBuf<double> q, ssf, posd[2];
     DevBuf<uint4> items, patches;
@@ -786,6 +796,7 @@ struct mdc_sq_plan {
     DevBuf<int> inc_slot;                      // set -> row of iisf (-1: none)
     std::vector<int2> pair_sets;
     int64_t isf_in_push = 0;                   // frames of the current push already processed
+    int nufft_rc = MDC_OK;                     // status of the last Nufft::density call
     bool sum_pairs = false;                    // all pairs accumulate into row 0 (single-chain structure factor)
     int n_rows = 0;                            // rows of ssf: n_pairs, or 1
     DevBuf<double2> part;
@@ -823,6 +834,7 @@ void plan_free(mdc_sq_plan *p)
     p->cisf.release();
     p->iisf.release();
     p->inc_slot.release();
+    p->nufft.release();
     p->row_cnt.release();
     p->row_qoff.release();
     p->part.release();
@@ -859,7 +871,8 @@ static int sq_plan_create_impl(mdc_ctx *ctx, int n_points, const double L0[3], d
     if (n_pairs < 1 || !pairs) return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: need at least one pair");
     if (precision != MDC_PRECISION_FP32 && precision != MDC_PRECISION_FP64)
         return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: unknown precision");
-    if (algo != MDC_SQ_ALGO_AUTO && algo != MDC_SQ_ALGO_DIRECT && algo != MDC_SQ_ALGO_FACTORED)
+    if (algo != MDC_SQ_ALGO_AUTO && algo != MDC_SQ_ALGO_DIRECT && algo != MDC_SQ_ALGO_FACTORED &&
+        algo != MDC_SQ_ALGO_NUFFT)
         return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: unknown algorithm");
     MDC_CUDA(cudaSetDevice(ctx->device));
 
@@ -959,8 +972,35 @@ static int sq_plan_create_impl(mdc_ctx *ctx, int n_points, const double L0[3], d
         plan_free(p);
         return fail(MDC_ERR_INVALID, "mdc_sq_plan_create: q_max removes every wavevector");
     }
-    p->lattice_fast = (precision == MDC_PRECISION_FP32) && p->n_lat > 0;
+    int64_t max_set = 1, sum_set = 0;
+    for (auto &s : p->sets) {
+        max_set = std::max<int64_t>(max_set, s.y - s.x);
+        sum_set += s.y - s.x;
+    }
+    if (algo == MDC_SQ_ALGO_NUFFT && p->n_lat > 0 && !Nufft::supported(n_points)) {
+        plan_free(p);
+        return fail(MDC_ERR_UNSUPPORTED, "mdc_sq_plan_create: the NUFFT path supports 2 <= n_points <= 682");
+    }
+    if (p->n_lat > 0 && Nufft::supported(n_points)) {
+        if (algo == MDC_SQ_ALGO_NUFFT) {
+            p->nufft_on = true;
+        } else if (algo == MDC_SQ_ALGO_AUTO && precision == MDC_PRECISION_FP32) {
+            // cost model (measured rates): factored kernel vs fine grid traffic + spreading
+            const double nf = 1.6 * n_points;
+            const double t_fact = (double)p->n_lat * (double)sum_set / 4.4e12;
+            const double t_nufft = p->n_sets * (nf * nf * nf * 16.0 * 5.0 / 4.0e12 + 60e-6) + (double)sum_set * 1728.0 / MDC_NUFFT_SPREAD_RATE;
+            p->nufft_on = t_nufft < t_fact;
+        }
+    }
+    p->lattice_fast = (precision == MDC_PRECISION_FP32) && p->n_lat > 0 && !p->nufft_on;
     p->factored = p->lattice_fast && algo != MDC_SQ_ALGO_DIRECT;
+    if (p->nufft_on) {
+        const int rn = p->nufft.init(ctx, n_points, precision == MDC_PRECISION_FP64 ? 1e-13 : 1e-9, max_set);
+        if (rn != MDC_OK) {
+            plan_free(p);
+            return rn;
+        }
+    }
 
     PLAN_TRY(p->q.alloc((size_t)p->nq * 3));
     PLAN_TRY(p->ssf.alloc((size_t)p->nq * p->n_rows));
@@ -984,7 +1024,9 @@ static int sq_plan_create_impl(mdc_ctx *ctx, int n_points, const double L0[3], d
         PLAN_CUDA(cudaGetLastError());
         PLAN_CUDA(cudaDeviceSynchronize());
         io.release();
-        if (!p->factored) {
+        if (p->nufft_on) {
+            p->items.release();   // the NUFFT scatters through row_cnt / row_qoff
+        } else if (!p->factored) {
             cnt.release();
             qo.release();
         } else {
@@ -1103,7 +1145,7 @@ int configure(mdc_sq_plan *p, int n_frames_hint)
     if (per_frame_min > budget * 8)
         return fail(MDC_ERR_NOMEM, "mdc_sq_push: wavevector grid too large for the partial-density buffer");
     const int64_t blocks_q = (p->factored ? p->n_patches : ceil_div(p->lattice_fast ? p->n_items : 0, SQ_THREADS)) +
-                             ceil_div(p->lattice_fast ? p->n_exp : p->nq, SQ_THREADS);
+                             ceil_div((p->lattice_fast || p->nufft_on) ? p->n_exp : p->nq, SQ_THREADS);
     int fblk = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_frames_hint, 32), budget / per_frame_min));
     if (p->factored) {
         const int64_t tab_frame = p->N * ((int64_t)p->nxp * 8 + (int64_t)p->nyp * 16 + (int64_t)p->nzp * 8);
@@ -1113,7 +1155,7 @@ int configure(mdc_sq_plan *p, int n_frames_hint)
     const int64_t want = (int64_t)p->ctx->sm_count * 32;
     int64_t min_len = p->N;
     for (auto &s : p->sets) min_len = std::min<int64_t>(min_len, std::max(1, s.y - s.x));
-    int64_t P = ceil_div(want, blocks_q * fblk * p->n_sets);
+    int64_t P = blocks_q > 0 ? ceil_div(want, blocks_q * fblk * p->n_sets) : 1;   // 0: NUFFT only, one partial
     P = std::min<int64_t>(P, std::max<int64_t>(1, min_len / (2 * SQ_TILE)));
     P = std::min<int64_t>(P, std::max<int64_t>(1, budget / (per_frame_min * fblk)));
     P = std::max<int64_t>(1, std::min<int64_t>(P, 65535));
@@ -1146,7 +1188,21 @@ void launch_density(mdc_sq_plan *p, const DensityIn &in, int F, int *launches)
 {
     cudaStream_t sk = p->st.compute;
     const unsigned gz = (unsigned)(F * p->n_sets);
-    if (p->lattice_fast) {
+    if (p->nufft_on) {
+        const double iL[3] = {1.0 / p->L0[0], 1.0 / p->L0[1], 1.0 / p->L0[2]};
+        p->nufft_rc = p->nufft.density(sk, in.posd, iL, p->N, p->d_sets.p, p->n_sets, F, p->row_cnt.p, p->row_qoff.p,
+                                       p->nq, p->P, p->part.p, launches);
+        if (p->n_exp > 0) {
+            dim3 ge((unsigned)ceil_div(p->n_exp, SQ_THREADS), (unsigned)p->P, gz);
+            if (p->precision == MDC_PRECISION_FP64)
+                sq_explicit_f64<<<ge, SQ_THREADS, 0, sk>>>(p->q.p, p->n_lat, p->n_exp, in.posd, p->N, p->d_sets.p,
+                                                          p->n_sets, p->P, p->nq, p->part.p);
+            else
+                sq_explicit_f32<<<ge, SQ_THREADS, 0, sk>>>(p->q.p, p->n_lat, p->n_exp, in.posd, p->N, p->d_sets.p,
+                                                          p->n_sets, p->P, p->nq, p->part.p);
+            ++*launches;
+        }
+    } else if (p->lattice_fast) {
         if (p->factored) {
             dim3 g((unsigned)p->n_patches, (unsigned)p->P, gz);
             sq_lattice_factored<<<g, FC_THREADS, FC_SMEM, sk>>>(p->patches.p, p->entries.p, in.tabx, in.taby, in.tabz,
@@ -1185,9 +1241,10 @@ int isf_frame(mdc_sq_plan *p, int slot, int *launches)
     const int cur = (int)(t % p->n_lags);
     const int n_valid = (int)std::min<int64_t>(p->n_lags, t + 1);
     const unsigned qb = (unsigned)ceil_div(p->nq, 256);
-    const int64_t dc_first = p->factored ? p->n_lat : 0;
+    const int64_t dc_first = (p->factored || p->nufft_on) ? p->n_lat : 0;
+    const int64_t p1_below = p->nufft_on ? p->n_lat : 0;
     sq_reduce_rho<<<qb, 256, 0, sk>>>(p->part.p, 1, p->n_sets, p->P, p->nq, p->d_sets.p, p->dc[0], p->dc[1], dc_first,
-                                     p->rho_ring.p + (size_t)cur * p->n_sets * p->nq);
+                                     p1_below, p->rho_ring.p + (size_t)cur * p->n_sets * p->nq);
     isf_coherent<<<qb, 256, 0, sk>>>(p->rho_ring.p, p->n_lags, p->n_sets, p->nq, cur, n_valid, p->d_pairs.p, p->n_pairs,
                                     p->cisf.p);
     *launches += 2;
@@ -1224,8 +1281,9 @@ int isf_frame(mdc_sq_plan *p, int slot, int *launches)
                 in.posd = p->dposd.p;
             }
             launch_density(p, in, L, launches);
+            MDC_CHECK(p->nufft_rc);
             isf_incoherent_accum<<<qb, 256, 0, sk>>>(p->part.p, L, p->n_sets, p->P, p->nq, p->d_sets.p, p->inc_slot.p,
-                                                    p->n_inc, lag0, p->dc[0], dc_first, p->iisf.p);
+                                                    p->n_inc, lag0, p->dc[0], dc_first, p1_below, p->iisf.p);
             ++*launches;
         }
     }
@@ -1264,6 +1322,7 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
     in.tabz = p->tabz[slot].p;
     in.posd = p->posd[slot].p;
     launch_density(p, in, F, launches);
+    MDC_CHECK(p->nufft_rc);
     if (ti >= 0) {
         MDC_CUDA(cudaEventRecord(p->st.k1[ti], sk));
         p->st.n_timed = ti + 1;
@@ -1273,7 +1332,8 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
     } else {
         sq_pair_accum<<<(unsigned)ceil_div(p->nq, 256), 256, 0, sk>>>(p->part.p, F, p->n_sets, p->P, p->nq,
                                                                      p->d_sets.p, p->d_pairs.p, p->n_pairs, p->dc[0],
-                                                                     p->dc[1], p->factored ? p->n_lat : 0, p->sum_pairs ? 1 : 0, p->ssf.p);
+                                                                     p->dc[1], (p->factored || p->nufft_on) ? p->n_lat : 0,
+                                                                     p->nufft_on ? p->n_lat : 0, p->sum_pairs ? 1 : 0, p->ssf.p);
         ++*launches;
     }
     MDC_CUDA(cudaGetLastError());
