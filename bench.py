@@ -15,9 +15,12 @@ frames already resident in HBM; `e2e` = the same through the C ABI with pinned H
 frames and D2H of the step's results inside the timed region).  Frames shard across ranks (weak scaling:
 every rank processes its own --frames per step); accumulators are all-reduced once at the end.
 
-The roofline is an ISSUE-RATE roofline: the dominant kernel (sq_lattice_direct) spends
-two SFU ops (sin, cos) per (wavevector, particle) term; the peak is measured on the box in this run with
-a MUFU.SIN + MUFU.COS microbenchmark (mdc_probe_rate).  HBM traffic is 12 B per particle per frame.
+Rooflines.  `roofline` describes the kernel with the largest share of the timed step: the g(r)
+pair kernel (issue-rate bound, ~24 issue slots per pair-distance).  S(q) on this grid runs as a gridding NUFFT
+(`roofline_sq`, HBM bound: fine grid + pruned FFT intermediates); the two O(Nq N) kernels it replaced are timed on
+one frame each and reported against their issue-rate rooflines measured on the box in this run
+(`roofline_sfu_direct`: 2 SFU ops per term, the contract kernel of BASELINE.json's north_star;
+`roofline_fp32_factored`: 4 FP32 FMAs per term).
 """
 
 from __future__ import annotations
@@ -40,6 +43,9 @@ N_PART = 100_000
 GR = dict(rho=2.5, n_bins=200, seed0=2000)
 SQ = dict(rho=0.8, n_points=161, q_max=20.0, seed0=3000)
 METRIC = "frames/sec for S(q) and g(r) at 1e5 particles"
+#: dram__bytes_read.sum + dram__bytes_write.sum of the NUFFT kernels per frame, one `ncu --set full` capture
+#: (profiles/sq_nufft_r01.txt)
+NUFFT_DRAM_BYTES_PER_FRAME = None
 UNIT = "frames/s"
 
 
@@ -294,12 +300,31 @@ def run_native(args, rank, world, emit=print):
     sq_default_fps = F * rep / (ctx.elapsed_ms() * 1e-3)
     sqd.close()
 
-    # secondary figure: the contract kernel of BASELINE.json's north_star (one fused sin/cos per term on the SFU)
-    # on the same full grid, against the SFU issue-rate roofline
-    direct = None
-    if args.sq_algo != "direct" and rank == 0:
+    sm = ctx.info()["sm_count"]
+    used = sqp.info()
+
+    def term_roofline(algo, ms, frames):
+        """Issue-rate roofline of one of the O(Nq N) lattice kernels from its device time over `frames` frames."""
+        ach = float(nq) * N_PART * frames / (ms * 1e-3)
+        if algo == "direct":
+            pk = ctx.probe_rate("mufu_sincos_pairs")      # measured on this box, this run
+            return {"bound": "sfu", "kernel": "sq_lattice_direct", "achieved": ach / 1e9, "peak": pk / 1e9,
+                    "unit": "G(q,particle) terms/s", "frac": ach / pk, "frames_per_s": frames * 1e3 / ms,
+                    "traffic": 5.8e7,
+                    "peak_source": f"measured in this run: MUFU.SIN+MUFU.COS pairs/s (mdc_probe_rate); nominal {sm} SMs x 8 pairs/clk",
+                    "algorithmic": "2 SFU ops + ~10 FP32/INT issue slots per term"}
+        pk = ctx.probe_rate("ffma") / 4.0                 # 4 FP32 FMAs (2 packed FFMA2) per term
+        return {"bound": "fp32", "kernel": "sq_lattice_factored", "achieved": ach / 1e9, "peak": pk / 1e9,
+                "unit": "G(q,particle) terms/s", "frac": ach / pk, "frames_per_s": frames * 1e3 / ms,
+                "traffic": 6.8e8,
+                "peak_source": (f"measured in this run: FFMA/s / 4 (mdc_probe_rate); nominal {sm} SMs x 128 FMA/clk / 4; "
+                                f"FFMA2 in this kernel's operand pattern sustains {ctx.probe_rate('ffma2_loop') / 2e9:.0f} G terms/s"),
+                "algorithmic": "one complex FMA = 4 FP32 FMAs (2 x fma.rn.f32x2) per term; 56 table phasors per 4096 terms"}
+
+    def one_frame(algo):
+        """One frame of the full grid through an O(Nq N) kernel (L2 flushed first): its device time in ms."""
         sqx = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=SQ["n_points"], L0=[Ls] * 3, q_max=SQ["q_max"],
-                           algo="direct")
+                           algo=algo)
         sqx.push(sq_dev[:1], n_frames=1)
         ctx.synchronize()
         flush.fill_(1)
@@ -307,12 +332,17 @@ def run_native(args, rank, world, emit=print):
         sqx.push(sq_dev[:1], n_frames=1)
         ctx.synchronize()
         ms, _ = sqx.last_push_stats()
-        ach = float(nq) * N_PART / (ms * 1e-3)
-        pk = ctx.probe_rate("mufu_sincos_pairs")
-        direct = {"bound": "sfu", "kernel": "sq_lattice_direct", "achieved": ach / 1e9, "peak": pk / 1e9,
-                  "unit": "G(q,particle) terms/s", "frac": ach / pk, "frames_per_s": 1e3 / ms,
-                  "peak_source": "measured in this run: MUFU.SIN+MUFU.COS pairs/s (mdc_probe_rate)"}
         sqx.close()
+        return ms
+
+    # secondary figures: the kernels the NUFFT replaced, on the same full grid against their issue-rate rooflines
+    # (direct = the contract kernel of BASELINE.json's north_star: one fused sin/cos per term on the SFU)
+    direct = factored = None
+    if rank == 0:
+        if used["algo"] != "direct":
+            direct = term_roofline("direct", one_frame("direct"), 1)
+        if used["algo"] != "factored":
+            factored = term_roofline("factored", one_frame("factored"), 1)
 
     # the once-per-run exchange step: all-reduce of the accumulators over NVLink (outside the timed steps)
     if world > 1:
@@ -322,55 +352,66 @@ def run_native(args, rank, world, emit=print):
         mdist.all_reduce_device(sqp.accumulator(), device=local)
 
     if rank == 0:
-        terms = float(nq) * N_PART * F * args.steps           # per rank
-        achieved = terms / (sq_ms * 1e-3)
-        sm = ctx.info()["sm_count"]
-        # DRAM bytes per launch of the dominant kernel from one `ncu --set full` capture (profiles/*_r01.txt)
-        traffic = 5.8e7 if args.sq_algo == "direct" else 6.8e8
-        if args.sq_algo == "direct":
-            kernel, bound = "sq_lattice_direct", "sfu"
-            peak = ctx.probe_rate("mufu_sincos_pairs")        # measured on this box, this run
-            peak_src = f"measured in this run: MUFU.SIN+MUFU.COS pairs/s (mdc_probe_rate); nominal {sm} SMs x 8 pairs/clk"
-            algorithmic = "2 SFU ops + ~10 FP32/INT issue slots per term"
+        frames_rank = F * args.steps
+        if used["algo"] == "nufft":
+            # HBM roofline of the NUFFT chain (memset, spread, three pruned FFT passes, pair accumulation):
+            # algorithmic bytes = every buffer written once and read once, 16 B per complex FP64
+            nf, n = used["nf"], SQ["n_points"]
+            ncp = (n + 1) & ~1
+            alg = 16.0 * (nf ** 3                                   # clear the fine grid
+                          + 2 * nf ** 3                            # spread: read-modify-write of the fine grid
+                          + nf ** 3 + nf * nf * ncp                # z pass
+                          + nf * nf * ncp + nf * n * ncp           # y pass
+                          + nf * n * ncp + nq                      # x pass + deconvolution
+                          + 2 * nq)                                # rho -> |rho|^2 accumulated into ssf
+            peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(peaks_file):
+                peak_gbs, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)"
+            else:
+                peak_gbs, peak_src = 6650.0, "of fallback (B200_PROFILING.md): 6.65 TB/s"
+            ach = alg * frames_rank / (sq_ms * 1e-3) / 1e9
+            roof_sq = {"bound": "hbm", "kernel": "nufft_spread + nufft_fft_z + nufft_fft_s<0> + nufft_fft_s<1> (+ memset, sq_pair_accum)",
+                       "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                       "traffic": NUFFT_DRAM_BYTES_PER_FRAME, "peak_source": peak_src,
+                       "algorithmic": f"{alg / 1e6:.0f} MB per frame: fine grid {nf}^3 complex FP64 cleared, spread into (w = {used['w']}: "
+                                      f"{used['w'] ** 3} FP64 complex reductions per particle, L2 resident) and read once; pruned "
+                                      f"intermediates {nf}^2 x {n} and {nf} x {n}^2 written and read once; {nq} densities"}
         else:
-            kernel, bound = "sq_lattice_factored", "fp32"
-            peak = ctx.probe_rate("ffma") / 4.0               # 4 FP32 FMAs (2 packed FFMA2) per term
-            peak_src = (f"measured in this run: FFMA/s / 4 (mdc_probe_rate); nominal {sm} SMs x 128 FMA/clk / 4; "
-                        f"FFMA2 in this kernel's operand pattern sustains {ctx.probe_rate('ffma2_loop') / 2e9:.0f} G terms/s")
-            algorithmic = "one complex FMA = 4 FP32 FMAs (2 x fma.rn.f32x2) per term; 56 table phasors per 4096 terms"
+            roof_sq = term_roofline(used["algo"], sq_ms, frames_rank)
         pairs = 0.5 * N_PART * (N_PART - 1) * F * args.steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (S(q) sums, SFU sin/cos) + f64 (g(r) distances)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (S(q): NUFFT grid, FFTs, sums) + f32 filter / f64 exact (g(r) distances)",
             "data": "synthetic", "config": workload_config(F, world), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int(gr_host.nbytes + sq_host.nbytes + F * 24),
                     "d2h_bytes_per_step": int(GR["n_bins"] * 8 + nq * 8)},
             "gpu_launches": launches,
-            "roofline": {
-                "bound": bound, "kernel": kernel, "achieved": achieved / 1e9, "peak": peak / 1e9,
-                "unit": "G(q,particle) terms/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic": algorithmic,
-            },
-            "sq_algo": args.sq_algo,
+            "sq_algo": args.sq_algo, "sq_algo_used": used,
+            "roofline_sq": roof_sq,
             "roofline_sfu_direct": direct,
-            # g(r): the filter kernel issues ~24 instructions per pair-distance (SASS count, profiles/rdf_fast_r01.txt);
-            # its ceiling is the issue rate, 4 schedulers x 32 lanes per SM per clock
-            "roofline_gr": {
-                "bound": "issue", "kernel": "rdf_pairs_fast", "achieved": pairs / (gr_ms * 1e-3) / 1e9,
-                "peak": sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 24.0 / 1e9, "unit": "G pair-distances/s",
-                "frac": pairs / (gr_ms * 1e-3) / (sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 24.0),
-                "traffic": 3.1e6,
-                "algorithmic": "24 issue slots + 1 SFU op (sqrt) + 0.52 shared-memory atomics per pair; "
-                               "24 B of positions per particle per frame (f32 + u32 fixed point)",
-            },
+            "roofline_fp32_factored": factored,
             "sq_frames_per_s": F * args.steps / (sq_ms * 1e-3),
             "sq_default_grid_frames_per_s": sq_default_fps,
             "gr_frames_per_s": F * args.steps / (gr_ms * 1e-3),
             "gr_pairs_per_s": pairs / (gr_ms * 1e-3),
             "wall_s": wall,
         }
+        # g(r): the filter kernel issues ~24 instructions per pair-distance (SASS count, profiles/rdf_fast_r01.txt);
+        # its ceiling is the issue rate, 4 schedulers x 32 lanes per SM per clock
+        gr_peak = sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 24.0
+        line["roofline_gr"] = {
+            "bound": "issue", "kernel": "rdf_pairs_fast", "achieved": pairs / (gr_ms * 1e-3) / 1e9,
+            "peak": gr_peak / 1e9, "unit": "G pair-distances/s", "frac": pairs / (gr_ms * 1e-3) / gr_peak,
+            "traffic": 3.1e6, "peak_source": f"{sm} SMs x 4 schedulers x 32 lanes x SM clock / 24 issue slots per pair",
+            "algorithmic": "24 issue slots + 1 SFU op (sqrt) + 0.52 shared-memory atomics per pair; "
+                           "24 B of positions per particle per frame (f32 + u32 fixed point)",
+        }
+        # the headline roofline: the kernel with the largest share of the timed step
+        share_gr = gr_ms / max(gr_ms + sq_ms, 1e-9)
+        line["roofline"] = dict(line["roofline_gr"] if share_gr >= 0.5 else roof_sq)
+        line["roofline"]["share_of_step"] = share_gr if share_gr >= 0.5 else 1.0 - share_gr
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
         emit(json.dumps(line))
@@ -386,8 +427,8 @@ def main():
     ap.add_argument("--frames", type=int, default=2, help="frames per step per GPU")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--sq-algo", default="auto", choices=["auto", "direct", "factored"],
-                    help="S(q) lattice kernel: factored (default) or the SFU-bound direct one")
+    ap.add_argument("--sq-algo", default="auto", choices=["auto", "direct", "factored", "nufft"],
+                    help="S(q) lattice kernel: auto (the plan's cost model: NUFFT on this grid), or force one")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -110,6 +110,13 @@ int  mdc_sq_plan_destroy(mdc_sq_plan *plan);
 
 /* Number of wavevectors kept (lattice after q_max + explicit). */
 int64_t mdc_sq_num_wavevectors(mdc_sq_plan *plan);
+/*
+ * What the plan decided: info[0] = kernel family of the lattice part (MDC_SQ_ALGO_DIRECT / FACTORED / NUFFT, 0 =
+ * FP64 reference arithmetic or no lattice part), info[1] = NUFFT fine-grid points per axis, info[2] = NUFFT kernel
+ * width, info[3] = n_points, info[4] = density sets per frame, info[5] = particle chunks per set, info[6] = frames
+ * per block, info[7] = (frame, set) elements per NUFFT batch.  info[5..7] are 0 before the first push.
+ */
+int  mdc_sq_plan_info(mdc_sq_plan *plan, int info[8]);
 /* Copies the device-built wavevectors, f64 (Nq, 3), to host memory. */
 int  mdc_sq_wavevectors(mdc_sq_plan *plan, double *q_out);
 

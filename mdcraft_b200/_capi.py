@@ -70,6 +70,7 @@ SIGNATURES = {
     "mdc_sq_plan_destroy": (c_int, [c_void_p]),
     "mdc_sq_num_wavevectors": (c_int64, [c_void_p]),
     "mdc_sq_wavevectors": (c_int, [c_void_p, _dp]),
+    "mdc_sq_plan_info": (c_int, [c_void_p, _ip]),
     "mdc_sq_push": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "mdc_sq_read": (c_int, [c_void_p, _dp, _lp]),
     "mdc_sq_reset": (c_int, [c_void_p]),
@@ -301,6 +302,14 @@ class SqPlan:
             self.close()
         except Exception:
             pass
+
+    def info(self) -> dict:
+        """What the plan decided: lattice kernel family and, for the NUFFT, its fine grid and kernel width."""
+        a = (c_int * 8)()
+        _check(lib().mdc_sq_plan_info(self._h, a))
+        names = {v: k for k, v in SQ_ALGOS.items() if k != "auto"}
+        return {"algo": names.get(a[0], "explicit"), "nf": a[1], "w": a[2], "n_points": a[3], "n_sets": a[4],
+                "chunks": a[5], "frame_block": a[6], "nufft_batch": a[7]}
 
     def wavevectors(self) -> np.ndarray:
         out = np.empty((self.n_wavevectors, 3), dtype=np.float64)

@@ -32,9 +32,7 @@ constexpr int SQ_Q = 8;          // consecutive c (z index) values per thread in
 constexpr int SQ_THREADS = 128;
 constexpr int SQ_TILE = 256;     // particles staged in shared memory per inner pass (one exact integer partial sum)
 constexpr double TWO_PI = 6.283185307179586;  // == 2 * np.pi
-#ifndef MDC_NUFFT_SPREAD_RATE
-#define MDC_NUFFT_SPREAD_RATE 1.0e11   // fine-grid points spread per second (complex FP64 reductions), see DESIGN.md
-#endif
+
 
 // ------------------------------------------------------------------------------------------
 // wavevector grid (structure.py:1837-1841, 1874-1887)
@@ -985,10 +983,10 @@ static int sq_plan_create_impl(mdc_ctx *ctx, int n_points, const double L0[3], d
         if (algo == MDC_SQ_ALGO_NUFFT) {
             p->nufft_on = true;
         } else if (algo == MDC_SQ_ALGO_AUTO && precision == MDC_PRECISION_FP32) {
-            // cost model (measured rates, DESIGN.md §3): factored kernel vs fine grid traffic + spreading
-            const double nf = 1.6 * n_points;
+            // cost model (measured rates, DESIGN.md §3.7): factored kernel vs fine grid traffic + spreading
+            NufftGeom ng;
             const double t_fact = (double)p->n_lat * (double)sum_set / 4.4e12;
-            const double t_nufft = p->n_sets * (nf * nf * nf * 16.0 * 5.0 / 4.0e12 + 60e-6) + (double)sum_set * 1728.0 / MDC_NUFFT_SPREAD_RATE;
+            const double t_nufft = Nufft::geometry(n_points, 1e-9, &ng) ? Nufft::cost(ng, p->n_sets, sum_set) : 1e30;
             p->nufft_on = t_nufft < t_fact;
         }
     }
@@ -1124,6 +1122,24 @@ extern "C" int mdc_sq_plan_destroy(mdc_sq_plan *plan)
 }
 
 extern "C" int64_t mdc_sq_num_wavevectors(mdc_sq_plan *plan) { return plan ? plan->nq : -1; }
+
+extern "C" int mdc_sq_plan_info(mdc_sq_plan *p, int info[8])
+{
+    if (!p || !info) return fail(MDC_ERR_INVALID, "mdc_sq_plan_info: NULL argument");
+    const int lattice_algo = p->n_lat == 0 ? 0
+                             : p->nufft_on ? MDC_SQ_ALGO_NUFFT
+                             : p->factored ? MDC_SQ_ALGO_FACTORED
+                             : p->lattice_fast ? MDC_SQ_ALGO_DIRECT : 0;
+    info[0] = lattice_algo;
+    info[1] = p->nufft_on ? p->nufft.g.nf : 0;
+    info[2] = p->nufft_on ? p->nufft.g.w : 0;
+    info[3] = p->n_points;
+    info[4] = p->n_sets;
+    info[5] = p->P;
+    info[6] = p->fblk;
+    info[7] = p->nufft_on ? p->nufft.G : 0;
+    return MDC_OK;
+}
 
 extern "C" int mdc_sq_wavevectors(mdc_sq_plan *plan, double *q_out)
 {

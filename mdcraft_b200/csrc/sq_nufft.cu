@@ -39,57 +39,115 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b)
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// position, after fft_line, of X[k]
-__device__ __forceinline__ int fft_pos(int k, const NufftGeom &g)
+// shared-memory index of element p of a line: one 16-byte slot of padding per 8 keeps the strided accesses of
+// the later FFT stages (stride nf / 8, nf / 64, ...) spread over all banks
+__device__ __forceinline__ int padded(int p) { return p + (p >> 3); }
+
+// y_r = sum_q v_q w^(r q), w = exp(+2 pi i / R), in place, natural order
+template <int R>
+__device__ __forceinline__ void dft(double2 *v);
+
+template <>
+__device__ __forceinline__ void dft<2>(double2 *v)
 {
-    int r = 0, j = k;
-    if (g.r3) {
-        j = k / 3;
-        r = k - 3 * j;
-    }
-    const int br = g.log2m ? (int)(__brev((unsigned)j) >> (32 - g.log2m)) : 0;
-    return r * g.m + br;
+    const double2 a = v[0], b = v[1];
+    v[0] = make_double2(a.x + b.x, a.y + b.y);
+    v[1] = make_double2(a.x - b.x, a.y - b.y);
 }
 
-// One warp transforms one line of nf complex doubles in shared memory, in place:
-//   X[k] = sum_l x[l] exp(+2 pi i k l / nf),   X[k] ends up at buf[fft_pos(k)].
-// Decimation in frequency: an optional radix-3 stage (nf = 3 m) followed by log2(m) radix-2 stages on
-// contiguous sub-blocks; the bit-reversed order is undone for free by the pruned read-out.
+template <>
+__device__ __forceinline__ void dft<3>(double2 *v)
+{
+    const double hs = 0.8660254037844386;   // sin(2 pi / 3)
+    const double2 a = v[0], b = v[1], c = v[2];
+    const double2 s = make_double2(b.x + c.x, b.y + c.y), d = make_double2(b.x - c.x, b.y - c.y);
+    const double2 h = make_double2(a.x - 0.5 * s.x, a.y - 0.5 * s.y);
+    v[0] = make_double2(a.x + s.x, a.y + s.y);
+    v[1] = make_double2(h.x - hs * d.y, h.y + hs * d.x);   // a + w3 b + w3^2 c
+    v[2] = make_double2(h.x + hs * d.y, h.y - hs * d.x);
+}
+
+template <>
+__device__ __forceinline__ void dft<4>(double2 *v)
+{
+    const double2 t0 = make_double2(v[0].x + v[2].x, v[0].y + v[2].y), t1 = make_double2(v[0].x - v[2].x, v[0].y - v[2].y);
+    const double2 t2 = make_double2(v[1].x + v[3].x, v[1].y + v[3].y), t3 = make_double2(v[1].x - v[3].x, v[1].y - v[3].y);
+    v[0] = make_double2(t0.x + t2.x, t0.y + t2.y);
+    v[2] = make_double2(t0.x - t2.x, t0.y - t2.y);
+    v[1] = make_double2(t1.x - t3.y, t1.y + t3.x);   // t1 + i t3
+    v[3] = make_double2(t1.x + t3.y, t1.y - t3.x);   // t1 - i t3
+}
+
+template <>
+__device__ __forceinline__ void dft<8>(double2 *v)
+{
+    double2 e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+    dft<4>(e);
+    dft<4>(o);
+    const double r = 0.7071067811865476;
+    // o_r * w8^r:  w8 = (1 + i) / sqrt(2), w8^2 = i, w8^3 = (-1 + i) / sqrt(2)
+    const double2 o1 = make_double2(r * (o[1].x - o[1].y), r * (o[1].x + o[1].y));
+    const double2 o2 = make_double2(-o[2].y, o[2].x);
+    const double2 o3 = make_double2(-r * (o[3].x + o[3].y), r * (o[3].x - o[3].y));
+    v[0] = make_double2(e[0].x + o[0].x, e[0].y + o[0].y);
+    v[4] = make_double2(e[0].x - o[0].x, e[0].y - o[0].y);
+    v[1] = make_double2(e[1].x + o1.x, e[1].y + o1.y);
+    v[5] = make_double2(e[1].x - o1.x, e[1].y - o1.y);
+    v[2] = make_double2(e[2].x + o2.x, e[2].y + o2.y);
+    v[6] = make_double2(e[2].x - o2.x, e[2].y - o2.y);
+    v[3] = make_double2(e[3].x + o3.x, e[3].y + o3.y);
+    v[7] = make_double2(e[3].x - o3.x, e[3].y - o3.y);
+}
+
+// One decimation-in-frequency stage of radix R on the blocks of length L = R << lgsub of one line:
+// sub-block r of every block receives the sequence whose length-(L / R) transform is X[R j + r].
+template <int R>
+__device__ __forceinline__ void fft_stage(double2 *buf, const double2 *tw, int nf, int lgsub, int lane)
+{
+    const int sub = 1 << lgsub, L = R << lgsub, tstep = nf / L;
+    for (int t = lane; t < nf / R; t += 32) {
+        const int blk = t >> lgsub, i = t & (sub - 1);
+        const int base = blk * L + i;
+        double2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = buf[padded(base + q * sub)];
+        dft<R>(v);
+        buf[padded(base)] = v[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) buf[padded(base + r * sub)] = (i == 0) ? v[r] : cmul(v[r], tw[r * i * tstep]);
+    }
+    __syncwarp();
+}
+
+// One warp transforms one line of nf complex doubles in shared memory (element p at buf[padded(p)]), in place:
+//   X[k] = sum_l x[l] exp(+2 pi i k l / nf);   X[k] ends up at element fft_pos(k) (mixed-radix digit reversal,
+// undone for free by the pruned read-out).  Radices: 3 (if nf = 3 * 2^a), then 8s, then 4 or 2.
 // tw[t] = exp(+2 pi i t / nf).
 __device__ __forceinline__ void fft_line(double2 *buf, const double2 *tw, const NufftGeom &g, int lane)
 {
-    const int nf = g.nf, m = g.m;
+    int lg = g.log2m;   // log2 of the current block length (after the radix-3 stage)
+    if (g.r3) fft_stage<3>(buf, tw, g.nf, lg, lane);
+    for (; lg >= 3; lg -= 3) fft_stage<8>(buf, tw, g.nf, lg - 3, lane);
+    if (lg == 2) fft_stage<4>(buf, tw, g.nf, 0, lane);
+    else if (lg == 1) fft_stage<2>(buf, tw, g.nf, 0, lane);
+}
+
+// element index, after fft_line, of X[k]
+__device__ __forceinline__ int fft_pos(int k, const NufftGeom &g)
+{
+    int p = 0, lg = g.log2m;
     if (g.r3) {
-        // X[3 j + r] = FFT_m(Y_r)[j],  Y_r[t] = W^(r t) sum_q w3^(r q) x[t + q m],  w3 = exp(2 pi i / 3)
-        const double hs = 0.8660254037844386;   // sin(2 pi / 3)
-        for (int t = lane; t < m; t += 32) {
-            const double2 a = buf[t], b = buf[t + m], c = buf[t + 2 * m];
-            const double2 s = make_double2(b.x + c.x, b.y + c.y);
-            const double2 d = make_double2(b.x - c.x, b.y - c.y);
-            const double2 y0 = make_double2(a.x + s.x, a.y + s.y);
-            const double2 h = make_double2(a.x - 0.5 * s.x, a.y - 0.5 * s.y);
-            // w3 b + w3^2 c = -s/2 + i hs d ;  w3^2 b + w3^4 c = -s/2 - i hs d
-            const double2 y1 = make_double2(h.x - hs * d.y, h.y + hs * d.x);
-            const double2 y2 = make_double2(h.x + hs * d.y, h.y - hs * d.x);
-            buf[t] = y0;
-            buf[t + m] = cmul(y1, tw[t]);
-            buf[t + 2 * m] = cmul(y2, tw[2 * t]);   // 2 t < 2 m < nf
-        }
-        __syncwarp();
+        const int d = k % 3;
+        k /= 3;
+        p = d * g.m;
     }
-    int tstep = nf / m;   // nf / L for the current stage
-    for (int lg = g.log2m; lg >= 1; --lg, tstep <<= 1) {
-        const int half = 1 << (lg - 1);
-        for (int t = lane; t < (nf >> 1); t += 32) {
-            const int blk = t >> (lg - 1), i = t & (half - 1);
-            const int base = (blk << lg) + i;
-            const double2 a = buf[base], b = buf[base + half];
-            buf[base] = make_double2(a.x + b.x, a.y + b.y);
-            const double2 d = make_double2(a.x - b.x, a.y - b.y);
-            buf[base + half] = (i == 0) ? d : cmul(d, tw[i * tstep]);
-        }
-        __syncwarp();
+    for (; lg >= 3; lg -= 3) {
+        p += (k & 7) << (lg - 3);
+        k >>= 3;
     }
+    if (lg == 2) p += k & 3;
+    else if (lg == 1) p += k & 1;
+    return p;
 }
 
 __global__ void nufft_twiddles(int nf, double2 *tw)
@@ -157,8 +215,10 @@ __global__ void nufft_bin_scatter(const double *__restrict__ posd, int64_t N, co
 // ---- spreading -------------------------------------------------------------------------------------
 
 // One warp per particle.  Lanes cover one z row of the kernel's support as interleaved (re, im) doubles, so a
-// warp-wide RED touches 2 w consecutive doubles; rows (x, y offsets) are walked in a loop.
+// warp-wide RED touches 2 W consecutive doubles; the W x W rows (x, y offsets) are walked in a fully unrolled
+// loop whose body is one DMUL, one address add and the RED (W <= 8: two rows per instruction, split by x).
 // posd f64 (F, 3, N): the float32 coordinates widened exactly; iL = 1 / L0.
+template <int W>
 __global__ void __launch_bounds__(NU_THREADS)
 nufft_spread(const double *__restrict__ posd, int64_t N, const int2 *__restrict__ sets, int n_sets, int e0,
              const int *__restrict__ order, int64_t maxlen, NufftGeom g, double iLx, double iLy, double iLz,
@@ -169,18 +229,19 @@ nufft_spread(const double *__restrict__ posd, int64_t N, const int2 *__restrict_
     const int e = e0 + blockIdx.y, f = e / n_sets, s = e - f * n_sets;
     const int2 set = sets[s];
     const int len = set.y - set.x;
-    const int nf = g.nf, w = g.w;
+    const int nf = g.nf;
     const double *px = posd + ((int64_t)f * 3 + 0) * N;
     const double *py = posd + ((int64_t)f * 3 + 1) * N;
     const double *pz = posd + ((int64_t)f * 3 + 2) * N;
     double *G = grid + (size_t)blockIdx.y * nf * nf * nf * 2;
-    const double hw = 0.5 * (double)w, ihw = 2.0 / (double)w, inf = 1.0 / (double)nf;
+    const double hw = 0.5 * (double)W, ihw = 2.0 / (double)W, inf = 1.0 / (double)nf;
 
-    const int lpr = (w <= 8) ? 16 : 32;          // lanes per z row
-    const int rpi = 32 / lpr;                    // rows per warp-wide instruction
-    const int rsel = lane / lpr, within = lane - rsel * lpr, dz = within >> 1, ri = within & 1;
-    const bool act = dz < w;
+    constexpr int LPR = (W <= 8) ? 16 : 32;      // lanes per z row
+    constexpr int RPI = 32 / LPR;                // rows per warp-wide instruction
+    const int rsel = lane / LPR, within = lane - rsel * LPR, dz = within >> 1, ri = within & 1;
+    const bool act = dz < W;
     const int t = lane & 15;
+    const unsigned plane = (unsigned)nf * (unsigned)nf * 2u;   // doubles per x plane (nf <= 1024: fits)
 
     for (int idx = blockIdx.x * (NU_THREADS / 32) + warp; idx < len; idx += gridDim.x * (NU_THREADS / 32)) {
         const int64_t j = order ? (int64_t)order[(int64_t)blockIdx.y * maxlen + idx] : (int64_t)set.x + idx;
@@ -193,38 +254,65 @@ nufft_spread(const double *__restrict__ posd, int64_t N, const int2 *__restrict_
             l0a = (int)c;
             const double z = (c + (double)t - x) * ihw;
             const double a = fmax(1.0 - z * z, 0.0);
-            sv[warp][lane >> 4][t] = t < w ? exp(g.beta * (sqrt(a) - 1.0)) : 0.0;
+            sv[warp][lane >> 4][t] = t < W ? exp(g.beta * (sqrt(a) - 1.0)) : 0.0;
         }
         {
             const double c = ceil(gz - hw);
             l0z = (int)c;
             const double z = (c + (double)t - gz) * ihw;
             const double a = fmax(1.0 - z * z, 0.0);
-            if (lane < 16) sv[warp][2][t] = t < w ? exp(g.beta * (sqrt(a) - 1.0)) : 0.0;
+            if (lane < 16) sv[warp][2][t] = t < W ? exp(g.beta * (sqrt(a) - 1.0)) : 0.0;
         }
         const int l0x = __shfl_sync(0xffffffffu, l0a, 0), l0y = __shfl_sync(0xffffffffu, l0a, 16);
         // strength exp(2 pi i k0 (sx + sy + sz)) of the centred modes
         double sn, cs;
         sincospi(2.0 * (double)g.k0 * ((gx + gy + gz) * inf), &sn, &cs);
         __syncwarp();
-        const double zc = act ? sv[warp][2][dz] * (ri ? sn : cs) : 0.0;
-        int Z = l0z + dz;
-        Z = Z < 0 ? Z + nf : (Z >= nf ? Z - nf : Z);
-        const size_t zoff = (size_t)Z * 2 + ri;
-        int ix = 0, iy = rsel;
-        for (int r = rsel; r < w * w; r += rpi) {
-            int X = l0x + ix, Y = l0y + iy;
-            X = X < 0 ? X + nf : (X >= nf ? X - nf : X);
-            Y = Y < 0 ? Y + nf : (Y >= nf ? Y - nf : Y);
-            const double v = zc * (sv[warp][0][ix] * sv[warp][1][iy]);
-            if (act) atomicAdd(G + ((size_t)X * nf + Y) * nf * 2 + zoff, v);
-            iy += rpi;
-            if (iy >= w) {
-                iy -= w;
-                ++ix;
+        if (act) {
+            const double zc = sv[warp][2][dz] * (ri ? sn : cs);
+            int Z = l0z + dz;
+            Z = Z < 0 ? Z + nf : (Z >= nf ? Z - nf : Z);
+            double vy[W];
+            unsigned yo[W];
+#pragma unroll
+            for (int iy = 0; iy < W; ++iy) {
+                int Y = l0y + iy;
+                Y = Y < 0 ? Y + nf : (Y >= nf ? Y - nf : Y);
+                vy[iy] = sv[warp][1][iy];
+                yo[iy] = ((unsigned)Y * (unsigned)nf + (unsigned)Z) * 2u + (unsigned)ri;
+            }
+#pragma unroll 2
+            for (int ix = rsel; ix < W; ix += RPI) {
+                int X = l0x + ix;
+                X = X < 0 ? X + nf : (X >= nf ? X - nf : X);
+                double *gp = G + (size_t)X * plane;
+                const double vxz = zc * sv[warp][0][ix];
+#pragma unroll
+                for (int iy = 0; iy < W; ++iy) atomicAdd(gp + yo[iy], vxz * vy[iy]);
             }
         }
         __syncwarp();
+    }
+}
+
+typedef void (*spread_fn)(const double *, int64_t, const int2 *, int, int, const int *, int64_t, NufftGeom, double,
+                          double, double, double *);
+spread_fn spread_kernel(int w)
+{
+    switch (w) {
+    case 4: return nufft_spread<4>;
+    case 5: return nufft_spread<5>;
+    case 6: return nufft_spread<6>;
+    case 7: return nufft_spread<7>;
+    case 8: return nufft_spread<8>;
+    case 9: return nufft_spread<9>;
+    case 10: return nufft_spread<10>;
+    case 11: return nufft_spread<11>;
+    case 12: return nufft_spread<12>;
+    case 13: return nufft_spread<13>;
+    case 14: return nufft_spread<14>;
+    case 15: return nufft_spread<15>;
+    default: return nufft_spread<16>;
     }
 }
 
@@ -238,13 +326,13 @@ nufft_fft_z(const double2 *__restrict__ grid, double2 *__restrict__ out, const d
     double2 *tw = reinterpret_cast<double2 *>(nu_smem);
     const int nf = g.nf;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double2 *line = tw + nf + warp * nf;
+    double2 *line = tw + nf + warp * (nf + (nf >> 3));
     for (int i = threadIdx.x; i < nf; i += NU_THREADS) tw[i] = tw_g[i];
     __syncthreads();
     const int64_t lines = (int64_t)nf * nf;
     for (int64_t ln = (int64_t)blockIdx.x * (NU_THREADS / 32) + warp; ln < lines; ln += (int64_t)gridDim.x * (NU_THREADS / 32)) {
         const double2 *src = grid + ((size_t)blockIdx.y * lines + ln) * nf;
-        for (int i = lane; i < nf; i += 32) line[i] = src[i];
+        for (int i = lane; i < nf; i += 32) line[padded(i)] = src[i];
         __syncwarp();
         fft_line(line, tw, g, lane);
         double2 *dst = out + ((size_t)blockIdx.y * lines + ln) * g.ncp;
@@ -253,7 +341,7 @@ nufft_fft_z(const double2 *__restrict__ grid, double2 *__restrict__ out, const d
             if (c < g.n) {
                 int k = c - g.k0;
                 if (k < 0) k += nf;
-                v = line[fft_pos(k, g)];
+                v = line[padded(fft_pos(k, g))];
             }
             dst[c] = v;
         }
@@ -262,7 +350,7 @@ nufft_fft_z(const double2 *__restrict__ grid, double2 *__restrict__ out, const d
 }
 
 // y and x axes: lines are strided.  in[(o * nf + l) * S + i] -> a block takes NU_TC consecutive i of one o,
-// transposes them into shared memory (pitch nf + 1: conflict free), one warp per line.
+// transposes them into shared memory (odd pitch: conflict free), one warp per line.
 //   !FINAL:  out[(o * n + k) * S + i]                      (y pass: O = nf, S = ncp)
 //   FINAL:   i = b * ncp + c, k = a;  part[row_qoff[b n + a] + c] = X * dec[a] dec[b] dec[c]   (x pass: O = 1, S = n ncp)
 template <bool FINAL>
@@ -273,7 +361,7 @@ nufft_fft_s(const double2 *__restrict__ in, double2 *__restrict__ out, const dou
 {
     extern __shared__ __align__(16) unsigned char nu_smem[];
     double2 *tw = reinterpret_cast<double2 *>(nu_smem);
-    const int nf = g.nf, n = g.n, pitch = nf + 1;
+    const int nf = g.nf, n = g.n, pitch = nf + (nf >> 3) + 1;   // odd: the transposing stores are conflict free
     double2 *tile = tw + nf;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tiles = (S + NU_TC - 1) / NU_TC;
@@ -296,7 +384,7 @@ nufft_fft_s(const double2 *__restrict__ in, double2 *__restrict__ out, const dou
     for (int e = threadIdx.x; e < nf * NU_TC; e += NU_THREADS) {
         const int l = e / NU_TC, ii = e - l * NU_TC;
         const int64_t gi = i0 + ii;
-        tile[ii * pitch + l] = gi < S ? src[(size_t)l * S + gi] : make_double2(0.0, 0.0);
+        tile[ii * pitch + padded(l)] = gi < S ? src[(size_t)l * S + gi] : make_double2(0.0, 0.0);
     }
     __syncthreads();
     fft_line(tile + warp * pitch, tw, g, lane);
@@ -307,7 +395,7 @@ nufft_fft_s(const double2 *__restrict__ in, double2 *__restrict__ out, const dou
         if (gi >= S) continue;
         int kk = k - g.k0;
         if (kk < 0) kk += nf;
-        const double2 v = tile[ii * pitch + fft_pos(kk, g)];
+        const double2 v = tile[ii * pitch + padded(fft_pos(kk, g))];
         if (!FINAL) {
             out[(((size_t)blockIdx.y * O + o) * n + k) * S + gi] = v;
         } else {
@@ -361,11 +449,9 @@ double phihat(double xi, double beta, const std::vector<double> &gx, const std::
 
 bool Nufft::supported(int n_points) { return n_points >= 2 && 1.5 * n_points <= 1024.0; }
 
-int Nufft::init(const Ctx *ctx, int n_points, double eps_, int64_t max_set_len)
+bool Nufft::geometry(int n_points, double eps, NufftGeom *out)
 {
-    if (!supported(n_points)) return fail(MDC_ERR_UNSUPPORTED, "nufft: n_points out of range");
-    eps = eps_;
-    maxlen = max_set_len;
+    if (!supported(n_points)) return false;
     // fine grid: the smallest 2^a or 3 * 2^a with nf >= 2 n while the grid is small, nf >= 1.5 n otherwise
     std::vector<int> cand;
     for (int a = 5; a <= 10; ++a) cand.push_back(1 << a);
@@ -378,7 +464,8 @@ int Nufft::init(const Ctx *ctx, int n_points, double eps_, int64_t max_set_len)
     };
     int nf = at_least(2.0 * n_points);
     if (nf == 0 || nf > 160) nf = at_least(1.5 * n_points);
-    if (nf == 0) return fail(MDC_ERR_UNSUPPORTED, "nufft: n_points out of range");
+    if (nf == 0) return false;
+    NufftGeom g{};
     g.n = n_points;
     g.ncp = (n_points + 1) & ~1;
     g.k0 = n_points / 2;
@@ -388,9 +475,27 @@ int Nufft::init(const Ctx *ctx, int n_points, double eps_, int64_t max_set_len)
     g.log2m = 0;
     while ((1 << g.log2m) < g.m) ++g.log2m;
     const double sigma = (double)nf / n_points;
-    int w = (int)ceil((log(1.0 / eps) + log(5.0)) / (M_PI * sqrt(1.0 - 1.0 / sigma)));
+    const int w = (int)ceil((log(1.0 / eps) + log(5.0)) / (M_PI * sqrt(1.0 - 1.0 / sigma)));
     g.w = std::max(4, std::min(16, w));
     g.beta = 0.975 * M_PI * g.w * (1.0 - 1.0 / (2.0 * sigma));
+    *out = g;
+    return true;
+}
+
+// seconds per frame for n_sets sets holding sum_len particles in total (rates measured on B200)
+double Nufft::cost(const NufftGeom &g, int n_sets, int64_t sum_len)
+{
+    const double nf = g.nf, n = g.n;
+    const double bytes = 16.0 * (2.0 * nf * nf * nf + 2.0 * nf * nf * n + 2.0 * nf * n * n);
+    return n_sets * (bytes / 3.0e12 + 60e-6) + (double)sum_len * g.w * g.w * g.w / 2.5e11;
+}
+
+int Nufft::init(const Ctx *ctx, int n_points, double eps_, int64_t max_set_len)
+{
+    if (!geometry(n_points, eps_, &g)) return fail(MDC_ERR_UNSUPPORTED, "nufft: n_points out of range");
+    eps = eps_;
+    maxlen = max_set_len;
+    const int nf = g.nf;
 
     std::vector<double> gx, gw, hdec(n_points);
     gauss_legendre(96, gx, gw);
@@ -404,8 +509,8 @@ int Nufft::init(const Ctx *ctx, int n_points, double eps_, int64_t max_set_len)
     nufft_twiddles<<<(nf + 255) / 256, 256>>>(nf, tw.p);
     MDC_CUDA(cudaGetLastError());
 
-    smem_z = sizeof(double2) * ((size_t)nf + (size_t)(NU_THREADS / 32) * nf);
-    smem_s = sizeof(double2) * ((size_t)nf + (size_t)NU_TC * (nf + 1));
+    smem_z = sizeof(double2) * ((size_t)nf + (size_t)(NU_THREADS / 32) * (nf + nf / 8));
+    smem_s = sizeof(double2) * ((size_t)nf + (size_t)NU_TC * (nf + nf / 8 + 1));
     if (smem_z > ctx->smem_optin || smem_s > ctx->smem_optin)
         return fail(MDC_ERR_UNSUPPORTED, "nufft: fine grid line does not fit shared memory");
     MDC_CUDA(cudaFuncSetAttribute(nufft_fft_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z));
@@ -467,7 +572,7 @@ int Nufft::density(cudaStream_t st, const double *posd, const double iL[3], int6
             ord = order.p;
         }
         const unsigned sblocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(maxlen, NU_THREADS / 32), 148 * 32));
-        nufft_spread<<<dim3(sblocks, B), NU_THREADS, 0, st>>>(posd, N, d_sets, n_sets, e0, ord, maxlen, g, iL[0], iL[1],
+        spread_kernel(g.w)<<<dim3(sblocks, B), NU_THREADS, 0, st>>>(posd, N, d_sets, n_sets, e0, ord, maxlen, g, iL[0], iL[1],
                                                              iL[2], reinterpret_cast<double *>(grid.p));
         const unsigned zblocks = (unsigned)std::min<int64_t>(ceil_div((int64_t)nf * nf, NU_THREADS / 32), 148 * 16);
         nufft_fft_z<<<dim3(zblocks, B), NU_THREADS, smem_z, st>>>(grid.p, buf1.p, tw.p, g);

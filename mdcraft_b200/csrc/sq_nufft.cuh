@@ -28,6 +28,8 @@ struct Nufft {
 
     // chooses nf / w for `n_points` modes per axis and the requested relative accuracy
     static bool supported(int n_points);
+    static bool geometry(int n_points, double eps, NufftGeom *out);
+    static double cost(const NufftGeom &g, int n_sets, int64_t sum_len);   // seconds per frame (model)
     int init(const Ctx *ctx, int n_points, double eps, int64_t max_set_len);
     int reserve(int batch_hint);      // allocates the work buffers (first push)
     void release();

@@ -60,6 +60,11 @@ sel = np.random.default_rng(0).choice(wv.shape[0], size=min(4096, wv.shape[0]), 
 ref = _capi.SqPlan(ctx, [N], [(None, None)], wavevectors=wv[sel], precision="fp64")
 ref.push(dev, n_frames=F)
 r, _ = ref.read()
+ctx.synchronize()
+ctx.mark(0)
+ref.push(dev, n_frames=F)
+ctx.mark(1)
+print(f"FP64 reference kernel: {sel.size * N * F / (ctx.elapsed_ms() * 1e-3) / 1e9:.2f} G terms/s")
 ref.close()
 r = r[0] / F / N
 for name, arr in (("nufft", a), ("nufft64", a64), ("factored", b)):
