@@ -229,6 +229,7 @@ def run_native(args, rank, world, emit=print):
     sq_dev = torch.from_numpy(sq_host).cuda()
     gr_pin = torch.from_numpy(gr_host).pin_memory()
     sq_pin = torch.from_numpy(sq_host).pin_memory()
+    ssf_pin = torch.empty((1, nq), dtype=torch.float64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -245,7 +246,7 @@ def run_native(args, rank, world, emit=print):
             rdf.push(gr_pin.numpy(), None, box_g, n_frames=F)
             sqp.push(sq_pin.numpy(), n_frames=F)
             rdf.read()
-            sqp.read()
+            sqp.read(out=ssf_pin.numpy())
 
     def timed(device_resident, steps):
         """Device time of `steps` steps: CUDA events on the library's compute stream around each step

@@ -224,6 +224,21 @@ int  mdc_radial_histogram(mdc_ctx *ctx, const float *pos_a, int64_t n_a,
                           int n_bins, double r0, double r1,
                           int64_t excl0, int64_t excl1, int64_t *counts_out);
 
+/* ---- g(r)-derived radial transforms ---------------- */
+
+#define MDC_TRANSFORM_FOURIER_3D  0   /* (4 pi / q) int f(r) r sin(q r) dr      structure.py:176-215 */
+#define MDC_TRANSFORM_HANKEL_2D   1   /* 2 pi int f(r) r J0(q r) dr             structure.py:134-173 */
+
+/*
+ * out[k] = prefactor(q_k) * sum_i weights[i] f[i] r[i] K(q_k r[i])  in FP64, with K = sin (3-D) or J0 (2-D) and
+ * the q = 0 limits of the reference.  `weights` are the quadrature weights of the samples r (the reference uses
+ * scipy.integrate.simpson, which is linear: weights = simpson(identity, x = r)).  Host arrays; r, f, weights have
+ * n_r elements, q and out n_q.
+ */
+int  mdc_radial_transform(mdc_ctx *ctx, int kind, const double *r, const double *f,
+                          const double *weights, int64_t n_r,
+                          const double *q, int64_t n_q, double *out);
+
 /* ---- timing (CUDA events on the context's compute stream) ---------------- */
 
 /*

@@ -101,6 +101,7 @@ SIGNATURES = {
         c_int,
         [c_void_p, _fp, c_int64, _fp, c_int64, _fp, c_int, c_double, c_double, c_int64, c_int64, _lp],
     ),
+    "mdc_radial_transform": (c_int, [c_void_p, c_int, _dp, _dp, _dp, c_int64, _dp, c_int64, _dp]),
     "mdc_sq_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_rdf_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_probe_rate": (c_int, [c_void_p, c_int, _dp]),
@@ -246,6 +247,21 @@ class Context:
         return out
 
 
+    def radial_transform(self, kind: str, r, f, weights, q) -> np.ndarray:
+        """``structure.py:134-215``: ``kind`` = ``"fourier3d"`` or ``"hankel2d"``; FP64 on the device."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1)
+        if not (r.shape == f.shape == w.shape) or r.ndim != 1:
+            raise ValueError("r, f and weights must be 1-D arrays of equal length")
+        out = np.empty(q.shape[0], dtype=np.float64)
+        _check(lib().mdc_radial_transform(
+            self._h, {"fourier3d": 0, "hankel2d": 1}[kind], _as(r, _dp), _as(f, _dp), _as(w, _dp), r.shape[0],
+            _as(q, _dp), q.shape[0], _as(out, _dp)))
+        return out
+
+
 class _DeviceArray:
     """Exposes a library-owned accumulator through ``__cuda_array_interface__`` (for NCCL via torch)."""
 
@@ -327,9 +343,13 @@ class SqPlan:
             raise ValueError(f"positions have {n_el} elements, expected {n_frames} x {self.n_particles} x 3")
         _check(lib().mdc_sq_push(self._h, ptr, int(n_frames), on_dev))
 
-    def read(self):
-        """Un-normalised sums ``(n_pairs, Nq)`` and the number of frames accumulated."""
-        out = np.empty((self.n_pairs, self.n_wavevectors), dtype=np.float64)
+    def read(self, out: Optional[np.ndarray] = None):
+        """Un-normalised sums ``(n_pairs, Nq)`` and the number of frames accumulated.  ``out``: optional
+        C-contiguous float64 array of that shape to read into (e.g. a view of pinned memory)."""
+        if out is None:
+            out = np.empty((self.n_pairs, self.n_wavevectors), dtype=np.float64)
+        elif out.dtype != np.float64 or not out.flags.c_contiguous or out.size != self.n_pairs * self.n_wavevectors:
+            raise ValueError("out must be a C-contiguous float64 array with n_pairs x Nq elements")
         nf = c_int64()
         _check(lib().mdc_sq_read(self._h, _as(out, _dp), byref(nf)))
         return out, nf.value

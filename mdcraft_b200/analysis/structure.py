@@ -119,12 +119,25 @@ def delta_fourier_transform_sum(qs, rs, *, precision: str = "fp64", device: int 
 # ----------------------------------------------------------------------------
 
 
-def zeroth_order_hankel_transform(r, f, q):
-    """``structure.py:134-173``: 2-D radial Fourier transform by Simpson quadrature."""
+def simpson_weights(r) -> np.ndarray:
+    """Quadrature weights ``w`` with ``simpson(y, x=r) == w @ y``: SciPy's composite Simpson rule is linear in its
+    integrand, so applying it to the identity yields its weights exactly (end correction for an even number of
+    samples included)."""
+    from scipy.integrate import simpson
+
+    r = np.asarray(r, dtype=float)
+    return simpson(np.eye(r.shape[0]), x=r)
+
+
+def zeroth_order_hankel_transform(r, f, q, *, device: Optional[int] = None):
+    """``structure.py:134-173``: 2-D radial Fourier transform by Simpson quadrature.  ``device``: evaluate the
+    dense ``(n_q, n_r)`` sum on that GPU (FP64) instead of in NumPy."""
     from scipy.integrate import simpson
     from scipy.special import jv
 
     r, f, q = np.asarray(r), np.asarray(f), np.asarray(q, dtype=float)
+    if device is not None:
+        return _context(device).radial_transform("hankel2d", r, f, simpson_weights(r), q).reshape(q.shape)
     ht = 2 * np.pi * simpson(f * r * jv(0, np.outer(q, r)), x=r)
     zero = q == 0
     if zero.any():
@@ -132,11 +145,14 @@ def zeroth_order_hankel_transform(r, f, q):
     return ht
 
 
-def radial_fourier_transform(r, f, q):
-    """``structure.py:176-215``: 3-D radial Fourier transform by Simpson quadrature."""
+def radial_fourier_transform(r, f, q, *, device: Optional[int] = None):
+    """``structure.py:176-215``: 3-D radial Fourier transform by Simpson quadrature.  ``device``: evaluate the
+    dense ``(n_q, n_r)`` sum on that GPU (FP64) instead of in NumPy."""
     from scipy.integrate import simpson
 
     r, f, q = np.asarray(r), np.asarray(f), np.asarray(q, dtype=float)
+    if device is not None:
+        return _context(device).radial_transform("fourier3d", r, f, simpson_weights(r), q).reshape(q.shape)
     with np.errstate(divide="ignore", invalid="ignore"):
         rft = 4 * np.pi * np.divide(simpson(f * r * np.sin(np.outer(q, r)), x=r), q)
     zero = q == 0
@@ -174,8 +190,10 @@ def calculate_coordination_numbers(bins, rdf, rho, *, n_coord_nums: int = 2, n_d
 def calculate_structure_factor(
     r, g, equal: bool, rho: float, x_a: float = 1, x_b: float = None, q=None, *,
     q_lower: float = None, q_upper: float = None, n_q: int = 1_000, n_dims: int = 3, formalism: str = "FZ",
+    device: Optional[int] = None,
 ):
-    """``structure.py:322-488``: S(q) from g(r) by radial Fourier (3-D) or Hankel (2-D) transform."""
+    """``structure.py:322-488``: S(q) from g(r) by radial Fourier (3-D) or Hankel (2-D) transform.  ``device``
+    (extra, optional): evaluate the transform on that GPU."""
     if q is None:
         if q_lower is None:
             q_lower = 2 * np.pi / r[-1]
@@ -188,7 +206,7 @@ def calculate_structure_factor(
         transform = zeroth_order_hankel_transform
     else:
         raise ValueError("Invalid number of dimensions.")
-    rho_sft = rho * transform(r, g - 1, q)
+    rho_sft = rho * transform(r, g - 1, q, device=device)
     if equal or formalism == "FZ":
         return q, 1 + rho_sft
     if formalism == "AL":
@@ -456,6 +474,7 @@ class RadialDistributionFunction(DynamicAnalysisBase):
         self.results.wavenumbers, self.results.ssf = calculate_structure_factor(
             self.results.bins, self._get_rdf(), self._groups[0] == self._groups[1], rho, x_a, x_b, q=q,
             q_lower=q_lower, q_upper=q_upper, n_q=n_q, n_dims=2 + (self._drop_axis is None), formalism=formalism,
+            device=self._device,   # the class already owns a context on this GPU
         )
 
 

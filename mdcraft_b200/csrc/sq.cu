@@ -982,12 +982,15 @@ static int sq_plan_create_impl(mdc_ctx *ctx, int n_points, const double L0[3], d
     if (p->n_lat > 0 && Nufft::supported(n_points)) {
         if (algo == MDC_SQ_ALGO_NUFFT) {
             p->nufft_on = true;
-        } else if (algo == MDC_SQ_ALGO_AUTO && precision == MDC_PRECISION_FP32) {
-            // cost model (measured rates): factored kernel vs fine grid traffic + spreading
+        } else if (algo == MDC_SQ_ALGO_AUTO) {
+            // cost model (rates measured on B200): the O(Nq N) kernel of this precision (factored
+            // FP32: 4.4e12 terms/s; FP64 reference arithmetic: 3.4e11 terms/s) vs fine-grid traffic + spreading
+            const bool f64 = precision == MDC_PRECISION_FP64;
             NufftGeom ng;
-            const double t_fact = (double)p->n_lat * (double)sum_set / 4.4e12;
-            const double t_nufft = Nufft::geometry(n_points, 1e-9, &ng) ? Nufft::cost(ng, p->n_sets, sum_set) : 1e30;
-            p->nufft_on = t_nufft < t_fact;
+            const double t_terms = (double)p->n_lat * (double)sum_set / (f64 ? 3.4e11 : 4.4e12);
+            const double t_nufft =
+                Nufft::geometry(n_points, f64 ? 1e-13 : 1e-9, &ng) ? Nufft::cost(ng, p->n_sets, sum_set) : 1e30;
+            p->nufft_on = t_nufft < t_terms;
         }
     }
     p->lattice_fast = (precision == MDC_PRECISION_FP32) && p->n_lat > 0 && !p->nufft_on;

@@ -214,5 +214,33 @@ def main():
     save("histogram_pins.npz", n_cases=len(cases), **hist)
 
 
+def transforms():
+    """g(r)-derived transforms: the reference's radial_fourier_transform,
+    zeroth_order_hankel_transform and calculate_structure_factor on a synthetic liquid-like g(r), for an odd and
+    an even number of samples (SciPy's Simpson rule treats them differently) and with q = 0 present."""
+    st, _ = ref_loader.load()
+    out = {}
+    for tag, n in (("odd", 201), ("even", 200)):
+        r = (np.arange(n) + 0.5) * (8.0 / n)
+        g = 1 + 1.8 * np.cos(2 * np.pi * (r - 1.0) / 0.95) * np.exp(-(r - 1.0) / 1.3) * (r > 0.85)
+        g[r <= 0.85] = 0.0
+        q = np.concatenate(([0.0], np.linspace(0.3, 25.0, 300)))
+        out[f"{tag}_r"], out[f"{tag}_g"], out[f"{tag}_q"] = r, g, q
+        out[f"{tag}_rft"] = st.radial_fourier_transform(r, g - 1, q)
+        # The reference's 2-D transform (structure.py:170-172) multiplies q * r elementwise instead of forming the
+        # outer product and then tests `0 in q`: it raises for every q except a length-1 array, the form pinned here.
+        out[f"{tag}_ht_q"] = np.array([2.5, 7.0])
+        out[f"{tag}_ht"] = np.array([float(st.zeroth_order_hankel_transform(r, g - 1, np.array([qq])))
+                                     for qq in (2.5, 7.0)])
+        out[f"{tag}_q3"], out[f"{tag}_s3"] = st.calculate_structure_factor(r, g, True, 0.8, n_q=64)
+        out[f"{tag}_qal"], out[f"{tag}_sal"] = st.calculate_structure_factor(r, g, False, 0.5, 0.3, 0.7, n_q=48,
+                                                                            formalism="AL")
+    save("transforms.npz", **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "transforms":
+        transforms()
+    else:
+        main()
+        transforms()

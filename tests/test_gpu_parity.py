@@ -270,6 +270,49 @@ def test_rdf_post_processing_runs():
     assert r.results.ssf.shape == (32,)
 
 
+def test_radial_transforms_on_device_golden():
+    """the dense (n_q x n_r) transforms evaluated by the device kernel, against the outputs of
+    the reference's own functions and against the host NumPy path."""
+    from mdcraft_b200.analysis import structure
+
+    g = golden("transforms.npz")
+    for tag in ("odd", "even"):
+        r, gr, q = g[f"{tag}_r"], g[f"{tag}_g"], g[f"{tag}_q"]
+        np.testing.assert_allclose(structure.radial_fourier_transform(r, gr - 1, q, device=0), g[f"{tag}_rft"],
+                                   rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(structure.zeroth_order_hankel_transform(r, gr - 1, g[f"{tag}_ht_q"], device=0),
+                                   g[f"{tag}_ht"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(structure.zeroth_order_hankel_transform(r, gr - 1, q, device=0),
+                                   structure.zeroth_order_hankel_transform(r, gr - 1, q), rtol=1e-12, atol=1e-12)
+        qq, s = structure.calculate_structure_factor(r, gr, True, 0.8, n_q=64, device=0)
+        np.testing.assert_array_equal(qq, g[f"{tag}_q3"])
+        np.testing.assert_allclose(s, g[f"{tag}_s3"], rtol=1e-12, atol=1e-12)
+
+
+def test_fourier_route_matches_direct_route():
+    """The consistency check rank 3 exists for: S(q) from g(r) by radial Fourier transform (device) against the
+    direct S(q) of the same frames, one call each.  Configuration: a lattice with jitter larger than half its
+    spacing, i.e. no Bragg peaks left and S(q) = 1 - exp(-q^2 sigma^2) (suppressed long-wavelength fluctuations).
+    The two estimators differ by the truncation of g(r) at L/2, binning and the noise of single |q| shells."""
+    from mdcraft_b200 import synthetic
+
+    n, rho, F, jitter = 4000, 0.8, 6, 0.6
+    L = synthetic.cubic_box_length(n, rho)
+    pos = np.stack([synthetic.lj_like_frame(n, L, 900 + f, jitter=jitter) for f in range(F)]).astype(np.float32)
+    u = universe_from(pos, np.array([L, L, L, 90, 90, 90], np.float32))
+    r = _rdf(u.atoms, n_bins=400, range_=(0.0, L / 2), exclusion=(1, 1))
+    s = _sq(u.atoms, n_points=24)
+    q = s.results.wavenumbers
+    sel = (q > 1.0) & (q < 8.0)
+    r.calculate_structure_factor(rho, q=q[sel])
+    direct, fourier = s.results.ssf[0][sel], r.results.ssf
+    k = np.ones(15) / 15   # shell-average the direct estimate (single |q| shells are noisy)
+    smooth = lambda y: np.convolve(y, k, mode="valid")   # noqa: E731
+    assert np.max(np.abs(smooth(direct) - smooth(fourier))) < 0.15
+    model = 1 - np.exp(-(smooth(q[sel]) * jitter) ** 2)
+    assert np.max(np.abs(smooth(fourier) - model)) < 0.15
+
+
 # --------------------------------------------------------------------------- S(q) class
 
 

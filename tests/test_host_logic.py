@@ -197,3 +197,28 @@ def test_center_of_mass_groupings():
     np.testing.assert_allclose(algorithm.center_of_mass(u.atoms), (masses[:, None] * pos[0]).sum(0) / masses.sum(), rtol=1e-12)
     with pytest.raises(ValueError, match="Invalid grouping"):
         algorithm.center_of_mass(u.atoms, "molecules")
+
+
+def test_transforms_match_the_reference_golden():
+    """radial_fourier_transform / calculate_structure_factor (host NumPy path) against outputs of the reference's
+    own functions (tests/golden/make_golden.py transforms); Simpson weights reproduce scipy's rule for odd and even
+    sample counts."""
+    from scipy.integrate import simpson
+
+    from conftest import golden
+
+    g = golden("transforms.npz")
+    for tag in ("odd", "even"):
+        r, gr, q = g[f"{tag}_r"], g[f"{tag}_g"], g[f"{tag}_q"]
+        np.testing.assert_allclose(structure.radial_fourier_transform(r, gr - 1, q), g[f"{tag}_rft"], rtol=1e-13, atol=1e-13)
+        qq, s = structure.calculate_structure_factor(r, gr, True, 0.8, n_q=64)
+        np.testing.assert_array_equal(qq, g[f"{tag}_q3"])
+        np.testing.assert_allclose(s, g[f"{tag}_s3"], rtol=1e-13, atol=1e-13)
+        qq, s = structure.calculate_structure_factor(r, gr, False, 0.5, 0.3, 0.7, n_q=48, formalism="AL")
+        np.testing.assert_allclose(s, g[f"{tag}_sal"], rtol=1e-13, atol=1e-13)
+        # the 2-D transform: the reference only works for length-1 q (structure.py:170-172); same numbers here
+        np.testing.assert_allclose(structure.zeroth_order_hankel_transform(r, gr - 1, g[f"{tag}_ht_q"]), g[f"{tag}_ht"],
+                                   rtol=1e-13, atol=1e-13)
+        w = structure.simpson_weights(r)
+        y = np.sin(r) * r
+        np.testing.assert_allclose(w @ y, simpson(y, x=r), rtol=1e-14)
