@@ -62,6 +62,7 @@ extern "C" {
 typedef struct mdc_ctx      mdc_ctx;
 typedef struct mdc_sq_plan  mdc_sq_plan;
 typedef struct mdc_rdf_plan mdc_rdf_plan;
+typedef struct mdc_dump     mdc_dump;
 
 /* ---- library / context ------------------------------------------------- */
 
@@ -238,6 +239,35 @@ int  mdc_radial_histogram(mdc_ctx *ctx, const float *pos_a, int64_t n_a,
 int  mdc_radial_transform(mdc_ctx *ctx, int kind, const double *r, const double *f,
                           const double *weights, int64_t n_r,
                           const double *q, int64_t n_q, double *out);
+
+/* ---- frame ingest: LAMMPS text dumps ---------------- */
+
+/*
+ * Replaces /root/reference/src/mdcraft/analysis/reader.py:24-572 (LAMMPSDumpTrajectoryReader) for orthogonal boxes
+ * and unscaled coordinates (x y z / xu yu zu), with or without an id column.
+ *
+ * mdc_dump_open memory-maps the file, reads the first header, builds the frame index with host threads
+ * (reader.py:138-210; every frame must hold the same number of atoms, as the reference requires at read time) and
+ * parses every frame's header (time step, box).  `conventions`: NULL = automatic (reader.py:438-447), else
+ * "cx,cy,cz" with c in {"u", "su", "", "s", "-"} ("-" ignores the axis).  n_threads <= 0: all host threads.
+ *
+ * mdc_dump_read parses frames [f0, f0 + n_frames) ON THE GPU: the raw text goes to HBM once, one thread converts
+ * one atom line, and positions come out as float32 (n_frames, n_atoms, 3) sorted by atom id (reader.py:550-552),
+ * each value equal to float32(float(token)) bit for bit.  pos_out is a device pointer (on_device != 0; ready to be
+ * handed to mdc_sq_push / mdc_rdf_push) or host memory.  The block must be below 2 GiB of text
+ * (mdc_dump_block_bytes).
+ *
+ * info: [n_frames, n_atoms, has_id, convention index of x, y, z in {"u","su","","s"} (-1: axis absent), n_columns,
+ *        values of the last read that needed the host parser].
+ * headers: steps i64 (n_frames), box f32 (n_frames, 6), origin f64 (n_frames, 3) = (xlo, ylo, zlo), offsets i64
+ *        (n_frames + 1) byte offsets of the frames; any pointer may be NULL.
+ */
+int      mdc_dump_open(const char *path, const char *conventions, int n_threads, mdc_dump **out);
+int      mdc_dump_close(mdc_dump *dump);
+int      mdc_dump_info(mdc_dump *dump, int64_t info[8]);
+int      mdc_dump_headers(mdc_dump *dump, int64_t *steps, float *box, double *origin, int64_t *offsets);
+int64_t  mdc_dump_block_bytes(mdc_dump *dump, int64_t f0, int n_frames);
+int      mdc_dump_read(mdc_dump *dump, mdc_ctx *ctx, int64_t f0, int n_frames, float *pos_out, int on_device);
 
 /* ---- timing (CUDA events on the context's compute stream) ---------------- */
 

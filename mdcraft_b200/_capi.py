@@ -102,6 +102,12 @@ SIGNATURES = {
         [c_void_p, _fp, c_int64, _fp, c_int64, _fp, c_int, c_double, c_double, c_int64, c_int64, _lp],
     ),
     "mdc_radial_transform": (c_int, [c_void_p, c_int, _dp, _dp, _dp, c_int64, _dp, c_int64, _dp]),
+    "mdc_dump_open": (c_int, [c_char_p, c_char_p, c_int, POINTER(c_void_p)]),
+    "mdc_dump_close": (c_int, [c_void_p]),
+    "mdc_dump_info": (c_int, [c_void_p, _lp]),
+    "mdc_dump_headers": (c_int, [c_void_p, _lp, _fp, _dp, _lp]),
+    "mdc_dump_block_bytes": (c_int64, [c_void_p, c_int64, c_int]),
+    "mdc_dump_read": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int]),
     "mdc_sq_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_rdf_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_probe_rate": (c_int, [c_void_p, c_int, _dp]),
@@ -262,6 +268,17 @@ class Context:
         return out
 
 
+_contexts: dict = {}
+
+
+def context(device: int = 0) -> Context:
+    """One library context per CUDA device per process (shared by the analysis classes and the readers)."""
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = _contexts[device] = Context(device)
+    return ctx
+
+
 class _DeviceArray:
     """Exposes a library-owned accumulator through ``__cuda_array_interface__`` (for NCCL via torch)."""
 
@@ -369,6 +386,64 @@ class SqPlan:
         ms, nl = c_float(), c_int()
         _check(lib().mdc_sq_last_push_stats(self._h, byref(ms), byref(nl)))
         return ms.value, nl.value
+
+
+class DumpFile:
+    """``mdc_dump``: a memory-mapped LAMMPS text dump whose atom lines are parsed on the GPU."""
+
+    CONVENTIONS = ("u", "su", "", "s")
+
+    def __init__(self, path: str, conventions: Optional[Sequence[Optional[str]]] = None, n_threads: int = 0):
+        self._h = c_void_p()
+        spec = None
+        if conventions is not None:
+            spec = ",".join("-" if c is None else c for c in conventions).encode()
+        _check(lib().mdc_dump_open(os.fsencode(path), spec, int(n_threads), byref(self._h)))
+        info = (c_int64 * 8)()
+        _check(lib().mdc_dump_info(self._h, info))
+        self.n_frames, self.n_atoms, self.has_id = int(info[0]), int(info[1]), bool(info[2])
+        self.conventions = [None if info[3 + k] < 0 else self.CONVENTIONS[info[3 + k]] for k in range(3)]
+        self.n_columns = int(info[6])
+        self.steps = np.empty(self.n_frames, dtype=np.int64)
+        self.box = np.empty((self.n_frames, 6), dtype=np.float32)
+        self.origin = np.empty((self.n_frames, 3), dtype=np.float64)
+        self.offsets = np.empty(self.n_frames + 1, dtype=np.int64)
+        _check(lib().mdc_dump_headers(self._h, _as(self.steps, _lp), _as(self.box, _fp), _as(self.origin, _dp),
+                                      _as(self.offsets, _lp)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().mdc_dump_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def block_bytes(self, f0: int, n_frames: int) -> int:
+        return int(lib().mdc_dump_block_bytes(self._h, int(f0), int(n_frames)))
+
+    def last_host_parsed(self) -> int:
+        """Values of the last ``read`` that the device's exact fast path handed to the host parser."""
+        info = (c_int64 * 8)()
+        _check(lib().mdc_dump_info(self._h, info))
+        return int(info[7])
+
+    def read(self, ctx: "Context", f0: int, n_frames: int, out=None):
+        """Positions of frames ``[f0, f0 + n_frames)`` as float32 ``(n_frames, n_atoms, 3)`` in atom-id order.
+        ``out``: a host array or a device buffer (``__cuda_array_interface__``) to fill; default: a new host array."""
+        if out is None:
+            out = np.empty((int(n_frames), self.n_atoms, 3), dtype=np.float32)
+        ptr, on_dev, keep = _buffer(out)
+        if not on_dev and keep is not out:
+            raise ValueError("out must be a C-contiguous float32 array")
+        n_el = int(np.prod(keep.shape)) if hasattr(keep, "shape") else None
+        if n_el is not None and n_el != int(n_frames) * self.n_atoms * 3:
+            raise ValueError(f"out has {n_el} elements, expected {n_frames} x {self.n_atoms} x 3")
+        _check(lib().mdc_dump_read(self._h, ctx._h, int(f0), int(n_frames), ptr, on_dev))
+        return out
 
 
 class ScsfPlan(SqPlan):

@@ -67,15 +67,9 @@ except ImportError:  # plain strings keep ``results.units`` meaningful without p
 #: N_A * k_B in kJ / (mol K) (exact, 2019 SI)
 _GAS_CONSTANT_KJ = 0.00831446261815324
 
-_contexts: dict = {}
-
-
 def _context(device: int = 0) -> _capi.Context:
     """One library context per CUDA device per process."""
-    ctx = _contexts.get(device)
-    if ctx is None:
-        ctx = _contexts[device] = _capi.Context(device)
-    return ctx
+    return _capi.context(device)
 
 
 # ----------------------------------------------------------------------------

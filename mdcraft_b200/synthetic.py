@@ -44,13 +44,14 @@ __all__ = [
 class Timestep:
     """One frame: positions, box and bookkeeping (MDAnalysis ``Timestep`` subset)."""
 
-    __slots__ = ("positions", "_dimensions", "frame", "time")
+    __slots__ = ("positions", "_dimensions", "frame", "time", "data")
 
-    def __init__(self, positions, dimensions, frame=0, time=0.0):
+    def __init__(self, positions, dimensions, frame=0, time=0.0, data=None):
         self.positions = positions
         self._dimensions = dimensions
         self.frame = frame
         self.time = time
+        self.data = {} if data is None else data
 
     @property
     def dimensions(self):
@@ -140,9 +141,12 @@ class MemoryTrajectory:
             pos = self._root._array[i]
         else:
             pos = np.ascontiguousarray(self._root._frame_fn(i), dtype=np.float32)
-        ts = Timestep(pos, self._root._dims_of(i), frame=i, time=i * self._root.dt)
+        ts = self._root._make_timestep(i, pos)
         self._root._ts = ts
         return ts
+
+    def _make_timestep(self, i: int, pos) -> Timestep:
+        return Timestep(pos, self._dims_of(i), frame=i, time=i * self.dt)
 
     @property
     def ts(self) -> Timestep:

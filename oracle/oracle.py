@@ -492,3 +492,58 @@ def rdf(
         "bin_edges": edges, "bins": bins, "counts": counts, "rdf": counts / nrm,
         "n_frames": n_frames, "volume": vol,
     }
+
+
+# ----------------------------------------------------------------------------
+# frame ingest
+# ----------------------------------------------------------------------------
+
+
+def read_lammps_dump(path: str, dt: float = 1.0):
+    """
+    CPU restatement of ``LAMMPSDumpTrajectoryReader`` (reader.py:353-562) for the layouts the GPU reader takes:
+    orthogonal box, unscaled coordinates, optional ids.  Pure Python (small files only); pinned by
+    tests/golden/dumps.npz, which the reference's own reader produced.
+
+    Returns ``positions f32 (F, N, 3)``, ``dimensions f32 (F, 6)``, ``steps i64 (F,)``, ``times f64 (F,)``,
+    ``offsets`` (byte offset of every frame, reader.py:138-210).
+    """
+    with open(path, "rb") as fh:
+        raw = fh.read()
+    lines = raw.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    starts = np.concatenate(([0], np.cumsum([len(x) + 1 for x in lines])))
+    positions, dims, steps, offsets = [], [], [], []
+    i = 0
+    while i + 9 <= len(lines):
+        n = int(lines[i + 3])
+        if i + 9 + n > len(lines):
+            break
+        offsets.append(int(starts[i]))
+        steps.append(int(lines[i + 1]))
+        bounds = [[float(v) for v in lines[i + 5 + ax].split()] for ax in range(3)]                # reader.py:415-417
+        dims.append(np.array([b[1] - b[0] for b in bounds] + [90, 90, 90]).astype(np.float32))       # :418
+        cols = {a.decode(): k for k, a in enumerate(lines[i + 8].split()[2:])}                       # :425
+        axes = []
+        for ax in "xyz":                                                                            # :438-447
+            for c in ("u", "su", "", "s"):
+                if ax + c in cols:
+                    axes.append(cols[ax + c])
+                    break
+            else:
+                axes.append(-1)
+        pos = np.zeros((n, 3), dtype=np.float32)
+        ids = np.empty(n, dtype=int)
+        for a in range(n):
+            values = lines[i + 9 + a].split()
+            if "id" in cols:
+                ids[a] = int(values[cols["id"]])
+            # ts.positions[i] = tuple(str): NumPy casts str -> float64 -> float32                    # :503-505
+            pos[a] = [0 if k == -1 else np.float32(float(values[k])) for k in axes]
+        if "id" in cols:
+            pos = pos[np.argsort(ids)]                                                               # :550-552
+        positions.append(pos)
+        i += 9 + n
+    steps = np.array(steps, dtype=np.int64)
+    return np.stack(positions), np.stack(dims), steps, steps * dt, np.array(offsets)

@@ -20,6 +20,8 @@ import os
 import sys
 import types
 
+import numpy as np
+
 REF_SRC = "/root/reference/src"
 _loaded = None
 
@@ -174,3 +176,64 @@ def load_polymer():
         sys.modules["mdcraft.fit"] = fit
         sys.modules["mdcraft"].fit = fit
     return importlib.import_module("mdcraft.analysis.polymer")
+
+
+class _RefTimestep:
+    """MDAnalysis ``Timestep`` subset the reference reader writes into (reader.py:353-562): float32 positions /
+    velocities / forces, a float32 ``dimensions`` setter, ``data`` and ``dt``."""
+
+    def __init__(self, n_atoms, dt=1.0, **kwargs):
+        self.n_atoms = n_atoms
+        self.positions = np.zeros((n_atoms, 3), dtype=np.float32)
+        self.velocities = np.zeros((n_atoms, 3), dtype=np.float32)
+        self.forces = np.zeros((n_atoms, 3), dtype=np.float32)
+        self.has_velocities = self.has_forces = False
+        self.data = {}
+        self.dt = dt
+        self.frame = -1
+        self._dimensions = np.zeros(6, dtype=np.float32)
+
+    @property
+    def dimensions(self):
+        return self._dimensions.copy()
+
+    @dimensions.setter
+    def dimensions(self, box):
+        self._dimensions = np.asarray(box, dtype=np.float32)   # [RECALL] MDAnalysis stores the box as float32
+
+    @property
+    def time(self):
+        return self.data.get("time", self.frame * self.dt)
+
+
+class _RefReaderBase:
+    """``MDAnalysis.coordinates.base.ReaderBase`` subset: what ``LAMMPSDumpTrajectoryReader.__init__`` relies on."""
+
+    _Timestep = _RefTimestep
+
+    def __init__(self, filename, convert_units=True, **kwargs):
+        self.filename = filename
+        self.convert_units = convert_units
+        self._ts_kwargs = {"dt": kwargs.get("dt", 1.0)}
+
+    def __len__(self):
+        return self.n_frames
+
+    def __getitem__(self, i):
+        return self._read_frame(int(i))
+
+
+def load_reader():
+    """The real ``mdcraft.analysis.reader`` (LAMMPSDumpTrajectoryReader) on a stub ``ReaderBase``."""
+    load()
+    sys.modules["MDAnalysis.coordinates.base"].ReaderBase = _RefReaderBase
+    dist = sys.modules["MDAnalysis.lib.distances"]
+    if not hasattr(dist, "transform_StoR"):
+        dist.transform_StoR = lambda coords, box: coords * np.asarray(box[:3])   # orthogonal boxes only; unused here
+    if "MDAnalysis.lib.util" not in sys.modules:
+        util = types.ModuleType("MDAnalysis.lib.util")
+        util.anyopen = lambda f, *a, **k: open(f, *a, **k)
+        util.store_init_arguments = lambda fn: fn
+        sys.modules["MDAnalysis.lib.util"] = util
+        sys.modules["MDAnalysis.lib"].util = util
+    return importlib.import_module("mdcraft.analysis.reader")

@@ -238,9 +238,83 @@ def transforms():
     save("transforms.npz", **out)
 
 
+def write_dump(path, pos, ids, box_lo, box_hi, steps, columns, fmt, extra=None, literal=None):
+    """A LAMMPS text dump: pos (F, N, 3) written with the per-frame format functions fmt[f](value) -> str."""
+    F, N, _ = pos.shape
+    with open(path, "w") as fh:
+        for f in range(F):
+            fh.write(f"ITEM: TIMESTEP\n{steps[f]}\nITEM: NUMBER OF ATOMS\n{N}\nITEM: BOX BOUNDS pp pp pp\n")
+            for ax in range(3):
+                fh.write(f"{float(box_lo[f][ax])!r} {float(box_hi[f][ax])!r}\n")
+            fh.write("ITEM: ATOMS " + " ".join(columns) + "\n")
+            for i in range(N):
+                fields = []
+                for c in columns:
+                    if c == "id":
+                        fields.append(str(ids[f][i]))
+                    elif c in ("x", "y", "z", "xu", "yu", "zu"):
+                        ax = "xyz".index(c[0])
+                        fields.append((literal or {}).get((f, i, ax)) or fmt[f](pos[f, i, ax]))
+                    else:
+                        fields.append(extra(c, f, i))
+                fh.write(" ".join(fields) + (" \n" if i % 7 == 3 else "\n"))   # some trailing blanks
+
+
+def dumps():
+    """Frame ingest: small LAMMPS dumps and what the reference's LAMMPSDumpTrajectoryReader
+    (reader.py, unmodified, on the ReaderBase stub of oracle/ref_loader.py) reads from them."""
+    rd = ref_loader.load_reader()
+    rng = np.random.default_rng(77)
+    out = {}
+    F, N = 5, 60
+    pos = rng.normal(scale=8.0, size=(F, N, 3))
+    # number syntax the device's exact fast path must get right or hand to the host parser: a float32 midpoint
+    # nudged by less than half a double ulp (double rounding), > 2^53 mantissas, long digit strings, odd but valid
+    # float() literals, non-finite values
+    lits = ["0", "-0", "1e-30", "123456789.125", "1.00000005960464477625798673798840354720596224069595336914062",
+            "9007199254740993", "0.1e1", "1E+2", "-.5", "5.", "+3.25", "1e23", "8.5e-23", "123456789012345678901234567890e-25",
+            "0.000000000000000000000000000001234", "nan", "-inf", "1e400", "4.35", "-7.0000000000000000000001"]
+    literal = {(0, i, i % 3): lit for i, lit in enumerate(lits)}
+    ids = np.stack([rng.permutation(N) + 1 for _ in range(F)])
+    lo = rng.normal(size=(F, 3)) - 10.0
+    hi = lo + 20.0 + rng.random((F, 3))
+    steps = [0, 500, 1000, 1500, 2500]
+    fmts = [lambda v: "%g" % v, lambda v: "%.17g" % v, lambda v: "%20.15e" % v, lambda v: "%+.8f" % v, lambda v: repr(float(v))]
+    extra = lambda c, f, i: {"type": str(1 + i % 3), "vx": "%g" % (0.1 * i), "q": "-1.5e-3"}[c]   # noqa: E731
+    # (a) ids shuffled per frame, extra columns around the coordinates
+    a = os.path.join(HERE, "dump_ids.lammpsdump")
+    write_dump(a, pos, ids, lo, hi, steps, ["id", "type", "x", "y", "vx", "z", "q"], fmts, extra, literal)
+    # (b) no id column, unwrapped names
+    b = os.path.join(HERE, "dump_noid.lammpsdump")
+    write_dump(b, pos, ids, lo, hi, steps, ["type", "xu", "yu", "zu"], fmts, extra, literal)
+    # (c) ids that are not a contiguous range (a dumped sub-group)
+    c = os.path.join(HERE, "dump_sparse_ids.lammpsdump")
+    sparse = np.stack([rng.permutation(np.arange(N) * 7 + 3) for _ in range(F)])
+    write_dump(c, pos, sparse, lo, hi, steps, ["x", "y", "z", "id"], fmts, extra)
+    for tag, path in (("ids", a), ("noid", b), ("sparse", c)):
+        r = rd.LAMMPSDumpTrajectoryReader(path, dt=0.005)
+        got_pos, got_dim, got_step, got_time = [], [], [], []
+        for f in range(r.n_frames):
+            ts = r[f]
+            got_pos.append(ts.positions.copy())
+            got_dim.append(ts.dimensions)
+            got_step.append(ts.data["step"])
+            got_time.append(ts.data["time"])
+        out[f"{tag}_positions"] = np.stack(got_pos)
+        out[f"{tag}_dimensions"] = np.stack(got_dim)
+        out[f"{tag}_steps"] = np.array(got_step)
+        out[f"{tag}_times"] = np.array(got_time)
+        out[f"{tag}_offsets"] = np.array(r._offsets)
+        out[f"{tag}_conventions"] = np.array(["-" if c_ is None else c_ for c_ in r._conventions])
+        r.close()
+    save("dumps.npz", **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "transforms":
-        transforms()
-    else:
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "main"):
         main()
+    if which in ("all", "transforms"):
         transforms()
+    if which in ("all", "dumps"):
+        dumps()

@@ -512,3 +512,99 @@ def test_scsf_golden(precision, algorithm):
         want = oracle.scsf([p[lo:hi] for p in g["pos"]], m, N, g["dims"][:3], n_points=int(g["n_points"]), q_max=3.0)
         np.testing.assert_array_equal(r2.results.wavenumbers, want["wavenumbers"])
         np.testing.assert_allclose(r2.results.scsf[ig], want["scsf"][0], **tol)
+
+
+# --------------------------------------------------------------------------- frame ingest (§8f rank 4)
+
+
+@pytest.mark.parametrize("tag,name", [("ids", "dump_ids"), ("noid", "dump_noid"), ("sparse", "dump_sparse_ids")])
+def test_dump_reader_golden(tag, name):
+    """LAMMPS dumps parsed on the GPU against what the reference's own reader read from the same files: positions
+    bit for bit (double-rounded literals, > 2^53 mantissas, nan / inf through the host parser), boxes, steps, times."""
+    import os
+
+    from conftest import GOLDEN
+    from mdcraft_b200.analysis.reader import LAMMPSDumpTrajectoryReader
+
+    g = golden("dumps.npz")
+    r = LAMMPSDumpTrajectoryReader(os.path.join(GOLDEN, name + ".lammpsdump"), dt=0.005, frame_block=2)
+    assert (r.n_frames, r.n_atoms) == (5, 60)
+    assert ["-" if c is None else c for c in r._conventions] == list(g[f"{tag}_conventions"])
+    assert r._offsets == list(g[f"{tag}_offsets"])
+    for f, ts in enumerate(r):
+        np.testing.assert_array_equal(ts.positions, g[f"{tag}_positions"][f])
+        np.testing.assert_array_equal(ts.dimensions, g[f"{tag}_dimensions"][f])
+        assert ts.frame == f and ts.data["step"] == g[f"{tag}_steps"][f] and ts.time == g[f"{tag}_times"][f]
+    np.testing.assert_array_equal(r.frames_block(0, 5), g[f"{tag}_positions"])
+    if tag != "sparse":                           # the literals of frame 0 that the exact fast path refuses
+        assert r.host_parsed_values() >= 5
+    np.testing.assert_array_equal(r.frames_block(1, 5), g[f"{tag}_positions"][1:])
+    assert r.host_parsed_values() <= 1            # %.17g, %e, %f and repr() output all take the device path
+    np.testing.assert_array_equal(r[3].positions, g[f"{tag}_positions"][3])          # random access
+    np.testing.assert_array_equal(r.frames_block_device(2, 4).cpu().numpy(), g[f"{tag}_positions"][2:4])
+    r.close()
+
+
+def test_dump_reader_feeds_the_analysis_classes(tmp_path):
+    """A 3,000-atom dump with shuffled ids: the GPU reader against the CPU oracle, and g(r) / S(q) driven from the
+    reader (per-frame protocol and device-resident blocks) against the same analyses on the in-memory trajectory."""
+    from mdcraft_b200 import _capi, synthetic
+    from mdcraft_b200.analysis.reader import LAMMPSDumpTrajectoryReader
+    from oracle import oracle
+
+    n, F, L = 3000, 7, 15.0
+    rng = np.random.default_rng(12)
+    pos = (rng.random((F, n, 3)) * L)
+    path = tmp_path / "traj.lammpsdump"
+    with open(path, "w") as fh:
+        for f in range(F):
+            fh.write(f"ITEM: TIMESTEP\n{100 * f}\nITEM: NUMBER OF ATOMS\n{n}\nITEM: BOX BOUNDS pp pp pp\n")
+            fh.write(f"0 {L}\n0 {L}\n0 {L}\nITEM: ATOMS id type x y z\n")
+            fmt = ("%d 1 %.8g %.8g %.8g\n", "%d 1 %.17g %.17g %.17g\n", "%d 1 %r %r %r\n", "%d 1 %.19e %.16e %.12f\n")[f % 4]
+            for i in rng.permutation(n):
+                fh.write(fmt % (i + 1, *(float(v) for v in pos[f, i])))
+    want, dims, steps, _, _ = oracle.read_lammps_dump(str(path))
+    r = LAMMPSDumpTrajectoryReader(str(path), parallel=True, frame_block=3)
+    np.testing.assert_array_equal(r.frames_block(0, F), want)
+    # 17-20 significant digits go through the checked double-double division on the device; only literals with more
+    # than 19 digits (%.19e) and quotients within 2^-30 ulp of a rounding boundary are left to the host
+    assert r.host_parsed_values() <= 2 * n * 3
+    np.testing.assert_array_equal(r.frames_block(0, 3), want[:3])
+    assert r.host_parsed_values() <= 2
+    np.testing.assert_array_equal(np.stack([ts.positions for ts in r[1:6:2]]), want[1:6:2])
+    u_file, u_mem = synthetic.Universe(r), universe_from(want, dims)
+    a = _rdf(u_file.atoms, n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1))
+    b = _rdf(u_mem.atoms, n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1))
+    np.testing.assert_array_equal(a.results.counts, b.results.counts)
+    np.testing.assert_array_equal(a.times, 100.0 * np.arange(F))     # time = step * dt (reader.py:373)
+    # device-resident blocks straight into a plan: the positions never visit the host
+    ctx = _capi.context(0)
+    plan = _capi.RdfPlan(ctx, 100, (0.0, L / 2), n, None, (1, 1))
+    plan.push(r.frames_block_device(0, 4), None, dims[:4], n_frames=4)
+    plan.push(r.frames_block_device(4, F), None, dims[4:], n_frames=F - 4)
+    counts, _ = plan.read()
+    np.testing.assert_array_equal(counts, b.results.counts)
+    plan.close()
+    s1 = _sq(u_file.atoms, n_points=8).results.ssf
+    s2 = _sq(u_mem.atoms, n_points=8).results.ssf
+    np.testing.assert_array_equal(s1, s2)
+    r.close()
+
+
+def test_dump_reader_refuses_what_it_cannot_match(tmp_path):
+    from mdcraft_b200.analysis.reader import LAMMPSDumpTrajectoryReader
+
+    head = "ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n2\nITEM: BOX BOUNDS pp pp pp\n0 1\n0 1\n0 1\n"
+    p = tmp_path / "s.lammpsdump"
+    p.write_text(head + "ITEM: ATOMS id xs ys zs\n1 0.1 0.2 0.3\n2 0.4 0.5 0.6\n")
+    with pytest.raises(NotImplementedError):
+        LAMMPSDumpTrajectoryReader(str(p))
+    p.write_text(head + "ITEM: ATOMS id x y z\n1 0.1 0.2 0.3\n2 0.4 0.5\n")
+    with pytest.raises(Exception, match="fewer columns"):
+        LAMMPSDumpTrajectoryReader(str(p))
+    with pytest.raises(ValueError, match="Invalid convention"):
+        LAMMPSDumpTrajectoryReader(str(p), conventions="q")
+    with pytest.raises(ValueError, match="length 3"):
+        LAMMPSDumpTrajectoryReader(str(p), conventions=["", ""])
+    with pytest.raises(NotImplementedError):
+        LAMMPSDumpTrajectoryReader(str(p), unwrap=True)

@@ -222,3 +222,55 @@ def test_transforms_match_the_reference_golden():
         w = structure.simpson_weights(r)
         y = np.sin(r) * r
         np.testing.assert_allclose(w @ y, simpson(y, x=r), rtol=1e-14)
+
+
+def test_dump_index_and_headers_on_the_host(tmp_path):
+    """mdc_dump_open is host code (memory map, threaded newline ranking, header parsing): frame offsets, steps and
+    boxes equal what the reference's reader found (tests/golden/dumps.npz); the threaded index equals the serial one."""
+    import os
+
+    from conftest import GOLDEN, golden
+    from mdcraft_b200 import _capi
+
+    g = golden("dumps.npz")
+    for tag, name, has_id in (("ids", "dump_ids", True), ("noid", "dump_noid", False), ("sparse", "dump_sparse_ids", True)):
+        d = _capi.DumpFile(os.path.join(GOLDEN, name + ".lammpsdump"))
+        assert (d.n_frames, d.n_atoms, d.has_id) == (5, 60, has_id)
+        np.testing.assert_array_equal(d.offsets[:-1], g[f"{tag}_offsets"])
+        np.testing.assert_array_equal(d.steps, g[f"{tag}_steps"])
+        np.testing.assert_array_equal(d.box, g[f"{tag}_dimensions"])
+        assert ["-" if c is None else c for c in d.conventions] == list(g[f"{tag}_conventions"])
+        d.close()
+    # a file large enough for the threaded index (> 4 MiB), last line without a newline
+    n, frames = 4000, 40
+    rng = np.random.default_rng(3)
+    path = tmp_path / "big.lammpsdump"
+    with open(path, "w") as fh:
+        for f in range(frames):
+            fh.write(f"ITEM: TIMESTEP\n{f * 10}\nITEM: NUMBER OF ATOMS\n{n}\nITEM: BOX BOUNDS pp pp pp\n0 10\n0 11\n0 12.5\n")
+            fh.write("ITEM: ATOMS id x y z\n")
+            body = "\n".join("%d %g %g %g" % (i + 1, *rng.random(3) * 10) for i in range(n))
+            fh.write(body + ("\n" if f < frames - 1 else ""))
+    serial = _capi.DumpFile(str(path), n_threads=1)
+    threaded = _capi.DumpFile(str(path), n_threads=7)
+    assert serial.n_frames == threaded.n_frames == frames
+    np.testing.assert_array_equal(serial.offsets, threaded.offsets)
+    assert serial.offsets[-1] == os.path.getsize(path)
+    np.testing.assert_array_equal(threaded.steps, np.arange(frames) * 10)
+    np.testing.assert_array_equal(threaded.box[0], np.array([10, 11, 12.5, 90, 90, 90], np.float32))
+    serial.close()
+    threaded.close()
+    # layouts the reader refuses, with the reference's message where it has one
+    bad = tmp_path / "bad.lammpsdump"
+    bad.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n1\nITEM: BOX BOUNDS xy xz yz pp pp pp\n0 1 0\n0 1 0\n0 1 0\n"
+                   "ITEM: ATOMS id x y z\n1 0 0 0\n")
+    with pytest.raises(_capi.MdcError, match="triclinic"):
+        _capi.DumpFile(str(bad))
+    bad.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n2\nITEM: BOX BOUNDS pp pp pp\n0 1\n0 1\n0 1\n"
+                   "ITEM: ATOMS id x y z\n1 0 0 0\n2 0 0 0\n"
+                   "ITEM: TIMESTEP\n5\nITEM: NUMBER OF ATOMS\n3\nITEM: BOX BOUNDS pp pp pp\n0 1\n0 1\n0 1\n"
+                   "ITEM: ATOMS id x y z\n1 0 0 0\n2 0 0 0\n")
+    with pytest.raises(_capi.MdcError, match="Timestep 5 has 3 atoms, but the topology has 2 atoms"):
+        _capi.DumpFile(str(bad))
+    with pytest.raises(_capi.MdcError, match="convention 'u'"):
+        _capi.DumpFile(os.path.join(GOLDEN, "dump_ids.lammpsdump"), conventions=["u", "u", "u"])

@@ -171,3 +171,20 @@ def test_pair_distance_minimum_image():
     for _ in range(100):
         p, q = (rng.random(3) * box).astype(np.float32), (rng.random(3) * box).astype(np.float32)
         assert oracle.pair_distance(p, q, box) == oracle.pair_distance(q, p, box)
+
+
+@pytest.mark.parametrize("tag,name", [("ids", "dump_ids"), ("noid", "dump_noid"), ("sparse", "dump_sparse_ids")])
+def test_dump_reader_oracle_matches_the_reference_reader(tag, name):
+    """oracle.read_lammps_dump against what the reference's own LAMMPSDumpTrajectoryReader read from the same
+    files (tests/golden/make_golden.py dumps): positions bit for bit (NaN == NaN), boxes, steps, times, offsets."""
+    import os
+
+    from conftest import GOLDEN as GOLDEN_DIR
+
+    g = golden("dumps.npz")
+    pos, dims, steps, times, offsets = oracle.read_lammps_dump(os.path.join(GOLDEN_DIR, name + ".lammpsdump"), dt=0.005)
+    np.testing.assert_array_equal(pos, g[f"{tag}_positions"])
+    np.testing.assert_array_equal(dims, g[f"{tag}_dimensions"])
+    np.testing.assert_array_equal(steps, g[f"{tag}_steps"])
+    np.testing.assert_array_equal(times, g[f"{tag}_times"])
+    np.testing.assert_array_equal(offsets, g[f"{tag}_offsets"])
