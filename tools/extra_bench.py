@@ -39,13 +39,20 @@ def timed(push, n_frames, reps=3):
     return n_frames * reps / (ctx.elapsed_ms() * 1e-3)
 
 
-# C3(i): default grid, FP32 factored / direct and FP64 mode
+# C3(i): default grid, every lattice algorithm and FP64 mode ("auto" = the plan's cost model; the choice is recorded)
 pos, L, n = frames("C3", count=4)
-for key, kw in (("c3_default_grid_factored", {}), ("c3_default_grid_direct", {"algo": "direct"}),
+for key, kw in (("c3_default_grid_auto", {}), ("c3_default_grid_nufft", {"algo": "nufft"}),
+                ("c3_default_grid_factored", {"algo": "factored"}), ("c3_default_grid_direct", {"algo": "direct"}),
                 ("c3_default_grid_fp64_mode", {"precision": "fp64"})):
     plan = _capi.SqPlan(ctx, [n], [(None, None)], n_points=32, L0=[L] * 3, **kw)
     out[key + "_fps"] = timed(lambda: plan.push(pos, n_frames=4), 4)
+    out[key + "_algo"] = plan.info()["algo"]
     plan.close()
+# C3(ii): the q_max = 20 / sigma grid in FP64 mode (auto: NUFFT at 1e-13)
+plan = _capi.SqPlan(ctx, [n], [(None, None)], n_points=161, L0=[L] * 3, q_max=20.0, precision="fp64")
+out["c3_full_grid_fp64_mode_fps"] = timed(lambda: plan.push(pos, n_frames=4), 4)
+out["c3_full_grid_fp64_mode_algo"] = plan.info()["algo"]
+plan.close()
 
 # C4: binary electrolyte, partial S(q) (default grid) and the three g(r)
 pos, L, n = frames("C4")
@@ -53,6 +60,12 @@ half = n // 2
 box = np.array([L, L, L, 90, 90, 90], np.float32)
 plan = _capi.SqPlan(ctx, [half, half], [(0, 0), (0, 1), (1, 1)], n_points=32, L0=[L] * 3)
 out["c4_partial_sq_default_grid_fps"] = timed(lambda: plan.push(pos, n_frames=2), 2)
+out["c4_partial_sq_default_grid_algo"] = plan.info()["algo"]
+plan.close()
+plan = _capi.SqPlan(ctx, [half, half], [(0, 0), (0, 1), (1, 1)], n_points=201, L0=[L] * 3, q_max=20.0)
+out["c4_partial_sq_full_grid_fps"] = timed(lambda: plan.push(pos, n_frames=2), 2)
+out["c4_partial_sq_full_grid_nq"] = plan.n_wavevectors
+out["c4_partial_sq_full_grid_algo"] = plan.info()["algo"]
 plan.close()
 pa, pb = pos[:, :half].contiguous(), pos[:, half:].contiguous()
 pp = _capi.RdfPlan(ctx, 200, (0.0, L / 2), half, None, (1, 1))
@@ -75,6 +88,7 @@ pos, L, n = frames("C5", count=1)
 box = np.array([L, L, L, 90, 90, 90], np.float32)
 plan = _capi.SqPlan(ctx, [n], [(None, None)], n_points=32, L0=[L] * 3)
 out["c5_sq_default_grid_fps"] = timed(lambda: plan.push(pos, n_frames=1), 1)
+out["c5_sq_default_grid_algo"] = plan.info()["algo"]
 plan.close()
 rdf = _capi.RdfPlan(ctx, 200, (0.0, L / 2), n, None, (1, 1))
 out["c5_rdf_fps"] = timed(lambda: rdf.push(pos, None, box, n_frames=1), 1, reps=2)
@@ -85,11 +99,13 @@ rdf.close()
 pos, L, n = frames("C3", n=20_000, count=8)
 isf = _capi.IsfPlan(ctx, [n], [(None, None)], 16, incoherent=True, n_points=32, L0=[L] * 3)
 out["isf_n20000_lags16_incoherent_fps"] = timed(lambda: isf.push(pos, n_frames=8), 8, reps=2)
+out["isf_n20000_lags16_incoherent_algo"] = isf.info()["algo"]
 isf.close()
 M, N = 1000, 100
 pos = torch.from_numpy(np.random.default_rng(0).random((2, M * N, 3)).astype(np.float32) * 40).cuda()
 sc = _capi.ScsfPlan(ctx, M, N, n_points=32, L0=[40.0] * 3)
 out["scsf_1000x100_fps"] = timed(lambda: sc.push(pos, n_frames=2), 2)
+out["scsf_1000x100_algo"] = sc.info()["algo"]
 sc.close()
 
 os.makedirs("gpurun_out", exist_ok=True)
