@@ -153,3 +153,44 @@ def test_c5_million_particles(ctx):
     want = np.abs(rho) ** 2 / n
     tol = 1e-5 * want + 2 * 5 * 1e-7 * np.sqrt(want) + 1e-12
     assert (np.abs(s32[idx] - want) <= tol).all()
+
+
+@pytest.mark.parametrize("n_points,q_max,nf", [(161, 20.0, 256), (171, None, 384), (50, 9.0, 128), (24, None, 48),
+                                               (343, 20.0, 768), (520, 30.0, 1024)])
+def test_nufft_every_fine_grid_family(ctx, n_points, q_max, nf):
+    """Every FFT radix plan of the NUFFT (2^a and 3 * 2^a fine grids, 32 ... 1024 points, shared-memory lines up to
+    147 KB) against the FP64 reference-arithmetic kernel on a random subset of the grid's wavevectors, plus the
+    FP64-mode NUFFT (w = 16) and the partial sum rule."""
+    from mdcraft_b200 import _capi
+
+    n, L = 3000, 40.0
+    rng = np.random.default_rng(n_points)
+    pos = (rng.random((2, n, 3)) * L - 5.0).astype(np.float32)     # some coordinates outside [0, L): the box is periodic
+    L0 = [L, L * 1.07, L * 0.94]
+    plan = _capi.SqPlan(ctx, [n], [(None, None)], n_points=n_points, L0=L0, q_max=q_max, algo="nufft")
+    assert plan.info()["algo"] == "nufft" and plan.info()["nf"] == nf
+    wv = plan.wavevectors()
+    plan.push(pos)
+    got, nfr = plan.read()
+    plan.close()
+    assert nfr == 2
+    sel = rng.choice(wv.shape[0], size=min(2048, wv.shape[0]), replace=False)
+    ref = _capi.SqPlan(ctx, [n], [(None, None)], wavevectors=wv[sel], precision="fp64")
+    ref.push(pos)
+    want, _ = ref.read()
+    ref.close()
+    # |rho|^2 summed over 2 frames; rho ~ sqrt(n): aliasing error <= 1e-8 sqrt(n) in rho
+    tol = 2 * 2 * 1e-8 * np.sqrt(n) * np.sqrt(np.abs(want[0]) / 2 + 1) + 1e-9
+    assert np.max(np.abs(got[0, sel] - want[0]) / tol) < 1.0
+    p64 = _capi.SqPlan(ctx, [n], [(None, None)], n_points=n_points, L0=L0, q_max=q_max, algo="nufft", precision="fp64")
+    p64.push(pos)
+    got64, _ = p64.read()
+    p64.close()
+    np.testing.assert_allclose(got64[0, sel], want[0], rtol=1e-10, atol=1e-9)
+    if n_points <= 171:
+        pp = _capi.SqPlan(ctx, [1200, n - 1200], [(0, 0), (0, 1), (1, 1)], n_points=n_points, L0=L0, q_max=q_max,
+                          algo="nufft")
+        pp.push(pos)
+        parts, _ = pp.read()
+        pp.close()
+        np.testing.assert_allclose(parts.sum(axis=0), got[0], rtol=1e-9, atol=1e-6)
