@@ -503,6 +503,143 @@ __device__ __forceinline__ unsigned bin_or_flag(float v, float thr, unsigned B, 
     return und;
 }
 
+#ifndef MDC_RDF_PACKED
+#define MDC_RDF_PACKED 1   // 1: the FP32 arithmetic of two pairs rides in one packed (f32x2) instruction
+#endif
+
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+
+// filter_v for two particles (u, u + 1) against the same j: identical operations in identical order, issued as
+// packed FP32 (mul / fma .f32x2), so the values are bit-identical to the scalar form
+template <bool CUBIC>
+__device__ __forceinline__ unsigned long long filter_v2(uint32_t ujx, uint32_t ujy, uint32_t ujz, uint32_t ax0,
+                                                        uint32_t ay0, uint32_t az0, uint32_t ax1, uint32_t ay1,
+                                                        uint32_t az1, unsigned long long fax, unsigned long long fay,
+                                                        unsigned long long faz, unsigned long long fc0)
+{
+    unsigned long long tx = pk2((float)(int)(ujx - ax0), (float)(int)(ujx - ax1));
+    unsigned long long ty = pk2((float)(int)(ujy - ay0), (float)(int)(ujy - ay1));
+    unsigned long long tz = pk2((float)(int)(ujz - az0), (float)(int)(ujz - az1));
+    unsigned long long t2, v;
+    float a, b, da, db;
+    if (!CUBIC) {
+        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(tx) : "l"(fax));
+        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(ty) : "l"(fay));
+        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(tz) : "l"(faz));
+    }
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t2) : "l"(tx));
+    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(t2) : "l"(ty));
+    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(t2) : "l"(tz));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(t2));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(da) : "f"(a));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(db) : "f"(b));
+    const unsigned long long d = pk2(da, db);
+    if (CUBIC) {
+        v = fc0;
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(v) : "l"(d), "l"(fax));
+    } else {
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(d), "l"(fc0));
+    }
+    return v;
+}
+
+// bin_or_flag for two pairs whose v arrive packed: w = v + MAGIC, kf = w - MAGIC, df = v - kf as three packed
+// instructions, then the integer / predicate tail per pair as in bin_or_flag
+template <unsigned BIT0, unsigned BIT1, bool HAS_OK>
+__device__ __forceinline__ unsigned bin_or_flag2(unsigned long long v, unsigned long long magic, unsigned long long nmagic,
+                                                 unsigned long long neg1, float thr, unsigned B, unsigned hist_addr,
+                                                 unsigned trash_addr, unsigned ok0, unsigned ok1, unsigned one)
+{
+    unsigned und;
+    if (HAS_OK) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, q, r;\n\t"
+            ".reg .b64 W, KF, DF;\n\t"
+            ".reg .f32 w0, w1, d0, d1;\n\t"
+            ".reg .u32 k, ad, u0, u1;\n\t"
+            "add.rn.f32x2 W, %1, %2;\n\t"
+            "add.rn.f32x2 KF, W, %3;\n\t"
+            "fma.rn.f32x2 DF, KF, %4, %1;\n\t"
+            "mov.b64 {w0, w1}, W;\n\t"
+            "mov.b64 {d0, d1}, DF;\n\t"
+            "abs.f32 d0, d0;\n\t"
+            "mov.b32 k, w0;\n\t"
+            "sub.u32 k, k, 0x4B400000;\n\t"
+            "setp.ne.u32 r, %9, 0;\n\t"
+            "setp.gt.and.f32 q, d0, %5, r;\n\t"
+            "setp.lt.and.u32 p, k, %6, r;\n\t"
+            "and.pred p, p, !q;\n\t"
+            "shl.b32 ad, k, 2;\n\t"
+            "add.u32 ad, ad, %7;\n\t"
+            "selp.u32 ad, ad, %8, p;\n\t"
+            "red.shared.add.u32 [ad], %11;\n\t"
+            "selp.u32 u0, %12, 0, q;\n\t"
+            "abs.f32 d1, d1;\n\t"
+            "mov.b32 k, w1;\n\t"
+            "sub.u32 k, k, 0x4B400000;\n\t"
+            "setp.ne.u32 r, %10, 0;\n\t"
+            "setp.gt.and.f32 q, d1, %5, r;\n\t"
+            "setp.lt.and.u32 p, k, %6, r;\n\t"
+            "and.pred p, p, !q;\n\t"
+            "shl.b32 ad, k, 2;\n\t"
+            "add.u32 ad, ad, %7;\n\t"
+            "selp.u32 ad, ad, %8, p;\n\t"
+            "red.shared.add.u32 [ad], %11;\n\t"
+            "selp.u32 u1, %13, 0, q;\n\t"
+            "or.b32 %0, u0, u1;\n\t"
+            "}"
+            : "=r"(und)
+            : "l"(v), "l"(magic), "l"(nmagic), "l"(neg1), "f"(thr), "r"(B), "r"(hist_addr), "r"(trash_addr), "r"(ok0),
+              "r"(ok1), "r"(one), "n"(BIT0), "n"(BIT1)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, q;\n\t"
+            ".reg .b64 W, KF, DF;\n\t"
+            ".reg .f32 w0, w1, d0, d1;\n\t"
+            ".reg .u32 k, ad, u0, u1;\n\t"
+            "add.rn.f32x2 W, %1, %2;\n\t"
+            "add.rn.f32x2 KF, W, %3;\n\t"
+            "fma.rn.f32x2 DF, KF, %4, %1;\n\t"
+            "mov.b64 {w0, w1}, W;\n\t"
+            "mov.b64 {d0, d1}, DF;\n\t"
+            "abs.f32 d0, d0;\n\t"
+            "mov.b32 k, w0;\n\t"
+            "sub.u32 k, k, 0x4B400000;\n\t"
+            "setp.gt.f32 q, d0, %5;\n\t"
+            "setp.lt.and.u32 p, k, %6, !q;\n\t"
+            "shl.b32 ad, k, 2;\n\t"
+            "add.u32 ad, ad, %7;\n\t"
+            "selp.u32 ad, ad, %8, p;\n\t"
+            "red.shared.add.u32 [ad], %9;\n\t"
+            "selp.u32 u0, %10, 0, q;\n\t"
+            "abs.f32 d1, d1;\n\t"
+            "mov.b32 k, w1;\n\t"
+            "sub.u32 k, k, 0x4B400000;\n\t"
+            "setp.gt.f32 q, d1, %5;\n\t"
+            "setp.lt.and.u32 p, k, %6, !q;\n\t"
+            "shl.b32 ad, k, 2;\n\t"
+            "add.u32 ad, ad, %7;\n\t"
+            "selp.u32 ad, ad, %8, p;\n\t"
+            "red.shared.add.u32 [ad], %9;\n\t"
+            "selp.u32 u1, %11, 0, q;\n\t"
+            "or.b32 %0, u0, u1;\n\t"
+            "}"
+            : "=r"(und)
+            : "l"(v), "l"(magic), "l"(nmagic), "l"(neg1), "f"(thr), "r"(B), "r"(hist_addr), "r"(trash_addr), "r"(one),
+              "n"(BIT0), "n"(BIT1)
+            : "memory");
+    }
+    return und;
+}
+
 template <bool CHECK, bool CUBIC, bool EXCL>
 __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, const uint32_t (&ux)[RF_IPT],
                                                 const uint32_t (&uy)[RF_IPT], const uint32_t (&uz)[RF_IPT],
@@ -515,15 +652,19 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     // an increment the compiler cannot see through (a literal 1 becomes ATOMS.POPC.INC inside a branch)
     const unsigned one = (unsigned)Tp->A.sym | 1u;
     constexpr bool HAS_OK = CHECK || EXCL;
+    static_assert(RF_IPT == 4, "the undecided-pair mask is built for four particles per thread");
+#if MDC_RDF_PACKED
+    const unsigned long long fax = pk2(ff.ax, ff.ax), fay = pk2(ff.ay, ff.ay), faz = pk2(ff.az, ff.az);
+    const unsigned long long fc0 = pk2(ff.c0, ff.c0);
+    const unsigned long long magic = pk2(12582912.f, 12582912.f), nmagic = pk2(-12582912.f, -12582912.f);
+    const unsigned long long neg1 = pk2(-1.f, -1.f);
+#endif
 #pragma unroll 2
     for (int j = 0; j < nj; ++j) {
         const uint4 pj = S->sj[j];
-        static_assert(RF_IPT == 4, "the undecided-pair mask is built for four particles per thread");
-        float v[RF_IPT];
         unsigned ok[RF_IPT];
 #pragma unroll
         for (int u = 0; u < RF_IPT; ++u) {
-            v[u] = filter_v<CUBIC>(pj.x, pj.y, pj.z, ux[u], uy[u], uz[u], ff);
             ok[u] = 1u;
             if (EXCL) ok[u] = bi[u] != (int)pj.w;
             if (CHECK) {
@@ -531,15 +672,31 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                 ok[u] = ok[u] && (ig < na) && (!diag || (j0 + j) > ig);
             }
         }
+#if MDC_RDF_PACKED
+        const unsigned long long v01 = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[0], uy[0], uz[0], ux[1], uy[1], uz[1], fax,
+                                                        fay, faz, fc0);
+        const unsigned long long v23 = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[2], uy[2], uz[2], ux[3], uy[3], uz[3], fax,
+                                                        fay, faz, fc0);
+        const unsigned und =
+            bin_or_flag2<1u, 2u, HAS_OK>(v01, magic, nmagic, neg1, thr, B, hist_addr, trash_addr, ok[0], ok[1], one) |
+            bin_or_flag2<4u, 8u, HAS_OK>(v23, magic, nmagic, neg1, thr, B, hist_addr, trash_addr, ok[2], ok[3], one);
+#else
+        float v[RF_IPT];
+#pragma unroll
+        for (int u = 0; u < RF_IPT; ++u) v[u] = filter_v<CUBIC>(pj.x, pj.y, pj.z, ux[u], uy[u], uz[u], ff);
         const unsigned und = bin_or_flag<1u, HAS_OK>(v[0], thr, B, hist_addr, trash_addr, ok[0], one) |
                              bin_or_flag<2u, HAS_OK>(v[1], thr, B, hist_addr, trash_addr, ok[1], one) |
                              bin_or_flag<4u, HAS_OK>(v[2], thr, B, hist_addr, trash_addr, ok[2], one) |
                              bin_or_flag<8u, HAS_OK>(v[3], thr, B, hist_addr, trash_addr, ok[3], one);
+#endif
         if (und) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
     }
 }
 
-__global__ void __launch_bounds__(RF_THREADS, 3)
+#ifndef MDC_RF_BLOCKS
+#define MDC_RF_BLOCKS 4   // resident blocks per SM the register budget is sized for (64 registers per thread)
+#endif
+__global__ void __launch_bounds__(RF_THREADS, MDC_RF_BLOCKS)
 rdf_pairs_fast(RdfArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -798,6 +955,8 @@ extern "C" int mdc_rdf_plan_create(mdc_ctx *ctx, int n_bins, double r0, double r
         e = cudaFuncSetAttribute(rdf_pairs_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
     if (e == cudaSuccess && !p->force_exact && p->smem_fast > 48 * 1024)
         e = cudaFuncSetAttribute(rdf_pairs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fast);
+    if (e == cudaSuccess && !p->force_exact)   // four ~42 KB blocks per SM need more than the default carve-out
+        e = cudaFuncSetAttribute(rdf_pairs_fast, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->occ_exact, rdf_pairs_exact, RDF_THREADS, p->smem);
     if (e == cudaSuccess && !p->force_exact)
