@@ -241,6 +241,58 @@ class _FrameBlock:
         return self.array[: self.count]
 
 
+def _atom_range(group):
+    """``(lo, hi)`` if the group is a contiguous run of atom indices, else ``None``."""
+    idx = np.asarray(getattr(group, "indices", ()))
+    if idx.size == 0 or idx[-1] - idx[0] + 1 != idx.size or np.any(np.diff(idx) != 1):
+        return None
+    return int(idx[0]), int(idx[-1]) + 1
+
+
+class _DeviceBlockRun:
+    """
+    ``run()`` for trajectories that can hand out frame blocks already resident in HBM
+    (``trajectory.frames_block_device(lo, hi)``, e.g. :class:`mdcraft_b200.analysis.reader.LAMMPSDumpTrajectoryReader`):
+    the per-frame host staging of ``_single_frame`` is skipped and every block goes from the reader's parser straight
+    into the plan.  Results are those of the per-frame protocol (same positions, same boxes, same order); ``frames``
+    and ``times`` are filled in, and the trajectory is left on the last analysed frame.  Used only when every group
+    is an ``"atoms"`` grouping over a contiguous index range; anything else takes the ordinary loop.
+    """
+
+    def _device_block_ranges(self):
+        src = getattr(self._trajectory, "_root", self._trajectory)
+        if not hasattr(src, "frames_block_device") or not hasattr(self._trajectory, "_indices"):
+            return None
+        if any(gr != "atoms" for gr in self._groupings):
+            return None
+        ranges = [_atom_range(g) for g in self._groups]
+        return None if any(r is None for r in ranges) else (src, ranges)
+
+    def _run_device_blocks(self, src, start, stop, step, frames) -> None:
+        from ..synthetic import Timestep
+
+        self._setup_frames(self._trajectory, start=start, stop=stop, step=step, frames=frames)
+        self._prepare()
+        idx = np.asarray(self._sliced_trajectory._indices, dtype=np.int64)
+        i = 0
+        while i < idx.size:
+            j = i + 1
+            while j < idx.size and j - i < self._frame_block and idx[j] == idx[j - 1] + 1:
+                j += 1
+            lo, hi = int(idx[i]), int(idx[j - 1]) + 1
+            block = src.frames_block_device(lo, hi)
+            dims = np.stack([np.asarray(src._dims_of(f), dtype=np.float32) for f in range(lo, hi)])
+            for k, f in enumerate(range(lo, hi)):
+                ts = src._make_timestep(f, None)
+                self.frames[i + k], self.times[i + k] = ts.frame, ts.time
+            self._consume_device_block(block, dims, [Timestep(None, d) for d in dims])
+            i = j
+        if idx.size:
+            self._ts = src[int(idx[-1])]
+            self._frame_index = idx.size - 1
+        self._conclude()
+
+
 def _entity_count(group, grouping: str) -> int:
     return int(getattr(group, f"n_{grouping}"))
 
@@ -254,7 +306,7 @@ def _entity_positions(group, grouping: str) -> np.ndarray:
 # ----------------------------------------------------------------------------
 
 
-class RadialDistributionFunction(DynamicAnalysisBase):
+class RadialDistributionFunction(_DeviceBlockRun, DynamicAnalysisBase):
     r"""
     Radial distribution function :math:`g_{ab}(r)` between two groups (or of one
     group with itself), drop-in for ``mdcraft.analysis.structure
@@ -380,6 +432,26 @@ class RadialDistributionFunction(DynamicAnalysisBase):
         self._frames_seen += 1
         if self._stage_a.full():
             self._flush()
+
+    def run(self, start=None, stop=None, step=None, frames=None, verbose=None, **kwargs):
+        ok = self._device_block_ranges() if self._drop_axis is None else None
+        if ok is None:
+            return super().run(start, stop, step, frames, verbose, **kwargs)
+        self._run_device_blocks(ok[0], start, stop, step, frames)
+        return self
+
+    def _consume_device_block(self, block, dims, timesteps) -> None:
+        (a_lo, a_hi), (b_lo, b_hi) = (_atom_range(g) for g in self._groups)
+        n_all = block.shape[1]
+        a = block if (a_lo, a_hi) == (0, n_all) else block[:, a_lo:a_hi].contiguous()
+        b = None
+        if not self._same:
+            b = block if (b_lo, b_hi) == (0, n_all) else block[:, b_lo:b_hi].contiguous()
+        if self._norm == "rdf":
+            for ts in timesteps:
+                self._area_or_volume += ts.volume
+        self._plan.push(a, b, dims, n_frames=block.shape[0])
+        self._frames_seen += block.shape[0]
 
     def _flush(self) -> None:
         n = self._stage_a.count
@@ -516,7 +588,7 @@ def combine_equal_wavenumbers(ssf: np.ndarray, wavenumbers: np.ndarray, unique_q
     return out
 
 
-class StructureFactor(NumbaAnalysisBase):
+class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
     r"""
     Static structure factor :math:`S(q)` and partial structure factors
     :math:`S_{\alpha\beta}(q)`, drop-in for ``mdcraft.analysis.structure
@@ -693,6 +765,24 @@ class StructureFactor(NumbaAnalysisBase):
         self._frames_seen += 1
         if self._stage.full():
             self._flush()
+
+    def run(self, start=None, stop=None, step=None, frames=None, verbose=None, **kwargs):
+        ok = self._device_block_ranges() if type(self) is StructureFactor else None
+        if ok is None:
+            return super().run(start, stop, step, frames, verbose, **kwargs)
+        self._run_device_blocks(ok[0], start, stop, step, frames)
+        return self
+
+    def _consume_device_block(self, block, dims, timesteps) -> None:
+        ranges = [_atom_range(g) for g in self._groups]
+        if ranges == [(0, block.shape[1])]:
+            pos = block
+        else:   # the groups, concatenated in order (structure.py:1943-1944), still on the device
+            import torch
+
+            pos = torch.cat([block[:, lo:hi] for lo, hi in ranges], dim=1).contiguous()
+        self._plan.push(pos, n_frames=block.shape[0])
+        self._frames_seen += block.shape[0]
 
     def _flush(self) -> None:
         if self._stage.count:

@@ -573,21 +573,51 @@ def test_dump_reader_feeds_the_analysis_classes(tmp_path):
     assert r.host_parsed_values() <= 2
     np.testing.assert_array_equal(np.stack([ts.positions for ts in r[1:6:2]]), want[1:6:2])
     u_file, u_mem = synthetic.Universe(r), universe_from(want, dims)
+    calls = []
+    real = r.frames_block_device
+    r.frames_block_device = lambda lo, hi: (calls.append((lo, hi)), real(lo, hi))[1]
+    # the analysis classes take the reader's device-resident blocks: no host staging, same results
     a = _rdf(u_file.atoms, n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1))
     b = _rdf(u_mem.atoms, n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1))
+    assert calls == [(0, 7)] and r.ts.frame == F - 1
     np.testing.assert_array_equal(a.results.counts, b.results.counts)
+    np.testing.assert_array_equal(a.results.rdf, b.results.rdf)
+    np.testing.assert_array_equal(a.frames, np.arange(F))
     np.testing.assert_array_equal(a.times, 100.0 * np.arange(F))     # time = step * dt (reader.py:373)
-    # device-resident blocks straight into a plan: the positions never visit the host
-    ctx = _capi.context(0)
-    plan = _capi.RdfPlan(ctx, 100, (0.0, L / 2), n, None, (1, 1))
-    plan.push(r.frames_block_device(0, 4), None, dims[:4], n_frames=4)
-    plan.push(r.frames_block_device(4, F), None, dims[4:], n_frames=F - 4)
-    counts, _ = plan.read()
-    np.testing.assert_array_equal(counts, b.results.counts)
-    plan.close()
+    # two groups (cross g(r), partial S(q)), a strided slice of the trajectory, small frame blocks
+    from mdcraft_b200.analysis.structure import RadialDistributionFunction, StructureFactor
+
+    del calls[:]
+    kw = dict(n_bins=64, range_=(0.5, 6.0), verbose=False, frame_block=2)
+    a = RadialDistributionFunction(u_file.select(0, 1200), u_file.select(1200, n), **kw).run(start=1, stop=6, step=2)
+    b = RadialDistributionFunction(u_mem.select(0, 1200), u_mem.select(1200, n), **kw).run(start=1, stop=6, step=2)
+    assert calls == [(1, 2), (3, 4), (5, 6)]
+    np.testing.assert_array_equal(a.results.counts, b.results.counts)
+    np.testing.assert_array_equal(a.results.rdf, b.results.rdf)
+    np.testing.assert_array_equal(a.frames, [1, 3, 5])
+    del calls[:]
+    kw = dict(mode="partial", n_points=8, verbose=False, frame_block=3)
+    s1 = StructureFactor([u_file.select(0, 1200), u_file.select(1200, n)], **kw).run(start=2)
+    s2 = StructureFactor([u_mem.select(0, 1200), u_mem.select(1200, n)], **kw).run(start=2)
+    assert calls == [(2, 5), (5, 7)]
+    np.testing.assert_array_equal(s1.results.ssf, s2.results.ssf)
     s1 = _sq(u_file.atoms, n_points=8).results.ssf
     s2 = _sq(u_mem.atoms, n_points=8).results.ssf
     np.testing.assert_array_equal(s1, s2)
+    # residues groupings fall back to the per-frame protocol (centres of mass are formed on the host)
+    del calls[:]
+    c = _rdf(u_file.atoms, groupings="residues", n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1))
+    assert calls == []
+    np.testing.assert_array_equal(c.results.counts, b.results.counts if False else _rdf(
+        u_mem.atoms, groupings="residues", n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1)).results.counts)
+    # device-resident blocks straight into a plan through the C ABI
+    ctx = _capi.context(0)
+    plan = _capi.RdfPlan(ctx, 100, (0.0, L / 2), n, None, (1, 1))
+    plan.push(real(0, 4), None, dims[:4], n_frames=4)
+    plan.push(real(4, F), None, dims[4:], n_frames=F - 4)
+    counts, _ = plan.read()
+    np.testing.assert_array_equal(counts, _rdf(u_mem.atoms, n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1)).results.counts)
+    plan.close()
     r.close()
 
 
