@@ -395,6 +395,10 @@ struct mdc_dump {
     DevBuf<int> mark, order, status;
     DevBuf<FixEntry> fix;
     int last_fix = 0;
+    // the parser's own stream: the text upload and the parse kernels of block k + 1 overlap the analysis kernels of
+    // block k, which run on the context's streams
+    cudaStream_t stream = nullptr;
+    int stream_device = -1;
 };
 
 namespace {
@@ -414,6 +418,7 @@ void dump_free(mdc_dump *d)
     d->order.release();
     d->status.release();
     d->fix.release();
+    if (d->stream) cudaStreamDestroy(d->stream);
     if (d->data) munmap((void *)d->data, d->size);
     if (d->fd >= 0) close(d->fd);
     delete d;
@@ -657,7 +662,13 @@ extern "C" int mdc_dump_read(mdc_dump *d, mdc_ctx *ctx, int64_t f0, int n_frames
     const int64_t padded = ceil_div(len, DT_TILE) * DT_TILE;
     const unsigned n_tiles = (unsigned)(padded / DT_TILE);
     const unsigned n_lines = (unsigned)((int64_t)F * (9 + N) - 9);
-    cudaStream_t st = ctx->compute;
+    if (!d->stream || d->stream_device != ctx->device) {
+        if (d->stream) cudaStreamDestroy(d->stream);
+        d->stream = nullptr;
+        MDC_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        d->stream_device = ctx->device;
+    }
+    cudaStream_t st = d->stream;
     MDC_CHECK(d->text.alloc((size_t)padded));
     MDC_CHECK(d->tile_count.alloc(n_tiles));
     MDC_CHECK(d->line_start.alloc((size_t)n_lines + 1));
