@@ -63,6 +63,7 @@ typedef struct mdc_ctx      mdc_ctx;
 typedef struct mdc_sq_plan  mdc_sq_plan;
 typedef struct mdc_rdf_plan mdc_rdf_plan;
 typedef struct mdc_dump     mdc_dump;
+typedef struct mdc_profile_plan mdc_profile_plan;
 
 /* ---- library / context ------------------------------------------------- */
 
@@ -268,6 +269,30 @@ int      mdc_dump_info(mdc_dump *dump, int64_t info[8]);
 int      mdc_dump_headers(mdc_dump *dump, int64_t *steps, float *box, double *origin, int64_t *offsets);
 int64_t  mdc_dump_block_bytes(mdc_dump *dump, int64_t f0, int n_frames);
 int      mdc_dump_read(mdc_dump *dump, mdc_ctx *ctx, int64_t f0, int n_frames, float *pos_out, int on_device);
+
+/* ---- 1-D density profiles ------------------------- */
+
+/*
+ * Replaces the per-frame arithmetic of DensityProfile._single_frame without recentring
+ * (/root/reference/src/mdcraft/analysis/profile.py:1128-1181): positions are wrapped into the box
+ * (algorithm/topology.py:620-624) and binned per axis and group with numba_histogram
+ * (algorithm/accelerated.py:46-81), in the reference's FP64 operation order: counts are exact.
+ *   group_sizes : positions pushed later hold the groups concatenated in order.
+ *   axes        : n_axes entries in {0, 1, 2}; n_bins one entry per axis; dims = the three box lengths.
+ * Count table layout: [axis][group][bin] (axis k starts at n_groups * sum of n_bins[0..k-1]).
+ * mdc_profile_push: pos f32 (n_frames, N, 3); per_frame_out NULL or host i64 (n_frames, total) receiving every
+ * frame's own counts (the reference's average=False).  mdc_profile_read: summed counts i64 (total).
+ */
+int      mdc_profile_plan_create(mdc_ctx *ctx, int n_groups, const int64_t *group_sizes,
+                                 int n_axes, const int *axes, const int *n_bins, const double dims[3],
+                                 mdc_profile_plan **out);
+int      mdc_profile_plan_destroy(mdc_profile_plan *plan);
+int64_t  mdc_profile_num_counts(mdc_profile_plan *plan);
+int      mdc_profile_push(mdc_profile_plan *plan, const float *pos, int n_frames, int on_device,
+                          int64_t *per_frame_out);
+int      mdc_profile_read(mdc_profile_plan *plan, int64_t *counts_out, int64_t *n_frames_out);
+int      mdc_profile_reset(mdc_profile_plan *plan);
+int      mdc_profile_accum_ptr(mdc_profile_plan *plan, void **dev_ptr, int64_t *n_elems);
 
 /* ---- timing (CUDA events on the context's compute stream) ---------------- */
 

@@ -108,6 +108,13 @@ SIGNATURES = {
     "mdc_dump_headers": (c_int, [c_void_p, _lp, _fp, _dp, _lp]),
     "mdc_dump_block_bytes": (c_int64, [c_void_p, c_int64, c_int]),
     "mdc_dump_read": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int]),
+    "mdc_profile_plan_create": (c_int, [c_void_p, c_int, _lp, c_int, _ip, _ip, _dp, POINTER(c_void_p)]),
+    "mdc_profile_plan_destroy": (c_int, [c_void_p]),
+    "mdc_profile_num_counts": (c_int64, [c_void_p]),
+    "mdc_profile_push": (c_int, [c_void_p, c_void_p, c_int, c_int, _lp]),
+    "mdc_profile_read": (c_int, [c_void_p, _lp, _lp]),
+    "mdc_profile_reset": (c_int, [c_void_p]),
+    "mdc_profile_accum_ptr": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
     "mdc_sq_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_rdf_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_probe_rate": (c_int, [c_void_p, c_int, _dp]),
@@ -386,6 +393,73 @@ class SqPlan:
         ms, nl = c_float(), c_int()
         _check(lib().mdc_sq_last_push_stats(self._h, byref(ms), byref(nl)))
         return ms.value, nl.value
+
+
+class ProfilePlan:
+    """``mdc_profile_plan``: per-axis, per-group 1-D histograms of wrapped positions (DensityProfile)."""
+
+    def __init__(self, ctx: Context, group_sizes: Sequence[int], axes: Sequence[int], n_bins: Sequence[int],
+                 dimensions: Sequence[float]):
+        self.ctx = ctx
+        self._h = c_void_p()
+        gs = np.ascontiguousarray(group_sizes, dtype=np.int64)
+        ax = np.ascontiguousarray(axes, dtype=np.int32)
+        nb = np.ascontiguousarray(n_bins, dtype=np.int32)
+        dims = np.ascontiguousarray(dimensions, dtype=np.float64)
+        if ax.shape != nb.shape or dims.shape != (3,):
+            raise ValueError("axes and n_bins must have equal length and dimensions three entries")
+        _check(lib().mdc_profile_plan_create(ctx._h, gs.shape[0], _as(gs, _lp), ax.shape[0], _as(ax, _ip), _as(nb, _ip),
+                                             _as(dims, _dp), byref(self._h)))
+        self.n_groups, self.n_particles = gs.shape[0], int(gs.sum())
+        self.n_bins = [int(n) for n in nb]
+        self.total = int(lib().mdc_profile_num_counts(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().mdc_profile_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _split(self, flat: np.ndarray) -> list:
+        """Count table ``(..., total)`` -> one ``(..., n_groups, n_bins[k])`` array per axis."""
+        out, off = [], 0
+        for n in self.n_bins:
+            out.append(flat[..., off:off + self.n_groups * n].reshape(flat.shape[:-1] + (self.n_groups, n)))
+            off += self.n_groups * n
+        return out
+
+    def push(self, pos, n_frames: Optional[int] = None, per_frame: bool = False):
+        """``pos``: float32 ``(F, N, 3)``.  ``per_frame``: also return every frame's own counts, per axis
+        ``(F, n_groups, n_bins)``."""
+        ptr, on_dev, keep = _buffer(pos)
+        shape = keep.shape
+        if n_frames is None:
+            n_frames = 1 if len(shape) == 2 else int(shape[0])
+        if int(np.prod(shape)) != n_frames * self.n_particles * 3:
+            raise ValueError(f"positions have {int(np.prod(shape))} elements, expected {n_frames} x {self.n_particles} x 3")
+        out = np.empty((n_frames, self.total), dtype=np.int64) if per_frame else None
+        _check(lib().mdc_profile_push(self._h, ptr, int(n_frames), on_dev, None if out is None else _as(out, _lp)))
+        return None if out is None else self._split(out)
+
+    def read(self):
+        """Summed counts per axis ``(n_groups, n_bins)`` and the number of frames pushed."""
+        out = np.empty(self.total, dtype=np.int64)
+        nf = c_int64()
+        _check(lib().mdc_profile_read(self._h, _as(out, _lp), byref(nf)))
+        return self._split(out), nf.value
+
+    def reset(self) -> None:
+        _check(lib().mdc_profile_reset(self._h))
+
+    def accumulator(self) -> _DeviceArray:
+        p, n = c_void_p(), c_int64()
+        _check(lib().mdc_profile_accum_ptr(self._h, byref(p), byref(n)))
+        return _DeviceArray(p.value, n.value, "<u8", self)
 
 
 class DumpFile:

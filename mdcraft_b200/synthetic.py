@@ -247,6 +247,11 @@ class _GroupList(list):
     def n_segments(self) -> int:
         return len(self)
 
+    @property
+    def masses(self) -> np.ndarray:
+        """``ResidueGroup.masses`` / ``SegmentGroup.masses``: total mass of every member."""
+        return np.array([g.masses.sum() for g in self])
+
 
 class AtomGroup:
     """Minimal stand-in for ``MDAnalysis.AtomGroup`` (index list into a Universe)."""
@@ -265,6 +270,11 @@ class AtomGroup:
         if self._contiguous and self.indices.size:
             return np.array(pos[self.indices[0] : self.indices[-1] + 1], dtype=np.float32)
         return np.asarray(pos[self.indices], dtype=np.float32)
+
+    @property
+    def atoms(self) -> "AtomGroup":
+        """MDAnalysis groups (and Residue / Segment objects) expose their atoms as ``.atoms``."""
+        return self
 
     @property
     def masses(self) -> np.ndarray:
@@ -287,9 +297,7 @@ class AtomGroup:
         mine = labels[self.indices]
         out = _GroupList()
         for lab in np.unique(mine):
-            g = AtomGroup(self.universe, self.indices[mine == lab])
-            g.atoms = g   # MDAnalysis' Residue / Segment expose their atoms as ``.atoms``
-            out.append(g)
+            out.append(AtomGroup(self.universe, self.indices[mine == lab]))   # ``.atoms`` of a Residue / Segment
         return out
 
     @property

@@ -547,3 +547,31 @@ def read_lammps_dump(path: str, dt: float = 1.0):
         i += 9 + n
     steps = np.array(steps, dtype=np.int64)
     return np.stack(positions), np.stack(dims), steps, steps * dt, np.array(offsets)
+
+
+# ----------------------------------------------------------------------------
+# density profiles
+# ----------------------------------------------------------------------------
+
+
+def density_profile_counts(frames: Iterable[np.ndarray], group_sizes, axes, n_bins, dimensions):
+    """
+    CPU restatement of ``DensityProfile._single_frame`` without recentring (profile.py:1128-1181): positions widened
+    to float64, ``wrap`` (algorithm/topology.py:620-624), ``numba_histogram`` per axis and group
+    (accelerated.py:46-81, through the C restatement pinned by histogram_pins.npz).  ``dimensions``: the three box
+    lengths as the class holds them (float32 from the universe, float64 when given explicitly).
+
+    Returns one int64 array ``(n_frames, n_groups, n_bins[k])`` per axis.
+    """
+    dims = np.asarray(dimensions)
+    edges = np.concatenate(([0], np.cumsum(group_sizes)))
+    out = [[] for _ in axes]
+    for pos in frames:
+        p = np.array(pos, dtype=np.float64)
+        wrap = (p < 0) | (p > dims)
+        p[wrap] -= (np.floor(p / dims) * dims)[wrap]
+        for k, (ia, n) in enumerate(zip(axes, n_bins)):
+            bin_edges = histogram_bin_edges((0.0, float(dims[ia])), int(n))
+            out[k].append(np.stack([histogram(np.ascontiguousarray(p[a:b, ia]), int(n), bin_edges)
+                                    for a, b in zip(edges[:-1], edges[1:])]))
+    return [np.stack(o) for o in out]

@@ -47,6 +47,13 @@ class _Unit:
     def __truediv__(self, o):
         return _Unit(f"{self.name}/{getattr(o, 'name', o)}")
 
+    def __rtruediv__(self, o):
+        return _Unit(f"{getattr(o, 'name', o)}/{self.name}")
+
+    def m_as(self, unit):
+        # only profile.py:30 asks for a magnitude: e / (eps0 * angstrom) in volts (CODATA 2018)
+        return 1.602176634e-19 / (8.8541878128e-12 * 1e-10)
+
     def __repr__(self):
         return f"<unit {self.name}>"
 
@@ -237,3 +244,9 @@ def load_reader():
         sys.modules["MDAnalysis.lib.util"] = util
         sys.modules["MDAnalysis.lib"].util = util
     return importlib.import_module("mdcraft.analysis.reader")
+
+
+def load_profile():
+    """The real ``mdcraft.analysis.profile`` (DensityProfile)."""
+    load()
+    return importlib.import_module("mdcraft.analysis.profile")

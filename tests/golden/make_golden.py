@@ -32,9 +32,9 @@ from mdcraft_b200 import synthetic  # noqa: E402
 from oracle import ref_loader  # noqa: E402
 
 
-def universe_from(pos, dims, resindices=None):
+def universe_from(pos, dims, resindices=None, masses=None):
     traj = synthetic.MemoryTrajectory(np.asarray(pos, np.float32), np.asarray(dims, np.float32))
-    return synthetic.Universe(traj, resindices=resindices)
+    return synthetic.Universe(traj, resindices=resindices, masses=masses)
 
 
 def lj_frames(n, n_frames, rho, seed0, scale=None):
@@ -310,8 +310,59 @@ def dumps():
     save("dumps.npz", **out)
 
 
+def profiles():
+    """DensityProfile: the reference class (profile.py, unmodified) on in-memory trajectories
+    whose positions partly lie outside the box (so that wrap() matters), plus its post-processing."""
+    import warnings
+
+    pr = ref_loader.load_profile()
+    rng = np.random.default_rng(4242)
+    out = {}
+    F, N = 6, 400
+    dims = np.array([9.5, 11.25, 14.0, 90, 90, 90], np.float32)
+    pos = (rng.random((F, N, 3)) * (dims[:3] * 1.6) - dims[:3] * 0.3).astype(np.float32)
+    pos[0, :3, 2] = [0.0, dims[2], -0.0]                       # on the edges
+    pos[1, :2, 0] = [np.float32(dims[0]) * 2, -dims[0]]        # exact multiples of the box
+    # slab-like charge separation along z so that the potential is not flat
+    pos[:, :150, 2] = (rng.normal(3.0, 0.8, size=(F, 150))).astype(np.float32)
+    pos[:, 150:, 2] = (rng.normal(10.5, 1.1, size=(F, N - 150))).astype(np.float32)
+    out["pos"], out["dims"] = pos, dims
+    u = universe_from(pos, dims)
+    # (a) two groups, two axes, per-axis bin counts, charges, reduced units
+    d = pr.DensityProfile([u.select(0, 150), u.select(150, N)], axes="xz", n_bins=[5, 48], charges=[1.0, -0.6],
+                          reduced=True, verbose=False).run()
+    for ax in "xz":
+        out[f"a_bins_{ax}"], out[f"a_edges_{ax}"] = d.results.bins[ax], d.results.bin_edges[ax]
+        out[f"a_number_{ax}"], out[f"a_charge_{ax}"] = d.results.number_densities[ax], d.results.charge_densities[ax]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # all axes at once: with a subset the reference zips the per-axis arrays against the wrong entries
+        # (profile.py:1377-1380 pairs axes[i] with self._dielectrics[i], not with its relative index) and yields NaN
+        d.calculate_surface_charge_densities(None, [1.5, 2.5], dVs=[0.1, 0.3])
+        out["a_sigma"] = d.results.surface_charge_densities.copy()
+        d.calculate_potential_profiles(None, [1.5, 2.5], sigmas_q=[0.02, 0.01])
+        out["a_potential_integral"] = d.results.potentials["z"].copy()
+        d.calculate_potential_profiles(None, [1.5, 2.5], sigmas_q=[0.02, 0.01], methods="matrix", V0s=[0.0, 0.2])
+        out["a_potential_matrix"] = d.results.potentials["z"].copy()
+        d.calculate_potential_profiles(None, [1.5, 2.5], sigmas_q=[0.02, 0.01], methods="matrix", pbcs=True)
+        out["a_potential_matrix_pbc"] = d.results.potentials["z"].copy()
+    # (b) one group, default bins on all axes, every frame kept, run(start, stop, step)
+    d = pr.DensityProfile(u.atoms, average=False, verbose=False).run(start=1, stop=6, step=2)
+    for ax in "xyz":
+        out[f"b_number_{ax}"] = d.results.number_densities[ax]
+    out["b_times"] = d.results.times
+    # (c) residues (pairs of atoms, unequal masses), explicit dimensions and scale factors
+    u2 = universe_from(pos, dims, resindices=np.arange(N) // 2, masses=1.0 + (np.arange(N) % 2) * 2.5)
+    d = pr.DensityProfile(u2.atoms, "residues", axes="y", n_bins=33, dimensions=[9.5, 11.25, 14.0],
+                          dim_scales=(1.0, 0.9, 1.0), verbose=False).run()
+    out["c_number_y"], out["c_edges_y"] = d.results.number_densities["y"], d.results.bin_edges["y"]
+    save("profiles.npz", **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "profiles"):
+        profiles()
     if which in ("all", "main"):
         main()
     if which in ("all", "transforms"):

@@ -638,3 +638,68 @@ def test_dump_reader_refuses_what_it_cannot_match(tmp_path):
         LAMMPSDumpTrajectoryReader(str(p), conventions=["", ""])
     with pytest.raises(NotImplementedError):
         LAMMPSDumpTrajectoryReader(str(p), unwrap=True)
+
+
+# --------------------------------------------------------------------------- density profiles (§8f rank 4)
+
+
+def test_density_profile_golden():
+    """DensityProfile on the GPU against the reference class's own results: number and charge densities are EQUAL
+    (exact counts, same normalisation expressions), post-processing to rounding."""
+    import warnings
+
+    from mdcraft_b200.analysis.profile import DensityProfile
+
+    g = golden("profiles.npz")
+    pos, dims = g["pos"], g["dims"]
+    n = pos.shape[1]
+    u = universe_from(pos, dims)
+    d = DensityProfile([u.select(0, 150), u.select(150, n)], axes="xz", n_bins=[5, 48], charges=[1.0, -0.6],
+                       reduced=True, verbose=False, frame_block=4).run()
+    for ax in "xz":
+        np.testing.assert_array_equal(d.results.bins[ax], g[f"a_bins_{ax}"])
+        np.testing.assert_array_equal(d.results.bin_edges[ax], g[f"a_edges_{ax}"])
+        np.testing.assert_array_equal(d.results.number_densities[ax], g[f"a_number_{ax}"])
+        np.testing.assert_array_equal(d.results.charge_densities[ax], g[f"a_charge_{ax}"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d.calculate_surface_charge_densities(None, [1.5, 2.5], dVs=[0.1, 0.3])
+        np.testing.assert_allclose(d.results.surface_charge_densities, g["a_sigma"], rtol=1e-13, equal_nan=True)
+        d.calculate_potential_profiles(None, [1.5, 2.5], sigmas_q=[0.02, 0.01])
+        np.testing.assert_allclose(d.results.potentials["z"], g["a_potential_integral"], rtol=1e-12, atol=1e-14)
+        d.calculate_potential_profiles(None, [1.5, 2.5], sigmas_q=[0.02, 0.01], methods="matrix", V0s=[0.0, 0.2])
+        np.testing.assert_allclose(d.results.potentials["z"], g["a_potential_matrix"], rtol=1e-10, atol=1e-12)
+    d = DensityProfile(u.atoms, average=False, verbose=False, frame_block=2).run(start=1, stop=6, step=2)
+    for ax in "xyz":
+        np.testing.assert_array_equal(d.results.number_densities[ax], g[f"b_number_{ax}"])
+    np.testing.assert_array_equal(d.results.times, g["b_times"])
+    u2 = universe_from(pos, dims, resindices=np.arange(n) // 2, masses=1.0 + (np.arange(n) % 2) * 2.5)
+    d = DensityProfile(u2.atoms, "residues", axes="y", n_bins=33, dimensions=[9.5, 11.25, 14.0],
+                       dim_scales=(1.0, 0.9, 1.0), verbose=False).run()
+    np.testing.assert_array_equal(d.results.bin_edges["y"], g["c_edges_y"])
+    np.testing.assert_array_equal(d.results.number_densities["y"], g["c_number_y"])
+    with pytest.raises(NotImplementedError):
+        DensityProfile(u.atoms, recenter=0)
+    with pytest.raises(ValueError, match="Invalid axis"):
+        DensityProfile(u.atoms, axes="xw")
+
+
+def test_density_profile_large_vs_oracle(ctx):
+    """100,000 particles, three axes, 1,000 bins: the device counts against the CPU restatement, exactly."""
+    from mdcraft_b200 import _capi, synthetic
+    from oracle import oracle
+
+    n, L = 100_000, 37.5
+    rng = np.random.default_rng(9)
+    pos = (rng.normal(L / 2, L, size=(2, n, 3))).astype(np.float32)      # most particles outside the box
+    dims = np.array([L, L * 0.8, L * 1.3], np.float32)
+    plan = _capi.ProfilePlan(ctx, [30_000, 70_000], [0, 1, 2], [1000, 7, 333], dims.astype(np.float64))
+    per = plan.push(pos, per_frame=True)
+    summed, nf = plan.read()
+    plan.close()
+    want = oracle.density_profile_counts(pos, [30_000, 70_000], [0, 1, 2], [1000, 7, 333], dims)
+    assert nf == 2
+    for got, tot, w in zip(per, summed, want):
+        np.testing.assert_array_equal(got, w)
+        np.testing.assert_array_equal(tot, w.sum(axis=0))
+        assert tot.sum() == 2 * n                                         # wrapping loses nobody

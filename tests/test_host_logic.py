@@ -274,3 +274,30 @@ def test_dump_index_and_headers_on_the_host(tmp_path):
         _capi.DumpFile(str(bad))
     with pytest.raises(_capi.MdcError, match="convention 'u'"):
         _capi.DumpFile(os.path.join(GOLDEN, "dump_ids.lammpsdump"), conventions=["u", "u", "u"])
+
+
+def test_profile_post_processing_matches_the_reference_golden():
+    """calculate_surface_charge_density / calculate_potential_profile (host NumPy / SciPy) on the reference's own
+    charge density profile against the reference's own results (integral, matrix and periodic matrix methods)."""
+    import warnings
+
+    from conftest import golden
+    from mdcraft_b200.analysis import profile
+
+    g = golden("profiles.npz")
+    bins, rho_q, L = g["a_bins_z"].copy(), g["a_charge_z"], float(g["dims"][2])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sigma = profile.calculate_surface_charge_density(bins, rho_q, 2.5, L=L, dV=0.3, reduced=True)
+        np.testing.assert_allclose(sigma, g["a_sigma"][1], rtol=1e-13)
+        kw = dict(L=L, sigma_q=0.01, reduced=True)
+        np.testing.assert_allclose(profile.calculate_potential_profile(bins, rho_q, 2.5, **kw), g["a_potential_integral"],
+                                   rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(profile.calculate_potential_profile(bins, rho_q, 2.5, method="matrix", V0=0.2, **kw),
+                                   g["a_potential_matrix"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(profile.calculate_potential_profile(bins, rho_q, 2.5, method="matrix", pbc=True, **kw),
+                                   g["a_potential_matrix_pbc"], rtol=1e-10, atol=1e-12)
+    with pytest.raises(ValueError, match="one-dimensional"):
+        profile.calculate_surface_charge_density(bins[None], rho_q)
+    with pytest.raises(ValueError, match="'dielectric' must be specified"):
+        profile.calculate_surface_charge_density(bins, rho_q, dV=1.0)

@@ -188,3 +188,21 @@ def test_dump_reader_oracle_matches_the_reference_reader(tag, name):
     np.testing.assert_array_equal(steps, g[f"{tag}_steps"])
     np.testing.assert_array_equal(times, g[f"{tag}_times"])
     np.testing.assert_array_equal(offsets, g[f"{tag}_offsets"])
+
+
+def test_density_profile_oracle_matches_the_reference_class():
+    """oracle.density_profile_counts, normalised as profile.py:1236-1248, against number densities the reference's
+    own DensityProfile produced (tests/golden/make_golden.py profiles): positions outside the box, on its edges
+    and at exact multiples of it included."""
+    g = golden("profiles.npz")
+    pos, dims = g["pos"], g["dims"][:3]          # float32, as the class holds them
+    F, N = pos.shape[:2]
+    volume = np.prod(dims)
+    cx, cz = oracle.density_profile_counts(pos, [150, N - 150], [0, 2], [5, 48], dims)
+    np.testing.assert_array_equal(cx.sum(axis=0) / (volume / 5 * F), g["a_number_x"])
+    np.testing.assert_array_equal(cz.sum(axis=0) / (volume / 48 * F), g["a_number_z"])
+    np.testing.assert_array_equal(oracle.histogram_bin_edges((0.0, float(dims[2])), 48), g["a_edges_z"])
+    sel = pos[1:6:2]
+    for k, ax in enumerate("xyz"):
+        (c,) = oracle.density_profile_counts(sel, [N], [k], [201], dims)
+        np.testing.assert_array_equal(c.transpose(1, 0, 2) / (volume / np.int64(201)), g[f"b_number_{ax}"])
