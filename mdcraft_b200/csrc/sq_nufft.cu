@@ -101,8 +101,18 @@ __device__ __forceinline__ void dft<8>(double2 *v)
 
 // One decimation-in-frequency stage of radix R on the blocks of length L = R << lgsub of one line:
 // sub-block r of every block receives the sequence whose length-(L / R) transform is X[R j + r].
-template <int R>
-__device__ __forceinline__ void fft_stage(double2 *buf, const double2 *tw, int nf, int lgsub, int lane)
+// src != nullptr: the inputs come straight from global memory (first stage of a contiguous line) instead of from
+// the shared-memory line.  Only W^i is read from the twiddle table; its powers are formed by multiplication
+// (depth 3, ~2 ulp), which takes 6 of the 7 table reads of a radix-8 butterfly off the shared-memory pipe.
+#ifndef MDC_FFT_POW_Z
+#define MDC_FFT_POW_Z 1
+#endif
+#ifndef MDC_FFT_POW_S
+#define MDC_FFT_POW_S 0
+#endif
+template <int R, bool POW>
+__device__ __forceinline__ void fft_stage(double2 *buf, const double2 *tw, int nf, int lgsub, int lane,
+                                          const double2 *__restrict__ src = nullptr)
 {
     const int sub = 1 << lgsub, L = R << lgsub, tstep = nf / L;
     for (int t = lane; t < nf / R; t += 32) {
@@ -110,11 +120,29 @@ __device__ __forceinline__ void fft_stage(double2 *buf, const double2 *tw, int n
         const int base = blk * L + i;
         double2 v[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = buf[padded(base + q * sub)];
+        for (int q = 0; q < R; ++q) v[q] = src ? src[base + q * sub] : buf[padded(base + q * sub)];
         dft<R>(v);
-        buf[padded(base)] = v[0];
+        if (i != 0) {
+            if (POW) {
+                double2 w[R];
+                w[1] = tw[i * tstep];
+                if (R > 2) w[2] = cmul(w[1], w[1]);
+                if (R > 3) w[3] = cmul(w[2], w[1]);
+                if (R > 4) {
+                    w[4] = cmul(w[2], w[2]);
+                    w[5] = cmul(w[4], w[1]);
+                    w[6] = cmul(w[4], w[2]);
+                    w[7] = cmul(w[4], w[3]);
+                }
 #pragma unroll
-        for (int r = 1; r < R; ++r) buf[padded(base + r * sub)] = (i == 0) ? v[r] : cmul(v[r], tw[r * i * tstep]);
+                for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
+            } else {
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw[r * i * tstep]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[padded(base + r * sub)] = v[r];
     }
     __syncwarp();
 }
@@ -122,14 +150,22 @@ __device__ __forceinline__ void fft_stage(double2 *buf, const double2 *tw, int n
 // One warp transforms one line of nf complex doubles in shared memory (element p at buf[padded(p)]), in place:
 //   X[k] = sum_l x[l] exp(+2 pi i k l / nf);   X[k] ends up at element fft_pos(k) (mixed-radix digit reversal,
 // undone for free by the pruned read-out).  Radices: 3 (if nf = 3 * 2^a), then 8s, then 4 or 2.
-// tw[t] = exp(+2 pi i t / nf).
-__device__ __forceinline__ void fft_line(double2 *buf, const double2 *tw, const NufftGeom &g, int lane)
+// tw[t] = exp(+2 pi i t / nf).  src != nullptr: the line is still in global memory; the first stage loads it.
+template <bool POW>
+__device__ __forceinline__ void fft_line(double2 *buf, const double2 *tw, const NufftGeom &g, int lane,
+                                         const double2 *__restrict__ src = nullptr)
 {
     int lg = g.log2m;   // log2 of the current block length (after the radix-3 stage)
-    if (g.r3) fft_stage<3>(buf, tw, g.nf, lg, lane);
-    for (; lg >= 3; lg -= 3) fft_stage<8>(buf, tw, g.nf, lg - 3, lane);
-    if (lg == 2) fft_stage<4>(buf, tw, g.nf, 0, lane);
-    else if (lg == 1) fft_stage<2>(buf, tw, g.nf, 0, lane);
+    if (g.r3) {
+        fft_stage<3, POW>(buf, tw, g.nf, lg, lane, src);
+        src = nullptr;
+    }
+    for (; lg >= 3; lg -= 3) {
+        fft_stage<8, POW>(buf, tw, g.nf, lg - 3, lane, src);
+        src = nullptr;
+    }
+    if (lg == 2) fft_stage<4, POW>(buf, tw, g.nf, 0, lane);
+    else if (lg == 1) fft_stage<2, POW>(buf, tw, g.nf, 0, lane);
 }
 
 // element index, after fft_line, of X[k]
@@ -332,9 +368,7 @@ nufft_fft_z(const double2 *__restrict__ grid, double2 *__restrict__ out, const d
     const int64_t lines = (int64_t)nf * nf;
     for (int64_t ln = (int64_t)blockIdx.x * (NU_THREADS / 32) + warp; ln < lines; ln += (int64_t)gridDim.x * (NU_THREADS / 32)) {
         const double2 *src = grid + ((size_t)blockIdx.y * lines + ln) * nf;
-        for (int i = lane; i < nf; i += 32) line[padded(i)] = src[i];
-        __syncwarp();
-        fft_line(line, tw, g, lane);
+        fft_line<MDC_FFT_POW_Z != 0>(line, tw, g, lane, src);   // the first radix stage reads the line from global memory
         double2 *dst = out + ((size_t)blockIdx.y * lines + ln) * g.ncp;
         for (int c = lane; c < g.ncp; c += 32) {
             double2 v = make_double2(0.0, 0.0);
@@ -387,7 +421,7 @@ nufft_fft_s(const double2 *__restrict__ in, double2 *__restrict__ out, const dou
         tile[ii * pitch + padded(l)] = gi < S ? src[(size_t)l * S + gi] : make_double2(0.0, 0.0);
     }
     __syncthreads();
-    fft_line(tile + warp * pitch, tw, g, lane);
+    fft_line<MDC_FFT_POW_S != 0>(tile + warp * pitch, tw, g, lane);
     __syncthreads();
     for (int e = threadIdx.x; e < n * NU_TC; e += NU_THREADS) {
         const int k = e / NU_TC, ii = e - k * NU_TC;
