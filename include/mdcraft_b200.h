@@ -64,6 +64,7 @@ typedef struct mdc_sq_plan  mdc_sq_plan;
 typedef struct mdc_rdf_plan mdc_rdf_plan;
 typedef struct mdc_dump     mdc_dump;
 typedef struct mdc_profile_plan mdc_profile_plan;
+typedef struct mdc_ncdf     mdc_ncdf;
 
 /* ---- library / context ------------------------------------------------- */
 
@@ -269,6 +270,24 @@ int      mdc_dump_info(mdc_dump *dump, int64_t info[8]);
 int      mdc_dump_headers(mdc_dump *dump, int64_t *steps, float *box, double *origin, int64_t *offsets);
 int64_t  mdc_dump_block_bytes(mdc_dump *dump, int64_t f0, int n_frames);
 int      mdc_dump_read(mdc_dump *dump, mdc_ctx *ctx, int64_t f0, int n_frames, float *pos_out, int on_device);
+
+/* ---- frame ingest: AMBER NetCDF trajectories -------- */
+
+/*
+ * Replaces the read side of /root/reference/src/mdcraft/openmm/file.py:22-306 (NetCDFFile.get_num_frames,
+ * get_num_atoms, get_dimensions, get_times, get_positions), which goes through netCDF4, for NetCDF-3 classic and
+ * 64-bit-offset files (what that class writes, file.py:52-54) following the AMBER trajectory convention.
+ * mdc_ncdf_open memory-maps the file and parses the header on the host.  mdc_ncdf_read sends the big-endian
+ * coordinates of frames [f0, f0 + n_frames) to HBM with one strided copy and byte-swaps them there into float32
+ * (n_frames, n_atoms, 3); pos_out is a device pointer (on_device != 0) or host memory.
+ * info: [n_frames, n_atoms, has cell_lengths / cell_angles, has time].
+ * headers: times (n_frames) as f64, cell_lengths and cell_angles f64 (n_frames, 3); any pointer may be NULL.
+ */
+int  mdc_ncdf_open(const char *path, mdc_ncdf **out);
+int  mdc_ncdf_close(mdc_ncdf *file);
+int  mdc_ncdf_info(mdc_ncdf *file, int64_t info[4]);
+int  mdc_ncdf_headers(mdc_ncdf *file, double *times, double *cell_lengths, double *cell_angles);
+int  mdc_ncdf_read(mdc_ncdf *file, mdc_ctx *ctx, int64_t f0, int n_frames, float *pos_out, int on_device);
 
 /* ---- 1-D density profiles ------------------------- */
 

@@ -115,6 +115,11 @@ SIGNATURES = {
     "mdc_profile_read": (c_int, [c_void_p, _lp, _lp]),
     "mdc_profile_reset": (c_int, [c_void_p]),
     "mdc_profile_accum_ptr": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
+    "mdc_ncdf_open": (c_int, [c_char_p, POINTER(c_void_p)]),
+    "mdc_ncdf_close": (c_int, [c_void_p]),
+    "mdc_ncdf_info": (c_int, [c_void_p, _lp]),
+    "mdc_ncdf_headers": (c_int, [c_void_p, _dp, _dp, _dp]),
+    "mdc_ncdf_read": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int]),
     "mdc_sq_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_rdf_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_probe_rate": (c_int, [c_void_p, c_int, _dp]),
@@ -517,6 +522,49 @@ class DumpFile:
         if n_el is not None and n_el != int(n_frames) * self.n_atoms * 3:
             raise ValueError(f"out has {n_el} elements, expected {n_frames} x {self.n_atoms} x 3")
         _check(lib().mdc_dump_read(self._h, ctx._h, int(f0), int(n_frames), ptr, on_dev))
+        return out
+
+
+class NcdfFile:
+    """``mdc_ncdf``: a memory-mapped AMBER NetCDF-3 trajectory whose coordinates are byte-swapped on the GPU."""
+
+    def __init__(self, path: str):
+        self._h = c_void_p()
+        _check(lib().mdc_ncdf_open(os.fsencode(path), byref(self._h)))
+        info = (c_int64 * 4)()
+        _check(lib().mdc_ncdf_info(self._h, info))
+        self.n_frames, self.n_atoms = int(info[0]), int(info[1])
+        self.has_box, self.has_time = bool(info[2]), bool(info[3])
+        self.times = np.empty(self.n_frames, dtype=np.float64) if self.has_time else None
+        self.cell_lengths = np.empty((self.n_frames, 3), dtype=np.float64) if self.has_box else None
+        self.cell_angles = np.empty((self.n_frames, 3), dtype=np.float64) if self.has_box else None
+        _check(lib().mdc_ncdf_headers(
+            self._h, None if self.times is None else _as(self.times, _dp),
+            None if self.cell_lengths is None else _as(self.cell_lengths, _dp),
+            None if self.cell_angles is None else _as(self.cell_angles, _dp)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().mdc_ncdf_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def read(self, ctx: "Context", f0: int, n_frames: int, out=None):
+        """Coordinates of frames ``[f0, f0 + n_frames)`` as float32 ``(n_frames, n_atoms, 3)``; ``out``: a host array
+        or a device buffer to fill."""
+        if out is None:
+            out = np.empty((int(n_frames), self.n_atoms, 3), dtype=np.float32)
+        ptr, on_dev, keep = _buffer(out)
+        if not on_dev and keep is not out:
+            raise ValueError("out must be a C-contiguous float32 array")
+        if int(np.prod(keep.shape)) != int(n_frames) * self.n_atoms * 3:
+            raise ValueError(f"out must hold {n_frames} x {self.n_atoms} x 3 elements")
+        _check(lib().mdc_ncdf_read(self._h, ctx._h, int(f0), int(n_frames), ptr, on_dev))
         return out
 
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmdcraft_b200.so")
-SOURCES = ("context.cu", "sq.cu", "sq_nufft.cu", "rdf.cu", "transforms.cu", "dump.cu", "profile.cu")
+SOURCES = ("context.cu", "sq.cu", "sq_nufft.cu", "rdf.cu", "transforms.cu", "dump.cu", "profile.cu", "ncdf.cu")
 HEADERS = ("common.cuh", "sq_math.cuh", "sq_nufft.cuh", os.path.join("..", "..", "include", "mdcraft_b200.h"))
 
 NVCC_FLAGS = [

@@ -575,3 +575,57 @@ def density_profile_counts(frames: Iterable[np.ndarray], group_sizes, axes, n_bi
             out[k].append(np.stack([histogram(np.ascontiguousarray(p[a:b, ia]), int(n), bin_edges)
                                     for a, b in zip(edges[:-1], edges[1:])]))
     return [np.stack(o) for o in out]
+
+
+def write_amber_netcdf(path: str, positions, times, cell_lengths=None, cell_angles=None, version: int = 2,
+                       velocities=None) -> None:
+    """Test helper: an AMBER-convention NetCDF-3 trajectory (what NetCDFFile.write_header lays out,
+    openmm/file.py:309-531) written with SciPy; version 2 = 64-bit offsets, the format the reference uses."""
+    from scipy.io import netcdf_file
+
+    positions = np.asarray(positions, dtype=np.float32)
+    F, N = positions.shape[:2]
+    f = netcdf_file(path, "w", version=version)
+    f.Conventions, f.ConventionVersion, f.program = "AMBER", "1.0", "oracle"
+    f.createDimension("frame", None)
+    f.createDimension("spatial", 3)
+    f.createDimension("atom", N)
+    v_time = f.createVariable("time", "f", ("frame",))
+    v_time.units = "picosecond"
+    v_pos = f.createVariable("coordinates", "f", ("frame", "atom", "spatial"))
+    v_pos.units = "angstrom"
+    if cell_lengths is not None:
+        f.createDimension("cell_spatial", 3)
+        f.createDimension("cell_angular", 3)
+        v_len = f.createVariable("cell_lengths", "d", ("frame", "cell_spatial"))
+        v_ang = f.createVariable("cell_angles", "d", ("frame", "cell_angular"))
+    if velocities is not None:
+        v_vel = f.createVariable("velocities", "f", ("frame", "atom", "spatial"))
+    for i in range(F):
+        v_time[i] = times[i]
+        v_pos[i] = positions[i]
+        if cell_lengths is not None:
+            v_len[i] = cell_lengths[i]
+            v_ang[i] = cell_angles[i]
+        if velocities is not None:
+            v_vel[i] = velocities[i]
+    f.close()
+
+
+def read_amber_netcdf(path: str):
+    """
+    Independent CPU reader for the NetCDF ingest: SciPy's NetCDF-3 implementation.
+    PARITY UNPINNED against the reference's NetCDFFile (openmm/file.py needs netCDF4 and OpenMM, both absent here);
+    the file format itself is the contract.  Returns positions f32 (F, N, 3), times f32 (F,), cell_lengths and
+    cell_angles f64 (F, 3) or None.
+    """
+    from scipy.io import netcdf_file
+
+    f = netcdf_file(path, "r", mmap=False)
+    pos = np.array(f.variables["coordinates"][:], dtype=np.float32)
+    times = np.array(f.variables["time"][:], dtype=np.float32)
+    box = "cell_lengths" in f.variables
+    lengths = np.array(f.variables["cell_lengths"][:], dtype=np.float64) if box else None
+    angles = np.array(f.variables["cell_angles"][:], dtype=np.float64) if box else None
+    f.close()
+    return pos, times, lengths, angles

@@ -703,3 +703,50 @@ def test_density_profile_large_vs_oracle(ctx):
         np.testing.assert_array_equal(got, w)
         np.testing.assert_array_equal(tot, w.sum(axis=0))
         assert tot.sum() == 2 * n                                         # wrapping loses nobody
+
+
+# --------------------------------------------------------------------------- NetCDF ingest (§8f rank 4)
+
+
+def test_netcdf_reader_vs_scipy(tmp_path):
+    """AMBER NetCDF trajectories: coordinates byte-swapped on the GPU against SciPy's independent NetCDF-3 reader
+    (bit for bit), frame selections as the reference indexes them, and g(r) driven from device-resident blocks."""
+    from mdcraft_b200 import synthetic
+    from mdcraft_b200.openmm.file import NetCDFFile, NetCDFTrajectory
+    from oracle import oracle
+
+    rng = np.random.default_rng(31)
+    F, N, L = 9, 2500, 14.0
+    pos = (rng.random((F, N, 3)) * L).astype(np.float32)
+    pos[0, :4, 0] = [np.float32("nan"), np.float32("inf"), -0.0, 1e-40]       # bit patterns survive the swap
+    times = 2.0 * np.arange(F)
+    lengths, angles = np.full((F, 3), L), np.full((F, 3), 90.0)
+    for version, vel in ((2, True), (1, False)):
+        path = str(tmp_path / f"traj{version}.nc")
+        oracle.write_amber_netcdf(path, pos, times, lengths, angles, version=version, velocities=pos + 1 if vel else None)
+        want, want_t, want_l, want_a = oracle.read_amber_netcdf(path)
+        f = NetCDFFile(path)
+        assert (f.get_num_frames(), f.get_num_atoms()) == (F, N)
+        np.testing.assert_array_equal(f.get_positions(units=False).view(np.uint32), want.view(np.uint32))
+        np.testing.assert_array_equal(f.get_positions(3, units=False).view(np.uint32), want[3].view(np.uint32))
+        np.testing.assert_array_equal(f.get_positions([1, 2, 5], units=False)[:, 10:], want[[1, 2, 5]][:, 10:])
+        np.testing.assert_array_equal(f.get_positions(slice(2, 9, 3), units=False)[:, 10:], want[2:9:3][:, 10:])
+        np.testing.assert_array_equal(f.get_positions(slice(4, 7), units=False, device=True).cpu().numpy()[:, 10:], want[4:7, 10:])
+        np.testing.assert_array_equal(f.get_times(units=False), want_t)
+        got_l, got_a = f.get_dimensions(units=False)
+        np.testing.assert_array_equal(got_l, want_l)
+        np.testing.assert_array_equal(got_a, want_a)
+        np.testing.assert_array_equal(f.get_dimensions(-1, units=False)[0], want_l[-1])
+        f.close()
+    pos[0, :4, 0] = 1.0
+    path = str(tmp_path / "clean.nc")
+    oracle.write_amber_netcdf(path, pos, times, lengths, angles)
+    traj = NetCDFTrajectory(path, frame_block=4)
+    u_file = synthetic.Universe(traj)
+    u_mem = universe_from(pos, np.array([L, L, L, 90, 90, 90], np.float32))
+    a = _rdf(u_file.atoms, n_bins=80, range_=(0.0, L / 2), exclusion=(1, 1), frame_block=4)
+    b = _rdf(u_mem.atoms, n_bins=80, range_=(0.0, L / 2), exclusion=(1, 1))
+    np.testing.assert_array_equal(a.results.counts, b.results.counts)
+    np.testing.assert_array_equal(a.times, times)
+    np.testing.assert_array_equal(np.stack([ts.positions for ts in traj[2:7:2]]), pos[2:7:2])
+    traj.close()

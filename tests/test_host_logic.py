@@ -301,3 +301,33 @@ def test_profile_post_processing_matches_the_reference_golden():
         profile.calculate_surface_charge_density(bins[None], rho_q)
     with pytest.raises(ValueError, match="'dielectric' must be specified"):
         profile.calculate_surface_charge_density(bins, rho_q, dV=1.0)
+
+
+def test_netcdf_header_on_the_host(tmp_path):
+    """mdc_ncdf_open is host code: NetCDF-3 classic and 64-bit-offset headers, record layout with and without other
+    record variables, against SciPy's reader."""
+    from mdcraft_b200 import _capi
+    from oracle import oracle
+
+    rng = np.random.default_rng(2)
+    F, N = 6, 41
+    pos = rng.normal(scale=20, size=(F, N, 3)).astype(np.float32)
+    times = 0.25 * np.arange(F)
+    lengths = np.column_stack((30 + 0.1 * np.arange(F), np.full(F, 31.5), np.full(F, 29.0)))
+    angles = np.full((F, 3), 90.0)
+    for version, box, vel in ((1, True, False), (2, True, True), (2, False, False)):
+        path = str(tmp_path / f"t{version}{int(box)}{int(vel)}.nc")
+        oracle.write_amber_netcdf(path, pos, times, lengths if box else None, angles if box else None, version=version,
+                                  velocities=pos * 0.5 if vel else None)
+        _, want_t, want_l, want_a = oracle.read_amber_netcdf(path)
+        nc = _capi.NcdfFile(path)
+        assert (nc.n_frames, nc.n_atoms, nc.has_box, nc.has_time) == (F, N, box, True)
+        np.testing.assert_array_equal(nc.times.astype(np.float32), want_t)
+        if box:
+            np.testing.assert_array_equal(nc.cell_lengths, want_l)
+            np.testing.assert_array_equal(nc.cell_angles, want_a)
+        nc.close()
+    bad = tmp_path / "bad.nc"
+    bad.write_bytes(b"CDF\x05" + bytes(64))
+    with pytest.raises(_capi.MdcError, match="classic"):
+        _capi.NcdfFile(str(bad))
