@@ -399,14 +399,14 @@ def run_native(args, rank, world, emit=print):
             "gr_pairs_per_s": pairs / (gr_ms * 1e-3),
             "wall_s": wall,
         }
-        # g(r): the filter kernel issues 21.9 instructions per pair-distance (SASS: 175 per 8 pairs, profiles/rdf_fast_r01.txt);
+        # g(r): the filter kernel issues 19.9 instructions per pair-distance (SASS: 159 per 8 pairs, profiles/rdf_fast_r01.txt);
         # its ceiling is the issue rate, 4 schedulers x 32 lanes per SM per clock
-        gr_peak = sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 21.9
+        gr_peak = sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 19.9
         line["roofline_gr"] = {
             "bound": "issue", "kernel": "rdf_pairs_fast", "achieved": pairs / (gr_ms * 1e-3) / 1e9,
             "peak": gr_peak / 1e9, "unit": "G pair-distances/s", "frac": pairs / (gr_ms * 1e-3) / gr_peak,
-            "traffic": 3.1e6, "peak_source": f"{sm} SMs x 4 schedulers x 32 lanes x SM clock / 21.9 issue slots per pair",
-            "algorithmic": "21.9 issue slots (FP32 arithmetic of two pairs per packed f32x2 instruction) + 1 SFU op (sqrt) + "
+            "traffic": 3.1e6, "peak_source": f"{sm} SMs x 4 schedulers x 32 lanes x SM clock / 19.9 issue slots per pair",
+            "algorithmic": "19.9 issue slots (FP32 arithmetic of two pairs per packed f32x2 instruction) + 1 SFU op (sqrt) + "
                            "0.52 shared-memory atomics per pair; "
                            "24 B of positions per particle per frame (f32 + u32 fixed point)",
         }

@@ -640,7 +640,92 @@ __device__ __forceinline__ unsigned bin_or_flag2(unsigned long long v, unsigned 
     return und;
 }
 
-template <bool CHECK, bool CUBIC, bool EXCL>
+// bin_or_flag for the four pairs of one row (two packed v's): the round-to-bin chain as six packed instructions,
+// then per pair  k = bits(w), undecided = |df| > thr, hist[(ok && !undecided && bin < B) ? bin : dummy] += 1.
+// With r0 == 0 (R0ZERO) v >= -0.5, so bits(w) >= bits(MAGIC) and neither the subtraction of bits(MAGIC) nor a
+// lower bound check is needed: the caller folds bits(MAGIC) into the limit and into the histogram base address.
+// Returns whether ANY pair is undecided (predicate OR, one SEL) and the four |df| so that the cold path can tell
+// which; that replaces four SELs and the adds that combined them.
+template <bool HAS_OK, bool R0ZERO>
+__device__ __forceinline__ unsigned bin_or_flag4(unsigned long long v01, unsigned long long v23, unsigned long long magic,
+                                                 unsigned long long nmagic, unsigned long long neg1, float thr,
+                                                 unsigned blim, unsigned hbase, unsigned trash_addr, unsigned one,
+                                                 const unsigned (&ok)[4], float (&adf)[4])
+{
+    unsigned any;
+#define RF_HEAD                                                   \
+    "{\n\t"                                                       \
+    ".reg .pred p, q, q0, q1, q2, q3, r;\n\t"                     \
+    ".reg .b64 W01, W23, KF, DF01, DF23;\n\t"                     \
+    ".reg .f32 w0, w1, w2, w3;\n\t"                               \
+    ".reg .u32 k, ad;\n\t"                                        \
+    "add.rn.f32x2 W01, %5, %12;\n\t"                              \
+    "add.rn.f32x2 W23, %6, %12;\n\t"                              \
+    "add.rn.f32x2 KF, W01, %13;\n\t"                              \
+    "fma.rn.f32x2 DF01, KF, %14, %5;\n\t"                         \
+    "add.rn.f32x2 KF, W23, %13;\n\t"                              \
+    "fma.rn.f32x2 DF23, KF, %14, %6;\n\t"                         \
+    "mov.b64 {w0, w1}, W01;\n\t"                                  \
+    "mov.b64 {w2, w3}, W23;\n\t"                                  \
+    "mov.b64 {%1, %2}, DF01;\n\t"                                 \
+    "mov.b64 {%3, %4}, DF23;\n\t"                                 \
+    "abs.f32 %1, %1;\n\t"                                         \
+    "abs.f32 %2, %2;\n\t"                                         \
+    "abs.f32 %3, %3;\n\t"                                         \
+    "abs.f32 %4, %4;\n\t"
+#define RF_FOOT                                                   \
+    "or.pred q, q0, q1;\n\t"                                      \
+    "or.pred q, q, q2;\n\t"                                       \
+    "or.pred q, q, q3;\n\t"                                       \
+    "selp.u32 %0, 1, 0, q;\n\t"                                   \
+    "}"
+#define RF_SUB "sub.u32 k, k, 0x4B400000;\n\t"
+// without the ok flags: p = (k < limit) && !q_u
+#define RF_P4(SUBK)                                                                                              \
+    "mov.b32 k, w0;\n\t" SUBK "setp.gt.f32 q0, %1, %7;\n\t setp.lt.and.u32 p, k, %8, !q0;\n\t"                  \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"                \
+    "mov.b32 k, w1;\n\t" SUBK "setp.gt.f32 q1, %2, %7;\n\t setp.lt.and.u32 p, k, %8, !q1;\n\t"                  \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"                \
+    "mov.b32 k, w2;\n\t" SUBK "setp.gt.f32 q2, %3, %7;\n\t setp.lt.and.u32 p, k, %8, !q2;\n\t"                  \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"                \
+    "mov.b32 k, w3;\n\t" SUBK "setp.gt.f32 q3, %4, %7;\n\t setp.lt.and.u32 p, k, %8, !q3;\n\t"                  \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"
+// with them: q_u = undecided && ok_u, p = (k < limit) && ok_u && !q_u
+#define RF_P4_OK(SUBK)                                                                                           \
+    "mov.b32 k, w0;\n\t" SUBK "setp.ne.u32 r, %15, 0;\n\t setp.gt.and.f32 q0, %1, %7, r;\n\t"                   \
+    "setp.lt.and.u32 p, k, %8, r;\n\t and.pred p, p, !q0;\n\t"                                                  \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"                \
+    "mov.b32 k, w1;\n\t" SUBK "setp.ne.u32 r, %16, 0;\n\t setp.gt.and.f32 q1, %2, %7, r;\n\t"                   \
+    "setp.lt.and.u32 p, k, %8, r;\n\t and.pred p, p, !q1;\n\t"                                                  \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"                \
+    "mov.b32 k, w2;\n\t" SUBK "setp.ne.u32 r, %17, 0;\n\t setp.gt.and.f32 q2, %3, %7, r;\n\t"                   \
+    "setp.lt.and.u32 p, k, %8, r;\n\t and.pred p, p, !q2;\n\t"                                                  \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"                \
+    "mov.b32 k, w3;\n\t" SUBK "setp.ne.u32 r, %18, 0;\n\t setp.gt.and.f32 q3, %4, %7, r;\n\t"                   \
+    "setp.lt.and.u32 p, k, %8, r;\n\t and.pred p, p, !q3;\n\t"                                                  \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"
+#define RF_OUT "=r"(any), "=f"(adf[0]), "=f"(adf[1]), "=f"(adf[2]), "=f"(adf[3])
+#define RF_IN "l"(v01), "l"(v23), "f"(thr), "r"(blim), "r"(hbase), "r"(trash_addr), "r"(one), "l"(magic), "l"(nmagic), "l"(neg1)
+    if (HAS_OK) {
+        if (R0ZERO)
+            asm volatile(RF_HEAD RF_P4_OK("") RF_FOOT : RF_OUT : RF_IN, "r"(ok[0]), "r"(ok[1]), "r"(ok[2]), "r"(ok[3]) : "memory");
+        else
+            asm volatile(RF_HEAD RF_P4_OK(RF_SUB) RF_FOOT : RF_OUT : RF_IN, "r"(ok[0]), "r"(ok[1]), "r"(ok[2]), "r"(ok[3]) : "memory");
+    } else {
+        if (R0ZERO) asm volatile(RF_HEAD RF_P4("") RF_FOOT : RF_OUT : RF_IN : "memory");
+        else asm volatile(RF_HEAD RF_P4(RF_SUB) RF_FOOT : RF_OUT : RF_IN : "memory");
+    }
+#undef RF_HEAD
+#undef RF_FOOT
+#undef RF_SUB
+#undef RF_P4
+#undef RF_P4_OK
+#undef RF_OUT
+#undef RF_IN
+    return any;
+}
+
+template <bool CHECK, bool CUBIC, bool EXCL, bool R0ZERO>
 __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, const uint32_t (&ux)[RF_IPT],
                                                 const uint32_t (&uy)[RF_IPT], const uint32_t (&uz)[RF_IPT],
                                                 const int (&bi)[RF_IPT], const FrameFast &ff, float thr, unsigned B,
@@ -658,6 +743,9 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     const unsigned long long fc0 = pk2(ff.c0, ff.c0);
     const unsigned long long magic = pk2(12582912.f, 12582912.f), nmagic = pk2(-12582912.f, -12582912.f);
     const unsigned long long neg1 = pk2(-1.f, -1.f);
+    // R0ZERO: bits(w) is used as it is; bits(MAGIC) = 0x4B400000 moves into the limit and the base address
+    const unsigned blim = R0ZERO ? B + 0x4B400000u : B;
+    const unsigned hbase = R0ZERO ? hist_addr - 4u * 0x4B400000u : hist_addr;
 #endif
 #pragma unroll 2
     for (int j = 0; j < nj; ++j) {
@@ -677,9 +765,14 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                                                         fay, faz, fc0);
         const unsigned long long v23 = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[2], uy[2], uz[2], ux[3], uy[3], uz[3], fax,
                                                         fay, faz, fc0);
-        const unsigned und =
-            bin_or_flag2<1u, 2u, HAS_OK>(v01, magic, nmagic, neg1, thr, B, hist_addr, trash_addr, ok[0], ok[1], one) |
-            bin_or_flag2<4u, 8u, HAS_OK>(v23, magic, nmagic, neg1, thr, B, hist_addr, trash_addr, ok[2], ok[3], one);
+        float adf[4];
+        if (bin_or_flag4<HAS_OK, R0ZERO>(v01, v23, magic, nmagic, neg1, thr, blim, hbase, trash_addr, one, ok, adf)) {
+            unsigned und = 0;   // cold: which of the four
+#pragma unroll
+            for (int u = 0; u < RF_IPT; ++u)
+                if (adf[u] > thr && ok[u]) und |= 1u << u;
+            park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
+        }
 #else
         float v[RF_IPT];
 #pragma unroll
@@ -688,8 +781,8 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                              bin_or_flag<2u, HAS_OK>(v[1], thr, B, hist_addr, trash_addr, ok[1], one) |
                              bin_or_flag<4u, HAS_OK>(v[2], thr, B, hist_addr, trash_addr, ok[2], one) |
                              bin_or_flag<8u, HAS_OK>(v[3], thr, B, hist_addr, trash_addr, ok[3], one);
-#endif
         if (und) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
+#endif
     }
 }
 
@@ -756,6 +849,7 @@ rdf_pairs_fast(RdfArgs A)
         }
         __syncthreads();
         const bool check = diag || (i0 + RF_TI > A.na);
+        const bool r0zero = ff.c0 == -0.5f;   // r0 == 0: v >= -0.5, the bin index cannot be negative
         // the block exclusion i / ex0 == j / ex1 can only bite where the two tiles' block ranges overlap
         bool excl = false;
         if (A.ex0 > 0) {
@@ -763,8 +857,13 @@ rdf_pairs_fast(RdfArgs A)
             const int64_t jlo = j0 / A.ex1, jhi = (j0 + nj - 1) / A.ex1;
             excl = ilo <= jhi && jlo <= ihi;
         }
-#define RF_CALL(C, Q, E) \
-    tile_pairs_fast<C, Q, E>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist)
+#define RF_CALL(C, Q, E)                                                                                              \
+    do {                                                                                                              \
+        if (r0zero)                                                                                                   \
+            tile_pairs_fast<C, Q, E, true>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist); \
+        else                                                                                                          \
+            tile_pairs_fast<C, Q, E, false>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist); \
+    } while (0)
         if (check) {
             if (ff.cubic) { if (excl) RF_CALL(true, true, true); else RF_CALL(true, true, false); }
             else          { if (excl) RF_CALL(true, false, true); else RF_CALL(true, false, false); }
