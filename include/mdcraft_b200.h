@@ -309,6 +309,9 @@ int      mdc_profile_plan_destroy(mdc_profile_plan *plan);
 int64_t  mdc_profile_num_counts(mdc_profile_plan *plan);
 int      mdc_profile_push(mdc_profile_plan *plan, const float *pos, int n_frames, int on_device,
                           int64_t *per_frame_out);
+/* The same for float64 positions (n_frames, N, 3): what DensityProfile holds after `recenter` (profile.py:1137-1165). */
+int      mdc_profile_push_f64(mdc_profile_plan *plan, const double *pos, int n_frames, int on_device,
+                              int64_t *per_frame_out);
 int      mdc_profile_read(mdc_profile_plan *plan, int64_t *counts_out, int64_t *n_frames_out);
 int      mdc_profile_reset(mdc_profile_plan *plan);
 int      mdc_profile_accum_ptr(mdc_profile_plan *plan, void **dev_ptr, int64_t *n_elems);

@@ -112,6 +112,7 @@ SIGNATURES = {
     "mdc_profile_plan_destroy": (c_int, [c_void_p]),
     "mdc_profile_num_counts": (c_int64, [c_void_p]),
     "mdc_profile_push": (c_int, [c_void_p, c_void_p, c_int, c_int, _lp]),
+    "mdc_profile_push_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, _lp]),
     "mdc_profile_read": (c_int, [c_void_p, _lp, _lp]),
     "mdc_profile_reset": (c_int, [c_void_p]),
     "mdc_profile_accum_ptr": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
@@ -439,16 +440,18 @@ class ProfilePlan:
         return out
 
     def push(self, pos, n_frames: Optional[int] = None, per_frame: bool = False):
-        """``pos``: float32 ``(F, N, 3)``.  ``per_frame``: also return every frame's own counts, per axis
-        ``(F, n_groups, n_bins)``."""
-        ptr, on_dev, keep = _buffer(pos)
+        """``pos``: float32 (or float64, for recentred positions) ``(F, N, 3)``.  ``per_frame``: also return every
+        frame's own counts, per axis ``(F, n_groups, n_bins)``."""
+        f64 = getattr(pos, "dtype", None) == np.float64
+        ptr, on_dev, keep = _buffer(pos, np.float64 if f64 else np.float32)
         shape = keep.shape
         if n_frames is None:
             n_frames = 1 if len(shape) == 2 else int(shape[0])
         if int(np.prod(shape)) != n_frames * self.n_particles * 3:
             raise ValueError(f"positions have {int(np.prod(shape))} elements, expected {n_frames} x {self.n_particles} x 3")
         out = np.empty((n_frames, self.total), dtype=np.int64) if per_frame else None
-        _check(lib().mdc_profile_push(self._h, ptr, int(n_frames), on_dev, None if out is None else _as(out, _lp)))
+        fn = lib().mdc_profile_push_f64 if f64 else lib().mdc_profile_push
+        _check(fn(self._h, ptr, int(n_frames), on_dev, None if out is None else _as(out, _lp)))
         return None if out is None else self._split(out)
 
     def read(self):

@@ -16,9 +16,11 @@ are identical.  The post-processing — surface charge densities and potential
 profiles from the charge density (``profile.py:38-515, 1290-1500``) — is host
 NumPy / SciPy on arrays of ``n_bins`` elements, as in the reference.
 
-Not supported: ``recenter`` (frame-to-frame unwrapping state plus a centre-of-mass
-shift whose NumPy summation order a device reduction cannot reproduce bit for
-bit); it raises ``NotImplementedError``.  ``parallel`` is accepted and ignored.
+``recenter`` keeps its frame-to-frame state (image flags) and its centre-of-mass
+shift on the host, in the reference's NumPy expressions (``topology.py:425-434``,
+``profile.py:1137-1165``; a device reduction could not reproduce NumPy's summation
+order bit for bit), and hands float64 positions to the same kernel.  ``parallel`` is
+accepted and ignored.
 """
 
 from __future__ import annotations
@@ -246,15 +248,65 @@ class DensityProfile(DynamicAnalysisBase):
         self._N = int(self._Ns.sum())
         edges = np.concatenate(([0], np.cumsum(self._Ns)))
         self._slices = [slice(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:])]
-        if recenter is not None:
-            raise NotImplementedError("'recenter' is not supported by the GPU DensityProfile.")
-        self._recenter = None
+        self._recenter = None if recenter is None else self._parse_recenter(recenter)
 
         self._dielectrics = np.full(self._n_axes, np.nan)
         self._dVs = np.full(self._n_axes, np.nan)
         self._average, self._reduced, self._verbose = average, reduced, verbose
         self._device, self._frame_block = int(device), max(1, int(frame_block))
         self._plan = None
+
+    def _parse_recenter(self, recenter):
+        """``profile.py:954-1005``: ``(indices or slice into the concatenated entities, target centre of mass)``."""
+        if isinstance(recenter, tuple) and len(recenter) == 2:
+            grp, com = recenter
+            if len(com) != 3:
+                raise ValueError("The target center of mass in 'recenter' must have length 3.")
+            com = np.asarray(com)
+        elif isinstance(recenter, (int, list)) or hasattr(recenter, "universe"):
+            grp, com = recenter, self._dimensions / 2
+        else:
+            raise ValueError("Invalid value passed to 'recenter'. The argument must either be an atom group, its index "
+                             "in 'groups', multiple groups/indices, or a tuple containing the aforementioned "
+                             "information and a target center of mass, in that order.")
+
+        def one(g):
+            if isinstance(g, int):
+                if not 0 <= g < self._n_groups:
+                    raise ValueError("Invalid group index passed to 'recenter'.")
+                return self._slices[g]
+            for k, mine in enumerate(self._groups):
+                if mine is g or bool(mine == g):
+                    return self._slices[k]
+            raise ValueError("The atom group passed to 'recenter' is not in 'groups'.")
+
+        if isinstance(grp, int) or hasattr(grp, "universe"):
+            return one(grp), com
+        try:
+            return np.r_[tuple(one(g) for g in grp)], com
+        except ValueError:
+            raise ValueError("Invalid atom group or index passed to 'recenter'.")
+
+    def _entity_positions(self) -> np.ndarray:
+        pos = np.empty((self._N, 3))
+        for ag, gr, s in zip(self._groups, self._groupings, self._slices):
+            pos[s] = ag.positions if gr == "atoms" else center_of_mass(ag, gr)
+        return pos
+
+    def _recentred(self) -> np.ndarray:
+        """Unwrap across frames (topology.py:425-434, in place form) and shift the chosen entities' centre of mass
+        onto its target (profile.py:1148-1165); float64, exactly the reference's NumPy expressions."""
+        pos = self._entity_positions()
+        dpos = pos - self._positions_old
+        mask = np.abs(dpos) >= self._thresholds
+        self._images[mask] -= np.sign(dpos[mask]).astype(int)
+        self._positions_old[:] = pos[:]
+        pos += self._images * self._dimensions
+        sel, target = self._recenter
+        masses = self._masses[sel]
+        com = np.einsum("...a,...ad->...d", masses, pos[sel]) / masses.sum(axis=-1, keepdims=True)
+        pos -= np.fromiter((0 if np.isnan(tx) else gx - tx for gx, tx in zip(com, target)), dtype=float, count=3)
+        return pos
 
     # -- AnalysisBase protocol ------------------------------------------------
     def _prepare(self) -> None:
@@ -267,6 +319,15 @@ class DensityProfile(DynamicAnalysisBase):
         self._plan = _capi.ProfilePlan(_context(self._device), self._Ns, self._axis_indices,
                                        [int(n) for n in self._n_bins], np.asarray(self._dimensions, dtype=np.float64))
         self._stage = _FrameBlock(self._frame_block, self._N)
+        if self._recenter is not None:
+            self._masses = np.empty(self._N)
+            for ag, gr, s in zip(self._groups, self._groupings, self._slices):
+                self._masses[s] = getattr(ag, gr).masses
+            self._sliced_trajectory[0]                       # profile.py:1038: start from the first analysed frame
+            self._positions_old = self._entity_positions()
+            self._images = np.zeros((self._N, 3), dtype=int)
+            self._thresholds = self._dimensions / 2
+            self._stage64 = np.empty((self._frame_block, self._N, 3))
         shape = [self._n_groups] if self._average else [self._n_groups, self.n_frames]
         self.results.number_densities = Hash({ax: np.zeros((*shape, n)) for ax, n in zip(self.axes, self._n_bins)})
         self._first_staged = 0
@@ -283,9 +344,12 @@ class DensityProfile(DynamicAnalysisBase):
             self.results.units["times"] = _ureg.picosecond if _ureg is not None else "picosecond"
 
     def _single_frame(self) -> None:
-        slot = self._stage.slot()
-        for ag, gr, s in zip(self._groups, self._groupings, self._slices):
-            slot[s] = ag.positions if gr == "atoms" else center_of_mass(ag, gr)
+        if self._recenter is not None:
+            self._stage64[self._stage.count] = self._recentred()
+        else:
+            slot = self._stage.slot()
+            for ag, gr, s in zip(self._groups, self._groupings, self._slices):
+                slot[s] = ag.positions if gr == "atoms" else center_of_mass(ag, gr)
         self._stage.count += 1
         if self._stage.full():
             self._flush()
@@ -294,7 +358,8 @@ class DensityProfile(DynamicAnalysisBase):
         n = self._stage.count
         if n == 0:
             return
-        per_frame = self._plan.push(self._stage.view(), n_frames=n, per_frame=not self._average)
+        block = self._stage.view() if self._recenter is None else self._stage64[:n]
+        per_frame = self._plan.push(block, n_frames=n, per_frame=not self._average)
         if per_frame is not None:
             lo = self._first_staged
             for ax, counts in zip(self.axes, per_frame):      # counts (n, n_groups, n_bins)

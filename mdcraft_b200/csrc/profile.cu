@@ -26,7 +26,8 @@ struct ProfileGeom {
     int total;
 };
 
-__global__ void profile_hist(const float *__restrict__ pos, int64_t N, int F, const int *__restrict__ group_end,
+template <typename T>   // float: positions as the trajectory holds them; double: recentred on the host
+__global__ void profile_hist(const T *__restrict__ pos, int64_t N, int F, const int *__restrict__ group_end,
                              ProfileGeom g, unsigned *__restrict__ frame_counts)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,7 +35,7 @@ __global__ void profile_hist(const float *__restrict__ pos, int64_t N, int F, co
     const int64_t f = i / N, j = i - f * N;
     int grp = 0;
     while (grp < g.n_groups - 1 && j >= group_end[grp]) ++grp;
-    const float *p = pos + 3 * i;
+    const T *p = pos + 3 * i;
     unsigned *out = frame_counts + f * g.total;
     for (int k = 0; k < g.n_axes; ++k) {
         double x = (double)p[g.axis[k]];
@@ -71,6 +72,7 @@ struct mdc_profile_plan {
     int fblk = 0;
     DevBuf<int> group_end;
     DevBuf<float> raw;
+    DevBuf<double> raw64;
     DevBuf<unsigned> frame_counts;
     DevBuf<unsigned long long> counts;
 };
@@ -143,6 +145,7 @@ extern "C" int mdc_profile_plan_destroy(mdc_profile_plan *p)
     cudaDeviceSynchronize();
     p->group_end.release();
     p->raw.release();
+    p->raw64.release();
     p->frame_counts.release();
     p->counts.release();
     delete p;
@@ -151,28 +154,31 @@ extern "C" int mdc_profile_plan_destroy(mdc_profile_plan *p)
 
 extern "C" int64_t mdc_profile_num_counts(mdc_profile_plan *p) { return p ? p->g.total : -1; }
 
-// pos f32 (n_frames, N, 3), groups concatenated in order.  per_frame_out: NULL, or host i64 (n_frames, total) that
-// receives the counts of every frame (average=False in the reference).
-extern "C" int mdc_profile_push(mdc_profile_plan *p, const float *pos, int n_frames, int on_device, int64_t *per_frame_out)
+namespace {
+
+// T positions (n_frames, N, 3), groups concatenated in order.  per_frame_out: NULL, or host i64 (n_frames, total)
+// that receives the counts of every frame (average=False in the reference).
+template <typename T>
+int profile_push(mdc_profile_plan *p, const T *pos, int n_frames, int on_device, int64_t *per_frame_out, DevBuf<T> &raw)
 {
     if (!p || !pos) return fail(MDC_ERR_INVALID, "mdc_profile_push: NULL argument");
     if (n_frames <= 0) return MDC_OK;
     MDC_CUDA(cudaSetDevice(p->ctx->device));
     cudaStream_t st = p->ctx->compute;
     const int total = p->g.total;
-    const int blk = (int)std::max<int64_t>(1, std::min<int64_t>(64, ((int64_t)1 << 28) / (p->N * 12)));
+    const int blk = (int)std::max<int64_t>(1, std::min<int64_t>(64, ((int64_t)1 << 28) / (p->N * 3 * (int64_t)sizeof(T))));
     std::vector<unsigned> host;
     for (int f0 = 0; f0 < n_frames; f0 += blk) {
         const int F = std::min(blk, n_frames - f0);
-        const float *src = pos + (size_t)f0 * p->N * 3;
+        const T *src = pos + (size_t)f0 * p->N * 3;
         if (!on_device) {
-            MDC_CHECK(p->raw.alloc((size_t)blk * p->N * 3));
-            MDC_CUDA(cudaMemcpyAsync(p->raw.p, src, (size_t)F * p->N * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-            src = p->raw.p;
+            MDC_CHECK(raw.alloc((size_t)blk * p->N * 3));
+            MDC_CUDA(cudaMemcpyAsync(raw.p, src, (size_t)F * p->N * 3 * sizeof(T), cudaMemcpyHostToDevice, st));
+            src = raw.p;
         }
         MDC_CHECK(p->frame_counts.alloc((size_t)blk * total));
         MDC_CUDA(cudaMemsetAsync(p->frame_counts.p, 0, (size_t)F * total * sizeof(unsigned), st));
-        profile_hist<<<(unsigned)ceil_div(p->N * F, 256), 256, 0, st>>>(src, p->N, F, p->group_end.p, p->g, p->frame_counts.p);
+        profile_hist<T><<<(unsigned)ceil_div(p->N * F, 256), 256, 0, st>>>(src, p->N, F, p->group_end.p, p->g, p->frame_counts.p);
         profile_accum<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(p->frame_counts.p, F, total, p->counts.p);
         MDC_CUDA(cudaGetLastError());
         if (per_frame_out) {
@@ -182,11 +188,28 @@ extern "C" int mdc_profile_push(mdc_profile_plan *p, const float *pos, int n_fra
             int64_t *dst = per_frame_out + (size_t)f0 * total;
             for (size_t i = 0; i < host.size(); ++i) dst[i] = (int64_t)host[i];
         } else if (!on_device) {
-            MDC_CUDA(cudaStreamSynchronize(st));   // the staging buffer is reused by the next block / the caller's buffer by the caller
+            MDC_CUDA(cudaStreamSynchronize(st));   // the staging buffer is reused by the next block, the caller's by the caller
         }
     }
     p->n_frames += n_frames;
     return MDC_OK;
+}
+
+}  // namespace
+
+extern "C" int mdc_profile_push(mdc_profile_plan *p, const float *pos, int n_frames, int on_device, int64_t *per_frame_out)
+{
+    if (!p) return fail(MDC_ERR_INVALID, "mdc_profile_push: NULL plan");
+    return profile_push<float>(p, pos, n_frames, on_device, per_frame_out, p->raw);
+}
+
+// float64 positions: what DensityProfile holds after recentring (profile.py:1137-1165, unwrap + centre-of-mass
+// shift, host bookkeeping with frame-to-frame state); wrapped and binned on the device like the float32 ones
+extern "C" int mdc_profile_push_f64(mdc_profile_plan *p, const double *pos, int n_frames, int on_device,
+                                    int64_t *per_frame_out)
+{
+    if (!p) return fail(MDC_ERR_INVALID, "mdc_profile_push_f64: NULL plan");
+    return profile_push<double>(p, pos, n_frames, on_device, per_frame_out, p->raw64);
 }
 
 extern "C" int mdc_profile_read(mdc_profile_plan *p, int64_t *counts_out, int64_t *n_frames_out)

@@ -356,6 +356,17 @@ def profiles():
     d = pr.DensityProfile(u2.atoms, "residues", axes="y", n_bins=33, dimensions=[9.5, 11.25, 14.0],
                           dim_scales=(1.0, 0.9, 1.0), verbose=False).run()
     out["c_number_y"], out["c_edges_y"] = d.results.number_densities["y"], d.results.bin_edges["y"]
+    # (d) recentring: a drifting slab (the whole system translates and crosses the periodic boundary), recentred on
+    # group 0 with the default target (box centre), and on both groups with an explicit target (NaN = leave that axis)
+    drift = (np.arange(F)[:, None, None] * np.array([0.0, 0.0, 2.7])).astype(np.float32)
+    pos_d = np.mod(pos + drift, dims[:3]).astype(np.float32)
+    out["pos_drift"] = pos_d
+    u3 = universe_from(pos_d, dims, masses=1.0 + (np.arange(N) % 3))
+    d = pr.DensityProfile([u3.select(0, 150), u3.select(150, N)], axes="z", n_bins=40, recenter=0, verbose=False).run()
+    out["d_number_z"] = d.results.number_densities["z"]
+    d = pr.DensityProfile([u3.select(0, 150), u3.select(150, N)], axes="xz", n_bins=[6, 40],
+                          recenter=([0, 1], [np.nan, np.nan, 3.5]), average=False, verbose=False).run(start=1)
+    out["e_number_x"], out["e_number_z"] = d.results.number_densities["x"], d.results.number_densities["z"]
     save("profiles.npz", **out)
 
 

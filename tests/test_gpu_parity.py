@@ -678,8 +678,17 @@ def test_density_profile_golden():
                        dim_scales=(1.0, 0.9, 1.0), verbose=False).run()
     np.testing.assert_array_equal(d.results.bin_edges["y"], g["c_edges_y"])
     np.testing.assert_array_equal(d.results.number_densities["y"], g["c_number_y"])
-    with pytest.raises(NotImplementedError):
-        DensityProfile(u.atoms, recenter=0)
+    # recentring (host unwrap + centre-of-mass shift in the reference's NumPy expressions, float64 positions to the device)
+    u3 = universe_from(g["pos_drift"], dims, masses=1.0 + (np.arange(n) % 3))
+    groups = [u3.select(0, 150), u3.select(150, n)]
+    d = DensityProfile(groups, axes="z", n_bins=40, recenter=0, verbose=False, frame_block=4).run()
+    np.testing.assert_array_equal(d.results.number_densities["z"], g["d_number_z"])
+    d = DensityProfile(groups, axes="xz", n_bins=[6, 40], recenter=([0, 1], [np.nan, np.nan, 3.5]), average=False,
+                       verbose=False, frame_block=2).run(start=1)
+    np.testing.assert_array_equal(d.results.number_densities["x"], g["e_number_x"])
+    np.testing.assert_array_equal(d.results.number_densities["z"], g["e_number_z"])
+    with pytest.raises(ValueError, match="Invalid group index"):
+        DensityProfile(u.atoms, recenter=3)
     with pytest.raises(ValueError, match="Invalid axis"):
         DensityProfile(u.atoms, axes="xw")
 
