@@ -289,17 +289,19 @@ def run_native(args, rank, world, emit=print):
     e2e = total_frames / (e2e_ms * 1e-3)
 
     # secondary figure: the reference's DEFAULT grid (n_points = 32, Nq = 32,768) on the same frames, device resident
-    sqd = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=32, L0=[Ls] * 3, algo=args.sq_algo)
-    rep = 16
-    for _ in range(3):
-        sqd.push(sq_dev, n_frames=F)
-    ctx.synchronize()
-    ctx.mark(0)
-    for _ in range(rep):
-        sqd.push(sq_dev, n_frames=F)
-    ctx.mark(1)
-    sq_default_fps = F * rep / (ctx.elapsed_ms() * 1e-3)
-    sqd.close()
+    sq_default_fps = None
+    if not args.no_extras:
+        sqd = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=32, L0=[Ls] * 3, algo=args.sq_algo)
+        rep = 16
+        for _ in range(3):
+            sqd.push(sq_dev, n_frames=F)
+        ctx.synchronize()
+        ctx.mark(0)
+        for _ in range(rep):
+            sqd.push(sq_dev, n_frames=F)
+        ctx.mark(1)
+        sq_default_fps = F * rep / (ctx.elapsed_ms() * 1e-3)
+        sqd.close()
 
     sm = ctx.info()["sm_count"]
     used = sqp.info()
@@ -339,7 +341,7 @@ def run_native(args, rank, world, emit=print):
     # secondary figures: the kernels the NUFFT replaced, on the same full grid against their issue-rate rooflines
     # (direct = the contract kernel of BASELINE.json's north_star: one fused sin/cos per term on the SFU)
     direct = factored = None
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         if used["algo"] != "direct":
             direct = term_roofline("direct", one_frame("direct"), 1)
         if used["algo"] != "factored":
@@ -429,6 +431,9 @@ def main():
     ap.add_argument("--frames", type=int, default=2, help="frames per step per GPU")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary figures (default grid, one frame each through the direct / factored S(q) "
+                         "kernels): only the timed steps launch kernels, which is what the ncu launch list is taken from")
     ap.add_argument("--sq-algo", default="auto", choices=["auto", "direct", "factored", "nufft"],
                     help="S(q) lattice kernel: auto (the plan's cost model: NUFFT on this grid), or force one")
     args = ap.parse_args()

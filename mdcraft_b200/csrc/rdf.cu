@@ -503,6 +503,9 @@ __device__ __forceinline__ unsigned bin_or_flag(float v, float thr, unsigned B, 
     return und;
 }
 
+#ifndef MDC_RF_UNROLL
+#define MDC_RF_UNROLL 2   // rows of j per loop iteration
+#endif
 #ifndef MDC_RDF_PACKED
 #define MDC_RDF_PACKED 1   // 1: the FP32 arithmetic of two pairs rides in one packed (f32x2) instruction
 #endif
@@ -747,7 +750,8 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     const unsigned blim = R0ZERO ? B + 0x4B400000u : B;
     const unsigned hbase = R0ZERO ? hist_addr - 4u * 0x4B400000u : hist_addr;
 #endif
-#pragma unroll 2
+    constexpr int RF_UNROLL = MDC_RF_UNROLL;
+#pragma unroll RF_UNROLL
     for (int j = 0; j < nj; ++j) {
         const uint4 pj = S->sj[j];
         unsigned ok[RF_IPT];
