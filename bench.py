@@ -229,7 +229,15 @@ def run_native(args, rank, world, emit=print):
     sq_dev = torch.from_numpy(sq_host).cuda()
     gr_pin = torch.from_numpy(gr_host).pin_memory()
     sq_pin = torch.from_numpy(sq_host).pin_memory()
-    ssf_pin = torch.empty((1, nq), dtype=torch.float64).pin_memory()
+    # the step's S(q) result is what StructureFactor.results.ssf holds: the |q|-shell means (unique=True), formed on the
+    # device; the windows are per-plan bookkeeping, set up once outside the timed region
+    from mdcraft_b200.analysis.structure import shell_windows
+
+    wavenumbers = np.linalg.norm(sqp.wavevectors(), axis=1)
+    unique_q = np.unique(wavenumbers.round(11))
+    sqp.set_shells(*shell_windows(wavenumbers, unique_q))
+    n_shells = int(unique_q.shape[0])
+    ssf_pin = torch.empty((1, n_shells), dtype=torch.float64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -246,7 +254,7 @@ def run_native(args, rank, world, emit=print):
             rdf.push(gr_pin.numpy(), None, box_g, n_frames=F)
             sqp.push(sq_pin.numpy(), n_frames=F)
             rdf.read()
-            sqp.read(out=ssf_pin.numpy())
+            sqp.read_shells(float(N_PART), out=ssf_pin.numpy())
 
     def timed(device_resident, steps):
         """Device time of `steps` steps: CUDA events on the library's compute stream around each step
@@ -389,7 +397,7 @@ def run_native(args, rank, world, emit=print):
             "data": "synthetic", "config": workload_config(F, world), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int(gr_host.nbytes + sq_host.nbytes + F * 24),
-                    "d2h_bytes_per_step": int(GR["n_bins"] * 8 + nq * 8)},
+                    "d2h_bytes_per_step": int(GR["n_bins"] * 8 + n_shells * 8)},
             "gpu_launches": launches,
             "sq_algo": args.sq_algo, "sq_algo_used": used,
             "roofline_sq": roof_sq,

@@ -132,6 +132,16 @@ int  mdc_sq_push(mdc_sq_plan *plan, const float *pos, int n_frames, int on_devic
 
 /* Un-normalised sums f64 (n_pairs, Nq) and the number of frames pushed. */
 int  mdc_sq_read(mdc_sq_plan *plan, double *ssf_out, int64_t *n_frames_out);
+/*
+ * |q|-shell averages on the device (StructureFactor._conclude with unique=True, structure.py:2000-2009: for every
+ * unique wavenumber the mean of the columns np.isclose selects).  mdc_sq_set_shells: `order` = wavevector indices
+ * sorted by |q| (n_order of them), shell s owns the window order[lo[s] : hi[s]] (windows may overlap, as
+ * np.isclose's do).  mdc_sq_read_shells: out f64 (n_pairs, n_shells) = mean over the window of sums / denom
+ * (denom = n_frames * N), so that only N_unique values per pair cross the bus instead of Nq.
+ */
+int  mdc_sq_set_shells(mdc_sq_plan *plan, const int64_t *order, int64_t n_order,
+                       const int64_t *lo, const int64_t *hi, int64_t n_shells);
+int  mdc_sq_read_shells(mdc_sq_plan *plan, double denom, double *out, int64_t *n_frames_out);
 int  mdc_sq_reset(mdc_sq_plan *plan);
 /* Device pointer / element count of the f64 accumulator (for NCCL). */
 int  mdc_sq_accum_ptr(mdc_sq_plan *plan, void **dev_ptr, int64_t *n_elems);

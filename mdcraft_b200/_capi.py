@@ -73,6 +73,8 @@ SIGNATURES = {
     "mdc_sq_plan_info": (c_int, [c_void_p, _ip]),
     "mdc_sq_push": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "mdc_sq_read": (c_int, [c_void_p, _dp, _lp]),
+    "mdc_sq_set_shells": (c_int, [c_void_p, _lp, c_int64, _lp, _lp, c_int64]),
+    "mdc_sq_read_shells": (c_int, [c_void_p, c_double, _dp, _lp]),
     "mdc_sq_reset": (c_int, [c_void_p]),
     "mdc_sq_accum_ptr": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
     "mdc_sq_set_frames": (c_int, [c_void_p, c_int64]),
@@ -382,6 +384,24 @@ class SqPlan:
             raise ValueError("out must be a C-contiguous float64 array with n_pairs x Nq elements")
         nf = c_int64()
         _check(lib().mdc_sq_read(self._h, _as(out, _dp), byref(nf)))
+        return out, nf.value
+
+    def set_shells(self, order: np.ndarray, lo: np.ndarray, hi: np.ndarray) -> None:
+        """|q|-shell windows for :meth:`read_shells`: shell ``s`` = wavevectors ``order[lo[s]:hi[s]]``."""
+        order = np.ascontiguousarray(order, dtype=np.int64)
+        lo = np.ascontiguousarray(lo, dtype=np.int64)
+        hi = np.ascontiguousarray(hi, dtype=np.int64)
+        _check(lib().mdc_sq_set_shells(self._h, _as(order, _lp), order.shape[0], _as(lo, _lp), _as(hi, _lp), lo.shape[0]))
+        self.n_shells = int(lo.shape[0])
+
+    def read_shells(self, denom: float, out: Optional[np.ndarray] = None):
+        """Shell means of ``sums / denom``, ``(n_pairs, n_shells)``, and the number of frames accumulated."""
+        if out is None:
+            out = np.empty((self.n_pairs, self.n_shells), dtype=np.float64)
+        elif out.dtype != np.float64 or not out.flags.c_contiguous or out.size != self.n_pairs * self.n_shells:
+            raise ValueError("out must be a C-contiguous float64 array with n_pairs x n_shells elements")
+        nf = c_int64()
+        _check(lib().mdc_sq_read_shells(self._h, float(denom), _as(out, _dp), byref(nf)))
         return out, nf.value
 
     def reset(self) -> None:

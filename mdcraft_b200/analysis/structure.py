@@ -549,18 +549,15 @@ class RadialDistributionFunction(_DeviceBlockRun, DynamicAnalysisBase):
 # ----------------------------------------------------------------------------
 
 
-def combine_equal_wavenumbers(ssf: np.ndarray, wavenumbers: np.ndarray, unique_q: np.ndarray) -> np.ndarray:
+def shell_windows(wavenumbers: np.ndarray, unique_q: np.ndarray):
     """
-    ``structure.py:2000-2009``: for every unique wavenumber ``q`` the mean of the
-    columns selected by ``np.isclose(q, wavenumbers)``.  The reference evaluates
-    that mask once per unique ``q`` (O(N_unique x Nq)); here the wavenumbers are
-    sorted once and each mask becomes a contiguous window found by bisection,
-    then checked against ``np.isclose`` itself at its borders so that membership
-    is identical.
+    The masks ``np.isclose(q, wavenumbers)`` of ``structure.py:2000-2009`` for every unique ``q``, as windows
+    ``order[lo[i]:hi[i]]`` of the wavevector indices sorted by ``|q|``.  The reference evaluates the mask once per
+    unique ``q`` (O(N_unique x Nq)); here the wavenumbers are sorted once and each mask becomes a contiguous window
+    found by bisection, then checked against ``np.isclose`` itself at its borders so that membership is identical.
     """
     order = np.argsort(wavenumbers, kind="stable")
     w = wavenumbers[order]
-    cols = ssf[:, order]
     rtol, atol = 1e-5, 1e-8
     # |q - w| <= atol + rtol * |w|   <=>   (q - atol) / (1 + rtol) <= w <= (q + atol) / (1 - rtol)  (w >= 0)
     lo = np.searchsorted(w, (unique_q - atol) / (1 + rtol), side="left")
@@ -582,6 +579,14 @@ def combine_equal_wavenumbers(ssf: np.ndarray, wavenumbers: np.ndarray, unique_q
             break
         lo = lo - grow_lo + (shrink_lo & ~grow_lo)
         hi = hi + grow_hi - (shrink_hi & ~grow_hi)
+    return order, lo, hi
+
+
+def combine_equal_wavenumbers(ssf: np.ndarray, wavenumbers: np.ndarray, unique_q: np.ndarray) -> np.ndarray:
+    """``structure.py:2000-2009`` on the host: for every unique wavenumber ``q`` the mean of the columns selected by
+    ``np.isclose(q, wavenumbers)`` (see :func:`shell_windows`)."""
+    order, lo, hi = shell_windows(wavenumbers, unique_q)
+    cols = ssf[:, order]
     out = np.empty((ssf.shape[0], unique_q.shape[0]))
     for i in range(unique_q.shape[0]):
         out[:, i] = cols[:, lo[i] : hi[i]].mean(axis=1)
@@ -746,6 +751,7 @@ class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
         # the grid is built on the device; the host only needs it for |q| bookkeeping
         self._wavevectors = self._plan.wavevectors()
         self._wavenumbers = np.linalg.norm(self._wavevectors, axis=1)
+        self._shells = None
 
     # -- AnalysisBase protocol ------------------------------------------------
     def _prepare(self) -> None:
@@ -798,12 +804,18 @@ class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
             n_frames = int(round(dist.all_reduce_sum(np.array([float(self._frames_seen)]), device=self._device)[0]))
             dist.all_reduce_device(self._plan.accumulator(), device=self._device)
             self.n_frames_total = n_frames
-        ssf, _ = self._plan.read()
-
         # structure.py:1995-2014
-        ssf /= n_frames * self._N
-        if self._unique:
-            ssf = combine_equal_wavenumbers(ssf, self._wavenumbers, self.results.wavenumbers)
+        if self._unique and type(self) is StructureFactor:
+            # the |q|-shell means are formed on the device (sq_shell_mean): N_unique values per pair cross the bus
+            if self._shells is None:
+                self._shells = shell_windows(self._wavenumbers, self.results.wavenumbers)
+                self._plan.set_shells(*self._shells)
+            ssf, _ = self._plan.read_shells(float(n_frames * self._N))
+        else:
+            ssf, _ = self._plan.read()
+            ssf /= n_frames * self._N
+            if self._unique:
+                ssf = combine_equal_wavenumbers(ssf, self._wavenumbers, self.results.wavenumbers)
         self.results.ssf = ssf
         if self._sort:
             order = np.argsort(self.results.wavenumbers)

@@ -586,6 +586,25 @@ __global__ void sq_pair_accum(double2 *__restrict__ part, int F, int n_sets, int
     if (sum_pairs) ssf[q] += total;
 }
 
+// |q|-shell averages (structure.py:2000-2009): out[row, s] = mean over the wavevectors m of shell s of ssf[row, m] / denom.
+// The members of a shell are a window [lo, hi) of `order` (wavevector indices sorted by |q|); windows may overlap,
+// as np.isclose's do.  One warp per (row, shell), lane-strided partial sums folded in a fixed order: deterministic.
+__global__ void sq_shell_mean(const double *__restrict__ ssf, int64_t nq, const int64_t *__restrict__ order,
+                              const int64_t *__restrict__ lo, const int64_t *__restrict__ hi, int64_t n_shells,
+                              int n_rows, double denom, double *__restrict__ out)
+{
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_shells * n_rows) return;
+    const int64_t row = warp / n_shells, s = warp - row * n_shells;
+    const int64_t a = lo[s], b = hi[s];
+    double sum = 0.0;
+    for (int64_t m = a + lane; m < b; m += 32) sum += ssf[row * nq + order[m]] / denom;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if (lane == 0) out[row * n_shells + s] = sum / (double)(b - a);   // empty shell: 0 / 0 = NaN, as np.mean([])
+}
+
 // ------------------------------------------------------------------------------------------
 // intermediate scattering function (structure.py:2198-2835): a ring of the last n_lags densities and,
 // for the self part, of the last n_lags position sets
@@ -798,6 +817,9 @@ struct mdc_sq_plan {
     bool sum_pairs = false;                    // all pairs accumulate into row 0 (single-chain structure factor)
     int n_rows = 0;                            // rows of ssf: n_pairs, or 1
     DevBuf<double2> part;
+    DevBuf<int64_t> shell_order, shell_lo, shell_hi;   // |q|-shell windows (mdc_sq_set_shells)
+    DevBuf<double> shell_out;
+    int64_t n_shells = 0;
     DevBuf<float> raw[2];
     DevBuf<uint32_t> fix[2];
     DevBuf<int2> d_sets, d_pairs;
@@ -832,6 +854,10 @@ void plan_free(mdc_sq_plan *p)
     p->cisf.release();
     p->iisf.release();
     p->inc_slot.release();
+    p->shell_order.release();
+    p->shell_lo.release();
+    p->shell_hi.release();
+    p->shell_out.release();
     p->nufft.release();
     p->row_cnt.release();
     p->row_qoff.release();
@@ -1403,6 +1429,44 @@ extern "C" int mdc_sq_read(mdc_sq_plan *p, double *ssf_out, int64_t *n_frames_ou
     MDC_CUDA(cudaStreamSynchronize(p->st.compute));
     if (ssf_out)
         MDC_CUDA(cudaMemcpy(ssf_out, p->ssf.p, (size_t)p->nq * p->n_rows * sizeof(double), cudaMemcpyDeviceToHost));
+    if (n_frames_out) *n_frames_out = p->n_frames;
+    return MDC_OK;
+}
+
+extern "C" int mdc_sq_set_shells(mdc_sq_plan *p, const int64_t *order, int64_t n_order, const int64_t *lo,
+                                 const int64_t *hi, int64_t n_shells)
+{
+    if (!p || !order || !lo || !hi || n_order <= 0 || n_shells <= 0)
+        return fail(MDC_ERR_INVALID, "mdc_sq_set_shells: bad argument");
+    for (int64_t i = 0; i < n_order; ++i)
+        if (order[i] < 0 || order[i] >= p->nq) return fail(MDC_ERR_INVALID, "mdc_sq_set_shells: wavevector index out of range");
+    for (int64_t s = 0; s < n_shells; ++s)
+        if (lo[s] < 0 || hi[s] < lo[s] || hi[s] > n_order) return fail(MDC_ERR_INVALID, "mdc_sq_set_shells: bad shell window");
+    MDC_CUDA(cudaSetDevice(p->ctx->device));
+    MDC_CHECK(p->shell_order.alloc((size_t)n_order));
+    MDC_CHECK(p->shell_lo.alloc((size_t)n_shells));
+    MDC_CHECK(p->shell_hi.alloc((size_t)n_shells));
+    MDC_CHECK(p->shell_out.alloc((size_t)n_shells * p->n_rows));
+    MDC_CUDA(cudaMemcpy(p->shell_order.p, order, n_order * sizeof(int64_t), cudaMemcpyHostToDevice));
+    MDC_CUDA(cudaMemcpy(p->shell_lo.p, lo, n_shells * sizeof(int64_t), cudaMemcpyHostToDevice));
+    MDC_CUDA(cudaMemcpy(p->shell_hi.p, hi, n_shells * sizeof(int64_t), cudaMemcpyHostToDevice));
+    p->n_shells = n_shells;
+    return MDC_OK;
+}
+
+extern "C" int mdc_sq_read_shells(mdc_sq_plan *p, double denom, double *out, int64_t *n_frames_out)
+{
+    if (!p || !out) return fail(MDC_ERR_INVALID, "mdc_sq_read_shells: NULL argument");
+    if (p->n_shells <= 0) return fail(MDC_ERR_INVALID, "mdc_sq_read_shells: call mdc_sq_set_shells first");
+    MDC_CUDA(cudaSetDevice(p->ctx->device));
+    cudaStream_t sk = p->st.compute;
+    const int64_t warps = p->n_shells * p->n_rows;
+    sq_shell_mean<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, sk>>>(p->ssf.p, p->nq, p->shell_order.p, p->shell_lo.p,
+                                                                      p->shell_hi.p, p->n_shells, p->n_rows, denom,
+                                                                      p->shell_out.p);
+    MDC_CUDA(cudaGetLastError());
+    MDC_CUDA(cudaMemcpyAsync(out, p->shell_out.p, (size_t)warps * sizeof(double), cudaMemcpyDeviceToHost, sk));
+    MDC_CUDA(cudaStreamSynchronize(sk));
     if (n_frames_out) *n_frames_out = p->n_frames;
     return MDC_OK;
 }

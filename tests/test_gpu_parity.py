@@ -438,6 +438,32 @@ def test_sq_large_n_accuracy_vs_oracle(algorithm):
         assert np.max(np.abs(s[m] / s0[m] - 1)) < 1e-6
 
 
+def test_sq_shell_means_on_device(ctx):
+    """StructureFactor._conclude's |q|-shell averaging (structure.py:2000-2009) on the device against the host
+    restatement of the reference loop: same windows (np.isclose membership, overlapping), means to rounding."""
+    from mdcraft_b200 import _capi
+    from mdcraft_b200.analysis.structure import combine_equal_wavenumbers, shell_windows
+
+    rng = np.random.default_rng(17)
+    n, L = 1500, 12.5
+    pos = (rng.random((3, n, 3)) * L).astype(np.float32)
+    plan = _capi.SqPlan(ctx, [600, 900], [(0, 0), (0, 1), (1, 1)], n_points=20, L0=[L, L * 1.02, L], q_max=9.0)
+    plan.push(pos)
+    sums, nf = plan.read()
+    wn = np.linalg.norm(plan.wavevectors(), axis=1)
+    uq = np.unique(wn.round(11))
+    order, lo, hi = shell_windows(wn, uq)
+    assert (hi - lo).max() > 1 and (lo[1:] < hi[:-1]).any()          # real shells, and overlapping windows
+    plan.set_shells(order, lo, hi)
+    got, nf2 = plan.read_shells(float(nf * n))
+    assert nf2 == nf == 3
+    want = combine_equal_wavenumbers(sums / (nf * n), wn, uq)
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-15)
+    again, _ = plan.read_shells(float(nf * n))
+    np.testing.assert_array_equal(got, again)                          # fixed reduction order
+    plan.close()
+
+
 # --------------------------------------------------------------------------- F(q, t) class (SURVEY.md §8f rank 1)
 
 
