@@ -43,9 +43,10 @@ N_PART = 100_000
 GR = dict(rho=2.5, n_bins=200, seed0=2000)
 SQ = dict(rho=0.8, n_points=161, q_max=20.0, seed0=3000)
 METRIC = "frames/sec for S(q) and g(r) at 1e5 particles"
-#: dram__bytes_read.sum + dram__bytes_write.sum of the NUFFT kernels per frame, one `ncu --set full` capture
-#: (profiles/sq_nufft_r01.txt)
-NUFFT_DRAM_BYTES_PER_FRAME = None
+#: dram__bytes_read.sum + dram__bytes_write.sum of the four NUFFT kernels (spread, z / y / x FFT passes) per frame from
+#: one `ncu --set full` capture (profiles/sq_nufft_r01.txt: 2,706 MB per 2-frame launch); clearing the fine grid adds
+#: 0.27e9 that ncu does not attribute to a kernel
+NUFFT_DRAM_BYTES_PER_FRAME = 1.353e9
 UNIT = "frames/s"
 
 
@@ -415,7 +416,7 @@ def run_native(args, rank, world, emit=print):
         line["roofline_gr"] = {
             "bound": "issue", "kernel": "rdf_pairs_fast", "achieved": pairs / (gr_ms * 1e-3) / 1e9,
             "peak": gr_peak / 1e9, "unit": "G pair-distances/s", "frac": pairs / (gr_ms * 1e-3) / gr_peak,
-            "traffic": 3.1e6, "peak_source": f"{sm} SMs x 4 schedulers x 32 lanes x SM clock / 19.9 issue slots per pair",
+            "traffic": 4.9e6, "peak_source": f"{sm} SMs x 4 schedulers x 32 lanes x SM clock / 19.9 issue slots per pair",
             "algorithmic": "19.9 issue slots (FP32 arithmetic of two pairs per packed f32x2 instruction) + 1 SFU op (sqrt) + "
                            "0.52 shared-memory atomics per pair; "
                            "24 B of positions per particle per frame (f32 + u32 fixed point)",

@@ -39,6 +39,16 @@ def test_no_cpu_fallback():
         structure.RadialDistributionFunction(u.atoms, n_bins=10, range_=(0.0, 3.0), verbose=False).run()
     with pytest.raises(_capi.MdcError):
         structure.StructureFactor(u.atoms, n_points=4, verbose=False)
+    # the widened rows too: transforms on a device, density profiles, the readers
+    with pytest.raises(_capi.MdcError):
+        structure.radial_fourier_transform(np.linspace(0.1, 1, 5), np.ones(5), np.ones(3), device=0)
+    from mdcraft_b200.analysis.profile import DensityProfile
+    from mdcraft_b200.analysis.reader import LAMMPSDumpTrajectoryReader
+
+    with pytest.raises(_capi.MdcError):
+        DensityProfile(u.atoms, n_bins=8, verbose=False).run()
+    with pytest.raises(_capi.MdcError):
+        LAMMPSDumpTrajectoryReader(os.path.join(os.path.dirname(__file__), "golden", "dump_ids.lammpsdump"))
     # nothing under mdcraft_b200/ may import the oracle
     root = os.path.dirname(os.path.abspath(build.__file__))
     for dirpath, _, files in os.walk(root):
