@@ -1009,7 +1009,7 @@ static int sq_plan_create_impl(mdc_ctx *ctx, int n_points, const double L0[3], d
         if (algo == MDC_SQ_ALGO_NUFFT) {
             p->nufft_on = true;
         } else if (algo == MDC_SQ_ALGO_AUTO) {
-            // cost model (rates measured on B200, DESIGN.md §3.7): the O(Nq N) kernel of this precision (factored
+            // cost model (rates measured on B200, DESIGN.md §3.6): the O(Nq N) kernel of this precision (factored
             // FP32: 4.4e12 terms/s; FP64 reference arithmetic: 3.4e11 terms/s) vs fine-grid traffic + spreading
             const bool f64 = precision == MDC_PRECISION_FP64;
             NufftGeom ng;

@@ -516,7 +516,7 @@ bool Nufft::geometry(int n_points, double eps, NufftGeom *out)
     return true;
 }
 
-// seconds per frame for n_sets sets holding sum_len particles in total (rates measured on B200, DESIGN.md §3.7)
+// seconds per frame for n_sets sets holding sum_len particles in total (rates measured on B200, DESIGN.md §3.6)
 double Nufft::cost(const NufftGeom &g, int n_sets, int64_t sum_len)
 {
     const double nf = g.nf, n = g.n;
