@@ -286,11 +286,16 @@ class Context:
 _contexts: dict = {}
 
 
-def context(device: int = 0) -> Context:
-    """One library context per CUDA device per process (shared by the analysis classes and the readers)."""
-    ctx = _contexts.get(device)
+def context(device: int = 0, lane: int = 0) -> Context:
+    """
+    One library context per CUDA device and LANE per process.  A context owns the streams its plans run on, so plans
+    of different lanes execute concurrently on the device: the analysis classes put g(r) on lane 0 and the S(q)
+    family on lane 1 (the g(r) pair kernel is issue bound, the NUFFT L2 / shared-memory bound: run side by side they
+    hide most of the S(q) time).  Readers and the one-shot seams use lane 0.
+    """
+    ctx = _contexts.get((device, lane))
     if ctx is None:
-        ctx = _contexts[device] = Context(device)
+        ctx = _contexts[(device, lane)] = Context(device)
     return ctx
 
 

@@ -157,3 +157,30 @@ class DynamicAnalysisBase(SerialAnalysisBase):
         for k in self._FARM_KWARGS:
             kwargs.pop(k, None)
         return super().run(start, stop, step, frames, verbose, **kwargs)
+
+
+def run_together(analyses, start=None, stop=None, step=None, frames=None):
+    """
+    Runs several analyses of the SAME trajectory in one pass over its frames: every frame is read once and handed to
+    each analysis' ``_single_frame`` in turn, exactly as their own ``run(start, stop, step, frames)`` would have done
+    (same ``frames`` / ``times`` bookkeeping, same results).  Because the analysis families queue their kernels on
+    different stream lanes (``_capi.context``), g(r) and S(q) of the same frame block execute side by side on the GPU.
+    Returns the analyses.
+    """
+    analyses = list(analyses)
+    if not analyses:
+        return analyses
+    trajectory = analyses[0]._trajectory
+    for a in analyses:
+        if a._trajectory is not trajectory:
+            raise ValueError("run_together needs analyses of one and the same trajectory.")
+        a._setup_frames(trajectory, start=start, stop=stop, step=step, frames=frames)
+        a._prepare()
+    for i, ts in enumerate(analyses[0]._sliced_trajectory):
+        for a in analyses:
+            a._frame_index, a._ts = i, ts
+            a.frames[i], a.times[i] = ts.frame, ts.time
+            a._single_frame()
+    for a in analyses:
+        a._conclude()
+    return analyses

@@ -18,7 +18,7 @@ import numpy as np
 from .. import _capi
 from ..algorithm import center_of_mass, get_closest_factors, strip_unit
 from .base import Hash, NumbaAnalysisBase
-from .structure import _ANGSTROM, _FrameBlock, _context, _ureg, combine_equal_wavenumbers
+from .structure import LANE_SQ, _ANGSTROM, _FrameBlock, _context, _ureg, combine_equal_wavenumbers
 
 
 class SingleChainStructureFactor(NumbaAnalysisBase):
@@ -159,7 +159,7 @@ class SingleChainStructureFactor(NumbaAnalysisBase):
         explicit = self._explicit if self._explicit is not None and len(self._explicit) else None
         for M, N in zip(self._n_chains, self._n_monomers):
             self._plans.append(_capi.ScsfPlan(
-                _context(self._device), int(M), int(N), n_points=n_points_, L0=L0_, q_max=self._q_max,
+                _context(self._device, LANE_SQ), int(M), int(N), n_points=n_points_, L0=L0_, q_max=self._q_max,
                 wavevectors=explicit, precision=precision, algo=algorithm,
             ))
         self._wavevectors = self._plans[0].wavevectors()

@@ -35,7 +35,7 @@ import numpy as np
 from .. import _capi
 from ..algorithm import center_of_mass, strip_unit
 from .base import DynamicAnalysisBase, Hash
-from .structure import _ANGSTROM, _FrameBlock, _context, _ureg, histogram_bin_edges
+from .structure import LANE_PROFILE, _ANGSTROM, _FrameBlock, _context, _ureg, histogram_bin_edges
 
 __all__ = ["DensityProfile", "calculate_surface_charge_density", "calculate_potential_profile"]
 
@@ -316,7 +316,7 @@ class DensityProfile(DynamicAnalysisBase):
             self.results.bins[ax] = (self.results.bin_edges[ax][:-1] + self.results.bin_edges[ax][1:]) / 2
         if self._plan is not None:
             self._plan.close()
-        self._plan = _capi.ProfilePlan(_context(self._device), self._Ns, self._axis_indices,
+        self._plan = _capi.ProfilePlan(_context(self._device, LANE_PROFILE), self._Ns, self._axis_indices,
                                        [int(n) for n in self._n_bins], np.asarray(self._dimensions, dtype=np.float64))
         self._stage = _FrameBlock(self._frame_block, self._N)
         if self._recenter is not None:

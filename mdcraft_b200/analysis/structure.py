@@ -67,9 +67,13 @@ except ImportError:  # plain strings keep ``results.units`` meaningful without p
 #: N_A * k_B in kJ / (mol K) (exact, 2019 SI)
 _GAS_CONSTANT_KJ = 0.00831446261815324
 
-def _context(device: int = 0) -> _capi.Context:
-    """One library context per CUDA device per process."""
-    return _capi.context(device)
+#: stream lanes of the analysis families (see ``_capi.context``)
+LANE_RDF, LANE_SQ, LANE_PROFILE = 0, 1, 2
+
+
+def _context(device: int = 0, lane: int = 0) -> _capi.Context:
+    """One library context per CUDA device and lane per process."""
+    return _capi.context(device, lane)
 
 
 # ----------------------------------------------------------------------------
@@ -745,7 +749,7 @@ class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
         n_points, L0 = self._lattice if self._lattice is not None else (0, None)
         explicit = self._explicit if self._explicit is not None and len(self._explicit) else None
         self._plan = _capi.SqPlan(
-            _context(self._device), self._Ns, self._pairs(), n_points=n_points, L0=L0, q_max=self._q_max,
+            _context(self._device, LANE_SQ), self._Ns, self._pairs(), n_points=n_points, L0=L0, q_max=self._q_max,
             wavevectors=explicit, precision=self._precision, algo=self._algorithm,
         )
         # the grid is built on the device; the host only needs it for |q| bookkeeping
@@ -895,7 +899,7 @@ class IntermediateScatteringFunction(StructureFactor):
         n_points, L0 = self._lattice if self._lattice is not None else (0, None)
         explicit = self._explicit if self._explicit is not None and len(self._explicit) else None
         self._plan = _capi.IsfPlan(
-            _context(self._device), self._Ns, self.results.pairs, self._n_lags, incoherent=self._incoherent,
+            _context(self._device, LANE_SQ), self._Ns, self.results.pairs, self._n_lags, incoherent=self._incoherent,
             n_points=n_points, L0=L0, q_max=self._q_max, wavevectors=explicit, precision=self._precision,
             algo=self._algorithm,
         )

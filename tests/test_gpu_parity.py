@@ -464,6 +464,35 @@ def test_sq_shell_means_on_device(ctx):
     plan.close()
 
 
+def test_run_together_equals_separate_runs():
+    """One pass over the trajectory feeding g(r), S(q) and a density profile (their kernels on different stream
+    lanes, side by side on the device): results and bookkeeping equal those of three separate run() calls."""
+    from mdcraft_b200.analysis.base import run_together
+    from mdcraft_b200.analysis.profile import DensityProfile
+    from mdcraft_b200.analysis.structure import RadialDistributionFunction, StructureFactor
+
+    g = golden("sq_total_c1.npz")
+    u = universe_from(g["pos"], g["dims"])
+    L = float(g["dims"][0])
+
+    def make():
+        return (RadialDistributionFunction(u.atoms, n_bins=50, range_=(0.0, L / 2), exclusion=(1, 1), verbose=False,
+                                           frame_block=2),
+                StructureFactor(u.atoms, n_points=10, verbose=False, frame_block=3),
+                DensityProfile(u.atoms, axes="z", n_bins=25, verbose=False, frame_block=2))
+
+    sep = [a.run(start=1, step=2) for a in make()]
+    tog = run_together(make(), start=1, step=2)
+    np.testing.assert_array_equal(tog[0].results.counts, sep[0].results.counts)
+    np.testing.assert_array_equal(tog[0].results.rdf, sep[0].results.rdf)
+    np.testing.assert_array_equal(tog[1].results.ssf, sep[1].results.ssf)
+    np.testing.assert_array_equal(tog[2].results.number_densities["z"], sep[2].results.number_densities["z"])
+    for a, b in zip(tog, sep):
+        np.testing.assert_array_equal(a.frames, b.frames)
+        np.testing.assert_array_equal(a.times, b.times)
+        assert a.n_frames == b.n_frames
+
+
 # --------------------------------------------------------------------------- F(q, t) class (SURVEY.md §8f rank 1)
 
 
