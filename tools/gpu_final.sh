@@ -7,7 +7,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; 
 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference arm exit $?"
 python tools/extra_bench.py > gpurun_out/extra.log 2>&1; echo "extra exit $?"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_bench.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-extras > gpurun_out/ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"rdf_pairs_fast" -c 1 -f -o gpurun_out/rdf_full python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_rdf.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"nufft_spread|nufft_fft" -c 4 -f -o gpurun_out/nufft_full python tools/nufft_check.py 100000 161 20 > gpurun_out/ncu_nufft.log 2>&1
 python - <<'PY'
