@@ -73,6 +73,12 @@ const char  *mdc_last_error(void);
 
 /* Binds a context to CUDA device `device` (creates nothing on other devices). */
 int  mdc_create(int device, mdc_ctx **out);
+/*
+ * The same with a stream priority: plans of a high-priority context get their thread blocks placed first whenever
+ * blocks of another context's kernels retire.  Meant for the short, memory-bound S(q) kernels running next to the
+ * long, issue-bound g(r) pair kernel of another context on the same device.
+ */
+int  mdc_create_with_priority(int device, int high_priority, mdc_ctx **out);
 int  mdc_destroy(mdc_ctx *ctx);
 int  mdc_device_info(mdc_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                      int *sm_clock_khz, int64_t *global_mem_bytes);
@@ -225,6 +231,12 @@ int  mdc_rdf_push(mdc_rdf_plan *plan, const float *pos_a, const float *pos_b,
                   const float *box, int n_frames, int on_device);
 
 int  mdc_rdf_read(mdc_rdf_plan *plan, int64_t *counts_out, int64_t *n_frames_out);
+/*
+ * The pair kernel is a persistent grid that fills every SM (4 blocks per SM at 200 bins).  blocks_per_sm > 0 caps it,
+ * leaving register file / shared memory on every SM for the kernels of ANOTHER context queued at the same time (the
+ * S(q) NUFFT kernels are sized to fit one such slot): the two analyses then run side by side.  0 = all that fit.
+ */
+int  mdc_rdf_set_blocks_per_sm(mdc_rdf_plan *plan, int blocks_per_sm);
 int  mdc_rdf_reset(mdc_rdf_plan *plan);
 int  mdc_rdf_accum_ptr(mdc_rdf_plan *plan, void **dev_ptr, int64_t *n_elems);
 

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mdc_version": (c_int, []),
     "mdc_last_error": (c_char_p, []),
     "mdc_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "mdc_create_with_priority": (c_int, [c_int, c_int, POINTER(c_void_p)]),
     "mdc_destroy": (c_int, [c_void_p]),
     "mdc_device_info": (c_int, [c_void_p, _ip, _ip, _ip, _ip, _lp]),
     "mdc_synchronize": (c_int, [c_void_p]),
@@ -97,6 +98,7 @@ SIGNATURES = {
     "mdc_rdf_plan_destroy": (c_int, [c_void_p]),
     "mdc_rdf_push": (c_int, [c_void_p, c_void_p, c_void_p, _fp, c_int, c_int]),
     "mdc_rdf_read": (c_int, [c_void_p, _lp, _lp]),
+    "mdc_rdf_set_blocks_per_sm": (c_int, [c_void_p, c_int]),
     "mdc_rdf_reset": (c_int, [c_void_p]),
     "mdc_rdf_accum_ptr": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
     "mdc_radial_histogram": (
@@ -195,10 +197,10 @@ def _buffer(x, dtype=np.float32):
 class Context:
     """One CUDA device (``mdc_create``)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, high_priority: bool = False):
         self._h = c_void_p()
         self.device = int(device)
-        _check(lib().mdc_create(self.device, byref(self._h)))
+        _check(lib().mdc_create_with_priority(self.device, int(bool(high_priority)), byref(self._h)))
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -295,7 +297,7 @@ def context(device: int = 0, lane: int = 0) -> Context:
     """
     ctx = _contexts.get((device, lane))
     if ctx is None:
-        ctx = _contexts[(device, lane)] = Context(device)
+        ctx = _contexts[(device, lane)] = Context(device, high_priority=lane != 0)
     return ctx
 
 
@@ -728,6 +730,11 @@ class RdfPlan:
         nf = c_int64()
         _check(lib().mdc_rdf_read(self._h, _as(out, _lp), byref(nf)))
         return out, nf.value
+
+    def set_blocks_per_sm(self, blocks_per_sm: int) -> None:
+        """Caps the persistent pair kernel at ``blocks_per_sm`` blocks per SM (0 = all that fit), leaving room on every
+        SM for the kernels of another context: see ``mdc_rdf_set_blocks_per_sm``."""
+        _check(lib().mdc_rdf_set_blocks_per_sm(self._h, int(blocks_per_sm)))
 
     def reset(self) -> None:
         _check(lib().mdc_rdf_reset(self._h))

@@ -176,6 +176,11 @@ def run_together(analyses, start=None, stop=None, step=None, frames=None):
             raise ValueError("run_together needs analyses of one and the same trajectory.")
         a._setup_frames(trajectory, start=start, stop=stop, step=step, frames=frames)
         a._prepare()
+    # g(r) next to analyses on other stream lanes: its persistent pair kernel leaves a quarter of every SM free
+    pair_plans = [a._plan for a in analyses if hasattr(getattr(a, "_plan", None), "set_blocks_per_sm")]
+    if pair_plans and len(pair_plans) < len(analyses):
+        for plan in pair_plans:
+            plan.set_blocks_per_sm(3)
     for i, ts in enumerate(analyses[0]._sliced_trajectory):
         for a in analyses:
             a._frame_index, a._ts = i, ts

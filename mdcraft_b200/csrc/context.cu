@@ -28,7 +28,16 @@ extern "C" int mdc_version(void) { return 100; }
 
 extern "C" const char *mdc_last_error(void) { return g_last_error.c_str(); }
 
-extern "C" int mdc_create(int device, mdc_ctx **out)
+static int create_impl(int device, int high_priority, mdc_ctx **out);
+
+extern "C" int mdc_create(int device, mdc_ctx **out) { return create_impl(device, 0, out); }
+
+extern "C" int mdc_create_with_priority(int device, int high_priority, mdc_ctx **out)
+{
+    return create_impl(device, high_priority, out);
+}
+
+static int create_impl(int device, int high_priority, mdc_ctx **out)
 {
     if (!out) return fail(MDC_ERR_INVALID, "mdc_create: out is NULL");
     *out = nullptr;
@@ -53,8 +62,12 @@ extern "C" int mdc_create(int device, mdc_ctx **out)
     c->clock_khz = khz;
     c->global_mem = (int64_t)prop.totalGlobalMem;
     c->smem_optin = prop.sharedMemPerBlockOptin;
-    cudaError_t e2 = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
-    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking);
+    // high priority: when thread blocks of another context's kernels retire, this context's blocks are placed first
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // numerically lower = higher priority
+    const int prio = high_priority ? prio_hi : prio_lo;
+    cudaError_t e2 = cudaStreamCreateWithPriority(&c->copy, cudaStreamNonBlocking, prio);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithPriority(&c->compute, cudaStreamNonBlocking, prio);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->mark[0]);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->mark[1]);
     if (e2 != cudaSuccess) {

@@ -193,6 +193,7 @@ struct RdfArgs {
     int F, nti, ntj;           // tiles
     int sym;                   // 1: self-RDF over unordered pairs (each counted twice)
     int64_t items_per_frame;
+    unsigned long long *ticket;   // next tile pair to hand out (filter kernel: blocks draw work items dynamically)
 };
 
 __device__ __forceinline__ double min_image_sq(float dxf, double inv, double box, int pbc)
@@ -809,10 +810,27 @@ rdf_pairs_fast(RdfArgs A)
     const int64_t total = A.items_per_frame * A.F;
     int since_flush = 0;
 
+#ifndef MDC_RF_DYNAMIC
+#define MDC_RF_DYNAMIC 1   // 1: tile pairs are drawn from a global ticket counter, so no block idles while another
+#endif                     //    still has a whole tile pair queued (static striding leaves up to one item of tail)
+#if MDC_RF_DYNAMIC
+    __shared__ unsigned long long s_ticket;
+    for (;;) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(A.ticket, 1ull);
+        __syncthreads();
+        const int64_t item = (int64_t)s_ticket;
+        if (item >= total) break;
+#else
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+#endif
         int f, I, J;
         bool diag;
-        if (!decode_item(A, item, f, I, J, diag)) continue;
+        if (!decode_item(A, item, f, I, J, diag)) {
+#if MDC_RF_DYNAMIC
+            __syncthreads();   // every thread has read the ticket before thread 0 draws the next one
+#endif
+            continue;
+        }
         const FrameFast ff = A.fast[f];
         const FrameBox fb = A.boxes[f];
         const uint32_t *ax = A.ua + ((int64_t)f * 3) * A.na, *ay = ax + A.na, *az = ay + A.na;
@@ -912,9 +930,10 @@ struct mdc_rdf_plan {
     int self_bin = -1;          // bin receiving the i == j pairs of a symmetric self-RDF (-1: none)
     int force_exact = 0;        // testing / diagnostics: MDC_RDF_EXACT=1 in the environment
     int occ_fast = 1, occ_exact = 1;   // resident blocks per SM (persistent grids)
+    int blocks_per_sm = 0;             // > 0: the filter kernel launches at most this many blocks per SM
     Thresholds th;
     DevBuf<double> T;
-    DevBuf<unsigned long long> counts;
+    DevBuf<unsigned long long> counts, ticket;
     DevBuf<float> raw_a[2], raw_b[2], soa_a[2], soa_b[2];
     DevBuf<uint32_t> fix_a[2], fix_b[2];
     DevBuf<unsigned> absmax[2];        // (2, F): group a, group b
@@ -936,6 +955,7 @@ void rdf_free(mdc_rdf_plan *p)
     cudaDeviceSynchronize();
     p->T.release();
     p->counts.release();
+    p->ticket.release();
     for (int i = 0; i < 2; ++i) {
         p->raw_a[i].release();
         p->raw_b[i].release();
@@ -1048,6 +1068,7 @@ extern "C" int mdc_rdf_plan_create(mdc_ctx *ctx, int n_bins, double r0, double r
     int rc = p->st.init(ctx);
     if (rc == MDC_OK) rc = p->T.alloc(n_bins + 1);
     if (rc == MDC_OK) rc = p->counts.alloc(n_bins);
+    if (rc == MDC_OK) rc = p->ticket.alloc(1);
     if (rc != MDC_OK) {
         rdf_free(p);
         return rc;
@@ -1144,6 +1165,7 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         A.fast = p->fast[slot].p;
         A.T = p->T.p;
         A.counts = p->counts.p;
+        A.ticket = p->ticket.p;
         A.e_lo = p->th.e_lo;
         A.e_hi = p->th.e_hi;
         A.r0f = (float)p->r0;
@@ -1163,7 +1185,11 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         const int ti = p->st.n_timed < 8 ? p->st.n_timed : -1;
         if (ti >= 0) MDC_CUDA(cudaEventRecord(p->st.k0[ti], sk));
         if (fast) {
-            const int grid = (int)std::min<int64_t>(total, (int64_t)p->ctx->sm_count * p->occ_fast);
+            // persistent grid: as many blocks as fit, or fewer per SM when the caller wants room left on every SM for
+            // the kernels of another stream (mdc_rdf_set_blocks_per_sm)
+            const int bps = p->blocks_per_sm > 0 ? std::min(p->blocks_per_sm, p->occ_fast) : p->occ_fast;
+            const int grid = (int)std::min<int64_t>(total, (int64_t)p->ctx->sm_count * bps);
+            MDC_CUDA(cudaMemsetAsync(p->ticket.p, 0, sizeof(unsigned long long), sk));
             rdf_pairs_fast<<<grid, RF_THREADS, p->smem_fast, sk>>>(A);
         } else {
             const int grid = (int)std::min<int64_t>(total, (int64_t)p->ctx->sm_count * p->occ_exact);
@@ -1196,6 +1222,13 @@ extern "C" int mdc_rdf_read(mdc_rdf_plan *p, int64_t *counts_out, int64_t *n_fra
     if (counts_out)
         MDC_CUDA(cudaMemcpy(counts_out, p->counts.p, p->n_bins * sizeof(int64_t), cudaMemcpyDeviceToHost));
     if (n_frames_out) *n_frames_out = p->n_frames;
+    return MDC_OK;
+}
+
+extern "C" int mdc_rdf_set_blocks_per_sm(mdc_rdf_plan *p, int blocks_per_sm)
+{
+    if (!p || blocks_per_sm < 0) return fail(MDC_ERR_INVALID, "mdc_rdf_set_blocks_per_sm: bad argument");
+    p->blocks_per_sm = blocks_per_sm;
     return MDC_OK;
 }
 

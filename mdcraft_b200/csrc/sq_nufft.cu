@@ -32,7 +32,13 @@ namespace mdc {
 namespace {
 
 constexpr int NU_TC = 8;         // lines per block in the strided FFT passes (8 x 16 B = one 128-byte segment)
-constexpr int NU_THREADS = 256;  // 8 warps: one line per warp
+#ifndef MDC_NU_THREADS
+#define MDC_NU_THREADS 128
+#endif
+// Threads per block of the spreading and FFT kernels (one line per warp and turn).  128 threads x <= 128 registers
+// fit the quarter of an SM that the g(r) pair kernel leaves free when it runs next to these kernels on another
+// stream (mdc_rdf_set_blocks_per_sm); alone, 256 threads are 3 % faster.
+constexpr int NU_THREADS = MDC_NU_THREADS;
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 {
@@ -421,7 +427,7 @@ nufft_fft_s(const double2 *__restrict__ in, double2 *__restrict__ out, const dou
         tile[ii * pitch + padded(l)] = gi < S ? src[(size_t)l * S + gi] : make_double2(0.0, 0.0);
     }
     __syncthreads();
-    fft_line<MDC_FFT_POW_S != 0>(tile + warp * pitch, tw, g, lane);
+    for (int ln = warp; ln < NU_TC; ln += NU_THREADS / 32) fft_line<MDC_FFT_POW_S != 0>(tile + ln * pitch, tw, g, lane);
     __syncthreads();
     for (int e = threadIdx.x; e < n * NU_TC; e += NU_THREADS) {
         const int k = e / NU_TC, ii = e - k * NU_TC;
@@ -605,10 +611,10 @@ int Nufft::density(cudaStream_t st, const double *posd, const double iL[3], int6
             *launches += 3;
             ord = order.p;
         }
-        const unsigned sblocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(maxlen, NU_THREADS / 32), 148 * 32));
+        const unsigned sblocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(maxlen, NU_THREADS / 32), 148 * 8192 / NU_THREADS));
         spread_kernel(g.w)<<<dim3(sblocks, B), NU_THREADS, 0, st>>>(posd, N, d_sets, n_sets, e0, ord, maxlen, g, iL[0], iL[1],
                                                              iL[2], reinterpret_cast<double *>(grid.p));
-        const unsigned zblocks = (unsigned)std::min<int64_t>(ceil_div((int64_t)nf * nf, NU_THREADS / 32), 148 * 16);
+        const unsigned zblocks = (unsigned)std::min<int64_t>(ceil_div((int64_t)nf * nf, NU_THREADS / 32), 148 * 4096 / NU_THREADS);
         nufft_fft_z<<<dim3(zblocks, B), NU_THREADS, smem_z, st>>>(grid.p, buf1.p, tw.p, g);
         // y pass: buf1 (nf, nf, ncp) -> grid reused as (nf, n, ncp)
         const int64_t ytiles = ceil_div(g.ncp, NU_TC);

@@ -6,7 +6,7 @@ N=100000; F=int(sys.argv[1]) if len(sys.argv)>1 else 2
 Lg=float(synthetic.cubic_box_length(N,2.5)); Ls=float(synthetic.cubic_box_length(N,0.8))
 gr=np.stack([synthetic.uniform_frame(N,Lg,2000+i) for i in range(F)]); sq=np.stack([synthetic.lj_like_frame(N,Ls,3000+i) for i in range(F)])
 gd=torch.from_numpy(gr).cuda(); sd=torch.from_numpy(sq).cuda(); box=np.array([Lg,Lg,Lg,90,90,90],np.float32)
-A=_capi.Context(0); B=_capi.Context(0)
+A=_capi.Context(0); B=_capi.Context(0, high_priority=True)
 for name,(ca,cb) in (("same context",(A,A)),("two contexts",(A,B))):
     rdf=_capi.RdfPlan(ca,200,(0.0,Lg/2),N,None,(1,1))
     sqp=_capi.SqPlan(cb,[N],[(None,None)],n_points=161,L0=[Ls]*3,q_max=20.0)
