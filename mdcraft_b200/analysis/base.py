@@ -181,11 +181,40 @@ def run_together(analyses, start=None, stop=None, step=None, frames=None):
     if pair_plans and len(pair_plans) < len(analyses):
         for plan in pair_plans:
             plan.set_blocks_per_sm(3)
-    for i, ts in enumerate(analyses[0]._sliced_trajectory):
-        for a in analyses:
-            a._frame_index, a._ts = i, ts
-            a.frames[i], a.times[i] = ts.frame, ts.time
-            a._single_frame()
+    # trajectories that hand out frame blocks resident in HBM (the GPU readers): every block is parsed once and
+    # consumed by each analysis on the device, when all of them can take it (see structure._DeviceBlockRun)
+    sources = [a._device_block_ranges() if hasattr(a, "_device_block_ranges") and getattr(a, "_drop_axis", None) is None
+               and type(a).__name__ in ("RadialDistributionFunction", "StructureFactor") else None for a in analyses]
+    if all(src is not None for src in sources):
+        from ..synthetic import Timestep
+
+        src = sources[0][0]
+        idx = np.asarray(analyses[0]._sliced_trajectory._indices, dtype=np.int64)
+        block_len = min(a._frame_block for a in analyses)
+        i = 0
+        while i < idx.size:
+            j = i + 1
+            while j < idx.size and j - i < block_len and idx[j] == idx[j - 1] + 1:
+                j += 1
+            lo, hi = int(idx[i]), int(idx[j - 1]) + 1
+            block = src.frames_block_device(lo, hi)
+            dims = np.stack([np.asarray(src._dims_of(f), dtype=np.float32) for f in range(lo, hi)])
+            stamps = [src._make_timestep(f, None) for f in range(lo, hi)]
+            for a in analyses:
+                for k, ts in enumerate(stamps):
+                    a.frames[i + k], a.times[i + k] = ts.frame, ts.time
+                a._consume_device_block(block, dims, [Timestep(None, d) for d in dims])
+            i = j
+        if idx.size:
+            last = src[int(idx[-1])]
+            for a in analyses:
+                a._ts, a._frame_index = last, idx.size - 1
+    else:
+        for i, ts in enumerate(analyses[0]._sliced_trajectory):
+            for a in analyses:
+                a._frame_index, a._ts = i, ts
+                a.frames[i], a.times[i] = ts.frame, ts.time
+                a._single_frame()
     for a in analyses:
         a._conclude()
     return analyses

@@ -659,6 +659,20 @@ def test_dump_reader_feeds_the_analysis_classes(tmp_path):
     s1 = _sq(u_file.atoms, n_points=8).results.ssf
     s2 = _sq(u_mem.atoms, n_points=8).results.ssf
     np.testing.assert_array_equal(s1, s2)
+    # both analyses from ONE pass over the file, blocks parsed once and consumed by each on the device
+    from mdcraft_b200.analysis.base import run_together
+
+    del calls[:]
+    ga = RadialDistributionFunction(u_file.atoms, n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1), verbose=False, frame_block=4)
+    sa = StructureFactor(u_file.atoms, n_points=8, verbose=False, frame_block=3)
+    run_together([ga, sa], start=1)
+    assert calls == [(1, 4), (4, 7)]
+    gb = RadialDistributionFunction(u_mem.atoms, n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1), verbose=False).run(start=1)
+    sb = StructureFactor(u_mem.atoms, n_points=8, verbose=False).run(start=1)
+    np.testing.assert_array_equal(ga.results.counts, gb.results.counts)
+    np.testing.assert_array_equal(ga.results.rdf, gb.results.rdf)
+    np.testing.assert_allclose(sa.results.ssf, sb.results.ssf, rtol=1e-13)   # frames summed in other block sizes
+    np.testing.assert_array_equal(ga.times, gb.times * 100.0)
     # residues groupings fall back to the per-frame protocol (centres of mass are formed on the host)
     del calls[:]
     c = _rdf(u_file.atoms, groupings="residues", n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1))
