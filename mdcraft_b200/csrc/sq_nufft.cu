@@ -283,7 +283,8 @@ nufft_spread(const double *__restrict__ posd, int64_t N, const int2 *__restrict_
     const int rsel = lane / LPR, within = lane - rsel * LPR, dz = within >> 1, ri = within & 1;
     const bool act = dz < W;
     const int t = lane & 15;
-    const unsigned plane = (unsigned)nf * (unsigned)nf * 2u;   // doubles per x plane (nf <= 1024: fits)
+    const size_t plane_bytes = (size_t)nf * nf * 16;           // one x plane of the grid
+    char *Gb = reinterpret_cast<char *>(G);
 
     for (int idx = blockIdx.x * (NU_THREADS / 32) + warp; idx < len; idx += gridDim.x * (NU_THREADS / 32)) {
         const int64_t j = order ? (int64_t)order[(int64_t)blockIdx.y * maxlen + idx] : (int64_t)set.x + idx;
@@ -321,16 +322,22 @@ nufft_spread(const double *__restrict__ posd, int64_t N, const int2 *__restrict_
                 int Y = l0y + iy;
                 Y = Y < 0 ? Y + nf : (Y >= nf ? Y - nf : Y);
                 vy[iy] = sv[warp][1][iy];
-                yo[iy] = ((unsigned)Y * (unsigned)nf + (unsigned)Z) * 2u + (unsigned)ri;
+                yo[iy] = (((unsigned)Y * (unsigned)nf + (unsigned)Z) * 2u + (unsigned)ri) * 8u;   // bytes, < 2^32
             }
 #pragma unroll 2
             for (int ix = rsel; ix < W; ix += RPI) {
                 int X = l0x + ix;
                 X = X < 0 ? X + nf : (X >= nf ? X - nf : X);
-                double *gp = G + (size_t)X * plane;
+                char *gp = Gb + (size_t)X * plane_bytes;
                 const double vxz = zc * sv[warp][0][ix];
 #pragma unroll
-                for (int iy = 0; iy < W; ++iy) atomicAdd(gp + yo[iy], vxz * vy[iy]);
+                for (int iy = 0; iy < W; ++iy) {
+                    // grid[gp + yo[iy]] += v: the address in ONE instruction (IMAD.WIDE.U32 with a 64-bit addend),
+                    // then the fire-and-forget reduction
+                    asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, 1, %1;\n\tred.global.add.f64 [a], %2;\n\t}"
+                                 ::"r"(yo[iy]), "l"(gp), "d"(vxz * vy[iy])
+                                 : "memory");
+                }
             }
         }
         __syncwarp();
