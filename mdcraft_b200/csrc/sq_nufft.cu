@@ -39,6 +39,9 @@ constexpr int NU_TC = 8;         // lines per block in the strided FFT passes (8
 // fit the quarter of an SM that the g(r) pair kernel leaves free when it runs next to these kernels on another
 // stream (mdc_rdf_set_blocks_per_sm); alone, 256 threads are 3 % faster.
 constexpr int NU_THREADS = MDC_NU_THREADS;
+#ifndef MDC_NU_FFT_BLOCKS
+#define MDC_NU_FFT_BLOCKS 4   // resident FFT blocks per SM the register budget is sized for (4: <= 128 registers)
+#endif
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 {
@@ -368,7 +371,7 @@ spread_fn spread_kernel(int w)
 // ---- pruned FFT passes --------------------------------------------------------------------------------
 
 // z axis: lines are contiguous.  grid (G, nf, nf, nf) -> out (G, nf, nf, ncp), mode c at column c.
-__global__ void __launch_bounds__(NU_THREADS)
+__global__ void __launch_bounds__(NU_THREADS, MDC_NU_FFT_BLOCKS)
 nufft_fft_z(const double2 *__restrict__ grid, double2 *__restrict__ out, const double2 *__restrict__ tw_g, NufftGeom g)
 {
     extern __shared__ __align__(16) unsigned char nu_smem[];
@@ -401,7 +404,7 @@ nufft_fft_z(const double2 *__restrict__ grid, double2 *__restrict__ out, const d
 //   !FINAL:  out[(o * n + k) * S + i]                      (y pass: O = nf, S = ncp)
 //   FINAL:   i = b * ncp + c, k = a;  part[row_qoff[b n + a] + c] = X * dec[a] dec[b] dec[c]   (x pass: O = 1, S = n ncp)
 template <bool FINAL>
-__global__ void __launch_bounds__(NU_THREADS)
+__global__ void __launch_bounds__(NU_THREADS, MDC_NU_FFT_BLOCKS)
 nufft_fft_s(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ tw_g, NufftGeom g,
             int O, int64_t S, const double *__restrict__ dec, const int *__restrict__ row_cnt,
             const int64_t *__restrict__ row_qoff, int64_t out_pitch)
