@@ -194,7 +194,134 @@ struct RdfArgs {
     int sym;                   // 1: self-RDF over unordered pairs (each counted twice)
     int64_t items_per_frame;
     unsigned long long *ticket;   // next tile pair to hand out (filter kernel: blocks draw work items dynamically)
+    // spatially sorted frames (filter kernel, cutoffs well below half the box): particles are in Morton order of a
+    // cell grid, so a tile of consecutive particles is a compact region and tile pairs farther apart than the
+    // cutoff are skipped.  oa / ob: original index of every sorted particle (the exclusion i / ex0 == j / ex1 is
+    // defined on those); tbox_a / tbox_b: bounding box of every tile {lo x, hi x, lo y, hi y, lo z, hi z} as
+    // 32-bit box fractions, (F, n_tiles, 6).  All NULL: original order, no culling.
+    const int *oa, *ob;
+    const uint32_t *tbox_a, *tbox_b;
+    double cull_r;                // a tile pair is skipped iff its boxes are farther apart than this (minimum image)
 };
+
+// ---- spatial sort (Morton order of an nc^3 cell grid, nc = 2^bits <= 32) -----------------------------------------
+
+__device__ __forceinline__ unsigned morton3(unsigned x, unsigned y, unsigned z, int bits)
+{
+    unsigned k = 0;
+    for (int b = 0; b < bits; ++b) k |= (((x >> b) & 1u) << (3 * b + 2)) | (((y >> b) & 1u) << (3 * b + 1)) | (((z >> b) & 1u) << (3 * b));
+    return k;
+}
+
+__device__ __forceinline__ unsigned cell_key(const uint32_t *fix, int64_t f, int64_t N, int64_t j, int bits)
+{
+    const int sh = 32 - bits;
+    return bits == 0 ? 0u : morton3(fix[(f * 3 + 0) * N + j] >> sh, fix[(f * 3 + 1) * N + j] >> sh, fix[(f * 3 + 2) * N + j] >> sh, bits);
+}
+
+__global__ void rdf_cell_count(const uint32_t *__restrict__ fix, int64_t N, int64_t total, int bits, int *__restrict__ cnt)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t f = i / N, j = i - f * N;
+    atomicAdd(&cnt[(f << (3 * bits)) + cell_key(fix, f, N, j, bits)], 1);
+}
+
+// exclusive scan of 8^bits <= 32768 counters per frame (one block of 1024 threads per frame)
+__global__ void __launch_bounds__(1024) rdf_cell_scan(int bits, int *__restrict__ cnt)
+{
+    __shared__ int sh[1024];
+    const int n = 1 << (3 * bits);
+    int *c = cnt + ((int64_t)blockIdx.x << (3 * bits));
+    const int per = (n + 1023) / 1024, lo = threadIdx.x * per, hi = min(n, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += c[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    int run = sh[threadIdx.x] - s;
+    for (int i = lo; i < hi; ++i) {
+        const int v = c[i];
+        c[i] = run;
+        run += v;
+    }
+}
+
+// soa / fix (F, 3, N) -> the same in cell order, plus the original index of every sorted particle
+__global__ void rdf_cell_scatter(const float *__restrict__ soa, const uint32_t *__restrict__ fix, int64_t N, int64_t total,
+                                 int bits, int *__restrict__ cursor, float *__restrict__ soa_s, uint32_t *__restrict__ fix_s,
+                                 int *__restrict__ orig)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t f = i / N, j = i - f * N;
+    const int pos = atomicAdd(&cursor[(f << (3 * bits)) + cell_key(fix, f, N, j, bits)], 1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        soa_s[(f * 3 + k) * N + pos] = soa[(f * 3 + k) * N + j];
+        fix_s[(f * 3 + k) * N + pos] = fix[(f * 3 + k) * N + j];
+    }
+    orig[f * N + pos] = (int)j;
+}
+
+// bounding box of every tile of `tile` consecutive (sorted) particles: one block per (tile, frame)
+__global__ void __launch_bounds__(256) rdf_tile_boxes(const uint32_t *__restrict__ fix, int64_t N, int tile, int n_tiles,
+                                                      uint32_t *__restrict__ tbox)
+{
+    __shared__ uint32_t lo[3][256], hi[3][256];
+    const int t = blockIdx.x, f = blockIdx.y;
+    const int64_t i0 = (int64_t)t * tile, i1 = min(N, i0 + tile);
+    uint32_t l[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, h[3] = {0u, 0u, 0u};
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += 256)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t v = fix[((int64_t)f * 3 + k) * N + i];
+            l[k] = min(l[k], v);
+            h[k] = max(h[k], v);
+        }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k][threadIdx.x] = l[k];
+        hi[k][threadIdx.x] = h[k];
+    }
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                lo[k][threadIdx.x] = min(lo[k][threadIdx.x], lo[k][threadIdx.x + o]);
+                hi[k][threadIdx.x] = max(hi[k][threadIdx.x], hi[k][threadIdx.x + o]);
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) {
+        uint32_t *o = tbox + ((int64_t)f * n_tiles + t) * 6;
+        o[2 * threadIdx.x] = lo[threadIdx.x][0];
+        o[2 * threadIdx.x + 1] = hi[threadIdx.x][0];
+    }
+}
+
+// squared minimum-image distance between two tile boxes (fractions of the box per axis, scaled by the box lengths)
+__device__ __forceinline__ double tile_gap2(const uint32_t *a, const uint32_t *b, const FrameBox &fb)
+{
+    double d2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double alo = a[2 * k] * (1.0 / 4294967296.0), ahi = a[2 * k + 1] * (1.0 / 4294967296.0);
+        const double blo = b[2 * k] * (1.0 / 4294967296.0), bhi = b[2 * k + 1] * (1.0 / 4294967296.0);
+        double gap = 1.0;
+#pragma unroll
+        for (int m = -1; m <= 1; ++m) gap = fmin(gap, fmax(0.0, fmax(blo + m - ahi, alo - (bhi + m))));
+        gap *= fb.box[k];
+        d2 += gap * gap;
+    }
+    return d2;
+}
 
 __device__ __forceinline__ double min_image_sq(float dxf, double inv, double box, int pbc)
 {
@@ -384,8 +511,32 @@ struct FastShared {
     unsigned qcount;
     unsigned pad[3];
     unsigned trash[RF_THREADS]; // per-thread dummy target of the branch-free histogram increment
-    unsigned char ctx[320];     // TileCtx of the tile in flight (cold passes read it from here)
+    unsigned char ctx[384];     // TileCtx of the tile in flight (cold passes read it from here)
+    // sorted frames only: bounding boxes {lo x, lo y, lo z, -, hi x, hi y, hi z, -} (32-bit box fractions) of the 128
+    // particles i of every warp and of every chunk of 32 rows j, and {L_k / 2^32 (k = x, y, z), cull_r^2}
+    uint4 ibox[RF_THREADS / 32][2];
+    uint4 jbox[RF_TJ / 32][2];
+    float cull[4];
 };
+
+// local index (within the tile) of particle u of this thread: a warp holds 128 consecutive particles, which in a
+// sorted frame is a compact region
+__device__ __forceinline__ int rf_il(int u) { return (int)(threadIdx.x & ~31u) * RF_IPT + u * 32 + (int)(threadIdx.x & 31u); }
+
+// sorted frames: is every particle of box a farther than the cutoff from every particle of box b (minimum image)?
+// Warp-uniform.  Per axis the gap between two intervals on the 2^32 circle that do not overlap is the smaller of the
+// two wrapped differences.
+__device__ __forceinline__ bool boxes_apart(const uint4 (&a)[2], const uint4 (&b)[2], const float (&c)[4])
+{
+    auto gap = [](uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi) -> float {
+        const bool overlap = blo <= ahi && alo <= bhi;
+        return overlap ? 0.f : (float)min(blo - ahi, alo - bhi);
+    };
+    const float gx = gap(a[0].x, a[1].x, b[0].x, b[1].x) * c[0];
+    const float gy = gap(a[0].y, a[1].y, b[0].y, b[1].y) * c[1];
+    const float gz = gap(a[0].z, a[1].z, b[0].z, b[1].z) * c[2];
+    return fmaf(gz, gz, fmaf(gy, gy, gx * gx)) > c[3];
+}
 
 // The filter's FP32 bin coordinate of one pair: v = bin coordinate - 0.5 (so that rint(v) is the bin).
 template <bool CUBIC>
@@ -435,7 +586,7 @@ __device__ __noinline__ void park_row(const TileCtx *Tp, unsigned *queue, unsign
 {
     for (int u = 0; u < RF_IPT; ++u) {
         if (!((mask >> u) & 1u)) continue;
-        const int il = threadIdx.x + u * RF_THREADS;
+        const int il = rf_il(u);
         const unsigned slot = atomicAdd(qcount, 1u);
         if (slot < RF_QCAP) queue[slot] = (unsigned)il | ((unsigned)jl << 16);
         else resolve_pair(Tp, il, jl, sT, hist);   // queue full (pathological inputs): resolve in line
@@ -729,7 +880,7 @@ __device__ __forceinline__ unsigned bin_or_flag4(unsigned long long v01, unsigne
     return any;
 }
 
-template <bool CHECK, bool CUBIC, bool EXCL, bool R0ZERO>
+template <bool CHECK, bool CUBIC, bool EXCL, bool R0ZERO, bool CULL>
 __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, const uint32_t (&ux)[RF_IPT],
                                                 const uint32_t (&uy)[RF_IPT], const uint32_t (&uz)[RF_IPT],
                                                 const int (&bi)[RF_IPT], const FrameFast &ff, float thr, unsigned B,
@@ -752,8 +903,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     const unsigned hbase = R0ZERO ? hist_addr - 4u * 0x4B400000u : hist_addr;
 #endif
     constexpr int RF_UNROLL = MDC_RF_UNROLL;
-#pragma unroll RF_UNROLL
-    for (int j = 0; j < nj; ++j) {
+    auto row = [&](int j) {
         const uint4 pj = S->sj[j];
         unsigned ok[RF_IPT];
 #pragma unroll
@@ -761,7 +911,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
             ok[u] = 1u;
             if (EXCL) ok[u] = bi[u] != (int)pj.w;
             if (CHECK) {
-                const int64_t ig = i0 + threadIdx.x + u * RF_THREADS;
+                const int64_t ig = i0 + rf_il(u);
                 ok[u] = ok[u] && (ig < na) && (!diag || (j0 + j) > ig);
             }
         }
@@ -788,6 +938,19 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                              bin_or_flag<8u, HAS_OK>(v[3], thr, B, hist_addr, trash_addr, ok[3], one);
         if (und) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
 #endif
+    };
+    if (CULL) {
+        // sorted frames: this warp's 128 particles against chunks of 32 rows; chunks out of reach are skipped
+        const uint4 (&ib)[2] = S->ibox[threadIdx.x >> 5];
+        for (int c = 0; c < nj; c += 32) {
+            if (boxes_apart(ib, S->jbox[c >> 5], S->cull)) continue;
+            const int je = min(nj, c + 32);
+#pragma unroll RF_UNROLL
+            for (int j = c; j < je; ++j) row(j);
+        }
+    } else {
+#pragma unroll RF_UNROLL
+        for (int j = 0; j < nj; ++j) row(j);
     }
 }
 
@@ -833,26 +996,74 @@ rdf_pairs_fast(RdfArgs A)
         }
         const FrameFast ff = A.fast[f];
         const FrameBox fb = A.boxes[f];
+        if (A.tbox_a) {   // sorted frames: skip tile pairs that lie farther apart than the cutoff (same for all threads)
+            const uint32_t *ta = A.tbox_a + ((int64_t)f * A.nti + I) * 6, *tb = A.tbox_b + ((int64_t)f * A.ntj + J) * 6;
+            if (tile_gap2(ta, tb, fb) > A.cull_r * A.cull_r) {
+#if MDC_RF_DYNAMIC
+                __syncthreads();
+#endif
+                continue;
+            }
+        }
         const uint32_t *ax = A.ua + ((int64_t)f * 3) * A.na, *ay = ax + A.na, *az = ay + A.na;
         const uint32_t *bx = A.ub + ((int64_t)f * 3) * A.nb, *by = bx + A.nb, *bz = by + A.nb;
+        const int *oa = A.oa ? A.oa + (int64_t)f * A.na : nullptr, *ob = A.ob ? A.ob + (int64_t)f * A.nb : nullptr;
         const int64_t i0 = (int64_t)I * RF_TI, j0 = (int64_t)J * RF_TJ;
 
         uint32_t ux[RF_IPT], uy[RF_IPT], uz[RF_IPT];
         int bi[RF_IPT];
 #pragma unroll
         for (int u = 0; u < RF_IPT; ++u) {
-            const int64_t ii = min(i0 + threadIdx.x + u * RF_THREADS, A.na - 1);
+            const int64_t ii = min(i0 + rf_il(u), A.na - 1);
             ux[u] = ax[ii];
             uy[u] = ay[ii];
             uz[u] = az[ii];
-            bi[u] = A.ex0 > 0 ? (int)(ii / A.ex0) : -1;
+            bi[u] = A.ex0 > 0 ? (int)((oa ? (int64_t)oa[ii] : ii) / A.ex0) : -1;
         }
         const int nj = (int)min((int64_t)RF_TJ, A.nb - j0);
         __syncthreads();
-        for (int j = threadIdx.x; j < nj; j += RF_THREADS) {
-            const int64_t jj = j0 + j;
-            const int bj = A.ex0 > 0 ? (int)(jj / A.ex1) : -2;
-            S->sj[j] = make_uint4(bx[jj], by[jj], bz[jj], (unsigned)bj);
+        const bool cull = A.tbox_a != nullptr;
+        for (int jb = 0; jb < nj; jb += RF_THREADS) {
+            const int j = jb + threadIdx.x;
+            uint4 pj = make_uint4(0u, 0u, 0u, 0u);
+            if (j < nj) {
+                const int64_t jj = j0 + j;
+                const int bj = A.ex0 > 0 ? (int)((ob ? (int64_t)ob[jj] : jj) / A.ex1) : -2;
+                pj = make_uint4(bx[jj], by[jj], bz[jj], (unsigned)bj);
+                S->sj[j] = pj;
+            }
+            if (cull) {   // one warp stages one chunk of 32 rows
+                const bool in = j < nj;
+                const uint4 lo = make_uint4(__reduce_min_sync(0xffffffffu, in ? pj.x : 0xffffffffu),
+                                            __reduce_min_sync(0xffffffffu, in ? pj.y : 0xffffffffu),
+                                            __reduce_min_sync(0xffffffffu, in ? pj.z : 0xffffffffu), 0u);
+                const uint4 hi = make_uint4(__reduce_max_sync(0xffffffffu, in ? pj.x : 0u),
+                                            __reduce_max_sync(0xffffffffu, in ? pj.y : 0u),
+                                            __reduce_max_sync(0xffffffffu, in ? pj.z : 0u), 0u);
+                if ((threadIdx.x & 31u) == 0u) {
+                    S->jbox[j >> 5][0] = lo;
+                    S->jbox[j >> 5][1] = hi;
+                }
+            }
+        }
+        if (cull) {
+            uint32_t lx = ux[0], ly = uy[0], lz = uz[0], hx = ux[0], hy = uy[0], hz = uz[0];
+#pragma unroll
+            for (int u = 1; u < RF_IPT; ++u) {
+                lx = min(lx, ux[u]); hx = max(hx, ux[u]);
+                ly = min(ly, uy[u]); hy = max(hy, uy[u]);
+                lz = min(lz, uz[u]); hz = max(hz, uz[u]);
+            }
+            const uint4 lo = make_uint4(__reduce_min_sync(0xffffffffu, lx), __reduce_min_sync(0xffffffffu, ly),
+                                        __reduce_min_sync(0xffffffffu, lz), 0u);
+            const uint4 hi = make_uint4(__reduce_max_sync(0xffffffffu, hx), __reduce_max_sync(0xffffffffu, hy),
+                                        __reduce_max_sync(0xffffffffu, hz), 0u);
+            if ((threadIdx.x & 31u) == 0u) {
+                S->ibox[threadIdx.x >> 5][0] = lo;
+                S->ibox[threadIdx.x >> 5][1] = hi;
+            }
+            if (threadIdx.x < 3) S->cull[threadIdx.x] = (float)(fb.box[threadIdx.x] * (1.0 / 4294967296.0));
+            if (threadIdx.x == 3) S->cull[3] = (float)(A.cull_r * A.cull_r);
         }
         __syncthreads();
         static_assert(sizeof(TileCtx) <= sizeof(S->ctx), "TileCtx must fit its shared-memory slot");
@@ -877,14 +1088,13 @@ rdf_pairs_fast(RdfArgs A)
         if (A.ex0 > 0) {
             const int64_t ilo = i0 / A.ex0, ihi = min(i0 + RF_TI - 1, A.na - 1) / A.ex0;
             const int64_t jlo = j0 / A.ex1, jhi = (j0 + nj - 1) / A.ex1;
-            excl = ilo <= jhi && jlo <= ihi;
+            excl = oa != nullptr || (ilo <= jhi && jlo <= ihi);   // sorted frames: a tile holds any original indices
         }
+#define RF_CALL2(C, Q, E, Z, U) tile_pairs_fast<C, Q, E, Z, U>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist)
 #define RF_CALL(C, Q, E)                                                                                              \
     do {                                                                                                              \
-        if (r0zero)                                                                                                   \
-            tile_pairs_fast<C, Q, E, true>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist); \
-        else                                                                                                          \
-            tile_pairs_fast<C, Q, E, false>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist); \
+        if (cull) { if (r0zero) RF_CALL2(C, Q, E, true, true); else RF_CALL2(C, Q, E, false, true); }                  \
+        else      { if (r0zero) RF_CALL2(C, Q, E, true, false); else RF_CALL2(C, Q, E, false, false); }                \
     } while (0)
         if (check) {
             if (ff.cubic) { if (excl) RF_CALL(true, true, true); else RF_CALL(true, true, false); }
@@ -894,6 +1104,7 @@ rdf_pairs_fast(RdfArgs A)
             else          { if (excl) RF_CALL(false, false, true); else RF_CALL(false, false, false); }
         }
 #undef RF_CALL
+#undef RF_CALL2
         // resolve the undecided pairs of this tile with the reference's FP64 arithmetic
         __syncthreads();
         const unsigned nq = min(S->qcount, (unsigned)RF_QCAP);
@@ -939,6 +1150,12 @@ struct mdc_rdf_plan {
     DevBuf<unsigned> absmax[2];        // (2, F): group a, group b
     DevBuf<FrameBox> boxes[2];
     DevBuf<FrameFast> fast[2];
+    // spatially sorted copies (cutoffs well below half the box), allocated on first use
+    DevBuf<float> sort_soa_a[2], sort_soa_b[2];
+    DevBuf<uint32_t> sort_fix_a[2], sort_fix_b[2], tbox_a[2], tbox_b[2];
+    DevBuf<int> orig_a[2], orig_b[2], cells[2];
+    int sort_bits_a = 0, sort_bits_b = 0;
+    int64_t last_culled_hint = 0;
     Streams st;
     int fblk = 0;
     size_t smem = 0, smem_fast = 0;
@@ -966,6 +1183,15 @@ void rdf_free(mdc_rdf_plan *p)
         p->absmax[i].release();
         p->boxes[i].release();
         p->fast[i].release();
+        p->sort_soa_a[i].release();
+        p->sort_soa_b[i].release();
+        p->sort_fix_a[i].release();
+        p->sort_fix_b[i].release();
+        p->tbox_a[i].release();
+        p->tbox_b[i].release();
+        p->orig_a[i].release();
+        p->orig_b[i].release();
+        p->cells[i].release();
     }
     p->st.destroy();
     delete p;
@@ -1144,23 +1370,85 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
             p->boxes[slot].p, p->absmax[slot].p, p->absmax[slot].p + (rb ? p->fblk : 0), F, p->n_bins, p->r0, p->r1,
             p->fast[slot].p);
         ++launches;
-        MDC_CUDA(cudaGetLastError());
-        MDC_CUDA(cudaEventRecord(p->st.staged[slot], sc));
-        MDC_CUDA(cudaStreamWaitEvent(sk, p->st.staged[slot], 0));
         // the filter kernel needs three periodic axes and a bin coordinate below 2^22 in every frame
         bool fast = !p->force_exact;
+        double min_len = 1e300, max_len = 0.0;
         for (int f = 0; f < F && fast; ++f) {
             const FrameBox &fb = hb[f0 + f];
             const double S = (double)p->n_bins / (p->r1 - p->r0);
             const double v_far = 0.5 * sqrt(fb.box[0] * fb.box[0] + fb.box[1] * fb.box[1] + fb.box[2] * fb.box[2]) * S +
                                  fabs(p->r0 * S) + 1.0;
             fast = fb.pbc[0] && fb.pbc[1] && fb.pbc[2] && v_far < 4.0e6;
+            for (int k = 0; k < 3; ++k) {
+                min_len = std::min(min_len, fb.box[k]);
+                max_len = std::max(max_len, fb.box[k]);
+            }
         }
+        // Cutoffs well below half the box: put every frame in Morton order of a cell grid, so that a tile of
+        // consecutive particles is a compact region, and let the pair kernel skip the tile pairs whose bounding
+        // boxes are farther apart than the cutoff (MDAnalysis switches capped_distance to a grid search in the
+        // same regime).  Counts do not depend on the particle order; exclusion uses the original indices.
+        const char *sort_env = getenv("MDC_RDF_SORT");   // "0": keep the original order (diagnostics / tests)
+        const bool sort_off = sort_env && sort_env[0] == '0';
+        const bool sorted = fast && !sort_off && p->r1 < 0.4 * min_len && p->na >= 4 * RF_TI && p->nb >= 4 * RF_TJ;
+        const int nti_fast = (int)ceil_div(p->na, RF_TI), ntj_fast = (int)ceil_div(p->nb, RF_TJ);
+        if (sorted) {
+            auto bits_for = [](int64_t n) {
+                int b = 0;
+                while (b < 5 && ((int64_t)32 << (3 * b)) < n) ++b;   // ~32 particles per cell
+                return b;
+            };
+            p->sort_bits_a = bits_for(p->na);
+            p->sort_bits_b = bits_for(p->nb);
+            const int max_bits = std::max(p->sort_bits_a, p->sort_bits_b);
+            MDC_CHECK(p->cells[slot].alloc((size_t)p->fblk << (3 * max_bits)));
+            auto sort_group = [&](const float *soa, const uint32_t *fix, int64_t n, int bits, int n_tiles, DevBuf<float> &soa_s,
+                                  DevBuf<uint32_t> &fix_s, DevBuf<int> &orig, DevBuf<uint32_t> &tbox) -> int {
+                MDC_CHECK(soa_s.alloc((size_t)p->fblk * n * 3));
+                MDC_CHECK(fix_s.alloc((size_t)p->fblk * n * 3));
+                MDC_CHECK(orig.alloc((size_t)p->fblk * n));
+                MDC_CHECK(tbox.alloc((size_t)p->fblk * n_tiles * 6));
+                const int64_t total = (int64_t)F * n;
+                MDC_CUDA(cudaMemsetAsync(p->cells[slot].p, 0, ((size_t)F << (3 * bits)) * sizeof(int), sc));
+                rdf_cell_count<<<(unsigned)ceil_div(total, 256), 256, 0, sc>>>(fix, n, total, bits, p->cells[slot].p);
+                rdf_cell_scan<<<F, 1024, 0, sc>>>(bits, p->cells[slot].p);
+                rdf_cell_scatter<<<(unsigned)ceil_div(total, 256), 256, 0, sc>>>(soa, fix, n, total, bits, p->cells[slot].p,
+                                                                              soa_s.p, fix_s.p, orig.p);
+                rdf_tile_boxes<<<dim3((unsigned)n_tiles, (unsigned)F), 256, 0, sc>>>(fix_s.p, n, RF_TI, n_tiles, tbox.p);
+                launches += 4;
+                return MDC_OK;
+            };
+            static_assert(RF_TI == RF_TJ, "one tile size for both groups");
+            MDC_CHECK(sort_group(p->soa_a[slot].p, p->fix_a[slot].p, p->na, p->sort_bits_a, nti_fast, p->sort_soa_a[slot],
+                                 p->sort_fix_a[slot], p->orig_a[slot], p->tbox_a[slot]));
+            if (!p->same)
+                MDC_CHECK(sort_group(p->soa_b[slot].p, p->fix_b[slot].p, p->nb, p->sort_bits_b, ntj_fast, p->sort_soa_b[slot],
+                                     p->sort_fix_b[slot], p->orig_b[slot], p->tbox_b[slot]));
+        }
+        MDC_CUDA(cudaGetLastError());
+        MDC_CUDA(cudaEventRecord(p->st.staged[slot], sc));
+        MDC_CUDA(cudaStreamWaitEvent(sk, p->st.staged[slot], 0));
         RdfArgs A;
         A.a = p->soa_a[slot].p;
         A.b = p->same ? p->soa_a[slot].p : p->soa_b[slot].p;
         A.ua = p->fix_a[slot].p;
         A.ub = p->same ? p->fix_a[slot].p : p->fix_b[slot].p;
+        A.oa = A.ob = nullptr;
+        A.tbox_a = A.tbox_b = nullptr;
+        A.cull_r = 0.0;
+        if (sorted) {
+            A.a = p->sort_soa_a[slot].p;
+            A.ua = p->sort_fix_a[slot].p;
+            A.oa = p->orig_a[slot].p;
+            A.tbox_a = p->tbox_a[slot].p;
+            A.b = p->same ? A.a : p->sort_soa_b[slot].p;
+            A.ub = p->same ? A.ua : p->sort_fix_b[slot].p;
+            A.ob = p->same ? A.oa : p->orig_b[slot].p;
+            A.tbox_b = p->same ? A.tbox_a : p->tbox_b[slot].p;
+            // conservative: far above the difference between the reference's float32-derived distance, the fixed-point
+            // boxes and the true separation (all below 1e-6 of the box)
+            A.cull_r = p->r1 * (1.0 + 1e-4) + 1e-5 * max_len;
+        }
         A.boxes = p->boxes[slot].p;
         A.fast = p->fast[slot].p;
         A.T = p->T.p;
