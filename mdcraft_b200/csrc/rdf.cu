@@ -194,7 +194,7 @@ struct RdfArgs {
     int sym;                   // 1: self-RDF over unordered pairs (each counted twice)
     int64_t items_per_frame;
     unsigned long long *ticket;   // next tile pair to hand out (filter kernel: blocks draw work items dynamically)
-    // spatially sorted frames (filter kernel, cutoffs well below half the box): particles are in Morton order of a
+    // spatially sorted frames (filter kernel, cutoffs well below half the box): particles are in Hilbert order of a
     // cell grid, so a tile of consecutive particles is a compact region and tile pairs farther apart than the
     // cutoff are skipped.  oa / ob: original index of every sorted particle (the exclusion i / ex0 == j / ex1 is
     // defined on those); tbox_a / tbox_b: bounding box of every tile {lo x, hi x, lo y, hi y, lo z, hi z} as
@@ -204,19 +204,45 @@ struct RdfArgs {
     double cull_r;                // a tile pair is skipped iff its boxes are farther apart than this (minimum image)
 };
 
-// ---- spatial sort (Morton order of an nc^3 cell grid, nc = 2^bits <= 32) -----------------------------------------
+// ---- spatial sort (Hilbert order of an nc^3 cell grid, nc = 2^bits <= 32) ----------------------------------------
 
-__device__ __forceinline__ unsigned morton3(unsigned x, unsigned y, unsigned z, int bits)
+// Hilbert index of cell (x, y, z) of a (2^bits)^3 grid (Skilling's transpose form).  Consecutive indices are
+// face-adjacent cells, so a run of consecutive particles has a tighter bounding box than in Morton order (measured:
+// half as many chunk pairs survive the culling at small cutoffs).
+__device__ __forceinline__ unsigned hilbert3(unsigned x, unsigned y, unsigned z, int bits)
 {
-    unsigned k = 0;
-    for (int b = 0; b < bits; ++b) k |= (((x >> b) & 1u) << (3 * b + 2)) | (((y >> b) & 1u) << (3 * b + 1)) | (((z >> b) & 1u) << (3 * b));
+    unsigned X[3] = {x, y, z};
+    const unsigned M = 1u << (bits - 1);
+    for (unsigned Q = M; Q > 1u; Q >>= 1) {
+        const unsigned P = Q - 1u;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) X[0] ^= P;
+            else {
+                const unsigned t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    unsigned t = 0u;
+    for (unsigned Q = M; Q > 1u; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1u;
+    X[0] ^= t;
+    X[1] ^= t;
+    X[2] ^= t;
+    unsigned k = 0u;
+    for (int b = 0; b < bits; ++b)
+        k |= (((X[0] >> b) & 1u) << (3 * b + 2)) | (((X[1] >> b) & 1u) << (3 * b + 1)) | (((X[2] >> b) & 1u) << (3 * b));
     return k;
 }
 
 __device__ __forceinline__ unsigned cell_key(const uint32_t *fix, int64_t f, int64_t N, int64_t j, int bits)
 {
     const int sh = 32 - bits;
-    return bits == 0 ? 0u : morton3(fix[(f * 3 + 0) * N + j] >> sh, fix[(f * 3 + 1) * N + j] >> sh, fix[(f * 3 + 2) * N + j] >> sh, bits);
+    return bits == 0 ? 0u : hilbert3(fix[(f * 3 + 0) * N + j] >> sh, fix[(f * 3 + 1) * N + j] >> sh, fix[(f * 3 + 2) * N + j] >> sh, bits);
 }
 
 __global__ void rdf_cell_count(const uint32_t *__restrict__ fix, int64_t N, int64_t total, int bits, int *__restrict__ cnt)
@@ -801,7 +827,10 @@ __device__ __forceinline__ unsigned bin_or_flag2(unsigned long long v, unsigned 
 // lower bound check is needed: the caller folds bits(MAGIC) into the limit and into the histogram base address.
 // Returns whether ANY pair is undecided (predicate OR, one SEL) and the four |df| so that the cold path can tell
 // which; that replaces four SELs and the adds that combined them.
-template <bool HAS_OK, bool R0ZERO>
+// GATE (sorted frames, i.e. cutoffs far below the box size): a pair whose k lies beyond the last bin + 1 is out of range
+// whatever the rounding, so it is never reported as undecided -- with narrow bins the margin is a sizeable
+// fraction of a bin and nearly every row would otherwise hold an "undecided" pair that is nowhere near the window.
+template <bool HAS_OK, bool R0ZERO, bool GATE>
 __device__ __forceinline__ unsigned bin_or_flag4(unsigned long long v01, unsigned long long v23, unsigned long long magic,
                                                  unsigned long long nmagic, unsigned long long neg1, float thr,
                                                  unsigned blim, unsigned hbase, unsigned trash_addr, unsigned one,
@@ -810,10 +839,10 @@ __device__ __forceinline__ unsigned bin_or_flag4(unsigned long long v01, unsigne
     unsigned any;
 #define RF_HEAD                                                   \
     "{\n\t"                                                       \
-    ".reg .pred p, q, q0, q1, q2, q3, r;\n\t"                     \
+    ".reg .pred p, q, q0, q1, q2, q3, r, g;\n\t"                  \
     ".reg .b64 W01, W23, KF, DF01, DF23;\n\t"                     \
     ".reg .f32 w0, w1, w2, w3;\n\t"                               \
-    ".reg .u32 k, ad;\n\t"                                        \
+    ".reg .u32 k, kk, ad;\n\t"                                    \
     "add.rn.f32x2 W01, %5, %12;\n\t"                              \
     "add.rn.f32x2 W23, %6, %12;\n\t"                              \
     "add.rn.f32x2 KF, W01, %13;\n\t"                              \
@@ -859,9 +888,45 @@ __device__ __forceinline__ unsigned bin_or_flag4(unsigned long long v01, unsigne
     "mov.b32 k, w3;\n\t" SUBK "setp.ne.u32 r, %18, 0;\n\t setp.gt.and.f32 q3, %4, %7, r;\n\t"                   \
     "setp.lt.and.u32 p, k, %8, r;\n\t and.pred p, p, !q3;\n\t"                                                  \
     "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"
+// gated forms: undecided only if -1 <= bin <= B.  GATEK sets predicate g from k (see RF_GATE_*)
+#define RF_GATE_R0ZERO "setp.le.u32 g, k, %8;\n\t"                              /* bits(w) <= B + bits(MAGIC) */
+#define RF_GATE_ANY(LIM1) "add.u32 kk, k, 1;\n\t setp.le.u32 g, kk, " LIM1 ";\n\t" /* k + 1 <= B + 1, unsigned */
+#define RF_G4(SUBK, GATEK) \
+    "mov.b32 k, w0;\n\t" SUBK GATEK "setp.gt.and.f32 q0, %1, %7, g;\n\t setp.lt.and.u32 p, k, %8, !q0;\n\t" \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t" \
+    "mov.b32 k, w1;\n\t" SUBK GATEK "setp.gt.and.f32 q1, %2, %7, g;\n\t setp.lt.and.u32 p, k, %8, !q1;\n\t" \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t" \
+    "mov.b32 k, w2;\n\t" SUBK GATEK "setp.gt.and.f32 q2, %3, %7, g;\n\t setp.lt.and.u32 p, k, %8, !q2;\n\t" \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t" \
+    "mov.b32 k, w3;\n\t" SUBK GATEK "setp.gt.and.f32 q3, %4, %7, g;\n\t setp.lt.and.u32 p, k, %8, !q3;\n\t" \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"
+#define RF_G4_OK(SUBK, GATEK) \
+    "mov.b32 k, w0;\n\t" SUBK "setp.ne.u32 r, %15, 0;\n\t" GATEK "and.pred g, g, r;\n\t setp.gt.and.f32 q0, %1, %7, g;\n\t" \
+    "setp.lt.and.u32 p, k, %8, r;\n\t and.pred p, p, !q0;\n\t" \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t" \
+    "mov.b32 k, w1;\n\t" SUBK "setp.ne.u32 r, %16, 0;\n\t" GATEK "and.pred g, g, r;\n\t setp.gt.and.f32 q1, %2, %7, g;\n\t" \
+    "setp.lt.and.u32 p, k, %8, r;\n\t and.pred p, p, !q1;\n\t" \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t" \
+    "mov.b32 k, w2;\n\t" SUBK "setp.ne.u32 r, %17, 0;\n\t" GATEK "and.pred g, g, r;\n\t setp.gt.and.f32 q2, %3, %7, g;\n\t" \
+    "setp.lt.and.u32 p, k, %8, r;\n\t and.pred p, p, !q2;\n\t" \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t" \
+    "mov.b32 k, w3;\n\t" SUBK "setp.ne.u32 r, %18, 0;\n\t" GATEK "and.pred g, g, r;\n\t setp.gt.and.f32 q3, %4, %7, g;\n\t" \
+    "setp.lt.and.u32 p, k, %8, r;\n\t and.pred p, p, !q3;\n\t" \
+    "mad.lo.u32 ad, k, 4, %9;\n\t selp.u32 ad, ad, %10, p;\n\t red.shared.add.u32 [ad], %11;\n\t"
 #define RF_OUT "=r"(any), "=f"(adf[0]), "=f"(adf[1]), "=f"(adf[2]), "=f"(adf[3])
 #define RF_IN "l"(v01), "l"(v23), "f"(thr), "r"(blim), "r"(hbase), "r"(trash_addr), "r"(one), "l"(magic), "l"(nmagic), "l"(neg1)
-    if (HAS_OK) {
+    if (GATE) {
+        const unsigned lim1 = blim + 1u;
+        if (HAS_OK) {
+            if (R0ZERO)
+                asm volatile(RF_HEAD RF_G4_OK("", RF_GATE_R0ZERO) RF_FOOT : RF_OUT : RF_IN, "r"(ok[0]), "r"(ok[1]), "r"(ok[2]), "r"(ok[3]) : "memory");
+            else
+                asm volatile(RF_HEAD RF_G4_OK(RF_SUB, RF_GATE_ANY("%19")) RF_FOOT : RF_OUT : RF_IN, "r"(ok[0]), "r"(ok[1]), "r"(ok[2]), "r"(ok[3]), "r"(lim1) : "memory");
+        } else {
+            if (R0ZERO) asm volatile(RF_HEAD RF_G4("", RF_GATE_R0ZERO) RF_FOOT : RF_OUT : RF_IN : "memory");
+            else asm volatile(RF_HEAD RF_G4(RF_SUB, RF_GATE_ANY("%15")) RF_FOOT : RF_OUT : RF_IN, "r"(lim1) : "memory");
+        }
+    } else if (HAS_OK) {
         if (R0ZERO)
             asm volatile(RF_HEAD RF_P4_OK("") RF_FOOT : RF_OUT : RF_IN, "r"(ok[0]), "r"(ok[1]), "r"(ok[2]), "r"(ok[3]) : "memory");
         else
@@ -875,6 +940,10 @@ __device__ __forceinline__ unsigned bin_or_flag4(unsigned long long v01, unsigne
 #undef RF_SUB
 #undef RF_P4
 #undef RF_P4_OK
+#undef RF_G4
+#undef RF_G4_OK
+#undef RF_GATE_R0ZERO
+#undef RF_GATE_ANY
 #undef RF_OUT
 #undef RF_IN
     return any;
@@ -921,8 +990,8 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
         const unsigned long long v23 = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[2], uy[2], uz[2], ux[3], uy[3], uz[3], fax,
                                                         fay, faz, fc0);
         float adf[4];
-        if (bin_or_flag4<HAS_OK, R0ZERO>(v01, v23, magic, nmagic, neg1, thr, blim, hbase, trash_addr, one, ok, adf)) {
-            unsigned und = 0;   // cold: which of the four
+        if (bin_or_flag4<HAS_OK, R0ZERO, CULL>(v01, v23, magic, nmagic, neg1, thr, blim, hbase, trash_addr, one, ok, adf)) {
+            unsigned und = 0;   // cold: which of the four (without the gate: a far pair parked here resolves to no bin)
 #pragma unroll
             for (int u = 0; u < RF_IPT; ++u)
                 if (adf[u] > thr && ok[u]) und |= 1u << u;
@@ -1088,7 +1157,9 @@ rdf_pairs_fast(RdfArgs A)
         if (A.ex0 > 0) {
             const int64_t ilo = i0 / A.ex0, ihi = min(i0 + RF_TI - 1, A.na - 1) / A.ex0;
             const int64_t jlo = j0 / A.ex1, jhi = (j0 + nj - 1) / A.ex1;
-            excl = oa != nullptr || (ilo <= jhi && jlo <= ihi);   // sorted frames: a tile holds any original indices
+            // sorted frames: a tile holds any original indices; but blocks of one particle within one group exclude
+            // the self pairs only, which a symmetric sweep (j > i) never evaluates
+            excl = oa != nullptr ? !(A.sym && A.ex0 == 1 && A.ex1 == 1) : (ilo <= jhi && jlo <= ihi);
         }
 #define RF_CALL2(C, Q, E, Z, U) tile_pairs_fast<C, Q, E, Z, U>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist)
 #define RF_CALL(C, Q, E)                                                                                              \
@@ -1372,25 +1443,24 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         ++launches;
         // the filter kernel needs three periodic axes and a bin coordinate below 2^22 in every frame
         bool fast = !p->force_exact;
-        double min_len = 1e300, max_len = 0.0;
+        double max_len = 0.0;
         for (int f = 0; f < F && fast; ++f) {
             const FrameBox &fb = hb[f0 + f];
             const double S = (double)p->n_bins / (p->r1 - p->r0);
             const double v_far = 0.5 * sqrt(fb.box[0] * fb.box[0] + fb.box[1] * fb.box[1] + fb.box[2] * fb.box[2]) * S +
                                  fabs(p->r0 * S) + 1.0;
             fast = fb.pbc[0] && fb.pbc[1] && fb.pbc[2] && v_far < 4.0e6;
-            for (int k = 0; k < 3; ++k) {
-                min_len = std::min(min_len, fb.box[k]);
-                max_len = std::max(max_len, fb.box[k]);
-            }
+            for (int k = 0; k < 3; ++k) max_len = std::max(max_len, fb.box[k]);
         }
-        // Cutoffs well below half the box: put every frame in Morton order of a cell grid, so that a tile of
-        // consecutive particles is a compact region, and let the pair kernel skip the tile pairs whose bounding
-        // boxes are farther apart than the cutoff (MDAnalysis switches capped_distance to a grid search in the
-        // same regime).  Counts do not depend on the particle order; exclusion uses the original indices.
+        // Put every frame in Hilbert order of a cell grid, so that runs of consecutive particles are compact regions,
+        // and let the pair kernel skip what lies farther apart than the cutoff: whole tile pairs, and inside a tile
+        // pair the (warp of 128 i) x (chunk of 32 j) blocks (MDAnalysis switches capped_distance to a grid search
+        // for small cutoffs; here the same sweep serves every cutoff: at r_max = L / 2 a few per cent of the blocks
+        // drop out, at r_max << L nearly all).  Counts do not depend on the particle order; exclusion uses the
+        // original indices.
         const char *sort_env = getenv("MDC_RDF_SORT");   // "0": keep the original order (diagnostics / tests)
         const bool sort_off = sort_env && sort_env[0] == '0';
-        const bool sorted = fast && !sort_off && p->r1 < 0.4 * min_len && p->na >= 4 * RF_TI && p->nb >= 4 * RF_TJ;
+        const bool sorted = fast && !sort_off && p->na >= 4 * RF_TI && p->nb >= 4 * RF_TJ;
         const int nti_fast = (int)ceil_div(p->na, RF_TI), ntj_fast = (int)ceil_div(p->nb, RF_TJ);
         if (sorted) {
             auto bits_for = [](int64_t n) {

@@ -236,3 +236,17 @@ def test_rdf_small_cutoff_sorted_and_culled(ctx):
         qb = pa if pb is None else pb
         want = oracle.radial_histogram(pa[0], qb[0], 64, rcut, boxes[0], exclusion=excl)
         np.testing.assert_array_equal(got0, want)
+
+    # a simple-cubic lattice (spacing 2) whose neighbour distances 2 and 4 sit exactly on bin and window edges: the
+    # undecided-pair path of the sorted kernel, window edges r0 exclusive / r1 inclusive
+    g = np.arange(32, dtype=np.float32) * 2.0
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(1, -1, 3)
+    lat = np.ascontiguousarray(lat[:, rng.permutation(lat.shape[1])])
+    boxes = np.array([[64.0, 64.0, 64.0, 90, 90, 90]], np.float32)
+    for rcut in ((0.0, 4.0), (2.0, 4.0)):
+        got, _ = counts(lat, None, None, True, rcut, frames=1)
+        plain, _ = counts(lat, None, None, False, rcut, frames=1)
+        np.testing.assert_array_equal(got, plain)
+        want = oracle.radial_histogram(lat[0], lat[0], 64, rcut, boxes[0])
+        np.testing.assert_array_equal(got, want)
+        assert got[-1] >= 6 * lat.shape[1]          # the d = 4 neighbours land in the last bin (upper edge inclusive)
