@@ -40,6 +40,7 @@ struct Ctx {
     int clock_khz = 0;
     int64_t global_mem = 0;
     size_t smem_optin = 0;
+    size_t smem_per_sm = 0;   // sharedMemPerMultiprocessor
     cudaStream_t copy = nullptr, compute = nullptr;
     cudaEvent_t mark[2] = {nullptr, nullptr};   // mdc_mark / mdc_elapsed_ms
 };

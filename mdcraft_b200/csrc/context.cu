@@ -62,6 +62,7 @@ static int create_impl(int device, int high_priority, mdc_ctx **out)
     c->clock_khz = khz;
     c->global_mem = (int64_t)prop.totalGlobalMem;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->smem_per_sm = prop.sharedMemPerMultiprocessor;
     // high priority: when thread blocks of another context's kernels retire, this context's blocks are placed first
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // numerically lower = higher priority

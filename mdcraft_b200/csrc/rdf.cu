@@ -202,6 +202,10 @@ struct RdfArgs {
     const int *oa, *ob;
     const uint32_t *tbox_a, *tbox_b;
     double cull_r;                // a tile pair is skipped iff its boxes are farther apart than this (minimum image)
+    // filter kernel, extended histograms: ext_k > 0 = words per histogram copy, ext_off = index of bin 0 in a copy.
+    // Every bin coordinate the filter can produce in these frames, in the window or not, then has a word of its
+    // own, so the hot loop increments without a range test (bins outside [0, B) are never read back).
+    int ext_k, ext_off;
 };
 
 // ---- spatial sort (Hilbert order of an nc^3 cell grid, nc = 2^bits <= 32) ----------------------------------------
@@ -442,13 +446,14 @@ __device__ __forceinline__ bool decode_item(const RdfArgs &A, int64_t item, int 
 }
 
 __device__ __forceinline__ void flush_hist(unsigned *sh, int B, int n_copies, unsigned long long weight,
-                                           unsigned long long *counts, bool clear)
+                                           unsigned long long *counts, bool clear, int stride = 0)
 {
+    if (stride == 0) stride = B;   // sh points at bin 0 of copy 0; copies are `stride` words apart
     for (int i = threadIdx.x; i < B; i += blockDim.x) {
         unsigned long long s = 0;
         for (int c = 0; c < n_copies; ++c) {
-            s += sh[c * B + i];
-            if (clear) sh[c * B + i] = 0u;
+            s += sh[c * stride + i];
+            if (clear) sh[c * stride + i] = 0u;
         }
         if (s) atomicAdd(&counts[i], s * weight);
     }
@@ -608,10 +613,19 @@ __device__ __noinline__ void resolve_pair(const TileCtx *Tp, int il, int jl, con
 
 // cold: the pairs (this thread's particle u, row jl) with bit u set in `mask` are undecided; park them
 __device__ __noinline__ void park_row(const TileCtx *Tp, unsigned *queue, unsigned *qcount, int jl, unsigned mask,
-                                      const double *sT, unsigned *hist)
+                                      const double *sT, unsigned *hist, unsigned long long v01 = 0ull,
+                                      unsigned long long v23 = 0ull, bool uncount = false)
 {
     for (int u = 0; u < RF_IPT; ++u) {
         if (!((mask >> u) & 1u)) continue;
+        if (uncount) {
+            // extended histograms: the hot loop has already counted this pair in the filter's bin (this thread, this
+            // copy, program order); take that back before the exact result is added
+            const unsigned long long vv = u < 2 ? v01 : v23;
+            const float v = __uint_as_float((unsigned)((u & 1) ? (vv >> 32) : (vv & 0xffffffffull)));
+            const int k = (int)(__float_as_uint(__fadd_rn(v, 12582912.f)) - 0x4B400000u);
+            atomicSub(&hist[k], 1u);
+        }
         const int il = rf_il(u);
         const unsigned slot = atomicAdd(qcount, 1u);
         if (slot < RF_QCAP) queue[slot] = (unsigned)il | ((unsigned)jl << 16);
@@ -949,7 +963,68 @@ __device__ __forceinline__ unsigned bin_or_flag4(unsigned long long v01, unsigne
     return any;
 }
 
-template <bool CHECK, bool CUBIC, bool EXCL, bool R0ZERO, bool CULL>
+// The four pairs of one row with extended histograms (RdfArgs::ext_k): every k the filter can produce has a word, so
+// the increment needs no range test and no dummy word: hist[k] += 1 (IMAD + ATOMS per pair) and ONE predicate that
+// says whether any pair is undecided (FSETP chain).  The cold path takes the increment of an undecided pair back.
+// hbase = shared address of bin 0 of this thread's copy - 4 * bits(MAGIC): bits(w) = bits(MAGIC) + k for any sign of k.
+template <bool HAS_OK>
+__device__ __forceinline__ unsigned bin_count4(unsigned long long v01, unsigned long long v23, unsigned long long magic,
+                                               unsigned long long nmagic, unsigned long long neg1, float thr,
+                                               unsigned hbase, unsigned trash_addr, unsigned one, const unsigned (&ok)[4],
+                                               float (&adf)[4])
+{
+    unsigned any;
+#define RX_HEAD                                                   \
+    "{\n\t"                                                       \
+    ".reg .pred q, r;\n\t"                                        \
+    ".reg .b64 W01, W23, KF, DF01, DF23;\n\t"                     \
+    ".reg .f32 w0, w1, w2, w3;\n\t"                               \
+    ".reg .u32 k, ad;\n\t"                                        \
+    "add.rn.f32x2 W01, %5, %11;\n\t"                              \
+    "add.rn.f32x2 W23, %6, %11;\n\t"                              \
+    "add.rn.f32x2 KF, W01, %12;\n\t"                              \
+    "fma.rn.f32x2 DF01, KF, %13, %5;\n\t"                         \
+    "add.rn.f32x2 KF, W23, %12;\n\t"                              \
+    "fma.rn.f32x2 DF23, KF, %13, %6;\n\t"                         \
+    "mov.b64 {w0, w1}, W01;\n\t"                                  \
+    "mov.b64 {w2, w3}, W23;\n\t"                                  \
+    "mov.b64 {%1, %2}, DF01;\n\t"                                 \
+    "mov.b64 {%3, %4}, DF23;\n\t"                                 \
+    "abs.f32 %1, %1;\n\t"                                         \
+    "abs.f32 %2, %2;\n\t"                                         \
+    "abs.f32 %3, %3;\n\t"                                         \
+    "abs.f32 %4, %4;\n\t"
+#define RX_OUT "=r"(any), "=f"(adf[0]), "=f"(adf[1]), "=f"(adf[2]), "=f"(adf[3])
+#define RX_IN "l"(v01), "l"(v23), "f"(thr), "r"(hbase), "r"(trash_addr), "r"(one), "l"(magic), "l"(nmagic), "l"(neg1)
+    if (HAS_OK) {
+        asm volatile(RX_HEAD
+            "mov.b32 k, w0;\n\t setp.ne.u32 r, %14, 0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t selp.u32 ad, ad, %9, r;\n\t"
+            "red.shared.add.u32 [ad], %10;\n\t setp.gt.and.f32 q, %1, %7, r;\n\t"
+            "mov.b32 k, w1;\n\t setp.ne.u32 r, %15, 0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t selp.u32 ad, ad, %9, r;\n\t"
+            "red.shared.add.u32 [ad], %10;\n\t setp.gt.and.f32 r, %2, %7, r;\n\t or.pred q, q, r;\n\t"
+            "mov.b32 k, w2;\n\t setp.ne.u32 r, %16, 0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t selp.u32 ad, ad, %9, r;\n\t"
+            "red.shared.add.u32 [ad], %10;\n\t setp.gt.and.f32 r, %3, %7, r;\n\t or.pred q, q, r;\n\t"
+            "mov.b32 k, w3;\n\t setp.ne.u32 r, %17, 0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t selp.u32 ad, ad, %9, r;\n\t"
+            "red.shared.add.u32 [ad], %10;\n\t setp.gt.and.f32 r, %4, %7, r;\n\t or.pred q, q, r;\n\t"
+            "selp.u32 %0, 1, 0, q;\n\t}"
+            : RX_OUT : RX_IN, "r"(ok[0]), "r"(ok[1]), "r"(ok[2]), "r"(ok[3]) : "memory");
+    } else {
+        asm volatile(RX_HEAD
+            "mov.b32 k, w0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], %10;\n\t"
+            "mov.b32 k, w1;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], %10;\n\t"
+            "mov.b32 k, w2;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], %10;\n\t"
+            "mov.b32 k, w3;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], %10;\n\t"
+            "setp.gt.f32 q, %1, %7;\n\t setp.gt.or.f32 q, %2, %7, q;\n\t setp.gt.or.f32 q, %3, %7, q;\n\t"
+            "setp.gt.or.f32 q, %4, %7, q;\n\t selp.u32 %0, 1, 0, q;\n\t}"
+            : RX_OUT : RX_IN : "memory");
+    }
+#undef RX_HEAD
+#undef RX_OUT
+#undef RX_IN
+    return any;
+}
+
+template <bool CHECK, bool CUBIC, bool EXCL, bool R0ZERO, bool CULL, bool EXT>
 __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, const uint32_t (&ux)[RF_IPT],
                                                 const uint32_t (&uy)[RF_IPT], const uint32_t (&uz)[RF_IPT],
                                                 const int (&bi)[RF_IPT], const FrameFast &ff, float thr, unsigned B,
@@ -969,7 +1044,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     const unsigned long long neg1 = pk2(-1.f, -1.f);
     // R0ZERO: bits(w) is used as it is; bits(MAGIC) = 0x4B400000 moves into the limit and the base address
     const unsigned blim = R0ZERO ? B + 0x4B400000u : B;
-    const unsigned hbase = R0ZERO ? hist_addr - 4u * 0x4B400000u : hist_addr;
+    const unsigned hbase = (R0ZERO || EXT) ? hist_addr - 4u * 0x4B400000u : hist_addr;
 #endif
     constexpr int RF_UNROLL = MDC_RF_UNROLL;
     auto row = [&](int j) {
@@ -990,12 +1065,16 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
         const unsigned long long v23 = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[2], uy[2], uz[2], ux[3], uy[3], uz[3], fax,
                                                         fay, faz, fc0);
         float adf[4];
-        if (bin_or_flag4<HAS_OK, R0ZERO, CULL>(v01, v23, magic, nmagic, neg1, thr, blim, hbase, trash_addr, one, ok, adf)) {
+        const unsigned any = EXT ? bin_count4<HAS_OK>(v01, v23, magic, nmagic, neg1, thr, hbase, trash_addr, one, ok, adf)
+                                 : bin_or_flag4<HAS_OK, R0ZERO, CULL>(v01, v23, magic, nmagic, neg1, thr, blim, hbase,
+                                                                      trash_addr, one, ok, adf);
+        if (any) {
             unsigned und = 0;   // cold: which of the four (without the gate: a far pair parked here resolves to no bin)
 #pragma unroll
             for (int u = 0; u < RF_IPT; ++u)
                 if (adf[u] > thr && ok[u]) und |= 1u << u;
-            park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
+            if (EXT) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, v01, v23, true);
+            else park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
         }
 #else
         float v[RF_IPT];
@@ -1035,9 +1114,11 @@ rdf_pairs_fast(RdfArgs A)
     unsigned *sh = reinterpret_cast<unsigned *>(sT + (A.n_bins + 1));
     const int B = A.n_bins;
     for (int i = threadIdx.x; i <= B; i += RF_THREADS) sT[i] = A.T[i];
-    for (int i = threadIdx.x; i < B * A.n_copies; i += RF_THREADS) sh[i] = 0u;
+    const int HS = A.ext_k > 0 ? A.ext_k : B;   // words per histogram copy
+    for (int i = threadIdx.x; i < HS * A.n_copies; i += RF_THREADS) sh[i] = 0u;
     if (threadIdx.x == 0) S->qcount = 0u;
-    unsigned *hist = sh + ((threadIdx.x >> 5) & (A.n_copies - 1)) * B;
+    unsigned *hist = sh + ((threadIdx.x >> 5) & (A.n_copies - 1)) * HS + A.ext_off;   // bin 0 of this warp's copy
+    const bool ext = A.ext_k > 0;
     const unsigned long long weight = A.sym ? 2ull : 1ull;
     const int64_t total = A.items_per_frame * A.F;
     int since_flush = 0;
@@ -1161,11 +1242,12 @@ rdf_pairs_fast(RdfArgs A)
             // the self pairs only, which a symmetric sweep (j > i) never evaluates
             excl = oa != nullptr ? !(A.sym && A.ex0 == 1 && A.ex1 == 1) : (ilo <= jhi && jlo <= ihi);
         }
-#define RF_CALL2(C, Q, E, Z, U) tile_pairs_fast<C, Q, E, Z, U>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist)
+#define RF_CALL2(C, Q, E, Z, U, X) tile_pairs_fast<C, Q, E, Z, U, X>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist)
 #define RF_CALL(C, Q, E)                                                                                              \
     do {                                                                                                              \
-        if (cull) { if (r0zero) RF_CALL2(C, Q, E, true, true); else RF_CALL2(C, Q, E, false, true); }                  \
-        else      { if (r0zero) RF_CALL2(C, Q, E, true, false); else RF_CALL2(C, Q, E, false, false); }                \
+        if (ext) { if (cull) RF_CALL2(C, Q, E, true, true, true); else RF_CALL2(C, Q, E, true, false, true); }         \
+        else if (cull) { if (r0zero) RF_CALL2(C, Q, E, true, true, false); else RF_CALL2(C, Q, E, false, true, false); } \
+        else { if (r0zero) RF_CALL2(C, Q, E, true, false, false); else RF_CALL2(C, Q, E, false, false, false); }        \
     } while (0)
         if (check) {
             if (ff.cubic) { if (excl) RF_CALL(true, true, true); else RF_CALL(true, true, false); }
@@ -1187,12 +1269,12 @@ rdf_pairs_fast(RdfArgs A)
         if (threadIdx.x == 0) S->qcount = 0u;
 
         if (++since_flush >= RF_FLUSH_ITEMS) {
-            flush_hist(sh, B, A.n_copies, weight, A.counts, true);
+            flush_hist(sh + A.ext_off, B, A.n_copies, weight, A.counts, true, HS);
             since_flush = 0;
         }
     }
     __syncthreads();
-    flush_hist(sh, B, A.n_copies, weight, A.counts, false);
+    flush_hist(sh + A.ext_off, B, A.n_copies, weight, A.counts, false, HS);
 }
 
 __global__ void rdf_add_const(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
@@ -1213,6 +1295,7 @@ struct mdc_rdf_plan {
     int force_exact = 0;        // testing / diagnostics: MDC_RDF_EXACT=1 in the environment
     int occ_fast = 1, occ_exact = 1;   // resident blocks per SM (persistent grids)
     int blocks_per_sm = 0;             // > 0: the filter kernel launches at most this many blocks per SM
+    int ext_cap = 0;                   // > 0: words per histogram copy the filter kernel's shared memory is sized for
     Thresholds th;
     DevBuf<double> T;
     DevBuf<unsigned long long> counts, ticket;
@@ -1359,6 +1442,16 @@ extern "C" int mdc_rdf_plan_create(mdc_ctx *ctx, int n_bins, double r0, double r
     while (copies_fast > 1 && fixed_fast + (size_t)copies_fast * n_bins * 4 > budget) copies_fast >>= 1;
     p->n_copies_fast = copies_fast;
     p->smem_fast = fixed_fast + (size_t)copies_fast * n_bins * 4;   // > budget: the filter kernel is not used
+    // extended histograms (RdfArgs::ext_k): as many words per copy as still leave MDC_RF_BLOCKS blocks per SM
+    {
+        const size_t per_block = ctx->smem_per_sm / MDC_RF_BLOCKS;
+        const size_t room = per_block > 1024 + fixed_fast ? per_block - 1024 - fixed_fast : 0;   // 1 KB reserved per block
+        const int cap = (int)std::min<size_t>(room / ((size_t)copies_fast * 4), 4096);
+        if (copies_fast == RF_THREADS / 32 && cap >= n_bins + 8 && fixed_fast + (size_t)copies_fast * cap * 4 <= budget) {
+            p->ext_cap = cap;
+            p->smem_fast = fixed_fast + (size_t)copies_fast * cap * 4;
+        }
+    }
     const char *env = getenv("MDC_RDF_EXACT");
     p->force_exact = (env && env[0] == '1') || p->smem_fast > budget;
 
@@ -1443,13 +1536,14 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         ++launches;
         // the filter kernel needs three periodic axes and a bin coordinate below 2^22 in every frame
         bool fast = !p->force_exact;
-        double max_len = 0.0;
+        double max_len = 0.0, v_far_max = 0.0;
         for (int f = 0; f < F && fast; ++f) {
             const FrameBox &fb = hb[f0 + f];
             const double S = (double)p->n_bins / (p->r1 - p->r0);
             const double v_far = 0.5 * sqrt(fb.box[0] * fb.box[0] + fb.box[1] * fb.box[1] + fb.box[2] * fb.box[2]) * S +
                                  fabs(p->r0 * S) + 1.0;
             fast = fb.pbc[0] && fb.pbc[1] && fb.pbc[2] && v_far < 4.0e6;
+            v_far_max = std::max(v_far_max, v_far);
             for (int k = 0; k < 3; ++k) max_len = std::max(max_len, fb.box[k]);
         }
         // Put every frame in Hilbert order of a cell grid, so that runs of consecutive particles are compact regions,
@@ -1503,6 +1597,17 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         A.b = p->same ? p->soa_a[slot].p : p->soa_b[slot].p;
         A.ua = p->fix_a[slot].p;
         A.ub = p->same ? p->fix_a[slot].p : p->fix_b[slot].p;
+        A.ext_k = A.ext_off = 0;
+        if (fast && p->ext_cap > 0) {
+            // bins the filter can produce: k >= -(r0 S) - 1 (d >= 0) and k <= v_far (half the box diagonal), with slack
+            const double S = (double)p->n_bins / (p->r1 - p->r0);
+            const double k_lo = -(std::ceil(std::fabs(p->r0 * S)) + 2.0), k_hi = std::ceil(v_far_max) + 1.0;
+            static const bool ext_off_env = getenv("MDC_RDF_EXT") && getenv("MDC_RDF_EXT")[0] == '0';
+            if (k_hi - k_lo + 1.0 <= (double)p->ext_cap && !ext_off_env) {
+                A.ext_k = p->ext_cap;
+                A.ext_off = (int)(-k_lo);
+            }
+        }
         A.oa = A.ob = nullptr;
         A.tbox_a = A.tbox_b = nullptr;
         A.cull_r = 0.0;
