@@ -16,7 +16,7 @@ frames and D2H of the step's results inside the timed region).  Frames shard acr
 every rank processes its own --frames per step); accumulators are all-reduced once at the end.
 
 Rooflines.  `roofline` describes the kernel with the largest share of the timed step: the g(r)
-pair kernel (issue-rate bound, ~24 issue slots per pair-distance).  S(q) on this grid runs as a gridding NUFFT
+pair kernel (issue-rate bound, 20 algorithmic issue slots per pair-distance).  S(q) on this grid runs as a gridding NUFFT
 (`roofline_sq`, HBM bound: fine grid + pruned FFT intermediates); the two O(Nq N) kernels it replaced are timed on
 one frame each and reported against their issue-rate rooflines measured on the box in this run
 (`roofline_sfu_direct`: 2 SFU ops per term, the contract kernel of BASELINE.json's north_star;
@@ -439,17 +439,22 @@ def run_native(args, rank, world, emit=print):
             "timed_kernel_ms_per_step": {"gr": gr_ms / args.steps, "sq": sq_ms / args.steps},
             "wall_s": wall,
         }
-        # g(r): the filter kernel issues 19.9 instructions per pair-distance (SASS: 159 per 8 pairs, profiles/rdf_fast_r01.txt);
-        # its ceiling is the issue rate, 4 schedulers x 32 lanes per SM per clock
-        gr_peak = sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 19.9
+        # g(r): SURVEY.md 8(d) fixes the algorithmic cost of one pair-distance at ~20 FP32/INT-pipe instructions (3 sub,
+        # 3 convert, r^2, sqrt, bin, range test, increment); the ceiling is the issue rate, 4 schedulers x 32 lanes per SM
+        # per clock, divided by that.  The kernel's own count is reported next to it and is NOT the denominator: it was
+        # 19.9 at the start of the round and is 15.1 in the hot loop now (SASS: 121 executed per 8 pairs), 17.8 per pair
+        # over the whole kernel with tile staging, culling tests and the undecided-pair path (ncu, profiles/).
+        SLOTS = 20.0
+        gr_peak = sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / SLOTS
         line["roofline_gr"] = {
             "bound": "issue", "kernel": "rdf_pairs_fast", "achieved": pairs / (gr_ms * 1e-3) / 1e9,
             "peak": gr_peak / 1e9, "unit": "G pair-distances/s", "frac": pairs / (gr_ms * 1e-3) / gr_peak,
             "frac_alone": 0.5 * N_PART * (N_PART - 1) * F / (gr_alone_ms * 1e-3) / gr_peak,
-            "traffic": 4.9e6, "peak_source": f"{sm} SMs x 4 schedulers x 32 lanes x SM clock / 19.9 issue slots per pair",
-            "algorithmic": "19.9 issue slots (FP32 arithmetic of two pairs per packed f32x2 instruction) + 1 SFU op (sqrt) + "
-                           "0.52 shared-memory atomics per pair; "
-                           "24 B of positions per particle per frame (f32 + u32 fixed point)",
+            "traffic": 3.1e6, "peak_source": f"{sm} SMs x 4 schedulers x 32 lanes x SM clock / {SLOTS:g} issue slots per pair "
+                                             "(SURVEY.md 8(d) algorithmic cost)",
+            "algorithmic": "20 FP32/INT issue slots + 1 SFU op (sqrt) + 1 shared-memory atomic per pair-distance "
+                           "(SURVEY.md 8(d)); 24 B of positions per particle per frame (f32 + u32 fixed point)",
+            "kernel_slots_per_pair": {"hot_loop_sass": 15.1, "whole_kernel_ncu": 17.8},
         }
         # the headline roofline: the kernel with the largest share of the step's WORK (device time of each analysis by
         # itself; side by side on two streams their durations overlap and stretch, so shares of the wall time do not

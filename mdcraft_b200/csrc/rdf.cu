@@ -1117,7 +1117,10 @@ rdf_pairs_fast(RdfArgs A)
     const int HS = A.ext_k > 0 ? A.ext_k : B;   // words per histogram copy
     for (int i = threadIdx.x; i < HS * A.n_copies; i += RF_THREADS) sh[i] = 0u;
     if (threadIdx.x == 0) S->qcount = 0u;
-    unsigned *hist = sh + ((threadIdx.x >> 5) & (A.n_copies - 1)) * HS + A.ext_off;   // bin 0 of this warp's copy
+    // Histogram copies are private to LANE groups, not to warps: bank conflicts and same-address serialisation only
+    // arise among the 32 lanes of one ATOMS instruction, and neighbouring lanes (neighbouring particles in a sorted
+    // frame, hence similar distances to the same j) are the ones that would collide.
+    unsigned *hist = sh + (threadIdx.x & (unsigned)(A.n_copies - 1)) * HS + A.ext_off;   // bin 0 of this lane's copy
     const bool ext = A.ext_k > 0;
     const unsigned long long weight = A.sym ? 2ull : 1ull;
     const int64_t total = A.items_per_frame * A.F;
@@ -1446,7 +1449,8 @@ extern "C" int mdc_rdf_plan_create(mdc_ctx *ctx, int n_bins, double r0, double r
     {
         const size_t per_block = ctx->smem_per_sm / MDC_RF_BLOCKS;
         const size_t room = per_block > 1024 + fixed_fast ? per_block - 1024 - fixed_fast : 0;   // 1 KB reserved per block
-        const int cap = (int)std::min<size_t>(room / ((size_t)copies_fast * 4), 4096);
+        int cap = (int)std::min<size_t>(room / ((size_t)copies_fast * 4), 4096);
+        if (cap > 36) cap -= (cap - 4) % 32;   // stride = 4 (mod 32) words: equal bins of the 8 copies sit in 8 different banks
         if (copies_fast == RF_THREADS / 32 && cap >= n_bins + 8 && fixed_fast + (size_t)copies_fast * cap * 4 <= budget) {
             p->ext_cap = cap;
             p->smem_fast = fixed_fast + (size_t)copies_fast * cap * 4;
