@@ -184,7 +184,9 @@ def test_rdf_npt_and_drop_axis_golden():
 
 
 @pytest.mark.parametrize("n,n_bins,frac", [(1, 8, 0.5), (2, 8, 0.5), (511, 33, 0.5), (512, 200, 0.5), (513, 200, 0.37),
-                                           (1025, 1000, 0.5), (3000, 200, 0.5), (2049, 4096, 0.45)])
+                                           (1025, 1000, 0.5), (3000, 200, 0.5), (2049, 4096, 0.45),
+                                           (4096, 200, 0.5), (4097, 64, 0.3), (5121, 300, 0.5), (6000, 3000, 0.2),
+                                           (12289, 200, 0.1)])
 def test_rdf_ragged_sizes_vs_oracle(n, n_bins, frac):
     """Tile-edge sizes (tiles are 512 x 512), tiny systems, many bins."""
     from oracle import oracle
@@ -203,6 +205,32 @@ def test_rdf_ragged_sizes_vs_oracle(n, n_bins, frac):
         want = oracle.rdf(list(pos[:, :na]), list(pos[:, na:]), [dims] * 2, n_bins, rng_)
         r = _rdf(u.select(0, na), u.select(na, n), n_bins=n_bins, range_=rng_)
         np.testing.assert_array_equal(r.results.counts, want["counts"])
+
+
+@pytest.mark.parametrize("window,n_bins,excl", [((0.0, 0.5), 200, None), ((0.9, 0.5), 200, (1, 1)), ((2.5, 0.31), 77, (3, 3)),
+                                                 ((0.2, 0.12), 500, None), ((0.05, 0.5), 1500, (2, 2))])
+def test_rdf_sorted_frames_windows_and_changing_boxes(window, n_bins, excl):
+    """Frames above the sort threshold (4096 particles): Hilbert-ordered frames, culling, extended histograms (or
+    the range-tested loop where the bin range does not fit), windows that start above zero, a box that changes a
+    lot from frame to frame, non-cubic boxes; self and cross g(r) with one group below the threshold."""
+    from oracle import oracle
+
+    rng = np.random.default_rng(77)
+    n, F = 5000, 3
+    dims = np.array([[17.0, 17.0, 17.0, 90, 90, 90], [19.5, 16.0, 21.0, 90, 90, 90], [14.0, 15.0, 14.5, 90, 90, 90]], np.float32)
+    pos = (rng.random((F, n, 3)) * dims[:, None, :3]).astype(np.float32)
+    pos[:, ::7] += dims[:, None, :3] * rng.integers(-2, 3, (F, len(range(0, n, 7)), 3))   # unwrapped particles
+    pos = pos.astype(np.float32)
+    r0, frac = window
+    rng_ = (r0, float(dims[:, :3].min()) * frac) if frac * dims[:, :3].min() > r0 else (r0, r0 + 3.0)
+    want = oracle.rdf(list(pos), None, list(dims), n_bins, rng_, exclusion=excl)
+    u = universe_from(pos, dims)
+    r = _rdf(u.atoms, n_bins=n_bins, range_=rng_, exclusion=excl)
+    np.testing.assert_array_equal(r.results.counts, want["counts"])
+    na = 4200
+    want = oracle.rdf(list(pos[:, :na]), list(pos[:, na:]), list(dims), n_bins, rng_, exclusion=excl)
+    r = _rdf(u.select(0, na), u.select(na, n), n_bins=n_bins, range_=rng_, exclusion=excl)
+    np.testing.assert_array_equal(r.results.counts, want["counts"])
 
 
 def test_rdf_adversarial_edge_distances():
