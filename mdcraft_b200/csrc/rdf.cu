@@ -633,73 +633,12 @@ __device__ __noinline__ void park_row(const TileCtx *Tp, unsigned *queue, unsign
     }
 }
 
-// One pair of the hot loop after v is known: bins it if v is clear of every bin edge, otherwise reports it
-// undecided.  Written in PTX to keep it branch free: a pair that is not to be counted increments a per-thread
-// dummy word instead of being branched around.
+// The hot loop after v is known: a pair is binned if v is clear of every bin edge, otherwise reported undecided.
+// Written in PTX to keep it branch free (bin_or_flag4 / bin_count4 below):
 //   w = v + MAGIC;  k = bits(w) - bits(MAGIC) = rint(v);  undecided = |v - (w - MAGIC)| > thr
-//   hist[(ok && !undecided && k < B) ? k : dummy] += 1;        returns (ok && undecided) ? BIT : 0
-template <unsigned BIT, bool HAS_OK>
-__device__ __forceinline__ unsigned bin_or_flag(float v, float thr, unsigned B, unsigned hist_addr, unsigned trash_addr,
-                                                unsigned ok, unsigned one)
-{
-    unsigned und;
-    if (HAS_OK) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p, q, r;\n\t"
-            ".reg .f32 w, kf, df;\n\t"
-            ".reg .u32 k, ad;\n\t"
-            "add.f32 w, %1, 0f4B400000;\n\t"
-            "sub.f32 kf, w, 0f4B400000;\n\t"
-            "sub.f32 df, %1, kf;\n\t"
-            "abs.f32 df, df;\n\t"
-            "mov.b32 k, w;\n\t"
-            "sub.u32 k, k, 0x4B400000;\n\t"
-            "setp.ne.u32 r, %6, 0;\n\t"
-            "setp.gt.and.f32 q, df, %2, r;\n\t"
-            "setp.lt.and.u32 p, k, %3, r;\n\t"
-            "and.pred p, p, !q;\n\t"
-            "shl.b32 ad, k, 2;\n\t"
-            "add.u32 ad, ad, %4;\n\t"
-            "selp.u32 ad, ad, %5, p;\n\t"
-            "red.shared.add.u32 [ad], %7;\n\t"
-            "selp.u32 %0, %8, 0, q;\n\t"
-            "}"
-            : "=r"(und)
-            : "f"(v), "f"(thr), "r"(B), "r"(hist_addr), "r"(trash_addr), "r"(ok), "r"(one), "n"(BIT)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p, q;\n\t"
-            ".reg .f32 w, kf, df;\n\t"
-            ".reg .u32 k, ad;\n\t"
-            "add.f32 w, %1, 0f4B400000;\n\t"
-            "sub.f32 kf, w, 0f4B400000;\n\t"
-            "sub.f32 df, %1, kf;\n\t"
-            "abs.f32 df, df;\n\t"
-            "mov.b32 k, w;\n\t"
-            "sub.u32 k, k, 0x4B400000;\n\t"
-            "setp.gt.f32 q, df, %2;\n\t"
-            "setp.lt.and.u32 p, k, %3, !q;\n\t"
-            "shl.b32 ad, k, 2;\n\t"
-            "add.u32 ad, ad, %4;\n\t"
-            "selp.u32 ad, ad, %5, p;\n\t"
-            "red.shared.add.u32 [ad], %6;\n\t"
-            "selp.u32 %0, %7, 0, q;\n\t"
-            "}"
-            : "=r"(und)
-            : "f"(v), "f"(thr), "r"(B), "r"(hist_addr), "r"(trash_addr), "r"(one), "n"(BIT)
-            : "memory");
-    }
-    return und;
-}
 
 #ifndef MDC_RF_UNROLL
 #define MDC_RF_UNROLL 2   // rows of j per loop iteration
-#endif
-#ifndef MDC_RDF_PACKED
-#define MDC_RDF_PACKED 1   // 1: the FP32 arithmetic of two pairs rides in one packed (f32x2) instruction
 #endif
 
 __device__ __forceinline__ unsigned long long pk2(float lo, float hi)
@@ -741,98 +680,6 @@ __device__ __forceinline__ unsigned long long filter_v2(uint32_t ujx, uint32_t u
         asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(d), "l"(fc0));
     }
     return v;
-}
-
-// bin_or_flag for two pairs whose v arrive packed: w = v + MAGIC, kf = w - MAGIC, df = v - kf as three packed
-// instructions, then the integer / predicate tail per pair as in bin_or_flag
-template <unsigned BIT0, unsigned BIT1, bool HAS_OK>
-__device__ __forceinline__ unsigned bin_or_flag2(unsigned long long v, unsigned long long magic, unsigned long long nmagic,
-                                                 unsigned long long neg1, float thr, unsigned B, unsigned hist_addr,
-                                                 unsigned trash_addr, unsigned ok0, unsigned ok1, unsigned one)
-{
-    unsigned und;
-    if (HAS_OK) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p, q, r;\n\t"
-            ".reg .b64 W, KF, DF;\n\t"
-            ".reg .f32 w0, w1, d0, d1;\n\t"
-            ".reg .u32 k, ad, u0, u1;\n\t"
-            "add.rn.f32x2 W, %1, %2;\n\t"
-            "add.rn.f32x2 KF, W, %3;\n\t"
-            "fma.rn.f32x2 DF, KF, %4, %1;\n\t"
-            "mov.b64 {w0, w1}, W;\n\t"
-            "mov.b64 {d0, d1}, DF;\n\t"
-            "abs.f32 d0, d0;\n\t"
-            "mov.b32 k, w0;\n\t"
-            "sub.u32 k, k, 0x4B400000;\n\t"
-            "setp.ne.u32 r, %9, 0;\n\t"
-            "setp.gt.and.f32 q, d0, %5, r;\n\t"
-            "setp.lt.and.u32 p, k, %6, r;\n\t"
-            "and.pred p, p, !q;\n\t"
-            "shl.b32 ad, k, 2;\n\t"
-            "add.u32 ad, ad, %7;\n\t"
-            "selp.u32 ad, ad, %8, p;\n\t"
-            "red.shared.add.u32 [ad], %11;\n\t"
-            "selp.u32 u0, %12, 0, q;\n\t"
-            "abs.f32 d1, d1;\n\t"
-            "mov.b32 k, w1;\n\t"
-            "sub.u32 k, k, 0x4B400000;\n\t"
-            "setp.ne.u32 r, %10, 0;\n\t"
-            "setp.gt.and.f32 q, d1, %5, r;\n\t"
-            "setp.lt.and.u32 p, k, %6, r;\n\t"
-            "and.pred p, p, !q;\n\t"
-            "shl.b32 ad, k, 2;\n\t"
-            "add.u32 ad, ad, %7;\n\t"
-            "selp.u32 ad, ad, %8, p;\n\t"
-            "red.shared.add.u32 [ad], %11;\n\t"
-            "selp.u32 u1, %13, 0, q;\n\t"
-            "or.b32 %0, u0, u1;\n\t"
-            "}"
-            : "=r"(und)
-            : "l"(v), "l"(magic), "l"(nmagic), "l"(neg1), "f"(thr), "r"(B), "r"(hist_addr), "r"(trash_addr), "r"(ok0),
-              "r"(ok1), "r"(one), "n"(BIT0), "n"(BIT1)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p, q;\n\t"
-            ".reg .b64 W, KF, DF;\n\t"
-            ".reg .f32 w0, w1, d0, d1;\n\t"
-            ".reg .u32 k, ad, u0, u1;\n\t"
-            "add.rn.f32x2 W, %1, %2;\n\t"
-            "add.rn.f32x2 KF, W, %3;\n\t"
-            "fma.rn.f32x2 DF, KF, %4, %1;\n\t"
-            "mov.b64 {w0, w1}, W;\n\t"
-            "mov.b64 {d0, d1}, DF;\n\t"
-            "abs.f32 d0, d0;\n\t"
-            "mov.b32 k, w0;\n\t"
-            "sub.u32 k, k, 0x4B400000;\n\t"
-            "setp.gt.f32 q, d0, %5;\n\t"
-            "setp.lt.and.u32 p, k, %6, !q;\n\t"
-            "shl.b32 ad, k, 2;\n\t"
-            "add.u32 ad, ad, %7;\n\t"
-            "selp.u32 ad, ad, %8, p;\n\t"
-            "red.shared.add.u32 [ad], %9;\n\t"
-            "selp.u32 u0, %10, 0, q;\n\t"
-            "abs.f32 d1, d1;\n\t"
-            "mov.b32 k, w1;\n\t"
-            "sub.u32 k, k, 0x4B400000;\n\t"
-            "setp.gt.f32 q, d1, %5;\n\t"
-            "setp.lt.and.u32 p, k, %6, !q;\n\t"
-            "shl.b32 ad, k, 2;\n\t"
-            "add.u32 ad, ad, %7;\n\t"
-            "selp.u32 ad, ad, %8, p;\n\t"
-            "red.shared.add.u32 [ad], %9;\n\t"
-            "selp.u32 u1, %11, 0, q;\n\t"
-            "or.b32 %0, u0, u1;\n\t"
-            "}"
-            : "=r"(und)
-            : "l"(v), "l"(magic), "l"(nmagic), "l"(neg1), "f"(thr), "r"(B), "r"(hist_addr), "r"(trash_addr), "r"(one),
-              "n"(BIT0), "n"(BIT1)
-            : "memory");
-    }
-    return und;
 }
 
 // bin_or_flag for the four pairs of one row (two packed v's): the round-to-bin chain as six packed instructions,
@@ -1037,7 +884,6 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     const unsigned one = (unsigned)Tp->A.sym | 1u;
     constexpr bool HAS_OK = CHECK || EXCL;
     static_assert(RF_IPT == 4, "the undecided-pair mask is built for four particles per thread");
-#if MDC_RDF_PACKED
     const unsigned long long fax = pk2(ff.ax, ff.ax), fay = pk2(ff.ay, ff.ay), faz = pk2(ff.az, ff.az);
     const unsigned long long fc0 = pk2(ff.c0, ff.c0);
     const unsigned long long magic = pk2(12582912.f, 12582912.f), nmagic = pk2(-12582912.f, -12582912.f);
@@ -1045,7 +891,6 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     // R0ZERO: bits(w) is used as it is; bits(MAGIC) = 0x4B400000 moves into the limit and the base address
     const unsigned blim = R0ZERO ? B + 0x4B400000u : B;
     const unsigned hbase = (R0ZERO || EXT) ? hist_addr - 4u * 0x4B400000u : hist_addr;
-#endif
     constexpr int RF_UNROLL = MDC_RF_UNROLL;
     auto row = [&](int j) {
         const uint4 pj = S->sj[j];
@@ -1059,7 +904,6 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                 ok[u] = ok[u] && (ig < na) && (!diag || (j0 + j) > ig);
             }
         }
-#if MDC_RDF_PACKED
         const unsigned long long v01 = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[0], uy[0], uz[0], ux[1], uy[1], uz[1], fax,
                                                         fay, faz, fc0);
         const unsigned long long v23 = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[2], uy[2], uz[2], ux[3], uy[3], uz[3], fax,
@@ -1076,16 +920,6 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
             if (EXT) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, v01, v23, true);
             else park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
         }
-#else
-        float v[RF_IPT];
-#pragma unroll
-        for (int u = 0; u < RF_IPT; ++u) v[u] = filter_v<CUBIC>(pj.x, pj.y, pj.z, ux[u], uy[u], uz[u], ff);
-        const unsigned und = bin_or_flag<1u, HAS_OK>(v[0], thr, B, hist_addr, trash_addr, ok[0], one) |
-                             bin_or_flag<2u, HAS_OK>(v[1], thr, B, hist_addr, trash_addr, ok[1], one) |
-                             bin_or_flag<4u, HAS_OK>(v[2], thr, B, hist_addr, trash_addr, ok[2], one) |
-                             bin_or_flag<8u, HAS_OK>(v[3], thr, B, hist_addr, trash_addr, ok[3], one);
-        if (und) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
-#endif
     };
     if (CULL) {
         // sorted frames: this warp's 128 particles against chunks of 32 rows; chunks out of reach are skipped
@@ -1126,25 +960,18 @@ rdf_pairs_fast(RdfArgs A)
     const int64_t total = A.items_per_frame * A.F;
     int since_flush = 0;
 
-#ifndef MDC_RF_DYNAMIC
-#define MDC_RF_DYNAMIC 1   // 1: tile pairs are drawn from a global ticket counter, so no block idles while another
-#endif                     //    still has a whole tile pair queued (static striding leaves up to one item of tail)
-#if MDC_RF_DYNAMIC
+    // Tile pairs are drawn from a global ticket counter, so that no block idles while another still has a whole
+    // tile pair queued (static striding left up to one item of tail: 11 % of the kernel at N = 1e5).
     __shared__ unsigned long long s_ticket;
     for (;;) {
         if (threadIdx.x == 0) s_ticket = atomicAdd(A.ticket, 1ull);
         __syncthreads();
         const int64_t item = (int64_t)s_ticket;
         if (item >= total) break;
-#else
-    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
-#endif
         int f, I, J;
         bool diag;
         if (!decode_item(A, item, f, I, J, diag)) {
-#if MDC_RF_DYNAMIC
             __syncthreads();   // every thread has read the ticket before thread 0 draws the next one
-#endif
             continue;
         }
         const FrameFast ff = A.fast[f];
@@ -1152,9 +979,7 @@ rdf_pairs_fast(RdfArgs A)
         if (A.tbox_a) {   // sorted frames: skip tile pairs that lie farther apart than the cutoff (same for all threads)
             const uint32_t *ta = A.tbox_a + ((int64_t)f * A.nti + I) * 6, *tb = A.tbox_b + ((int64_t)f * A.ntj + J) * 6;
             if (tile_gap2(ta, tb, fb) > A.cull_r * A.cull_r) {
-#if MDC_RF_DYNAMIC
                 __syncthreads();
-#endif
                 continue;
             }
         }
