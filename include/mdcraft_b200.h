@@ -226,6 +226,10 @@ int  mdc_rdf_plan_destroy(mdc_rdf_plan *plan);
  * (n_frames, n_b, 3) or NULL when same_group; box f32 (n_frames, 6)
  * [lx, ly, lz, alpha, beta, gamma] (host memory always).  Only orthorhombic
  * boxes (90/90/90) are supported: MDC_ERR_UNSUPPORTED otherwise.
+ * Groups of 4096 particles or more are put in Hilbert order of a cell grid on the device first, and the pair kernel
+ * skips the blocks of pairs farther apart than r1 (what capped_distance's grid search does for the reference,
+ * structure.py:109-115); counts do not depend on it.  Environment, for diagnostics: MDC_RDF_SORT=0 keeps the original
+ * order, MDC_RDF_EXT=0 the range-tested histogram update, MDC_RDF_EXACT=1 the all-FP64 kernel.
  */
 int  mdc_rdf_push(mdc_rdf_plan *plan, const float *pos_a, const float *pos_b,
                   const float *box, int n_frames, int on_device);
