@@ -544,8 +544,9 @@ struct FastShared {
     unsigned trash[RF_THREADS]; // per-thread dummy target of the branch-free histogram increment
     unsigned char ctx[384];     // TileCtx of the tile in flight (cold passes read it from here)
     // sorted frames only: bounding boxes {lo x, lo y, lo z, -, hi x, hi y, hi z, -} (32-bit box fractions) of the 128
-    // particles i of every warp and of every chunk of 32 rows j, and {L_k / 2^32 (k = x, y, z), cull_r^2}
-    uint4 ibox[RF_THREADS / 32][2];
+    // particles i of every warp (followed by the box's centre and half extents) and of every chunk of 32 rows j, and
+    // {L_k / 2^32 (k = x, y, z), cull_r^2}
+    uint4 ibox[RF_THREADS / 32][4];   // + {centre x, y, z, -}, {half extent x, y, z, -}
     uint4 jbox[RF_TJ / 32][2];
     float cull[4];
 };
@@ -557,7 +558,7 @@ __device__ __forceinline__ int rf_il(int u) { return (int)(threadIdx.x & ~31u) *
 // sorted frames: is every particle of box a farther than the cutoff from every particle of box b (minimum image)?
 // Warp-uniform.  Per axis the gap between two intervals on the 2^32 circle that do not overlap is the smaller of the
 // two wrapped differences.
-__device__ __forceinline__ bool boxes_apart(const uint4 (&a)[2], const uint4 (&b)[2], const float (&c)[4])
+__device__ __forceinline__ bool boxes_apart(const uint4 *a, const uint4 *b, const float (&c)[4])
 {
     auto gap = [](uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi) -> float {
         const bool overlap = blo <= ahi && alo <= bhi;
@@ -567,6 +568,25 @@ __device__ __forceinline__ bool boxes_apart(const uint4 (&a)[2], const uint4 (&b
     const float gy = gap(a[0].y, a[1].y, b[0].y, b[1].y) * c[1];
     const float gz = gap(a[0].z, a[1].z, b[0].z, b[1].z) * c[2];
     return fmaf(gz, gz, fmaf(gy, gy, gx * gx)) > c[3];
+}
+
+// sorted frames: which of the 32 rows j of a chunk (one row per lane) have ANY of this warp's 128 particles within the
+// cutoff?  Gap between the point and the warp's box per axis: the wrapped difference to the box centre is the
+// nearest image, minus the half extent.  Returns the ballot; the tests of 32 rows cost what one would.
+__device__ __forceinline__ unsigned rows_in_reach(const FastShared *S, const uint4 *ib, int c, int nj)
+{
+    const int j = c + (int)(threadIdx.x & 31u);
+    const uint4 pj = S->sj[min(j, nj - 1)];
+    const uint4 ctr = ib[2], hf = ib[3];
+    auto gap = [](uint32_t u, uint32_t centre, uint32_t half) -> float {
+        const unsigned ad = (unsigned)abs((int)(u - centre));
+        return (float)max((int)(ad - half), 0);
+    };
+    const float gx = gap(pj.x, ctr.x, hf.x) * S->cull[0];
+    const float gy = gap(pj.y, ctr.y, hf.y) * S->cull[1];
+    const float gz = gap(pj.z, ctr.z, hf.z) * S->cull[2];
+    const bool in = j < nj && fmaf(gz, gz, fmaf(gy, gy, gx * gx)) <= S->cull[3];
+    return __ballot_sync(0xffffffffu, in);
 }
 
 // The filter's FP32 bin coordinate of one pair: v = bin coordinate - 0.5 (so that rint(v) is the bin).
@@ -923,12 +943,22 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     };
     if (CULL) {
         // sorted frames: this warp's 128 particles against chunks of 32 rows; chunks out of reach are skipped
-        const uint4 (&ib)[2] = S->ibox[threadIdx.x >> 5];
+        const uint4 *ib = S->ibox[threadIdx.x >> 5];
         for (int c = 0; c < nj; c += 32) {
             if (boxes_apart(ib, S->jbox[c >> 5], S->cull)) continue;
-            const int je = min(nj, c + 32);
+            // then row by row (one test per lane): only the rows within reach of the warp's box are evaluated
+            unsigned m = rows_in_reach(S, ib, c, nj);
+            if (__popc(m) >= 29) {   // (nearly) all of them: the plain loop has less overhead per row than the bit walk
+                const int je = min(nj, c + 32);
 #pragma unroll RF_UNROLL
-            for (int j = c; j < je; ++j) row(j);
+                for (int j = c; j < je; ++j) row(j);
+                continue;
+            }
+            while (m) {
+                const int j = c + __ffs((int)m) - 1;
+                m &= m - 1u;
+                row(j);
+            }
         }
     } else {
 #pragma unroll RF_UNROLL
@@ -1039,6 +1069,11 @@ rdf_pairs_fast(RdfArgs A)
             if ((threadIdx.x & 31u) == 0u) {
                 S->ibox[threadIdx.x >> 5][0] = lo;
                 S->ibox[threadIdx.x >> 5][1] = hi;
+                // centre (rounded down) and half extent (rounded up, + 1): |u - centre| <= half for every u in the box
+                const uint4 hf = make_uint4(((hi.x - lo.x) >> 1) + 1u, ((hi.y - lo.y) >> 1) + 1u, ((hi.z - lo.z) >> 1) + 1u, 0u);
+                S->ibox[threadIdx.x >> 5][2] = make_uint4(lo.x + ((hi.x - lo.x) >> 1), lo.y + ((hi.y - lo.y) >> 1),
+                                                          lo.z + ((hi.z - lo.z) >> 1), 0u);
+                S->ibox[threadIdx.x >> 5][3] = hf;
             }
             if (threadIdx.x < 3) S->cull[threadIdx.x] = (float)(fb.box[threadIdx.x] * (1.0 / 4294967296.0));
             if (threadIdx.x == 3) S->cull[3] = (float)(A.cull_r * A.cull_r);
