@@ -301,7 +301,7 @@ int      mdc_dump_read(mdc_dump *dump, mdc_ctx *ctx, int64_t f0, int n_frames, f
 
 /*
  * Replaces the read side of /root/reference/src/mdcraft/openmm/file.py:22-306 (NetCDFFile.get_num_frames,
- * get_num_atoms, get_dimensions, get_times, get_positions), which goes through netCDF4, for NetCDF-3 classic and
+ * get_num_atoms, get_dimensions, get_times, get_positions, get_velocities, get_forces), which goes through netCDF4, for NetCDF-3 classic and
  * 64-bit-offset files (what that class writes, file.py:52-54) following the AMBER trajectory convention.
  * mdc_ncdf_open memory-maps the file and parses the header on the host.  mdc_ncdf_read sends the big-endian
  * coordinates of frames [f0, f0 + n_frames) to HBM with one strided copy and byte-swaps them there into float32
@@ -314,6 +314,16 @@ int  mdc_ncdf_close(mdc_ncdf *file);
 int  mdc_ncdf_info(mdc_ncdf *file, int64_t info[4]);
 int  mdc_ncdf_headers(mdc_ncdf *file, double *times, double *cell_lengths, double *cell_angles);
 int  mdc_ncdf_read(mdc_ncdf *file, mdc_ctx *ctx, int64_t f0, int n_frames, float *pos_out, int on_device);
+/*
+ * The other per-atom record variables of the convention, same layout and same path as the coordinates
+ * (file.py:217-306, get_velocities / get_forces): which = MDC_NCDF_COORDINATES, _VELOCITIES (angstrom / ps as stored)
+ * or _FORCES (kcal / mol / angstrom).  mdc_ncdf_has returns 1 if the file holds the variable, else 0.
+ */
+#define MDC_NCDF_COORDINATES 0
+#define MDC_NCDF_VELOCITIES  1
+#define MDC_NCDF_FORCES      2
+int  mdc_ncdf_has(mdc_ncdf *file, int which);
+int  mdc_ncdf_read_var(mdc_ncdf *file, mdc_ctx *ctx, int which, int64_t f0, int n_frames, float *out, int on_device);
 
 /* ---- 1-D density profiles ------------------------- */
 

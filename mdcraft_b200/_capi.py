@@ -125,6 +125,8 @@ SIGNATURES = {
     "mdc_ncdf_info": (c_int, [c_void_p, _lp]),
     "mdc_ncdf_headers": (c_int, [c_void_p, _dp, _dp, _dp]),
     "mdc_ncdf_read": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int]),
+    "mdc_ncdf_has": (c_int, [c_void_p, c_int]),
+    "mdc_ncdf_read_var": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int]),
     "mdc_sq_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_rdf_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_probe_rate": (c_int, [c_void_p, c_int, _dp]),
@@ -558,6 +560,8 @@ class DumpFile:
 class NcdfFile:
     """``mdc_ncdf``: a memory-mapped AMBER NetCDF-3 trajectory whose coordinates are byte-swapped on the GPU."""
 
+    VARIABLES = {"coordinates": 0, "velocities": 1, "forces": 2}   # MDC_NCDF_*
+
     def __init__(self, path: str):
         self._h = c_void_p()
         _check(lib().mdc_ncdf_open(os.fsencode(path), byref(self._h)))
@@ -565,6 +569,8 @@ class NcdfFile:
         _check(lib().mdc_ncdf_info(self._h, info))
         self.n_frames, self.n_atoms = int(info[0]), int(info[1])
         self.has_box, self.has_time = bool(info[2]), bool(info[3])
+        self.has_velocities = bool(lib().mdc_ncdf_has(self._h, self.VARIABLES["velocities"]))
+        self.has_forces = bool(lib().mdc_ncdf_has(self._h, self.VARIABLES["forces"]))
         self.times = np.empty(self.n_frames, dtype=np.float64) if self.has_time else None
         self.cell_lengths = np.empty((self.n_frames, 3), dtype=np.float64) if self.has_box else None
         self.cell_angles = np.empty((self.n_frames, 3), dtype=np.float64) if self.has_box else None
@@ -584,9 +590,9 @@ class NcdfFile:
         except Exception:
             pass
 
-    def read(self, ctx: "Context", f0: int, n_frames: int, out=None):
-        """Coordinates of frames ``[f0, f0 + n_frames)`` as float32 ``(n_frames, n_atoms, 3)``; ``out``: a host array
-        or a device buffer to fill."""
+    def read(self, ctx: "Context", f0: int, n_frames: int, out=None, variable: str = "coordinates"):
+        """Coordinates (or ``variable="velocities"`` / ``"forces"``) of frames ``[f0, f0 + n_frames)`` as float32
+        ``(n_frames, n_atoms, 3)``; ``out``: a host array or a device buffer to fill."""
         if out is None:
             out = np.empty((int(n_frames), self.n_atoms, 3), dtype=np.float32)
         ptr, on_dev, keep = _buffer(out)
@@ -594,7 +600,7 @@ class NcdfFile:
             raise ValueError("out must be a C-contiguous float32 array")
         if int(np.prod(keep.shape)) != int(n_frames) * self.n_atoms * 3:
             raise ValueError(f"out must hold {n_frames} x {self.n_atoms} x 3 elements")
-        _check(lib().mdc_ncdf_read(self._h, ctx._h, int(f0), int(n_frames), ptr, on_dev))
+        _check(lib().mdc_ncdf_read_var(self._h, ctx._h, self.VARIABLES[variable], int(f0), int(n_frames), ptr, on_dev))
         return out
 
 

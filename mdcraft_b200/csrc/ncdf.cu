@@ -121,8 +121,8 @@ struct mdc_ncdf {
     const unsigned char *data = nullptr;
     size_t size = 0;
     int64_t n_frames = 0, n_atoms = 0, recsize = 0;
-    Var coords, lengths, angles, time;
-    bool has_box = false, has_time = false;
+    Var coords, lengths, angles, time, velocities, forces;
+    bool has_box = false, has_time = false, has_velocities = false, has_forces = false;
     std::string conventions;
     DevBuf<uint32_t> stage;
     DevBuf<float> out;
@@ -234,10 +234,22 @@ extern "C" int mdc_ncdf_open(const char *path, mdc_ncdf **out)
     d->has_box = find("cell_lengths", &d->lengths) && find("cell_angles", &d->angles) && d->lengths.type == NC_DOUBLE &&
                  d->angles.type == NC_DOUBLE && d->lengths.record && d->angles.record;
     d->has_time = find("time", &d->time) && d->time.type == NC_FLOAT && d->time.record;
+    // optional per-atom vectors with the layout of the coordinates (file.py:217-306: get_velocities, get_forces)
+    auto per_atom = [&](const char *nm, Var *dst) {
+        return find(nm, dst) && dst->type == NC_FLOAT && dst->record && dst->dimids.size() == 3 &&
+               dim_sizes[dst->dimids[1]] == d->n_atoms && dim_sizes[dst->dimids[2]] == 3;
+    };
+    d->has_velocities = per_atom("velocities", &d->velocities);
+    d->has_forces = per_atom("forces", &d->forces);
     d->n_frames = numrecs;
     if (numrecs == 0xffffffffu && d->recsize > 0) d->n_frames = ((int64_t)d->size - d->coords.begin + d->recsize - d->n_atoms * 12) / d->recsize;
     if (d->n_frames > 0 && d->coords.begin + (d->n_frames - 1) * d->recsize + d->n_atoms * 12 > (int64_t)d->size)
         return ncdf_fail(d, MDC_ERR_INVALID, "mdc_ncdf_open: file is shorter than its record count");
+    for (Var *v : {&d->velocities, &d->forces}) {
+        const bool present = v == &d->velocities ? d->has_velocities : d->has_forces;
+        if (present && d->n_frames > 0 && v->begin + (d->n_frames - 1) * d->recsize + d->n_atoms * 12 > (int64_t)d->size)
+            return ncdf_fail(d, MDC_ERR_INVALID, "mdc_ncdf_open: file is shorter than its record count");
+    }
     *out = d;
     return MDC_OK;
 }
@@ -278,9 +290,24 @@ extern "C" int mdc_ncdf_headers(mdc_ncdf *d, double *times, double *cell_lengths
     return MDC_OK;
 }
 
+extern "C" int mdc_ncdf_has(mdc_ncdf *d, int which)
+{
+    if (!d) return 0;
+    return which == MDC_NCDF_COORDINATES ? 1 : which == MDC_NCDF_VELOCITIES ? (int)d->has_velocities
+                                             : which == MDC_NCDF_FORCES   ? (int)d->has_forces : 0;
+}
+
 extern "C" int mdc_ncdf_read(mdc_ncdf *d, mdc_ctx *ctx, int64_t f0, int n_frames, float *pos_out, int on_device)
 {
+    return mdc_ncdf_read_var(d, ctx, MDC_NCDF_COORDINATES, f0, n_frames, pos_out, on_device);
+}
+
+extern "C" int mdc_ncdf_read_var(mdc_ncdf *d, mdc_ctx *ctx, int which, int64_t f0, int n_frames, float *pos_out,
+                                 int on_device)
+{
     if (!d || !ctx || !pos_out) return fail(MDC_ERR_INVALID, "mdc_ncdf_read: NULL argument");
+    if (!mdc_ncdf_has(d, which)) return fail(MDC_ERR_INVALID, "mdc_ncdf_read_var: the file does not hold that variable");
+    const Var &var = which == MDC_NCDF_VELOCITIES ? d->velocities : which == MDC_NCDF_FORCES ? d->forces : d->coords;
     if (f0 < 0 || n_frames <= 0 || f0 + n_frames > d->n_frames) return fail(MDC_ERR_INVALID, "mdc_ncdf_read: frame range out of bounds");
     MDC_CUDA(cudaSetDevice(ctx->device));
     if (!d->stream || d->stream_device != ctx->device) {
@@ -299,7 +326,7 @@ extern "C" int mdc_ncdf_read(mdc_ncdf *d, mdc_ctx *ctx, int64_t f0, int n_frames
         out_dev = d->out.p;
     }
     // one strided copy: the coordinates of consecutive records are recsize bytes apart in the file
-    MDC_CUDA(cudaMemcpy2DAsync(d->stage.p, row, d->data + d->coords.begin + f0 * d->recsize, (size_t)d->recsize, row,
+    MDC_CUDA(cudaMemcpy2DAsync(d->stage.p, row, d->data + var.begin + f0 * d->recsize, (size_t)d->recsize, row,
                                (size_t)n_frames, cudaMemcpyHostToDevice, st));
     ncdf_bswap32<<<(unsigned)ceil_div(words, 256), 256, 0, st>>>(d->stage.p, words, reinterpret_cast<uint32_t *>(out_dev));
     MDC_CUDA(cudaGetLastError());

@@ -16,6 +16,7 @@ the reference; pass ``units=False`` where OpenMM is not installed.
 
 from __future__ import annotations
 
+import warnings
 from typing import Optional, Union
 
 import numpy as np
@@ -95,6 +96,25 @@ class NetCDFFile:
     def get_positions(self, frames=None, units: bool = True, device: bool = False):
         """``file.py:180-215``: float32 ``(n, n_atoms, 3)`` (``(n_atoms, 3)`` for one frame).  ``device=True``: a CUDA
         ``torch`` tensor that never visits the host (``units`` must be False)."""
+        return self._per_atom("coordinates", frames, units, device, lambda u: u.angstrom)
+
+    def get_velocities(self, frames=None, units: bool = True, device: bool = False):
+        """``file.py:217-261``: float32 velocities in angstrom / ps, ``None`` (with the reference's warning) if the
+        file holds none."""
+        if not self._nc.has_velocities:
+            warnings.warn("The NetCDF file does not contain information about the atom velocities.")
+            return None
+        return self._per_atom("velocities", frames, units, device, lambda u: u.angstrom / u.picosecond)
+
+    def get_forces(self, frames=None, units: bool = True, device: bool = False):
+        """``file.py:263-306``: float32 forces in kcal / mol / angstrom, ``None`` (with the reference's warning) if
+        the file holds none."""
+        if not self._nc.has_forces:
+            warnings.warn("The NetCDF file does not contain information about the forces acting on the atoms.")
+            return None
+        return self._per_atom("forces", frames, units, device, lambda u: u.kilocalorie_per_mole / u.angstrom)
+
+    def _per_atom(self, variable: str, frames, units: bool, device: bool, unit_of):
         idx, scalar = _frame_list(frames, self._nc.n_frames)
         runs = np.split(idx, np.flatnonzero(np.diff(idx) != 1) + 1) if idx.size else []
         n_atoms = self._nc.n_atoms
@@ -108,11 +128,11 @@ class NetCDFFile:
             out = np.empty((idx.size, n_atoms, 3), dtype=np.float32)
         at = 0
         for run in runs:   # consecutive frames go through one strided copy + one kernel
-            self._nc.read(self._ctx, int(run[0]), run.size, out=out[at:at + run.size])
+            self._nc.read(self._ctx, int(run[0]), run.size, out=out[at:at + run.size], variable=variable)
             at += run.size
         if scalar:
             out = out[0]
-        return out * _unit().angstrom if units else out
+        return out * unit_of(_unit()) if units else out
 
 
 class NetCDFTrajectory(MemoryTrajectory):

@@ -578,7 +578,7 @@ def density_profile_counts(frames: Iterable[np.ndarray], group_sizes, axes, n_bi
 
 
 def write_amber_netcdf(path: str, positions, times, cell_lengths=None, cell_angles=None, version: int = 2,
-                       velocities=None) -> None:
+                       velocities=None, forces=None) -> None:
     """Test helper: an AMBER-convention NetCDF-3 trajectory (what NetCDFFile.write_header lays out,
     openmm/file.py:309-531) written with SciPy; version 2 = 64-bit offsets, the format the reference uses."""
     from scipy.io import netcdf_file
@@ -601,6 +601,8 @@ def write_amber_netcdf(path: str, positions, times, cell_lengths=None, cell_angl
         v_ang = f.createVariable("cell_angles", "d", ("frame", "cell_angular"))
     if velocities is not None:
         v_vel = f.createVariable("velocities", "f", ("frame", "atom", "spatial"))
+    if forces is not None:
+        v_frc = f.createVariable("forces", "f", ("frame", "atom", "spatial"))
     for i in range(F):
         v_time[i] = times[i]
         v_pos[i] = positions[i]
@@ -609,6 +611,8 @@ def write_amber_netcdf(path: str, positions, times, cell_lengths=None, cell_angl
             v_ang[i] = cell_angles[i]
         if velocities is not None:
             v_vel[i] = velocities[i]
+        if forces is not None:
+            v_frc[i] = forces[i]
     f.close()
 
 

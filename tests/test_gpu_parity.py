@@ -829,7 +829,8 @@ def test_netcdf_reader_vs_scipy(tmp_path):
     lengths, angles = np.full((F, 3), L), np.full((F, 3), 90.0)
     for version, vel in ((2, True), (1, False)):
         path = str(tmp_path / f"traj{version}.nc")
-        oracle.write_amber_netcdf(path, pos, times, lengths, angles, version=version, velocities=pos + 1 if vel else None)
+        oracle.write_amber_netcdf(path, pos, times, lengths, angles, version=version, velocities=pos + 1 if vel else None,
+                                  forces=-2 * pos if vel else None)
         want, want_t, want_l, want_a = oracle.read_amber_netcdf(path)
         f = NetCDFFile(path)
         assert (f.get_num_frames(), f.get_num_atoms()) == (F, N)
@@ -843,6 +844,15 @@ def test_netcdf_reader_vs_scipy(tmp_path):
         np.testing.assert_array_equal(got_l, want_l)
         np.testing.assert_array_equal(got_a, want_a)
         np.testing.assert_array_equal(f.get_dimensions(-1, units=False)[0], want_l[-1])
+        if vel:   # the other per-atom record variables (file.py:217-306) take the same path
+            np.testing.assert_array_equal(f.get_velocities(units=False)[:, 10:], (pos + 1)[:, 10:])
+            np.testing.assert_array_equal(f.get_forces([0, 8], units=False)[:, 10:], (-2 * pos)[[0, 8]][:, 10:])
+            np.testing.assert_array_equal(f.get_forces(5, units=False, device=True).cpu().numpy(), (-2 * pos)[5])
+        else:
+            with pytest.warns(UserWarning, match="velocities"):
+                assert f.get_velocities(units=False) is None
+            with pytest.warns(UserWarning, match="forces"):
+                assert f.get_forces(units=False) is None
         f.close()
     pos[0, :4, 0] = 1.0
     path = str(tmp_path / "clean.nc")
