@@ -644,6 +644,9 @@ __device__ __noinline__ void park_row(const TileCtx *Tp, unsigned *queue, unsign
             const unsigned long long vv = u < 2 ? v01 : v23;
             const float v = __uint_as_float((unsigned)((u & 1) ? (vv >> 32) : (vv & 0xffffffffull)));
             const int k = (int)(__float_as_uint(__fadd_rn(v, 12582912.f)) - 0x4B400000u);
+            // rint(v) beyond B (or below -1): |v_ref - v| < 0.5 puts the pair outside the window whatever the rounding;
+            // it sits in a word that is never read back and needs no FP64 pass (40 % of the flagged pairs at L/2)
+            if (k > Tp->A.n_bins || k < -1) continue;
             atomicSub(&hist[k], 1u);
         }
         const int il = rf_il(u);
