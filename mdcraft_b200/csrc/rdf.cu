@@ -880,10 +880,10 @@ __device__ __forceinline__ unsigned bin_count4(unsigned long long v01, unsigned 
             : RX_OUT : RX_IN, "r"(ok[0]), "r"(ok[1]), "r"(ok[2]), "r"(ok[3]) : "memory");
     } else {
         asm volatile(RX_HEAD
-            "mov.b32 k, w0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], %10;\n\t"
-            "mov.b32 k, w1;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], %10;\n\t"
-            "mov.b32 k, w2;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], %10;\n\t"
-            "mov.b32 k, w3;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], %10;\n\t"
+            "mov.b32 k, w0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w1;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w2;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w3;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], 1;\n\t"
             "setp.gt.f32 q, %1, %7;\n\t setp.gt.or.f32 q, %2, %7, q;\n\t setp.gt.or.f32 q, %3, %7, q;\n\t"
             "setp.gt.or.f32 q, %4, %7, q;\n\t selp.u32 %0, 1, 0, q;\n\t}"
             : RX_OUT : RX_IN : "memory");
