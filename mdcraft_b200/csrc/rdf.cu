@@ -546,7 +546,7 @@ struct FastShared {
     // sorted frames only: bounding boxes {lo x, lo y, lo z, -, hi x, hi y, hi z, -} (32-bit box fractions) of the 128
     // particles i of every warp (followed by the box's centre and half extents) and of every chunk of 32 rows j, and
     // {L_k / 2^32 (k = x, y, z), cull_r^2}
-    uint4 ibox[RF_THREADS / 32][4];   // + {centre x, y, z, -}, {half extent x, y, z, -}
+    uint4 ibox[RF_THREADS / 32][8];   // + {centre}, {half extent} of the box, of its first 64 and of its last 64 particles
     uint4 jbox[RF_TJ / 32][2];
     float cull[4];
 };
@@ -573,11 +573,11 @@ __device__ __forceinline__ bool boxes_apart(const uint4 *a, const uint4 *b, cons
 // sorted frames: which of the 32 rows j of a chunk (one row per lane) have ANY of this warp's 128 particles within the
 // cutoff?  Gap between the point and the warp's box per axis: the wrapped difference to the box centre is the
 // nearest image, minus the half extent.  Returns the ballot; the tests of 32 rows cost what one would.
-__device__ __forceinline__ unsigned rows_in_reach(const FastShared *S, const uint4 *ib, int c, int nj)
+__device__ __forceinline__ unsigned rows_in_reach(const FastShared *S, const uint4 *ch, int c, int nj)
 {
     const int j = c + (int)(threadIdx.x & 31u);
     const uint4 pj = S->sj[min(j, nj - 1)];
-    const uint4 ctr = ib[2], hf = ib[3];
+    const uint4 ctr = ch[0], hf = ch[1];   // {centre, half extent}
     auto gap = [](uint32_t u, uint32_t centre, uint32_t half) -> float {
         const unsigned ad = (unsigned)abs((int)(u - centre));
         return (float)max((int)(ad - half), 0);
@@ -894,6 +894,34 @@ __device__ __forceinline__ unsigned bin_count4(unsigned long long v01, unsigned 
     return any;
 }
 
+// bin_count4 for half a row: the two pairs of one packed v (extended histograms, no ok flags)
+__device__ __forceinline__ unsigned bin_count2(unsigned long long v, unsigned long long magic, unsigned long long nmagic,
+                                               unsigned long long neg1, float thr, unsigned hbase, float (&adf)[2])
+{
+    unsigned any;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        ".reg .b64 W, KF, DF;\n\t"
+        ".reg .f32 w0, w1;\n\t"
+        ".reg .u32 k, ad;\n\t"
+        "add.rn.f32x2 W, %3, %6;\n\t"
+        "add.rn.f32x2 KF, W, %7;\n\t"
+        "fma.rn.f32x2 DF, KF, %8, %3;\n\t"
+        "mov.b64 {w0, w1}, W;\n\t"
+        "mov.b64 {%1, %2}, DF;\n\t"
+        "abs.f32 %1, %1;\n\t"
+        "abs.f32 %2, %2;\n\t"
+        "mov.b32 k, w0;\n\t mad.lo.u32 ad, k, 4, %5;\n\t red.shared.add.u32 [ad], 1;\n\t"
+        "mov.b32 k, w1;\n\t mad.lo.u32 ad, k, 4, %5;\n\t red.shared.add.u32 [ad], 1;\n\t"
+        "setp.gt.f32 q, %1, %4;\n\t setp.gt.or.f32 q, %2, %4, q;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(any), "=f"(adf[0]), "=f"(adf[1])
+        : "l"(v), "f"(thr), "r"(hbase), "l"(magic), "l"(nmagic), "l"(neg1)
+        : "memory");
+    return any;
+}
+
 template <bool CHECK, bool CUBIC, bool EXCL, bool R0ZERO, bool CULL, bool EXT>
 __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, const uint32_t (&ux)[RF_IPT],
                                                 const uint32_t (&uy)[RF_IPT], const uint32_t (&uz)[RF_IPT],
@@ -944,24 +972,56 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
             else park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
         }
     };
+    // half a row: the pairs of particles (2 H, 2 H + 1) only (extended histograms, tiles without ok flags)
+    auto half_row = [&](int j, int H) {
+        const uint4 pj = S->sj[j];
+        const int a = 2 * H, b = 2 * H + 1;
+        const unsigned long long v = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[a], uy[a], uz[a], ux[b], uy[b], uz[b], fax, fay,
+                                                      faz, fc0);
+        float adf[2];
+        if (bin_count2(v, magic, nmagic, neg1, thr, hbase, adf)) {
+            unsigned und = 0;
+            if (adf[0] > thr) und |= 1u << a;
+            if (adf[1] > thr) und |= 1u << b;
+            park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, v, v, true);   // park_row picks v01 / v23 by u
+        }
+    };
+    auto walk = [&](unsigned m, int c, auto &&body) {
+        while (m) {
+            const int j = c + __ffs((int)m) - 1;
+            m &= m - 1u;
+            body(j);
+        }
+    };
     if (CULL) {
         // sorted frames: this warp's 128 particles against chunks of 32 rows; chunks out of reach are skipped
         const uint4 *ib = S->ibox[threadIdx.x >> 5];
         for (int c = 0; c < nj; c += 32) {
             if (boxes_apart(ib, S->jbox[c >> 5], S->cull)) continue;
             // then row by row (one test per lane): only the rows within reach of the warp's box are evaluated
-            unsigned m = rows_in_reach(S, ib, c, nj);
+            if (EXT && !HAS_OK) {
+                // ... and half row by half row: the warp's first and last 64 particles have boxes of their own
+                const unsigned ma = rows_in_reach(S, ib + 4, c, nj), mb = rows_in_reach(S, ib + 6, c, nj);
+                const unsigned both = ma & mb;
+                if (__popc(both) >= 29) {   // (nearly) all rows in full: the plain loop has less overhead per row
+                    const int je = min(nj, c + 32);
+#pragma unroll RF_UNROLL
+                    for (int j = c; j < je; ++j) row(j);
+                    continue;
+                }
+                walk(both, c, [&](int j) { row(j); });
+                walk(ma & ~mb, c, [&](int j) { half_row(j, 0); });
+                walk(mb & ~ma, c, [&](int j) { half_row(j, 1); });
+                continue;
+            }
+            unsigned m = rows_in_reach(S, ib + 2, c, nj);
             if (__popc(m) >= 29) {   // (nearly) all of them: the plain loop has less overhead per row than the bit walk
                 const int je = min(nj, c + 32);
 #pragma unroll RF_UNROLL
                 for (int j = c; j < je; ++j) row(j);
                 continue;
             }
-            while (m) {
-                const int j = c + __ffs((int)m) - 1;
-                m &= m - 1u;
-                row(j);
-            }
+            walk(m, c, [&](int j) { row(j); });
         }
     } else {
 #pragma unroll RF_UNROLL
@@ -1058,25 +1118,30 @@ rdf_pairs_fast(RdfArgs A)
             }
         }
         if (cull) {
-            uint32_t lx = ux[0], ly = uy[0], lz = uz[0], hx = ux[0], hy = uy[0], hz = uz[0];
+            // bounding boxes of the warp's first 64 particles (u = 0, 1), of its last 64 (u = 2, 3) and of all 128
+            uint4 lo2[2], hi2[2];
 #pragma unroll
-            for (int u = 1; u < RF_IPT; ++u) {
-                lx = min(lx, ux[u]); hx = max(hx, ux[u]);
-                ly = min(ly, uy[u]); hy = max(hy, uy[u]);
-                lz = min(lz, uz[u]); hz = max(hz, uz[u]);
+            for (int h = 0; h < 2; ++h) {
+                const int a = 2 * h, b = 2 * h + 1;
+                lo2[h] = make_uint4(__reduce_min_sync(0xffffffffu, min(ux[a], ux[b])), __reduce_min_sync(0xffffffffu, min(uy[a], uy[b])),
+                                    __reduce_min_sync(0xffffffffu, min(uz[a], uz[b])), 0u);
+                hi2[h] = make_uint4(__reduce_max_sync(0xffffffffu, max(ux[a], ux[b])), __reduce_max_sync(0xffffffffu, max(uy[a], uy[b])),
+                                    __reduce_max_sync(0xffffffffu, max(uz[a], uz[b])), 0u);
             }
-            const uint4 lo = make_uint4(__reduce_min_sync(0xffffffffu, lx), __reduce_min_sync(0xffffffffu, ly),
-                                        __reduce_min_sync(0xffffffffu, lz), 0u);
-            const uint4 hi = make_uint4(__reduce_max_sync(0xffffffffu, hx), __reduce_max_sync(0xffffffffu, hy),
-                                        __reduce_max_sync(0xffffffffu, hz), 0u);
             if ((threadIdx.x & 31u) == 0u) {
-                S->ibox[threadIdx.x >> 5][0] = lo;
-                S->ibox[threadIdx.x >> 5][1] = hi;
+                uint4 *ib = S->ibox[threadIdx.x >> 5];
+                const uint4 lo = make_uint4(min(lo2[0].x, lo2[1].x), min(lo2[0].y, lo2[1].y), min(lo2[0].z, lo2[1].z), 0u);
+                const uint4 hi = make_uint4(max(hi2[0].x, hi2[1].x), max(hi2[0].y, hi2[1].y), max(hi2[0].z, hi2[1].z), 0u);
+                ib[0] = lo;
+                ib[1] = hi;
                 // centre (rounded down) and half extent (rounded up, + 1): |u - centre| <= half for every u in the box
-                const uint4 hf = make_uint4(((hi.x - lo.x) >> 1) + 1u, ((hi.y - lo.y) >> 1) + 1u, ((hi.z - lo.z) >> 1) + 1u, 0u);
-                S->ibox[threadIdx.x >> 5][2] = make_uint4(lo.x + ((hi.x - lo.x) >> 1), lo.y + ((hi.y - lo.y) >> 1),
-                                                          lo.z + ((hi.z - lo.z) >> 1), 0u);
-                S->ibox[threadIdx.x >> 5][3] = hf;
+                auto centre_half = [](const uint4 &l, const uint4 &h, uint4 *out) {
+                    out[0] = make_uint4(l.x + ((h.x - l.x) >> 1), l.y + ((h.y - l.y) >> 1), l.z + ((h.z - l.z) >> 1), 0u);
+                    out[1] = make_uint4(((h.x - l.x) >> 1) + 1u, ((h.y - l.y) >> 1) + 1u, ((h.z - l.z) >> 1) + 1u, 0u);
+                };
+                centre_half(lo, hi, ib + 2);
+                centre_half(lo2[0], hi2[0], ib + 4);
+                centre_half(lo2[1], hi2[1], ib + 6);
             }
             if (threadIdx.x < 3) S->cull[threadIdx.x] = (float)(fb.box[threadIdx.x] * (1.0 / 4294967296.0));
             if (threadIdx.x == 3) S->cull[3] = (float)(A.cull_r * A.cull_r);
