@@ -442,8 +442,8 @@ def run_native(args, rank, world, emit=print):
         # g(r): SURVEY.md 8(d) fixes the algorithmic cost of one pair-distance at ~20 FP32/INT-pipe instructions (3 sub,
         # 3 convert, r^2, sqrt, bin, range test, increment); the ceiling is the issue rate, 4 schedulers x 32 lanes per SM
         # per clock, divided by that.  The kernel's own count is reported next to it and is NOT the denominator: it was
-        # 19.9 at the start of the round and is 15.1 in the hot loop now (SASS: 121 executed per 8 pairs), 16.2 per
-        # algorithmic pair over the whole kernel (tile staging, culling tests, undecided-pair path; 12 % of the pairs are
+        # 19.9 at the start of the round and is 15.1 in the hot loop now (SASS: 121 executed per 8 pairs), 15.6 per
+        # algorithmic pair over the whole kernel (tile staging, culling tests, undecided-pair path; 19 % of the pairs are
         # culled and never evaluated; ncu, profiles/rdf_fast_r01.txt).
         SLOTS = 20.0
         gr_peak = sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / SLOTS
@@ -455,7 +455,7 @@ def run_native(args, rank, world, emit=print):
                                              "(SURVEY.md 8(d) algorithmic cost)",
             "algorithmic": "20 FP32/INT issue slots + 1 SFU op (sqrt) + 1 shared-memory atomic per pair-distance "
                            "(SURVEY.md 8(d)); 24 B of positions per particle per frame (f32 + u32 fixed point)",
-            "kernel_slots_per_pair": {"hot_loop_sass": 15.1, "whole_kernel_ncu_per_algorithmic_pair": 16.2},
+            "kernel_slots_per_pair": {"hot_loop_sass": 15.1, "whole_kernel_ncu_per_algorithmic_pair": 15.6},
         }
         # the headline roofline: the kernel with the largest share of the step's WORK (device time of each analysis by
         # itself; side by side on two streams their durations overlap and stretch, so shares of the wall time do not
