@@ -137,6 +137,12 @@ int  mdc_sq_wavevectors(mdc_sq_plan *plan, double *q_out);
  * respect to the device; synchronous with respect to the host buffer.
  */
 int  mdc_sq_push(mdc_sq_plan *plan, const float *pos, int n_frames, int on_device);
+/*
+ * The same with f64 positions (n_frames, N, 3).  structure.py:1943-1944 gathers the groups into a float64
+ * buffer: atom positions are float32 values widened, but centres of mass (groupings="residues",
+ * algorithm/molecule.py:16-441) are genuine float64 and q . r is evaluated on them in FP64.
+ */
+int  mdc_sq_push_f64(mdc_sq_plan *plan, const double *pos, int n_frames, int on_device);
 
 /* Un-normalised sums f64 (n_pairs, Nq) and the number of frames pushed. */
 int  mdc_sq_read(mdc_sq_plan *plan, double *ssf_out, int64_t *n_frames_out);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "mdc_sq_wavevectors": (c_int, [c_void_p, _dp]),
     "mdc_sq_plan_info": (c_int, [c_void_p, _ip]),
     "mdc_sq_push": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "mdc_sq_push_f64": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "mdc_sq_read": (c_int, [c_void_p, _dp, _lp]),
     "mdc_sq_set_shells": (c_int, [c_void_p, _lp, c_int64, _lp, _lp, c_int64]),
     "mdc_sq_read_shells": (c_int, [c_void_p, c_double, _dp, _lp]),
@@ -194,6 +195,14 @@ def _buffer(x, dtype=np.float32):
         return c_void_p(cai["data"][0]), 1, x
     a = np.ascontiguousarray(x, dtype=dtype)
     return c_void_p(a.ctypes.data), 0, a
+
+
+def _dtype_of(x):
+    """NumPy dtype of a host array or of a ``__cuda_array_interface__`` buffer (``None`` if unknown)."""
+    if isinstance(x, np.ndarray):
+        return x.dtype
+    cai = getattr(x, "__cuda_array_interface__", None)
+    return np.dtype(cai["typestr"]) if cai else None
 
 
 class Context:
@@ -374,15 +383,16 @@ class SqPlan:
         return out
 
     def push(self, pos, n_frames: Optional[int] = None) -> None:
-        """``pos``: float32 ``(F, N, 3)`` (or ``(N, 3)``), host array or device buffer."""
-        ptr, on_dev, keep = _buffer(pos)
+        """``pos``: float32 (or float64: centres of mass) ``(F, N, 3)`` (or ``(N, 3)``), host array or device buffer."""
+        f64 = _dtype_of(pos) == np.float64
+        ptr, on_dev, keep = _buffer(pos, np.float64 if f64 else np.float32)
         shape = keep.shape if hasattr(keep, "shape") else None
         if n_frames is None:
             n_frames = 1 if len(shape) == 2 else int(shape[0])
         n_el = int(np.prod(shape))
         if n_el != n_frames * self.n_particles * 3:
             raise ValueError(f"positions have {n_el} elements, expected {n_frames} x {self.n_particles} x 3")
-        _check(lib().mdc_sq_push(self._h, ptr, int(n_frames), on_dev))
+        _check((lib().mdc_sq_push_f64 if f64 else lib().mdc_sq_push)(self._h, ptr, int(n_frames), on_dev))
 
     def read(self, out: Optional[np.ndarray] = None):
         """Un-normalised sums ``(n_pairs, Nq)`` and the number of frames accumulated.  ``out``: optional
@@ -668,7 +678,10 @@ class IsfPlan(SqPlan):
         self.n_wavevectors = int(lib().mdc_sq_num_wavevectors(self._h))
 
     def push(self, pos, n_frames: Optional[int] = None) -> None:
-        """Frames must arrive in time order."""
+        """Frames must arrive in time order.  float32, or float64 (centres of mass: ``mdc_sq_push_f64``, which
+        serves ISF plans too)."""
+        if _dtype_of(pos) == np.float64:
+            return super().push(pos, n_frames)
         ptr, on_dev, keep = _buffer(pos)
         if n_frames is None:
             n_frames = 1 if len(keep.shape) == 2 else int(keep.shape[0])

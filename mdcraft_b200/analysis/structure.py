@@ -220,9 +220,11 @@ def calculate_structure_factor(
 
 
 class _FrameBlock:
-    """Host staging of up to ``capacity`` frames of float32 positions (pinned when torch has CUDA)."""
+    """Host staging of up to ``capacity`` frames of positions (pinned when torch has CUDA): float32 for atoms,
+    float64 when a group is reduced to centres of mass (the reference keeps those in float64,
+    ``structure.py:1943-1944``)."""
 
-    def __init__(self, capacity: int, n: int, pinned: bool = True):
+    def __init__(self, capacity: int, n: int, pinned: bool = True, dtype=np.float32):
         self.capacity, self.n, self.count = int(capacity), int(n), 0
         self._torch = None
         if pinned:
@@ -230,10 +232,11 @@ class _FrameBlock:
                 import torch
 
                 if torch.cuda.is_available():
-                    self._torch = torch.empty((self.capacity, self.n, 3), dtype=torch.float32, pin_memory=True)
+                    tdtype = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+                    self._torch = torch.empty((self.capacity, self.n, 3), dtype=tdtype, pin_memory=True)
             except Exception:  # pragma: no cover - torch is plumbing only
                 self._torch = None
-        self.array = self._torch.numpy() if self._torch is not None else np.empty((self.capacity, self.n, 3), np.float32)
+        self.array = self._torch.numpy() if self._torch is not None else np.empty((self.capacity, self.n, 3), dtype)
 
     def slot(self) -> np.ndarray:
         return self.array[self.count]
@@ -243,6 +246,18 @@ class _FrameBlock:
 
     def view(self) -> np.ndarray:
         return self.array[: self.count]
+
+
+def _sync_torch(device: int) -> None:
+    """
+    Orders torch's current stream before the library's own (non-blocking) streams: a device tensor produced by a
+    torch kernel (a slice made contiguous, a concatenation) is complete before ``mdc_*_push`` reads it, and memory
+    that torch's caching allocator has just handed out is no longer in use by earlier torch work before a reader
+    writes into it on its own stream.
+    """
+    import torch
+
+    torch.cuda.current_stream(device).synchronize()
 
 
 def _atom_range(group):
@@ -416,9 +431,11 @@ class RadialDistributionFunction(_DeviceBlockRun, DynamicAnalysisBase):
             slot_b = self._stage_b.slot()
             slot_b[:] = _entity_positions(self._groups[1], self._groupings[1])
 
+        # The reference adds the volume / area only when norm == "rdf" (structure.py:879-893) and then reads it in
+        # _get_rdf for every OTHER norm (structure.py:1024-1044), which yields an all-zero g(r) there; it is
+        # accumulated for every norm here (results.rdf / counts do not depend on it unless norm == "rdf").
         if self._drop_axis is None:
-            if self._norm == "rdf":
-                self._area_or_volume += self._ts.volume
+            self._area_or_volume += self._ts.volume
         else:
             # structure.py:887-893: flatten the dropped coordinate and make that box length
             # the largest one so that no periodic image is picked up along it
@@ -426,8 +443,7 @@ class RadialDistributionFunction(_DeviceBlockRun, DynamicAnalysisBase):
             if slot_b is not None:
                 slot_b[:, self._drop_axis] = 0
             dimensions[self._drop_axis] = dimensions[:3].max()
-            if self._norm == "rdf":
-                self._area_or_volume += np.delete(dimensions[:3], self._drop_axis).prod()
+            self._area_or_volume += np.delete(dimensions[:3], self._drop_axis).prod()
 
         self._stage_box[self._stage_a.count] = dimensions
         self._stage_a.count += 1
@@ -451,9 +467,10 @@ class RadialDistributionFunction(_DeviceBlockRun, DynamicAnalysisBase):
         b = None
         if not self._same:
             b = block if (b_lo, b_hi) == (0, n_all) else block[:, b_lo:b_hi].contiguous()
-        if self._norm == "rdf":
-            for ts in timesteps:
-                self._area_or_volume += ts.volume
+        if a is not block or (b is not None and b is not block):
+            _sync_torch(self._device)   # the slices were written by torch kernels on torch's stream
+        for ts in timesteps:
+            self._area_or_volume += ts.volume
         self._plan.push(a, b, dims, n_frames=block.shape[0])
         self._frames_seen += block.shape[0]
 
@@ -757,11 +774,15 @@ class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
         self._wavenumbers = np.linalg.norm(self._wavevectors, axis=1)
         self._shells = None
 
+    def _stage_dtype(self):
+        """float32 positions of atoms are staged as they are; centres of mass keep their float64."""
+        return np.float32 if all(gr == "atoms" for gr in self._groupings) else np.float64
+
     # -- AnalysisBase protocol ------------------------------------------------
     def _prepare(self) -> None:
         self.results.pairs = self._pairs()
         self._plan.reset()
-        self._stage = _FrameBlock(self._frame_block, self._N)
+        self._stage = _FrameBlock(self._frame_block, self._N, dtype=self._stage_dtype())
         self._frames_seen = 0
         self.results.ssf = np.zeros((len(self.results.pairs), len(self._wavenumbers)))
         self.results.wavenumbers = np.unique(self._wavenumbers.round(11)) if self._unique else self._wavenumbers
@@ -791,6 +812,7 @@ class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
             import torch
 
             pos = torch.cat([block[:, lo:hi] for lo, hi in ranges], dim=1).contiguous()
+            _sync_torch(self._device)   # written by a torch kernel on torch's stream
         self._plan.push(pos, n_frames=block.shape[0])
         self._frames_seen += block.shape[0]
 
@@ -903,7 +925,7 @@ class IntermediateScatteringFunction(StructureFactor):
             n_points=n_points, L0=L0, q_max=self._q_max, wavevectors=explicit, precision=self._precision,
             algo=self._algorithm,
         )
-        self._stage = _FrameBlock(self._frame_block, self._N)
+        self._stage = _FrameBlock(self._frame_block, self._N, dtype=self._stage_dtype())
         self._frames_seen = 0
         self.results.times = df * self._dt * np.arange(self._n_lags)
         self.results.wavenumbers = np.unique(self._wavenumbers.round(11)) if self._unique else self._wavenumbers

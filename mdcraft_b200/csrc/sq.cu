@@ -94,14 +94,15 @@ __global__ void lat_fill(int n, double Lx, double Ly, double Lz, const int *cnt,
 // layout kernels
 // ------------------------------------------------------------------------------------------
 
-// raw f32 (F, N, 3) -> fix u32 (F, 3, N): frac(x / L0) * 2^32, rounded to nearest (wraps mod 2^32)
-__global__ void prep_fix(const float *__restrict__ raw, int64_t N, int64_t total, double iLx, double iLy,
+// raw f32 / f64 (F, N, 3) -> fix u32 (F, 3, N): frac(x / L0) * 2^32, rounded to nearest (wraps mod 2^32)
+template <typename T>
+__global__ void prep_fix(const T *__restrict__ raw, int64_t N, int64_t total, double iLx, double iLy,
                          double iLz, uint32_t *__restrict__ fix)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int64_t f = i / N, j = i - f * N;
-    const float *p = raw + 3 * i;
+    const T *p = raw + 3 * i;
     const double inv[3] = {iLx, iLy, iLz};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -111,8 +112,9 @@ __global__ void prep_fix(const float *__restrict__ raw, int64_t N, int64_t total
     }
 }
 
-// raw f32 (F, N, 3) -> posd f64 (F, 3, N)
-__global__ void prep_f64(const float *__restrict__ raw, int64_t N, int64_t total, double *__restrict__ posd)
+// raw f32 / f64 (F, N, 3) -> posd f64 (F, 3, N)
+template <typename T>
+__global__ void prep_f64(const T *__restrict__ raw, int64_t N, int64_t total, double *__restrict__ posd)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -821,6 +823,7 @@ struct mdc_sq_plan {
     DevBuf<double> shell_out;
     int64_t n_shells = 0;
     DevBuf<float> raw[2];
+    DevBuf<double> raw64[2];                           // staging of mdc_sq_push_f64 (allocated on first use)
     DevBuf<uint32_t> fix[2];
     DevBuf<int2> d_sets, d_pairs;
     std::vector<int2> sets;
@@ -867,6 +870,7 @@ void plan_free(mdc_sq_plan *p)
     for (int i = 0; i < 2; ++i) {
         p->posd[i].release();
         p->raw[i].release();
+        p->raw64[i].release();
         p->fix[i].release();
         p->tabx[i].release();
         p->taby[i].release();
@@ -1346,13 +1350,14 @@ int isf_frame(mdc_sq_plan *p, int slot, int *launches)
     return MDC_OK;
 }
 
-int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launches)
+template <typename T>
+int launch_block(mdc_sq_plan *p, const T *raw, int F, int slot, int *launches)
 {
     cudaStream_t sc = p->st.copy, sk = p->st.compute;
     const int64_t total = (int64_t)F * p->N;
     const int pb = (int)ceil_div(total, 256);
     if (p->lattice_fast) {
-        prep_fix<<<pb, 256, 0, sc>>>(raw, p->N, total, 1.0 / p->L0[0], 1.0 / p->L0[1], 1.0 / p->L0[2], p->fix[slot].p);
+        prep_fix<T><<<pb, 256, 0, sc>>>(raw, p->N, total, 1.0 / p->L0[0], 1.0 / p->L0[1], 1.0 / p->L0[2], p->fix[slot].p);
         ++*launches;
     }
     if (p->factored) {
@@ -1361,7 +1366,7 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
         ++*launches;
     }
     if (!p->lattice_fast || p->n_exp > 0) {
-        prep_f64<<<pb, 256, 0, sc>>>(raw, p->N, total, p->posd[slot].p);
+        prep_f64<T><<<pb, 256, 0, sc>>>(raw, p->N, total, p->posd[slot].p);
         ++*launches;
     }
     MDC_CUDA(cudaGetLastError());
@@ -1398,7 +1403,10 @@ int launch_block(mdc_sq_plan *p, const float *raw, int F, int slot, int *launche
 
 }  // namespace
 
-extern "C" int mdc_sq_push(mdc_sq_plan *p, const float *pos, int n_frames, int on_device)
+namespace {
+
+template <typename T>
+int sq_push_impl(mdc_sq_plan *p, const T *pos, int n_frames, int on_device, DevBuf<T> (&stage)[2])
 {
     if (!p || !pos) return fail(MDC_ERR_INVALID, "mdc_sq_push: NULL argument");
     if (n_frames <= 0) return MDC_OK;
@@ -1415,20 +1423,36 @@ extern "C" int mdc_sq_push(mdc_sq_plan *p, const float *pos, int n_frames, int o
         // the slot's layout buffers (and `part`, shared by both slots through stream order on
         // `compute`) may still be read by the kernels of two blocks ago
         if (p->st.used[slot]) MDC_CUDA(cudaStreamWaitEvent(p->st.copy, p->st.consumed[slot], 0));
-        const float *src = pos + (size_t)f0 * p->N * 3;
-        const float *raw = src;
+        const T *src = pos + (size_t)f0 * p->N * 3;
+        const T *raw = src;
         if (!on_device) {
-            MDC_CUDA(cudaMemcpyAsync(p->raw[slot].p, src, (size_t)F * p->N * 3 * sizeof(float),
-                                     cudaMemcpyHostToDevice, p->st.copy));
-            raw = p->raw[slot].p;
+            MDC_CHECK(stage[slot].alloc((size_t)p->fblk * p->N * 3));
+            MDC_CUDA(cudaMemcpyAsync(stage[slot].p, src, (size_t)F * p->N * 3 * sizeof(T), cudaMemcpyHostToDevice,
+                                     p->st.copy));
+            raw = stage[slot].p;
         }
-        MDC_CHECK(launch_block(p, raw, F, slot, &launches));
+        MDC_CHECK(launch_block<T>(p, raw, F, slot, &launches));
     }
     // the caller may reuse `pos` on return: wait for the copies / layout kernels (not the analysis kernels)
     MDC_CUDA(cudaStreamSynchronize(p->st.copy));
     p->n_frames += n_frames;
     p->last_launches = launches;
     return MDC_OK;
+}
+
+}  // namespace
+
+extern "C" int mdc_sq_push(mdc_sq_plan *p, const float *pos, int n_frames, int on_device)
+{
+    if (!p) return fail(MDC_ERR_INVALID, "mdc_sq_push: NULL argument");
+    return sq_push_impl<float>(p, pos, n_frames, on_device, p->raw);
+}
+
+// float64 positions (centres of mass of residues: structure.py:1943-1944 keeps them in a float64 buffer)
+extern "C" int mdc_sq_push_f64(mdc_sq_plan *p, const double *pos, int n_frames, int on_device)
+{
+    if (!p) return fail(MDC_ERR_INVALID, "mdc_sq_push_f64: NULL argument");
+    return sq_push_impl<double>(p, pos, n_frames, on_device, p->raw64);
 }
 
 extern "C" int mdc_sq_read(mdc_sq_plan *p, double *ssf_out, int64_t *n_frames_out)

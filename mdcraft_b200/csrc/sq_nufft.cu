@@ -563,9 +563,10 @@ int Nufft::init(const Ctx *ctx, int n_points, double eps_, int64_t max_set_len)
     smem_s = sizeof(double2) * ((size_t)nf + (size_t)NU_TC * (nf + nf / 8 + 1));
     if (smem_z > ctx->smem_optin || smem_s > ctx->smem_optin)
         return fail(MDC_ERR_UNSUPPORTED, "nufft: fine grid line does not fit shared memory");
-    MDC_CUDA(cudaFuncSetAttribute(nufft_fft_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z));
-    MDC_CUDA(cudaFuncSetAttribute(nufft_fft_s<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-    MDC_CUDA(cudaFuncSetAttribute(nufft_fft_s<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    // per-function attribute shared by every live plan (any fine grid): only ever the device maximum
+    MDC_CUDA(cudaFuncSetAttribute(nufft_fft_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    MDC_CUDA(cudaFuncSetAttribute(nufft_fft_s<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    MDC_CUDA(cudaFuncSetAttribute(nufft_fft_s<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     const char *env = getenv("MDC_NUFFT_SORT");
     sort = !(env && env[0] == '0');
     return MDC_OK;

@@ -58,11 +58,12 @@ def frame_block(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def shard_slice(trajectory_length: int, start=None, stop=None, step=None, rank: Optional[int] = None,
-                world: Optional[int] = None) -> Tuple[int, int, int]:
+                world: Optional[int] = None) -> Tuple[int, Optional[int], int]:
     """
     ``(start, stop, step)`` for this rank such that the ranks together visit
     exactly the frames of ``range(*slice(start, stop, step).indices(n))``, each
-    rank a contiguous run of them.
+    rank a contiguous run of them.  ``stop`` is ``None`` when a backward run ends
+    on frame 0 (a literal ``-1`` would be read as "the last frame").
     """
     if rank is None or world is None:
         rank, world = rank_and_world()
@@ -73,7 +74,9 @@ def shard_slice(trajectory_length: int, start=None, stop=None, step=None, rank: 
         return s0, s0, st   # empty
     first = frames[lo]
     last = frames[hi - 1]
-    return first, last + (1 if st > 0 else -1), st
+    if st > 0:
+        return first, last + 1, st
+    return first, (last - 1 if last > 0 else None), st
 
 
 def run_sharded(analysis, start=None, stop=None, step=None, **kwargs):

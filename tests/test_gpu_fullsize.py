@@ -99,7 +99,7 @@ def test_c4_binary_electrolyte_partials(ctx):
     tot.close()
 
 
-@pytest.mark.parametrize("algo,kappa", [("factored", 1e-7), ("direct", 5e-7)])
+@pytest.mark.parametrize("algo,kappa", [("factored", 1e-7), ("direct", 5e-7), ("nufft", 1e-8)])
 def test_c3_sq_full_size(ctx, algo, kappa):
     """C3: S(q) on 100,000 particles, default 32^3 grid: FP32 kernels against the FP64-mode kernel."""
     from mdcraft_b200 import _capi
@@ -124,8 +124,124 @@ def test_c3_sq_full_size(ctx, algo, kappa):
     plan.close()
     tol = 1e-5 * s64 + 2 * 5 * kappa * np.sqrt(s64) + 1e-12
     assert (np.abs(s32 - s64) <= tol).all(), float(np.max(np.abs(s32 - s64) / tol))
-    big = s64 > (0.01 if algo == "factored" else 0.25)
+    big = s64 > (0.25 if algo == "direct" else 0.01)
     assert np.max(np.abs(s32[big] / s64[big] - 1)) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_c3_full_grid_nufft_vs_oracle(ctx, precision):
+    """The HEADLINE S(q) configuration (bench.py): N = 100,000, n_points = 161, q_max = 20 (Nq = 2,140,871; NUFFT with
+    nf = 256, w = 12 / 16) against the CPU restatement of delta_fourier_transform_sum (structure.py:1240-1280) on 512
+    random wavevectors of the full grid, two frames: 1e-5 relative in FP32 mode, 1e-10 in FP64 mode."""
+    from mdcraft_b200 import _capi
+    from oracle import oracle
+
+    frames = np.stack([_frame("C3", frame=f)[0] for f in range(2)])
+    n, L = frames.shape[1], float(_frame("C3")[1][0])
+    plan = _capi.SqPlan(ctx, [n], [(None, None)], n_points=161, L0=[L] * 3, q_max=20.0, algo="nufft", precision=precision)
+    info = plan.info()
+    assert plan.n_wavevectors == 2_140_871 and info["algo"] == "nufft" and info["nf"] == 256
+    assert info["w"] == (12 if precision == "fp32" else 16)
+    wv = plan.wavevectors()
+    plan.push(frames)
+    got, nfr = plan.read()
+    plan.close()
+    assert nfr == 2
+    # the grid itself is the reference's (structure.py:1822-1887), order included
+    want_wv, _ = oracle.wavevector_grid(np.full(3, L), 161, 20.0)
+    np.testing.assert_array_equal(wv, want_wv)
+    idx = np.sort(np.random.default_rng(161).choice(len(wv), 512, replace=False))
+    want = sum(np.abs(oracle.delta_fourier_transform_sum(wv[idx], f.astype(np.float64))) ** 2 for f in frames) / (2 * n)
+    s = got[0, idx] / (2 * n)
+    if precision == "fp64":
+        np.testing.assert_allclose(s, want, rtol=1e-10, atol=1e-12)
+    else:
+        # error model of DESIGN.md 3.10 (kappa = 1e-8: the spreading kernel's aliasing), and the literal bound
+        tol = 1e-5 * want + 2 * 5 * 1e-8 * np.sqrt(want) + 1e-12
+        assert (np.abs(s - want) <= tol).all(), float(np.max(np.abs(s - want) / tol))
+        big = want > 0.01
+        assert big.sum() > 256 and np.max(np.abs(s[big] / want[big] - 1)) < 1e-5
+
+
+def test_c4_partials_vs_oracle(ctx):
+    """C4 (binary electrolyte, 100k cations + 100k anions) against the CPU oracle: a 256-cation slab against all anions
+    (cross g(r), bit-exact), a 256-cation slab of the ++ self g(r) with exclusion, and the three partial S(q) rows on
+    128 wavevectors of the FULL q_max = 20 grid (n_points = 201, Nq = 4,269,143)."""
+    from mdcraft_b200 import _capi
+    from oracle import oracle
+
+    pos, box = _frame("C4")
+    n, L = len(pos), float(box[0])
+    half = n // 2
+    cat, an = pos[:half], pos[half:]
+    rng = (0.0, L / 2)
+    # (structure.py:34-131) slabs of i against all j; exclusion indices are local to each group (block (1, 1))
+    np.testing.assert_array_equal(_rdf_counts(ctx, cat[1000:1256], an, box, 200, rng),
+                                  oracle.radial_histogram(cat[1000:1256], an, 200, rng, box))
+    np.testing.assert_array_equal(_rdf_counts(ctx, cat[:256], cat, box, 200, rng, exclusion=(1, 1)),
+                                  oracle.radial_histogram(cat[:256], cat, 200, rng, box, exclusion=(1, 1)))
+    # the full cross g(r) restricted to those 256 cations is what the class computes for the whole group: check the
+    # whole-group kernel against the slab through additivity over i (cations 1000..1255 removed = the rest)
+    full = _rdf_counts(ctx, cat, an, box, 200, rng)
+    rest = _rdf_counts(ctx, np.concatenate((cat[:1000], cat[1256:])), an, box, 200, rng)
+    np.testing.assert_array_equal(full - rest, oracle.radial_histogram(cat[1000:1256], an, 200, rng, box))
+
+    pairs = [(0, 0), (0, 1), (1, 1)]
+    plan = _capi.SqPlan(ctx, [half, half], pairs, n_points=201, L0=[L] * 3, q_max=20.0)
+    assert plan.n_wavevectors == 4_269_143 and plan.info()["algo"] == "nufft"
+    wv = plan.wavevectors()
+    plan.push(pos[None])
+    got, _ = plan.read()
+    plan.close()
+    idx = np.sort(np.random.default_rng(4).choice(len(wv), 128, replace=False))
+    want, nfr = oracle.sq_accumulate([pos], [half, half], wv[idx], pairs)
+    assert nfr == 1
+    got, want = got[:, idx] / n, want / n
+    saa, sbb = want[0], want[2]
+    for i, scale in enumerate((np.sqrt(saa), np.sqrt(saa) + np.sqrt(sbb), np.sqrt(sbb))):
+        tol = 1e-5 * np.abs(want[i]) + 2 * 5 * 1e-8 * scale + 1e-12
+        assert (np.abs(got[i] - want[i]) <= tol).all(), (i, float(np.max(np.abs(got[i] - want[i]) / tol)))
+    big = saa > 0.01
+    assert np.max(np.abs(got[0][big] / saa[big] - 1)) < 1e-5
+
+
+def test_device_blocks_with_subrange_groups_at_full_size(ctx):
+    """Frame blocks resident in HBM (trajectory.frames_block_device) consumed by groups that are SUB-RANGES of the atoms
+    (cross g(r), partial S(q)) at N = 120,000: the slices are made contiguous by torch kernels on torch's stream and
+    then read by the library's own (non-blocking) streams: results must equal the per-frame host protocol."""
+    import torch
+
+    from mdcraft_b200 import synthetic
+    from mdcraft_b200.analysis.base import run_together
+    from mdcraft_b200.analysis.structure import RadialDistributionFunction, StructureFactor
+
+    class DeviceTrajectory(synthetic.MemoryTrajectory):
+        def frames_block_device(self, lo, hi):
+            return torch.from_numpy(self._root._array[lo:hi]).cuda()
+
+    n, F = 120_000, 3
+    L = float(synthetic.cubic_box_length(n, 0.8))
+    arr = np.stack([synthetic.uniform_frame(n, L, 77 + f) for f in range(F)])
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    results = []
+    for cls in (DeviceTrajectory, synthetic.MemoryTrajectory):
+        u = synthetic.Universe(cls(arr, dims))
+        a, b = u.select(0, 50_000), u.select(50_000, n)
+        g = RadialDistributionFunction(a, b, n_bins=100, range_=(0.0, 0.2 * L), verbose=False, frame_block=2)
+        s = StructureFactor([a, b], mode="partial", n_points=24, verbose=False, frame_block=2)
+        # a sub-range with itself: the exclusion acts on the indices local to the group
+        e = RadialDistributionFunction(b, n_bins=50, range_=(0.0, 0.1 * L), exclusion=(1, 1), verbose=False, frame_block=3)
+        if cls is DeviceTrajectory:
+            run_together([g, s])
+            e.run()
+        else:
+            g.run(), s.run(), e.run()
+        results.append((g.results.counts, s.results.ssf, e.results.counts, g.results.rdf))
+    np.testing.assert_array_equal(results[0][0], results[1][0])
+    np.testing.assert_allclose(results[0][1], results[1][1], rtol=1e-12, atol=1e-13)
+    np.testing.assert_array_equal(results[0][2], results[1][2])
+    np.testing.assert_array_equal(results[0][3], results[1][3])
+    assert results[0][0].sum() > 0 and results[0][2].sum() > 0
 
 
 def test_c5_million_particles(ctx):

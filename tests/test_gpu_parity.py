@@ -265,10 +265,11 @@ def test_rdf_and_sq_residue_groupings(tmp_path):
     dims = np.array([L, L, L, 90, 90, 90], np.float32)
     traj = synthetic.MemoryTrajectory(pos, dims)
     u = synthetic.Universe(traj, resindices=np.repeat(np.arange(n_res), per), masses=masses)
-    coms = []
+    coms, coms64 = [], []
     for i in range(2):
         u.trajectory[i]
-        coms.append(algorithm.center_of_mass(u.atoms, "residues").astype(np.float32))
+        coms64.append(algorithm.center_of_mass(u.atoms, "residues"))
+        coms.append(coms64[-1].astype(np.float32))          # capped_distance itself casts to float32
     want = oracle.rdf(coms, None, [dims] * 2, 60, (0.0, 6.0))
     r = _rdf(u.atoms, n_bins=60, range_=(0.0, 6.0), groupings="residues")
     np.testing.assert_array_equal(r.results.counts, want["counts"])
@@ -280,10 +281,15 @@ def test_rdf_and_sq_residue_groupings(tmp_path):
     want2 = oracle.rdf([p for p in pos], coms, [dims] * 2, 40, (0.0, 5.0))
     r2 = _rdf(u.atoms, u.atoms, n_bins=40, range_=(0.0, 5.0), groupings=("atoms", "residues"))
     np.testing.assert_array_equal(r2.results.counts, want2["counts"])
+    # S(q): the reference keeps the float64 centres of mass and evaluates q . r on them in FP64 (structure.py:1943-1944);
+    # a float32 staging buffer would cost ~q |r| 6e-8 of phase and break the FP64-mode tolerance
+    ws = oracle.structure_factor(coms64, [n_res], dims[:3], mode="pair", n_points=6)
     s = _sq(u.atoms, "residues", mode="pair", n_points=6)
-    ws = oracle.structure_factor(coms, [n_res], dims[:3], mode="pair", n_points=6)
     np.testing.assert_array_equal(s.results.wavenumbers, ws["wavenumbers"])
     np.testing.assert_allclose(s.results.ssf, ws["ssf"], rtol=1e-5, atol=1e-6)
+    for algorithm_ in ("direct", "nufft"):
+        s64 = _sq(u.atoms, "residues", mode="pair", n_points=6, precision="fp64", algorithm=algorithm_)
+        np.testing.assert_allclose(s64.results.ssf, ws["ssf"], rtol=1e-10, atol=1e-12)
 
 
 def test_rdf_post_processing_runs():

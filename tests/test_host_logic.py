@@ -135,14 +135,18 @@ def test_frame_block_partition():
             covered = [i for lo, hi in blocks for i in range(lo, hi)]
             assert covered == list(range(n))
             assert max(hi - lo for lo, hi in blocks) <= -(-n // world) if n else True
-    for start, stop, step in ((None, None, None), (3, 97, 4), (10, 11, 1), (5, 5, 1), (0, 100, 7)):
-        want = list(range(*slice(start, stop, step).indices(100)))
-        for world in (1, 2, 4, 8):
-            got = []
-            for r in range(world):
-                s0, s1, st = distributed.shard_slice(100, start, stop, step, rank=r, world=world)
-                got += list(range(s0, s1, st))
-            assert got == want
+    # forward and BACKWARD runs (a backward run that ends on frame 0 has stop=None, not -1), every rank's triple read
+    # the way run() reads it: through slice.indices of the trajectory length
+    for n in (100, 10):
+        for start, stop, step in ((None, None, None), (3, 97, 4), (10, 11, 1), (5, 5, 1), (0, 100, 7), (None, None, -1),
+                                  (None, None, -3), (9, None, -1), (8, 2, -2), (4, None, -1)):
+            want = list(range(*slice(start, stop, step).indices(n)))
+            for world in (1, 2, 3, 4, 8):
+                got = []
+                for r in range(world):
+                    s0, s1, st = distributed.shard_slice(n, start, stop, step, rank=r, world=world)
+                    got += list(range(*slice(s0, s1, st).indices(n)))
+                assert got == want, (n, start, stop, step, world)
 
 
 def test_post_processing_functions():
