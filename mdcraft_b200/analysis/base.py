@@ -22,9 +22,13 @@ When MDAnalysis is importable the classes derive from its real
 
 from __future__ import annotations
 
+import logging
+import time
 from typing import TextIO, Union
 
 import numpy as np
+
+logger = logging.getLogger("mdcraft_b200.analysis")
 
 try:  # pragma: no cover - MDAnalysis is absent in the build image
     from MDAnalysis.analysis.base import AnalysisBase as _MDAAnalysisBase
@@ -112,6 +116,51 @@ else:
             return self
 
 
+class _RunLog:
+    """
+    ``verbose=True``: one ``logging.info`` line when a run starts and one when it ends (the reference logs the
+    start and the wall time of its process farm the same way, base.py:378-384, 514-515): device, frames per block,
+    the plan's algorithm, frames/s.  Silent when ``verbose`` is false.
+    """
+
+    def __init__(self, analysis, verbose=None, n_frames=None):
+        self.analysis = analysis
+        self.on = bool(getattr(analysis, "_verbose", False) if verbose is None else verbose)
+        self.t0 = time.perf_counter()
+        if self.on:
+            n = getattr(analysis, "n_frames", None) if n_frames is None else n_frames
+            logger.info("%s: analysing %s frames on cuda:%s (frames per block: %s)", type(analysis).__name__,
+                        "the selected" if n is None else n, getattr(analysis, "_device", "?"),
+                        getattr(analysis, "_frame_block", "?"))
+
+    @staticmethod
+    def count(trajectory, start, stop, step, frames):
+        """Number of frames a ``run(start, stop, step, frames)`` will visit (``None`` if it cannot be told)."""
+        try:
+            if frames is not None:
+                f = np.asarray(frames)
+                return int(f.sum()) if f.dtype == bool else int(f.size)
+            return len(range(*trajectory.check_slice_indices(start, stop, step)))
+        except Exception:
+            return None
+
+    def done(self) -> None:
+        if not self.on:
+            return
+        a = self.analysis
+        dt = max(time.perf_counter() - self.t0, 1e-12)
+        plan = getattr(a, "_plan", None)
+        detail = ""
+        if plan is not None and hasattr(plan, "info"):
+            try:
+                info = plan.info()
+                detail = f", algorithm {info['algo']}" + (f" (nf = {info['nf']}, w = {info['w']})" if info["algo"] == "nufft" else "")
+            except Exception:  # pragma: no cover - diagnostics only
+                detail = ""
+        logger.info("%s: %d frames in %.3f s (%.1f frames/s) on cuda:%s%s", type(a).__name__, a.n_frames, dt,
+                    a.n_frames / dt, getattr(a, "_device", "?"), detail)
+
+
 class SerialAnalysisBase(AnalysisBase):
     """base.py:106-206."""
 
@@ -119,7 +168,10 @@ class SerialAnalysisBase(AnalysisBase):
         super().__init__(trajectory, verbose, **kwargs)
 
     def run(self, start=None, stop=None, step=None, frames=None, verbose=None, **kwargs):
-        return super().run(start, stop, step, frames, verbose, **kwargs)
+        log = _RunLog(self, verbose, _RunLog.count(self._trajectory, start, stop, step, frames))
+        out = super().run(start, stop, step, frames, verbose, **kwargs)
+        log.done()
+        return out
 
     def save(self, file: Union[str, TextIO], archive: bool = True, compress: bool = True, **kwargs) -> None:
         """Saves ``results`` in NumPy format (base.py:167-206)."""
@@ -161,20 +213,27 @@ class DynamicAnalysisBase(SerialAnalysisBase):
 
 def run_together(analyses, start=None, stop=None, step=None, frames=None):
     """
-    Runs several analyses of the SAME trajectory in one pass over its frames: every frame is read once and handed to
-    each analysis' ``_single_frame`` in turn, exactly as their own ``run(start, stop, step, frames)`` would have done
-    (same ``frames`` / ``times`` bookkeeping, same results).  Because the analysis families queue their kernels on
+    Runs several analyses in ONE pass over their frames: every frame is read once and handed to each analysis'
+    ``_single_frame`` in turn, exactly as their own ``run(start, stop, step, frames)`` would have done (same
+    ``frames`` / ``times`` bookkeeping, same results).  Because the analysis families queue their kernels on
     different stream lanes (``_capi.context``), g(r) and S(q) of the same frame block execute side by side on the GPU.
-    Returns the analyses.
+
+    The analyses normally share one trajectory.  Analyses of DIFFERENT trajectories (e.g. g(r) of one system next to
+    S(q) of another) are stepped in lockstep, frame i of every trajectory in the same turn; the selected frame ranges
+    must then have equal lengths.  Returns the analyses.
     """
     analyses = list(analyses)
     if not analyses:
         return analyses
-    trajectory = analyses[0]._trajectory
+    trajectories = []
     for a in analyses:
-        if a._trajectory is not trajectory:
-            raise ValueError("run_together needs analyses of one and the same trajectory.")
-        a._setup_frames(trajectory, start=start, stop=stop, step=step, frames=frames)
+        if not any(a._trajectory is t for t in trajectories):
+            trajectories.append(a._trajectory)
+        a._setup_frames(a._trajectory, start=start, stop=stop, step=step, frames=frames)
+    if len({a.n_frames for a in analyses}) != 1:
+        raise ValueError("run_together needs the same number of selected frames in every trajectory.")
+    timers = [_RunLog(a) for a in analyses]
+    for a in analyses:
         a._prepare()
     # g(r) next to analyses on other stream lanes: its persistent pair kernel leaves a quarter of every SM free
     pair_plans = [a._plan for a in analyses if hasattr(getattr(a, "_plan", None), "set_blocks_per_sm")]
@@ -185,7 +244,7 @@ def run_together(analyses, start=None, stop=None, step=None, frames=None):
     # consumed by each analysis on the device, when all of them can take it (see structure._DeviceBlockRun)
     sources = [a._device_block_ranges() if hasattr(a, "_device_block_ranges") and getattr(a, "_drop_axis", None) is None
                and type(a).__name__ in ("RadialDistributionFunction", "StructureFactor") else None for a in analyses]
-    if all(src is not None for src in sources):
+    if len(trajectories) == 1 and all(src is not None for src in sources):
         from ..synthetic import Timestep
 
         src = sources[0][0]
@@ -210,11 +269,14 @@ def run_together(analyses, start=None, stop=None, step=None, frames=None):
             for a in analyses:
                 a._ts, a._frame_index = last, idx.size - 1
     else:
-        for i, ts in enumerate(analyses[0]._sliced_trajectory):
-            for a in analyses:
-                a._frame_index, a._ts = i, ts
-                a.frames[i], a.times[i] = ts.frame, ts.time
-                a._single_frame()
-    for a in analyses:
+        groups = [[a for a in analyses if a._trajectory is t] for t in trajectories]
+        for i, stamps in enumerate(zip(*(g[0]._sliced_trajectory for g in groups))):
+            for ts, group in zip(stamps, groups):
+                for a in group:
+                    a._frame_index, a._ts = i, ts
+                    a.frames[i], a.times[i] = ts.frame, ts.time
+                    a._single_frame()
+    for a, t in zip(analyses, timers):
         a._conclude()
+        t.done()
     return analyses

@@ -289,8 +289,10 @@ class _DeviceBlockRun:
 
     def _run_device_blocks(self, src, start, stop, step, frames) -> None:
         from ..synthetic import Timestep
+        from .base import _RunLog
 
         self._setup_frames(self._trajectory, start=start, stop=stop, step=step, frames=frames)
+        log = _RunLog(self)
         self._prepare()
         idx = np.asarray(self._sliced_trajectory._indices, dtype=np.int64)
         i = 0
@@ -310,6 +312,7 @@ class _DeviceBlockRun:
             self._ts = src[int(idx[-1])]
             self._frame_index = idx.size - 1
         self._conclude()
+        log.done()
 
 
 def _entity_count(group, grouping: str) -> int:

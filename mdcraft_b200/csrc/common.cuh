@@ -45,6 +45,19 @@ struct Ctx {
     cudaEvent_t mark[2] = {nullptr, nullptr};   // mdc_mark / mdc_elapsed_ms
 };
 
+// Raises a kernel's dynamic shared-memory limit to the device maximum (minus the kernel's static shared memory).
+// The limit is a per-function, per-device attribute shared by every live plan, so it is never set to one plan's own
+// footprint: a later, smaller plan would lower it under an earlier plan's launches.
+template <typename K>
+static inline cudaError_t raise_smem_limit(K kernel, size_t smem_optin)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    const size_t room = smem_optin > fa.sharedSizeBytes ? smem_optin - fa.sharedSizeBytes : 0;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room);
+}
+
 // Device buffer helper (plans free in their destroy).
 template <typename T>
 struct DevBuf {

@@ -1399,10 +1399,8 @@ extern "C" int mdc_rdf_plan_create(mdc_ctx *ctx, int n_bins, double r0, double r
     if (e == cudaSuccess) e = cudaMemset(p->counts.p, 0, n_bins * sizeof(unsigned long long));
     // The limit is a per-function (per-device) attribute shared by every live plan: it is only ever set to the device
     // maximum, so that a later plan with a smaller histogram cannot lower it under an earlier plan's launches.
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(rdf_pairs_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(rdf_pairs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    if (e == cudaSuccess) e = raise_smem_limit(rdf_pairs_exact, ctx->smem_optin);
+    if (e == cudaSuccess) e = raise_smem_limit(rdf_pairs_fast, ctx->smem_optin);
     if (e == cudaSuccess && !p->force_exact)   // four ~42 KB blocks per SM need more than the default carve-out
         e = cudaFuncSetAttribute(rdf_pairs_fast, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess)

@@ -564,9 +564,9 @@ int Nufft::init(const Ctx *ctx, int n_points, double eps_, int64_t max_set_len)
     if (smem_z > ctx->smem_optin || smem_s > ctx->smem_optin)
         return fail(MDC_ERR_UNSUPPORTED, "nufft: fine grid line does not fit shared memory");
     // per-function attribute shared by every live plan (any fine grid): only ever the device maximum
-    MDC_CUDA(cudaFuncSetAttribute(nufft_fft_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-    MDC_CUDA(cudaFuncSetAttribute(nufft_fft_s<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-    MDC_CUDA(cudaFuncSetAttribute(nufft_fft_s<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    MDC_CUDA(raise_smem_limit(nufft_fft_z, ctx->smem_optin));
+    MDC_CUDA(raise_smem_limit(nufft_fft_s<false>, ctx->smem_optin));
+    MDC_CUDA(raise_smem_limit(nufft_fft_s<true>, ctx->smem_optin));
     const char *env = getenv("MDC_NUFFT_SORT");
     sort = !(env && env[0] == '0');
     return MDC_OK;

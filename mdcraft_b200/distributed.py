@@ -90,6 +90,19 @@ def run_sharded(analysis, start=None, stop=None, step=None, **kwargs):
     return analysis.run(start=s0, stop=s1, step=st, **kwargs)
 
 
+def run_together_sharded(analyses, start=None, stop=None, step=None):
+    """
+    :func:`mdcraft_b200.analysis.base.run_together` on this rank's frame block: several analyses (constructed with
+    ``distributed=True``) fed from one pass over the rank's frames, each all-reducing in its ``_conclude``.
+    """
+    from .analysis.base import run_together
+
+    analyses = list(analyses)
+    n = len(analyses[0]._trajectory)
+    s0, s1, st = shard_slice(n, start, stop, step)
+    return run_together(analyses, start=s0, stop=s1, step=st)
+
+
 def all_reduce_sum(values: np.ndarray, device: int = 0) -> np.ndarray:
     """Sum of a small host array over all ranks (identity when not distributed)."""
     values = np.ascontiguousarray(values)
