@@ -5,27 +5,43 @@ bench.py — frames/s of the S(q) + g(r) hot path at 100,000 particles.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1] + configs[2], SURVEY.md §8d C2 + C3):
+Workload (BASELINE.json configs[1] + configs[2], SURVEY.md §8d C2 + C3), ONE fixed job for every N:
   * g(r): N = 100,000 uniform ("GCMe-like", rho* = 2.5, L = 34.2), self-RDF, 200 bins to L/2,
           exclusion = (1, 1)  -> 1e10 ordered pairs per frame;
   * S(q): N = 100,000 lattice + jitter ("LJ-like", rho* = 0.8, L = 50), the FULL reciprocal grid to
-          q_max = 20 / sigma (n_points = 161 -> Nq = 2,140,871 wavevectors) -> 2.14e11 terms per frame.
-A "step" is one frame block (--frames, default 2) through BOTH analyses.  `value` = frames/s with the
-frames already resident in HBM; `e2e` = the same through the C ABI with pinned HOST buffers (H2D of the
-frames and D2H of the step's results inside the timed region).  Frames shard across ranks (weak scaling:
-every rank processes its own --frames per step); accumulators are all-reduced once at the end.
+          q_max = 20 / sigma (n_points = 161 -> Nq = 2,140,871 wavevectors) -> 2.14e11 terms per frame;
+  * a trajectory of K x B frames of each system (K = --steps, B = --frames = 48 frames per step: 960 frames with
+    the driver's K = 20, the 1,000-frame trajectories of the configs), frames SHARDED over the N ranks — one
+    contiguous block of K x B / N frames per rank — and one all-reduce of the accumulators at the end
+    (`scaling: "strong"`: the job is the same for every N).
+
+A "step" is B frames through BOTH analyses (B / N per rank).  Timed region = the K steps + the finalisation (NCCL
+all-reduce of the int64 histogram and the FP64 S(q) sums, |q|-shell means on the device, read-back, normalisation).
+`value` = K x B frames / that time, frames resident in HBM when the region starts and pushed through the C ABI
+(`e2e_capi` is the same with pinned host buffers).  `e2e` = the same job through the API the reference's users call:
+`RadialDistributionFunction(...)` and `StructureFactor(...)` fed by `run_together` from host trajectories (per-frame
+`_single_frame` protocol, pinned staging, H2D, `_prepare` and `_conclude` with the all-reduce inside the timer,
+constructors outside), sharded with `distributed.run_together_sharded`.
+
+After the timed regions the line's results are CHECKED (`parity_check`): the timed S(q) accumulator on 64
+wavevectors against the CPU oracle over every frame of the job, the g(r) kernel on a slab of the first frame against
+the oracle, the class results against the plan-level results; with N > 1 (`allreduce_check`) the NCCL result against
+the sum of the ranks' own accumulators gathered before the all-reduce, and for N <= 2 against a single-GPU pass over
+all frames.  A failed check exits non-zero.
 
 Rooflines.  `roofline` describes the kernel with the largest share of the timed step: the g(r)
-pair kernel (issue-rate bound, 20 algorithmic issue slots per pair-distance).  S(q) on this grid runs as a gridding NUFFT
-(`roofline_sq`, HBM bound: fine grid + pruned FFT intermediates); the two O(Nq N) kernels it replaced are timed on
-one frame each and reported against their issue-rate rooflines measured on the box in this run
-(`roofline_sfu_direct`: 2 SFU ops per term, the contract kernel of BASELINE.json's north_star;
-`roofline_fp32_factored`: 4 FP32 FMAs per term).
+pair kernel (issue-rate bound, 20 algorithmic issue slots per pair-distance); its `traffic`,
+`issue_active` and `slots_per_pair` are read from the committed ncu summary (profiles/ncu_r02.json: `traffic_source`
+says which capture, and whether the kernels' sources have changed since).  S(q) on this grid runs as a gridding
+NUFFT (`roofline_sq`, HBM bound); the two O(Nq N) kernels it replaced are timed on one frame each against their
+issue-rate rooflines measured on the box in this run (`roofline_sfu_direct`: the contract kernel of BASELINE.json's
+north_star; `roofline_fp32_factored`).
 """
 
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -41,39 +57,106 @@ if ROOT not in sys.path:
 
 N_PART = 100_000
 GR = dict(rho=2.5, n_bins=200, seed0=2000)
-SQ = dict(rho=0.8, n_points=161, q_max=20.0, seed0=3000)
+SQ = dict(rho=0.8, n_points=161, q_max=20.0, seed0=3000, jitter=0.15)
+NQ_FULL = 2_140_871
 METRIC = "frames/sec for S(q) and g(r) at 1e5 particles"
-#: dram__bytes_read.sum + dram__bytes_write.sum of the four NUFFT kernels (spread, z / y / x FFT passes) per frame from
-#: one `ncu --set full` capture (profiles/sq_nufft_r01.txt: 2,706 MB per 2-frame launch); clearing the fine grid adds
-#: 0.27e9 that ncu does not attribute to a kernel
-NUFFT_DRAM_BYTES_PER_FRAME = 1.353e9
 UNIT = "frames/s"
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "ncu_r02.json")
 
 
-def workload_config(frames, n_gpus):
+def workload_config(frames, n_gpus, steps):
     return {
         "workload": "C2 g(r) (N=1e5 uniform rho*=2.5, 200 bins to L/2, exclusion (1,1)) + "
                     "C3 S(q) (N=1e5 LJ-like rho*=0.8, full lattice grid to q_max=20/sigma, Nq=2,140,871)",
         "n_particles": N_PART,
-        "frames_per_step_per_gpu": frames,
-        "sharding": f"frames x{n_gpus}",
-        "l2": "256 MiB device buffer written between timed steps (L2 flush)",
+        "frames_per_step": frames,
+        "frames_per_step_per_gpu": frames // max(1, n_gpus),
+        "trajectory_frames": frames * steps,
+        "sharding": f"one contiguous block of {frames * steps // max(1, n_gpus)} frames per rank x{n_gpus}; "
+                    "one all-reduce of the accumulators at the end, inside the timed region",
+        "l2": "256 MiB device buffer written between timed steps (L2 flush); every step reads new frames",
     }
+
+
+def csrc_sha():
+    """Hash of the CUDA sources the library is built from (ties an ncu capture to the kernels it measured)."""
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "mdcraft_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, name), "rb") as fh:
+                h.update(name.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_summary():
+    """The committed ncu summary (tools/ncu_summary.py --json), or None."""
+    try:
+        with open(NCU_SUMMARY) as fh:
+            d = json.load(fh)
+    except Exception:
+        return None
+    d["_stale"] = d.get("csrc_sha") != csrc_sha()
+    return d
+
+
+def ncu_kernel(summary, pattern):
+    if not summary:
+        return None
+    for k in summary.get("kernels", []):
+        if pattern in k.get("name", ""):
+            return k
+    return None
+
+
+def ncu_source(summary):
+    if not summary:
+        return "not measured in this run and no committed ncu summary: omitted"
+    return (f"profiles/ncu_r02.json (ncu --set full, {summary.get('captured', '?')}, csrc {summary.get('csrc_sha', '?')}"
+            + ("; kernel sources have CHANGED since that capture" if summary["_stale"] else "; kernel sources unchanged") + ")")
 
 
 # ----------------------------------------------------------------------------- inputs
 
 
-def make_frames(frames, rank):
+def rank_frames(total, rank, world):
+    from mdcraft_b200 import distributed
+
+    return distributed.frame_block(total, rank, world)
+
+
+def device_frames(kind, lo, hi, device):
+    """
+    Frames [lo, hi) of the job's synthetic trajectory as a float32 CUDA tensor (hi - lo, N, 3).  Generated on the
+    device (torch is plumbing: inputs, not the measured path), one generator per GLOBAL frame index, so every rank
+    — and the single-GPU pass that re-checks a 2-rank run — sees the same frames.
+    """
+    import torch
+
     from mdcraft_b200 import synthetic
 
-    Lg = synthetic.cubic_box_length(N_PART, GR["rho"])
-    Ls = synthetic.cubic_box_length(N_PART, SQ["rho"])
-    off = rank * 1000
-    gr = np.stack([synthetic.uniform_frame(N_PART, Lg, GR["seed0"] + off + i) for i in range(frames)])
-    sq = np.stack([synthetic.lj_like_frame(N_PART, Ls, SQ["seed0"] + off + i) for i in range(frames)])
-    box_g = np.array([Lg, Lg, Lg, 90, 90, 90], np.float32)
-    return gr, box_g, sq, float(Ls)
+    rho, seed0 = (GR["rho"], GR["seed0"]) if kind == "gr" else (SQ["rho"], SQ["seed0"])
+    L = float(synthetic.cubic_box_length(N_PART, rho))
+    out = torch.empty((hi - lo, N_PART, 3), dtype=torch.float32, device=device)
+    lattice = None
+    if kind == "sq":
+        m = int(round(N_PART ** (1.0 / 3.0)))
+        while m ** 3 < N_PART:
+            m += 1
+        g = (torch.arange(m, dtype=torch.float64, device=device) + 0.5) * (L / m)
+        lattice = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)[:N_PART]
+    gen = torch.Generator(device=device)
+    for i in range(lo, hi):
+        gen.manual_seed(seed0 + i)
+        if kind == "gr":
+            p = torch.rand((N_PART, 3), generator=gen, device=device, dtype=torch.float64) * L
+        else:
+            p = lattice + SQ["jitter"] * torch.randn((N_PART, 3), generator=gen, device=device, dtype=torch.float64)
+            p = torch.remainder(p, L)
+        p = p.to(torch.float32)
+        p[p >= L] = 0.0
+        out[i - lo] = p
+    return out, L
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -109,12 +192,13 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
             for n, v in zip(names, r[3:7]):
@@ -122,7 +206,9 @@ class ClockSampler:
                     reasons.add(n)
         return {
             "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_mhz_min": float(min(sm)) if sm else None,
             "sm_max_mhz": float(max(mx)) if mx else None,
+            "power_w_max": float(max(pw)) if pw else None,
             "reasons": sorted(reasons),
             "samples": len(sm),
         }
@@ -131,20 +217,31 @@ class ClockSampler:
 # ----------------------------------------------------------------------------- CPU baseline (oracle)
 
 
-def cpu_baseline(seconds_target=10.0):
+def host_frame(kind, index=0):
+    """Frame `index` of the job's trajectory on the host WITHOUT a GPU (NumPy generators of the same fluids): the
+    reference arm and the cpu_baseline leg only need one representative frame."""
+    from mdcraft_b200 import synthetic
+
+    if kind == "gr":
+        L = synthetic.cubic_box_length(N_PART, GR["rho"])
+        return synthetic.uniform_frame(N_PART, L, GR["seed0"] + index), float(L)
+    L = synthetic.cubic_box_length(N_PART, SQ["rho"])
+    return synthetic.lj_like_frame(N_PART, L, SQ["seed0"] + index, SQ["jitter"]), float(L)
+
+
+def cpu_baseline(numba_leg=False):
     """
     The CPU restatement of the reference path (oracle/oracle.c, OpenMP over all host cores) on a bounded
     sample of the same workload: S(q) on a slab of the wavevector grid, g(r) on a slab of i-particles,
-    both against all 100,000 particles of one frame; scaled to frames/s by the exact work ratio.
+    both against all 100,000 particles of one frame; EXTRAPOLATED to frames/s by the exact work ratio (the work
+    is exactly linear in the number of wavevectors and of i-particles).
     """
-    from mdcraft_b200 import synthetic
     from oracle import oracle
 
     cores = oracle.num_threads()
-    Ls = synthetic.cubic_box_length(N_PART, SQ["rho"])
-    pos_s = synthetic.lj_like_frame(N_PART, Ls, SQ["seed0"]).astype(np.float64)
+    pos_sf, Ls = host_frame("sq")
+    pos_s = pos_sf.astype(np.float64)
     wv, _ = oracle.wavevector_grid(np.full(3, float(Ls)), 64, SQ["q_max"])
-    nq_full = 2_140_871
     wv = wv[-min(2048 * cores, len(wv)):]
     nq = len(wv)
     oracle.delta_fourier_transform_sum(wv[:cores], pos_s[:1000])   # warm the thread pool
@@ -153,8 +250,7 @@ def cpu_baseline(seconds_target=10.0):
     t_sq = time.perf_counter() - t0
     terms_per_s = nq * N_PART / t_sq
 
-    Lg = synthetic.cubic_box_length(N_PART, GR["rho"])
-    pos_g = synthetic.uniform_frame(N_PART, Lg, GR["seed0"])
+    pos_g, Lg = host_frame("gr")
     box = np.array([Lg, Lg, Lg, 90, 90, 90], np.float32)
     na = 1024 * cores
     oracle.radial_histogram(pos_g[:cores], pos_g[:2000], GR["n_bins"], (0.0, float(Lg) / 2), box)
@@ -163,18 +259,43 @@ def cpu_baseline(seconds_target=10.0):
     t_gr = time.perf_counter() - t0
     pairs_per_s = na * N_PART / t_gr
 
-    t_frame = nq_full * N_PART / terms_per_s + float(N_PART) ** 2 / pairs_per_s
-    return {
+    t_frame = NQ_FULL * N_PART / terms_per_s + float(N_PART) ** 2 / pairs_per_s
+    out = {
         "value": 1.0 / t_frame,
         "unit": UNIT,
         "cores": cores,
         "kind": "port",
-        "sample": f"S(q): {nq} of {nq_full} wavevectors x 1e5 particles in {t_sq:.2f} s "
+        "extrapolated": True,
+        "measured_sample_s": t_sq + t_gr,
+        "sample_fraction": {"sq_wavevectors": nq / NQ_FULL, "gr_i_particles": na / N_PART},
+        "sample": f"S(q): {nq} of {NQ_FULL} wavevectors x 1e5 particles in {t_sq:.2f} s "
                   f"({terms_per_s / 1e6:.0f} M terms/s); g(r): {na} x 1e5 ordered pairs in {t_gr:.2f} s "
-                  f"({pairs_per_s / 1e6:.0f} M pairs/s); one frame = 2.14e11 terms + 1e10 ordered pairs",
-        "sq_frames_per_s": terms_per_s / (nq_full * N_PART),
+                  f"({pairs_per_s / 1e6:.0f} M pairs/s); one frame = 2.14e11 terms + 1e10 ordered pairs, "
+                  "scaled by the exact work ratio",
+        "sq_frames_per_s": terms_per_s / (NQ_FULL * N_PART),
         "gr_frames_per_s": pairs_per_s / float(N_PART) ** 2,
     }
+    if numba_leg:
+        # the reference's own technology for the S(q) kernel (Numba, fastmath, prange over wavevectors): the factor
+        # between it and the C/OpenMP port, on the same sample
+        from oracle import numba_port
+
+        if numba_port.available():
+            try:
+                numba_port.set_num_threads(cores)
+                numba_port.delta_fourier_transform_sum(wv[:64], pos_s[:256])     # JIT compile
+                sub = wv[: max(cores, nq // 4)]
+                t0 = time.perf_counter()
+                numba_port.delta_fourier_transform_sum(sub, pos_s)
+                t_nb = time.perf_counter() - t0
+                nb = len(sub) * N_PART / t_nb
+                out["numba"] = {"terms_per_s": nb, "threads": numba_port.num_threads(), "port_over_numba": terms_per_s / nb,
+                                "sample": f"{len(sub)} wavevectors x 1e5 particles in {t_nb:.2f} s"}
+            except Exception as err:   # pragma: no cover - diagnostics only
+                out["numba"] = {"unavailable": str(err)[:200]}
+        else:
+            out["numba"] = {"unavailable": "numba does not import on this box"}
+    return out
 
 
 def run_reference(args, rank, emit=print):
@@ -188,15 +309,22 @@ def run_reference(args, rank, emit=print):
     oracle.set_num_threads(len(os.sched_getaffinity(0)))
     vals = []
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline()
+        cb = cpu_baseline(numba_leg=(i == args.warmup + args.steps - 1))
         if i >= args.warmup:
             vals.append(cb)
     v = float(np.mean([c["value"] for c in vals]))
-    cb = dict(vals[-1], value=v)
+    sample_s = float(np.mean([c["measured_sample_s"] for c in vals]))
+    cb = dict(vals[-1], value=v, measured_sample_s=sample_s)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * args.frames / v, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.frames, args.gpus),
+        "warmup": args.warmup,
+        # what was TIMED per step: the bounded sample; `value` is that sample scaled to whole frames by the exact work ratio
+        "ms_per_step": 1e3 * sample_s,
+        "ms_per_step_extrapolated": 1e3 * args.frames / v,
+        "extrapolated": True,
+        "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.frames, args.gpus, args.steps),
         "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -206,108 +334,306 @@ def run_reference(args, rank, emit=print):
 # ----------------------------------------------------------------------------- native arm
 
 
+def gr_normalise(counts, n_frames, volume_sum, edges):
+    """structure.py:990-1010 for norm="rdf", exclusion (1, 1), a self-RDF."""
+    norm = n_frames * (4 * np.pi * np.diff(edges ** 3) / 3)
+    norm = norm * (N_PART * (N_PART - 1) * n_frames / volume_sum)
+    return counts / norm
+
+
 def run_native(args, rank, world, emit=print):
     import torch
 
     from mdcraft_b200 import _capi
+    from mdcraft_b200 import distributed as mdist
+    from mdcraft_b200 import synthetic
+    from mdcraft_b200.algorithm import histogram_bin_edges
+    from mdcraft_b200.analysis.structure import RadialDistributionFunction, StructureFactor, shell_windows
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.frames, args.steps, max(args.warmup, 3)
+    if B % world:
+        raise SystemExit(f"--frames ({B}) must be a multiple of the number of GPUs ({world})")
+    b = B // world                       # frames per step on this rank
+    T = K * B                            # the job
+    lo, hi = rank_frames(T, rank, world)
+    assert hi - lo == K * b
+
     # one context (= one pair of streams) per analysis: g(r) is issue bound, the NUFFT L2 / shared-memory bound, and
     # on separate streams the device runs them side by side (the analysis classes do the same through their lanes)
     ctx = _capi.Context(local)
     ctx_s = ctx if args.one_stream else _capi.Context(local, high_priority=True)
-    F = args.frames
-    gr_host, box_g, sq_host, Ls = make_frames(F, rank)
-    Lg = float(box_g[0])
+    gr_dev, Lg = device_frames("gr", lo, hi, dev)
+    sq_dev, Ls = device_frames("sq", lo, hi, dev)
+    box_g = np.array([Lg, Lg, Lg, 90, 90, 90], np.float32)
+    box_s = np.array([Ls, Ls, Ls, 90, 90, 90], np.float32)
+    edges = histogram_bin_edges(np.asarray((0.0, Lg / 2), dtype=float), GR["n_bins"])
 
-    rdf = _capi.RdfPlan(ctx, GR["n_bins"], (0.0, Lg / 2), N_PART, None, (1, 1))
+    rdf = _capi.RdfPlan(ctx, GR["n_bins"], (edges[0], edges[-1]), N_PART, None, (1, 1))
     if ctx_s is not ctx:
         rdf.set_blocks_per_sm(3)   # of the 4 that fit: the free quarter of every SM hosts the S(q) kernels
     sqp = _capi.SqPlan(ctx_s, [N_PART], [(None, None)], n_points=SQ["n_points"], L0=[Ls] * 3, q_max=SQ["q_max"],
                        algo=args.sq_algo)
     nq = sqp.n_wavevectors
-    gr_dev = torch.from_numpy(gr_host).cuda()
-    sq_dev = torch.from_numpy(sq_host).cuda()
-    gr_pin = torch.from_numpy(gr_host).pin_memory()
-    sq_pin = torch.from_numpy(sq_host).pin_memory()
     # the step's S(q) result is what StructureFactor.results.ssf holds: the |q|-shell means (unique=True), formed on the
     # device; the windows are per-plan bookkeeping, set up once outside the timed region
-    from mdcraft_b200.analysis.structure import shell_windows
-
-    wavenumbers = np.linalg.norm(sqp.wavevectors(), axis=1)
+    wavevectors = sqp.wavevectors()
+    wavenumbers = np.linalg.norm(wavevectors, axis=1)
     unique_q = np.unique(wavenumbers.round(11))
     sqp.set_shells(*shell_windows(wavenumbers, unique_q))
     n_shells = int(unique_q.shape[0])
-    ssf_pin = torch.empty((1, n_shells), dtype=torch.float64).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
         ctx.synchronize()
         ctx_s.synchronize()
         if world > 1:
-            torch.distributed.barrier()
+            dist.barrier()
 
-    def step(device_resident):
-        if device_resident:
-            rdf.push(gr_dev, None, box_g, n_frames=F)
-            sqp.push(sq_dev, n_frames=F)
-        else:
-            rdf.push(gr_pin.numpy(), None, box_g, n_frames=F)
-            sqp.push(sq_pin.numpy(), n_frames=F)
-            rdf.read()
-            sqp.read_shells(float(N_PART), out=ssf_pin.numpy())
+    def finalise(rdf_plan, sq_plan, frames_local):
+        """The once-per-job exchange and read-out: all-reduce of the accumulators (NCCL on the library-owned device
+        buffers), |q|-shell means on the device, D2H of both results, the reference's normalisation.  Returns the
+        results, the device time of the collectives (CUDA events) and the wall time between two full syncs."""
+        barrier()
+        w0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        totals = mdist.all_reduce_sum(np.array([frames_local, frames_local * float(Lg) ** 3], dtype=np.float64), device=local)
+        mdist.all_reduce_device(rdf_plan.accumulator(), device=local)
+        mdist.all_reduce_device(sq_plan.accumulator(), device=local)
+        e1.record()
+        n_frames = int(round(totals[0]))
+        counts, _ = rdf_plan.read()
+        ssf, _ = sq_plan.read_shells(float(n_frames) * N_PART)
+        g = gr_normalise(counts, n_frames, float(totals[1]), edges)
+        torch.cuda.synchronize()
+        wall_ms = 1e3 * (time.perf_counter() - w0)
+        return (counts, g, ssf, n_frames), (e0.elapsed_time(e1) if world > 1 else 0.0), wall_ms
 
-    def timed(device_resident, steps):
-        """Device time of `steps` steps: CUDA events on the library's compute stream around each step
+    def timed(src_g, src_s, steps, first):
+        """Device time of `steps` steps of this rank: CUDA events on the library's compute streams around each step
         (L2 flushed in between, outside the events), wall clock around the whole region as a cross-check."""
         launches, dev_ms, sq_ms, gr_ms = 0, 0.0, 0.0, 0.0
         barrier()
         w0 = time.perf_counter()
-        for _ in range(steps):
+        for k in range(first, first + steps):
             flush.fill_(1)
             torch.cuda.synchronize()
             ctx.mark(0)
             ctx_s.mark(0)
-            step(device_resident)
+            rdf.push(src_g[k * b:(k + 1) * b], None, box_g, n_frames=b)
+            sqp.push(src_s[k * b:(k + 1) * b], n_frames=b)
             ctx.mark(1)
             ctx_s.mark(1)
-            # both start events are recorded on idle streams (barrier above): the step ends when the later one does
+            # both start events are recorded on idle streams (sync above): the step ends when the later one does
             dev_ms += max(ctx.elapsed_ms(), ctx_s.elapsed_ms()) if ctx_s is not ctx else ctx.elapsed_ms()
             a, la = rdf.last_push_stats()
-            b, lb = sqp.last_push_stats()
-            gr_ms, sq_ms, launches = gr_ms + a, sq_ms + b, launches + la + lb
+            c, lb = sqp.last_push_stats()
+            gr_ms, sq_ms, launches = gr_ms + a, sq_ms + c, launches + la + lb
         barrier()
         wall = time.perf_counter() - w0
         return dev_ms, wall, launches, sq_ms, gr_ms
 
-    for _ in range(max(args.warmup, 3)):
-        step(True)
-    barrier()
+    # ------------------------------------------------------------------ value: frames resident in HBM, C ABI
+    timed(gr_dev, sq_dev, min(W, K), 0)
+    rdf.reset()
+    sqp.reset()
     with ClockSampler(local) as clk:
-        dev_ms, wall, launches, sq_ms, gr_ms = timed(True, args.steps)
+        dev_ms, wall, launches, sq_ms, gr_ms = timed(gr_dev, sq_dev, K, 0)
+        # (outside the timer) this rank's own accumulators, kept for the all-reduce check
+        pre = None
+        if world > 1:
+            pre = (torch.as_tensor(rdf.accumulator(), device=dev).clone(), torch.as_tensor(sqp.accumulator(), device=dev).clone())
+        (counts, g_r, ssf, n_frames_total), coll_ms, fin_ms = finalise(rdf, sqp, K * b)
     clocks = clk.summary()
-    for _ in range(2):
-        step(False)
-    e2e_ms, e2e_wall, _, _, _ = timed(False, args.steps)
+    launches += 1                                           # sq_shell_mean of the finalisation
+    acc_sq = sqp.read()[0][0].copy()                        # all-reduced FP64 sums (n_pairs = 1), for the checks below
+    assert n_frames_total == T
+
+    # ------------------------------------------------------------------ e2e_capi: the same from pinned host buffers
+    rdf.reset()
+    sqp.reset()
+    n_pin = min(K, max(2, 192 // B)) if args.full_capi_e2e else min(K, 4)
+    gr_pin = gr_dev[: n_pin * b].cpu().pin_memory()
+    sq_pin = sq_dev[: n_pin * b].cpu().pin_memory()
+    timed(gr_pin.numpy(), sq_pin.numpy(), 1, 0)
+    capi_ms, _, _, _, _ = timed(gr_pin.numpy(), sq_pin.numpy(), n_pin, 0)
+    _, _, capi_fin_ms = finalise(rdf, sqp, n_pin * b)
+    del gr_pin, sq_pin
+
+    # ------------------------------------------------------------------ e2e: the classes, per-frame protocol, host trajectories
+    def host_universe(dev_frames, box):
+        arr = np.empty((T, N_PART, 3), dtype=np.float32)    # virtual: only this rank's block is ever touched
+        arr[lo:hi] = dev_frames.cpu().numpy()
+        return synthetic.Universe(synthetic.MemoryTrajectory(arr, box))
+
+    u_g, u_s = host_universe(gr_dev, box_g), host_universe(sq_dev, box_s)
+    kw = dict(verbose=False, device=local, distributed=world > 1)
+    rdf_c = RadialDistributionFunction(u_g.atoms, n_bins=GR["n_bins"], range_=(0.0, Lg / 2), exclusion=(1, 1), **kw)
+    sf_c = StructureFactor(u_s.atoms, n_points=SQ["n_points"], q_max=SQ["q_max"], algorithm=args.sq_algo, **kw)
+    from mdcraft_b200.analysis.base import run_together
+
+    run_together([rdf_c, sf_c], start=lo, stop=lo + min(W, K) * b)       # warm-up: first frames of this rank's block
+    barrier()
+    w0 = time.perf_counter()
+    mdist.run_together_sharded([rdf_c, sf_c])                            # _prepare, K x b frames, _conclude (all-reduce)
+    barrier()
+    e2e_s = time.perf_counter() - w0
 
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_ms, sq_ms, gr_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms + fin_ms, e2e_s, sq_ms, gr_ms, coll_ms, fin_ms, (capi_ms + capi_fin_ms) / (n_pin * B), dev_ms],
+                     dtype=torch.float64, device=dev)
     if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    dev_ms, e2e_ms, sq_ms, gr_ms = t.tolist()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s, sq_ms, gr_ms, coll_ms, fin_ms, capi_ms_per_frame, dev_ms = t.tolist()
+    value = T / (total_ms * 1e-3)
+    e2e = T / e2e_s
 
-    total_frames = F * args.steps * world
-    value = total_frames / (dev_ms * 1e-3)
-    e2e = total_frames / (e2e_ms * 1e-3)
+    # ------------------------------------------------------------------ checks (outside every timed region)
+    checks = parity_checks(rank, world, local, dev, ctx, dist, gr_dev, sq_dev, lo, hi, Lg, Ls, box_g, wavevectors, acc_sq,
+                           counts, g_r, ssf, rdf_c, sf_c, unique_q, T)
+    if world > 1:
+        checks["allreduce_check"] = allreduce_check(rank, world, local, dev, dist, pre, counts, acc_sq, ctx, ctx_s, box_g, Lg,
+                                                    Ls, edges, T, args.sq_algo)
+        checks["ok"] = checks["ok"] and checks["allreduce_check"]["result"] == "ok"
 
-    def alone(push, plan, reps=3):
-        """Device time (ms per push of F frames) of one analysis' dominant kernels with the other analysis idle."""
+    # ------------------------------------------------------------------ secondary figures (rank 0 of a single-GPU run)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = secondary_figures(args, ctx, ctx_s, rdf, sqp, gr_dev, sq_dev, box_g, Ls, b, flush, nq)
+
+    if rank == 0:
+        sm = ctx.info()["sm_count"]
+        used = sqp.info()
+        summary = ncu_summary()
+        gr_alone_ms, sq_alone_ms = extras.get("gr_alone_ms"), extras.get("sq_alone_ms")
+        pairs = 0.5 * N_PART * (N_PART - 1) * K * b            # pair-distances this rank's pair kernel evaluated
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 (S(q): NUFFT grid, FFTs, sums) + f32 filter / f64 exact (g(r) distances)",
+            "data": "synthetic", "config": workload_config(B, world, K), "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT,
+                    "through": "RadialDistributionFunction + StructureFactor fed by run_together from host trajectories "
+                               "(_single_frame per frame, pinned staging, _prepare / _conclude with the all-reduce inside; "
+                               "constructors outside), wall clock between barrier + device synchronisation on both sides",
+                    "h2d_bytes_per_step": int(B * N_PART * 3 * 4 * 2 + B * 24),
+                    "d2h_bytes_per_step": int(world * (GR["n_bins"] * 8 + n_shells * 8) / K),
+                    "seconds": e2e_s},
+            "e2e_capi": {"value": 1e3 / capi_ms_per_frame, "unit": UNIT,
+                         "through": "mdc_rdf_push / mdc_sq_push with pinned host buffers + the same finalisation"},
+            "gpu_launches": launches * world,
+            "timing": {"steps_ms": dev_ms, "finalise_ms": fin_ms, "collective_ms": coll_ms,
+                       "how": "CUDA events on the library's compute streams around every step, max over ranks; the finalisation "
+                              "(all-reduce, shell means, D2H, normalisation: host-driven and serial) by wall clock between two "
+                              "device synchronisations, its collectives by CUDA events on torch's stream",
+                       "wall_s": wall},
+            "sustained": {"frames": T, "seconds": wall, "clocks": clocks},
+            "sq_algo": args.sq_algo, "sq_algo_used": used,
+            "streams": "one" if ctx_s is ctx else "g(r) and S(q) on separate streams (side by side)",
+            "timed_kernel_ms_per_step": {"gr": gr_ms / K, "sq": sq_ms / K},
+        }
+        line.update(checks)
+        # g(r): SURVEY.md 8(d) fixes the algorithmic cost of one pair-distance at ~20 FP32/INT-pipe instructions (3 sub,
+        # 3 convert, r^2, sqrt, bin, range test, increment); the ceiling is the issue rate, 4 schedulers x 32 lanes per SM
+        # per clock, divided by that.  That is a MODEL, not a hardware fraction: what the kernel itself issues per pair
+        # and how busy the issue slots are comes from the committed ncu capture, next to it.
+        SLOTS = 20.0
+        gr_peak = sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / SLOTS
+        kn = ncu_kernel(summary, "rdf_pairs_fast")
+        line["roofline_gr"] = {
+            "bound": "issue", "kernel": "rdf_pairs_fast", "achieved": pairs / (gr_ms * 1e-3) / 1e9,
+            "peak": gr_peak / 1e9, "unit": "G pair-distances/s", "frac": pairs / (gr_ms * 1e-3) / gr_peak,
+            "frac_alone": (0.5 * N_PART * (N_PART - 1) * b / (gr_alone_ms * 1e-3) / gr_peak) if gr_alone_ms else None,
+            "traffic": kn.get("dram_bytes") if kn else None,
+            "traffic_source": ncu_source(summary),
+            "issue_active": kn.get("issue_active_pct") if kn else None,
+            "slots_per_pair": kn.get("slots_per_algorithmic_pair") if kn else None,
+            "peak_source": f"MODEL: {sm} SMs x 4 schedulers x 32 lanes x SM clock / {SLOTS:g} issue slots per pair "
+                           "(SURVEY.md 8(d) algorithmic cost); `issue_active` and `slots_per_pair` (ncu) are the hardware-side pair",
+            "algorithmic": "20 FP32/INT issue slots + 1 SFU op (sqrt) + 1 shared-memory atomic per pair-distance "
+                           "(SURVEY.md 8(d)); 24 B of positions per particle per frame (f32 + u32 fixed point)",
+        }
+        roof_sq = None
+        if used["algo"] == "nufft" and sq_alone_ms:
+            roof_sq = nufft_roofline(used, sq_alone_ms, b, nq, summary)
+        line["roofline_sq"] = roof_sq
+        for k in ("direct", "factored", "sq_default_fps"):
+            if k in extras:
+                line[{"direct": "roofline_sfu_direct", "factored": "roofline_fp32_factored",
+                      "sq_default_fps": "sq_default_grid_frames_per_s"}[k]] = extras[k]
+        if gr_alone_ms:
+            line["gr_frames_per_s"] = b / (gr_alone_ms * 1e-3)
+            line["gr_pairs_per_s"] = 0.5 * N_PART * (N_PART - 1) * b / (gr_alone_ms * 1e-3)
+        if sq_alone_ms:
+            line["sq_frames_per_s"] = b / (sq_alone_ms * 1e-3)
+        # the headline roofline: the kernel with the largest share of the step's WORK.  Its `achieved` / `frac` are those
+        # of the timed steps (where it shares the SMs with S(q)), `frac_alone` that of the kernel alone.
+        line["roofline"] = dict(line["roofline_gr"])
+        if gr_alone_ms and sq_alone_ms:
+            line["roofline"]["share_of_step"] = gr_alone_ms / (gr_alone_ms + sq_alone_ms)
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        emit(json.dumps(line))
+        if not checks.get("ok", False):
+            sys.stderr.write("bench.py: a parity check FAILED: " + json.dumps(checks) + "\n")
+    failed = not checks.get("ok", False)
+    if world > 1:
+        flag = torch.tensor([1.0 if failed else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        failed = bool(flag.item())
+        dist.destroy_process_group()
+    return 3 if failed else 0
+
+
+def nufft_roofline(used, sq_alone_ms, frames, nq, summary):
+    """HBM roofline of the NUFFT chain (memset, spread, three pruned FFT passes, pair accumulation):
+    algorithmic bytes = every buffer written once and read once, 16 B per complex FP64."""
+    nf, n = used["nf"], SQ["n_points"]
+    ncp = (n + 1) & ~1
+    alg = 16.0 * (nf ** 3                                   # clear the fine grid
+                  + 2 * nf ** 3                            # spread: read-modify-write of the fine grid
+                  + nf ** 3 + nf * nf * ncp                # z pass
+                  + nf * nf * ncp + nf * n * ncp           # y pass
+                  + nf * n * ncp + nq                      # x pass + deconvolution
+                  + 2 * nq)                                # rho -> |rho|^2 accumulated into ssf
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peak_gbs, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md): 6.65 TB/s"
+    ach = alg * frames / (sq_alone_ms * 1e-3) / 1e9
+    traffic = None
+    if summary:
+        parts = [k.get("dram_bytes_per_frame") for k in summary.get("kernels", []) if k.get("name", "").startswith("nufft_")]
+        if parts and all(p is not None for p in parts):
+            traffic = float(sum(parts))
+    return {"bound": "hbm", "measured": "S(q) alone (in the timed steps these kernels share the device with g(r))",
+            "kernel": "nufft_spread + nufft_fft_z + nufft_fft_s<0> + nufft_fft_s<1> (+ memset, sq_pair_accum)",
+            "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+            "traffic": traffic, "traffic_unit": "bytes per frame (sum of the NUFFT kernels)", "traffic_source": ncu_source(summary),
+            "peak_source": peak_src,
+            "algorithmic": f"{alg / 1e6:.0f} MB per frame: fine grid {nf}^3 complex FP64 cleared, spread into (w = {used['w']}) "
+                           f"and read once; pruned intermediates {nf}^2 x {n} and {nf} x {n}^2 written and read once; {nq} densities"}
+
+
+def secondary_figures(args, ctx, ctx_s, rdf, sqp, gr_dev, sq_dev, box_g, Ls, b, flush, nq):
+    """Each analysis by itself, the reference's default grid, and the O(Nq N) kernels against their issue-rate rooflines."""
+    import torch
+
+    from mdcraft_b200 import _capi
+
+    out = {}
+
+    def alone(push, plan, reps=2):
         ms = 0.0
         for _ in range(reps):
             flush.fill_(1)
@@ -318,50 +644,50 @@ def run_native(args, rank, world, emit=print):
             ms += plan.last_push_stats()[0]
         return ms / reps
 
+    rdf.reset()
+    sqp.reset()
     rdf.set_blocks_per_sm(0)       # by itself g(r) takes the whole SM
-    gr_alone_ms = alone(lambda: rdf.push(gr_dev, None, box_g, n_frames=F), rdf)
-    sq_alone_ms = alone(lambda: sqp.push(sq_dev, n_frames=F), sqp)
+    out["gr_alone_ms"] = alone(lambda: rdf.push(gr_dev[:b], None, box_g, n_frames=b), rdf)
+    out["sq_alone_ms"] = alone(lambda: sqp.push(sq_dev[:b], n_frames=b), sqp)
+    if ctx_s is not ctx:
+        rdf.set_blocks_per_sm(3)
 
-    # secondary figure: the reference's DEFAULT grid (n_points = 32, Nq = 32,768) on the same frames, device resident
-    sq_default_fps = None
-    if not args.no_extras:
-        sqd = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=32, L0=[Ls] * 3, algo=args.sq_algo)
-        rep = 16
-        for _ in range(3):
-            sqd.push(sq_dev, n_frames=F)
-        ctx.synchronize()
-        ctx.mark(0)
-        for _ in range(rep):
-            sqd.push(sq_dev, n_frames=F)
-        ctx.mark(1)
-        sq_default_fps = F * rep / (ctx.elapsed_ms() * 1e-3)
-        sqd.close()
+    # the reference's DEFAULT grid (n_points = 32, Nq = 32,768) on the same frames, device resident
+    sqd = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=32, L0=[Ls] * 3, algo=args.sq_algo)
+    F, rep = min(b, 8), 8
+    for _ in range(3):
+        sqd.push(sq_dev[:F], n_frames=F)
+    ctx.synchronize()
+    ctx.mark(0)
+    for _ in range(rep):
+        sqd.push(sq_dev[:F], n_frames=F)
+    ctx.mark(1)
+    out["sq_default_fps"] = F * rep / (ctx.elapsed_ms() * 1e-3)
+    sqd.close()
 
     sm = ctx.info()["sm_count"]
-    used = sqp.info()
+    summary = ncu_summary()
 
-    def term_roofline(algo, ms, frames):
-        """Issue-rate roofline of one of the O(Nq N) lattice kernels from its device time over `frames` frames."""
-        ach = float(nq) * N_PART * frames / (ms * 1e-3)
+    def term_roofline(algo, ms):
+        ach = float(nq) * N_PART / (ms * 1e-3)
+        kn = ncu_kernel(summary, "sq_lattice_" + algo)
+        traffic = kn.get("dram_bytes") if kn else None
         if algo == "direct":
             pk = ctx.probe_rate("mufu_sincos_pairs")      # measured on this box, this run
             return {"bound": "sfu", "kernel": "sq_lattice_direct", "achieved": ach / 1e9, "peak": pk / 1e9,
-                    "unit": "G(q,particle) terms/s", "frac": ach / pk, "frames_per_s": frames * 1e3 / ms,
-                    "traffic": 5.8e7,
+                    "unit": "G(q,particle) terms/s", "frac": ach / pk, "frames_per_s": 1e3 / ms,
+                    "traffic": traffic, "traffic_source": ncu_source(summary) if kn else "not captured: omitted",
                     "peak_source": f"measured in this run: MUFU.SIN+MUFU.COS pairs/s (mdc_probe_rate); nominal {sm} SMs x 8 pairs/clk",
                     "algorithmic": "2 SFU ops + ~10 FP32/INT issue slots per term"}
         pk = ctx.probe_rate("ffma") / 4.0                 # 4 FP32 FMAs (2 packed FFMA2) per term
         return {"bound": "fp32", "kernel": "sq_lattice_factored", "achieved": ach / 1e9, "peak": pk / 1e9,
-                "unit": "G(q,particle) terms/s", "frac": ach / pk, "frames_per_s": frames * 1e3 / ms,
-                "traffic": 6.8e8,
-                "peak_source": (f"measured in this run: FFMA/s / 4 (mdc_probe_rate); nominal {sm} SMs x 128 FMA/clk / 4; "
-                                f"FFMA2 in this kernel's operand pattern sustains {ctx.probe_rate('ffma2_loop') / 2e9:.0f} G terms/s"),
+                "unit": "G(q,particle) terms/s", "frac": ach / pk, "frames_per_s": 1e3 / ms,
+                "traffic": traffic, "traffic_source": ncu_source(summary) if kn else "not captured: omitted",
+                "peak_source": f"measured in this run: FFMA/s / 4 (mdc_probe_rate); nominal {sm} SMs x 128 FMA/clk / 4",
                 "algorithmic": "one complex FMA = 4 FP32 FMAs (2 x fma.rn.f32x2) per term; 56 table phasors per 4096 terms"}
 
     def one_frame(algo):
-        """One frame of the full grid through an O(Nq N) kernel (L2 flushed first): its device time in ms."""
-        sqx = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=SQ["n_points"], L0=[Ls] * 3, q_max=SQ["q_max"],
-                           algo=algo)
+        sqx = _capi.SqPlan(ctx, [N_PART], [(None, None)], n_points=SQ["n_points"], L0=[Ls] * 3, q_max=SQ["q_max"], algo=algo)
         sqx.push(sq_dev[:1], n_frames=1)
         ctx.synchronize()
         flush.fill_(1)
@@ -372,102 +698,112 @@ def run_native(args, rank, world, emit=print):
         sqx.close()
         return ms
 
-    # secondary figures: the kernels the NUFFT replaced, on the same full grid against their issue-rate rooflines
-    # (direct = the contract kernel of BASELINE.json's north_star: one fused sin/cos per term on the SFU)
-    direct = factored = None
-    if rank == 0 and not args.no_extras:
-        if used["algo"] != "direct":
-            direct = term_roofline("direct", one_frame("direct"), 1)
-        if used["algo"] != "factored":
-            factored = term_roofline("factored", one_frame("factored"), 1)
+    used = sqp.info()["algo"]
+    if used != "direct":
+        out["direct"] = term_roofline("direct", one_frame("direct"))
+    if used != "factored":
+        out["factored"] = term_roofline("factored", one_frame("factored"))
+    return out
 
-    # the once-per-run exchange step: all-reduce of the accumulators over NVLink (outside the timed steps)
+
+def parity_checks(rank, world, local, dev, ctx, dist, gr_dev, sq_dev, lo, hi, Lg, Ls, box_g, wavevectors, acc_sq, counts, g_r,
+                  ssf, rdf_c, sf_c, unique_q, T):
+    """
+    The outputs of the timed regions against the CPU oracle (test infrastructure; never on the measured path):
+      * S(q): the all-reduced accumulator of the timed steps on 64 random wavevectors of the full grid against
+        sum over EVERY frame of the job of |delta_fourier_transform_sum|^2 (every rank restates its own frames);
+      * g(r): the kernel's counts for a slab of 512 particles of this job's first frame against all 100,000
+        (exclusion (1, 1)) against the oracle, bit for bit; identities of the timed histogram (every count even,
+        in-range fraction pi / 6 of an ideal gas);
+      * the class path (`e2e`) against the plan path (`value`): same frames, so the histogram must be EQUAL and
+        the shell means of S(q) equal to rounding.
+    """
+    import torch
+
+    from oracle import oracle
+
+    out = {}
+    cores = max(1, len(os.sched_getaffinity(0)) // world)
+    oracle.set_num_threads(cores)
+    t0 = time.perf_counter()
+    idx = np.sort(np.random.default_rng(20).choice(len(wavevectors), 64, replace=False))
+    part = np.zeros(64)
+    frames_host = sq_dev.cpu().numpy()
+    for f in range(hi - lo):
+        part += np.abs(oracle.delta_fourier_transform_sum(wavevectors[idx], frames_host[f].astype(np.float64))) ** 2
+    want = torch.from_numpy(part).to(dev)
     if world > 1:
-        from mdcraft_b200 import distributed as mdist
-
-        mdist.all_reduce_device(rdf.accumulator(), device=local)
-        mdist.all_reduce_device(sqp.accumulator(), device=local)
-
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+    want = want.cpu().numpy() / (T * N_PART)
+    got = acc_sq[idx] / (T * N_PART)
+    # the 1e-5 contract plus the error model of DESIGN.md 3.10 where the frame-averaged S is tiny (kappa = 1e-8)
+    tol = 1e-5 * want + 2 * 5 * 1e-8 * np.sqrt(want) + 1e-12
+    out["sq_max_rel_err_64_wavevectors_all_frames"] = float(np.max(np.abs(got / want - 1.0)))
+    out["sq_max_err_over_tolerance"] = float(np.max(np.abs(got - want) / tol))
+    ok = bool(np.all(np.abs(got - want) <= tol))
     if rank == 0:
-        frames_rank = F * args.steps
-        if used["algo"] == "nufft":
-            # HBM roofline of the NUFFT chain (memset, spread, three pruned FFT passes, pair accumulation):
-            # algorithmic bytes = every buffer written once and read once, 16 B per complex FP64
-            nf, n = used["nf"], SQ["n_points"]
-            ncp = (n + 1) & ~1
-            alg = 16.0 * (nf ** 3                                   # clear the fine grid
-                          + 2 * nf ** 3                            # spread: read-modify-write of the fine grid
-                          + nf ** 3 + nf * nf * ncp                # z pass
-                          + nf * nf * ncp + nf * n * ncp           # y pass
-                          + nf * n * ncp + nq                      # x pass + deconvolution
-                          + 2 * nq)                                # rho -> |rho|^2 accumulated into ssf
-            peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-            if os.path.exists(peaks_file):
-                peak_gbs, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)"
-            else:
-                peak_gbs, peak_src = 6650.0, "of fallback (B200_PROFILING.md): 6.65 TB/s"
-            ach = alg * F / (sq_alone_ms * 1e-3) / 1e9
-            roof_sq = {"bound": "hbm", "measured": "S(q) alone (in the timed steps these kernels share the device with g(r))",
-                       "kernel": "nufft_spread + nufft_fft_z + nufft_fft_s<0> + nufft_fft_s<1> (+ memset, sq_pair_accum)",
-                       "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                       "traffic": NUFFT_DRAM_BYTES_PER_FRAME, "peak_source": peak_src,
-                       "algorithmic": f"{alg / 1e6:.0f} MB per frame: fine grid {nf}^3 complex FP64 cleared, spread into (w = {used['w']}: "
-                                      f"{used['w'] ** 3} FP64 complex reductions per particle, L2 resident) and read once; pruned "
-                                      f"intermediates {nf}^2 x {n} and {nf} x {n}^2 written and read once; {nq} densities"}
-        else:
-            roof_sq = term_roofline(used["algo"], sq_alone_ms, F)
-        pairs = 0.5 * N_PART * (N_PART - 1) * F * args.steps
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (S(q): NUFFT grid, FFTs, sums) + f32 filter / f64 exact (g(r) distances)",
-            "data": "synthetic", "config": workload_config(F, world), "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT,
-                    "h2d_bytes_per_step": int(gr_host.nbytes + sq_host.nbytes + F * 24),
-                    "d2h_bytes_per_step": int(GR["n_bins"] * 8 + n_shells * 8)},
-            "gpu_launches": launches,
-            "sq_algo": args.sq_algo, "sq_algo_used": used,
-            "roofline_sq": roof_sq,
-            "roofline_sfu_direct": direct,
-            "roofline_fp32_factored": factored,
-            # each analysis by itself (the other idle), and the kernel time each spent inside the timed steps
-            "sq_frames_per_s": F / (sq_alone_ms * 1e-3),
-            "sq_default_grid_frames_per_s": sq_default_fps,
-            "gr_frames_per_s": F / (gr_alone_ms * 1e-3),
-            "gr_pairs_per_s": 0.5 * N_PART * (N_PART - 1) * F / (gr_alone_ms * 1e-3),
-            "streams": "one" if ctx_s is ctx else "g(r) and S(q) on separate streams (side by side)",
-            "timed_kernel_ms_per_step": {"gr": gr_ms / args.steps, "sq": sq_ms / args.steps},
-            "wall_s": wall,
-        }
-        # g(r): SURVEY.md 8(d) fixes the algorithmic cost of one pair-distance at ~20 FP32/INT-pipe instructions (3 sub,
-        # 3 convert, r^2, sqrt, bin, range test, increment); the ceiling is the issue rate, 4 schedulers x 32 lanes per SM
-        # per clock, divided by that.  The kernel's own count is reported next to it and is NOT the denominator: it was
-        # 19.9 at the start of the round and is 15.1 in the hot loop now (SASS: 121 executed per 8 pairs), 15.6 per
-        # algorithmic pair over the whole kernel (tile staging, culling tests, undecided-pair path; 19 % of the pairs are
-        # culled and never evaluated; ncu, profiles/rdf_fast_r01.txt).
-        SLOTS = 20.0
-        gr_peak = sm * 4 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / SLOTS
-        line["roofline_gr"] = {
-            "bound": "issue", "kernel": "rdf_pairs_fast", "achieved": pairs / (gr_ms * 1e-3) / 1e9,
-            "peak": gr_peak / 1e9, "unit": "G pair-distances/s", "frac": pairs / (gr_ms * 1e-3) / gr_peak,
-            "frac_alone": 0.5 * N_PART * (N_PART - 1) * F / (gr_alone_ms * 1e-3) / gr_peak,
-            "traffic": 3.1e6, "peak_source": f"{sm} SMs x 4 schedulers x 32 lanes x SM clock / {SLOTS:g} issue slots per pair "
-                                             "(SURVEY.md 8(d) algorithmic cost)",
-            "algorithmic": "20 FP32/INT issue slots + 1 SFU op (sqrt) + 1 shared-memory atomic per pair-distance "
-                           "(SURVEY.md 8(d)); 24 B of positions per particle per frame (f32 + u32 fixed point)",
-            "kernel_slots_per_pair": {"hot_loop_sass": 15.1, "whole_kernel_ncu_per_algorithmic_pair": 15.6},
-        }
-        # the headline roofline: the kernel with the largest share of the step's WORK (device time of each analysis by
-        # itself; side by side on two streams their durations overlap and stretch, so shares of the wall time do not
-        # add up).  Its `achieved` / `frac` are those of the timed steps, `frac_alone` that of the kernel alone.
-        share_gr = gr_alone_ms / (gr_alone_ms + sq_alone_ms)
-        line["roofline"] = dict(line["roofline_gr"] if share_gr >= 0.5 else roof_sq)
-        line["roofline"]["share_of_step"] = max(share_gr, 1.0 - share_gr)
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline()
-        emit(json.dumps(line))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+        pos = gr_dev[0].cpu().numpy()
+        slab = ctx.radial_histogram(pos[:512], pos, GR["n_bins"], (0.0, Lg / 2), box_g, (1, 1))
+        want_h = oracle.radial_histogram(pos[:512], pos, GR["n_bins"], (0.0, Lg / 2), box_g, exclusion=(1, 1))
+        out["gr_slab_equal"] = bool(np.array_equal(slab, want_h))
+        frac = float(counts.sum() / (T * N_PART * (N_PART - 1.0)))
+        out["gr_in_range_fraction_minus_pi_6"] = frac - np.pi / 6
+        ok = ok and out["gr_slab_equal"] and bool((counts % 2 == 0).all()) and abs(frac - np.pi / 6) < 2e-4
+        # class path vs plan path
+        out["classes_counts_equal_plans"] = bool(np.array_equal(rdf_c.results.counts, counts))
+        out["classes_rdf_max_rel"] = float(np.max(np.abs(rdf_c.results.rdf[counts > 0] / g_r[counts > 0] - 1.0)))
+        order = np.argsort(unique_q)
+        out["classes_ssf_max_rel"] = float(np.max(np.abs(sf_c.results.ssf[0] / ssf[0][order] - 1.0)))
+        ok = ok and out["classes_counts_equal_plans"] and out["classes_rdf_max_rel"] < 1e-12 and out["classes_ssf_max_rel"] < 1e-10
+    out["parity_check_seconds"] = time.perf_counter() - t0
+    out["ok"] = bool(ok)
+    out["parity_check"] = "ok" if ok else "FAILED"
+    return out
+
+
+def allreduce_check(rank, world, local, dev, dist, pre, counts, acc_sq, ctx, ctx_s, box_g, Lg, Ls, edges, T, sq_algo):
+    """N > 1: the NCCL all-reduce of the timed run against the ranks' own accumulators gathered BEFORE it (integer sum:
+    equal; FP64: 1e-13), and for N <= 2 against a single-GPU pass over all T frames of the job."""
+    import torch
+
+    from mdcraft_b200 import _capi
+
+    out = {}
+    hist = [torch.empty_like(pre[0]) for _ in range(world)]
+    sums = [torch.empty_like(pre[1]) for _ in range(world)]
+    dist.all_gather(hist, pre[0])
+    dist.all_gather(sums, pre[1])
+    ok = True
+    if rank == 0:
+        total_h = np.sum([h.cpu().numpy().astype(np.int64) for h in hist], axis=0)
+        total_s = np.sum([s.cpu().numpy() for s in sums], axis=0)
+        out["histogram_equals_sum_of_ranks"] = bool(np.array_equal(total_h, counts))
+        out["sq_max_rel_vs_sum_of_ranks"] = float(np.max(np.abs(acc_sq - total_s) / np.maximum(np.abs(total_s), 1e-300)))
+        ok = out["histogram_equals_sum_of_ranks"] and out["sq_max_rel_vs_sum_of_ranks"] < 1e-13
+        if world <= 2:
+            rdf1 = _capi.RdfPlan(ctx, GR["n_bins"], (edges[0], edges[-1]), N_PART, None, (1, 1))
+            sq1 = _capi.SqPlan(ctx_s, [N_PART], [(None, None)], n_points=SQ["n_points"], L0=[Ls] * 3, q_max=SQ["q_max"], algo=sq_algo)
+            step = 48
+            for f0 in range(0, T, step):
+                f1 = min(T, f0 + step)
+                g, _ = device_frames("gr", f0, f1, dev)
+                s, _ = device_frames("sq", f0, f1, dev)
+                torch.cuda.synchronize()
+                rdf1.push(g, None, box_g, n_frames=f1 - f0)
+                sq1.push(s, n_frames=f1 - f0)
+                ctx.synchronize()
+                ctx_s.synchronize()
+            c1, _ = rdf1.read()
+            s1 = sq1.read()[0][0]
+            out["histogram_equals_single_gpu"] = bool(np.array_equal(c1, counts))
+            out["sq_max_rel_vs_single_gpu"] = float(np.max(np.abs(acc_sq - s1) / np.maximum(np.abs(s1), 1e-300)))
+            ok = ok and out["histogram_equals_single_gpu"] and out["sq_max_rel_vs_single_gpu"] < 1e-11
+            rdf1.close()
+            sq1.close()
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.broadcast(flag, 0)
+    out["result"] = "ok" if flag.item() == 1.0 else "FAILED"
+    return out
 
 
 def main():
@@ -475,14 +811,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=2, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=48, help="frames per step, over all GPUs (a multiple of --gpus)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--one-stream", action="store_true",
                     help="queue g(r) and S(q) on ONE context (the two analyses then run back to back, not side by side)")
     ap.add_argument("--no-extras", action="store_true",
-                    help="skip the secondary figures (default grid, one frame each through the direct / factored S(q) "
-                         "kernels): only the timed steps launch kernels, which is what the ncu launch list is taken from")
+                    help="skip the secondary figures (each analysis alone, default grid, one frame each through the direct / "
+                         "factored S(q) kernels): only the timed steps launch kernels, which is what the ncu launch list is taken from")
+    ap.add_argument("--full-capi-e2e", action="store_true", help="e2e_capi over up to 192 frames instead of 4 steps")
     ap.add_argument("--sq-algo", default="auto", choices=["auto", "direct", "factored", "nufft"],
                     help="S(q) lattice kernel: auto (the plan's cost model: NUFFT on this grid), or force one")
     args = ap.parse_args()
@@ -495,17 +832,19 @@ def main():
     os.dup2(2, 1)
     lines = []
     emit = lines.append
+    rc = 0
     try:
         if args.impl == "reference":
             run_reference(args, rank, emit)
         else:
-            run_native(args, rank, world, emit)
+            rc = run_native(args, rank, world, emit)
     finally:
         sys.stdout.flush()
         os.dup2(saved, 1)
         os.close(saved)
     for line in lines:
         print(line, flush=True)
+    sys.exit(rc or 0)
 
 
 if __name__ == "__main__":

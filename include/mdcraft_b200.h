@@ -46,7 +46,7 @@ extern "C" {
 #define MDC_ERR_INVALID       -1   /* bad argument */
 #define MDC_ERR_CUDA          -2   /* CUDA runtime error (message has details) */
 #define MDC_ERR_NOMEM         -3
-#define MDC_ERR_UNSUPPORTED   -4   /* e.g. triclinic box */
+#define MDC_ERR_UNSUPPORTED   -4   /* e.g. a dump layout the GPU parser does not take */
 
 #define MDC_PRECISION_FP32     0   /* phases exact (fixed point / FP64), sin/cos on the SFU, FP32 partial sums */
 #define MDC_PRECISION_FP64     1   /* everything FP64 (reference arithmetic) */
@@ -232,8 +232,11 @@ int  mdc_rdf_plan_destroy(mdc_rdf_plan *plan);
 /*
  * Accumulates n_frames frames.  pos_a f32 (n_frames, n_a, 3); pos_b f32
  * (n_frames, n_b, 3) or NULL when same_group; box f32 (n_frames, 6)
- * [lx, ly, lz, alpha, beta, gamma] (host memory always).  Only orthorhombic
- * boxes (90/90/90) are supported: MDC_ERR_UNSUPPORTED otherwise.
+ * [lx, ly, lz, alpha, beta, gamma] (host memory always).  The reference hands all six values to capped_distance
+ * (structure.py:109-115).  Orthorhombic frames (90/90/90) go through the FP32 filter + FP64 kernel pair; frames with
+ * any other angle take MDAnalysis' triclinic routine in FP64 for every pair (triclinic_vectors, _triclinic_pbc,
+ * minimum_image_triclinic: coordinates moved into the primary cell, then the shortest of the 27 nearest images), about
+ * 40x slower per pair.  MDC_ERR_INVALID for angles that do not describe a cell.
  * Groups of 4096 particles or more are put in Hilbert order of a cell grid on the device first, and the pair kernel
  * skips the blocks of pairs farther apart than r1 (what capped_distance's grid search does for the reference,
  * structure.py:109-115); counts do not depend on it.  Environment, for diagnostics: MDC_RDF_SORT=0 keeps the original

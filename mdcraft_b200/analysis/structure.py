@@ -399,6 +399,7 @@ class RadialDistributionFunction(_DeviceBlockRun, DynamicAnalysisBase):
         self._frame_block = max(1, int(frame_block))
         self._distributed = bool(distributed)
         self._plan = None
+        self._stage_a = self._stage_b = None
 
     # -- AnalysisBase protocol ------------------------------------------------
     def _prepare(self) -> None:
@@ -414,15 +415,27 @@ class RadialDistributionFunction(_DeviceBlockRun, DynamicAnalysisBase):
         n_a = _entity_count(self._groups[0], self._groupings[0])
         n_b = _entity_count(self._groups[1], self._groupings[1])
         edges = self.results.bin_edges
-        if self._plan is not None:
-            self._plan.close()
-        self._plan = _capi.RdfPlan(
-            _context(self._device), self._n_bins, (edges[0], edges[-1]), n_a, None if self._same else n_b,
-            self._exclusion,
-        )
-        self._stage_a = _FrameBlock(self._frame_block, n_a)
-        self._stage_b = None if self._same else _FrameBlock(self._frame_block, n_b)
-        self._stage_box = np.empty((self._frame_block, 6), dtype=np.float32)
+        # the plan (device buffers, thresholds) and the pinned staging blocks are kept from one run() to the next as
+        # long as nothing they were sized for has changed: a repeated run() only clears the accumulator
+        sig = (n_a, None if self._same else n_b, int(self._n_bins), float(edges[0]), float(edges[-1]),
+               None if not self._exclusion else tuple(int(e) for e in self._exclusion), self._device, self._frame_block)
+        if self._plan is not None and getattr(self, "_plan_sig", None) == sig and self._stage_a is not None:
+            self._plan.reset()
+            self._plan.set_blocks_per_sm(0)
+            self._stage_a.count = 0
+            if self._stage_b is not None:
+                self._stage_b.count = 0
+        else:
+            if self._plan is not None:
+                self._plan.close()
+            self._plan = _capi.RdfPlan(
+                _context(self._device), self._n_bins, (edges[0], edges[-1]), n_a, None if self._same else n_b,
+                self._exclusion,
+            )
+            self._plan_sig = sig
+            self._stage_a = _FrameBlock(self._frame_block, n_a)
+            self._stage_b = None if self._same else _FrameBlock(self._frame_block, n_b)
+            self._stage_box = np.empty((self._frame_block, 6), dtype=np.float32)
         self._frames_seen = 0
 
     def _single_frame(self) -> None:
@@ -521,7 +534,6 @@ class RadialDistributionFunction(_DeviceBlockRun, DynamicAnalysisBase):
         self._n_frames_norm = n_frames
         with np.errstate(divide="ignore", invalid="ignore"):
             self.results.rdf = self.results.counts / norm
-        self._stage_a = self._stage_b = None
 
     # -- post-processing (structure.py:1012-1201) ------------------------------
     def _get_rdf(self) -> np.ndarray:
@@ -775,7 +787,15 @@ class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
         # the grid is built on the device; the host only needs it for |q| bookkeeping
         self._wavevectors = self._plan.wavevectors()
         self._wavenumbers = np.linalg.norm(self._wavevectors, axis=1)
+        # The grid is fixed at construction (structure.py:1822-1887), and so is everything derived from it: the unique
+        # |q| of structure.py:1923-1926 and the np.isclose windows of structure.py:2000-2009 are formed once, here,
+        # instead of in every run()'s _prepare / _conclude (a sort of Nq values: 0.2 s on the q_max = 20 grid).
+        self._unique_q = np.unique(self._wavenumbers.round(11)) if self._unique else None
         self._shells = None
+        if self._unique and type(self) is StructureFactor:
+            self._shells = shell_windows(self._wavenumbers, self._unique_q)
+            self._plan.set_shells(*self._shells)
+        self._stage = None
 
     def _stage_dtype(self):
         """float32 positions of atoms are staged as they are; centres of mass keep their float64."""
@@ -785,10 +805,13 @@ class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
     def _prepare(self) -> None:
         self.results.pairs = self._pairs()
         self._plan.reset()
-        self._stage = _FrameBlock(self._frame_block, self._N, dtype=self._stage_dtype())
+        if self._stage is None:   # pinned staging, kept from one run() to the next
+            self._stage = _FrameBlock(self._frame_block, self._N, dtype=self._stage_dtype())
+        self._stage.count = 0
         self._frames_seen = 0
-        self.results.ssf = np.zeros((len(self.results.pairs), len(self._wavenumbers)))
-        self.results.wavenumbers = np.unique(self._wavenumbers.round(11)) if self._unique else self._wavenumbers
+        # structure.py:1922 allocates zeros((n_pairs, Nq)) here; _conclude replaces it, so it is not materialised
+        self.results.ssf = None
+        self.results.wavenumbers = self._unique_q.copy() if self._unique else self._wavenumbers
         self.results.units = Hash({"wavenumbers": _ANGSTROM**-1 if _ureg is not None else "1 / angstrom"})
 
     def _single_frame(self) -> None:
@@ -836,9 +859,6 @@ class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
         # structure.py:1995-2014
         if self._unique and type(self) is StructureFactor:
             # the |q|-shell means are formed on the device (sq_shell_mean): N_unique values per pair cross the bus
-            if self._shells is None:
-                self._shells = shell_windows(self._wavenumbers, self.results.wavenumbers)
-                self._plan.set_shells(*self._shells)
             ssf, _ = self._plan.read_shells(float(n_frames * self._N))
         else:
             ssf, _ = self._plan.read()
@@ -850,7 +870,6 @@ class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
             order = np.argsort(self.results.wavenumbers)
             self.results.wavenumbers = self.results.wavenumbers[order]
             self.results.ssf = self.results.ssf[:, order]
-        self._stage = None
 
 
 def _combine_last_axis(values: np.ndarray, wavenumbers: np.ndarray, unique_q: np.ndarray) -> np.ndarray:

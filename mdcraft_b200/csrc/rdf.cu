@@ -37,6 +37,13 @@ struct FrameBox {
     int pad;
 };
 
+// Triclinic frames (any box angle != 90): the lower-triangular box matrix of MDAnalysis' triclinic_vectors, float32
+// values widened: a = (ax, 0, 0), b = (bx, by, 0), c = (cx, cy, cz).  on == 0: orthorhombic frame (FrameBox applies).
+struct FrameTri {
+    double ax, bx, by, cx, cy, cz;
+    int on, pad;
+};
+
 // ------------------------------------------------------------------------------------------
 // host: thresholds (the plan's own statement of numba_histogram's arithmetic)
 // ------------------------------------------------------------------------------------------
@@ -112,10 +119,43 @@ struct FrameFast {
     int pad;
 };
 
+// MDAnalysis' _triclinic_pbc for one coordinate (calc_distances.h; restated in oracle/oracle.c:orc_triclinic_wrap, same
+// operations in the same order, no FMA contraction): into the primary cell along c, then b, then a.
+__device__ __forceinline__ void tri_wrap(float &xf, float &yf, float &zf, const FrameTri &t)
+{
+    const double bi0 = __ddiv_rn(1.0, t.ax), bi4 = __ddiv_rn(1.0, t.by), bi8 = __ddiv_rn(1.0, t.cz);
+    const double a_y = __dmul_rn(t.bx, bi4), b_z = __dmul_rn(t.cy, bi8);
+    const double a_z = __dmul_rn(__dsub_rn(t.cx, __dmul_rn(t.cy, a_y)), bi8);
+    double x = (double)xf, y = (double)yf, z = (double)zf;
+    if (z < 0.0 || z >= t.cz) {
+        const double s = floor(__dmul_rn(z, bi8));
+        z = __dsub_rn(z, __dmul_rn(s, t.cz));
+        y = __dsub_rn(y, __dmul_rn(s, t.cy));
+        x = __dsub_rn(x, __dmul_rn(s, t.cx));
+    }
+    double lb = __dmul_rn(z, b_z);
+    if (y < lb || y >= __dadd_rn(lb, t.by)) {
+        const double s = floor(__dmul_rn(__dsub_rn(y, lb), bi4));
+        y = __dsub_rn(y, __dmul_rn(s, t.by));
+        x = __dsub_rn(x, __dmul_rn(s, t.bx));
+    }
+    lb = __dadd_rn(__dmul_rn(y, a_y), __dmul_rn(z, a_z));
+    if (x < lb || x >= __dadd_rn(lb, t.ax)) {
+        const double s = floor(__dmul_rn(__dsub_rn(x, lb), bi0));
+        x = __dsub_rn(x, __dmul_rn(s, t.ax));
+    }
+    xf = (float)x;
+    yf = (float)y;
+    zf = (float)z;
+}
+
 // raw f32 (F, N, 3) -> soa f32 (F, 3, N); also fix u32 (F, 3, N) = frac(x / L) * 2^32 and the per-frame
 // max |coordinate| (float bits, atomicMax) that bounds the float32 subtraction error of the reference.
+// Triclinic frames: soa holds the coordinates moved into the primary cell (what the reference's distance routine
+// works on); fix is not used by the kernel that takes such frames.
 __global__ void rdf_prep(const float *__restrict__ raw, int64_t N, int64_t total, const FrameBox *__restrict__ boxes,
-                         float *__restrict__ soa, uint32_t *__restrict__ fix, unsigned *__restrict__ absmax)
+                         const FrameTri *__restrict__ tri, float *__restrict__ soa, uint32_t *__restrict__ fix,
+                         unsigned *__restrict__ absmax)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.f;
@@ -124,9 +164,12 @@ __global__ void rdf_prep(const float *__restrict__ raw, int64_t N, int64_t total
         f = i / N;
         const int64_t j = i - f * N;
         const FrameBox fb = boxes[f];
+        float p[3] = {raw[3 * i], raw[3 * i + 1], raw[3 * i + 2]};
+        const FrameTri ft = tri[f];
+        if (ft.on) tri_wrap(p[0], p[1], p[2], ft);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float x = raw[3 * i + k];
+            const float x = p[k];
             soa[(f * 3 + k) * N + j] = x;
             double s = fb.pbc[k] ? (double)x / fb.box[k] : 0.0;
             s -= floor(s);
@@ -182,6 +225,7 @@ struct RdfArgs {
     const float *a, *b;        // SoA f32 (F, 3, Na), (F, 3, Nb); b == a for a self-RDF
     const uint32_t *ua, *ub;   // SoA u32 fixed-point fractions, same shapes
     const FrameBox *boxes;     // (F)
+    const FrameTri *tri;       // (F): triclinic frames (exact kernel only)
     const FrameFast *fast;     // (F)
     const double *T;           // (B + 1)
     unsigned long long *counts;
@@ -376,6 +420,30 @@ __device__ __forceinline__ double exact_r2(float xi, float yi, float zi, float x
     return r2;
 }
 
+// The reference's r^2 for one pair of a TRICLINIC frame, bit for bit (calc_distances.h: minimum_image_triclinic on the
+// float32 difference of coordinates already moved into the primary cell; restated in oracle/oracle.c): the shortest
+// of the 27 images dx + ix a + iy b + iz c.  The image shifts are +-(one float32 matrix entry), exact in double.
+__device__ __forceinline__ double tri_r2(float xi, float yi, float zi, float xj, float yj, float zj, const FrameTri &t)
+{
+    const double d0 = (double)(xj - xi), d1 = (double)(yj - yi), d2 = (double)(zj - zi);
+    double best = 3.4028234663852886e38;   // FLT_MAX
+#pragma unroll
+    for (int ix = -1; ix < 2; ++ix) {
+        const double rx = __dadd_rn(d0, ix * t.ax);
+#pragma unroll
+        for (int iy = -1; iy < 2; ++iy) {
+            const double ry0 = __dadd_rn(rx, iy * t.bx), ry1 = __dadd_rn(d1, iy * t.by);
+#pragma unroll
+            for (int iz = -1; iz < 2; ++iz) {
+                const double rz0 = __dadd_rn(ry0, iz * t.cx), rz1 = __dadd_rn(ry1, iz * t.cy), rz2 = __dadd_rn(d2, iz * t.cz);
+                const double dsq = __dadd_rn(__dadd_rn(__dmul_rn(rz0, rz0), __dmul_rn(rz1, rz1)), __dmul_rn(rz2, rz2));
+                best = fmin(best, dsq);
+            }
+        }
+    }
+    return best;
+}
+
 // Exact bin of an exact r^2 (-1: not counted), by comparison with the precomputed thresholds.
 __device__ __forceinline__ int exact_bin(double r2, const RdfArgs &A, const double *sT)
 {
@@ -403,15 +471,16 @@ template <bool CHECK>
 __device__ __forceinline__ void tile_pairs(const RdfArgs &A, const float4 *__restrict__ sj, int nj, int64_t j0,
                                            const float (&xi)[RDF_IPT], const float (&yi)[RDF_IPT],
                                            const float (&zi)[RDF_IPT], const int (&bi)[RDF_IPT],
-                                           const int64_t (&ig)[RDF_IPT], const FrameBox &fb, const double *sT,
-                                           unsigned *hist, bool diag)
+                                           const int64_t (&ig)[RDF_IPT], const FrameBox &fb, const FrameTri &ft,
+                                           const double *sT, unsigned *hist, bool diag)
 {
     for (int j = 0; j < nj; ++j) {
         const float4 pj = sj[j];
         const int bj = __float_as_int(pj.w);
 #pragma unroll
         for (int u = 0; u < RDF_IPT; ++u) {
-            const double r2 = exact_r2(xi[u], yi[u], zi[u], pj.x, pj.y, pj.z, fb);
+            const double r2 = ft.on ? tri_r2(xi[u], yi[u], zi[u], pj.x, pj.y, pj.z, ft)
+                                    : exact_r2(xi[u], yi[u], zi[u], pj.x, pj.y, pj.z, fb);
             bool ok = bi[u] != bj;
             if (CHECK) ok = ok && (ig[u] < A.na) && (!diag || (j0 + j) > ig[u]);
             if (ok) {
@@ -479,6 +548,7 @@ rdf_pairs_exact(RdfArgs A)
         bool diag;
         if (!decode_item(A, item, f, I, J, diag)) continue;
         const FrameBox fb = A.boxes[f];
+        const FrameTri ft = A.tri[f];
         const float *ax = A.a + ((int64_t)f * 3) * A.na, *ay = ax + A.na, *az = ay + A.na;
         const float *bx = A.b + ((int64_t)f * 3) * A.nb, *by = bx + A.nb, *bz = by + A.nb;
 
@@ -505,9 +575,9 @@ rdf_pairs_exact(RdfArgs A)
         __syncthreads();
         const bool edge = (int64_t)(I + 1) * RDF_TI > A.na;
         if (diag || edge)
-            tile_pairs<true>(A, sj, nj, j0, xi, yi, zi, bi, ig, fb, sT, hist, diag);
+            tile_pairs<true>(A, sj, nj, j0, xi, yi, zi, bi, ig, fb, ft, sT, hist, diag);
         else
-            tile_pairs<false>(A, sj, nj, j0, xi, yi, zi, bi, ig, fb, sT, hist, false);
+            tile_pairs<false>(A, sj, nj, j0, xi, yi, zi, bi, ig, fb, ft, sT, hist, false);
 
         if (++since_flush >= RDF_FLUSH_ITEMS) {
             __syncthreads();
@@ -1234,6 +1304,7 @@ struct mdc_rdf_plan {
     DevBuf<uint32_t> fix_a[2], fix_b[2];
     DevBuf<unsigned> absmax[2];        // (2, F): group a, group b
     DevBuf<FrameBox> boxes[2];
+    DevBuf<FrameTri> tri[2];
     DevBuf<FrameFast> fast[2];
     // spatially sorted copies (cutoffs well below half the box), allocated on first use
     DevBuf<float> sort_soa_a[2], sort_soa_b[2];
@@ -1267,6 +1338,7 @@ void rdf_free(mdc_rdf_plan *p)
         p->fix_b[i].release();
         p->absmax[i].release();
         p->boxes[i].release();
+        p->tri[i].release();
         p->fast[i].release();
         p->sort_soa_a[i].release();
         p->sort_soa_b[i].release();
@@ -1299,18 +1371,53 @@ int rdf_configure(mdc_rdf_plan *p, int n_frames_hint)
         }
         MDC_CHECK(p->absmax[i].alloc((size_t)2 * fblk));
         MDC_CHECK(p->boxes[i].alloc(fblk));
+        MDC_CHECK(p->tri[i].alloc(fblk));
         MDC_CHECK(p->fast[i].alloc(fblk));
     }
     return MDC_OK;
 }
 
-int make_boxes(const float *box, int F, std::vector<FrameBox> &out)
+// MDAnalysis.lib.mdamath.triclinic_vectors(dimensions, dtype=float32), restated (see oracle/oracle.c): the box matrix is
+// formed in float64 and rounded to float32; cos(90 deg) is exactly 0.  false: not a valid cell.
+bool triclinic_vectors(const float *b, FrameTri &t)
+{
+    const double lx = b[0], ly = b[1], lz = b[2], alpha = b[3], beta = b[4], gamma = b[5];
+    const double deg = 0.017453292519943295;
+    if (!(lx > 0 && ly > 0 && lz > 0 && alpha > 0 && beta > 0 && gamma > 0 && alpha < 180 && beta < 180 && gamma < 180))
+        return false;
+    const double cos_alpha = alpha == 90.0 ? 0.0 : cos(alpha * deg);
+    const double cos_beta = beta == 90.0 ? 0.0 : cos(beta * deg);
+    double cos_gamma = 0.0, sin_gamma = 1.0;
+    if (gamma != 90.0) {
+        cos_gamma = cos(gamma * deg);
+        sin_gamma = sin(gamma * deg);
+    }
+    const double bx = ly * cos_gamma, by = ly * sin_gamma;
+    const double cx = lz * cos_beta, cy = lz * (cos_alpha - cos_beta * cos_gamma) / sin_gamma;
+    const double cz = sqrt(lz * lz - cx * cx - cy * cy);
+    if (!(cz > 0.0)) return false;
+    t.ax = (double)(float)lx;
+    t.bx = (double)(float)bx;
+    t.by = (double)(float)by;
+    t.cx = (double)(float)cx;
+    t.cy = (double)(float)cy;
+    t.cz = (double)(float)cz;
+    t.on = 1;
+    t.pad = 0;
+    return true;
+}
+
+int make_boxes(const float *box, int F, std::vector<FrameBox> &out, std::vector<FrameTri> &tri)
 {
     out.resize(F);
+    tri.resize(F);
     for (int f = 0; f < F; ++f) {
         const float *b = box + 6 * f;
-        if (!(b[3] == 90.f && b[4] == 90.f && b[5] == 90.f))
-            return fail(MDC_ERR_UNSUPPORTED, "mdc_rdf_push: only orthorhombic boxes (90/90/90) are supported");
+        memset(&tri[f], 0, sizeof(FrameTri));
+        if (!(b[3] == 90.f && b[4] == 90.f && b[5] == 90.f)) {
+            if (!triclinic_vectors(b, tri[f]))
+                return fail(MDC_ERR_INVALID, "mdc_rdf_push: box lengths must be positive and box angles must describe a valid cell");
+        }
         for (int k = 0; k < 3; ++k) {
             if (!(b[k] >= 0.f) || !isfinite(b[k])) return fail(MDC_ERR_INVALID, "mdc_rdf_push: invalid box length");
             const float inv = (float)(1.0 / (double)b[k]);   // calc_distances.h: inverse_box stored as float
@@ -1432,7 +1539,8 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
     MDC_CUDA(cudaSetDevice(p->ctx->device));
     MDC_CHECK(rdf_configure(p, n_frames));
     std::vector<FrameBox> hb;
-    MDC_CHECK(make_boxes(box, n_frames, hb));
+    std::vector<FrameTri> ht;
+    MDC_CHECK(make_boxes(box, n_frames, hb, ht));
     cudaStream_t sc = p->st.copy, sk = p->st.compute;
     p->st.n_timed = 0;
     int launches = 0;
@@ -1452,13 +1560,15 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
             }
         }
         MDC_CUDA(cudaMemcpyAsync(p->boxes[slot].p, hb.data() + f0, F * sizeof(FrameBox), cudaMemcpyHostToDevice, sc));
+        MDC_CUDA(cudaMemcpyAsync(p->tri[slot].p, ht.data() + f0, F * sizeof(FrameTri), cudaMemcpyHostToDevice, sc));
         MDC_CUDA(cudaMemsetAsync(p->absmax[slot].p, 0, 2 * (size_t)p->fblk * sizeof(unsigned), sc));
         rdf_prep<<<(unsigned)ceil_div((int64_t)F * p->na, 256), 256, 0, sc>>>(
-            ra, p->na, (int64_t)F * p->na, p->boxes[slot].p, p->soa_a[slot].p, p->fix_a[slot].p, p->absmax[slot].p);
+            ra, p->na, (int64_t)F * p->na, p->boxes[slot].p, p->tri[slot].p, p->soa_a[slot].p, p->fix_a[slot].p,
+            p->absmax[slot].p);
         ++launches;
         if (rb) {
             rdf_prep<<<(unsigned)ceil_div((int64_t)F * p->nb, 256), 256, 0, sc>>>(
-                rb, p->nb, (int64_t)F * p->nb, p->boxes[slot].p, p->soa_b[slot].p, p->fix_b[slot].p,
+                rb, p->nb, (int64_t)F * p->nb, p->boxes[slot].p, p->tri[slot].p, p->soa_b[slot].p, p->fix_b[slot].p,
                 p->absmax[slot].p + p->fblk);
             ++launches;
         }
@@ -1466,8 +1576,10 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
             p->boxes[slot].p, p->absmax[slot].p, p->absmax[slot].p + (rb ? p->fblk : 0), F, p->n_bins, p->r0, p->r1,
             p->fast[slot].p);
         ++launches;
-        // the filter kernel needs three periodic axes and a bin coordinate below 2^22 in every frame
+        // the filter kernel needs an orthorhombic cell, three periodic axes and a bin coordinate below 2^22 in every frame
+        // (triclinic frames take the exact kernel: minimum_image_triclinic in FP64 for every pair)
         bool fast = !p->force_exact;
+        for (int f = 0; f < F && fast; ++f) fast = ht[f0 + f].on == 0;
         double max_len = 0.0, v_far_max = 0.0;
         for (int f = 0; f < F && fast; ++f) {
             const FrameBox &fb = hb[f0 + f];
@@ -1557,6 +1669,7 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
             A.cull_r = p->r1 * (1.0 + 1e-4) + 1e-5 * max_len;
         }
         A.boxes = p->boxes[slot].p;
+        A.tri = p->tri[slot].p;
         A.fast = p->fast[slot].p;
         A.T = p->T.p;
         A.counts = p->counts.p;

@@ -336,14 +336,28 @@ def cubic_box_length(n: int, rho: float) -> np.float32:
     return np.float32((n / rho) ** (1.0 / 3.0))
 
 
+_LATTICES: dict = {}
+
+
+def _simple_cubic(n: int, L: float) -> np.ndarray:
+    """The first ``n`` sites of the smallest simple-cubic lattice with at least ``n`` sites in a box of edge ``L``."""
+    key = (int(n), float(L))
+    lat = _LATTICES.get(key)
+    if lat is None:
+        m = int(round(n ** (1.0 / 3.0)))
+        while m**3 < n:
+            m += 1
+        g = (np.arange(m) + 0.5) * (float(L) / m)
+        lat = np.ascontiguousarray(np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)[:n])
+        if len(_LATTICES) < 8:
+            _LATTICES[key] = lat
+    return lat
+
+
 def lj_like_frame(n: int, L: float, seed: int, jitter: float = 0.15) -> np.ndarray:
     """Simple-cubic lattice plus Gaussian jitter, wrapped into ``[0, L)``."""
-    m = int(round(n ** (1.0 / 3.0)))
-    while m**3 < n:
-        m += 1
     rng = np.random.default_rng(seed)
-    g = (np.arange(m) + 0.5) * (float(L) / m)
-    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)[:n]
+    pos = _simple_cubic(n, L)
     pos = pos + rng.normal(scale=jitter, size=pos.shape)
     pos = np.mod(pos, float(L)).astype(np.float32)
     pos[pos >= np.float32(L)] = 0.0

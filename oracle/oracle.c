@@ -16,8 +16,11 @@
  *           not installed (requirements.txt:3 "mdanalysis >= 2.2.0", no lock
  *           file).  Its brute-force orthorhombic arithmetic is restated below
  *           from the published algorithm (calc_distances.h:
- *           _calc_distance_array_ortho + minimum_image).  That part is
- *           "parity unpinned" against a live MDAnalysis.
+ *           _calc_distance_array_ortho + minimum_image; for triclinic cells
+ *           _calc_distance_array_triclinic = _triclinic_pbc +
+ *           minimum_image_triclinic, and mdamath.triclinic_vectors for the
+ *           box matrix).  That part is "parity unpinned" against a live
+ *           MDAnalysis.
  *
  * Build: see oracle/Makefile (-O2 -fopenmp -ffp-contract=off, no fast-math:
  * FMA contraction would change r^2 in the last bit).
@@ -196,12 +199,116 @@ static inline double orc_pair_r2(const float *a, const float *b, const float box
     return r2;
 }
 
-/* exported so tests can pin single pairs */
+/*
+ * Triclinic cells (any box angle != 90), restated from the published MDAnalysis 2.x source:
+ *
+ *   lib/mdamath.py triclinic_vectors(dimensions, dtype=float32):  lower-triangular box matrix, formed in
+ *       float64 and rounded to float32:  a = (lx, 0, 0);  b = (ly cos g, ly sin g, 0);
+ *       c = (lz cos b, lz (cos a - cos b cos g) / sin g, sqrt(lz^2 - c_x^2 - c_y^2)); cos(90 deg) is exactly 0.
+ *   lib/include/calc_distances.h _calc_distance_array_triclinic:
+ *       _triclinic_pbc(ref), _triclinic_pbc(conf): every coordinate is moved into the primary cell (c axis first,
+ *         then b, then a; shifts by whole box vectors, arithmetic in double, result stored as float);
+ *       dx = conf[j] - ref[i]   (float subtract, widened to double);
+ *       minimum_image_triclinic(dx, box): the shortest of the 27 images dx + ix a + iy b + iz c, ix, iy, iz in
+ *         {-1, 0, 1} (rsq = rz0^2 + rz1^2 + rz2^2, left to right, first minimum kept);
+ *       d = sqrt(rsq).
+ * m = {a_x, b_x, b_y, c_x, c_y, c_z} as float32 values.
+ */
+int orc_triclinic_vectors(const float *box6, float m[6])
+{
+    const double lx = box6[0], ly = box6[1], lz = box6[2];
+    const double alpha = box6[3], beta = box6[4], gamma = box6[5];
+    const double deg = 0.017453292519943295;   /* numpy.deg2rad: x * (pi / 180) */
+    memset(m, 0, 6 * sizeof(float));
+    if (!(lx > 0 && ly > 0 && lz > 0 && alpha > 0 && beta > 0 && gamma > 0 && alpha < 180 && beta < 180 && gamma < 180))
+        return -1;
+    const double cos_alpha = alpha == 90.0 ? 0.0 : cos(alpha * deg);
+    const double cos_beta = beta == 90.0 ? 0.0 : cos(beta * deg);
+    double cos_gamma = 0.0, sin_gamma = 1.0;
+    if (gamma != 90.0) {
+        cos_gamma = cos(gamma * deg);
+        sin_gamma = sin(gamma * deg);
+    }
+    const double bx = ly * cos_gamma, by = ly * sin_gamma;
+    const double cx = lz * cos_beta, cy = lz * (cos_alpha - cos_beta * cos_gamma) / sin_gamma;
+    const double cz = sqrt(lz * lz - cx * cx - cy * cy);
+    if (!(cz > 0.0)) return -1;
+    m[0] = (float)lx;
+    m[1] = (float)bx;
+    m[2] = (float)by;
+    m[3] = (float)cx;
+    m[4] = (float)cy;
+    m[5] = (float)cz;
+    return 0;
+}
+
+/* _triclinic_pbc for one coordinate, in place */
+void orc_triclinic_wrap(float *p, const float m[6])
+{
+    const double ax = m[0], bx = m[1], by = m[2], cx = m[3], cy = m[4], cz = m[5];
+    const double bi0 = 1.0 / ax, bi4 = 1.0 / by, bi8 = 1.0 / cz;
+    const double a_y = bx * bi4, b_z = cy * bi8;
+    const double a_z = (cx - cy * a_y) * bi8;
+    double x = p[0], y = p[1], z = p[2];
+    if (z < 0.0 || z >= cz) {
+        const double s = floor(z * bi8);
+        z -= s * cz;
+        y -= s * cy;
+        x -= s * cx;
+    }
+    double lb = z * b_z;
+    if (y < lb || y >= lb + by) {
+        const double s = floor((y - lb) * bi4);
+        y -= s * by;
+        x -= s * bx;
+    }
+    lb = y * a_y + z * a_z;
+    if (x < lb || x >= lb + ax) {
+        const double s = floor((x - lb) * bi0);
+        x -= s * ax;
+    }
+    p[0] = (float)x;
+    p[1] = (float)y;
+    p[2] = (float)z;
+}
+
+/* minimum_image_triclinic + rsq for one pair of WRAPPED coordinates */
+static inline double orc_pair_r2_triclinic(const float *a, const float *b, const float m[6])
+{
+    const double d0 = (double)(b[0] - a[0]), d1 = (double)(b[1] - a[1]), d2 = (double)(b[2] - a[2]);
+    double best = (double)FLT_MAX;
+    for (int ix = -1; ix < 2; ++ix) {
+        const double rx = d0 + (double)(m[0] * (float)ix);
+        for (int iy = -1; iy < 2; ++iy) {
+            const double ry0 = rx + (double)(m[1] * (float)iy);
+            const double ry1 = d1 + (double)(m[2] * (float)iy);
+            for (int iz = -1; iz < 2; ++iz) {
+                const double rz0 = ry0 + (double)(m[3] * (float)iz);
+                const double rz1 = ry1 + (double)(m[4] * (float)iz);
+                const double rz2 = d2 + (double)(m[5] * (float)iz);
+                const double dsq = rz0 * rz0 + rz1 * rz1 + rz2 * rz2;
+                if (dsq < best) best = dsq;
+            }
+        }
+    }
+    return best;
+}
+
+/* exported so tests can pin single pairs (orthorhombic, or triclinic when an angle of box[3..5] is not 90) */
 double orc_pair_distance(const float *a, const float *b, const float *box)
 {
     float inv[3];
     for (int k = 0; k < 3; ++k) inv[k] = (float)(1.0 / (double)box[k]);
     return sqrt(orc_pair_r2(a, b, box, inv));
+}
+
+double orc_pair_distance_triclinic(const float *a, const float *b, const float *box6)
+{
+    float m[6], pa[3] = {a[0], a[1], a[2]}, pb[3] = {b[0], b[1], b[2]};
+    if (orc_triclinic_vectors(box6, m) != 0) return NAN;
+    orc_triclinic_wrap(pa, m);
+    orc_triclinic_wrap(pb, m);
+    return sqrt(orc_pair_r2_triclinic(pa, pb, m));
 }
 
 /*
@@ -212,15 +319,28 @@ double orc_pair_distance(const float *a, const float *b, const float *box)
  *   drop pairs with i / ex0 == j / ex1                 (structure.py:119-122)
  *   bin with numba_histogram over edges[0]=range_[0], edges[-1]=range_[1].
  * ex0 <= 0 means "no exclusion".  hist is accumulated in place.
+ * triclinic != 0: box holds six values and the triclinic routine above is used.
  */
-void orc_radial_histogram(const float *pos_a, int64_t na, const float *pos_b,
-                          int64_t nb, const float *box, int n_bins, double r0,
-                          double r1, int64_t ex0, int64_t ex1, int64_t *hist)
+static void orc_radial_histogram_impl(const float *pos_a, int64_t na, const float *pos_b,
+                                      int64_t nb, const float *box, int triclinic, int n_bins, double r0,
+                                      double r1, int64_t ex0, int64_t ex1, int64_t *hist)
 {
-    float inv[3], bx[3];
+    float inv[3], bx[3], m[6];
     for (int k = 0; k < 3; ++k) {
         bx[k] = box[k];
         inv[k] = (float)(1.0 / (double)box[k]);
+    }
+    float *wa = NULL, *wb = NULL;
+    if (triclinic) {
+        if (orc_triclinic_vectors(box, m) != 0) return;
+        wa = (float *)malloc(sizeof(float) * 3 * (size_t)na);
+        wb = (float *)malloc(sizeof(float) * 3 * (size_t)nb);
+        memcpy(wa, pos_a, sizeof(float) * 3 * (size_t)na);
+        memcpy(wb, pos_b, sizeof(float) * 3 * (size_t)nb);
+        for (int64_t i = 0; i < na; ++i) orc_triclinic_wrap(wa + 3 * i, m);
+        for (int64_t j = 0; j < nb; ++j) orc_triclinic_wrap(wb + 3 * j, m);
+        pos_a = wa;
+        pos_b = wb;
     }
     const double min_cut = r0 - DBL_EPSILON;
     const double nd = (double)n_bins, invw = 1.0 / (r1 - r0);
@@ -235,7 +355,8 @@ void orc_radial_histogram(const float *pos_a, int64_t na, const float *pos_b,
             const int64_t bi = ex0 > 0 ? i / ex0 : -1;
             for (int64_t j = 0; j < nb; ++j) {
                 if (ex0 > 0 && bi == j / ex1) continue;
-                const double r2 = orc_pair_r2(a, pos_b + 3 * j, bx, inv);
+                const double r2 = triclinic ? orc_pair_r2_triclinic(a, pos_b + 3 * j, m)
+                                            : orc_pair_r2(a, pos_b + 3 * j, bx, inv);
                 if (r2 > r2_hi) continue;
                 const double d = sqrt(r2);
                 if (!(d <= r1 && d > min_cut)) continue;
@@ -247,6 +368,22 @@ void orc_radial_histogram(const float *pos_a, int64_t na, const float *pos_b,
         for (int b = 0; b < n_bins; ++b) hist[b] += local[b];
         free(local);
     }
+    free(wa);
+    free(wb);
+}
+
+void orc_radial_histogram(const float *pos_a, int64_t na, const float *pos_b,
+                          int64_t nb, const float *box, int n_bins, double r0,
+                          double r1, int64_t ex0, int64_t ex1, int64_t *hist)
+{
+    orc_radial_histogram_impl(pos_a, na, pos_b, nb, box, 0, n_bins, r0, r1, ex0, ex1, hist);
+}
+
+void orc_radial_histogram_triclinic(const float *pos_a, int64_t na, const float *pos_b,
+                                    int64_t nb, const float *box6, int n_bins, double r0,
+                                    double r1, int64_t ex0, int64_t ex1, int64_t *hist)
+{
+    orc_radial_histogram_impl(pos_a, na, pos_b, nb, box6, 1, n_bins, r0, r1, ex0, ex1, hist);
 }
 
 int orc_num_threads(void)

@@ -61,6 +61,11 @@ def lib() -> ctypes.CDLL:
             c_fp, ctypes.c_int64, c_fp, ctypes.c_int64, c_fp, ctypes.c_int,
             ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_int64, c_lp,
         ]
+        L.orc_radial_histogram_triclinic.argtypes = L.orc_radial_histogram.argtypes
+        L.orc_pair_distance_triclinic.argtypes = [c_fp, c_fp, c_fp]
+        L.orc_pair_distance_triclinic.restype = ctypes.c_double
+        L.orc_triclinic_vectors.argtypes = [c_fp, c_fp]
+        L.orc_triclinic_vectors.restype = ctypes.c_int
         L.orc_num_threads.restype = ctypes.c_int
         L.orc_set_num_threads.argtypes = [ctypes.c_int]
         _lib = L
@@ -396,7 +401,22 @@ def pair_distance(a, b, box) -> float:
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)
     box = np.ascontiguousarray(box, dtype=np.float32)
+    if _is_triclinic(box):
+        return float(lib().orc_pair_distance_triclinic(_fp(a), _fp(b), _fp(box)))
     return float(lib().orc_pair_distance(_fp(a), _fp(b), _fp(box)))
+
+
+def _is_triclinic(box) -> bool:
+    return len(box) >= 6 and not np.all(np.asarray(box[3:6]) == 90)
+
+
+def triclinic_vectors(dimensions) -> np.ndarray:
+    """``MDAnalysis.lib.mdamath.triclinic_vectors(dimensions, dtype=float32)`` as restated in ``oracle.c``:
+    the lower-triangular box matrix ``(3, 3)`` float32 (zeros for an invalid box)."""
+    box = np.ascontiguousarray(dimensions, dtype=np.float32)
+    m = np.zeros(6, dtype=np.float32)
+    lib().orc_triclinic_vectors(_fp(box), _fp(m))
+    return np.array([[m[0], 0, 0], [m[1], m[2], 0], [m[3], m[4], m[5]]], dtype=np.float32)
 
 
 def radial_histogram(
@@ -406,11 +426,10 @@ def radial_histogram(
     a = np.ascontiguousarray(np.atleast_2d(positions_a), dtype=np.float32)
     b = np.ascontiguousarray(np.atleast_2d(positions_b), dtype=np.float32)
     box = np.ascontiguousarray(dimensions, dtype=np.float32)
-    if box.shape[0] >= 6 and not np.all(box[3:6] == 90):
-        raise NotImplementedError("oracle restates the orthorhombic distance routine only")
     h = np.zeros(n_bins, dtype=np.int64)
     ex0, ex1 = (0, 0) if exclusion is None else (int(exclusion[0]), int(exclusion[1]))
-    lib().orc_radial_histogram(
+    fn = lib().orc_radial_histogram_triclinic if _is_triclinic(box) else lib().orc_radial_histogram
+    fn(
         _fp(a), a.shape[0], _fp(b), b.shape[0], _fp(box), int(n_bins),
         float(range_[0]), float(range_[1]), ex0, ex1, _lp(h),
     )
@@ -427,6 +446,12 @@ def capped_distance(reference, configuration, max_cutoff, min_cutoff=None, box=N
     a = np.atleast_2d(np.asarray(reference, dtype=np.float32))
     b = np.atleast_2d(np.asarray(configuration, dtype=np.float32))
     box = np.asarray(box, dtype=np.float32)
+    if _is_triclinic(box):
+        d = _triclinic_distance_array(a, b, box)
+        mask = d <= max_cutoff
+        if min_cutoff is not None:
+            mask &= d > min_cutoff
+        return np.argwhere(mask).astype(np.intp), d[mask]
     inv = (1.0 / box[:3].astype(np.float64)).astype(np.float32)
     r2 = np.zeros((a.shape[0], b.shape[0]))
     for k in range(3):
@@ -444,6 +469,56 @@ def capped_distance(reference, configuration, max_cutoff, min_cutoff=None, box=N
         mask &= d > min_cutoff
     pairs = np.argwhere(mask)
     return pairs.astype(np.intp), d[mask]
+
+
+def _triclinic_wrap(pos: np.ndarray, m: np.ndarray) -> np.ndarray:
+    """``_triclinic_pbc`` (see ``oracle.c``) in NumPy: float32 coordinates moved into the primary cell."""
+    ax, bx, by, cx, cy, cz = (np.float64(v) for v in (m[0, 0], m[1, 0], m[1, 1], m[2, 0], m[2, 1], m[2, 2]))
+    bi0, bi4, bi8 = 1.0 / ax, 1.0 / by, 1.0 / cz
+    a_y, b_z = bx * bi4, cy * bi8
+    a_z = (cx - cy * a_y) * bi8
+    x, y, z = (pos[:, k].astype(np.float64) for k in range(3))
+    s = np.where((z < 0.0) | (z >= cz), np.floor(z * bi8), 0.0)
+    z, y, x = z - s * cz, y - s * cy, x - s * cx
+    lb = z * b_z
+    s = np.where((y < lb) | (y >= lb + by), np.floor((y - lb) * bi4), 0.0)
+    y, x = y - s * by, x - s * bx
+    lb = y * a_y + z * a_z
+    s = np.where((x < lb) | (x >= lb + ax), np.floor((x - lb) * bi0), 0.0)
+    x = x - s * ax
+    return np.stack((x, y, z), axis=1).astype(np.float32)
+
+
+def _triclinic_distance_array(a: np.ndarray, b: np.ndarray, box: np.ndarray) -> np.ndarray:
+    """``_calc_distance_array_triclinic`` (see ``oracle.c``) in NumPy, for small inputs."""
+    m = triclinic_vectors(box)
+    a, b = _triclinic_wrap(a, m), _triclinic_wrap(b, m)
+    d = [(b[None, :, k] - a[:, None, k]).astype(np.float64) for k in range(3)]   # float32 subtract, widened
+    best = np.full(d[0].shape, np.float64(np.finfo(np.float32).max))
+    f64 = np.float64
+    for ix in (-1, 0, 1):
+        rx = d[0] + f64(m[0, 0] * np.float32(ix))
+        for iy in (-1, 0, 1):
+            ry0 = rx + f64(m[1, 0] * np.float32(iy))
+            ry1 = d[1] + f64(m[1, 1] * np.float32(iy))
+            for iz in (-1, 0, 1):
+                rz0 = ry0 + f64(m[2, 0] * np.float32(iz))
+                rz1 = ry1 + f64(m[2, 1] * np.float32(iz))
+                rz2 = d[2] + f64(m[2, 2] * np.float32(iz))
+                dsq = rz0 * rz0 + rz1 * rz1 + rz2 * rz2
+                best = np.where(dsq < best, dsq, best)
+    return np.sqrt(best)
+
+
+def box_volume(dims) -> float:
+    """``ts.volume`` (MDAnalysis ``box_volume``): product of the lengths, times the triclinic factor."""
+    d = np.asarray(dims, dtype=np.float32)
+    lx, ly, lz = (float(v) for v in d[:3])
+    if not _is_triclinic(d):
+        return lx * ly * lz
+    a, b, g = np.deg2rad(d[3:6].astype(np.float64))
+    ca, cb, cg = np.cos(a), np.cos(b), np.cos(g)
+    return lx * ly * lz * float(np.sqrt(1 - ca * ca - cb * cb - cg * cg + 2 * ca * cb * cg))
 
 
 def rdf(
@@ -471,7 +546,7 @@ def rdf(
         dims = np.array(dims, dtype=np.float32)
         n_a, n_b = pa.shape[0], pb.shape[0]
         if drop_axis is None:
-            vol += float(dims[0]) * float(dims[1]) * float(dims[2])
+            vol += box_volume(dims)
         else:
             pa[:, drop_axis] = 0
             pb[:, drop_axis] = 0

@@ -370,8 +370,40 @@ def profiles():
     save("profiles.npz", **out)
 
 
+def triclinic():
+    """g(r) in triclinic cells: the reference classes (binning, exclusion, accumulation, normalisation, ts.volume) over
+    the restated triclinic capped_distance (oracle.capped_distance: triclinic_vectors, _triclinic_pbc,
+    minimum_image_triclinic).  Cells: 60/90/75 (as VERDICT r01 asks), a strongly skewed 50/65/55, an NPT sequence that
+    mixes orthorhombic and triclinic frames; positions in and outside the primary cell."""
+    from oracle import oracle
+
+    st, _ = ref_loader.load()
+    rng = np.random.default_rng(60_90_75)
+    out = {}
+    n, F = 500, 3
+    box = np.array([11.0, 12.5, 10.0, 60, 90, 75], np.float32)
+    m = oracle.triclinic_vectors(box).astype(np.float64)
+    pos = ((rng.random((F, n, 3)) * 2.2 - 0.6) @ m).astype(np.float32)          # fractional coordinates in [-0.6, 1.6)
+    u = universe_from(pos, box)
+    r = st.RadialDistributionFunction(u.atoms, n_bins=80, range_=(0.0, 4.5), verbose=False).run()
+    out.update(a_pos=pos, a_dims=box, a_counts=r.results.counts, a_rdf=r.results.rdf)
+    r = st.RadialDistributionFunction(u.select(0, 180), u.select(180, n), n_bins=57, range_=(0.4, 4.9), exclusion=(3, 5),
+                                      verbose=False).run()
+    out.update(a_cross_counts=r.results.counts, a_cross_rdf=r.results.rdf)
+    boxes = np.array([[9.0, 9.5, 10.0, 50, 65, 55], [9.2, 9.4, 10.1, 90, 90, 90], [9.1, 9.6, 9.9, 90, 101.5, 90],
+                      [9.3, 9.3, 10.2, 120, 90, 90]], np.float32)
+    posb = np.stack([((rng.random((n, 3)) * 1.4 - 0.2) @ oracle.triclinic_vectors(b).astype(np.float64)).astype(np.float32)
+                     for b in boxes])
+    u = universe_from(posb, boxes)
+    r = st.RadialDistributionFunction(u.atoms, n_bins=64, range_=(0.0, 3.9), exclusion=(1, 1), verbose=False).run()
+    out.update(b_pos=posb, b_dims=boxes, b_counts=r.results.counts, b_rdf=r.results.rdf)
+    save("rdf_triclinic.npz", **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "triclinic"):
+        triclinic()
     if which in ("all", "profiles"):
         profiles()
     if which in ("all", "main"):

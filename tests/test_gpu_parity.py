@@ -183,6 +183,41 @@ def test_rdf_npt_and_drop_axis_golden():
     np.testing.assert_allclose(rd.results.rdf, g["rdf_drop"], rtol=1e-12)
 
 
+def test_rdf_triclinic_golden_and_vs_oracle(ctx):
+    """Triclinic cells (structure.py:109-115 hands all six box values to capped_distance): the classes against the
+    golden vectors of the reference classes (60/90/75 cell; NPT mixing orthorhombic and triclinic frames), and the
+    functional seam against the CPU oracle at sizes where every code path of the kernel runs (ragged tiles, two groups,
+    exclusion, coordinates far outside the primary cell)."""
+    from mdcraft_b200.analysis.structure import radial_histogram
+    from oracle import oracle
+
+    g = golden("rdf_triclinic.npz")
+    u = universe_from(g["a_pos"], g["a_dims"])
+    r = _rdf(u.atoms, n_bins=80, range_=(0.0, 4.5), frame_block=2)
+    np.testing.assert_array_equal(r.results.counts, g["a_counts"])
+    np.testing.assert_allclose(r.results.rdf, g["a_rdf"], rtol=1e-12)
+    r = _rdf(u.select(0, 180), u.select(180, 500), n_bins=57, range_=(0.4, 4.9), exclusion=(3, 5))
+    np.testing.assert_array_equal(r.results.counts, g["a_cross_counts"])
+    np.testing.assert_allclose(r.results.rdf, g["a_cross_rdf"], rtol=1e-12)
+    u = universe_from(g["b_pos"], g["b_dims"])
+    r = _rdf(u.atoms, n_bins=64, range_=(0.0, 3.9), exclusion=(1, 1), frame_block=3)    # mixed blocks: ortho + triclinic
+    np.testing.assert_array_equal(r.results.counts, g["b_counts"])
+    np.testing.assert_allclose(r.results.rdf, g["b_rdf"], rtol=1e-12)
+
+    rng = np.random.default_rng(75)
+    for box, n_a, n_b, excl in (([30.0, 28.0, 33.0, 60, 90, 75], 2500, None, None), ([22.0, 25.0, 21.0, 70, 110, 95], 700, 1800, (2, 3)),
+                                ([18.0, 18.0, 18.0, 90, 90, 120], 1025, None, (1, 1))):
+        box = np.array(box, np.float32)
+        m = oracle.triclinic_vectors(box).astype(np.float64)
+        a = ((rng.random((n_a, 3)) * 5 - 2) @ m).astype(np.float32)
+        b = a if n_b is None else ((rng.random((n_b, 3)) * 5 - 2) @ m).astype(np.float32)
+        rcut = (0.0, 0.45 * float(min(m[0, 0], m[1, 1], m[2, 2])))
+        got = radial_histogram(a, b, n_bins=90, range_=rcut, dimensions=box, exclusion=excl)
+        np.testing.assert_array_equal(got, oracle.radial_histogram(a, b, 90, rcut, box, exclusion=excl))
+    with pytest.raises(Exception, match="valid cell"):
+        radial_histogram(a, a, n_bins=10, range_=(0.0, 3.0), dimensions=np.array([10, 10, 10, 30, 100, 160], np.float32))
+
+
 @pytest.mark.parametrize("n,n_bins,frac", [(1, 8, 0.5), (2, 8, 0.5), (511, 33, 0.5), (512, 200, 0.5), (513, 200, 0.37),
                                            (1025, 1000, 0.5), (3000, 200, 0.5), (2049, 4096, 0.45),
                                            (4096, 200, 0.5), (4097, 64, 0.3), (5121, 300, 0.5), (6000, 3000, 0.2),
