@@ -91,8 +91,9 @@ def test_plan_errors(ctx):
     with pytest.raises(_capi.MdcError):
         _capi.SqPlan(ctx, [10], [(None, None)], n_points=0)
     plan = _capi.RdfPlan(ctx, 10, (0.0, 1.0), 10)
-    with pytest.raises(_capi.MdcError, match="orthorhombic"):
-        plan.push(np.zeros((1, 10, 3), np.float32), None, np.array([[5, 5, 5, 90, 60, 90]], np.float32))
+    with pytest.raises(_capi.MdcError, match="valid cell"):      # 30 + 60 < 100: no such cell
+        plan.push(np.zeros((1, 10, 3), np.float32), None, np.array([[5, 5, 5, 30, 60, 100]], np.float32))
+    plan.push(np.zeros((1, 10, 3), np.float32), None, np.array([[5, 5, 5, 90, 60, 90]], np.float32))   # triclinic: accepted
     with pytest.raises(ValueError):
         plan.push(np.zeros((1, 11, 3), np.float32), None, np.array([[5, 5, 5, 90, 90, 90]], np.float32))
     plan.close()
