@@ -629,6 +629,54 @@ def combine_equal_wavenumbers(ssf: np.ndarray, wavenumbers: np.ndarray, unique_q
     return out
 
 
+def _cell_vectors(parameters) -> np.ndarray:
+    """Reduced box vectors (rows a, b, c) of the cell ``(a, b, c, alpha, beta, gamma)`` — the ``parameters=`` branch of
+    ``algorithm/topology.py:667-742`` (entries within 5e-6 of zero are flushed to zero there, too)."""
+    p = np.asarray(parameters, dtype=float)
+    if p.shape[0] == 3:
+        warnings.warn("Only cell lengths are specified. Assuming cubic cell.")
+        p = np.concatenate((p, (90, 90, 90)))
+    elif p.shape[0] != 6:
+        raise ValueError("Invalid number of lattice parameters in 'parameters'.")
+    alpha, beta, gamma = np.radians(p[3:])
+    v = np.zeros((3, 3))
+    v[0, 0] = p[0]
+    v[1, 0] = p[1] * np.cos(gamma)
+    v[1, 1] = p[1] * np.sin(gamma)
+    v[2, 0] = p[2] * np.cos(beta)
+    v[2, 1] = p[2] * (np.cos(alpha) - np.cos(beta) * np.cos(gamma)) / np.sin(gamma)
+    v[2, 2] = np.sqrt(p[2] ** 2 - v[2, 0] ** 2 - v[2, 1] ** 2)
+    v[np.isclose(v, 0, atol=5e-6)] = 0
+    return v
+
+
+def generate_spherical_wavevectors(dimensions, *, n_points=32, q_max: float = None, wavenumbers: bool = False):
+    """
+    ``structure.py:1436-1507``: the reciprocal-lattice wavevectors ``(i, j, k) @ 2 pi inv(cell.T)`` of a (triclinic)
+    cell given as box vectors ``(3, 3)`` or lattice parameters ``(6,)``, ``i, j, k`` in ``[0, n_points)`` per axis
+    (``q_max``: as many points per axis as reach ``q_max``, then only ``|q| <= q_max`` is kept).  A host helper for
+    ``StructureFactor(..., wavevectors=...)``; the result feeds the explicit-wavevector kernels.
+    """
+    cell = np.asarray(dimensions)
+    if cell.ndim == 1:
+        cell = _cell_vectors(cell)
+    recip = 2 * np.pi * np.linalg.inv(cell.T)
+    if q_max is None:
+        if isinstance(n_points, (int, np.integer)):
+            n_points = 3 * [int(n_points)]
+        elif len(n_points) != 3:
+            raise ValueError("'n_points' must be an integer or a tuple with length 3.")
+    else:
+        n_points = np.floor(q_max * np.linalg.norm(np.linalg.inv(recip.T), axis=1)).astype(int)
+    index = np.stack(np.meshgrid(*[np.arange(n) for n in n_points]), axis=-1).reshape(-1, 3)
+    q = index @ recip
+    norms = np.linalg.norm(q, axis=1)
+    if q_max is not None:
+        keep = norms <= q_max
+        q, norms = q[keep], norms[keep]
+    return (q, norms) if wavenumbers else q
+
+
 class StructureFactor(_DeviceBlockRun, NumbaAnalysisBase):
     r"""
     Static structure factor :math:`S(q)` and partial structure factors

@@ -397,6 +397,13 @@ def triclinic():
     u = universe_from(posb, boxes)
     r = st.RadialDistributionFunction(u.atoms, n_bins=64, range_=(0.0, 3.9), exclusion=(1, 1), verbose=False).run()
     out.update(b_pos=posb, b_dims=boxes, b_counts=r.results.counts, b_rdf=r.results.rdf)
+    # generate_spherical_wavevectors (structure.py:1436-1507) of the same cell: box vectors / lattice parameters, q_max
+    cell = oracle.triclinic_vectors(box).astype(np.float64)
+    out["w_cell"] = cell
+    out["w_points"] = st.generate_spherical_wavevectors(cell, n_points=(3, 4, 5))
+    out["w_params"] = st.generate_spherical_wavevectors(np.array([11.0, 12.5, 10.0, 60, 90, 75]), n_points=4)
+    q, k = st.generate_spherical_wavevectors(cell, q_max=2.5, wavenumbers=True)
+    out["w_qmax"], out["w_qmax_norm"] = q, k
     save("rdf_triclinic.npz", **out)
 
 

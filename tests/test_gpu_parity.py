@@ -328,6 +328,26 @@ def test_rdf_and_sq_residue_groupings(tmp_path):
         np.testing.assert_allclose(s64.results.ssf, ws["ssf"], rtol=1e-10, atol=1e-12)
 
 
+def test_verbose_logs_the_run(caplog):
+    """verbose=True (the reference's default): a start and a finish line per run with device, frames per block, the plan's
+    algorithm and frames/s (the reference logs its process farm the same way, base.py:378-384, 514-515); silent otherwise."""
+    import logging
+
+    from mdcraft_b200.analysis.structure import RadialDistributionFunction, StructureFactor
+
+    g = golden("rdf_self_c1.npz")
+    u = universe_from(g["pos"], g["dims"])
+    with caplog.at_level(logging.INFO, logger="mdcraft_b200.analysis"):
+        RadialDistributionFunction(u.atoms, n_bins=20, range_=(0.0, 3.0), verbose=False).run()
+        assert not caplog.records
+        RadialDistributionFunction(u.atoms, n_bins=20, range_=(0.0, 3.0)).run(stop=3)
+        StructureFactor(u.atoms, n_points=8, algorithm="nufft").run(stop=2)
+    text = [r.getMessage() for r in caplog.records]
+    assert len(text) == 4
+    assert "RadialDistributionFunction: analysing 3 frames on cuda:0" in text[0] and "frames/s" in text[1]
+    assert "algorithm nufft (nf = " in text[3]
+
+
 def test_rdf_post_processing_runs():
     g = golden("rdf_self_c1.npz")
     u = universe_from(g["pos"], g["dims"])

@@ -345,3 +345,19 @@ def test_netcdf_header_on_the_host(tmp_path):
     bad.write_bytes(b"CDF\x05" + bytes(64))
     with pytest.raises(_capi.MdcError, match="classic"):
         _capi.NcdfFile(str(bad))
+
+
+def test_generate_spherical_wavevectors_matches_the_reference():
+    """structure.py:1436-1507, golden from the reference function (tests/golden/make_golden.py triclinic)."""
+    from conftest import golden
+
+    g = golden("rdf_triclinic.npz")
+    cell = g["w_cell"]
+    np.testing.assert_array_equal(structure.generate_spherical_wavevectors(cell, n_points=(3, 4, 5)), g["w_points"])
+    np.testing.assert_array_equal(
+        structure.generate_spherical_wavevectors(np.array([11.0, 12.5, 10.0, 60, 90, 75]), n_points=4), g["w_params"])
+    q, k = structure.generate_spherical_wavevectors(cell, q_max=2.5, wavenumbers=True)
+    np.testing.assert_array_equal(q, g["w_qmax"])
+    np.testing.assert_array_equal(k, g["w_qmax_norm"])
+    with pytest.raises(ValueError):
+        structure.generate_spherical_wavevectors(cell, n_points=(3, 4))
