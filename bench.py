@@ -377,8 +377,9 @@ def run_native(args, rank, world, emit=print):
     edges = histogram_bin_edges(np.asarray((0.0, Lg / 2), dtype=float), GR["n_bins"])
 
     rdf = _capi.RdfPlan(ctx, GR["n_bins"], (edges[0], edges[-1]), N_PART, None, (1, 1))
+    GR_BLOCKS = int(os.environ.get("MDC_BENCH_GR_BLOCKS", "3"))   # experiments only
     if ctx_s is not ctx:
-        rdf.set_blocks_per_sm(3)   # of the 4 that fit: the free quarter of every SM hosts the S(q) kernels
+        rdf.set_blocks_per_sm(GR_BLOCKS)   # of the 4 that fit: the free quarter of every SM hosts the S(q) kernels
     sqp = _capi.SqPlan(ctx_s, [N_PART], [(None, None)], n_points=SQ["n_points"], L0=[Ls] * 3, q_max=SQ["q_max"],
                        algo=args.sq_algo)
     nq = sqp.n_wavevectors

@@ -347,6 +347,322 @@ nufft_spread(const double *__restrict__ posd, int64_t N, const int2 *__restrict_
     }
 }
 
+
+// ---- spreading by gather: one block per 16^3 tile of the fine grid --------------------------------------
+//
+// The scatter kernel above issues w^3 complex FP64 reductions per particle into L2 (3,456 REDs at w = 12) and runs at
+// the L2 atomic rate.  Here the roles are swapped: a block OWNS a tile of 16 x 16 x 16 fine-grid cells, a thread owns
+// tile of 8 x 16 x 16 fine-grid cells, each of its four warps a patch of 4 x 8 x 16 cells.  The lanes of a warp are the
+// 32 doubles of one z line of the patch (16 cells x (re, im)), and every lane keeps the 4 x 8 (x, y) positions of its
+// (z, re / im) in registers.  The block walks over the particles whose support touches the tile (those of the 27
+// surrounding tile bins, pre-filtered); per particle and warp the update is an outer product
+//     acc[i][j] += (vx[i] * wz_lane) * vy[j]            (4 DMUL + 32 DFMA, vx / vy warp-uniform broadcast loads)
+// with vx, vy, wz zero-padded in shared memory, so the body needs no range test whatever the offset of the support.
+// Every cell is then written to HBM exactly once, in 256-byte lines: no atomics, no clearing pass, no
+// read-modify-write traffic.  Per particle the kernel values are computed once by nufft_records (3 w FP64
+// exponentials) and staged in shared memory in chunks of 32.
+
+constexpr int NT_T = 16;                 // bin edge = tile extent in y and z (cells); also the pencil length per thread
+constexpr int NT_TX = 8;                 // tile extent in x: half a bin, so that a block is 128 threads x < 128 registers and
+                                         // fits the quarter of an SM that the g(r) pair kernel leaves free (see NU_THREADS)
+constexpr int NT_PX = 4, NT_PY = 8;      // patch of one warp: 4 x 8 (x, y) positions x 16 z; 2 x 2 patches per tile
+constexpr int NT_THREADS = 128;          // 4 warps
+constexpr int NT_LIST = 1024;            // candidate list (particle slots) per drain
+
+__device__ __forceinline__ int tile_of(double g) { return ((int)g) >> 4; }
+
+__global__ void nufft_tile_count(const double *__restrict__ posd, int64_t N, const int2 *__restrict__ sets, int n_sets,
+                                 int e0, int nf, int nb, double iLx, double iLy, double iLz, int *__restrict__ cnt)
+{
+    const int e = e0 + blockIdx.y, f = e / n_sets, s = e - f * n_sets;
+    const int2 set = sets[s];
+    const int64_t j = (int64_t)set.x + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= set.y) return;
+    const int bx = tile_of(fine_coord(posd[((int64_t)f * 3 + 0) * N + j], iLx, nf));
+    const int by = tile_of(fine_coord(posd[((int64_t)f * 3 + 1) * N + j], iLy, nf));
+    const int bz = tile_of(fine_coord(posd[((int64_t)f * 3 + 2) * N + j], iLz, nf));
+    atomicAdd(&cnt[(size_t)blockIdx.y * nb * nb * nb + ((size_t)bx * nb + by) * nb + bz], 1);
+}
+
+// exclusive scan of n counters per element (one block of 128 threads per element, any n).  128 threads, like every
+// kernel of this chain: a larger block would not fit next to the persistent g(r) pair kernel and would wait for it.
+__global__ void __launch_bounds__(128) nufft_scan_any(int n, int *__restrict__ cnt)
+{
+    __shared__ int sh[128];
+    int *c = cnt + (size_t)blockIdx.x * n;
+    const int per = (n + 127) / 128, lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += c[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 128; o <<= 1) {
+        const int add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    int run = sh[threadIdx.x] - s;
+    for (int i = lo; i < hi; ++i) {
+        const int v = c[i];
+        c[i] = run;
+        run += v;
+    }
+}
+
+// sorted slot of every particle (order[slot] = particle); afterwards cursor[b] = END of bin b
+__global__ void nufft_tile_scatter(const double *__restrict__ posd, int64_t N, const int2 *__restrict__ sets, int n_sets,
+                                   int e0, int nf, int nb, double iLx, double iLy, double iLz, int *__restrict__ cursor,
+                                   int *__restrict__ order, int64_t maxlen)
+{
+    const int e = e0 + blockIdx.y, f = e / n_sets, s = e - f * n_sets;
+    const int2 set = sets[s];
+    const int64_t j = (int64_t)set.x + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= set.y) return;
+    const int bx = tile_of(fine_coord(posd[((int64_t)f * 3 + 0) * N + j], iLx, nf));
+    const int by = tile_of(fine_coord(posd[((int64_t)f * 3 + 1) * N + j], iLy, nf));
+    const int bz = tile_of(fine_coord(posd[((int64_t)f * 3 + 2) * N + j], iLz, nf));
+    const int pos = atomicAdd(&cursor[(size_t)blockIdx.y * nb * nb * nb + ((size_t)bx * nb + by) * nb + bz], 1);
+    order[(int64_t)blockIdx.y * maxlen + pos] = (int)j;
+}
+
+// Kernel values of every particle, in sorted order: rec[slot] = {vx[W], vy[W], (vz[W] * strength) as (re, im)[W]},
+// cell[slot] = first cell of the support per axis (may be negative: periodic).  One warp per particle.
+template <int W>
+__global__ void __launch_bounds__(128)
+nufft_records(const double *__restrict__ posd, int64_t N, const int2 *__restrict__ sets, int n_sets, int e0,
+              const int *__restrict__ order, int64_t maxlen, NufftGeom g, double iLx, double iLy, double iLz,
+              double *__restrict__ rec, int4 *__restrict__ cell)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = e0 + blockIdx.y, f = e / n_sets, s = e - f * n_sets;
+    const int2 set = sets[s];
+    const int len = set.y - set.x;
+    const int idx = blockIdx.x * 4 + warp;
+    if (idx >= len) return;
+    const int nf = g.nf;
+    const int64_t slot = (int64_t)blockIdx.y * maxlen + idx;
+    const int64_t j = order[slot];
+    const double gx = fine_coord(posd[((int64_t)f * 3 + 0) * N + j], iLx, nf);
+    const double gy = fine_coord(posd[((int64_t)f * 3 + 1) * N + j], iLy, nf);
+    const double gz = fine_coord(posd[((int64_t)f * 3 + 2) * N + j], iLz, nf);
+    const double hw = 0.5 * (double)W, ihw = 2.0 / (double)W, inf = 1.0 / (double)nf;
+    const int t = lane & 15;
+    double *R = rec + slot * (4 * W);
+    int l0a;
+    {
+        const double x = (lane < 16) ? gx : gy;
+        const double c = ceil(x - hw);
+        l0a = (int)c;
+        const double z = (c + (double)t - x) * ihw;
+        const double a = fmax(1.0 - z * z, 0.0);
+        if (t < W) R[(lane >> 4) * W + t] = exp(g.beta * (sqrt(a) - 1.0));
+    }
+    const int l0x = __shfl_sync(0xffffffffu, l0a, 0), l0y = __shfl_sync(0xffffffffu, l0a, 16);
+    const double c = ceil(gz - hw);
+    const int l0z = (int)c;
+    if (lane < 16 && t < W) {
+        const double z = (c + (double)t - gz) * ihw;
+        const double a = fmax(1.0 - z * z, 0.0);
+        const double vz = exp(g.beta * (sqrt(a) - 1.0));
+        // strength exp(2 pi i k0 (sx + sy + sz)) of the centred modes
+        double sn, cs;
+        sincospi(2.0 * (double)g.k0 * ((gx + gy + gz) * inf), &sn, &cs);
+        R[2 * W + 2 * t] = vz * cs;
+        R[2 * W + 2 * t + 1] = vz * sn;
+    }
+    if (lane == 0) cell[slot] = make_int4(l0x, l0y, l0z, 0);
+}
+
+// d = a - b reduced to (-span, nf - span]: the offset of cell a from support start b on the periodic grid
+__device__ __forceinline__ int wrap_off(int d, int nf, int span)
+{
+    d += (d <= -span) ? nf : 0;
+    d -= (d > nf - span) ? nf : 0;
+    return d;
+}
+
+template <int W>
+__global__ void __launch_bounds__(NT_THREADS, 4)
+nufft_spread_tiles(const double *__restrict__ rec, const int4 *__restrict__ cell, const int *__restrict__ binend,
+                   int64_t maxlen, int nf, int nb, double2 *__restrict__ grid)
+{
+    // per-particle kernel values; vx / vy zero-padded by one patch extent on either side, so that a warp reads the
+    // NT_PX / NT_PY entries its patch needs at ANY offset of the support without a range test.  Two stages: the
+    // records of chunk c + 1 arrive (cp.async) while chunk c is being consumed.
+    constexpr int VXP = W + 2 * NT_PX, VYP = W + 2 * NT_PY;
+    constexpr int NT_CHUNK = W <= 12 ? 32 : 24;          // particles per stage (static shared memory stays below 48 KB)
+    __shared__ int list[NT_LIST];
+    __shared__ int n_list;
+    __shared__ __align__(16) double s_vx[2][NT_CHUNK][VXP], s_vy[2][NT_CHUNK][VYP], s_wz[2][NT_CHUNK][2 * W];   // wz: (re, im)
+    __shared__ int4 s_cell[2][NT_CHUNK];
+    __shared__ int r_lo[27], r_off[28];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tb = blockIdx.x;                          // tile: (tx2 * nb + ty) * nb + tz, tx2 = half-bin index along x
+    const int tz = tb % nb, ty = (tb / nb) % nb, tx2 = tb / (nb * nb), tx = tx2 >> 1;
+    const int X0 = tx2 * NT_TX, Y0 = ty * NT_T, Z0 = tz * NT_T;
+    // a warp owns a patch of NT_PX x NT_PY x 16 cells; lane = (z, re / im): the 32 lanes cover one z line of the patch
+    // as 32 consecutive doubles, and every lane accumulates the NT_PX x NT_PY (x, y) positions of its (z, re / im)
+    const int XW = X0 + (warp >> 1) * NT_PX, YW = Y0 + (warp & 1) * NT_PY;
+    const size_t ebase = (size_t)blockIdx.y * maxlen;
+    const int *bend = binend + (size_t)blockIdx.y * nb * nb * nb;
+
+    double acc[NT_PX][NT_PY];
+#pragma unroll
+    for (int i = 0; i < NT_PX; ++i)
+#pragma unroll
+        for (int j = 0; j < NT_PY; ++j) acc[i][j] = 0.0;
+    for (int i = tid; i < 2 * NT_CHUNK * VXP; i += NT_THREADS) (&s_vx[0][0][0])[i] = 0.0;
+    for (int i = tid; i < 2 * NT_CHUNK * VYP; i += NT_THREADS) (&s_vy[0][0][0])[i] = 0.0;
+    if (tid == 0) n_list = 0;
+    if (tid < 27) {
+        const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
+        const int b = (((tx + ox + nb) % nb) * nb + (ty + oy + nb) % nb) * nb + (tz + oz + nb) % nb;
+        const int lo = b == 0 ? 0 : bend[b - 1];
+        r_lo[tid] = lo;
+        r_off[tid + 1] = bend[b] - lo;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        r_off[0] = 0;
+        for (int r = 0; r < 27; ++r) r_off[r + 1] += r_off[r];
+    }
+    __syncthreads();
+
+    // stage the records of list[c0 .. c0 + nc) into buffer `buf`: four threads per particle, a quarter of the record
+    // (W doubles) each: vx | vy | first half of wz | second half of wz; asynchronous (LDGSTS), committed as one group
+    auto stage = [&](int buf, int c0, int nc) {
+        const int p = tid >> 2, part = tid & 3;
+        if (p < nc) {
+            const int slot = list[c0 + p];
+            const double *src = rec + (ebase + slot) * (4 * W) + part * W;
+            double *dst = part == 0 ? &s_vx[buf][p][NT_PX] : part == 1 ? &s_vy[buf][p][NT_PY] : &s_wz[buf][p][(part - 2) * W];
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll
+            for (int o = 0; o < W; ++o)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8u * o), "l"(src + o) : "memory");
+            if (part == 0)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_cell[buf][p])),
+                             "l"(cell + ebase + slot)
+                             : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    auto drain = [&]() {
+        const int n = n_list;
+        if (n > 0) stage(0, 0, min(NT_CHUNK, n));
+        int buf = 0;
+        for (int c0 = 0; c0 < n; c0 += NT_CHUNK, buf ^= 1) {
+            const int nc = min(NT_CHUNK, n - c0);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();   // chunk c0 has landed; every warp is done with the other buffer (chunk c0 - 32)
+            if (c0 + NT_CHUNK < n) stage(buf ^ 1, c0 + NT_CHUNK, min(NT_CHUNK, n - c0 - NT_CHUNK));
+            // which particles of the chunk reach this warp's patch (one particle per lane), and at which offsets
+            int sx = 0, sy = 0, sz = 0;
+            bool take = false;
+            if (lane < nc) {
+                const int4 l0 = s_cell[buf][lane];
+                sx = wrap_off(XW - l0.x, nf, NT_PX);    // offset of the patch's first cell in the support, per axis
+                sy = wrap_off(YW - l0.y, nf, NT_PY);
+                sz = wrap_off(Z0 - l0.z, nf, NT_T);
+                take = sx < W && sy < W && sz < W;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, take);
+            while (m) {
+                const int p = __ffs((int)m) - 1;
+                m &= m - 1u;
+                const int px = __shfl_sync(0xffffffffu, sx, p), py = __shfl_sync(0xffffffffu, sy, p);
+                const int pz = __shfl_sync(0xffffffffu, sz, p) + (lane >> 1);            // this lane's offset in the z support
+                // vz(z) * strength (re or im) of this lane; zero outside the support
+                const double wzc = (unsigned)pz < (unsigned)W ? s_wz[buf][p][2 * pz + (lane & 1)] : 0.0;
+                const double *vxp = &s_vx[buf][p][NT_PX + px], *vyp = &s_vy[buf][p][NT_PY + py];
+                double vy[NT_PY];
+#pragma unroll
+                for (int j = 0; j < NT_PY; ++j) vy[j] = vyp[j];
+#pragma unroll
+                for (int i = 0; i < NT_PX; ++i) {
+                    const double a = vxp[i] * wzc;
+#pragma unroll
+                    for (int j = 0; j < NT_PY; ++j) acc[i][j] = fma(a, vy[j], acc[i][j]);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) n_list = 0;
+        __syncthreads();
+    };
+
+    // candidates: the particles of the 27 surrounding tile bins whose support reaches this tile.  The 27 index ranges
+    // are concatenated so that every thread tests its candidates with independent loads (one round trip, not 27).
+    const int total = r_off[27];
+    for (int seg = 0; seg < total; seg += NT_LIST) {
+        const int seg_end = min(total, seg + NT_LIST);
+        // four candidates per thread and round: the loads of a round are independent (one L2 round trip per round)
+        int r = 0;
+        for (int q0 = seg + tid; q0 < seg_end; q0 += 4 * NT_THREADS) {
+            int idx[4];
+            int4 l0[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = q0 + u * NT_THREADS;
+                idx[u] = -1;
+                if (q < seg_end) {
+                    while (q >= r_off[r + 1]) ++r;     // q grows from one candidate to the next: r never goes back
+                    idx[u] = r_lo[r] + (q - r_off[r]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (idx[u] >= 0) l0[u] = cell[ebase + idx[u]];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                // the support [l0, l0 + W) reaches the tile [T0, T0 + extent) iff T0 - l0 (periodic) lies in (-extent, W)
+                if (idx[u] >= 0 && wrap_off(X0 - l0[u].x, nf, NT_TX) < W && wrap_off(Y0 - l0[u].y, nf, NT_T) < W &&
+                    wrap_off(Z0 - l0[u].z, nf, NT_T) < W)
+                    list[atomicAdd(&n_list, 1)] = idx[u];
+            }
+        }
+        __syncthreads();
+        drain();
+    }
+
+    // every cell of the tile is written once; a warp store covers one z line of the patch (256 contiguous bytes)
+    double *out = reinterpret_cast<double *>(grid) + ((((size_t)blockIdx.y * nf + XW) * nf + YW) * nf + Z0) * 2 + lane;
+#pragma unroll
+    for (int i = 0; i < NT_PX; ++i)
+#pragma unroll
+        for (int j = 0; j < NT_PY; ++j) out[((size_t)i * nf + j) * nf * 2] = acc[i][j];
+}
+
+typedef void (*records_fn)(const double *, int64_t, const int2 *, int, int, const int *, int64_t, NufftGeom, double, double,
+                           double, double *, int4 *);
+typedef void (*tiles_fn)(const double *, const int4 *, const int *, int64_t, int, int, double2 *);
+template <int W>
+void tile_kernels_of(records_fn *r, tiles_fn *t)
+{
+    *r = nufft_records<W>;
+    *t = nufft_spread_tiles<W>;
+}
+void tile_kernels(int w, records_fn *r, tiles_fn *t)
+{
+    switch (w) {
+    case 4: return tile_kernels_of<4>(r, t);
+    case 5: return tile_kernels_of<5>(r, t);
+    case 6: return tile_kernels_of<6>(r, t);
+    case 7: return tile_kernels_of<7>(r, t);
+    case 8: return tile_kernels_of<8>(r, t);
+    case 9: return tile_kernels_of<9>(r, t);
+    case 10: return tile_kernels_of<10>(r, t);
+    case 11: return tile_kernels_of<11>(r, t);
+    case 12: return tile_kernels_of<12>(r, t);
+    case 13: return tile_kernels_of<13>(r, t);
+    case 14: return tile_kernels_of<14>(r, t);
+    case 15: return tile_kernels_of<15>(r, t);
+    default: return tile_kernels_of<16>(r, t);
+    }
+}
+
 typedef void (*spread_fn)(const double *, int64_t, const int2 *, int, int, const int *, int64_t, NufftGeom, double,
                           double, double, double *);
 spread_fn spread_kernel(int w)
@@ -569,6 +885,14 @@ int Nufft::init(const Ctx *ctx, int n_points, double eps_, int64_t max_set_len)
     MDC_CUDA(raise_smem_limit(nufft_fft_s<true>, ctx->smem_optin));
     const char *env = getenv("MDC_NUFFT_SORT");
     sort = !(env && env[0] == '0');
+    // spreading by gather (nufft_spread_tiles) where the fine grid holds enough 16^3 tiles to fill the GPU; small grids
+    // keep the scatter kernel (their spreading cost is small, and a support may wrap onto its own tile there).
+    // MDC_NUFFT_SPREAD=atomic / tiles in the environment forces one (tiles needs nf >= 64).
+    nb = nf / NT_T;
+    tiles = nf % NT_T == 0 && nf >= 128;
+    const char *sp = getenv("MDC_NUFFT_SPREAD");
+    if (sp && sp[0] == 'a') tiles = false;
+    if (sp && sp[0] == 't') tiles = nf % NT_T == 0 && nf >= 64;
     return MDC_OK;
 }
 
@@ -582,7 +906,12 @@ int Nufft::reserve(int batch_hint)
     G_ = std::max(1, std::min(G_, batch_hint));
     MDC_CHECK(grid.alloc((size_t)G_ * nf * nf * nf));
     MDC_CHECK(buf1.alloc((size_t)G_ * nf * nf * g.ncp));
-    if (sort) {
+    if (tiles) {
+        MDC_CHECK(bins.alloc((size_t)G_ * nb * nb * nb));
+        MDC_CHECK(order.alloc((size_t)G_ * maxlen));
+        MDC_CHECK(rec.alloc((size_t)G_ * maxlen * 4 * g.w));
+        MDC_CHECK(cell.alloc((size_t)G_ * maxlen));
+    } else if (sort) {
         MDC_CHECK(bins.alloc((size_t)G_ * nf));
         MDC_CHECK(order.alloc((size_t)G_ * maxlen));
     }
@@ -598,8 +927,57 @@ void Nufft::release()
     dec.release();
     bins.release();
     order.release();
+    rec.release();
+    cell.release();
     G = 0;
 }
+
+// MDC_NUFFT_PROFILE=1 in the environment: device time of every stage of the chain (CUDA events on the plan's stream, so
+// also when the chain shares the device with kernels of another stream), printed when the process exits.  Diagnostics.
+namespace {
+struct StageProfile {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;
+    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    StageProfile()
+    {
+        const char *e = getenv("MDC_NUFFT_PROFILE");
+        on = e && e[0] == '1';
+    }
+    void mark(cudaStream_t st, int t)
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        tag.push_back(t);
+        if (ev.size() > 4096) flush();
+    }
+    void flush()
+    {
+        for (size_t i = 1; i < ev.size(); ++i) {
+            if (tag[i] == 0) continue;   // 0 = start of a batch
+            float m = 0.f;
+            cudaEventSynchronize(ev[i]);
+            cudaEventElapsedTime(&m, ev[i - 1], ev[i]);
+            ms[tag[i]] += m;
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        tag.clear();
+    }
+    ~StageProfile()
+    {
+        if (!on) return;
+        flush();
+        fprintf(stderr, "MDC_NUFFT_PROFILE ms: sort+records %.3f spread %.3f fft_z %.3f fft_y %.3f fft_x %.3f\n", ms[1], ms[2], ms[3],
+                ms[4], ms[5]);
+    }
+};
+StageProfile g_prof;
+}  // namespace
 
 int Nufft::density(cudaStream_t st, const double *posd, const double iL[3], int64_t N, const int2 *d_sets, int n_sets, int F,
                    const int *row_cnt, const int64_t *row_qoff, int64_t nq, int P, double2 *part, int *launches)
@@ -611,6 +989,25 @@ int Nufft::density(cudaStream_t st, const double *posd, const double iL[3], int6
     const unsigned pblocks = (unsigned)ceil_div(maxlen, 256);
     for (int e0 = 0; e0 < total; e0 += G) {
         const unsigned B = (unsigned)std::min(G, total - e0);
+        g_prof.mark(st, 0);
+        if (tiles) {
+            // sort by 16^3 tile bin, kernel values once per particle, then one block per tile gathers: the grid is
+            // written exactly once (no clearing pass, no atomics)
+            const size_t nbins = (size_t)nb * nb * nb;
+            records_fn rk;
+            tiles_fn tk;
+            tile_kernels(g.w, &rk, &tk);
+            MDC_CUDA(cudaMemsetAsync(bins.p, 0, (size_t)B * nbins * sizeof(int), st));
+            nufft_tile_count<<<dim3(pblocks, B), 256, 0, st>>>(posd, N, d_sets, n_sets, e0, g.nf, nb, iL[0], iL[1], iL[2], bins.p);
+            nufft_scan_any<<<B, 128, 0, st>>>((int)nbins, bins.p);
+            nufft_tile_scatter<<<dim3(pblocks, B), 256, 0, st>>>(posd, N, d_sets, n_sets, e0, g.nf, nb, iL[0], iL[1], iL[2],
+                                                                bins.p, order.p, maxlen);
+            rk<<<dim3((unsigned)ceil_div(maxlen, 4), B), 128, 0, st>>>(posd, N, d_sets, n_sets, e0, order.p, maxlen, g, iL[0],
+                                                                       iL[1], iL[2], rec.p, cell.p);
+            g_prof.mark(st, 1);
+            tk<<<dim3((unsigned)(nbins * (NT_T / NT_TX)), B), NT_THREADS, 0, st>>>(rec.p, cell.p, bins.p, maxlen, g.nf, nb, grid.p);
+            *launches += 5;
+        } else {
         MDC_CUDA(cudaMemsetAsync(grid.p, 0, (size_t)B * nf * nf * nf * sizeof(double2), st));
         const int *ord = nullptr;
         if (sort) {
@@ -625,17 +1022,23 @@ int Nufft::density(cudaStream_t st, const double *posd, const double iL[3], int6
         const unsigned sblocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(maxlen, NU_THREADS / 32), 148 * 8192 / NU_THREADS));
         spread_kernel(g.w)<<<dim3(sblocks, B), NU_THREADS, 0, st>>>(posd, N, d_sets, n_sets, e0, ord, maxlen, g, iL[0], iL[1],
                                                              iL[2], reinterpret_cast<double *>(grid.p));
+        ++*launches;
+        }
+        g_prof.mark(st, 2);
         const unsigned zblocks = (unsigned)std::min<int64_t>(ceil_div((int64_t)nf * nf, NU_THREADS / 32), 148 * 4096 / NU_THREADS);
         nufft_fft_z<<<dim3(zblocks, B), NU_THREADS, smem_z, st>>>(grid.p, buf1.p, tw.p, g);
+        g_prof.mark(st, 3);
         // y pass: buf1 (nf, nf, ncp) -> grid reused as (nf, n, ncp)
         const int64_t ytiles = ceil_div(g.ncp, NU_TC);
         nufft_fft_s<false><<<dim3((unsigned)(nf * ytiles), B), NU_THREADS, smem_s, st>>>(
             buf1.p, grid.p, tw.p, g, (int)nf, (int64_t)g.ncp, nullptr, nullptr, nullptr, 0);
+        g_prof.mark(st, 4);
         // x pass + deconvolution + scatter into the plan's wavevector order
         const int64_t S = (int64_t)n * g.ncp, xtiles = ceil_div(S, NU_TC);
         nufft_fft_s<true><<<dim3((unsigned)xtiles, B), NU_THREADS, smem_s, st>>>(
             grid.p, part + (size_t)e0 * P * nq, tw.p, g, 1, S, dec.p, row_cnt, row_qoff, (int64_t)P * nq);
-        *launches += 4;
+        g_prof.mark(st, 5);
+        *launches += 3;
     }
     MDC_CUDA(cudaGetLastError());
     return MDC_OK;

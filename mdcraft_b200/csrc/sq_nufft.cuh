@@ -21,6 +21,10 @@ struct Nufft {
     int G = 0;                        // (frame, set) elements processed per batch
     int64_t maxlen = 0;               // longest particle set
     bool sort = true;                 // order every set by fine-grid x plane before spreading (L2 locality)
+    bool tiles = false;               // spread by GATHER: one block per 16^3 tile of the fine grid, no atomics (nf >= 128)
+    int nb = 0;                       // tiles per axis (nf / 16)
+    DevBuf<double> rec;               // (G, maxlen, 4 w) per-particle kernel values {vx(w), vy(w), wz(w) complex}
+    DevBuf<int4> cell;                // (G, maxlen) first fine-grid cell of every particle's support {l0x, l0y, l0z, -}
     size_t smem_z = 0, smem_s = 0;
     DevBuf<double2> grid, buf1, tw;   // (G, nf, nf, nf) [reused as (G, nf, n, ncp)], (G, nf, nf, ncp), (nf)
     DevBuf<double> dec;               // (n) deconvolution factors 1 / ((w / 2) phihat(pi k' w / nf))
