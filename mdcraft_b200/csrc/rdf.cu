@@ -619,11 +619,18 @@ struct FastShared {
     uint4 ibox[RF_THREADS / 32][8];   // + {centre}, {half extent} of the box, of its first 64 and of its last 64 particles
     uint4 jbox[RF_TJ / 32][2];
     float cull[4];
+    // sorted frames: next chunk of 32 rows to hand out for the 128 particles i of every warp ("group").  A warp draws the
+    // chunks of its own group from here and, once those are gone, the remaining chunks of the other groups (it then
+    // reloads that group's particles): uneven culling no longer leaves warps idle at the end of a tile pair.
+    int next_chunk[RF_THREADS / 32];
+    int pad2[8 - (RF_THREADS / 32) % 8];
 };
 
 // local index (within the tile) of particle u of this thread: a warp holds 128 consecutive particles, which in a
 // sorted frame is a compact region
 __device__ __forceinline__ int rf_il(int u) { return (int)(threadIdx.x & ~31u) * RF_IPT + u * 32 + (int)(threadIdx.x & 31u); }
+// the same for the particles of group g (the warp's own group is g = threadIdx.x / 32)
+__device__ __forceinline__ int rf_il_of(int g, int u) { return g * (32 * RF_IPT) + u * 32 + (int)(threadIdx.x & 31u); }
 
 // sorted frames: is every particle of box a farther than the cutoff from every particle of box b (minimum image)?
 // Warp-uniform.  Per axis the gap between two intervals on the 2^32 circle that do not overlap is the smaller of the
@@ -703,7 +710,7 @@ __device__ __noinline__ void resolve_pair(const TileCtx *Tp, int il, int jl, con
 
 // cold: the pairs (this thread's particle u, row jl) with bit u set in `mask` are undecided; park them
 __device__ __noinline__ void park_row(const TileCtx *Tp, unsigned *queue, unsigned *qcount, int jl, unsigned mask,
-                                      const double *sT, unsigned *hist, unsigned long long v01 = 0ull,
+                                      const double *sT, unsigned *hist, int group, unsigned long long v01 = 0ull,
                                       unsigned long long v23 = 0ull, bool uncount = false)
 {
     for (int u = 0; u < RF_IPT; ++u) {
@@ -719,7 +726,7 @@ __device__ __noinline__ void park_row(const TileCtx *Tp, unsigned *queue, unsign
             if (k > Tp->A.n_bins || k < -1) continue;
             atomicSub(&hist[k], 1u);
         }
-        const int il = rf_il(u);
+        const int il = rf_il_of(group, u);
         const unsigned slot = atomicAdd(qcount, 1u);
         if (slot < RF_QCAP) queue[slot] = (unsigned)il | ((unsigned)jl << 16);
         else resolve_pair(Tp, il, jl, sT, hist);   // queue full (pathological inputs): resolve in line
@@ -993,9 +1000,9 @@ __device__ __forceinline__ unsigned bin_count2(unsigned long long v, unsigned lo
 }
 
 template <bool CHECK, bool CUBIC, bool EXCL, bool R0ZERO, bool CULL, bool EXT>
-__device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, const uint32_t (&ux)[RF_IPT],
-                                                const uint32_t (&uy)[RF_IPT], const uint32_t (&uz)[RF_IPT],
-                                                const int (&bi)[RF_IPT], const FrameFast &ff, float thr, unsigned B,
+__device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, uint32_t (&ux)[RF_IPT],
+                                                uint32_t (&uy)[RF_IPT], uint32_t (&uz)[RF_IPT],
+                                                int (&bi)[RF_IPT], const FrameFast &ff, float thr, unsigned B,
                                                 int64_t na, int64_t i0, int64_t j0, bool diag, const double *sT,
                                                 unsigned *hist)
 {
@@ -1013,6 +1020,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     const unsigned blim = R0ZERO ? B + 0x4B400000u : B;
     const unsigned hbase = (R0ZERO || EXT) ? hist_addr - 4u * 0x4B400000u : hist_addr;
     constexpr int RF_UNROLL = MDC_RF_UNROLL;
+    int group = (int)(threadIdx.x >> 5);   // whose particles ux / uy / uz hold: the warp's own, or a group it helps out
     auto row = [&](int j) {
         const uint4 pj = S->sj[j];
         unsigned ok[RF_IPT];
@@ -1021,7 +1029,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
             ok[u] = 1u;
             if (EXCL) ok[u] = bi[u] != (int)pj.w;
             if (CHECK) {
-                const int64_t ig = i0 + rf_il(u);
+                const int64_t ig = i0 + rf_il_of(group, u);
                 ok[u] = ok[u] && (ig < na) && (!diag || (j0 + j) > ig);
             }
         }
@@ -1038,8 +1046,8 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
 #pragma unroll
             for (int u = 0; u < RF_IPT; ++u)
                 if (adf[u] > thr && ok[u]) und |= 1u << u;
-            if (EXT) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, v01, v23, true);
-            else park_row(Tp, S->queue, &S->qcount, j, und, sT, hist);
+            if (EXT) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, group, v01, v23, true);
+            else park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, group);
         }
     };
     // half a row: the pairs of particles (2 H, 2 H + 1) only (extended histograms, tiles without ok flags)
@@ -1053,7 +1061,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
             unsigned und = 0;
             if (adf[0] > thr) und |= 1u << a;
             if (adf[1] > thr) und |= 1u << b;
-            park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, v, v, true);   // park_row picks v01 / v23 by u
+            park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, group, v, v, true);   // park_row picks v01 / v23 by u
         }
     };
     auto walk = [&](unsigned m, int c, auto &&body) {
@@ -1064,34 +1072,59 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
         }
     };
     if (CULL) {
-        // sorted frames: this warp's 128 particles against chunks of 32 rows; chunks out of reach are skipped
-        const uint4 *ib = S->ibox[threadIdx.x >> 5];
-        for (int c = 0; c < nj; c += 32) {
-            if (boxes_apart(ib, S->jbox[c >> 5], S->cull)) continue;
-            // then row by row (one test per lane): only the rows within reach of the warp's box are evaluated
-            if (EXT && !HAS_OK) {
-                // ... and half row by half row: the warp's first and last 64 particles have boxes of their own
-                const unsigned ma = rows_in_reach(S, ib + 4, c, nj), mb = rows_in_reach(S, ib + 6, c, nj);
-                const unsigned both = ma & mb;
-                if (__popc(both) >= 29) {   // (nearly) all rows in full: the plain loop has less overhead per row
+        // sorted frames: a group of 128 particles against chunks of 32 rows; chunks out of reach are skipped.  Chunks are
+        // drawn from the group's counter: first the warp's own group, then what is left of the others (work stealing).
+        const int own = group;
+        for (int turn = 0; turn < RF_THREADS / 32; ++turn) {
+            const int g = (own + turn) & (RF_THREADS / 32 - 1);
+            if (turn > 0) {
+                if (*(volatile int *)&S->next_chunk[g] * 32 >= nj) continue;   // nothing left there (warp-uniform)
+                // take over group g: its particles replace this warp's own (not needed again for this tile pair)
+                const RdfArgs &A = Tp->A;
+                const uint32_t *ax = A.ua + ((int64_t)Tp->f * 3) * A.na, *ay = ax + A.na, *az = ay + A.na;
+                const int *oa = A.oa ? A.oa + (int64_t)Tp->f * A.na : nullptr;
+                group = g;
+#pragma unroll
+                for (int u = 0; u < RF_IPT; ++u) {
+                    const int64_t ii = min(i0 + rf_il_of(g, u), na - 1);
+                    ux[u] = ax[ii];
+                    uy[u] = ay[ii];
+                    uz[u] = az[ii];
+                    bi[u] = A.ex0 > 0 ? (int)((oa ? (int64_t)oa[ii] : ii) / A.ex0) : -1;
+                }
+            }
+            const uint4 *ib = S->ibox[g];
+            for (;;) {
+                int c = 0;
+                if ((threadIdx.x & 31u) == 0u) c = atomicAdd(&S->next_chunk[g], 1);
+                c = __shfl_sync(0xffffffffu, c, 0) * 32;
+                if (c >= nj) break;
+                if (boxes_apart(ib, S->jbox[c >> 5], S->cull)) continue;
+                // then row by row (one test per lane): only the rows within reach of the group's box are evaluated
+                if (EXT && !HAS_OK) {
+                    // ... and half row by half row: the group's first and last 64 particles have boxes of their own
+                    const unsigned ma = rows_in_reach(S, ib + 4, c, nj), mb = rows_in_reach(S, ib + 6, c, nj);
+                    const unsigned both = ma & mb;
+                    if (__popc(both) >= 29) {   // (nearly) all rows in full: the plain loop has less overhead per row
+                        const int je = min(nj, c + 32);
+#pragma unroll RF_UNROLL
+                        for (int j = c; j < je; ++j) row(j);
+                        continue;
+                    }
+                    walk(both, c, [&](int j) { row(j); });
+                    walk(ma & ~mb, c, [&](int j) { half_row(j, 0); });
+                    walk(mb & ~ma, c, [&](int j) { half_row(j, 1); });
+                    continue;
+                }
+                unsigned m = rows_in_reach(S, ib + 2, c, nj);
+                if (__popc(m) >= 29) {   // (nearly) all of them: the plain loop has less overhead per row than the bit walk
                     const int je = min(nj, c + 32);
 #pragma unroll RF_UNROLL
                     for (int j = c; j < je; ++j) row(j);
                     continue;
                 }
-                walk(both, c, [&](int j) { row(j); });
-                walk(ma & ~mb, c, [&](int j) { half_row(j, 0); });
-                walk(mb & ~ma, c, [&](int j) { half_row(j, 1); });
-                continue;
+                walk(m, c, [&](int j) { row(j); });
             }
-            unsigned m = rows_in_reach(S, ib + 2, c, nj);
-            if (__popc(m) >= 29) {   // (nearly) all of them: the plain loop has less overhead per row than the bit walk
-                const int je = min(nj, c + 32);
-#pragma unroll RF_UNROLL
-                for (int j = c; j < je; ++j) row(j);
-                continue;
-            }
-            walk(m, c, [&](int j) { row(j); });
         }
     } else {
 #pragma unroll RF_UNROLL
@@ -1215,6 +1248,7 @@ rdf_pairs_fast(RdfArgs A)
             }
             if (threadIdx.x < 3) S->cull[threadIdx.x] = (float)(fb.box[threadIdx.x] * (1.0 / 4294967296.0));
             if (threadIdx.x == 3) S->cull[3] = (float)(A.cull_r * A.cull_r);
+            if (threadIdx.x >= 32 && threadIdx.x < 32 + RF_THREADS / 32) S->next_chunk[threadIdx.x - 32] = 0;
         }
         __syncthreads();
         static_assert(sizeof(TileCtx) <= sizeof(S->ctx), "TileCtx must fit its shared-memory slot");
