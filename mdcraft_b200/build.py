@@ -49,7 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *SOURCES]
+    extra = os.environ.get("MDC_NVCC_EXTRA", "").split()   # kernel experiments only (e.g. -DMDC_NU_FFT_BLOCKS=8)
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
