@@ -596,16 +596,19 @@ def run_native(args, rank, world, emit=print):
 
 
 def nufft_roofline(used, sq_alone_ms, frames, nq, summary):
-    """HBM roofline of the NUFFT chain (memset, spread, three pruned FFT passes, pair accumulation):
-    algorithmic bytes = every buffer written once and read once, 16 B per complex FP64."""
-    nf, n = used["nf"], SQ["n_points"]
+    """HBM roofline of the NUFFT chain (per-particle kernel tables, gather spreading, three pruned FFT passes, pair
+    accumulation): algorithmic bytes = every buffer written once and read once, 16 B per complex FP64.  The spreading
+    kernel itself is FP64-issue / latency bound, not HBM bound (it writes the fine grid exactly once); the FFT passes are
+    the HBM-bound part.  With the scatter kernel of round 1 (grids below 128 points per axis still use it) the fine grid is
+    also cleared and read-modify-written."""
+    nf, n, w = used["nf"], SQ["n_points"], used["w"]
     ncp = (n + 1) & ~1
-    alg = 16.0 * (nf ** 3                                   # clear the fine grid
-                  + 2 * nf ** 3                            # spread: read-modify-write of the fine grid
-                  + nf ** 3 + nf * nf * ncp                # z pass
-                  + nf * nf * ncp + nf * n * ncp           # y pass
-                  + nf * n * ncp + nq                      # x pass + deconvolution
-                  + 2 * nq)                                # rho -> |rho|^2 accumulated into ssf
+    tiles = nf >= 128 and os.environ.get("MDC_NUFFT_SPREAD", "t")[0] != "a"
+    spread = (N_PART * (4 * w * 8 + 16) * 2 + nf ** 3 * 16) if tiles else 16.0 * 3 * nf ** 3
+    alg = spread + 16.0 * (nf ** 3 + nf * nf * ncp            # z pass
+                           + nf * nf * ncp + nf * n * ncp     # y pass
+                           + nf * n * ncp + nq                # x pass + deconvolution
+                           + 2 * nq)                          # rho -> |rho|^2 accumulated into ssf
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_file):
         peak_gbs, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)"
@@ -618,12 +621,15 @@ def nufft_roofline(used, sq_alone_ms, frames, nq, summary):
         if parts and all(p is not None for p in parts):
             traffic = float(sum(parts))
     return {"bound": "hbm", "measured": "S(q) alone (in the timed steps these kernels share the device with g(r))",
-            "kernel": "nufft_spread + nufft_fft_z + nufft_fft_s<0> + nufft_fft_s<1> (+ memset, sq_pair_accum)",
+            "kernel": ("nufft_records + nufft_spread_tiles" if tiles else "memset + nufft_spread")
+                      + " + nufft_fft_z + nufft_fft_s<0> + nufft_fft_s<1> (+ sq_pair_accum)",
             "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
             "traffic": traffic, "traffic_unit": "bytes per frame (sum of the NUFFT kernels)", "traffic_source": ncu_source(summary),
             "peak_source": peak_src,
-            "algorithmic": f"{alg / 1e6:.0f} MB per frame: fine grid {nf}^3 complex FP64 cleared, spread into (w = {used['w']}) "
-                           f"and read once; pruned intermediates {nf}^2 x {n} and {nf} x {n}^2 written and read once; {nq} densities"}
+            "algorithmic": f"{alg / 1e6:.0f} MB per frame: fine grid {nf}^3 complex FP64 "
+                           + ("written once by the gather kernel" if tiles else "cleared and spread into (read-modify-write)")
+                           + f" (w = {w}) and read once; pruned intermediates {nf}^2 x {n} and {nf} x {n}^2 written and read "
+                           f"once; {nq} densities"}
 
 
 def secondary_figures(args, ctx, ctx_s, rdf, sqp, gr_dev, sq_dev, box_g, Ls, b, flush, nq):

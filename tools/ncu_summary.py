@@ -3,7 +3,7 @@
 Prints the handful of ncu metrics this project reads, from one or more .ncu-rep files (runs `ncu -i ... --page raw --csv`).
 
     python tools/ncu_summary.py a.ncu-rep [b.ncu-rep ...]                      text, one block per kernel launch
-    python tools/ncu_summary.py --json OUT.json [--frames-per-launch F] [--pairs-per-launch P] a.ncu-rep ...
+    python tools/ncu_summary.py --json OUT.json [--frames-per-launch F] [--pairs-per-launch P] a.ncu-rep[@F] ...
 
 --json writes the machine-readable summary that bench.py reads for `roofline.traffic`, `issue_active` and
 `slots_per_pair` (profiles/ncu_r02.json): per kernel the DRAM bytes, issue-slot utilisation, executed warp instructions
@@ -78,7 +78,12 @@ def main(argv):
         else:
             files.append(a)
     kernels = []
+    default_frames = frames
     for path in files:
+        frames = default_frames
+        if '@' in path:                      # file.ncu-rep@F: F frames per launch in that capture
+            path, f = path.rsplit('@', 1)
+            frames = float(f)
         hdr, units_row, launches = rows_of(path)
         units = dict(zip(hdr, units_row))
         for d in launches:
