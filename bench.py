@@ -445,6 +445,7 @@ def run_native(args, rank, world, emit=print):
 
     # ------------------------------------------------------------------ value: frames resident in HBM, C ABI
     timed(gr_dev, sq_dev, min(W, K), 0)
+    finalise(rdf, sqp, min(W, K) * b)     # the warm-up covers the finalisation too (NCCL sets its channels up on first use)
     rdf.reset()
     sqp.reset()
     with ClockSampler(local) as clk:
