@@ -11,16 +11,20 @@
 //   1. centre the modes: k' = k - k0, strength c_j = exp(2 pi i k0 (sx + sy + sz)),
 //      so a fine grid of nf >= 1.5 n points per axis suffices instead of 1.5 (2 n - 1);
 //   2. spread c_j onto the fine grid with the separable "exponential of semicircle" kernel
-//      phi(z) = exp(beta (sqrt(1 - z^2) - 1)), z = (l - s nf) / (w / 2), |z| <= 1  (Barnett et al., FINUFFT);
+//      phi(z) = exp(beta (sqrt(1 - z^2) - 1)), z = (l - s nf) / (w / 2), |z| <= 1  (Barnett et al., FINUFFT):
+//      fine grids of 128 points or more BY GATHER (nufft_records / nufft_tile_fill / nufft_spread_tiles: a block owns a
+//      tile of the grid, accumulates in registers and writes every cell once), smaller ones by scatter (nufft_spread:
+//      one warp per particle, FP64 reductions into an L2-resident grid);
 //   3. pruned FFTs, one axis at a time, in FP64, in shared memory: nf inputs -> the n wanted modes, so the
 //      intermediates shrink (nf^3 -> nf^2 n -> nf n^2 -> kept wavevectors);
 //   4. divide by the kernel's Fourier transform (per-axis table) while scattering into the plan's wavevector order.
 // The relative l2 error is set by (nf / n, w): 1e-9 requested in FP32 mode (the factored FP32 kernel reaches
 // 8e-8), 1e-13 in FP64 mode; tools/nufft_model.py holds the NumPy model these parameters were derived with.
 //
-// Roofline: HBM.  Algorithmic bytes per (frame, set) = the fine grid written and read once plus the pruned
-// intermediates: 16 B * (2 nf^3 + 2 nf^2 n + 2 nf n^2 + Nq); the spreading kernel adds N w^3 FP64 reductions
-// (RED.E.ADD.F64) that land in L2 because particles are visited in x-plane order.
+// Rooflines: the FFT passes are HBM bound (every intermediate written and read once: 16 B * (nf^3 + 2 nf^2 n +
+// 2 nf n^2 + Nq) per (frame, set)); the gather kernel is FP64-issue / latency bound (4 DMUL + 32 DFMA per particle and
+// patch of 4 x 8 x 16 cells) and writes 16 B * nf^3 once; the scatter kernel is bound by the L2 reduction rate
+// (N w^3 complex RED.E.ADD.F64).
 #include "sq_nufft.cuh"
 
 #include <math.h>
@@ -367,21 +371,21 @@ constexpr int NT_TX = 8;                 // tile extent in x: half a bin, so tha
                                          // fits the quarter of an SM that the g(r) pair kernel leaves free (see NU_THREADS)
 constexpr int NT_PX = 4, NT_PY = 8;      // patch of one warp: 4 x 8 (x, y) positions x 16 z; 2 x 2 patches per tile
 constexpr int NT_THREADS = 128;          // 4 warps
-constexpr int NT_LIST = 1024;            // candidate list (particle slots) per drain
+constexpr int NT_MAX_TILES = 12;         // tiles a support of <= 16 cells can reach: 3 x 2 x 2
 
-__device__ __forceinline__ int tile_of(double g) { return ((int)g) >> 4; }
-
-__global__ void nufft_tile_count(const double *__restrict__ posd, int64_t N, const int2 *__restrict__ sets, int n_sets,
-                                 int e0, int nf, int nb, double iLx, double iLy, double iLz, int *__restrict__ cnt)
+// Tiles (8 x 16 x 16 cells, index (tx2 * nb + ty) * nb + tz) that the support [l0, l0 + W) of a particle reaches, per
+// axis: first tile and count (periodic).  At most 3 x 2 x 2 for W <= 16.
+template <int W>
+__device__ __forceinline__ void tiles_reached(const int4 &l0, int nf, int (&t0)[3], int (&nt)[3])
 {
-    const int e = e0 + blockIdx.y, f = e / n_sets, s = e - f * n_sets;
-    const int2 set = sets[s];
-    const int64_t j = (int64_t)set.x + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= set.y) return;
-    const int bx = tile_of(fine_coord(posd[((int64_t)f * 3 + 0) * N + j], iLx, nf));
-    const int by = tile_of(fine_coord(posd[((int64_t)f * 3 + 1) * N + j], iLy, nf));
-    const int bz = tile_of(fine_coord(posd[((int64_t)f * 3 + 2) * N + j], iLz, nf));
-    atomicAdd(&cnt[(size_t)blockIdx.y * nb * nb * nb + ((size_t)bx * nb + by) * nb + bz], 1);
+    const int ext[3] = {NT_TX, NT_T, NT_T};
+    const int lo[3] = {l0.x, l0.y, l0.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int a = lo[k] + nf, e = a + W - 1;          // shifted by nf: non-negative (l0 >= -W / 2)
+        t0[k] = a / ext[k];
+        nt[k] = e / ext[k] - t0[k] + 1;
+    }
 }
 
 // exclusive scan of n counters per element (one block of 128 threads per element, any n).  128 threads, like every
@@ -409,29 +413,14 @@ __global__ void __launch_bounds__(128) nufft_scan_any(int n, int *__restrict__ c
     }
 }
 
-// sorted slot of every particle (order[slot] = particle); afterwards cursor[b] = END of bin b
-__global__ void nufft_tile_scatter(const double *__restrict__ posd, int64_t N, const int2 *__restrict__ sets, int n_sets,
-                                   int e0, int nf, int nb, double iLx, double iLy, double iLz, int *__restrict__ cursor,
-                                   int *__restrict__ order, int64_t maxlen)
-{
-    const int e = e0 + blockIdx.y, f = e / n_sets, s = e - f * n_sets;
-    const int2 set = sets[s];
-    const int64_t j = (int64_t)set.x + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= set.y) return;
-    const int bx = tile_of(fine_coord(posd[((int64_t)f * 3 + 0) * N + j], iLx, nf));
-    const int by = tile_of(fine_coord(posd[((int64_t)f * 3 + 1) * N + j], iLy, nf));
-    const int bz = tile_of(fine_coord(posd[((int64_t)f * 3 + 2) * N + j], iLz, nf));
-    const int pos = atomicAdd(&cursor[(size_t)blockIdx.y * nb * nb * nb + ((size_t)bx * nb + by) * nb + bz], 1);
-    order[(int64_t)blockIdx.y * maxlen + pos] = (int)j;
-}
-
-// Kernel values of every particle, in sorted order: rec[slot] = {vx[W], vy[W], (vz[W] * strength) as (re, im)[W]},
-// cell[slot] = first cell of the support per axis (may be negative: periodic).  One warp per particle.
+// Kernel values of every particle of an element (slot = index within its set): rec[slot] = {vx[W], vy[W],
+// (vz[W] * strength) as (re, im)[W]}, cell[slot] = first cell of the support per axis (may be negative: periodic); and
+// one count per tile the support reaches (tcount: the CSR row lengths of the tile -> particles lists).  One warp per particle.
 template <int W>
 __global__ void __launch_bounds__(128)
 nufft_records(const double *__restrict__ posd, int64_t N, const int2 *__restrict__ sets, int n_sets, int e0,
-              const int *__restrict__ order, int64_t maxlen, NufftGeom g, double iLx, double iLy, double iLz,
-              double *__restrict__ rec, int4 *__restrict__ cell)
+              int64_t maxlen, NufftGeom g, int nb, double iLx, double iLy, double iLz, double *__restrict__ rec,
+              int4 *__restrict__ cell, int *__restrict__ tcount)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = e0 + blockIdx.y, f = e / n_sets, s = e - f * n_sets;
@@ -441,7 +430,7 @@ nufft_records(const double *__restrict__ posd, int64_t N, const int2 *__restrict
     if (idx >= len) return;
     const int nf = g.nf;
     const int64_t slot = (int64_t)blockIdx.y * maxlen + idx;
-    const int64_t j = order[slot];
+    const int64_t j = (int64_t)set.x + idx;
     const double gx = fine_coord(posd[((int64_t)f * 3 + 0) * N + j], iLx, nf);
     const double gy = fine_coord(posd[((int64_t)f * 3 + 1) * N + j], iLy, nf);
     const double gz = fine_coord(posd[((int64_t)f * 3 + 2) * N + j], iLz, nf);
@@ -470,7 +459,40 @@ nufft_records(const double *__restrict__ posd, int64_t N, const int2 *__restrict
         R[2 * W + 2 * t] = vz * cs;
         R[2 * W + 2 * t + 1] = vz * sn;
     }
-    if (lane == 0) cell[slot] = make_int4(l0x, l0y, l0z, 0);
+    const int4 l0 = make_int4(l0x, l0y, l0z, 0);
+    if (lane == 0) cell[slot] = l0;
+    // one lane per reached tile (at most 12)
+    int t0[3], nt[3];
+    tiles_reached<W>(l0, nf, t0, nt);
+    if (lane < nt[0] * nt[1] * nt[2]) {
+        const int ix = lane / (nt[1] * nt[2]), iy = (lane / nt[2]) % nt[1], iz = lane % nt[2];
+        const int tile = (((t0[0] + ix) % (2 * nb)) * nb + (t0[1] + iy) % nb) * nb + (t0[2] + iz) % nb;
+        atomicAdd(&tcount[(size_t)blockIdx.y * 2 * nb * nb * nb + tile], 1);
+    }
+}
+
+// CSR fill: every particle appends its slot to the list of every tile its support reaches; afterwards cursor[tile] = END
+// of the tile's list (cursor starts as the exclusive scan of the counts).  One thread per particle.
+template <int W>
+__global__ void nufft_tile_fill(const int2 *__restrict__ sets, int n_sets, int e0, int64_t maxlen, int nf, int nb,
+                                const int4 *__restrict__ cell, int *__restrict__ cursor, int *__restrict__ tlist,
+                                int64_t list_pitch)
+{
+    const int e = e0 + blockIdx.y, f = e / n_sets, s = e - f * n_sets;
+    const int2 set = sets[s];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= set.y - set.x) return;
+    const int4 l0 = cell[(int64_t)blockIdx.y * maxlen + idx];
+    int t0[3], nt[3];
+    tiles_reached<W>(l0, nf, t0, nt);
+    int *cur = cursor + (size_t)blockIdx.y * 2 * nb * nb * nb;
+    int *out = tlist + (size_t)blockIdx.y * list_pitch;
+    for (int ix = 0; ix < nt[0]; ++ix)
+        for (int iy = 0; iy < nt[1]; ++iy)
+            for (int iz = 0; iz < nt[2]; ++iz) {
+                const int tile = (((t0[0] + ix) % (2 * nb)) * nb + (t0[1] + iy) % nb) * nb + (t0[2] + iz) % nb;
+                out[atomicAdd(&cur[tile], 1)] = idx;
+            }
 }
 
 // d = a - b reduced to (-span, nf - span]: the offset of cell a from support start b on the periodic grid
@@ -483,51 +505,36 @@ __device__ __forceinline__ int wrap_off(int d, int nf, int span)
 
 template <int W>
 __global__ void __launch_bounds__(NT_THREADS, 4)
-nufft_spread_tiles(const double *__restrict__ rec, const int4 *__restrict__ cell, const int *__restrict__ binend,
-                   int64_t maxlen, int nf, int nb, double2 *__restrict__ grid)
+nufft_spread_tiles(const double *__restrict__ rec, const int4 *__restrict__ cell, const int *__restrict__ tend,
+                   const int *__restrict__ tlist, int64_t list_pitch, int64_t maxlen, int nf, int nb,
+                   double2 *__restrict__ grid)
 {
     // per-particle kernel values; vx / vy zero-padded by one patch extent on either side, so that a warp reads the
     // NT_PX / NT_PY entries its patch needs at ANY offset of the support without a range test.  Two stages: the
     // records of chunk c + 1 arrive (cp.async) while chunk c is being consumed.
     constexpr int VXP = W + 2 * NT_PX, VYP = W + 2 * NT_PY;
-    constexpr int NT_CHUNK = W <= 12 ? 32 : 24;          // particles per stage (static shared memory stays below 48 KB)
-    __shared__ int list[NT_LIST];
-    __shared__ int n_list;
+    constexpr int NT_CHUNK = 32;                         // particles per stage
     __shared__ __align__(16) double s_vx[2][NT_CHUNK][VXP], s_vy[2][NT_CHUNK][VYP], s_wz[2][NT_CHUNK][2 * W];   // wz: (re, im)
     __shared__ int4 s_cell[2][NT_CHUNK];
-    __shared__ int r_lo[27], r_off[28];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tb = blockIdx.x;                          // tile: (tx2 * nb + ty) * nb + tz, tx2 = half-bin index along x
-    const int tz = tb % nb, ty = (tb / nb) % nb, tx2 = tb / (nb * nb), tx = tx2 >> 1;
+    const int tz = tb % nb, ty = (tb / nb) % nb, tx2 = tb / (nb * nb);
     const int X0 = tx2 * NT_TX, Y0 = ty * NT_T, Z0 = tz * NT_T;
     // a warp owns a patch of NT_PX x NT_PY x 16 cells; lane = (z, re / im): the 32 lanes cover one z line of the patch
     // as 32 consecutive doubles, and every lane accumulates the NT_PX x NT_PY (x, y) positions of its (z, re / im)
     const int XW = X0 + (warp >> 1) * NT_PX, YW = Y0 + (warp & 1) * NT_PY;
     const size_t ebase = (size_t)blockIdx.y * maxlen;
-    const int *bend = binend + (size_t)blockIdx.y * nb * nb * nb;
+    // the particles whose support reaches this tile: tlist[lo .. hi) (built by nufft_records / nufft_tile_fill)
+    const int *te = tend + (size_t)blockIdx.y * 2 * nb * nb * nb;
+    const int lo = tb == 0 ? 0 : te[tb - 1], n = te[tb] - lo;
+    const int *list = tlist + (size_t)blockIdx.y * list_pitch + lo;
 
     double acc[NT_PX][NT_PY];
 #pragma unroll
     for (int i = 0; i < NT_PX; ++i)
 #pragma unroll
         for (int j = 0; j < NT_PY; ++j) acc[i][j] = 0.0;
-    for (int i = tid; i < 2 * NT_CHUNK * VXP; i += NT_THREADS) (&s_vx[0][0][0])[i] = 0.0;
-    for (int i = tid; i < 2 * NT_CHUNK * VYP; i += NT_THREADS) (&s_vy[0][0][0])[i] = 0.0;
-    if (tid == 0) n_list = 0;
-    if (tid < 27) {
-        const int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
-        const int b = (((tx + ox + nb) % nb) * nb + (ty + oy + nb) % nb) * nb + (tz + oz + nb) % nb;
-        const int lo = b == 0 ? 0 : bend[b - 1];
-        r_lo[tid] = lo;
-        r_off[tid + 1] = bend[b] - lo;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        r_off[0] = 0;
-        for (int r = 0; r < 27; ++r) r_off[r + 1] += r_off[r];
-    }
-    __syncthreads();
 
     // stage the records of list[c0 .. c0 + nc) into buffer `buf`: four threads per particle, a quarter of the record
     // (W doubles) each: vx | vy | first half of wz | second half of wz; asynchronous (LDGSTS), committed as one group
@@ -549,82 +556,53 @@ nufft_spread_tiles(const double *__restrict__ rec, const int4 *__restrict__ cell
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    auto drain = [&]() {
-        const int n = n_list;
-        if (n > 0) stage(0, 0, min(NT_CHUNK, n));
-        int buf = 0;
-        for (int c0 = 0; c0 < n; c0 += NT_CHUNK, buf ^= 1) {
-            const int nc = min(NT_CHUNK, n - c0);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();   // chunk c0 has landed; every warp is done with the other buffer (chunk c0 - 32)
-            if (c0 + NT_CHUNK < n) stage(buf ^ 1, c0 + NT_CHUNK, min(NT_CHUNK, n - c0 - NT_CHUNK));
-            // which particles of the chunk reach this warp's patch (one particle per lane), and at which offsets
-            int sx = 0, sy = 0, sz = 0;
-            bool take = false;
-            if (lane < nc) {
-                const int4 l0 = s_cell[buf][lane];
-                sx = wrap_off(XW - l0.x, nf, NT_PX);    // offset of the patch's first cell in the support, per axis
-                sy = wrap_off(YW - l0.y, nf, NT_PY);
-                sz = wrap_off(Z0 - l0.z, nf, NT_T);
-                take = sx < W && sy < W && sz < W;
-            }
-            unsigned m = __ballot_sync(0xffffffffu, take);
-            while (m) {
-                const int p = __ffs((int)m) - 1;
-                m &= m - 1u;
-                const int px = __shfl_sync(0xffffffffu, sx, p), py = __shfl_sync(0xffffffffu, sy, p);
-                const int pz = __shfl_sync(0xffffffffu, sz, p) + (lane >> 1);            // this lane's offset in the z support
-                // vz(z) * strength (re or im) of this lane; zero outside the support
-                const double wzc = (unsigned)pz < (unsigned)W ? s_wz[buf][p][2 * pz + (lane & 1)] : 0.0;
-                const double *vxp = &s_vx[buf][p][NT_PX + px], *vyp = &s_vy[buf][p][NT_PY + py];
-                double vy[NT_PY];
+    if (n > 0) stage(0, 0, min(NT_CHUNK, n));
+    // the zero pads of vx / vy (never written by the staging) while the first records are in flight
+    for (int i = tid; i < 2 * NT_CHUNK * 2 * NT_PX; i += NT_THREADS) {
+        const int r = i / (2 * NT_PX), o = i - r * (2 * NT_PX);
+        (&s_vx[0][0][0])[r * VXP + (o < NT_PX ? o : W + o)] = 0.0;
+    }
+    for (int i = tid; i < 2 * NT_CHUNK * 2 * NT_PY; i += NT_THREADS) {
+        const int r = i / (2 * NT_PY), o = i - r * (2 * NT_PY);
+        (&s_vy[0][0][0])[r * VYP + (o < NT_PY ? o : W + o)] = 0.0;
+    }
+    int buf = 0;
+    for (int c0 = 0; c0 < n; c0 += NT_CHUNK, buf ^= 1) {
+        const int nc = min(NT_CHUNK, n - c0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();   // chunk c0 has landed; every warp is done with the other buffer (chunk c0 - 32)
+        if (c0 + NT_CHUNK < n) stage(buf ^ 1, c0 + NT_CHUNK, min(NT_CHUNK, n - c0 - NT_CHUNK));
+        // which particles of the chunk reach this warp's patch (one particle per lane), and at which offsets
+        int sx = 0, sy = 0, sz = 0;
+        bool take = false;
+        if (lane < nc) {
+            const int4 l0 = s_cell[buf][lane];
+            sx = wrap_off(XW - l0.x, nf, NT_PX);    // offset of the patch's first cell in the support, per axis
+            sy = wrap_off(YW - l0.y, nf, NT_PY);
+            sz = wrap_off(Z0 - l0.z, nf, NT_T);
+            take = sx < W && sy < W && sz < W;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, take);
+        while (m) {
+            const int p = __ffs((int)m) - 1;
+            m &= m - 1u;
+            const int px = __shfl_sync(0xffffffffu, sx, p), py = __shfl_sync(0xffffffffu, sy, p);
+            const int pz = __shfl_sync(0xffffffffu, sz, p) + (lane >> 1);            // this lane's offset in the z support
+            // vz(z) * strength (re or im) of this lane; zero outside the support
+            const double wzc = (unsigned)pz < (unsigned)W ? s_wz[buf][p][2 * pz + (lane & 1)] : 0.0;
+            const double *vxp = &s_vx[buf][p][NT_PX + px], *vyp = &s_vy[buf][p][NT_PY + py];
+            double vy[NT_PY];
 #pragma unroll
-                for (int j = 0; j < NT_PY; ++j) vy[j] = vyp[j];
+            for (int j = 0; j < NT_PY; ++j) vy[j] = vyp[j];
+            // (loading the next particle's factors while these FMAs issue, with vy fetched just in time, was tried: 10 %
+            // slower alone and 20 % slower next to the pair kernel)
 #pragma unroll
-                for (int i = 0; i < NT_PX; ++i) {
-                    const double a = vxp[i] * wzc;
+            for (int i = 0; i < NT_PX; ++i) {
+                const double a = vxp[i] * wzc;
 #pragma unroll
-                    for (int j = 0; j < NT_PY; ++j) acc[i][j] = fma(a, vy[j], acc[i][j]);
-                }
+                for (int j = 0; j < NT_PY; ++j) acc[i][j] = fma(a, vy[j], acc[i][j]);
             }
         }
-        __syncthreads();
-        if (tid == 0) n_list = 0;
-        __syncthreads();
-    };
-
-    // candidates: the particles of the 27 surrounding tile bins whose support reaches this tile.  The 27 index ranges
-    // are concatenated so that every thread tests its candidates with independent loads (one round trip, not 27).
-    const int total = r_off[27];
-    for (int seg = 0; seg < total; seg += NT_LIST) {
-        const int seg_end = min(total, seg + NT_LIST);
-        // four candidates per thread and round: the loads of a round are independent (one L2 round trip per round)
-        int r = 0;
-        for (int q0 = seg + tid; q0 < seg_end; q0 += 4 * NT_THREADS) {
-            int idx[4];
-            int4 l0[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int q = q0 + u * NT_THREADS;
-                idx[u] = -1;
-                if (q < seg_end) {
-                    while (q >= r_off[r + 1]) ++r;     // q grows from one candidate to the next: r never goes back
-                    idx[u] = r_lo[r] + (q - r_off[r]);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (idx[u] >= 0) l0[u] = cell[ebase + idx[u]];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                // the support [l0, l0 + W) reaches the tile [T0, T0 + extent) iff T0 - l0 (periodic) lies in (-extent, W)
-                if (idx[u] >= 0 && wrap_off(X0 - l0[u].x, nf, NT_TX) < W && wrap_off(Y0 - l0[u].y, nf, NT_T) < W &&
-                    wrap_off(Z0 - l0[u].z, nf, NT_T) < W)
-                    list[atomicAdd(&n_list, 1)] = idx[u];
-            }
-        }
-        __syncthreads();
-        drain();
     }
 
     // every cell of the tile is written once; a warp store covers one z line of the patch (256 contiguous bytes)
@@ -635,31 +613,36 @@ nufft_spread_tiles(const double *__restrict__ rec, const int4 *__restrict__ cell
         for (int j = 0; j < NT_PY; ++j) out[((size_t)i * nf + j) * nf * 2] = acc[i][j];
 }
 
-typedef void (*records_fn)(const double *, int64_t, const int2 *, int, int, const int *, int64_t, NufftGeom, double, double,
-                           double, double *, int4 *);
-typedef void (*tiles_fn)(const double *, const int4 *, const int *, int64_t, int, int, double2 *);
+typedef void (*records_fn)(const double *, int64_t, const int2 *, int, int, int64_t, NufftGeom, int, double, double, double,
+                           double *, int4 *, int *);
+typedef void (*fill_fn)(const int2 *, int, int, int64_t, int, int, const int4 *, int *, int *, int64_t);
+typedef void (*tiles_fn)(const double *, const int4 *, const int *, const int *, int64_t, int64_t, int, int, double2 *);
+struct TileKernels {
+    records_fn records;
+    fill_fn fill;
+    tiles_fn tiles;
+};
 template <int W>
-void tile_kernels_of(records_fn *r, tiles_fn *t)
+TileKernels tile_kernels_of()
 {
-    *r = nufft_records<W>;
-    *t = nufft_spread_tiles<W>;
+    return TileKernels{nufft_records<W>, nufft_tile_fill<W>, nufft_spread_tiles<W>};
 }
-void tile_kernels(int w, records_fn *r, tiles_fn *t)
+TileKernels tile_kernels(int w)
 {
     switch (w) {
-    case 4: return tile_kernels_of<4>(r, t);
-    case 5: return tile_kernels_of<5>(r, t);
-    case 6: return tile_kernels_of<6>(r, t);
-    case 7: return tile_kernels_of<7>(r, t);
-    case 8: return tile_kernels_of<8>(r, t);
-    case 9: return tile_kernels_of<9>(r, t);
-    case 10: return tile_kernels_of<10>(r, t);
-    case 11: return tile_kernels_of<11>(r, t);
-    case 12: return tile_kernels_of<12>(r, t);
-    case 13: return tile_kernels_of<13>(r, t);
-    case 14: return tile_kernels_of<14>(r, t);
-    case 15: return tile_kernels_of<15>(r, t);
-    default: return tile_kernels_of<16>(r, t);
+    case 4: return tile_kernels_of<4>();
+    case 5: return tile_kernels_of<5>();
+    case 6: return tile_kernels_of<6>();
+    case 7: return tile_kernels_of<7>();
+    case 8: return tile_kernels_of<8>();
+    case 9: return tile_kernels_of<9>();
+    case 10: return tile_kernels_of<10>();
+    case 11: return tile_kernels_of<11>();
+    case 12: return tile_kernels_of<12>();
+    case 13: return tile_kernels_of<13>();
+    case 14: return tile_kernels_of<14>();
+    case 15: return tile_kernels_of<15>();
+    default: return tile_kernels_of<16>();
     }
 }
 
@@ -907,8 +890,8 @@ int Nufft::reserve(int batch_hint)
     MDC_CHECK(grid.alloc((size_t)G_ * nf * nf * nf));
     MDC_CHECK(buf1.alloc((size_t)G_ * nf * nf * g.ncp));
     if (tiles) {
-        MDC_CHECK(bins.alloc((size_t)G_ * nb * nb * nb));
-        MDC_CHECK(order.alloc((size_t)G_ * maxlen));
+        MDC_CHECK(bins.alloc((size_t)G_ * 2 * nb * nb * nb));               // per tile: count, then end of its list
+        MDC_CHECK(order.alloc((size_t)G_ * maxlen * NT_MAX_TILES));         // the lists (CSR)
         MDC_CHECK(rec.alloc((size_t)G_ * maxlen * 4 * g.w));
         MDC_CHECK(cell.alloc((size_t)G_ * maxlen));
     } else if (sort) {
@@ -953,7 +936,7 @@ struct StageProfile {
         cudaEventRecord(e, st);
         ev.push_back(e);
         tag.push_back(t);
-        if (ev.size() > 4096) flush();
+        if (t == 0 && ev.size() > 150) flush();   // at a batch boundary (waits for the events: diagnostics only)
     }
     void flush()
     {
@@ -991,22 +974,21 @@ int Nufft::density(cudaStream_t st, const double *posd, const double iL[3], int6
         const unsigned B = (unsigned)std::min(G, total - e0);
         g_prof.mark(st, 0);
         if (tiles) {
-            // sort by 16^3 tile bin, kernel values once per particle, then one block per tile gathers: the grid is
-            // written exactly once (no clearing pass, no atomics)
-            const size_t nbins = (size_t)nb * nb * nb;
-            records_fn rk;
-            tiles_fn tk;
-            tile_kernels(g.w, &rk, &tk);
-            MDC_CUDA(cudaMemsetAsync(bins.p, 0, (size_t)B * nbins * sizeof(int), st));
-            nufft_tile_count<<<dim3(pblocks, B), 256, 0, st>>>(posd, N, d_sets, n_sets, e0, g.nf, nb, iL[0], iL[1], iL[2], bins.p);
-            nufft_scan_any<<<B, 128, 0, st>>>((int)nbins, bins.p);
-            nufft_tile_scatter<<<dim3(pblocks, B), 256, 0, st>>>(posd, N, d_sets, n_sets, e0, g.nf, nb, iL[0], iL[1], iL[2],
-                                                                bins.p, order.p, maxlen);
-            rk<<<dim3((unsigned)ceil_div(maxlen, 4), B), 128, 0, st>>>(posd, N, d_sets, n_sets, e0, order.p, maxlen, g, iL[0],
-                                                                       iL[1], iL[2], rec.p, cell.p);
+            // kernel values once per particle (+ one count per tile its support reaches), CSR lists tile -> particles,
+            // then one block per tile gathers: the grid is written exactly once (no clearing pass, no atomics)
+            const size_t ntiles = (size_t)2 * nb * nb * nb;
+            const int64_t pitch = maxlen * NT_MAX_TILES;
+            const TileKernels tk = tile_kernels(g.w);
+            MDC_CUDA(cudaMemsetAsync(bins.p, 0, (size_t)B * ntiles * sizeof(int), st));
+            tk.records<<<dim3((unsigned)ceil_div(maxlen, 4), B), 128, 0, st>>>(posd, N, d_sets, n_sets, e0, maxlen, g, nb, iL[0],
+                                                                               iL[1], iL[2], rec.p, cell.p, bins.p);
+            nufft_scan_any<<<B, 128, 0, st>>>((int)ntiles, bins.p);
+            tk.fill<<<dim3((unsigned)ceil_div(maxlen, 128), B), 128, 0, st>>>(d_sets, n_sets, e0, maxlen, g.nf, nb, cell.p, bins.p,
+                                                                              order.p, pitch);
             g_prof.mark(st, 1);
-            tk<<<dim3((unsigned)(nbins * (NT_T / NT_TX)), B), NT_THREADS, 0, st>>>(rec.p, cell.p, bins.p, maxlen, g.nf, nb, grid.p);
-            *launches += 5;
+            tk.tiles<<<dim3((unsigned)ntiles, B), NT_THREADS, 0, st>>>(rec.p, cell.p, bins.p, order.p, pitch, maxlen, g.nf, nb,
+                                                                       grid.p);
+            *launches += 4;
         } else {
         MDC_CUDA(cudaMemsetAsync(grid.p, 0, (size_t)B * nf * nf * nf * sizeof(double2), st));
         const int *ord = nullptr;
