@@ -415,59 +415,61 @@ __global__ void __launch_bounds__(128) nufft_scan_any(int n, int *__restrict__ c
 
 // Kernel values of every particle of an element (slot = index within its set): rec[slot] = {vx[W], vy[W],
 // (vz[W] * strength) as (re, im)[W]}, cell[slot] = first cell of the support per axis (may be negative: periodic); and
-// one count per tile the support reaches (tcount: the CSR row lengths of the tile -> particles lists).  One warp per particle.
+// one count per tile the support reaches (tcount: the CSR row lengths of the tile -> particles lists).
+// Half a warp per particle (lane t of the half evaluates offset t of the support: x, then y, then z), and two particles
+// per half in flight (independent chains of FP64 exponentials: the kernel is latency bound, next to the pair kernel
+// it has four warps per SM): 16 particles per block of 128 threads.
+constexpr int NR_PER_BLOCK = 16;
 template <int W>
 __global__ void __launch_bounds__(128)
 nufft_records(const double *__restrict__ posd, int64_t N, const int2 *__restrict__ sets, int n_sets, int e0,
               int64_t maxlen, NufftGeom g, int nb, double iLx, double iLy, double iLz, double *__restrict__ rec,
               int4 *__restrict__ cell, int *__restrict__ tcount)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, t = lane & 15;
     const int e = e0 + blockIdx.y, f = e / n_sets, s = e - f * n_sets;
     const int2 set = sets[s];
     const int len = set.y - set.x;
-    const int idx = blockIdx.x * 4 + warp;
-    if (idx >= len) return;
     const int nf = g.nf;
-    const int64_t slot = (int64_t)blockIdx.y * maxlen + idx;
-    const int64_t j = (int64_t)set.x + idx;
-    const double gx = fine_coord(posd[((int64_t)f * 3 + 0) * N + j], iLx, nf);
-    const double gy = fine_coord(posd[((int64_t)f * 3 + 1) * N + j], iLy, nf);
-    const double gz = fine_coord(posd[((int64_t)f * 3 + 2) * N + j], iLz, nf);
     const double hw = 0.5 * (double)W, ihw = 2.0 / (double)W, inf = 1.0 / (double)nf;
-    const int t = lane & 15;
-    double *R = rec + slot * (4 * W);
-    int l0a;
-    {
-        const double x = (lane < 16) ? gx : gy;
-        const double c = ceil(x - hw);
-        l0a = (int)c;
-        const double z = (c + (double)t - x) * ihw;
-        const double a = fmax(1.0 - z * z, 0.0);
-        if (t < W) R[(lane >> 4) * W + t] = exp(g.beta * (sqrt(a) - 1.0));
-    }
-    const int l0x = __shfl_sync(0xffffffffu, l0a, 0), l0y = __shfl_sync(0xffffffffu, l0a, 16);
-    const double c = ceil(gz - hw);
-    const int l0z = (int)c;
-    if (lane < 16 && t < W) {
-        const double z = (c + (double)t - gz) * ihw;
-        const double a = fmax(1.0 - z * z, 0.0);
-        const double vz = exp(g.beta * (sqrt(a) - 1.0));
-        // strength exp(2 pi i k0 (sx + sy + sz)) of the centred modes
-        double sn, cs;
-        sincospi(2.0 * (double)g.k0 * ((gx + gy + gz) * inf), &sn, &cs);
-        R[2 * W + 2 * t] = vz * cs;
-        R[2 * W + 2 * t + 1] = vz * sn;
-    }
-    const int4 l0 = make_int4(l0x, l0y, l0z, 0);
-    if (lane == 0) cell[slot] = l0;
-    // one lane per reached tile (at most 12)
-    int t0[3], nt[3];
-    tiles_reached<W>(l0, nf, t0, nt);
-    if (lane < nt[0] * nt[1] * nt[2]) {
-        const int ix = lane / (nt[1] * nt[2]), iy = (lane / nt[2]) % nt[1], iz = lane % nt[2];
-        const int tile = (((t0[0] + ix) % (2 * nb)) * nb + (t0[1] + iy) % nb) * nb + (t0[2] + iz) % nb;
-        atomicAdd(&tcount[(size_t)blockIdx.y * 2 * nb * nb * nb + tile], 1);
+    const double iL[3] = {iLx, iLy, iLz};
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+        const int idx = blockIdx.x * NR_PER_BLOCK + warp * 4 + rep * 2 + half;
+        if (idx >= len) continue;
+        const int64_t slot = (int64_t)blockIdx.y * maxlen + idx;
+        const int64_t j = (int64_t)set.x + idx;
+        double *R = rec + slot * (4 * W);
+        double gk[3], v[3];
+        int l0[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            gk[k] = fine_coord(posd[((int64_t)f * 3 + k) * N + j], iL[k], nf);
+            const double c = ceil(gk[k] - hw);
+            l0[k] = (int)c;
+            const double z = (c + (double)t - gk[k]) * ihw;
+            const double a = fmax(1.0 - z * z, 0.0);
+            v[k] = exp(g.beta * (sqrt(a) - 1.0));
+        }
+        if (t < W) {
+            // strength exp(2 pi i k0 (sx + sy + sz)) of the centred modes
+            double sn, cs;
+            sincospi(2.0 * (double)g.k0 * ((gk[0] + gk[1] + gk[2]) * inf), &sn, &cs);
+            R[t] = v[0];
+            R[W + t] = v[1];
+            R[2 * W + 2 * t] = v[2] * cs;
+            R[2 * W + 2 * t + 1] = v[2] * sn;
+        }
+        const int4 c4 = make_int4(l0[0], l0[1], l0[2], 0);
+        if (t == 0) cell[slot] = c4;
+        // one lane per reached tile (at most 12)
+        int t0[3], nt[3];
+        tiles_reached<W>(c4, nf, t0, nt);
+        if (t < nt[0] * nt[1] * nt[2]) {
+            const int ix = t / (nt[1] * nt[2]), iy = (t / nt[2]) % nt[1], iz = t % nt[2];
+            const int tile = (((t0[0] + ix) % (2 * nb)) * nb + (t0[1] + iy) % nb) * nb + (t0[2] + iz) % nb;
+            atomicAdd(&tcount[(size_t)blockIdx.y * 2 * nb * nb * nb + tile], 1);
+        }
     }
 }
 
@@ -980,7 +982,7 @@ int Nufft::density(cudaStream_t st, const double *posd, const double iL[3], int6
             const int64_t pitch = maxlen * NT_MAX_TILES;
             const TileKernels tk = tile_kernels(g.w);
             MDC_CUDA(cudaMemsetAsync(bins.p, 0, (size_t)B * ntiles * sizeof(int), st));
-            tk.records<<<dim3((unsigned)ceil_div(maxlen, 4), B), 128, 0, st>>>(posd, N, d_sets, n_sets, e0, maxlen, g, nb, iL[0],
+            tk.records<<<dim3((unsigned)ceil_div(maxlen, NR_PER_BLOCK), B), 128, 0, st>>>(posd, N, d_sets, n_sets, e0, maxlen, g, nb, iL[0],
                                                                                iL[1], iL[2], rec.p, cell.p, bins.p);
             nufft_scan_any<<<B, 128, 0, st>>>((int)ntiles, bins.p);
             tk.fill<<<dim3((unsigned)ceil_div(maxlen, 128), B), 128, 0, st>>>(d_sets, n_sets, e0, maxlen, g.nf, nb, cell.p, bins.p,
