@@ -680,7 +680,14 @@ nufft_fft_z(const double2 *__restrict__ grid, double2 *__restrict__ out, const d
     const int nf = g.nf;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double2 *line = tw + nf + warp * (nf + (nf >> 3));
+    // where the pruned read-out finds mode c of a transformed line (digit reversal + padding): once per block
+    int *ptab = reinterpret_cast<int *>(tw + nf + (NU_THREADS / 32) * (nf + (nf >> 3)));
     for (int i = threadIdx.x; i < nf; i += NU_THREADS) tw[i] = tw_g[i];
+    for (int c = threadIdx.x; c < g.n; c += NU_THREADS) {
+        int k = c - g.k0;
+        if (k < 0) k += nf;
+        ptab[c] = padded(fft_pos(k, g));
+    }
     __syncthreads();
     const int64_t lines = (int64_t)nf * nf;
     for (int64_t ln = (int64_t)blockIdx.x * (NU_THREADS / 32) + warp; ln < lines; ln += (int64_t)gridDim.x * (NU_THREADS / 32)) {
@@ -688,13 +695,7 @@ nufft_fft_z(const double2 *__restrict__ grid, double2 *__restrict__ out, const d
         fft_line<MDC_FFT_POW_Z != 0>(line, tw, g, lane, src);   // the first radix stage reads the line from global memory
         double2 *dst = out + ((size_t)blockIdx.y * lines + ln) * g.ncp;
         for (int c = lane; c < g.ncp; c += 32) {
-            double2 v = make_double2(0.0, 0.0);
-            if (c < g.n) {
-                int k = c - g.k0;
-                if (k < 0) k += nf;
-                v = line[padded(fft_pos(k, g))];
-            }
-            dst[c] = v;
+            dst[c] = c < g.n ? line[ptab[c]] : make_double2(0.0, 0.0);
         }
         __syncwarp();
     }
@@ -731,6 +732,12 @@ nufft_fft_s(const double2 *__restrict__ in, double2 *__restrict__ out, const dou
         if (!__syncthreads_or(keep)) return;
     }
     for (int i = threadIdx.x; i < nf; i += NU_THREADS) tw[i] = tw_g[i];
+    int *ptab = reinterpret_cast<int *>(tile + NU_TC * pitch);   // position of mode k in a transformed line
+    for (int k = threadIdx.x; k < n; k += NU_THREADS) {
+        int kk = k - g.k0;
+        if (kk < 0) kk += nf;
+        ptab[k] = padded(fft_pos(kk, g));
+    }
     const double2 *src = in + ((size_t)blockIdx.y * O + o) * nf * S;
     for (int e = threadIdx.x; e < nf * NU_TC; e += NU_THREADS) {
         const int l = e / NU_TC, ii = e - l * NU_TC;
@@ -744,9 +751,7 @@ nufft_fft_s(const double2 *__restrict__ in, double2 *__restrict__ out, const dou
         const int k = e / NU_TC, ii = e - k * NU_TC;
         const int64_t gi = i0 + ii;
         if (gi >= S) continue;
-        int kk = k - g.k0;
-        if (kk < 0) kk += nf;
-        const double2 v = tile[ii * pitch + padded(fft_pos(kk, g))];
+        const double2 v = tile[ii * pitch + ptab[k]];
         if (!FINAL) {
             out[(((size_t)blockIdx.y * O + o) * n + k) * S + gi] = v;
         } else {
@@ -860,8 +865,9 @@ int Nufft::init(const Ctx *ctx, int n_points, double eps_, int64_t max_set_len)
     nufft_twiddles<<<(nf + 255) / 256, 256>>>(nf, tw.p);
     MDC_CUDA(cudaGetLastError());
 
-    smem_z = sizeof(double2) * ((size_t)nf + (size_t)(NU_THREADS / 32) * (nf + nf / 8));
-    smem_s = sizeof(double2) * ((size_t)nf + (size_t)NU_TC * (nf + nf / 8 + 1));
+    const size_t ptab_bytes = ((size_t)n_points * sizeof(int) + 15) & ~(size_t)15;   // read-out position table
+    smem_z = sizeof(double2) * ((size_t)nf + (size_t)(NU_THREADS / 32) * (nf + nf / 8)) + ptab_bytes;
+    smem_s = sizeof(double2) * ((size_t)nf + (size_t)NU_TC * (nf + nf / 8 + 1)) + ptab_bytes;
     if (smem_z > ctx->smem_optin || smem_s > ctx->smem_optin)
         return fail(MDC_ERR_UNSUPPORTED, "nufft: fine grid line does not fit shared memory");
     // per-function attribute shared by every live plan (any fine grid): only ever the device maximum
