@@ -88,7 +88,9 @@ else:
                 self._sliced_trajectory = trajectory[frames]
             else:
                 start, stop, step = trajectory.check_slice_indices(start, stop, step)
-                self._sliced_trajectory = trajectory[start:stop:step]
+                # range(), not slice, semantics: check_slice_indices normalises a backward run that ends on frame 0 to
+                # stop = -1, which a Python slice would read as "the last frame"
+                self._sliced_trajectory = trajectory[np.arange(start, stop, step)]
             self.start, self.stop, self.step = start, stop, step
             self.n_frames = len(self._sliced_trajectory)
             self.frames = np.zeros(self.n_frames, dtype=int)

@@ -328,6 +328,25 @@ def test_rdf_and_sq_residue_groupings(tmp_path):
         np.testing.assert_allclose(s64.results.ssf, ws["ssf"], rtol=1e-10, atol=1e-12)
 
 
+def test_backward_and_strided_runs():
+    """run(step=-1) visits the frames of run() backwards (a sum: same counts), and a strided backward run that ends on
+    frame 0 visits exactly range(start, -1, step) (check_slice_indices normalises its stop to -1)."""
+    from mdcraft_b200.analysis.structure import RadialDistributionFunction
+
+    g = golden("rdf_self_c1.npz")
+    u = universe_from(g["pos"], g["dims"])
+    kw = dict(n_bins=int(g["n_bins"]), range_=tuple(g["range_"]), verbose=False, frame_block=2)
+    fwd = RadialDistributionFunction(u.atoms, **kw).run()
+    bwd = RadialDistributionFunction(u.atoms, **kw).run(step=-1)
+    np.testing.assert_array_equal(bwd.results.counts, fwd.results.counts)
+    np.testing.assert_array_equal(bwd.frames, fwd.frames[::-1])
+    n = len(u.trajectory)
+    part = RadialDistributionFunction(u.atoms, **kw).run(start=n - 1, step=-2)
+    np.testing.assert_array_equal(part.frames, np.arange(n - 1, -1, -2))
+    same = RadialDistributionFunction(u.atoms, **kw).run(frames=list(range(n - 1, -1, -2)))
+    np.testing.assert_array_equal(part.results.counts, same.results.counts)
+
+
 def test_verbose_logs_the_run(caplog):
     """verbose=True (the reference's default): a start and a finish line per run with device, frames per block, the plan's
     algorithm and frames/s (the reference logs its process farm the same way, base.py:378-384, 514-515); silent otherwise."""

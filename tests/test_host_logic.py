@@ -361,3 +361,54 @@ def test_generate_spherical_wavevectors_matches_the_reference():
     np.testing.assert_array_equal(k, g["w_qmax_norm"])
     with pytest.raises(ValueError):
         structure.generate_spherical_wavevectors(cell, n_points=(3, 4))
+
+
+class _CountingAnalysis:
+    """Host-only analysis on the in-repo AnalysisBase protocol (no kernels): records what run_together feeds it."""
+
+    def __new__(cls, universe, verbose=False):
+        from mdcraft_b200.analysis.base import SerialAnalysisBase
+
+        class Impl(SerialAnalysisBase):
+            def __init__(self, universe, verbose):
+                super().__init__(universe.trajectory, verbose)
+                self.universe = universe
+                self._device, self._frame_block = 0, 1
+
+            def _prepare(self):
+                self.seen, self.sums = [], []
+
+            def _single_frame(self):
+                self.seen.append(self._ts.frame)
+                self.sums.append(float(self.universe.atoms.positions.sum()))
+
+            def _conclude(self):
+                self.results.total = float(np.sum(self.sums))
+
+        return Impl(universe, verbose)
+
+
+def test_run_together_steps_different_trajectories_in_lockstep(caplog):
+    """run_together over analyses of DIFFERENT trajectories: frame i of each in the same turn, the bookkeeping of a
+    plain run(); unequal frame counts are refused; verbose=True logs a start and a finish line per analysis."""
+    import logging
+
+    from mdcraft_b200 import synthetic
+    from mdcraft_b200.analysis.base import run_together
+
+    rng = np.random.default_rng(3)
+    dims = np.array([5, 5, 5, 90, 90, 90], np.float32)
+    ua = synthetic.Universe(synthetic.MemoryTrajectory(rng.random((7, 11, 3)).astype(np.float32), dims))
+    ub = synthetic.Universe(synthetic.MemoryTrajectory(rng.random((7, 5, 3)).astype(np.float32), dims, dt=2.0))
+    a, a2, b = _CountingAnalysis(ua), _CountingAnalysis(ua), _CountingAnalysis(ub, verbose=True)
+    with caplog.at_level(logging.INFO, logger="mdcraft_b200.analysis"):
+        run_together([a, b, a2], start=1, step=2)
+    assert a.seen == a2.seen == b.seen == [1, 3, 5]
+    np.testing.assert_array_equal(a.frames, [1, 3, 5])
+    np.testing.assert_array_equal(b.times, [2.0, 6.0, 10.0])
+    solo = _CountingAnalysis(ub).run(start=1, step=2)
+    assert solo.results.total == b.results.total and solo.seen == b.seen
+    assert [r.getMessage().split(":")[0] for r in caplog.records] == ["Impl", "Impl"] and "3 frames" in caplog.records[0].getMessage()
+    uc = synthetic.Universe(synthetic.MemoryTrajectory(rng.random((6, 5, 3)).astype(np.float32), dims))
+    with pytest.raises(ValueError, match="same number of selected frames"):
+        run_together([a, _CountingAnalysis(uc)])
