@@ -608,7 +608,7 @@ constexpr int RF_FLUSH_ITEMS = 1024;         // 1024 * 1024 * 1024 pairs < 2^31
 struct TileCtx;
 struct FastShared {
     uint4 sj[RF_TJ];            // {ux, uy, uz, exclusion block of j}
-    unsigned queue[RF_QCAP];    // i_local | j_local << 16
+    unsigned queue[RF_QCAP];    // row j | lane << 10 | group << 15 | mask of the lane's four particles << 18
     unsigned qcount;
     unsigned pad[3];
     unsigned trash[RF_THREADS]; // per-thread dummy target of the branch-free histogram increment
@@ -696,10 +696,15 @@ struct TileCtx {            // everything the cold passes need (kept in shared m
     float thr;
 };
 
+// Undecided pairs are PARKED, not handled where they are found: a flagged lane only appends one word to the block's
+// queue — {row j (10 bits), lane (5), group (3), mask of its four particles (4)} — and the tile's resolve pass, in
+// which every lane works on an entry, does the rest: take the filter's increment back (extended histograms), evaluate
+// the reference's FP64 distance, count.  (In round 1 the flagged lane did the take-back and one queue slot per pair
+// on the spot: one active lane of 32 for ~60 instructions in 13 % of all rows, a tenth of the kernel's instructions.)
+
 // cold: the reference's exact FP64 result for a pair the filter could not decide
-__device__ __noinline__ void resolve_pair(const TileCtx *Tp, int il, int jl, const double *sT, unsigned *hist)
+__device__ __forceinline__ void resolve_pair(const TileCtx &T, int il, int jl, const double *sT, unsigned *hist)
 {
-    const TileCtx &T = *Tp;
     const int64_t ig = T.i0 + il, jg = T.j0 + jl;
     const float *ax = T.A.a + ((int64_t)T.f * 3) * T.A.na, *bx = T.A.b + ((int64_t)T.f * 3) * T.A.nb;
     const double r2 = exact_r2(ax[ig], ax[T.A.na + ig], ax[2 * T.A.na + ig], bx[jg], bx[T.A.nb + jg],
@@ -708,29 +713,51 @@ __device__ __noinline__ void resolve_pair(const TileCtx *Tp, int il, int jl, con
     if (k >= 0) atomicAdd(&hist[k], 1u);
 }
 
-// cold: the pairs (this thread's particle u, row jl) with bit u set in `mask` are undecided; park them
-__device__ __noinline__ void park_row(const TileCtx *Tp, unsigned *queue, unsigned *qcount, int jl, unsigned mask,
-                                      const double *sT, unsigned *hist, int group, unsigned long long v01 = 0ull,
-                                      unsigned long long v23 = 0ull, bool uncount = false)
+// cold: one queue entry.  copies = bin 0 of histogram copy 0 (copies are `stride` words apart); hist = the calling
+// thread's own copy (any copy may receive the exact count; the take-back must hit the copy the flagged lane used).
+__device__ __noinline__ void resolve_entry(const FastShared *S, unsigned entry, bool uncount, const double *sT, unsigned *copies,
+                                           int stride, unsigned *hist)
 {
+    const TileCtx &T = *reinterpret_cast<const TileCtx *>(S->ctx);
+    const int jl = (int)(entry & 1023u), lane = (int)((entry >> 10) & 31u), group = (int)((entry >> 15) & 7u);
+    const unsigned mask = (entry >> 18) & 15u;
     for (int u = 0; u < RF_IPT; ++u) {
         if (!((mask >> u) & 1u)) continue;
+        const int il = group * (32 * RF_IPT) + u * 32 + lane;
         if (uncount) {
-            // extended histograms: the hot loop has already counted this pair in the filter's bin (this thread, this
-            // copy, program order); take that back before the exact result is added
-            const unsigned long long vv = u < 2 ? v01 : v23;
-            const float v = __uint_as_float((unsigned)((u & 1) ? (vv >> 32) : (vv & 0xffffffffull)));
+            // the filter's bin of this pair, recomputed with the filter's own arithmetic (bit-identical: same operations
+            // in the same order as filter_v2 in the hot loop)
+            const int64_t ig = min(T.i0 + il, T.A.na - 1);
+            const uint32_t *ua = T.A.ua + ((int64_t)T.f * 3) * T.A.na;
+            const uint4 pj = S->sj[jl];
+            const float v = T.ff.cubic ? filter_v<true>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], T.ff)
+                                       : filter_v<false>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], T.ff);
             const int k = (int)(__float_as_uint(__fadd_rn(v, 12582912.f)) - 0x4B400000u);
             // rint(v) beyond B (or below -1): |v_ref - v| < 0.5 puts the pair outside the window whatever the rounding;
             // it sits in a word that is never read back and needs no FP64 pass (40 % of the flagged pairs at L/2)
-            if (k > Tp->A.n_bins || k < -1) continue;
-            atomicSub(&hist[k], 1u);
+            if (k > T.A.n_bins || k < -1) continue;
+            atomicSub(&copies[(lane & (T.A.n_copies - 1)) * stride + k], 1u);
         }
-        const int il = rf_il_of(group, u);
-        const unsigned slot = atomicAdd(qcount, 1u);
-        if (slot < RF_QCAP) queue[slot] = (unsigned)il | ((unsigned)jl << 16);
-        else resolve_pair(Tp, il, jl, sT, hist);   // queue full (pathological inputs): resolve in line
+        resolve_pair(T, il, jl, sT, hist);
     }
+}
+
+// cold: this lane's pairs (row jl, particles with a bit in `mask`) are undecided: one word into the queue
+__device__ __noinline__ void park_row(FastShared *S, int jl, unsigned mask, int group, bool uncount)
+{
+    const unsigned entry = (unsigned)jl | ((threadIdx.x & 31u) << 10) | ((unsigned)group << 15) | (mask << 18);
+    const unsigned slot = atomicAdd(&S->qcount, 1u);
+    if (slot < RF_QCAP) {
+        S->queue[slot] = entry;
+        return;
+    }
+    // queue full (pathological inputs, e.g. lattices whose spacings sit on bin edges): resolve in line
+    const TileCtx &T = *reinterpret_cast<const TileCtx *>(S->ctx);
+    double *sT = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(S) + ((sizeof(FastShared) + 15) & ~size_t(15)));
+    unsigned *sh = reinterpret_cast<unsigned *>(sT + (T.A.n_bins + 1));
+    const int stride = T.A.ext_k > 0 ? T.A.ext_k : T.A.n_bins;
+    unsigned *copies = sh + T.A.ext_off;
+    resolve_entry(S, entry, uncount, sT, copies, stride, copies + (threadIdx.x & (unsigned)(T.A.n_copies - 1)) * stride);
 }
 
 // The hot loop after v is known: a pair is binned if v is clear of every bin edge, otherwise reported undecided.
@@ -1046,8 +1073,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
 #pragma unroll
             for (int u = 0; u < RF_IPT; ++u)
                 if (adf[u] > thr && ok[u]) und |= 1u << u;
-            if (EXT) park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, group, v01, v23, true);
-            else park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, group);
+            if (und) park_row(S, j, und, group, EXT);
         }
     };
     // half a row: the pairs of particles (2 H, 2 H + 1) only (extended histograms, tiles without ok flags)
@@ -1061,7 +1087,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
             unsigned und = 0;
             if (adf[0] > thr) und |= 1u << a;
             if (adf[1] > thr) und |= 1u << b;
-            park_row(Tp, S->queue, &S->qcount, j, und, sT, hist, group, v, v, true);   // park_row picks v01 / v23 by u
+            if (und) park_row(S, j, und, group, true);
         }
     };
     auto walk = [&](unsigned m, int c, auto &&body) {
@@ -1296,10 +1322,8 @@ rdf_pairs_fast(RdfArgs A)
         // resolve the undecided pairs of this tile with the reference's FP64 arithmetic
         __syncthreads();
         const unsigned nq = min(S->qcount, (unsigned)RF_QCAP);
-        for (unsigned e = threadIdx.x; e < nq; e += RF_THREADS) {
-            const unsigned q = S->queue[e];
-            resolve_pair(Tp, (int)(q & 0xffffu), (int)(q >> 16), sT, hist);
-        }
+        for (unsigned e = threadIdx.x; e < nq; e += RF_THREADS)
+            resolve_entry(S, S->queue[e], ext, sT, sh + A.ext_off, HS, hist);
         __syncthreads();
         if (threadIdx.x == 0) S->qcount = 0u;
 
