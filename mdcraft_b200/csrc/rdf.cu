@@ -149,16 +149,17 @@ __device__ __forceinline__ void tri_wrap(float &xf, float &yf, float &zf, const 
     zf = (float)z;
 }
 
-// raw f32 (F, N, 3) -> soa f32 (F, 3, N); also fix u32 (F, 3, N) = frac(x / L) * 2^32 and the per-frame
-// max |coordinate| (float bits, atomicMax) that bounds the float32 subtraction error of the reference.
+// raw f32 (F, N, 3) -> soa f32 (F, 3, N); also fix u32 (F, 3, N) = frac(x / L) * 2^32 and, per frame, the largest
+// coordinate and the largest NEGATED coordinate (float bits, atomicMax; both clamped at 0): their sum bounds the range
+// of the coordinates, hence every |a - b| that the reference subtracts in float32.  extent = {max x, max -x} x (F).
 // Triclinic frames: soa holds the coordinates moved into the primary cell (what the reference's distance routine
 // works on); fix is not used by the kernel that takes such frames.
 __global__ void rdf_prep(const float *__restrict__ raw, int64_t N, int64_t total, const FrameBox *__restrict__ boxes,
-                         const FrameTri *__restrict__ tri, float *__restrict__ soa, uint32_t *__restrict__ fix,
-                         unsigned *__restrict__ absmax)
+                         const FrameTri *__restrict__ tri, int F, float *__restrict__ soa, uint32_t *__restrict__ fix,
+                         unsigned *__restrict__ extent)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    float m = 0.f;
+    float mp = 0.f, mn = 0.f;
     int64_t f = 0;
     if (i < total) {
         f = i / N;
@@ -174,42 +175,55 @@ __global__ void rdf_prep(const float *__restrict__ raw, int64_t N, int64_t total
             double s = fb.pbc[k] ? (double)x / fb.box[k] : 0.0;
             s -= floor(s);
             fix[(f * 3 + k) * N + j] = (uint32_t)(unsigned long long)(s * 4294967296.0 + 0.5);
-            m = fmaxf(m, fabsf(x));
+            mp = fmaxf(mp, x);
+            mn = fmaxf(mn, -x);
         }
     }
-    // one atomic per warp (lanes of a warp may straddle two frames: fall back to per-lane atomics then)
+    // one pair of atomics per warp (lanes of a warp may straddle two frames: fall back to per-lane atomics then)
     const int64_t f0 = __shfl_sync(0xffffffffu, f, 0);
     const bool same = __all_sync(0xffffffffu, (i >= total) || f == f0);
     if (same) {
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&absmax[f0], __float_as_uint(m));
-    } else if (i < total && m > 0.f) {
-        atomicMax(&absmax[f], __float_as_uint(m));
+        for (int o = 16; o > 0; o >>= 1) {
+            mp = fmaxf(mp, __shfl_xor_sync(0xffffffffu, mp, o));
+            mn = fmaxf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (mp > 0.f) atomicMax(&extent[f0], __float_as_uint(mp));
+            if (mn > 0.f) atomicMax(&extent[F + f0], __float_as_uint(mn));
+        }
+    } else if (i < total) {
+        if (mp > 0.f) atomicMax(&extent[f], __float_as_uint(mp));
+        if (mn > 0.f) atomicMax(&extent[F + f], __float_as_uint(mn));
     }
 }
 
-// One thread per frame: turns the box, the plan's range and the coordinate bound into the filter's
-// constants.  The margin bounds |v_filter - v_reference| ("g(r) filter error budget"):
-//   reference vs true separation: float32 subtraction (<= 2^-24 * 2M per axis) and the (box * inv_box)
-//     factor (<= 2^-24 * 2M per axis), M = max |coordinate|;
-//   fixed point vs true separation: 2^-32 * L per axis;
-//   FP32 evaluation (I2F, squares, sum, MUFU.SQRT, FMA): <= 3.5e-7 relative + one ulp of v.
-__global__ void rdf_frame_params(const FrameBox *__restrict__ boxes, const unsigned *__restrict__ absmax_a,
-                                 const unsigned *__restrict__ absmax_b, int F, int n_bins, double r0, double r1,
+// One thread per frame: turns the box, the plan's range and the coordinate range into the filter's constants.  The
+// margin bounds |v_filter - v_reference|:
+//   reference vs true separation, per axis: float32 subtraction of two coordinates (<= 2^-24 |a - b|) and the
+//     (box * inv_box) factor of its minimum image (inverse box stored as float32: <= 2^-24 |a - b|); |a - b| <= R, the
+//     range of the coordinates of both groups (R = L for wrapped positions): 2^-23 R.  A pair within that of half a box
+//     may take the other image in the reference; its |separation| then differs by <= 2^-24 L <= 2^-23 R as well;
+//   fixed point vs true separation: 2^-32 L per axis (2^-31 L is used);
+//   FP32 evaluation (I2F, squares, sum, MUFU.SQRT, FMA): <= 3.5e-7 relative + one ulp of v (4.7e-7 is used);
+//   all of it times 1.25.
+__global__ void rdf_frame_params(const FrameBox *__restrict__ boxes, const unsigned *__restrict__ extent_a,
+                                 const unsigned *__restrict__ extent_b, int Fa, int F, int n_bins, double r0, double r1,
                                  FrameFast *__restrict__ out)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     const FrameBox fb = boxes[f];
     const double S = (double)n_bins / (r1 - r0);
-    const double M = fmax((double)__uint_as_float(absmax_a[f]), (double)__uint_as_float(absmax_b[f]));
+    const double hi = fmax((double)__uint_as_float(extent_a[f]), (double)__uint_as_float(extent_b[f]));
+    const double lo = fmax((double)__uint_as_float(extent_a[Fa + f]), (double)__uint_as_float(extent_b[Fa + f]));
+    const double R = hi + lo;   // >= max - min over both groups and all three axes
     const double Lmax = fmax(fb.box[0], fmax(fb.box[1], fb.box[2]));
     FrameFast p;
     p.ax = (float)(fb.box[0] * S / 4294967296.0);
     p.ay = (float)(fb.box[1] * S / 4294967296.0);
     p.az = (float)(fb.box[2] * S / 4294967296.0);
     p.c0 = (float)(-r0 * S - 0.5);
-    const double e_abs = 1.7320508 * (2.0 * M / 4194304.0 + Lmax / 2147483648.0);
+    const double e_abs = 1.7320508 * (R / 8388608.0 + Lmax / 2147483648.0);
     const double vmax = (double)n_bins + 2.0 + fabs(r0 * S);
     const double margin = 1.25 * (S * e_abs + 4.7e-7 * vmax) + 1e-6;
     p.thr = (float)fmax(0.5 - margin, -1.0);
@@ -1360,7 +1374,7 @@ struct mdc_rdf_plan {
     DevBuf<unsigned long long> counts, ticket;
     DevBuf<float> raw_a[2], raw_b[2], soa_a[2], soa_b[2];
     DevBuf<uint32_t> fix_a[2], fix_b[2];
-    DevBuf<unsigned> absmax[2];        // (2, F): group a, group b
+    DevBuf<unsigned> absmax[2];        // (2 groups, {max x, max -x}, fblk): coordinate extents per frame
     DevBuf<FrameBox> boxes[2];
     DevBuf<FrameTri> tri[2];
     DevBuf<FrameFast> fast[2];
@@ -1427,7 +1441,7 @@ int rdf_configure(mdc_rdf_plan *p, int n_frames_hint)
             MDC_CHECK(p->soa_b[i].alloc((size_t)fblk * p->nb * 3));
             MDC_CHECK(p->fix_b[i].alloc((size_t)fblk * p->nb * 3));
         }
-        MDC_CHECK(p->absmax[i].alloc((size_t)2 * fblk));
+        MDC_CHECK(p->absmax[i].alloc((size_t)4 * fblk));
         MDC_CHECK(p->boxes[i].alloc(fblk));
         MDC_CHECK(p->tri[i].alloc(fblk));
         MDC_CHECK(p->fast[i].alloc(fblk));
@@ -1619,19 +1633,19 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         }
         MDC_CUDA(cudaMemcpyAsync(p->boxes[slot].p, hb.data() + f0, F * sizeof(FrameBox), cudaMemcpyHostToDevice, sc));
         MDC_CUDA(cudaMemcpyAsync(p->tri[slot].p, ht.data() + f0, F * sizeof(FrameTri), cudaMemcpyHostToDevice, sc));
-        MDC_CUDA(cudaMemsetAsync(p->absmax[slot].p, 0, 2 * (size_t)p->fblk * sizeof(unsigned), sc));
+        MDC_CUDA(cudaMemsetAsync(p->absmax[slot].p, 0, 4 * (size_t)p->fblk * sizeof(unsigned), sc));
         rdf_prep<<<(unsigned)ceil_div((int64_t)F * p->na, 256), 256, 0, sc>>>(
-            ra, p->na, (int64_t)F * p->na, p->boxes[slot].p, p->tri[slot].p, p->soa_a[slot].p, p->fix_a[slot].p,
+            ra, p->na, (int64_t)F * p->na, p->boxes[slot].p, p->tri[slot].p, p->fblk, p->soa_a[slot].p, p->fix_a[slot].p,
             p->absmax[slot].p);
         ++launches;
         if (rb) {
             rdf_prep<<<(unsigned)ceil_div((int64_t)F * p->nb, 256), 256, 0, sc>>>(
-                rb, p->nb, (int64_t)F * p->nb, p->boxes[slot].p, p->tri[slot].p, p->soa_b[slot].p, p->fix_b[slot].p,
-                p->absmax[slot].p + p->fblk);
+                rb, p->nb, (int64_t)F * p->nb, p->boxes[slot].p, p->tri[slot].p, p->fblk, p->soa_b[slot].p, p->fix_b[slot].p,
+                p->absmax[slot].p + 2 * p->fblk);
             ++launches;
         }
         rdf_frame_params<<<(unsigned)ceil_div(F, 64), 64, 0, sc>>>(
-            p->boxes[slot].p, p->absmax[slot].p, p->absmax[slot].p + (rb ? p->fblk : 0), F, p->n_bins, p->r0, p->r1,
+            p->boxes[slot].p, p->absmax[slot].p, p->absmax[slot].p + (rb ? 2 * p->fblk : 0), p->fblk, F, p->n_bins, p->r0, p->r1,
             p->fast[slot].p);
         ++launches;
         // the filter kernel needs an orthorhombic cell, three periodic axes and a bin coordinate below 2^22 in every frame

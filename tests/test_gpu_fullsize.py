@@ -68,6 +68,32 @@ def test_c2_rdf_full_size(ctx):
                                   _rdf_counts(ctx, sub, None, box, 200, rng, exact=True))
 
 
+@pytest.mark.parametrize("n_bins,lo,hi", [(200, 0.0, 0.5), (1000, 0.0, 0.45), (64, 0.11, 0.3), (2000, 0.0, 0.5)])
+def test_rdf_filter_margin_with_unwrapped_coordinates(ctx, n_bins, lo, hi):
+    """The FP32 filter's margin is derived from the RANGE of the coordinates (float32 subtraction error of the
+    reference, rdf_frame_params): coordinates well outside the box (unwrapped, negative) widen it.  The filtered kernel
+    must agree with the all-FP64 kernel on every count, and a slab with the CPU oracle, for narrow and wide bins."""
+    from oracle import oracle
+
+    rng = np.random.default_rng(n_bins)
+    n, L = 40_000, 30.0
+    box = np.array([L, L * 1.1, L * 0.93, 90, 90, 90], np.float32)
+    pos = ((rng.random((n, 3)) * 2.6 - 0.7) * box[:3]).astype(np.float32)
+    window = (lo * L * 0.93, hi * L * 0.93)
+    fast = _rdf_counts(ctx, pos, None, box, n_bins, window, exclusion=(1, 1))
+    exact = _rdf_counts(ctx, pos, None, box, n_bins, window, exclusion=(1, 1), exact=True)
+    np.testing.assert_array_equal(fast, exact)
+    slab = _rdf_counts(ctx, pos[:256], pos, box, n_bins, window)
+    np.testing.assert_array_equal(slab, oracle.radial_histogram(pos[:256], pos, n_bins, window, box))
+    # wrapped positions of the same configuration: a smaller range, a tighter margin, other counts near the edges
+    wrapped = np.mod(pos.astype(np.float64), box[:3].astype(np.float64)).astype(np.float32)
+    wrapped[wrapped >= box[:3]] = 0.0
+    np.testing.assert_array_equal(_rdf_counts(ctx, wrapped, None, box, n_bins, window, exclusion=(1, 1)),
+                                  _rdf_counts(ctx, wrapped, None, box, n_bins, window, exclusion=(1, 1), exact=True))
+    slab = _rdf_counts(ctx, wrapped[:256], wrapped, box, n_bins, window)
+    np.testing.assert_array_equal(slab, oracle.radial_histogram(wrapped[:256], wrapped, n_bins, window, box))
+
+
 def test_c4_binary_electrolyte_partials(ctx):
     """C4: 100k cations + 100k anions: ++, +-, -- g(r) and the partial S(q) sum rule."""
     from mdcraft_b200 import _capi
