@@ -891,7 +891,8 @@ int Nufft::reserve(int batch_hint)
 {
     if (G > 0) return MDC_OK;
     const size_t nf = g.nf;
-    const size_t per = sizeof(double2) * (nf * nf * nf + nf * nf * g.ncp);
+    size_t per = sizeof(double2) * (nf * nf * nf + nf * nf * g.ncp);
+    if (tiles) per += (size_t)maxlen * (4 * g.w * sizeof(double) + sizeof(int4) + NT_MAX_TILES * sizeof(int));   // records, lists
     const size_t budget = (size_t)2 << 30;
     int G_ = (int)std::max<size_t>(1, std::min<size_t>(budget / per, 32));
     G_ = std::max(1, std::min(G_, batch_hint));
