@@ -24,6 +24,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include <vector>
 
 using namespace mdc;
@@ -223,7 +224,11 @@ __global__ void rdf_frame_params(const FrameBox *__restrict__ boxes, const unsig
     p.ay = (float)(fb.box[1] * S / 4294967296.0);
     p.az = (float)(fb.box[2] * S / 4294967296.0);
     p.c0 = (float)(-r0 * S - 0.5);
-    const double e_abs = 1.7320508 * (R / 8388608.0 + Lmax / 2147483648.0);
+    // + the relative-coordinate rows of the filter (rows_rel): the row's difference to the box centre is rounded to FP32
+    // on its own (<= 2^-26 L: 32-bit integers below 2^31), the particle's too (<= 2^-28 L: boxes below 2^-3 L); the
+    // rounding of their FP32 difference is relative (<= 1.3 x 2^-24 of the wrapped difference at the seam) and part of
+    // the 4.7e-7 below, like the conversion it replaces
+    const double e_abs = 1.7320508 * (R / 8388608.0 + Lmax / 2147483648.0 + Lmax * (1.0 / 67108864.0 + 1.0 / 268435456.0));
     const double vmax = (double)n_bins + 2.0 + fabs(r0 * S);
     const double margin = 1.25 * (S * e_abs + 4.7e-7 * vmax) + 1e-6;
     p.thr = (float)fmax(0.5 - margin, -1.0);
@@ -264,6 +269,13 @@ struct RdfArgs {
     // Every bin coordinate the filter can produce in these frames, in the window or not, then has a word of its
     // own, so the hot loop increments without a range test (bins outside [0, B) are never read back).
     int ext_k, ext_off;
+    // filter kernel: histogram layout in shared memory, in words: bin k of copy c sits at k * hist_ks + c * hist_cs.
+    // Copies one after the other (hist_ks = 1, hist_cs = words per copy, 8 copies chosen by lane & 7), or -- extended
+    // histograms that fit -- 32 INTERLEAVED copies, one per lane (hist_ks = 32, hist_cs = 1): every lane then owns a
+    // bank and the increments of a warp never conflict (tools/atoms_probe.cu: 1.0 instead of 3.1 cycles per ATOMS).
+    int hist_ks, hist_cs;
+    int qcap;                     // filter kernel: capacity of the queue of undecided rows (words, after the histograms)
+    int rel;                      // filter kernel, sorted frames: relative-coordinate rows allowed (MDC_RDF_REL=0 turns them off)
 };
 
 // ---- spatial sort (Hilbert order of an nc^3 cell grid, nc = 2^bits <= 32) ----------------------------------------
@@ -529,14 +541,14 @@ __device__ __forceinline__ bool decode_item(const RdfArgs &A, int64_t item, int 
 }
 
 __device__ __forceinline__ void flush_hist(unsigned *sh, int B, int n_copies, unsigned long long weight,
-                                           unsigned long long *counts, bool clear, int stride = 0)
+                                           unsigned long long *counts, bool clear, int stride = 0, int ks = 1)
 {
-    if (stride == 0) stride = B;   // sh points at bin 0 of copy 0; copies are `stride` words apart
+    if (stride == 0) stride = B;   // sh points at bin 0 of copy 0; copies are `stride` words apart, bins `ks` words
     for (int i = threadIdx.x; i < B; i += blockDim.x) {
         unsigned long long s = 0;
         for (int c = 0; c < n_copies; ++c) {
-            s += sh[c * stride + i];
-            if (clear) sh[c * stride + i] = 0u;
+            s += sh[c * stride + i * ks];
+            if (clear) sh[c * stride + i * ks] = 0u;
         }
         if (s) atomicAdd(&counts[i], s * weight);
     }
@@ -615,16 +627,19 @@ constexpr int RF_THREADS = 256;
 constexpr int RF_IPT = 4;
 constexpr int RF_TI = RF_THREADS * RF_IPT;   // 1024
 constexpr int RF_TJ = 1024;
-constexpr int RF_QCAP = 4096;                // undecided pairs per tile before falling back to in-line resolution
+constexpr int RF_QCAP = 4096;                // undecided rows per tile pair before falling back to in-line resolution
+constexpr int RF_QCAP_L32 = 1024;            // ... when the 32 interleaved histogram copies need the room
 constexpr int RF_FLUSH_ITEMS = 1024;         // 1024 * 1024 * 1024 pairs < 2^31
 // the filter rounds with the magic number 1.5 * 2^23 = 12582912.0f = 0x4B400000 (bin_or_flag)
 
 struct TileCtx;
 struct FastShared {
     uint4 sj[RF_TJ];            // {ux, uy, uz, exclusion block of j}
-    unsigned queue[RF_QCAP];    // row j | lane << 10 | group << 15 | mask of the lane's four particles << 18
+    // undecided rows: row j | lane << 10 | group << 15 | mask of the lane's four particles << 18 | relative form << 22;
+    // RdfArgs::qcap words behind the histograms
+    unsigned *queue;
     unsigned qcount;
-    unsigned pad[3];
+    unsigned qcap;
     unsigned trash[RF_THREADS]; // per-thread dummy target of the branch-free histogram increment
     unsigned char ctx[384];     // TileCtx of the tile in flight (cold passes read it from here)
     // sorted frames only: bounding boxes {lo x, lo y, lo z, -, hi x, hi y, hi z, -} (32-bit box fractions) of the 128
@@ -638,6 +653,9 @@ struct FastShared {
     // reloads that group's particles): uneven culling no longer leaves warps idle at the end of a tile pair.
     int next_chunk[RF_THREADS / 32];
     int pad2[8 - (RF_THREADS / 32) % 8];
+    // sorted frames, relative-coordinate rows (rows_rel): per warp, the 32 rows of the chunk in flight as FP32
+    // differences to the centre of the group's box {x, y, z, -}
+    float4 rel[RF_THREADS / 32][32];
 };
 
 // local index (within the tile) of particle u of this thread: a warp holds 128 consecutive particles, which in a
@@ -680,6 +698,28 @@ __device__ __forceinline__ unsigned rows_in_reach(const FastShared *S, const uin
     return __ballot_sync(0xffffffffu, in);
 }
 
+// sorted frames, relative-coordinate rows: every lane takes its row of the chunk relative to the centre of the group's
+// box (ch = {centre, half extent}) with the integer wrap, leaves the three differences as FP32 in the warp's scratch
+// and reports whether the row lies at the periodic SEAM of the box: if |u_j - centre| + half extent reaches 2^31 on
+// some axis, the particles of the box do not all see the same image of j and the differences need the period back
+// (rel_wrap).  For every other row  (u_j - centre) - (u_i - centre)  IS the wrapped difference u_j - u_i, as plain
+// integers.
+__device__ __forceinline__ unsigned rows_rel(FastShared *S, const uint4 *ch, int c, int nj)
+{
+    const int lane = (int)(threadIdx.x & 31u);
+    const uint4 pj = S->sj[min(c + lane, nj - 1)];
+    const uint4 ctr = ch[0], hf = ch[1];
+    const int dx = (int)(pj.x - ctr.x), dy = (int)(pj.y - ctr.y), dz = (int)(pj.z - ctr.z);
+    // half extents are below 2^29 here (rel_ok), so the sums cannot overflow
+    const bool seam = (unsigned)abs(dx) + hf.x > 0x7fffffffu || (unsigned)abs(dy) + hf.y > 0x7fffffffu ||
+                      (unsigned)abs(dz) + hf.z > 0x7fffffffu;
+    __syncwarp();   // the previous chunk's rows have been read by every lane
+    S->rel[threadIdx.x >> 5][lane] = make_float4((float)dx, (float)dy, (float)dz, 0.f);
+    const unsigned m = __ballot_sync(0xffffffffu, seam);   // also orders the scratch writes before the reads below
+    __syncwarp();
+    return m;
+}
+
 // The filter's FP32 bin coordinate of one pair: v = bin coordinate - 0.5 (so that rint(v) is the bin).
 template <bool CUBIC>
 __device__ __forceinline__ float filter_v(uint32_t ujx, uint32_t ujy, uint32_t ujz, uint32_t uix, uint32_t uiy,
@@ -698,6 +738,40 @@ __device__ __forceinline__ float filter_v(uint32_t ujx, uint32_t ujy, uint32_t u
         const float t2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
         return d + ff.c0;
+    }
+}
+
+// Relative-coordinate form of the filter (sorted frames, rows clear of the periodic seam of the group's box, see
+// rows_rel): both particles are taken relative to the centre of the group's box with the integer wrap, converted to
+// FP32 ONCE, and the pair's difference is a floating-point subtraction -- packed, two pairs per instruction, in the
+// hot loop (filter_v2_rel); this is the same arithmetic in scalar form, operation for operation, for the resolve pass.
+// Rows AT the seam get the period back in floating point (rel_wrap: three more packed operations per axis, exact);
+// applied to a row clear of the seam it changes nothing, so the resolve pass need not know which form a pair took.
+// difference of two FP32 coordinates relative to the box centre, brought back to the nearest image: at most one period
+// (2^32) off, and then an exact correction; rows clear of the seam are left as they are (q = 0)
+__device__ __forceinline__ float rel_wrap(float e)
+{
+    const float q = __fadd_rn(__fmaf_rn(e, 2.3283064365386963e-10f, 12582912.f), -12582912.f);   // rint(e / 2^32)
+    return __fmaf_rn(q, -4294967296.f, e);
+}
+
+template <bool CUBIC>
+__device__ __forceinline__ float filter_v_rel(uint32_t ujx, uint32_t ujy, uint32_t ujz, uint32_t uix, uint32_t uiy,
+                                              uint32_t uiz, const uint4 &ctr, const FrameFast &ff)
+{
+    const float tx = rel_wrap(__fadd_rn((float)(int)(ujx - ctr.x), -(float)(int)(uix - ctr.x)));
+    const float ty = rel_wrap(__fadd_rn((float)(int)(ujy - ctr.y), -(float)(int)(uiy - ctr.y)));
+    const float tz = rel_wrap(__fadd_rn((float)(int)(ujz - ctr.z), -(float)(int)(uiz - ctr.z)));
+    float d;
+    if (CUBIC) {
+        const float t2 = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, __fmul_rn(tx, tx)));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
+        return __fmaf_rn(d, ff.ax, ff.c0);
+    } else {
+        const float ex = __fmul_rn(tx, ff.ax), ey = __fmul_rn(ty, ff.ay), ez = __fmul_rn(tz, ff.az);
+        const float t2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
+        return __fadd_rn(d, ff.c0);
     }
 }
 
@@ -724,17 +798,18 @@ __device__ __forceinline__ void resolve_pair(const TileCtx &T, int il, int jl, c
     const double r2 = exact_r2(ax[ig], ax[T.A.na + ig], ax[2 * T.A.na + ig], bx[jg], bx[T.A.nb + jg],
                                bx[2 * T.A.nb + jg], T.fb);
     const int k = exact_bin(r2, T.A, sT);
-    if (k >= 0) atomicAdd(&hist[k], 1u);
+    if (k >= 0) atomicAdd(&hist[k * T.A.hist_ks], 1u);
 }
 
-// cold: one queue entry.  copies = bin 0 of histogram copy 0 (copies are `stride` words apart); hist = the calling
-// thread's own copy (any copy may receive the exact count; the take-back must hit the copy the flagged lane used).
+// cold: one queue entry.  copies = bin 0 of histogram copy 0 (layout: RdfArgs::hist_ks / hist_cs); hist = bin 0 of the
+// calling thread's own copy (any copy may receive the exact count; the take-back must hit the copy the flagged lane used).
 __device__ __noinline__ void resolve_entry(const FastShared *S, unsigned entry, bool uncount, const double *sT, unsigned *copies,
-                                           int stride, unsigned *hist)
+                                           unsigned *hist)
 {
     const TileCtx &T = *reinterpret_cast<const TileCtx *>(S->ctx);
     const int jl = (int)(entry & 1023u), lane = (int)((entry >> 10) & 31u), group = (int)((entry >> 15) & 7u);
     const unsigned mask = (entry >> 18) & 15u;
+    const bool rel = (entry >> 22) & 1u;   // the filter's bin came from the relative-coordinate form
     for (int u = 0; u < RF_IPT; ++u) {
         if (!((mask >> u) & 1u)) continue;
         const int il = group * (32 * RF_IPT) + u * 32 + lane;
@@ -744,24 +819,31 @@ __device__ __noinline__ void resolve_entry(const FastShared *S, unsigned entry, 
             const int64_t ig = min(T.i0 + il, T.A.na - 1);
             const uint32_t *ua = T.A.ua + ((int64_t)T.f * 3) * T.A.na;
             const uint4 pj = S->sj[jl];
-            const float v = T.ff.cubic ? filter_v<true>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], T.ff)
-                                       : filter_v<false>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], T.ff);
+            float v;
+            if (rel) {
+                const uint4 ctr = S->ibox[group][2];
+                v = T.ff.cubic ? filter_v_rel<true>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], ctr, T.ff)
+                               : filter_v_rel<false>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], ctr, T.ff);
+            } else {
+                v = T.ff.cubic ? filter_v<true>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], T.ff)
+                               : filter_v<false>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], T.ff);
+            }
             const int k = (int)(__float_as_uint(__fadd_rn(v, 12582912.f)) - 0x4B400000u);
             // rint(v) beyond B (or below -1): |v_ref - v| < 0.5 puts the pair outside the window whatever the rounding;
             // it sits in a word that is never read back and needs no FP64 pass (40 % of the flagged pairs at L/2)
             if (k > T.A.n_bins || k < -1) continue;
-            atomicSub(&copies[(lane & (T.A.n_copies - 1)) * stride + k], 1u);
+            atomicSub(&copies[(lane & (T.A.n_copies - 1)) * T.A.hist_cs + k * T.A.hist_ks], 1u);
         }
         resolve_pair(T, il, jl, sT, hist);
     }
 }
 
 // cold: this lane's pairs (row jl, particles with a bit in `mask`) are undecided: one word into the queue
-__device__ __noinline__ void park_row(FastShared *S, int jl, unsigned mask, int group, bool uncount)
+__device__ __noinline__ void park_row(FastShared *S, int jl, unsigned mask, int group, bool uncount, unsigned rel = 0u)
 {
-    const unsigned entry = (unsigned)jl | ((threadIdx.x & 31u) << 10) | ((unsigned)group << 15) | (mask << 18);
+    const unsigned entry = (unsigned)jl | ((threadIdx.x & 31u) << 10) | ((unsigned)group << 15) | (mask << 18) | (rel << 22);
     const unsigned slot = atomicAdd(&S->qcount, 1u);
-    if (slot < RF_QCAP) {
+    if (slot < S->qcap) {
         S->queue[slot] = entry;
         return;
     }
@@ -769,15 +851,17 @@ __device__ __noinline__ void park_row(FastShared *S, int jl, unsigned mask, int 
     const TileCtx &T = *reinterpret_cast<const TileCtx *>(S->ctx);
     double *sT = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(S) + ((sizeof(FastShared) + 15) & ~size_t(15)));
     unsigned *sh = reinterpret_cast<unsigned *>(sT + (T.A.n_bins + 1));
-    const int stride = T.A.ext_k > 0 ? T.A.ext_k : T.A.n_bins;
-    unsigned *copies = sh + T.A.ext_off;
-    resolve_entry(S, entry, uncount, sT, copies, stride, copies + (threadIdx.x & (unsigned)(T.A.n_copies - 1)) * stride);
+    unsigned *copies = sh + T.A.ext_off * T.A.hist_ks;
+    resolve_entry(S, entry, uncount, sT, copies, copies + (threadIdx.x & (unsigned)(T.A.n_copies - 1)) * T.A.hist_cs);
 }
 
 // The hot loop after v is known: a pair is binned if v is clear of every bin edge, otherwise reported undecided.
 // Written in PTX to keep it branch free (bin_or_flag4 / bin_count4 below):
 //   w = v + MAGIC;  k = bits(w) - bits(MAGIC) = rint(v);  undecided = |v - (w - MAGIC)| > thr
 
+#ifndef MDC_RF_UNROLL2
+#define MDC_RF_UNROLL2 1   // pairs of rows per loop iteration (relative-coordinate form)
+#endif
 #ifndef MDC_RF_UNROLL
 #define MDC_RF_UNROLL 2   // rows of j per loop iteration
 #endif
@@ -791,15 +875,12 @@ __device__ __forceinline__ unsigned long long pk2(float lo, float hi)
 
 // filter_v for two particles (u, u + 1) against the same j: identical operations in identical order, issued as
 // packed FP32 (mul / fma .f32x2), so the values are bit-identical to the scalar form
+// the filter's v for two pairs from their packed coordinate differences (in 2^-32 box fractions)
 template <bool CUBIC>
-__device__ __forceinline__ unsigned long long filter_v2(uint32_t ujx, uint32_t ujy, uint32_t ujz, uint32_t ax0,
-                                                        uint32_t ay0, uint32_t az0, uint32_t ax1, uint32_t ay1,
-                                                        uint32_t az1, unsigned long long fax, unsigned long long fay,
-                                                        unsigned long long faz, unsigned long long fc0)
+__device__ __forceinline__ unsigned long long filter_v2_tail(unsigned long long tx, unsigned long long ty, unsigned long long tz,
+                                                             unsigned long long fax, unsigned long long fay,
+                                                             unsigned long long faz, unsigned long long fc0)
 {
-    unsigned long long tx = pk2((float)(int)(ujx - ax0), (float)(int)(ujx - ax1));
-    unsigned long long ty = pk2((float)(int)(ujy - ay0), (float)(int)(ujy - ay1));
-    unsigned long long tz = pk2((float)(int)(ujz - az0), (float)(int)(ujz - az1));
     unsigned long long t2, v;
     float a, b, da, db;
     if (!CUBIC) {
@@ -821,6 +902,49 @@ __device__ __forceinline__ unsigned long long filter_v2(uint32_t ujx, uint32_t u
         asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(d), "l"(fc0));
     }
     return v;
+}
+
+template <bool CUBIC>
+__device__ __forceinline__ unsigned long long filter_v2(uint32_t ujx, uint32_t ujy, uint32_t ujz, uint32_t ax0,
+                                                        uint32_t ay0, uint32_t az0, uint32_t ax1, uint32_t ay1,
+                                                        uint32_t az1, unsigned long long fax, unsigned long long fay,
+                                                        unsigned long long faz, unsigned long long fc0)
+{
+    const unsigned long long tx = pk2((float)(int)(ujx - ax0), (float)(int)(ujx - ax1));
+    const unsigned long long ty = pk2((float)(int)(ujy - ay0), (float)(int)(ujy - ay1));
+    const unsigned long long tz = pk2((float)(int)(ujz - az0), (float)(int)(ujz - az1));
+    return filter_v2_tail<CUBIC>(tx, ty, tz, fax, fay, faz, fc0);
+}
+
+// filter_v_rel for two particles: r = the row's FP32 coordinates relative to the centre of the group's box, n = MINUS the
+// two particles' (packed): three packed additions replace six integer subtractions and six conversions.  WRAP: rows at
+// the seam of the box (rel_wrap, packed).
+template <bool CUBIC, bool WRAP>
+__device__ __forceinline__ unsigned long long filter_v2_rel(float rx, float ry, float rz, unsigned long long nx,
+                                                            unsigned long long ny, unsigned long long nz,
+                                                            unsigned long long fax, unsigned long long fay,
+                                                            unsigned long long faz, unsigned long long fc0)
+{
+    unsigned long long tx, ty, tz;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(tx) : "l"(pk2(rx, rx)), "l"(nx));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ty) : "l"(pk2(ry, ry)), "l"(ny));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(tz) : "l"(pk2(rz, rz)), "l"(nz));
+    if (WRAP) {
+        const unsigned long long inv = pk2(2.3283064365386963e-10f, 2.3283064365386963e-10f);
+        const unsigned long long mg = pk2(12582912.f, 12582912.f), nmg = pk2(-12582912.f, -12582912.f);
+        const unsigned long long per = pk2(-4294967296.f, -4294967296.f);
+        unsigned long long q;
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q) : "l"(tx), "l"(inv), "l"(mg));
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(q) : "l"(nmg));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(tx) : "l"(q), "l"(per));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q) : "l"(ty), "l"(inv), "l"(mg));
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(q) : "l"(nmg));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ty) : "l"(q), "l"(per));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q) : "l"(tz), "l"(inv), "l"(mg));
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(q) : "l"(nmg));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(tz) : "l"(q), "l"(per));
+    }
+    return filter_v2_tail<CUBIC>(tx, ty, tz, fax, fay, faz, fc0);
 }
 
 // bin_or_flag for the four pairs of one row (two packed v's): the round-to-bin chain as six packed instructions,
@@ -955,7 +1079,11 @@ __device__ __forceinline__ unsigned bin_or_flag4(unsigned long long v01, unsigne
 // the increment needs no range test and no dummy word: hist[k] += 1 (IMAD + ATOMS per pair) and ONE predicate that
 // says whether any pair is undecided (FSETP chain).  The cold path takes the increment of an undecided pair back.
 // hbase = shared address of bin 0 of this thread's copy - 4 * bits(MAGIC): bits(w) = bits(MAGIC) + k for any sign of k.
-template <bool HAS_OK>
+// LEA: the word address as a funnel shift + add (LEA.HI, ALU pipe) instead of a multiply-add (IMAD, the FMA pipe that
+// the packed arithmetic of the relative-coordinate rows already fills); the integer rows keep IMAD (their ALU pipe
+// carries the conversions).  SH: log2 of the BYTES between consecutive bins of one copy: 2 (copies one after the other)
+// or 7 (32 interleaved copies, one per lane = per bank: RdfArgs::hist_ks).
+template <bool HAS_OK, bool LEA, int SH>
 __device__ __forceinline__ unsigned bin_count4(unsigned long long v01, unsigned long long v23, unsigned long long magic,
                                                unsigned long long nmagic, unsigned long long neg1, float thr,
                                                unsigned hbase, unsigned trash_addr, unsigned one, const unsigned (&ok)[4],
@@ -983,25 +1111,36 @@ __device__ __forceinline__ unsigned bin_count4(unsigned long long v01, unsigned 
     "abs.f32 %3, %3;\n\t"                                         \
     "abs.f32 %4, %4;\n\t"
 #define RX_OUT "=r"(any), "=f"(adf[0]), "=f"(adf[1]), "=f"(adf[2]), "=f"(adf[3])
-#define RX_IN "l"(v01), "l"(v23), "f"(thr), "r"(hbase), "r"(trash_addr), "r"(one), "l"(magic), "l"(nmagic), "l"(neg1)
+#define RX_IN "l"(v01), "l"(v23), "f"(thr), "r"(hbase), "r"(trash_addr), "r"(one), "l"(magic), "l"(nmagic), "l"(neg1), "n"(1 << SH), "n"(SH)
+#define RX_MAD "mad.lo.u32 ad, k, %14, %8;\n\t"
+#define RX_LEA "shf.l.wrap.b32 ad, 0, k, %15;\n\t add.u32 ad, ad, %8;\n\t"
     if (HAS_OK) {
         asm volatile(RX_HEAD
-            "mov.b32 k, w0;\n\t setp.ne.u32 r, %14, 0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t selp.u32 ad, ad, %9, r;\n\t"
+            "mov.b32 k, w0;\n\t setp.ne.u32 r, %16, 0;\n\t" RX_MAD "selp.u32 ad, ad, %9, r;\n\t"
             "red.shared.add.u32 [ad], %10;\n\t setp.gt.and.f32 q, %1, %7, r;\n\t"
-            "mov.b32 k, w1;\n\t setp.ne.u32 r, %15, 0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t selp.u32 ad, ad, %9, r;\n\t"
+            "mov.b32 k, w1;\n\t setp.ne.u32 r, %17, 0;\n\t" RX_MAD "selp.u32 ad, ad, %9, r;\n\t"
             "red.shared.add.u32 [ad], %10;\n\t setp.gt.and.f32 r, %2, %7, r;\n\t or.pred q, q, r;\n\t"
-            "mov.b32 k, w2;\n\t setp.ne.u32 r, %16, 0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t selp.u32 ad, ad, %9, r;\n\t"
+            "mov.b32 k, w2;\n\t setp.ne.u32 r, %18, 0;\n\t" RX_MAD "selp.u32 ad, ad, %9, r;\n\t"
             "red.shared.add.u32 [ad], %10;\n\t setp.gt.and.f32 r, %3, %7, r;\n\t or.pred q, q, r;\n\t"
-            "mov.b32 k, w3;\n\t setp.ne.u32 r, %17, 0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t selp.u32 ad, ad, %9, r;\n\t"
+            "mov.b32 k, w3;\n\t setp.ne.u32 r, %19, 0;\n\t" RX_MAD "selp.u32 ad, ad, %9, r;\n\t"
             "red.shared.add.u32 [ad], %10;\n\t setp.gt.and.f32 r, %4, %7, r;\n\t or.pred q, q, r;\n\t"
             "selp.u32 %0, 1, 0, q;\n\t}"
             : RX_OUT : RX_IN, "r"(ok[0]), "r"(ok[1]), "r"(ok[2]), "r"(ok[3]) : "memory");
+    } else if (LEA) {
+        asm volatile(RX_HEAD
+            "mov.b32 k, w0;\n\t" RX_LEA "red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w1;\n\t" RX_LEA "red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w2;\n\t" RX_LEA "red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w3;\n\t" RX_LEA "red.shared.add.u32 [ad], 1;\n\t"
+            "setp.gt.f32 q, %1, %7;\n\t setp.gt.or.f32 q, %2, %7, q;\n\t setp.gt.or.f32 q, %3, %7, q;\n\t"
+            "setp.gt.or.f32 q, %4, %7, q;\n\t selp.u32 %0, 1, 0, q;\n\t}"
+            : RX_OUT : RX_IN : "memory");
     } else {
         asm volatile(RX_HEAD
-            "mov.b32 k, w0;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], 1;\n\t"
-            "mov.b32 k, w1;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], 1;\n\t"
-            "mov.b32 k, w2;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], 1;\n\t"
-            "mov.b32 k, w3;\n\t mad.lo.u32 ad, k, 4, %8;\n\t red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w0;\n\t" RX_MAD "red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w1;\n\t" RX_MAD "red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w2;\n\t" RX_MAD "red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w3;\n\t" RX_MAD "red.shared.add.u32 [ad], 1;\n\t"
             "setp.gt.f32 q, %1, %7;\n\t setp.gt.or.f32 q, %2, %7, q;\n\t setp.gt.or.f32 q, %3, %7, q;\n\t"
             "setp.gt.or.f32 q, %4, %7, q;\n\t selp.u32 %0, 1, 0, q;\n\t}"
             : RX_OUT : RX_IN : "memory");
@@ -1009,38 +1148,52 @@ __device__ __forceinline__ unsigned bin_count4(unsigned long long v01, unsigned 
 #undef RX_HEAD
 #undef RX_OUT
 #undef RX_IN
+#undef RX_MAD
+#undef RX_LEA
     return any;
 }
 
 // bin_count4 for half a row: the two pairs of one packed v (extended histograms, no ok flags)
+template <bool LEA, int SH>
 __device__ __forceinline__ unsigned bin_count2(unsigned long long v, unsigned long long magic, unsigned long long nmagic,
                                                unsigned long long neg1, float thr, unsigned hbase, float (&adf)[2])
 {
     unsigned any;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred q;\n\t"
-        ".reg .b64 W, KF, DF;\n\t"
-        ".reg .f32 w0, w1;\n\t"
-        ".reg .u32 k, ad;\n\t"
-        "add.rn.f32x2 W, %3, %6;\n\t"
-        "add.rn.f32x2 KF, W, %7;\n\t"
-        "fma.rn.f32x2 DF, KF, %8, %3;\n\t"
-        "mov.b64 {w0, w1}, W;\n\t"
-        "mov.b64 {%1, %2}, DF;\n\t"
-        "abs.f32 %1, %1;\n\t"
-        "abs.f32 %2, %2;\n\t"
-        "mov.b32 k, w0;\n\t mad.lo.u32 ad, k, 4, %5;\n\t red.shared.add.u32 [ad], 1;\n\t"
-        "mov.b32 k, w1;\n\t mad.lo.u32 ad, k, 4, %5;\n\t red.shared.add.u32 [ad], 1;\n\t"
-        "setp.gt.f32 q, %1, %4;\n\t setp.gt.or.f32 q, %2, %4, q;\n\t"
-        "selp.u32 %0, 1, 0, q;\n\t}"
-        : "=r"(any), "=f"(adf[0]), "=f"(adf[1])
-        : "l"(v), "f"(thr), "r"(hbase), "l"(magic), "l"(nmagic), "l"(neg1)
-        : "memory");
+#define RY_HEAD                                                   \
+    "{\n\t"                                                       \
+    ".reg .pred q;\n\t"                                           \
+    ".reg .b64 W, KF, DF;\n\t"                                    \
+    ".reg .f32 w0, w1;\n\t"                                       \
+    ".reg .u32 k, ad;\n\t"                                        \
+    "add.rn.f32x2 W, %3, %6;\n\t"                                 \
+    "add.rn.f32x2 KF, W, %7;\n\t"                                 \
+    "fma.rn.f32x2 DF, KF, %8, %3;\n\t"                            \
+    "mov.b64 {w0, w1}, W;\n\t"                                    \
+    "mov.b64 {%1, %2}, DF;\n\t"                                   \
+    "abs.f32 %1, %1;\n\t"                                         \
+    "abs.f32 %2, %2;\n\t"
+#define RY_FOOT                                                   \
+    "setp.gt.f32 q, %1, %4;\n\t setp.gt.or.f32 q, %2, %4, q;\n\t" \
+    "selp.u32 %0, 1, 0, q;\n\t}"
+#define RY_OPS "=r"(any), "=f"(adf[0]), "=f"(adf[1]) : "l"(v), "f"(thr), "r"(hbase), "l"(magic), "l"(nmagic), "l"(neg1), "n"(1 << SH), "n"(SH) : "memory"
+    if (LEA) {
+        asm volatile(RY_HEAD
+            "mov.b32 k, w0;\n\t shf.l.wrap.b32 ad, 0, k, %10;\n\t add.u32 ad, ad, %5;\n\t red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w1;\n\t shf.l.wrap.b32 ad, 0, k, %10;\n\t add.u32 ad, ad, %5;\n\t red.shared.add.u32 [ad], 1;\n\t"
+            RY_FOOT : RY_OPS);
+    } else {
+        asm volatile(RY_HEAD
+            "mov.b32 k, w0;\n\t mad.lo.u32 ad, k, %9, %5;\n\t red.shared.add.u32 [ad], 1;\n\t"
+            "mov.b32 k, w1;\n\t mad.lo.u32 ad, k, %9, %5;\n\t red.shared.add.u32 [ad], 1;\n\t"
+            RY_FOOT : RY_OPS);
+    }
+#undef RY_HEAD
+#undef RY_FOOT
+#undef RY_OPS
     return any;
 }
 
-template <bool CHECK, bool CUBIC, bool EXCL, bool R0ZERO, bool CULL, bool EXT>
+template <bool CHECK, bool CUBIC, bool EXCL, bool R0ZERO, bool CULL, bool EXT, bool L32>
 __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, uint32_t (&ux)[RF_IPT],
                                                 uint32_t (&uy)[RF_IPT], uint32_t (&uz)[RF_IPT],
                                                 int (&bi)[RF_IPT], const FrameFast &ff, float thr, unsigned B,
@@ -1059,8 +1212,12 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     const unsigned long long neg1 = pk2(-1.f, -1.f);
     // R0ZERO: bits(w) is used as it is; bits(MAGIC) = 0x4B400000 moves into the limit and the base address
     const unsigned blim = R0ZERO ? B + 0x4B400000u : B;
-    const unsigned hbase = (R0ZERO || EXT) ? hist_addr - 4u * 0x4B400000u : hist_addr;
+    // bytes between consecutive bins of this thread's copy: 4, or 128 with the 32 interleaved copies (L32, EXT only)
+    constexpr int SH = L32 ? 7 : 2;
+    static_assert(!L32 || EXT, "the interleaved copies come with the extended histograms");
+    const unsigned hbase = (R0ZERO || EXT) ? hist_addr - (1u << SH) * 0x4B400000u : hist_addr;
     constexpr int RF_UNROLL = MDC_RF_UNROLL;
+    constexpr int RF_UNROLL2 = MDC_RF_UNROLL2;
     int group = (int)(threadIdx.x >> 5);   // whose particles ux / uy / uz hold: the warp's own, or a group it helps out
     auto row = [&](int j) {
         const uint4 pj = S->sj[j];
@@ -1079,7 +1236,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
         const unsigned long long v23 = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[2], uy[2], uz[2], ux[3], uy[3], uz[3], fax,
                                                         fay, faz, fc0);
         float adf[4];
-        const unsigned any = EXT ? bin_count4<HAS_OK>(v01, v23, magic, nmagic, neg1, thr, hbase, trash_addr, one, ok, adf)
+        const unsigned any = EXT ? bin_count4<HAS_OK, false, SH>(v01, v23, magic, nmagic, neg1, thr, hbase, trash_addr, one, ok, adf)
                                  : bin_or_flag4<HAS_OK, R0ZERO, CULL>(v01, v23, magic, nmagic, neg1, thr, blim, hbase,
                                                                       trash_addr, one, ok, adf);
         if (any) {
@@ -1097,13 +1254,106 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
         const unsigned long long v = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[a], uy[a], uz[a], ux[b], uy[b], uz[b], fax, fay,
                                                       faz, fc0);
         float adf[2];
-        if (bin_count2(v, magic, nmagic, neg1, thr, hbase, adf)) {
+        if (bin_count2<false, SH>(v, magic, nmagic, neg1, thr, hbase, adf)) {
             unsigned und = 0;
             if (adf[0] > thr) und |= 1u << a;
             if (adf[1] > thr) und |= 1u << b;
             if (und) park_row(S, j, und, group, true);
         }
     };
+    // the same in the relative-coordinate form (rows_rel).  The group's particles then live in ux / uy / uz as MINUS their
+    // FP32 differences to the centre of the group's box (the same twelve registers: the integer form is not used for
+    // such a group), packed (0, 1) and (2, 3); groups whose box is wider than an eighth of the cell keep the integers.
+    constexpr bool REL = CULL && EXT && !HAS_OK;
+    bool rel_ok = false;
+    // shared address of the warp's scratch row 0, minus 16 c for the chunk in flight: a value the compiler must keep
+    // (it otherwise rebuilds the address from the thread index for every row)
+    unsigned rel_at = 0;
+    auto rel_row = [&](int j) {
+        float4 r;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(rel_at + 16u * (unsigned)j));
+        return r;
+    };
+    auto load_rel = [&](const uint4 *ib) {
+        if (!REL) return;
+        const uint4 ctr = ib[2], hf = ib[3];
+        rel_ok = Tp->A.rel && (hf.x | hf.y | hf.z) < (1u << 29);   // warp-uniform
+        if (!rel_ok) return;
+#pragma unroll
+        for (int u = 0; u < RF_IPT; ++u) {
+            ux[u] = __float_as_uint(-(float)(int)(ux[u] - ctr.x));
+            uy[u] = __float_as_uint(-(float)(int)(uy[u] - ctr.y));
+            uz[u] = __float_as_uint(-(float)(int)(uz[u] - ctr.z));
+        }
+    };
+    auto nrel = [&](const uint32_t (&w)[RF_IPT], int H) { return pk2(__uint_as_float(w[2 * H]), __uint_as_float(w[2 * H + 1])); };
+    // One row, branch free: the four v's, the increments, whether any pair is undecided (adf: |v - rint(v)| per pair).
+    auto vs_rel = [&](const float4 &r, auto wrap, unsigned long long (&v)[2]) {
+        constexpr bool W = decltype(wrap)::value;
+        v[0] = filter_v2_rel<CUBIC, W>(r.x, r.y, r.z, nrel(ux, 0), nrel(uy, 0), nrel(uz, 0), fax, fay, faz, fc0);
+        v[1] = filter_v2_rel<CUBIC, W>(r.x, r.y, r.z, nrel(ux, 1), nrel(uy, 1), nrel(uz, 1), fax, fay, faz, fc0);
+    };
+    auto count_rel = [&](const unsigned long long (&v)[2], float (&adf)[4]) -> unsigned {
+        const unsigned ok[RF_IPT] = {1u, 1u, 1u, 1u};
+        return bin_count4<false, true, SH>(v[0], v[1], magic, nmagic, neg1, thr, hbase, trash_addr, one, ok, adf);
+    };
+    auto park_rel = [&](int j, const float (&adf)[4]) {   // cold
+        unsigned und = 0;
+#pragma unroll
+        for (int u = 0; u < RF_IPT; ++u)
+            if (adf[u] > thr) und |= 1u << u;
+        if (und) park_row(S, j, und, group, true, 1u);
+    };
+    auto row_rel = [&](int j, int c, auto wrap) {
+        float adf[4];
+        unsigned long long v[2];
+        vs_rel(rel_row(j), wrap, v);
+        if (count_rel(v, adf)) park_rel(j, adf);
+    };
+    // Two rows at a time with ONE branch to the cold path: the branch around the parking code ends a scheduling region,
+    // and one row alone is only two dependent chains of packed operations (fixed-latency waits were the top stall).
+    // Both rows are loaded and all four v's formed before the first increment (the increments are volatile and keep
+    // their order, the arithmetic before them is free to interleave).
+    auto rows2_rel = [&](int j0, int j1, auto wrap) {
+        float adf0[4], adf1[4];
+        unsigned long long v0[2], v1[2];
+        const float4 r0 = rel_row(j0), r1 = rel_row(j1);
+        vs_rel(r0, wrap, v0);
+        vs_rel(r1, wrap, v1);
+        const unsigned a0 = count_rel(v0, adf0), a1 = count_rel(v1, adf1);
+        if (a0 | a1) {
+            if (a0) park_rel(j0, adf0);
+            if (a1) park_rel(j1, adf1);
+        }
+    };
+    auto half_row_rel = [&](int j, int c, int H, auto wrap) {
+        constexpr bool W = decltype(wrap)::value;
+        const float4 r = rel_row(j);
+        const unsigned long long v = filter_v2_rel<CUBIC, W>(r.x, r.y, r.z, nrel(ux, H), nrel(uy, H), nrel(uz, H), fax, fay, faz, fc0);
+        float adf[2];
+        if (bin_count2<true, SH>(v, magic, nmagic, neg1, thr, hbase, adf)) {
+            unsigned und = 0;
+            if (adf[0] > thr) und |= 1u << (2 * H);
+            if (adf[1] > thr) und |= 1u << (2 * H + 1);
+            if (und) park_row(S, j, und, group, true, 1u);
+        }
+    };
+    // the rows of a mask two at a time
+    auto walk2_rel = [&](unsigned m, int c, auto wrap) {
+        while (m) {
+            const int j0 = c + __ffs((int)m) - 1;
+            m &= m - 1u;
+            if (!m) {
+                row_rel(j0, c, wrap);
+                break;
+            }
+            const int j1 = c + __ffs((int)m) - 1;
+            m &= m - 1u;
+            rows2_rel(j0, j1, wrap);
+        }
+    };
+    using Yes = std::true_type;
+    using No = std::false_type;
     auto walk = [&](unsigned m, int c, auto &&body) {
         while (m) {
             const int j = c + __ffs((int)m) - 1;
@@ -1134,6 +1384,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                 }
             }
             const uint4 *ib = S->ibox[g];
+            load_rel(ib);
             for (;;) {
                 int c = 0;
                 if ((threadIdx.x & 31u) == 0u) c = atomicAdd(&S->next_chunk[g], 1);
@@ -1145,6 +1396,29 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                     // ... and half row by half row: the group's first and last 64 particles have boxes of their own
                     const unsigned ma = rows_in_reach(S, ib + 4, c, nj), mb = rows_in_reach(S, ib + 6, c, nj);
                     const unsigned both = ma & mb;
+                    if (REL && rel_ok) {
+                        // relative-coordinate form: 3 packed additions instead of 6 subtractions + 6 conversions per two
+                        // pairs; rows at the seam of the group's box pay 9 more packed operations for the period
+                        const unsigned seam = rows_rel(S, ib + 2, c, nj);
+                        asm volatile("mov.u32 %0, %1;" : "=r"(rel_at) : "r"((unsigned)__cvta_generic_to_shared(S->rel[threadIdx.x >> 5]) - 16u * (unsigned)c));
+                        if (seam == 0u && __popc(both) >= 29) {
+                            const int je = min(nj, c + 32);
+                            int j = c;
+#pragma unroll RF_UNROLL2
+                            for (; j + 1 < je; j += 2) rows2_rel(j, j + 1, No());
+                            if (j < je) row_rel(j, c, No());
+                            continue;
+                        }
+                        walk2_rel(both & ~seam, c, No());
+                        walk(ma & ~mb & ~seam, c, [&](int j) { half_row_rel(j, c, 0, No()); });
+                        walk(mb & ~ma & ~seam, c, [&](int j) { half_row_rel(j, c, 1, No()); });
+                        if (seam & (ma | mb)) {
+                            walk2_rel(both & seam, c, Yes());
+                            walk(ma & ~mb & seam, c, [&](int j) { half_row_rel(j, c, 0, Yes()); });
+                            walk(mb & ~ma & seam, c, [&](int j) { half_row_rel(j, c, 1, Yes()); });
+                        }
+                        continue;
+                    }
                     if (__popc(both) >= 29) {   // (nearly) all rows in full: the plain loop has less overhead per row
                         const int je = min(nj, c + 32);
 #pragma unroll RF_UNROLL
@@ -1173,7 +1447,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
 }
 
 #ifndef MDC_RF_BLOCKS
-#define MDC_RF_BLOCKS 4   // resident blocks per SM the register budget is sized for (64 registers per thread)
+#define MDC_RF_BLOCKS 3   // resident blocks per SM the register budget is sized for (80 registers per thread)
 #endif
 __global__ void __launch_bounds__(RF_THREADS, MDC_RF_BLOCKS)
 rdf_pairs_fast(RdfArgs A)
@@ -1186,12 +1460,16 @@ rdf_pairs_fast(RdfArgs A)
     for (int i = threadIdx.x; i <= B; i += RF_THREADS) sT[i] = A.T[i];
     const int HS = A.ext_k > 0 ? A.ext_k : B;   // words per histogram copy
     for (int i = threadIdx.x; i < HS * A.n_copies; i += RF_THREADS) sh[i] = 0u;
-    if (threadIdx.x == 0) S->qcount = 0u;
+    if (threadIdx.x == 0) {
+        S->qcount = 0u;
+        S->qcap = (unsigned)A.qcap;
+        S->queue = sh + HS * A.n_copies;
+    }
     // Histogram copies are private to LANE groups, not to warps: bank conflicts and same-address serialisation only
     // arise among the 32 lanes of one ATOMS instruction, and neighbouring lanes (neighbouring particles in a sorted
     // frame, hence similar distances to the same j) are the ones that would collide.
-    unsigned *hist = sh + (threadIdx.x & (unsigned)(A.n_copies - 1)) * HS + A.ext_off;   // bin 0 of this lane's copy
-    const bool ext = A.ext_k > 0;
+    unsigned *hist = sh + (threadIdx.x & (unsigned)(A.n_copies - 1)) * A.hist_cs + A.ext_off * A.hist_ks;   // bin 0 of this lane's copy
+    const bool ext = A.ext_k > 0, l32 = A.hist_ks == 32;
     const unsigned long long weight = A.sym ? 2ull : 1ull;
     const int64_t total = A.items_per_frame * A.F;
     int since_flush = 0;
@@ -1317,12 +1595,13 @@ rdf_pairs_fast(RdfArgs A)
             // the self pairs only, which a symmetric sweep (j > i) never evaluates
             excl = oa != nullptr ? !(A.sym && A.ex0 == 1 && A.ex1 == 1) : (ilo <= jhi && jlo <= ihi);
         }
-#define RF_CALL2(C, Q, E, Z, U, X) tile_pairs_fast<C, Q, E, Z, U, X>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist)
+#define RF_CALL2(C, Q, E, Z, U, X, L) tile_pairs_fast<C, Q, E, Z, U, X, L>(Tp, S, nj, ux, uy, uz, bi, ff, thr, (unsigned)B, A.na, i0, j0, diag, sT, hist)
 #define RF_CALL(C, Q, E)                                                                                              \
     do {                                                                                                              \
-        if (ext) { if (cull) RF_CALL2(C, Q, E, true, true, true); else RF_CALL2(C, Q, E, true, false, true); }         \
-        else if (cull) { if (r0zero) RF_CALL2(C, Q, E, true, true, false); else RF_CALL2(C, Q, E, false, true, false); } \
-        else { if (r0zero) RF_CALL2(C, Q, E, true, false, false); else RF_CALL2(C, Q, E, false, false, false); }        \
+        if (ext && l32) { if (cull) RF_CALL2(C, Q, E, true, true, true, true); else RF_CALL2(C, Q, E, true, false, true, true); } \
+        else if (ext) { if (cull) RF_CALL2(C, Q, E, true, true, true, false); else RF_CALL2(C, Q, E, true, false, true, false); } \
+        else if (cull) { if (r0zero) RF_CALL2(C, Q, E, true, true, false, false); else RF_CALL2(C, Q, E, false, true, false, false); } \
+        else { if (r0zero) RF_CALL2(C, Q, E, true, false, false, false); else RF_CALL2(C, Q, E, false, false, false, false); }        \
     } while (0)
         if (check) {
             if (ff.cubic) { if (excl) RF_CALL(true, true, true); else RF_CALL(true, true, false); }
@@ -1335,19 +1614,19 @@ rdf_pairs_fast(RdfArgs A)
 #undef RF_CALL2
         // resolve the undecided pairs of this tile with the reference's FP64 arithmetic
         __syncthreads();
-        const unsigned nq = min(S->qcount, (unsigned)RF_QCAP);
+        const unsigned nq = min(S->qcount, S->qcap);
         for (unsigned e = threadIdx.x; e < nq; e += RF_THREADS)
-            resolve_entry(S, S->queue[e], ext, sT, sh + A.ext_off, HS, hist);
+            resolve_entry(S, S->queue[e], ext, sT, sh + A.ext_off * A.hist_ks, hist);
         __syncthreads();
         if (threadIdx.x == 0) S->qcount = 0u;
 
         if (++since_flush >= RF_FLUSH_ITEMS) {
-            flush_hist(sh + A.ext_off, B, A.n_copies, weight, A.counts, true, HS);
+            flush_hist(sh + A.ext_off * A.hist_ks, B, A.n_copies, weight, A.counts, true, A.hist_cs, A.hist_ks);
             since_flush = 0;
         }
     }
     __syncthreads();
-    flush_hist(sh + A.ext_off, B, A.n_copies, weight, A.counts, false, HS);
+    flush_hist(sh + A.ext_off * A.hist_ks, B, A.n_copies, weight, A.counts, false, A.hist_cs, A.hist_ks);
 }
 
 __global__ void rdf_add_const(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
@@ -1369,6 +1648,7 @@ struct mdc_rdf_plan {
     int occ_fast = 1, occ_exact = 1;   // resident blocks per SM (persistent grids)
     int blocks_per_sm = 0;             // > 0: the filter kernel launches at most this many blocks per SM
     int ext_cap = 0;                   // > 0: words per histogram copy the filter kernel's shared memory is sized for
+    int ext_cap32 = 0;                 // > 0: the same with 32 interleaved copies (RdfArgs::hist_ks = 32)
     Thresholds th;
     DevBuf<double> T;
     DevBuf<unsigned long long> counts, ticket;
@@ -1547,12 +1827,14 @@ extern "C" int mdc_rdf_plan_create(mdc_ctx *ctx, int n_bins, double r0, double r
     }
     p->n_copies = copies;
     p->smem = fixed + (size_t)copies * n_bins * 4;
-    const size_t fixed_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + sizeof(double) * (n_bins + 1);
+    const size_t fixed_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + sizeof(double) * (n_bins + 1) + sizeof(unsigned) * RF_QCAP;
     int copies_fast = RF_THREADS / 32;
     while (copies_fast > 1 && fixed_fast + (size_t)copies_fast * n_bins * 4 > budget) copies_fast >>= 1;
     p->n_copies_fast = copies_fast;
     p->smem_fast = fixed_fast + (size_t)copies_fast * n_bins * 4;   // > budget: the filter kernel is not used
-    // extended histograms (RdfArgs::ext_k): as many words per copy as still leave MDC_RF_BLOCKS blocks per SM
+    // extended histograms (RdfArgs::ext_k): as many words per copy as still leave MDC_RF_BLOCKS blocks per SM -- eight
+    // copies one after the other, or (preferred where the bins of a frame block fit) 32 interleaved ones with a
+    // shorter queue of undecided rows
     {
         const size_t per_block = ctx->smem_per_sm / MDC_RF_BLOCKS;
         const size_t room = per_block > 1024 + fixed_fast ? per_block - 1024 - fixed_fast : 0;   // 1 KB reserved per block
@@ -1561,6 +1843,13 @@ extern "C" int mdc_rdf_plan_create(mdc_ctx *ctx, int n_bins, double r0, double r
         if (copies_fast == RF_THREADS / 32 && cap >= n_bins + 8 && fixed_fast + (size_t)copies_fast * cap * 4 <= budget) {
             p->ext_cap = cap;
             p->smem_fast = fixed_fast + (size_t)copies_fast * cap * 4;
+            const size_t room32 = room + sizeof(unsigned) * (RF_QCAP - RF_QCAP_L32);
+            const int cap32 = (int)std::min<size_t>(room32 / 128, 4096);
+            static const bool l32_off_env = getenv("MDC_RDF_L32") && getenv("MDC_RDF_L32")[0] == '0';
+            if (cap32 >= n_bins + 8 && !l32_off_env) {
+                p->ext_cap32 = cap32;
+                p->smem_fast = std::max(p->smem_fast, fixed_fast - sizeof(unsigned) * (RF_QCAP - RF_QCAP_L32) + (size_t)cap32 * 128);
+            }
         }
     }
     const char *env = getenv("MDC_RDF_EXACT");
@@ -1714,14 +2003,30 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         A.ua = p->fix_a[slot].p;
         A.ub = p->same ? p->fix_a[slot].p : p->fix_b[slot].p;
         A.ext_k = A.ext_off = 0;
+        A.n_copies = fast ? p->n_copies_fast : p->n_copies;
+        A.hist_ks = 1;
+        A.hist_cs = p->n_bins;
+        A.qcap = RF_QCAP;
+        {
+            static const bool rel_off_env = getenv("MDC_RDF_REL") && getenv("MDC_RDF_REL")[0] == '0';
+            A.rel = rel_off_env ? 0 : 1;
+        }
         if (fast && p->ext_cap > 0) {
             // bins the filter can produce: k >= -(r0 S) - 1 (d >= 0) and k <= v_far (half the box diagonal), with slack
             const double S = (double)p->n_bins / (p->r1 - p->r0);
             const double k_lo = -(std::ceil(std::fabs(p->r0 * S)) + 2.0), k_hi = std::ceil(v_far_max) + 1.0;
             static const bool ext_off_env = getenv("MDC_RDF_EXT") && getenv("MDC_RDF_EXT")[0] == '0';
-            if (k_hi - k_lo + 1.0 <= (double)p->ext_cap && !ext_off_env) {
+            if (k_hi - k_lo + 1.0 <= (double)p->ext_cap32 && !ext_off_env) {
+                A.ext_k = p->ext_cap32;   // one copy per lane (= per bank), bins 32 words apart
+                A.ext_off = (int)(-k_lo);
+                A.n_copies = 32;
+                A.hist_ks = 32;
+                A.hist_cs = 1;
+                A.qcap = RF_QCAP_L32;
+            } else if (k_hi - k_lo + 1.0 <= (double)p->ext_cap && !ext_off_env) {
                 A.ext_k = p->ext_cap;
                 A.ext_off = (int)(-k_lo);
+                A.hist_cs = p->ext_cap;
             }
         }
         A.oa = A.ob = nullptr;
@@ -1755,7 +2060,6 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         A.ex0 = p->ex0;
         A.ex1 = p->ex1;
         A.n_bins = p->n_bins;
-        A.n_copies = fast ? p->n_copies_fast : p->n_copies;
         A.F = F;
         A.nti = (int)ceil_div(p->na, fast ? RF_TI : RDF_TI);
         A.ntj = (int)ceil_div(p->nb, fast ? RF_TJ : RDF_TJ);
