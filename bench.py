@@ -509,12 +509,19 @@ def run_native(args, rank, world, emit=print):
 
     # ------------------------------------------------------------------ secondary figures (rank 0 of a single-GPU run)
     extras = {}
+    used = sqp.info()
     if world == 1 and not args.no_extras:
         extras = secondary_figures(args, ctx, ctx_s, rdf, sqp, gr_dev, sq_dev, box_g, Ls, b, flush, nq)
+        # free this job's device buffers before the two larger systems below
+        rdf.close()
+        sqp.close()
+        del gr_dev, sq_dev
+        torch.cuda.empty_cache()
+        extras["other_configs"] = other_configs(ctx, flush)
+        checks["ok"] = checks["ok"] and all(c["parity"] == "ok" for c in extras["other_configs"].values())
 
     if rank == 0:
         sm = ctx.info()["sm_count"]
-        used = sqp.info()
         summary = ncu_summary()
         gr_alone_ms, sq_alone_ms = extras.get("gr_alone_ms"), extras.get("sq_alone_ms")
         pairs = 0.5 * N_PART * (N_PART - 1) * K * b            # pair-distances this rank's pair kernel evaluated
@@ -572,6 +579,8 @@ def run_native(args, rank, world, emit=print):
             if k in extras:
                 line[{"direct": "roofline_sfu_direct", "factored": "roofline_fp32_factored",
                       "sq_default_fps": "sq_default_grid_frames_per_s"}[k]] = extras[k]
+        if "other_configs" in extras:
+            line["other_configs"] = extras["other_configs"]
         if gr_alone_ms:
             line["gr_frames_per_s"] = b / (gr_alone_ms * 1e-3)
             line["gr_pairs_per_s"] = 0.5 * N_PART * (N_PART - 1) * b / (gr_alone_ms * 1e-3)
@@ -631,6 +640,124 @@ def nufft_roofline(used, sq_alone_ms, frames, nq, summary):
                            + ("written once by the gather kernel" if tiles else "cleared and spread into (read-modify-write)")
                            + f" (w = {w}) and read once; pruned intermediates {nf}^2 x {n} and {nf} x {n}^2 written and read "
                            f"once; {nq} densities"}
+
+
+def other_configs(ctx, flush):
+    """
+    BASELINE.json configs 4 and 5 (C4: 2e5-ion binary electrolyte, three g(r) + three partial S(q) on the full
+    q_max = 20/sigma grid; C5: 1e6 particles, g(r) + S(q) on the reference's default grid): frames/s of each on two
+    (C4) / one (C5) device-resident frames, CUDA events on the library's compute stream after a warm-up push, L2 flushed
+    before the timed push -- and every figure's RESULT checked against the CPU oracle (a slab of i-particles against
+    all j bit for bit, 32 wavevectors within the NUFFT's tolerance).  Secondary figures: the headline stays C2 + C3.
+    """
+    import torch
+
+    from mdcraft_b200 import _capi, synthetic
+    from oracle import oracle
+
+    out = {}
+
+    def timed(push, plans, reset=True):
+        push()                      # warm-up (allocations, tables)
+        ctx.synchronize()
+        for p in plans:
+            p.reset()
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ctx.mark(0)
+        push()
+        ctx.mark(1)
+        return ctx.elapsed_ms()
+
+    def sq_close(got, want, n_total, scale):
+        got, want = got / n_total, want / n_total                    # sums over the frames of S per frame
+        tol = 1e-5 * np.abs(want) + 2 * 5 * 1e-8 * scale + 1e-12     # tests/test_gpu_parity.py::_sq_close, NUFFT kappa
+        return bool((np.abs(got - want) <= tol).all())
+
+    # ---- C4
+    n, _, rho, _, seed0 = synthetic.CONFIGS["C4"]
+    L = float(synthetic.cubic_box_length(n, rho))
+    F, half = 2, n // 2
+    host = np.stack([synthetic.lj_like_frame(n, L, seed0 + i) for i in range(F)])
+    pos = torch.from_numpy(host).cuda()
+    box = np.array([L, L, L, 90, 90, 90], np.float32)
+    pa, pb = pos[:, :half].contiguous(), pos[:, half:].contiguous()
+    rng = (0.0, L / 2)
+    pp = _capi.RdfPlan(ctx, 200, rng, half, None, (1, 1))
+    mm = _capi.RdfPlan(ctx, 200, rng, half, None, (1, 1))
+    pm = _capi.RdfPlan(ctx, 200, rng, half, half)
+
+    def c4_rdf():
+        pp.push(pa, None, box, n_frames=F)
+        mm.push(pb, None, box, n_frames=F)
+        pm.push(pa, pb, box, n_frames=F)
+
+    gr_ms = timed(c4_rdf, (pp, mm, pm))
+    cross, _ = pm.read()
+    # oracle: cations 1000..1255 against all anions, both frames -- against the kernel through additivity over i
+    slab = _capi.RdfPlan(ctx, 200, rng, half - 256, half)
+    rest = torch.cat((pa[:, :1000], pa[:, 1256:]), 1).contiguous()
+    slab.push(rest, pb, box, n_frames=F)
+    rest_counts, _ = slab.read()
+    want = sum(oracle.radial_histogram(host[f, 1000:1256], host[f, half:], 200, rng, box) for f in range(F))
+    gr_ok = bool(np.array_equal(cross - rest_counts, want))
+    for p in (pp, mm, pm, slab):
+        p.close()
+    pairs = [(0, 0), (0, 1), (1, 1)]
+    sq = _capi.SqPlan(ctx, [half, half], pairs, n_points=201, L0=[L] * 3, q_max=20.0)
+    sq_ms = timed(lambda: sq.push(pos, n_frames=F), (sq,))
+    got, _ = sq.read()
+    wv = sq.wavevectors()
+    idx = np.sort(np.random.default_rng(4).choice(len(wv), 32, replace=False))
+    want, _ = oracle.sq_accumulate(list(host), [half, half], wv[idx], pairs)
+    saa, sbb = np.sqrt(want[0] / (n * F)), np.sqrt(want[2] / (n * F))
+    sq_ok = all(sq_close(got[i][idx], want[i], n, F * sc) for i, sc in enumerate((saa, saa + sbb, sbb)))
+    info = sq.info()
+    nq4 = sq.n_wavevectors
+    sq.close()
+    out["C4"] = {"workload": f"binary electrolyte, {half} + {half} ions (LJ-like rho* = 0.8): g(r) ++, --, +- (200 bins to L/2) and "
+                             f"partial S(q) ++, +-, -- on the full lattice grid to q_max = 20/sigma (Nq = {nq4})",
+                 "frames": F, "gr_three_frames_per_s": 1e3 * F / gr_ms, "sq_partial_frames_per_s": 1e3 * F / sq_ms,
+                 "frames_per_s": 1e3 * F / (gr_ms + sq_ms), "sq_algo": info["algo"],
+                 "gr_cross_slab_equal_oracle": gr_ok, "sq_32_wavevectors_within_tolerance": sq_ok,
+                 "parity": "ok" if gr_ok and sq_ok else "FAILED"}
+    del pos, pa, pb, rest
+    torch.cuda.empty_cache()
+
+    # ---- C5
+    n, _, rho, _, seed0 = synthetic.CONFIGS["C5"]
+    L = float(synthetic.cubic_box_length(n, rho))
+    host = synthetic.uniform_frame(n, L, seed0)[None]
+    pos = torch.from_numpy(host).cuda()
+    box = np.array([L, L, L, 90, 90, 90], np.float32)
+    rng = (0.0, L / 2)
+    rdf = _capi.RdfPlan(ctx, 200, rng, n, None, (1, 1))
+    gr_ms = timed(lambda: rdf.push(pos, None, box, n_frames=1), (rdf,))
+    full, _ = rdf.read()
+    # oracle: the ordered pairs (i in 5000..5063, all j, the 64 i = j pairs in bin 0 included on both sides)
+    slab = _capi.RdfPlan(ctx, 200, rng, 64, n)
+    slab.push(pos[:, 5000:5064].contiguous(), pos, box, n_frames=1)
+    got, _ = slab.read()
+    want = oracle.radial_histogram(host[0, 5000:5064], host[0], 200, rng, box)
+    gr_ok = bool(np.array_equal(got, want)) and int(full.sum()) > 0
+    rdf.close()
+    slab.close()
+    sq = _capi.SqPlan(ctx, [n], [(None, None)], n_points=32, L0=[L] * 3)
+    sq_ms = timed(lambda: sq.push(pos, n_frames=1), (sq,))
+    got, _ = sq.read()
+    wv = sq.wavevectors()
+    idx = np.sort(np.random.default_rng(5).choice(len(wv), 32, replace=False))
+    want, _ = oracle.sq_accumulate(list(host), [n], wv[idx], [(None, None)])
+    sq_ok = sq_close(got[0][idx], want[0], n, np.sqrt(want[0] / n))
+    info = sq.info()
+    sq.close()
+    out["C5"] = {"workload": f"{n} particles (uniform rho* = 0.8): g(r) (200 bins to L/2, exclusion (1, 1)) and S(q) on the "
+                             f"reference's default grid (n_points = 32, Nq = 32768)",
+                 "frames": 1, "gr_frames_per_s": 1e3 / gr_ms, "gr_pairs_per_s": 0.5 * n * (n - 1.0) * 1e3 / gr_ms,
+                 "sq_frames_per_s": 1e3 / sq_ms, "frames_per_s": 1e3 / (gr_ms + sq_ms), "sq_algo": info["algo"],
+                 "gr_slab_equal_oracle": gr_ok, "sq_32_wavevectors_within_tolerance": sq_ok,
+                 "parity": "ok" if gr_ok and sq_ok else "FAILED"}
+    return out
 
 
 def secondary_figures(args, ctx, ctx_s, rdf, sqp, gr_dev, sq_dev, box_g, Ls, b, flush, nq):
