@@ -42,6 +42,7 @@ struct FrameBox {
 // values widened: a = (ax, 0, 0), b = (bx, by, 0), c = (cx, cy, cz).  on == 0: orthorhombic frame (FrameBox applies).
 struct FrameTri {
     double ax, bx, by, cx, cy, cz;
+    double w[3];      // perpendicular widths of the cell along a, b, c (distance between opposite faces)
     int on, pad;
 };
 
@@ -115,10 +116,12 @@ struct FrameFast {
     float ax, ay, az;   // (float)(int32)(u_j - u_i) * a_k  =  separation along k in units of one bin width
     float c0;           // v = |separation| + c0 = bin coordinate - 0.5   (c0 = -r0 * S - 0.5)
     float thr;          // 0.5 - margin: a pair is decided in FP32 iff |v - rint(v)| <= thr
-    int cubic;          // ax == ay == az
+    int kind;           // FK_CUBIC: ax == ay == az; FK_ORTHO; FK_TRI: triclinic cell, the separation is
+                        //   (tx ax + ty bx + tz cx, ty ay + tz cy, tz az) with t = differences of the FRACTIONAL coordinates
     int usable;         // 0: this frame must take the exact kernel's arithmetic for every pair
-    int pad;
+    float bx, cx, cy;   // FK_TRI: off-diagonal entries of the cell matrix, scaled like ax / ay / az (= its diagonal)
 };
+enum { FK_CUBIC = 0, FK_ORTHO = 1, FK_TRI = 2 };
 
 // MDAnalysis' _triclinic_pbc for one coordinate (calc_distances.h; restated in oracle/oracle.c:orc_triclinic_wrap, same
 // operations in the same order, no FMA contraction): into the primary cell along c, then b, then a.
@@ -154,7 +157,8 @@ __device__ __forceinline__ void tri_wrap(float &xf, float &yf, float &zf, const 
 // coordinate and the largest NEGATED coordinate (float bits, atomicMax; both clamped at 0): their sum bounds the range
 // of the coordinates, hence every |a - b| that the reference subtracts in float32.  extent = {max x, max -x} x (F).
 // Triclinic frames: soa holds the coordinates moved into the primary cell (what the reference's distance routine
-// works on); fix is not used by the kernel that takes such frames.
+// works on); fix the fractions of THOSE along the cell vectors a, b, c (the filter kernel's minimum image is the wrap
+// of the fractional differences, valid for cutoffs below half the smallest width of the cell: see rdf_frame_params).
 __global__ void rdf_prep(const float *__restrict__ raw, int64_t N, int64_t total, const FrameBox *__restrict__ boxes,
                          const FrameTri *__restrict__ tri, int F, float *__restrict__ soa, uint32_t *__restrict__ fix,
                          unsigned *__restrict__ extent)
@@ -169,11 +173,18 @@ __global__ void rdf_prep(const float *__restrict__ raw, int64_t N, int64_t total
         float p[3] = {raw[3 * i], raw[3 * i + 1], raw[3 * i + 2]};
         const FrameTri ft = tri[f];
         if (ft.on) tri_wrap(p[0], p[1], p[2], ft);
+        // triclinic frames: fractions along a, b, c of the (wrapped) position, x = sa a + sb b + sc c
+        double fr[3] = {0.0, 0.0, 0.0};
+        if (ft.on) {
+            fr[2] = (double)p[2] / ft.cz;
+            fr[1] = ((double)p[1] - fr[2] * ft.cy) / ft.by;
+            fr[0] = ((double)p[0] - fr[1] * ft.bx - fr[2] * ft.cx) / ft.ax;
+        }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const float x = p[k];
             soa[(f * 3 + k) * N + j] = x;
-            double s = fb.pbc[k] ? (double)x / fb.box[k] : 0.0;
+            double s = ft.on ? fr[k] : (fb.pbc[k] ? (double)x / fb.box[k] : 0.0);
             s -= floor(s);
             fix[(f * 3 + k) * N + j] = (uint32_t)(unsigned long long)(s * 4294967296.0 + 0.5);
             mp = fmaxf(mp, x);
@@ -207,36 +218,66 @@ __global__ void rdf_prep(const float *__restrict__ raw, int64_t N, int64_t total
 //   fixed point vs true separation: 2^-32 L per axis (2^-31 L is used);
 //   FP32 evaluation (I2F, squares, sum, MUFU.SQRT, FMA): <= 3.5e-7 relative + one ulp of v (4.7e-7 is used);
 //   all of it times 1.25.
-__global__ void rdf_frame_params(const FrameBox *__restrict__ boxes, const unsigned *__restrict__ extent_a,
-                                 const unsigned *__restrict__ extent_b, int Fa, int F, int n_bins, double r0, double r1,
-                                 FrameFast *__restrict__ out)
+__global__ void rdf_frame_params(const FrameBox *__restrict__ boxes, const FrameTri *__restrict__ tri,
+                                 const unsigned *__restrict__ extent_a, const unsigned *__restrict__ extent_b, int Fa, int F,
+                                 int n_bins, double r0, double r1, FrameFast *__restrict__ out)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     const FrameBox fb = boxes[f];
+    const FrameTri ft = tri[f];
     const double S = (double)n_bins / (r1 - r0);
     const double hi = fmax((double)__uint_as_float(extent_a[f]), (double)__uint_as_float(extent_b[f]));
     const double lo = fmax((double)__uint_as_float(extent_a[Fa + f]), (double)__uint_as_float(extent_b[Fa + f]));
     const double R = hi + lo;   // >= max - min over both groups and all three axes
-    const double Lmax = fmax(fb.box[0], fmax(fb.box[1], fb.box[2]));
     FrameFast p;
-    p.ax = (float)(fb.box[0] * S / 4294967296.0);
-    p.ay = (float)(fb.box[1] * S / 4294967296.0);
-    p.az = (float)(fb.box[2] * S / 4294967296.0);
     p.c0 = (float)(-r0 * S - 0.5);
-    // + the relative-coordinate rows of the filter (rows_rel): the row's difference to the box centre is rounded to FP32
-    // on its own (<= 2^-26 L: 32-bit integers below 2^31), the particle's too (<= 2^-28 L: boxes below 2^-3 L); the
-    // rounding of their FP32 difference is relative (<= 1.3 x 2^-24 of the wrapped difference at the seam) and part of
-    // the 4.7e-7 below, like the conversion it replaces
-    const double e_abs = 1.7320508 * (R / 8388608.0 + Lmax / 2147483648.0 + Lmax * (1.0 / 67108864.0 + 1.0 / 268435456.0));
+    p.bx = p.cx = p.cy = 0.f;
     const double vmax = (double)n_bins + 2.0 + fabs(r0 * S);
-    const double margin = 1.25 * (S * e_abs + 4.7e-7 * vmax) + 1e-6;
+    double margin, v_far;
+    bool ok = true;
+    if (ft.on) {
+        // Triclinic cell.  The filter's image of a pair is the wrap of its FRACTIONAL differences (|s_k| <= 1/2).  A
+        // separation shorter than half the smallest width w of the cell has |s_k| = |d . n_k| / w_k < 1/2 on every
+        // axis, so it IS that image; and if that image is longer than the cutoff, so is the true one (or it is at
+        // least w / 2): for r1 < w / 2 the filter and the reference (minimum_image_triclinic: the shortest of 27
+        // images) see the same image of every pair that can lie in the window.
+        p.ax = (float)(ft.ax * S / 4294967296.0);
+        p.ay = (float)(ft.by * S / 4294967296.0);
+        p.az = (float)(ft.cz * S / 4294967296.0);
+        p.bx = (float)(ft.bx * S / 4294967296.0);
+        p.cx = (float)(ft.cx * S / 4294967296.0);
+        p.cy = (float)(ft.cy * S / 4294967296.0);
+        p.kind = FK_TRI;
+        const double la = fabs(ft.ax), lb = sqrt(ft.bx * ft.bx + ft.by * ft.by),
+                     lc = sqrt(ft.cx * ft.cx + ft.cy * ft.cy + ft.cz * ft.cz), Lsum = la + lb + lc;
+        // reference: float32 subtraction of two wrapped coordinates per axis (<= 2^-24 R; the image shifts are exact);
+        // filter: fractions to 2^-32 (2^-31 |a| + |b| + |c|), the two conversions of the relative rows (2^-26 + 2^-28),
+        // and the matrix product in FP32: six roundings of terms of up to half a cell vector (2^-22 (|a| + |b| + |c|))
+        const double e_abs = 1.7320508 * R / 8388608.0 +
+                             Lsum * (1.0 / 2147483648.0 + 1.0 / 67108864.0 + 1.0 / 268435456.0 + 1.0 / 4194304.0);
+        margin = 1.25 * (S * e_abs + 4.7e-7 * vmax) + 1e-6;
+        v_far = 0.5 * Lsum * S + fabs(r0 * S) + 1.0;
+        const double wmin = fmin(ft.w[0], fmin(ft.w[1], ft.w[2]));
+        ok = r1 * (1.0 + 1e-4) + 1e-5 * Lsum < 0.5 * wmin;
+    } else {
+        const double Lmax = fmax(fb.box[0], fmax(fb.box[1], fb.box[2]));
+        p.ax = (float)(fb.box[0] * S / 4294967296.0);
+        p.ay = (float)(fb.box[1] * S / 4294967296.0);
+        p.az = (float)(fb.box[2] * S / 4294967296.0);
+        // + the relative-coordinate rows of the filter (rows_rel): the row's difference to the box centre is rounded to FP32
+        // on its own (<= 2^-26 L: 32-bit integers below 2^31), the particle's too (<= 2^-28 L: boxes below 2^-3 L); the
+        // rounding of their FP32 difference is relative (<= 1.3 x 2^-24 of the wrapped difference at the seam) and part of
+        // the 4.7e-7 below, like the conversion it replaces
+        const double e_abs = 1.7320508 * (R / 8388608.0 + Lmax / 2147483648.0 + Lmax * (1.0 / 67108864.0 + 1.0 / 268435456.0));
+        margin = 1.25 * (S * e_abs + 4.7e-7 * vmax) + 1e-6;
+        p.kind = (p.ax == p.ay && p.ay == p.az) ? FK_CUBIC : FK_ORTHO;
+        v_far = 0.5 * sqrt(fb.box[0] * fb.box[0] + fb.box[1] * fb.box[1] + fb.box[2] * fb.box[2]) * S + fabs(r0 * S) + 1.0;
+        ok = fb.pbc[0] && fb.pbc[1] && fb.pbc[2];
+    }
     p.thr = (float)fmax(0.5 - margin, -1.0);
-    p.cubic = (p.ax == p.ay && p.ay == p.az) ? 1 : 0;
     // the magic-number rounding below needs |v| < 2^22; all three axes must be periodic
-    const double v_far = 0.5 * sqrt(fb.box[0] * fb.box[0] + fb.box[1] * fb.box[1] + fb.box[2] * fb.box[2]) * S + fabs(r0 * S) + 1.0;
-    p.usable = (fb.pbc[0] && fb.pbc[1] && fb.pbc[2] && v_far < 4.0e6 && margin < 0.5) ? 1 : 0;
-    p.pad = 0;
+    p.usable = (ok && v_far < 4.0e6 && margin < 0.5) ? 1 : 0;
     out[f] = p;
 }
 
@@ -275,6 +316,7 @@ struct RdfArgs {
     // bank and the increments of a warp never conflict (tools/atoms_probe.cu: 1.0 instead of 3.1 cycles per ATOMS).
     int hist_ks, hist_cs;
     int qcap;                     // filter kernel: capacity of the queue of undecided rows (words, after the histograms)
+    unsigned char *ovf;           // filter kernel: per block, RF_TJ x RF_THREADS bytes for the rows that do not fit the queue (park_row)
     int rel;                      // filter kernel, sorted frames: relative-coordinate rows allowed (MDC_RDF_REL=0 turns them off)
 };
 
@@ -407,9 +449,12 @@ __global__ void __launch_bounds__(256) rdf_tile_boxes(const uint32_t *__restrict
 }
 
 // squared minimum-image distance between two tile boxes (fractions of the box per axis, scaled by the box lengths)
-__device__ __forceinline__ double tile_gap2(const uint32_t *a, const uint32_t *b, const FrameBox &fb)
+// Triclinic frames: the boxes bound the FRACTIONS along a, b, c; two points whose fractions differ by g along k are at
+// least g w_k apart (w_k: width of the cell along k), so the bound is the LARGEST of the three, not their root sum.
+__device__ __forceinline__ double tile_gap2(const uint32_t *a, const uint32_t *b, const FrameBox &fb, const FrameTri *ftp)
 {
     double d2 = 0.0;
+    const bool tri = ftp->on != 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const double alo = a[2 * k] * (1.0 / 4294967296.0), ahi = a[2 * k + 1] * (1.0 / 4294967296.0);
@@ -417,8 +462,8 @@ __device__ __forceinline__ double tile_gap2(const uint32_t *a, const uint32_t *b
         double gap = 1.0;
 #pragma unroll
         for (int m = -1; m <= 1; ++m) gap = fmin(gap, fmax(0.0, fmax(blo + m - ahi, alo - (bhi + m))));
-        gap *= fb.box[k];
-        d2 += gap * gap;
+        gap *= tri ? ftp->w[k] : fb.box[k];
+        d2 = tri ? fmax(d2, gap * gap) : d2 + gap * gap;
     }
     return d2;
 }
@@ -640,14 +685,19 @@ struct FastShared {
     unsigned *queue;
     unsigned qcount;
     unsigned qcap;
+    unsigned char *ovf;         // this block's overflow table (RdfArgs::ovf), RF_TJ x RF_THREADS bytes, all zero between tile pairs
+    unsigned overflow;          // a row of this tile pair went to the table
+    unsigned pad0[3];
     unsigned trash[RF_THREADS]; // per-thread dummy target of the branch-free histogram increment
-    unsigned char ctx[384];     // TileCtx of the tile in flight (cold passes read it from here)
+    unsigned char ctx[512];     // TileCtx of the tile in flight (cold passes read it from here)
     // sorted frames only: bounding boxes {lo x, lo y, lo z, -, hi x, hi y, hi z, -} (32-bit box fractions) of the 128
     // particles i of every warp (followed by the box's centre and half extents) and of every chunk of 32 rows j, and
     // {L_k / 2^32 (k = x, y, z), cull_r^2}
     uint4 ibox[RF_THREADS / 32][8];   // + {centre}, {half extent} of the box, of its first 64 and of its last 64 particles
     uint4 jbox[RF_TJ / 32][2];
     float cull[4];
+    int cull_tri;               // triclinic frame: the boxes hold fractions along the cell vectors (gap_norm2)
+    int pad3[3];
     // sorted frames: next chunk of 32 rows to hand out for the 128 particles i of every warp ("group").  A warp draws the
     // chunks of its own group from here and, once those are gone, the remaining chunks of the other groups (it then
     // reloads that group's particles): uneven culling no longer leaves warps idle at the end of a tile pair.
@@ -667,7 +717,13 @@ __device__ __forceinline__ int rf_il_of(int g, int u) { return g * (32 * RF_IPT)
 // sorted frames: is every particle of box a farther than the cutoff from every particle of box b (minimum image)?
 // Warp-uniform.  Per axis the gap between two intervals on the 2^32 circle that do not overlap is the smaller of the
 // two wrapped differences.
-__device__ __forceinline__ bool boxes_apart(const uint4 *a, const uint4 *b, const float (&c)[4])
+__device__ __forceinline__ float gap_norm2(float gx, float gy, float gz, bool tri)
+{
+    // orthorhombic: Euclidean; triclinic (gaps along the cell vectors times the cell's widths): the largest one
+    return tri ? fmaxf(gx * gx, fmaxf(gy * gy, gz * gz)) : fmaf(gz, gz, fmaf(gy, gy, gx * gx));
+}
+
+__device__ __forceinline__ bool boxes_apart(const uint4 *a, const uint4 *b, const float (&c)[4], bool tri)
 {
     auto gap = [](uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi) -> float {
         const bool overlap = blo <= ahi && alo <= bhi;
@@ -676,7 +732,7 @@ __device__ __forceinline__ bool boxes_apart(const uint4 *a, const uint4 *b, cons
     const float gx = gap(a[0].x, a[1].x, b[0].x, b[1].x) * c[0];
     const float gy = gap(a[0].y, a[1].y, b[0].y, b[1].y) * c[1];
     const float gz = gap(a[0].z, a[1].z, b[0].z, b[1].z) * c[2];
-    return fmaf(gz, gz, fmaf(gy, gy, gx * gx)) > c[3];
+    return gap_norm2(gx, gy, gz, tri) > c[3];
 }
 
 // sorted frames: which of the 32 rows j of a chunk (one row per lane) have ANY of this warp's 128 particles within the
@@ -694,7 +750,7 @@ __device__ __forceinline__ unsigned rows_in_reach(const FastShared *S, const uin
     const float gx = gap(pj.x, ctr.x, hf.x) * S->cull[0];
     const float gy = gap(pj.y, ctr.y, hf.y) * S->cull[1];
     const float gz = gap(pj.z, ctr.z, hf.z) * S->cull[2];
-    const bool in = j < nj && fmaf(gz, gz, fmaf(gy, gy, gx * gx)) <= S->cull[3];
+    const bool in = j < nj && gap_norm2(gx, gy, gz, S->cull_tri != 0) <= S->cull[3];
     return __ballot_sync(0xffffffffu, in);
 }
 
@@ -720,25 +776,37 @@ __device__ __forceinline__ unsigned rows_rel(FastShared *S, const uint4 *ch, int
     return m;
 }
 
-// The filter's FP32 bin coordinate of one pair: v = bin coordinate - 0.5 (so that rint(v) is the bin).
-template <bool CUBIC>
+// The filter's FP32 bin coordinate of one pair from its three coordinate differences (2^-32 box fractions; for a
+// triclinic cell: differences of the fractions along a, b, c): v = bin coordinate - 0.5 (so that rint(v) is the bin).
+template <int KIND>
+__device__ __forceinline__ float filter_v_tail(float tx, float ty, float tz, const FrameFast &ff)
+{
+    float d;
+    if (KIND == FK_CUBIC) {
+        const float t2 = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, __fmul_rn(tx, tx)));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
+        return __fmaf_rn(d, ff.ax, ff.c0);
+    }
+    float ex, ey, ez;
+    if (KIND == FK_TRI) {
+        ex = __fmaf_rn(tz, ff.cx, __fmaf_rn(ty, ff.bx, __fmul_rn(tx, ff.ax)));
+        ey = __fmaf_rn(tz, ff.cy, __fmul_rn(ty, ff.ay));
+        ez = __fmul_rn(tz, ff.az);
+    } else {
+        ex = __fmul_rn(tx, ff.ax);
+        ey = __fmul_rn(ty, ff.ay);
+        ez = __fmul_rn(tz, ff.az);
+    }
+    const float t2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
+    return __fadd_rn(d, ff.c0);
+}
+
+template <int KIND>
 __device__ __forceinline__ float filter_v(uint32_t ujx, uint32_t ujy, uint32_t ujz, uint32_t uix, uint32_t uiy,
                                           uint32_t uiz, const FrameFast &ff)
 {
-    const float tx = (float)(int)(ujx - uix);
-    const float ty = (float)(int)(ujy - uiy);
-    const float tz = (float)(int)(ujz - uiz);
-    float d;
-    if (CUBIC) {
-        const float t2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
-        return fmaf(d, ff.ax, ff.c0);
-    } else {
-        const float ex = tx * ff.ax, ey = ty * ff.ay, ez = tz * ff.az;
-        const float t2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
-        return d + ff.c0;
-    }
+    return filter_v_tail<KIND>((float)(int)(ujx - uix), (float)(int)(ujy - uiy), (float)(int)(ujz - uiz), ff);
 }
 
 // Relative-coordinate form of the filter (sorted frames, rows clear of the periodic seam of the group's box, see
@@ -755,30 +823,21 @@ __device__ __forceinline__ float rel_wrap(float e)
     return __fmaf_rn(q, -4294967296.f, e);
 }
 
-template <bool CUBIC>
+template <int KIND>
 __device__ __forceinline__ float filter_v_rel(uint32_t ujx, uint32_t ujy, uint32_t ujz, uint32_t uix, uint32_t uiy,
                                               uint32_t uiz, const uint4 &ctr, const FrameFast &ff)
 {
     const float tx = rel_wrap(__fadd_rn((float)(int)(ujx - ctr.x), -(float)(int)(uix - ctr.x)));
     const float ty = rel_wrap(__fadd_rn((float)(int)(ujy - ctr.y), -(float)(int)(uiy - ctr.y)));
     const float tz = rel_wrap(__fadd_rn((float)(int)(ujz - ctr.z), -(float)(int)(uiz - ctr.z)));
-    float d;
-    if (CUBIC) {
-        const float t2 = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, __fmul_rn(tx, tx)));
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
-        return __fmaf_rn(d, ff.ax, ff.c0);
-    } else {
-        const float ex = __fmul_rn(tx, ff.ax), ey = __fmul_rn(ty, ff.ay), ez = __fmul_rn(tz, ff.az);
-        const float t2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(t2));
-        return __fadd_rn(d, ff.c0);
-    }
+    return filter_v_tail<KIND>(tx, ty, tz, ff);
 }
 
 struct TileCtx {            // everything the cold passes need (kept in shared memory, one per block)
     RdfArgs A;
     FrameFast ff;
     FrameBox fb;
+    FrameTri ft;
     int64_t i0, j0;
     int f, diag;
     float thr;
@@ -790,13 +849,22 @@ struct TileCtx {            // everything the cold passes need (kept in shared m
 // the reference's FP64 distance, count.  (In round 1 the flagged lane did the take-back and one queue slot per pair
 // on the spot: one active lane of 32 for ~60 instructions in 13 % of all rows, a tenth of the kernel's instructions.)
 
+// tri_r2 behind a call: inlined into resolve_entry, its 27 images raise the register needs of every function on the call
+// chain, and the hot loops (which call park_row in their cold branch) spill around the call
+__device__ __noinline__ double tri_r2_call(float xi, float yi, float zi, float xj, float yj, float zj, const FrameTri *t)
+{
+    return tri_r2(xi, yi, zi, xj, yj, zj, *t);
+}
+
 // cold: the reference's exact FP64 result for a pair the filter could not decide
 __device__ __forceinline__ void resolve_pair(const TileCtx &T, int il, int jl, const double *sT, unsigned *hist)
 {
     const int64_t ig = T.i0 + il, jg = T.j0 + jl;
     const float *ax = T.A.a + ((int64_t)T.f * 3) * T.A.na, *bx = T.A.b + ((int64_t)T.f * 3) * T.A.nb;
-    const double r2 = exact_r2(ax[ig], ax[T.A.na + ig], ax[2 * T.A.na + ig], bx[jg], bx[T.A.nb + jg],
-                               bx[2 * T.A.nb + jg], T.fb);
+    const double r2 = T.ft.on ? tri_r2_call(ax[ig], ax[T.A.na + ig], ax[2 * T.A.na + ig], bx[jg], bx[T.A.nb + jg],
+                                             bx[2 * T.A.nb + jg], &T.ft)
+                              : exact_r2(ax[ig], ax[T.A.na + ig], ax[2 * T.A.na + ig], bx[jg], bx[T.A.nb + jg],
+                                         bx[2 * T.A.nb + jg], T.fb);
     const int k = exact_bin(r2, T.A, sT);
     if (k >= 0) atomicAdd(&hist[k * T.A.hist_ks], 1u);
 }
@@ -820,13 +888,16 @@ __device__ __noinline__ void resolve_entry(const FastShared *S, unsigned entry, 
             const uint32_t *ua = T.A.ua + ((int64_t)T.f * 3) * T.A.na;
             const uint4 pj = S->sj[jl];
             float v;
+            const uint32_t uix = ua[ig], uiy = ua[T.A.na + ig], uiz = ua[2 * T.A.na + ig];
             if (rel) {
                 const uint4 ctr = S->ibox[group][2];
-                v = T.ff.cubic ? filter_v_rel<true>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], ctr, T.ff)
-                               : filter_v_rel<false>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], ctr, T.ff);
+                v = T.ff.kind == FK_CUBIC  ? filter_v_rel<FK_CUBIC>(pj.x, pj.y, pj.z, uix, uiy, uiz, ctr, T.ff)
+                    : T.ff.kind == FK_TRI ? filter_v_rel<FK_TRI>(pj.x, pj.y, pj.z, uix, uiy, uiz, ctr, T.ff)
+                                          : filter_v_rel<FK_ORTHO>(pj.x, pj.y, pj.z, uix, uiy, uiz, ctr, T.ff);
             } else {
-                v = T.ff.cubic ? filter_v<true>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], T.ff)
-                               : filter_v<false>(pj.x, pj.y, pj.z, ua[ig], ua[T.A.na + ig], ua[2 * T.A.na + ig], T.ff);
+                v = T.ff.kind == FK_CUBIC  ? filter_v<FK_CUBIC>(pj.x, pj.y, pj.z, uix, uiy, uiz, T.ff)
+                    : T.ff.kind == FK_TRI ? filter_v<FK_TRI>(pj.x, pj.y, pj.z, uix, uiy, uiz, T.ff)
+                                          : filter_v<FK_ORTHO>(pj.x, pj.y, pj.z, uix, uiy, uiz, T.ff);
             }
             const int k = (int)(__float_as_uint(__fadd_rn(v, 12582912.f)) - 0x4B400000u);
             // rint(v) beyond B (or below -1): |v_ref - v| < 0.5 puts the pair outside the window whatever the rounding;
@@ -839,20 +910,22 @@ __device__ __noinline__ void resolve_entry(const FastShared *S, unsigned entry, 
 }
 
 // cold: this lane's pairs (row jl, particles with a bit in `mask`) are undecided: one word into the queue
-__device__ __noinline__ void park_row(FastShared *S, int jl, unsigned mask, int group, bool uncount, unsigned rel = 0u)
+// Queue full (lattices whose spacings sit on bin edges, margins of a sizeable fraction of a bin): the row is noted in the
+// block's overflow table in global memory instead -- one byte per (row, group, lane) of the tile pair, written only by
+// the thread that owns it -- and the resolve pass scans that table when the flag is up.  (The first version resolved
+// such rows on the spot; the FP64 code behind that call raised the register needs of park_row's whole call tree, and
+// every hot loop, which calls park_row in its cold branch, spilled its particles around the call.)
+__device__ __forceinline__ void park_row(FastShared *S, int jl, unsigned mask, int group, bool, unsigned rel = 0u)
 {
-    const unsigned entry = (unsigned)jl | ((threadIdx.x & 31u) << 10) | ((unsigned)group << 15) | (mask << 18) | (rel << 22);
+    const unsigned lane = threadIdx.x & 31u;
     const unsigned slot = atomicAdd(&S->qcount, 1u);
     if (slot < S->qcap) {
-        S->queue[slot] = entry;
+        S->queue[slot] = (unsigned)jl | (lane << 10) | ((unsigned)group << 15) | (mask << 18) | (rel << 22);
         return;
     }
-    // queue full (pathological inputs, e.g. lattices whose spacings sit on bin edges): resolve in line
-    const TileCtx &T = *reinterpret_cast<const TileCtx *>(S->ctx);
-    double *sT = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(S) + ((sizeof(FastShared) + 15) & ~size_t(15)));
-    unsigned *sh = reinterpret_cast<unsigned *>(sT + (T.A.n_bins + 1));
-    unsigned *copies = sh + T.A.ext_off * T.A.hist_ks;
-    resolve_entry(S, entry, uncount, sT, copies, copies + (threadIdx.x & (unsigned)(T.A.n_copies - 1)) * T.A.hist_cs);
+    unsigned char *t = S->ovf + ((unsigned)jl * (RF_THREADS / 32) + (unsigned)group) * 32u + lane;
+    *t = (unsigned char)(*t | mask | (rel << 4));
+    S->overflow = 1u;
 }
 
 // The hot loop after v is known: a pair is binned if v is clear of every bin edge, otherwise reported undecided.
@@ -875,18 +948,30 @@ __device__ __forceinline__ unsigned long long pk2(float lo, float hi)
 
 // filter_v for two particles (u, u + 1) against the same j: identical operations in identical order, issued as
 // packed FP32 (mul / fma .f32x2), so the values are bit-identical to the scalar form
-// the filter's v for two pairs from their packed coordinate differences (in 2^-32 box fractions)
-template <bool CUBIC>
+// the frame's constants (FrameFast), each twice in a 64-bit register pair (packed FP32 operands): separate values, not a
+// struct -- a struct captured by the row lambdas ends up in local memory
+#define RF_K_PARAMS unsigned long long kax, unsigned long long kay, unsigned long long kaz, unsigned long long kc0, \
+                    unsigned long long kbx, unsigned long long kcx, unsigned long long kcy
+#define RF_K_ARGS kax, kay, kaz, kc0, kbx, kcx, kcy
+
+// the filter's v for two pairs from their packed coordinate differences (in 2^-32 box fractions): filter_v_tail, packed
+template <int KIND>
 __device__ __forceinline__ unsigned long long filter_v2_tail(unsigned long long tx, unsigned long long ty, unsigned long long tz,
-                                                             unsigned long long fax, unsigned long long fay,
-                                                             unsigned long long faz, unsigned long long fc0)
+                                                             RF_K_PARAMS)
 {
     unsigned long long t2, v;
     float a, b, da, db;
-    if (!CUBIC) {
-        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(tx) : "l"(fax));
-        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(ty) : "l"(fay));
-        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(tz) : "l"(faz));
+    if (KIND == FK_TRI) {
+        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(tx) : "l"(kax));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(tx) : "l"(ty), "l"(kbx));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(tx) : "l"(tz), "l"(kcx));
+        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(ty) : "l"(kay));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ty) : "l"(tz), "l"(kcy));
+        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(tz) : "l"(kaz));
+    } else if (KIND == FK_ORTHO) {
+        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(tx) : "l"(kax));
+        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(ty) : "l"(kay));
+        asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(tz) : "l"(kaz));
     }
     asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t2) : "l"(tx));
     asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(t2) : "l"(ty));
@@ -895,35 +980,32 @@ __device__ __forceinline__ unsigned long long filter_v2_tail(unsigned long long 
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(da) : "f"(a));
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(db) : "f"(b));
     const unsigned long long d = pk2(da, db);
-    if (CUBIC) {
-        v = fc0;
-        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(v) : "l"(d), "l"(fax));
+    if (KIND == FK_CUBIC) {
+        v = kc0;
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(v) : "l"(d), "l"(kax));
     } else {
-        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(d), "l"(fc0));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(d), "l"(kc0));
     }
     return v;
 }
 
-template <bool CUBIC>
+template <int KIND>
 __device__ __forceinline__ unsigned long long filter_v2(uint32_t ujx, uint32_t ujy, uint32_t ujz, uint32_t ax0,
                                                         uint32_t ay0, uint32_t az0, uint32_t ax1, uint32_t ay1,
-                                                        uint32_t az1, unsigned long long fax, unsigned long long fay,
-                                                        unsigned long long faz, unsigned long long fc0)
+                                                        uint32_t az1, RF_K_PARAMS)
 {
     const unsigned long long tx = pk2((float)(int)(ujx - ax0), (float)(int)(ujx - ax1));
     const unsigned long long ty = pk2((float)(int)(ujy - ay0), (float)(int)(ujy - ay1));
     const unsigned long long tz = pk2((float)(int)(ujz - az0), (float)(int)(ujz - az1));
-    return filter_v2_tail<CUBIC>(tx, ty, tz, fax, fay, faz, fc0);
+    return filter_v2_tail<KIND>(tx, ty, tz, RF_K_ARGS);
 }
 
 // filter_v_rel for two particles: r = the row's FP32 coordinates relative to the centre of the group's box, n = MINUS the
 // two particles' (packed): three packed additions replace six integer subtractions and six conversions.  WRAP: rows at
 // the seam of the box (rel_wrap, packed).
-template <bool CUBIC, bool WRAP>
+template <int KIND, bool WRAP>
 __device__ __forceinline__ unsigned long long filter_v2_rel(float rx, float ry, float rz, unsigned long long nx,
-                                                            unsigned long long ny, unsigned long long nz,
-                                                            unsigned long long fax, unsigned long long fay,
-                                                            unsigned long long faz, unsigned long long fc0)
+                                                            unsigned long long ny, unsigned long long nz, RF_K_PARAMS)
 {
     unsigned long long tx, ty, tz;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(tx) : "l"(pk2(rx, rx)), "l"(nx));
@@ -944,7 +1026,7 @@ __device__ __forceinline__ unsigned long long filter_v2_rel(float rx, float ry, 
         asm("add.rn.f32x2 %0, %0, %1;" : "+l"(q) : "l"(nmg));
         asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(tz) : "l"(q), "l"(per));
     }
-    return filter_v2_tail<CUBIC>(tx, ty, tz, fax, fay, faz, fc0);
+    return filter_v2_tail<KIND>(tx, ty, tz, RF_K_ARGS);
 }
 
 // bin_or_flag for the four pairs of one row (two packed v's): the round-to-bin chain as six packed instructions,
@@ -1193,7 +1275,7 @@ __device__ __forceinline__ unsigned bin_count2(unsigned long long v, unsigned lo
     return any;
 }
 
-template <bool CHECK, bool CUBIC, bool EXCL, bool R0ZERO, bool CULL, bool EXT, bool L32>
+template <bool CHECK, int KIND, bool EXCL, bool R0ZERO, bool CULL, bool EXT, bool L32>
 __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S, int nj, uint32_t (&ux)[RF_IPT],
                                                 uint32_t (&uy)[RF_IPT], uint32_t (&uz)[RF_IPT],
                                                 int (&bi)[RF_IPT], const FrameFast &ff, float thr, unsigned B,
@@ -1206,8 +1288,9 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     const unsigned one = (unsigned)Tp->A.sym | 1u;
     constexpr bool HAS_OK = CHECK || EXCL;
     static_assert(RF_IPT == 4, "the undecided-pair mask is built for four particles per thread");
-    const unsigned long long fax = pk2(ff.ax, ff.ax), fay = pk2(ff.ay, ff.ay), faz = pk2(ff.az, ff.az);
-    const unsigned long long fc0 = pk2(ff.c0, ff.c0);
+    const unsigned long long kax = pk2(ff.ax, ff.ax), kay = pk2(ff.ay, ff.ay), kaz = pk2(ff.az, ff.az);
+    const unsigned long long kc0 = pk2(ff.c0, ff.c0);
+    const unsigned long long kbx = pk2(ff.bx, ff.bx), kcx = pk2(ff.cx, ff.cx), kcy = pk2(ff.cy, ff.cy);
     const unsigned long long magic = pk2(12582912.f, 12582912.f), nmagic = pk2(-12582912.f, -12582912.f);
     const unsigned long long neg1 = pk2(-1.f, -1.f);
     // R0ZERO: bits(w) is used as it is; bits(MAGIC) = 0x4B400000 moves into the limit and the base address
@@ -1231,10 +1314,8 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                 ok[u] = ok[u] && (ig < na) && (!diag || (j0 + j) > ig);
             }
         }
-        const unsigned long long v01 = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[0], uy[0], uz[0], ux[1], uy[1], uz[1], fax,
-                                                        fay, faz, fc0);
-        const unsigned long long v23 = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[2], uy[2], uz[2], ux[3], uy[3], uz[3], fax,
-                                                        fay, faz, fc0);
+        const unsigned long long v01 = filter_v2<KIND>(pj.x, pj.y, pj.z, ux[0], uy[0], uz[0], ux[1], uy[1], uz[1], RF_K_ARGS);
+        const unsigned long long v23 = filter_v2<KIND>(pj.x, pj.y, pj.z, ux[2], uy[2], uz[2], ux[3], uy[3], uz[3], RF_K_ARGS);
         float adf[4];
         const unsigned any = EXT ? bin_count4<HAS_OK, false, SH>(v01, v23, magic, nmagic, neg1, thr, hbase, trash_addr, one, ok, adf)
                                  : bin_or_flag4<HAS_OK, R0ZERO, CULL>(v01, v23, magic, nmagic, neg1, thr, blim, hbase,
@@ -1251,8 +1332,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     auto half_row = [&](int j, int H) {
         const uint4 pj = S->sj[j];
         const int a = 2 * H, b = 2 * H + 1;
-        const unsigned long long v = filter_v2<CUBIC>(pj.x, pj.y, pj.z, ux[a], uy[a], uz[a], ux[b], uy[b], uz[b], fax, fay,
-                                                      faz, fc0);
+        const unsigned long long v = filter_v2<KIND>(pj.x, pj.y, pj.z, ux[a], uy[a], uz[a], ux[b], uy[b], uz[b], RF_K_ARGS);
         float adf[2];
         if (bin_count2<false, SH>(v, magic, nmagic, neg1, thr, hbase, adf)) {
             unsigned und = 0;
@@ -1290,8 +1370,8 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     // One row, branch free: the four v's, the increments, whether any pair is undecided (adf: |v - rint(v)| per pair).
     auto vs_rel = [&](const float4 &r, auto wrap, unsigned long long (&v)[2]) {
         constexpr bool W = decltype(wrap)::value;
-        v[0] = filter_v2_rel<CUBIC, W>(r.x, r.y, r.z, nrel(ux, 0), nrel(uy, 0), nrel(uz, 0), fax, fay, faz, fc0);
-        v[1] = filter_v2_rel<CUBIC, W>(r.x, r.y, r.z, nrel(ux, 1), nrel(uy, 1), nrel(uz, 1), fax, fay, faz, fc0);
+        v[0] = filter_v2_rel<KIND, W>(r.x, r.y, r.z, nrel(ux, 0), nrel(uy, 0), nrel(uz, 0), RF_K_ARGS);
+        v[1] = filter_v2_rel<KIND, W>(r.x, r.y, r.z, nrel(ux, 1), nrel(uy, 1), nrel(uz, 1), RF_K_ARGS);
     };
     auto count_rel = [&](const unsigned long long (&v)[2], float (&adf)[4]) -> unsigned {
         const unsigned ok[RF_IPT] = {1u, 1u, 1u, 1u};
@@ -1329,7 +1409,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     auto half_row_rel = [&](int j, int c, int H, auto wrap) {
         constexpr bool W = decltype(wrap)::value;
         const float4 r = rel_row(j);
-        const unsigned long long v = filter_v2_rel<CUBIC, W>(r.x, r.y, r.z, nrel(ux, H), nrel(uy, H), nrel(uz, H), fax, fay, faz, fc0);
+        const unsigned long long v = filter_v2_rel<KIND, W>(r.x, r.y, r.z, nrel(ux, H), nrel(uy, H), nrel(uz, H), RF_K_ARGS);
         float adf[2];
         if (bin_count2<true, SH>(v, magic, nmagic, neg1, thr, hbase, adf)) {
             unsigned und = 0;
@@ -1390,7 +1470,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                 if ((threadIdx.x & 31u) == 0u) c = atomicAdd(&S->next_chunk[g], 1);
                 c = __shfl_sync(0xffffffffu, c, 0) * 32;
                 if (c >= nj) break;
-                if (boxes_apart(ib, S->jbox[c >> 5], S->cull)) continue;
+                if (boxes_apart(ib, S->jbox[c >> 5], S->cull, S->cull_tri != 0)) continue;
                 // then row by row (one test per lane): only the rows within reach of the group's box are evaluated
                 if (EXT && !HAS_OK) {
                     // ... and half row by half row: the group's first and last 64 particles have boxes of their own
@@ -1464,6 +1544,8 @@ rdf_pairs_fast(RdfArgs A)
         S->qcount = 0u;
         S->qcap = (unsigned)A.qcap;
         S->queue = sh + HS * A.n_copies;
+        S->ovf = A.ovf + (size_t)blockIdx.x * (RF_TJ * RF_THREADS);
+        S->overflow = 0u;
     }
     // Histogram copies are private to LANE groups, not to warps: bank conflicts and same-address serialisation only
     // arise among the 32 lanes of one ATOMS instruction, and neighbouring lanes (neighbouring particles in a sorted
@@ -1490,9 +1572,10 @@ rdf_pairs_fast(RdfArgs A)
         }
         const FrameFast ff = A.fast[f];
         const FrameBox fb = A.boxes[f];
+        const FrameTri *ftp = A.tri + f;   // read where it is needed: twenty registers otherwise
         if (A.tbox_a) {   // sorted frames: skip tile pairs that lie farther apart than the cutoff (same for all threads)
             const uint32_t *ta = A.tbox_a + ((int64_t)f * A.nti + I) * 6, *tb = A.tbox_b + ((int64_t)f * A.ntj + J) * 6;
-            if (tile_gap2(ta, tb, fb) > A.cull_r * A.cull_r) {
+            if (tile_gap2(ta, tb, fb, ftp) > A.cull_r * A.cull_r) {
                 __syncthreads();
                 continue;
             }
@@ -1564,7 +1647,8 @@ rdf_pairs_fast(RdfArgs A)
                 centre_half(lo2[0], hi2[0], ib + 4);
                 centre_half(lo2[1], hi2[1], ib + 6);
             }
-            if (threadIdx.x < 3) S->cull[threadIdx.x] = (float)(fb.box[threadIdx.x] * (1.0 / 4294967296.0));
+            if (threadIdx.x < 3) S->cull[threadIdx.x] = (float)((ftp->on ? ftp->w[threadIdx.x] : fb.box[threadIdx.x]) * (1.0 / 4294967296.0));
+            if (threadIdx.x == 4) S->cull_tri = ftp->on;
             if (threadIdx.x == 3) S->cull[3] = (float)(A.cull_r * A.cull_r);
             if (threadIdx.x >= 32 && threadIdx.x < 32 + RF_THREADS / 32) S->next_chunk[threadIdx.x - 32] = 0;
         }
@@ -1577,6 +1661,7 @@ rdf_pairs_fast(RdfArgs A)
             Tp->A = A;
             Tp->ff = ff;
             Tp->fb = fb;
+            Tp->ft = *ftp;
             Tp->i0 = i0;
             Tp->j0 = j0;
             Tp->f = f;
@@ -1603,13 +1688,18 @@ rdf_pairs_fast(RdfArgs A)
         else if (cull) { if (r0zero) RF_CALL2(C, Q, E, true, true, false, false); else RF_CALL2(C, Q, E, false, true, false, false); } \
         else { if (r0zero) RF_CALL2(C, Q, E, true, false, false, false); else RF_CALL2(C, Q, E, false, false, false, false); }        \
     } while (0)
+#define RF_KIND(C, E)                                            \
+    do {                                                         \
+        if (ff.kind == FK_CUBIC) RF_CALL(C, FK_CUBIC, E);        \
+        else if (ff.kind == FK_TRI) RF_CALL(C, FK_TRI, E);       \
+        else RF_CALL(C, FK_ORTHO, E);                            \
+    } while (0)
         if (check) {
-            if (ff.cubic) { if (excl) RF_CALL(true, true, true); else RF_CALL(true, true, false); }
-            else          { if (excl) RF_CALL(true, false, true); else RF_CALL(true, false, false); }
+            if (excl) RF_KIND(true, true); else RF_KIND(true, false);
         } else {
-            if (ff.cubic) { if (excl) RF_CALL(false, true, true); else RF_CALL(false, true, false); }
-            else          { if (excl) RF_CALL(false, false, true); else RF_CALL(false, false, false); }
+            if (excl) RF_KIND(false, true); else RF_KIND(false, false);
         }
+#undef RF_KIND
 #undef RF_CALL
 #undef RF_CALL2
         // resolve the undecided pairs of this tile with the reference's FP64 arithmetic
@@ -1617,8 +1707,26 @@ rdf_pairs_fast(RdfArgs A)
         const unsigned nq = min(S->qcount, S->qcap);
         for (unsigned e = threadIdx.x; e < nq; e += RF_THREADS)
             resolve_entry(S, S->queue[e], ext, sT, sh + A.ext_off * A.hist_ks, hist);
+        if (S->overflow) {   // block-uniform: rows that did not fit the queue, one byte per (row, group, lane)
+            unsigned *tab = reinterpret_cast<unsigned *>(S->ovf);
+            for (unsigned w = threadIdx.x; w < (unsigned)(RF_TJ * RF_THREADS / 4); w += RF_THREADS) {
+                unsigned four = tab[w];
+                if (!four) continue;
+                tab[w] = 0u;
+                for (unsigned b = 0; b < 4u; ++b, four >>= 8) {
+                    const unsigned v = four & 0xffu;
+                    if (!v) continue;
+                    const unsigned idx = 4u * w + b, jl = idx / RF_THREADS, gl = idx % RF_THREADS;   // gl = group * 32 + lane
+                    resolve_entry(S, jl | ((gl & 31u) << 10) | ((gl >> 5) << 15) | ((v & 15u) << 18) | ((v >> 4) << 22), ext, sT,
+                                  sh + A.ext_off * A.hist_ks, hist);
+                }
+            }
+        }
         __syncthreads();
-        if (threadIdx.x == 0) S->qcount = 0u;
+        if (threadIdx.x == 0) {
+            S->qcount = 0u;
+            S->overflow = 0u;
+        }
 
         if (++since_flush >= RF_FLUSH_ITEMS) {
             flush_hist(sh + A.ext_off * A.hist_ks, B, A.n_copies, weight, A.counts, true, A.hist_cs, A.hist_ks);
@@ -1652,6 +1760,7 @@ struct mdc_rdf_plan {
     Thresholds th;
     DevBuf<double> T;
     DevBuf<unsigned long long> counts, ticket;
+    DevBuf<unsigned char> ovf;         // filter kernel: overflow tables, one per block of the persistent grid, kept zero
     DevBuf<float> raw_a[2], raw_b[2], soa_a[2], soa_b[2];
     DevBuf<uint32_t> fix_a[2], fix_b[2];
     DevBuf<unsigned> absmax[2];        // (2 groups, {max x, max -x}, fblk): coordinate extents per frame
@@ -1681,6 +1790,7 @@ void rdf_free(mdc_rdf_plan *p)
     p->T.release();
     p->counts.release();
     p->ticket.release();
+    p->ovf.release();
     for (int i = 0; i < 2; ++i) {
         p->raw_a[i].release();
         p->raw_b[i].release();
@@ -1754,6 +1864,13 @@ bool triclinic_vectors(const float *b, FrameTri &t)
     t.cx = (double)(float)cx;
     t.cy = (double)(float)cy;
     t.cz = (double)(float)cz;
+    // perpendicular widths: volume / area of the opposite face (a x b = (0, 0, ax by), c x a = (0, cz ax, -cy ax),
+    // b x c = (by cz, -bx cz, bx cy - by cx))
+    const double vol = t.ax * t.by * t.cz;
+    const double bc = sqrt(t.by * t.cz * t.by * t.cz + t.bx * t.cz * t.bx * t.cz + (t.bx * t.cy - t.by * t.cx) * (t.bx * t.cy - t.by * t.cx));
+    t.w[0] = vol / bc;
+    t.w[1] = vol / (fabs(t.ax) * sqrt(t.cz * t.cz + t.cy * t.cy));
+    t.w[2] = fabs(t.cz);
     t.on = 1;
     t.pad = 0;
     return true;
@@ -1934,22 +2051,34 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
             ++launches;
         }
         rdf_frame_params<<<(unsigned)ceil_div(F, 64), 64, 0, sc>>>(
-            p->boxes[slot].p, p->absmax[slot].p, p->absmax[slot].p + (rb ? 2 * p->fblk : 0), p->fblk, F, p->n_bins, p->r0, p->r1,
+            p->boxes[slot].p, p->tri[slot].p, p->absmax[slot].p, p->absmax[slot].p + (rb ? 2 * p->fblk : 0), p->fblk, F, p->n_bins, p->r0, p->r1,
             p->fast[slot].p);
         ++launches;
         // the filter kernel needs an orthorhombic cell, three periodic axes and a bin coordinate below 2^22 in every frame
         // (triclinic frames take the exact kernel: minimum_image_triclinic in FP64 for every pair)
+        // (triclinic frames: the filter's image is the wrap of the fractional differences, which is the reference's
+        // minimum image for cutoffs below half the smallest width of the cell -- rdf_frame_params; wider windows take
+        // the exact kernel: minimum_image_triclinic in FP64 for every pair)
         bool fast = !p->force_exact;
-        for (int f = 0; f < F && fast; ++f) fast = ht[f0 + f].on == 0;
+        static const bool tri_filter_off = getenv("MDC_RDF_TRI_FILTER") && getenv("MDC_RDF_TRI_FILTER")[0] == '0';
         double max_len = 0.0, v_far_max = 0.0;
         for (int f = 0; f < F && fast; ++f) {
             const FrameBox &fb = hb[f0 + f];
+            const FrameTri &ft = ht[f0 + f];
             const double S = (double)p->n_bins / (p->r1 - p->r0);
-            const double v_far = 0.5 * sqrt(fb.box[0] * fb.box[0] + fb.box[1] * fb.box[1] + fb.box[2] * fb.box[2]) * S +
-                                 fabs(p->r0 * S) + 1.0;
-            fast = fb.pbc[0] && fb.pbc[1] && fb.pbc[2] && v_far < 4.0e6;
+            double v_far;
+            if (ft.on) {
+                const double Lsum = fabs(ft.ax) + sqrt(ft.bx * ft.bx + ft.by * ft.by) + sqrt(ft.cx * ft.cx + ft.cy * ft.cy + ft.cz * ft.cz);
+                const double wmin = std::min(ft.w[0], std::min(ft.w[1], ft.w[2]));
+                v_far = 0.5 * Lsum * S + fabs(p->r0 * S) + 1.0;
+                fast = !tri_filter_off && p->r1 * (1.0 + 1e-4) + 1e-5 * Lsum < 0.5 * wmin && v_far < 4.0e6;
+                max_len = std::max(max_len, Lsum);
+            } else {
+                v_far = 0.5 * sqrt(fb.box[0] * fb.box[0] + fb.box[1] * fb.box[1] + fb.box[2] * fb.box[2]) * S + fabs(p->r0 * S) + 1.0;
+                fast = fb.pbc[0] && fb.pbc[1] && fb.pbc[2] && v_far < 4.0e6;
+                for (int k = 0; k < 3; ++k) max_len = std::max(max_len, fb.box[k]);
+            }
             v_far_max = std::max(v_far_max, v_far);
-            for (int k = 0; k < 3; ++k) max_len = std::max(max_len, fb.box[k]);
         }
         // Put every frame in Hilbert order of a cell grid, so that runs of consecutive particles are compact regions,
         // and let the pair kernel skip what lies farther apart than the cutoff: whole tile pairs, and inside a tile
@@ -2066,6 +2195,15 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         A.sym = p->sym ? 1 : 0;
         A.items_per_frame = p->sym ? (int64_t)A.nti * (A.nti / 2 + 1) : (int64_t)A.nti * A.ntj;
         const int64_t total = A.items_per_frame * F;
+        A.ovf = nullptr;
+        if (fast) {   // (before the timed region: the allocation blocks the host)
+            const size_t ovf_bytes = (size_t)p->ctx->sm_count * p->occ_fast * RF_TJ * RF_THREADS;
+            if (p->ovf.n < ovf_bytes) {   // first filtered push: the tables start (and are left) all zero
+                MDC_CHECK(p->ovf.alloc(ovf_bytes));
+                MDC_CUDA(cudaMemsetAsync(p->ovf.p, 0, ovf_bytes, sk));
+            }
+            A.ovf = p->ovf.p;
+        }
         const int ti = p->st.n_timed < 8 ? p->st.n_timed : -1;
         if (ti >= 0) MDC_CUDA(cudaEventRecord(p->st.k0[ti], sk));
         if (fast) {

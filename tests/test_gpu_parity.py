@@ -219,6 +219,43 @@ def test_rdf_triclinic_golden_and_vs_oracle(ctx):
         radial_histogram(a, a, n_bins=10, range_=(0.0, 3.0), dimensions=np.array([10, 10, 10, 30, 100, 160], np.float32))
 
 
+def _cell_widths(m):
+    """Perpendicular widths of the cell with row vectors ``m`` (distance between opposite faces)."""
+    vol = abs(np.linalg.det(m))
+    return np.array([vol / np.linalg.norm(np.cross(m[(k + 1) % 3], m[(k + 2) % 3])) for k in range(3)])
+
+
+@pytest.mark.parametrize("box,n_a,n_b,excl,n_bins,frac", [
+    ([30.0, 28.0, 33.0, 60, 90, 75], 6000, None, (1, 1), 200, 0.499),      # sorted frames, relative rows, extended histograms
+    ([30.0, 28.0, 33.0, 60, 90, 75], 2500, None, None, 90, 0.49),          # below the sort threshold
+    ([22.0, 25.0, 21.0, 70, 110, 95], 4500, 5200, (2, 3), 128, 0.45),      # two groups, exclusion
+    ([40.0, 40.0, 40.0, 50, 65, 55], 7000, None, (1, 1), 300, 0.2),        # strongly skewed cell, small cutoff (culling)
+    ([18.0, 18.0, 18.0, 90, 90, 120], 4100, None, (1, 1), 64, 0.48),       # hexagonal
+    ([25.0, 25.0, 25.0, 80, 95, 100], 5000, None, None, 2000, 0.3),        # narrow bins (range-tested loop)
+])
+def test_rdf_triclinic_filter_vs_oracle(box, n_a, n_b, excl, n_bins, frac):
+    """Triclinic cells with the window below half the smallest width of the cell: these frames take the FILTER kernel
+    (minimum image = wrap of the fractional differences; undecided pairs resolved with minimum_image_triclinic in
+    FP64) and must give the reference's counts bit for bit (oracle.c: orc_radial_histogram_triclinic).  Coordinates far
+    outside the primary cell; a lattice along the cell vectors puts separations on bin edges."""
+    from mdcraft_b200.analysis.structure import radial_histogram
+    from oracle import oracle
+
+    rng = np.random.default_rng(n_a + n_bins)
+    box = np.array(box, np.float32)
+    m = oracle.triclinic_vectors(box).astype(np.float64)
+    a = ((rng.random((n_a, 3)) * 5 - 2) @ m).astype(np.float32)
+    a[: n_a // 8] = ((np.round(rng.random((n_a // 8, 3)) * 16) / 16) @ m).astype(np.float32)   # lattice points
+    b = a if n_b is None else ((rng.random((n_b, 3)) * 3 - 1) @ m).astype(np.float32)
+    rcut = (0.0, frac * float(_cell_widths(m).min()))
+    got = radial_histogram(a, b, n_bins=n_bins, range_=rcut, dimensions=box, exclusion=excl)
+    np.testing.assert_array_equal(got, oracle.radial_histogram(a, b, n_bins, rcut, box, exclusion=excl))
+    # a window that starts above zero, and one beyond half the width (exact kernel)
+    for r0, r1 in ((0.3 * rcut[1], rcut[1]), (0.0, 0.62 * float(_cell_widths(m).min()))):
+        got = radial_histogram(a[:3000], b[:3500], n_bins=57, range_=(r0, r1), dimensions=box, exclusion=excl)
+        np.testing.assert_array_equal(got, oracle.radial_histogram(a[:3000], b[:3500], 57, (r0, r1), box, exclusion=excl))
+
+
 @pytest.mark.parametrize("n,n_bins,frac", [(1, 8, 0.5), (2, 8, 0.5), (511, 33, 0.5), (512, 200, 0.5), (513, 200, 0.37),
                                            (1025, 1000, 0.5), (3000, 200, 0.5), (2049, 4096, 0.45),
                                            (4096, 200, 0.5), (4097, 64, 0.3), (5121, 300, 0.5), (6000, 3000, 0.2),
