@@ -658,7 +658,8 @@ def other_configs(ctx, flush):
     out = {}
 
     def timed(push, plans, reset=True):
-        push()                      # warm-up (allocations, tables)
+        push()                      # warm-up: twice, a plan has two staging slots and sizes each at its first use
+        push()
         ctx.synchronize()
         for p in plans:
             p.reset()
