@@ -94,6 +94,32 @@ def test_rdf_filter_margin_with_unwrapped_coordinates(ctx, n_bins, lo, hi):
     np.testing.assert_array_equal(slab, oracle.radial_histogram(wrapped[:256], wrapped, n_bins, window, box))
 
 
+@pytest.mark.parametrize("n,n_bins,frac,tri", [(6000, 30_000, 0.45, False), (5000, 30_000, 0.012, False), (4500, 20_000, 0.45, True)])
+def test_rdf_overflow_of_the_undecided_row_queue(ctx, n, n_bins, frac, tri):
+    """Bins so narrow that the filter's margin is a large part of a bin (or exceeds half of it: the frame is then not
+    usable and EVERY pair is undecided): far more undecided rows per tile pair than the shared-memory queue holds, so
+    they take the per-block overflow table in global memory (park_row) and are resolved from there.  Counts must still
+    be the exact kernel's and the oracle's; orthorhombic and triclinic cells."""
+    from oracle import oracle
+
+    rng = np.random.default_rng(n)
+    if tri:
+        box = np.array([22.0, 20.0, 24.0, 70, 100, 80], np.float32)
+        m = oracle.triclinic_vectors(box).astype(np.float64)
+        pos = ((rng.random((n, 3)) * 3 - 1) @ m).astype(np.float32)
+        vol = abs(np.linalg.det(m))
+        w = min(vol / np.linalg.norm(np.cross(m[(k + 1) % 3], m[(k + 2) % 3])) for k in range(3))
+        window = (0.0, frac * w)
+    else:
+        L = 25.0
+        box = np.array([L, L * 1.05, L * 0.97, 90, 90, 90], np.float32)
+        pos = (rng.random((n, 3)) * box[:3]).astype(np.float32)
+        window = (0.0, frac * L)
+    fast = _rdf_counts(ctx, pos, None, box, n_bins, window, exclusion=(1, 1))
+    np.testing.assert_array_equal(fast, _rdf_counts(ctx, pos, None, box, n_bins, window, exclusion=(1, 1), exact=True))
+    np.testing.assert_array_equal(fast, oracle.radial_histogram(pos, pos, n_bins, window, box, exclusion=(1, 1)))
+
+
 def test_c4_binary_electrolyte_partials(ctx):
     """C4: 100k cations + 100k anions: ++, +-, -- g(r) and the partial S(q) sum rule."""
     from mdcraft_b200 import _capi
