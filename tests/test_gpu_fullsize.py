@@ -94,7 +94,7 @@ def test_rdf_filter_margin_with_unwrapped_coordinates(ctx, n_bins, lo, hi):
     np.testing.assert_array_equal(slab, oracle.radial_histogram(wrapped[:256], wrapped, n_bins, window, box))
 
 
-@pytest.mark.parametrize("n,n_bins,frac,tri", [(6000, 30_000, 0.45, False), (5000, 30_000, 0.012, False), (4500, 20_000, 0.45, True)])
+@pytest.mark.parametrize("n,n_bins,frac,tri", [(6000, 12_000, 0.45, False), (5000, 12_000, 0.006, False), (4500, 12_000, 0.45, True)])
 def test_rdf_overflow_of_the_undecided_row_queue(ctx, n, n_bins, frac, tri):
     """Bins so narrow that the filter's margin is a large part of a bin (or exceeds half of it: the frame is then not
     usable and EVERY pair is undecided): far more undecided rows per tile pair than the shared-memory queue holds, so
