@@ -233,23 +233,27 @@ int  mdc_rdf_plan_destroy(mdc_rdf_plan *plan);
  * Accumulates n_frames frames.  pos_a f32 (n_frames, n_a, 3); pos_b f32
  * (n_frames, n_b, 3) or NULL when same_group; box f32 (n_frames, 6)
  * [lx, ly, lz, alpha, beta, gamma] (host memory always).  The reference hands all six values to capped_distance
- * (structure.py:109-115).  Orthorhombic frames (90/90/90) go through the FP32 filter + FP64 kernel pair; frames with
- * any other angle take MDAnalysis' triclinic routine in FP64 for every pair (triclinic_vectors, _triclinic_pbc,
- * minimum_image_triclinic: coordinates moved into the primary cell, then the shortest of the 27 nearest images), about
- * 40x slower per pair.  MDC_ERR_INVALID for angles that do not describe a cell.
+ * (structure.py:109-115).  Frames go through the FP32 filter kernel, which resolves the pairs it cannot decide with the
+ * reference's FP64 arithmetic: orthorhombic frames (90/90/90) always; frames with any other angle (MDAnalysis' triclinic
+ * routine: triclinic_vectors, _triclinic_pbc, minimum_image_triclinic -- coordinates moved into the primary cell, then the
+ * shortest of the 27 nearest images) when r1 is below half the smallest width of the cell, where the wrap of the
+ * fractional differences is that image; wider windows, non-periodic axes and MDC_RDF_EXACT=1 take the FP64 kernel for
+ * every pair (~20-40x slower per pair).  MDC_ERR_INVALID for angles that do not describe a cell.
  * Groups of 4096 particles or more are put in Hilbert order of a cell grid on the device first, and the pair kernel
  * skips the blocks of pairs farther apart than r1 (what capped_distance's grid search does for the reference,
  * structure.py:109-115); counts do not depend on it.  Environment, for diagnostics: MDC_RDF_SORT=0 keeps the original
- * order, MDC_RDF_EXT=0 the range-tested histogram update, MDC_RDF_EXACT=1 the all-FP64 kernel.
+ * order, MDC_RDF_EXT=0 the range-tested histogram update, MDC_RDF_EXACT=1 the all-FP64 kernel, MDC_RDF_REL=0 the integer
+ * form of the coordinate differences, MDC_RDF_L32=0 eight histogram copies instead of one per bank, MDC_RDF_TRI_FILTER=0
+ * the FP64 kernel for every triclinic frame.
  */
 int  mdc_rdf_push(mdc_rdf_plan *plan, const float *pos_a, const float *pos_b,
                   const float *box, int n_frames, int on_device);
 
 int  mdc_rdf_read(mdc_rdf_plan *plan, int64_t *counts_out, int64_t *n_frames_out);
 /*
- * The pair kernel is a persistent grid that fills every SM (4 blocks per SM at 200 bins).  blocks_per_sm > 0 caps it,
- * leaving register file / shared memory on every SM for the kernels of ANOTHER context queued at the same time (the
- * S(q) NUFFT kernels are sized to fit one such slot): the two analyses then run side by side.  0 = all that fit.
+ * The pair kernel is a persistent grid that fills every SM (3 blocks of 80 registers x 256 threads per SM).
+ * blocks_per_sm > 0 caps it, leaving register file / shared memory on every SM for the kernels of ANOTHER context
+ * queued at the same time, which then run side by side with it.  0 = all that fit.
  */
 int  mdc_rdf_set_blocks_per_sm(mdc_rdf_plan *plan, int blocks_per_sm);
 int  mdc_rdf_reset(mdc_rdf_plan *plan);
