@@ -18,11 +18,12 @@ what the reference's ``ts.positions[i] = tuple(str)`` stores.
 that it can be handed straight to the S(q) / g(r) plans (``_capi.SqPlan.push`` /
 ``_capi.RdfPlan.push``) without a host round trip.
 
-Supported dump layouts (anything else raises): orthogonal boxes; unscaled
-coordinates, wrapped (``x y z``) or unwrapped (``xu yu zu``); with or without
-``id``; a constant number of atoms.  ``unwrap=True`` (image flags), scaled
-coordinates (``xs``, ``xsu``), triclinic boxes, ``style grid`` dumps and ``extras``
-are not: for scaled or unwrapped coordinates the reference adds the box origin to
+Supported dump layouts (anything else raises): orthogonal and restricted
+triclinic boxes (``ITEM: BOX BOUNDS xy xz yz``: the dimensions are formed as the
+reference does, ``reader.py:372-388``); unscaled coordinates, wrapped (``x y z``)
+or unwrapped (``xu yu zu``); with or without ``id``; a constant number of atoms.
+``unwrap=True`` (image flags), scaled coordinates (``xs``, ``xsu``), general
+triclinic boxes (``abc origin``), ``style grid`` dumps and ``extras`` are not: for scaled or unwrapped coordinates the reference adds the box origin to
 EVERY atom once per atom (``reader.py:524-526`` sits inside the per-atom loop), so
 there is no well-defined reference result to match unless the origin is zero.
 """

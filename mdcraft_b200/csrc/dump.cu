@@ -592,16 +592,47 @@ extern "C" int mdc_dump_open(const char *path, const char *conventions, int n_th
             return dump_fail(d, MDC_ERR_INVALID, "Timestep " + std::to_string(d->steps[f]) + " has " + std::to_string(n) +
                                                      " atoms, but the topology has " + std::to_string(d->n_atoms) + " atoms.");
         const std::string bb(h[4].b, h[4].e);
-        if (bb.find("xy xz yz") != std::string::npos || bb.find("abc origin") != std::string::npos)
-            return dump_fail(d, MDC_ERR_UNSUPPORTED, "mdc_dump_open: triclinic boxes are not supported");
+        if (bb.find("abc origin") != std::string::npos)
+            return dump_fail(d, MDC_ERR_UNSUPPORTED, "mdc_dump_open: general triclinic boxes (abc origin) are not supported");
+        const bool tri = bb.find("xy xz yz") != std::string::npos;   // restricted triclinic: lo hi tilt per line (reader.py:372-375)
+        double lo[3], hi[3], tilt[3] = {0.0, 0.0, 0.0};
         for (int ax = 0; ax < 3; ++ax) {
             const std::string l(h[5 + ax].b, h[5 + ax].e);
-            char *e1 = nullptr, *e2 = nullptr;
-            const double lo = strtod(l.c_str(), &e1), hi = strtod(e1, &e2);
+            char *e1 = nullptr, *e2 = nullptr, *e3 = nullptr;
+            lo[ax] = strtod(l.c_str(), &e1);
+            hi[ax] = strtod(e1, &e2);
             if (e1 == l.c_str() || e2 == e1) return dump_fail(d, MDC_ERR_INVALID, "mdc_dump_open: bad box bounds");
-            d->box[f * 6 + ax] = (float)(hi - lo);   // reader.py:418, stored by MDAnalysis as float32
-            d->box[f * 6 + 3 + ax] = 90.f;
-            d->origin[f * 3 + ax] = lo;
+            if (tri) {
+                tilt[ax] = strtod(e2, &e3);
+                if (e3 == e2) return dump_fail(d, MDC_ERR_INVALID, "mdc_dump_open: bad box bounds (tilt factor missing)");
+            }
+        }
+        if (!tri) {
+            for (int ax = 0; ax < 3; ++ax) {
+                d->box[f * 6 + ax] = (float)(hi[ax] - lo[ax]);   // reader.py:418, stored by MDAnalysis as float32
+                d->box[f * 6 + 3 + ax] = 90.f;
+                d->origin[f * 3 + ax] = lo[ax];
+            }
+        } else {
+            // reader.py:376-388: the bounds of a tilted box hold its extent, take the tilts back out; box vectors
+            // a = (lx, 0, 0), b = (xy, ly, 0), c = (xz, yz, lz); convert_cell_representation (algorithm/topology.py:
+            // 743-757): lengths = norms, angles = degrees(arccos(dot / (|u| |v|))), float64, stored as float32
+            const double xy = tilt[0], xz = tilt[1], yz = tilt[2];
+            lo[0] -= std::min(std::min(0.0, xy), std::min(xz, xy + xz));
+            hi[0] -= std::max(std::max(0.0, xy), std::max(xz, xy + xz));
+            lo[1] -= std::min(0.0, yz);
+            hi[1] -= std::max(0.0, yz);
+            const double a[3] = {hi[0] - lo[0], 0.0, 0.0}, b[3] = {xy, hi[1] - lo[1], 0.0}, c[3] = {xz, yz, hi[2] - lo[2]};
+            auto norm = [](const double *v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+            auto dot = [](const double *u, const double *v) { return u[0] * v[0] + u[1] * v[1] + u[2] * v[2]; };
+            const double la = norm(a), lb = norm(b), lc = norm(c), deg = 180.0 / 3.141592653589793;
+            d->box[f * 6 + 0] = (float)la;
+            d->box[f * 6 + 1] = (float)lb;
+            d->box[f * 6 + 2] = (float)lc;
+            d->box[f * 6 + 3] = (float)(acos(dot(b, c) / (lb * lc)) * deg);
+            d->box[f * 6 + 4] = (float)(acos(dot(a, c) / (la * lc)) * deg);
+            d->box[f * 6 + 5] = (float)(acos(dot(a, b) / (la * lb)) * deg);
+            for (int ax = 0; ax < 3; ++ax) d->origin[f * 3 + ax] = lo[ax];
         }
         if ((size_t)(h[8].e - h[8].b) != d->atoms_header.size() || memcmp(h[8].b, d->atoms_header.data(), d->atoms_header.size()) != 0)
             return dump_fail(d, MDC_ERR_UNSUPPORTED, "mdc_dump_open: the ATOMS columns change between frames");

@@ -577,7 +577,7 @@ def rdf(
 def read_lammps_dump(path: str, dt: float = 1.0):
     """
     CPU restatement of ``LAMMPSDumpTrajectoryReader`` (reader.py:353-562) for the layouts the GPU reader takes:
-    orthogonal box, unscaled coordinates, optional ids.  Pure Python (small files only); pinned by
+    orthogonal or restricted triclinic (xy xz yz) box, unscaled coordinates, optional ids.  Pure Python (small files only); pinned by
     tests/golden/dumps.npz, which the reference's own reader produced.
 
     Returns ``positions f32 (F, N, 3)``, ``dimensions f32 (F, 6)``, ``steps i64 (F,)``, ``times f64 (F,)``,
@@ -598,7 +598,21 @@ def read_lammps_dump(path: str, dt: float = 1.0):
         offsets.append(int(starts[i]))
         steps.append(int(lines[i + 1]))
         bounds = [[float(v) for v in lines[i + 5 + ax].split()] for ax in range(3)]                # reader.py:415-417
-        dims.append(np.array([b[1] - b[0] for b in bounds] + [90, 90, 90]).astype(np.float32))       # :418
+        if b"xy xz yz" in lines[i + 4]:                                                              # :372-388
+            (xlo, xhi, xy), (ylo, yhi, xz), (zlo, zhi, yz) = bounds
+            xlo -= min(0, xy, xz, xy + xz)
+            xhi -= max(0, xy, xz, xy + xz)
+            ylo -= min(0, yz)
+            yhi -= max(0, yz)
+            vec = np.array([[xhi - xlo, 0, 0], [xy, yhi - ylo, 0], [xz, yz, zhi - zlo]], dtype=float)
+            par = np.empty(6)                                                 # algorithm/topology.py:743-757
+            par[:3] = np.linalg.norm(vec, axis=1)
+            par[3] = np.degrees(np.arccos(np.dot(vec[1], vec[2]) / (par[1] * par[2])))
+            par[4] = np.degrees(np.arccos(np.dot(vec[0], vec[2]) / (par[0] * par[2])))
+            par[5] = np.degrees(np.arccos(np.dot(vec[0], vec[1]) / (par[0] * par[1])))
+            dims.append(par.astype(np.float32))
+        else:
+            dims.append(np.array([b[1] - b[0] for b in bounds] + [90, 90, 90]).astype(np.float32))   # :418
         cols = {a.decode(): k for k, a in enumerate(lines[i + 8].split()[2:])}                       # :425
         axes = []
         for ax in "xyz":                                                                            # :438-447

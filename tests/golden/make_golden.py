@@ -238,14 +238,17 @@ def transforms():
     save("transforms.npz", **out)
 
 
-def write_dump(path, pos, ids, box_lo, box_hi, steps, columns, fmt, extra=None, literal=None):
-    """A LAMMPS text dump: pos (F, N, 3) written with the per-frame format functions fmt[f](value) -> str."""
+def write_dump(path, pos, ids, box_lo, box_hi, steps, columns, fmt, extra=None, literal=None, tilt=None):
+    """A LAMMPS text dump: pos (F, N, 3) written with the per-frame format functions fmt[f](value) -> str.
+    tilt (F, 3) = (xy, xz, yz): restricted triclinic boxes, box_lo / box_hi are then the BOUNDS LAMMPS writes."""
     F, N, _ = pos.shape
     with open(path, "w") as fh:
         for f in range(F):
-            fh.write(f"ITEM: TIMESTEP\n{steps[f]}\nITEM: NUMBER OF ATOMS\n{N}\nITEM: BOX BOUNDS pp pp pp\n")
+            kind = "xy xz yz pp pp pp" if tilt is not None else "pp pp pp"
+            fh.write(f"ITEM: TIMESTEP\n{steps[f]}\nITEM: NUMBER OF ATOMS\n{N}\nITEM: BOX BOUNDS {kind}\n")
             for ax in range(3):
-                fh.write(f"{float(box_lo[f][ax])!r} {float(box_hi[f][ax])!r}\n")
+                t = f" {float(tilt[f][ax])!r}" if tilt is not None else ""
+                fh.write(f"{float(box_lo[f][ax])!r} {float(box_hi[f][ax])!r}{t}\n")
             fh.write("ITEM: ATOMS " + " ".join(columns) + "\n")
             for i in range(N):
                 fields = []
@@ -291,7 +294,20 @@ def dumps():
     c = os.path.join(HERE, "dump_sparse_ids.lammpsdump")
     sparse = np.stack([rng.permutation(np.arange(N) * 7 + 3) for _ in range(F)])
     write_dump(c, pos, sparse, lo, hi, steps, ["x", "y", "z", "id"], fmts, extra)
-    for tag, path in (("ids", a), ("noid", b), ("sparse", c)):
+    # (d) restricted triclinic boxes (ITEM: BOX BOUNDS xy xz yz): bounds = extent of the tilted box, as LAMMPS writes them
+    d = os.path.join(HERE, "dump_triclinic.lammpsdump")
+    rng_t = np.random.default_rng(78)
+    edge = 18.0 + 4.0 * rng_t.random((F, 3))
+    tilt = (rng_t.random((F, 3)) - 0.5) * 0.9 * edge[:, [0, 0, 1]]
+    tilt[1] = [0.0, -3.5, 0.0]                      # one tilt only
+    tilt[2, 0] = 0.0
+    org = rng_t.normal(size=(F, 3)) - 5.0
+    xy, xz, yz = tilt[:, 0], tilt[:, 1], tilt[:, 2]
+    zero = np.zeros(F)
+    tlo = org + np.stack([np.min([zero, xy, xz, xy + xz], axis=0), np.minimum(0, yz), zero], axis=1)
+    thi = org + edge + np.stack([np.max([zero, xy, xz, xy + xz], axis=0), np.maximum(0, yz), zero], axis=1)
+    write_dump(d, pos, ids, tlo, thi, steps, ["id", "x", "y", "z"], fmts, extra, tilt=tilt)
+    for tag, path in (("ids", a), ("noid", b), ("sparse", c), ("triclinic", d)):
         r = rd.LAMMPSDumpTrajectoryReader(path, dt=0.005)
         got_pos, got_dim, got_step, got_time = [], [], [], []
         for f in range(r.n_frames):

@@ -718,7 +718,8 @@ def test_scsf_golden(precision, algorithm):
 # --------------------------------------------------------------------------- frame ingest (§8f rank 4)
 
 
-@pytest.mark.parametrize("tag,name", [("ids", "dump_ids"), ("noid", "dump_noid"), ("sparse", "dump_sparse_ids")])
+@pytest.mark.parametrize("tag,name", [("ids", "dump_ids"), ("noid", "dump_noid"), ("sparse", "dump_sparse_ids"),
+                                      ("triclinic", "dump_triclinic")])
 def test_dump_reader_golden(tag, name):
     """LAMMPS dumps parsed on the GPU against what the reference's own reader read from the same files: positions
     bit for bit (double-rounded literals, > 2^53 mantissas, nan / inf through the host parser), boxes, steps, times."""
@@ -737,7 +738,7 @@ def test_dump_reader_golden(tag, name):
         np.testing.assert_array_equal(ts.dimensions, g[f"{tag}_dimensions"][f])
         assert ts.frame == f and ts.data["step"] == g[f"{tag}_steps"][f] and ts.time == g[f"{tag}_times"][f]
     np.testing.assert_array_equal(r.frames_block(0, 5), g[f"{tag}_positions"])
-    if tag != "sparse":                           # the literals of frame 0 that the exact fast path refuses
+    if tag not in ("sparse", "triclinic"):        # the literals of frame 0 that the exact fast path refuses
         assert r.host_parsed_values() >= 5
     np.testing.assert_array_equal(r.frames_block(1, 5), g[f"{tag}_positions"][1:])
     assert r.host_parsed_values() <= 1            # %.17g, %e, %f and repr() output all take the device path
@@ -833,6 +834,47 @@ def test_dump_reader_feeds_the_analysis_classes(tmp_path):
     counts, _ = plan.read()
     np.testing.assert_array_equal(counts, _rdf(u_mem.atoms, n_bins=100, range_=(0.0, L / 2), exclusion=(1, 1)).results.counts)
     plan.close()
+    r.close()
+
+
+def test_triclinic_dump_to_rdf(tmp_path):
+    """A LAMMPS dump with restricted triclinic boxes (xy xz yz) that change from frame to frame: GPU reader -> device
+    blocks -> g(r) (filter kernel on the fractional coordinates) against the CPU oracle on what the oracle's reader
+    read from the same file, counts bit for bit; and the reference's rdf normalisation through the classes."""
+    from mdcraft_b200 import synthetic
+    from mdcraft_b200.analysis.reader import LAMMPSDumpTrajectoryReader
+    from oracle import oracle
+
+    n, F = 4500, 3
+    rng = np.random.default_rng(31)
+    path = tmp_path / "tri.lammpsdump"
+    with open(path, "w") as fh:
+        for f in range(F):
+            lx, ly, lz = 17.0 + f, 16.0 + 0.5 * f, 18.0
+            xy, xz, yz = 4.0 - f, -3.0, 2.5 + 0.25 * f
+            org = rng.normal(size=3)
+            blo = org + [min(0, xy, xz, xy + xz), min(0, yz), 0]
+            bhi = org + [lx, ly, lz] + np.array([max(0, xy, xz, xy + xz), max(0, yz), 0])
+            fh.write(f"ITEM: TIMESTEP\n{10 * f}\nITEM: NUMBER OF ATOMS\n{n}\nITEM: BOX BOUNDS xy xz yz pp pp pp\n")
+            fh.write("%r %r %r\n%r %r %r\n%r %r %r\n" % (float(blo[0]), float(bhi[0]), xy, float(blo[1]), float(bhi[1]), xz,
+                                                      float(blo[2]), float(bhi[2]), yz))
+            fh.write("ITEM: ATOMS id x y z\n")
+            cell = np.array([[lx, 0, 0], [xy, ly, 0], [xz, yz, lz]])
+            pos = org + rng.random((n, 3)) @ cell
+            for i in rng.permutation(n):
+                fh.write("%d %.9g %.9g %.9g\n" % (i + 1, *pos[i]))
+    want_pos, dims, _, _, _ = oracle.read_lammps_dump(str(path))
+    r = LAMMPSDumpTrajectoryReader(str(path), frame_block=2)
+    np.testing.assert_array_equal(r.frames_block(0, F), want_pos)
+    np.testing.assert_array_equal(np.stack([ts.dimensions for ts in r]), dims)
+    assert not np.any(dims[:, 3:] == 90.0)
+    u = synthetic.Universe(r)
+    window = (0.0, 7.0)                       # below half the smallest width of every frame's cell
+    a = _rdf(u.atoms, n_bins=140, range_=window, exclusion=(1, 1))
+    want = sum(oracle.radial_histogram(want_pos[f], want_pos[f], 140, window, dims[f], exclusion=(1, 1)) for f in range(F))
+    np.testing.assert_array_equal(a.results.counts, want)
+    b = _rdf(universe_from(want_pos, dims).atoms, n_bins=140, range_=window, exclusion=(1, 1))
+    np.testing.assert_array_equal(a.results.rdf, b.results.rdf)
     r.close()
 
 

@@ -247,7 +247,8 @@ def test_dump_index_and_headers_on_the_host(tmp_path):
     from mdcraft_b200 import _capi
 
     g = golden("dumps.npz")
-    for tag, name, has_id in (("ids", "dump_ids", True), ("noid", "dump_noid", False), ("sparse", "dump_sparse_ids", True)):
+    for tag, name, has_id in (("ids", "dump_ids", True), ("noid", "dump_noid", False), ("sparse", "dump_sparse_ids", True),
+                              ("triclinic", "dump_triclinic", True)):   # restricted triclinic bounds: reader.py:372-388
         d = _capi.DumpFile(os.path.join(GOLDEN, name + ".lammpsdump"))
         assert (d.n_frames, d.n_atoms, d.has_id) == (5, 60, has_id)
         np.testing.assert_array_equal(d.offsets[:-1], g[f"{tag}_offsets"])
@@ -276,9 +277,13 @@ def test_dump_index_and_headers_on_the_host(tmp_path):
     threaded.close()
     # layouts the reader refuses, with the reference's message where it has one
     bad = tmp_path / "bad.lammpsdump"
-    bad.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n1\nITEM: BOX BOUNDS xy xz yz pp pp pp\n0 1 0\n0 1 0\n0 1 0\n"
+    bad.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n1\nITEM: BOX BOUNDS abc origin pp pp pp\n1 0 0 0\n0 1 0 0\n0 0 1 0\n"
                    "ITEM: ATOMS id x y z\n1 0 0 0\n")
-    with pytest.raises(_capi.MdcError, match="triclinic"):
+    with pytest.raises(_capi.MdcError, match="general triclinic"):
+        _capi.DumpFile(str(bad))
+    bad.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n1\nITEM: BOX BOUNDS xy xz yz pp pp pp\n0 1 0\n0 1\n0 1 0\n"
+                   "ITEM: ATOMS id x y z\n1 0 0 0\n")
+    with pytest.raises(_capi.MdcError, match="tilt factor missing"):
         _capi.DumpFile(str(bad))
     bad.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n2\nITEM: BOX BOUNDS pp pp pp\n0 1\n0 1\n0 1\n"
                    "ITEM: ATOMS id x y z\n1 0 0 0\n2 0 0 0\n"

@@ -204,7 +204,8 @@ def test_pair_distance_minimum_image():
         assert oracle.pair_distance(p, q, box) == oracle.pair_distance(q, p, box)
 
 
-@pytest.mark.parametrize("tag,name", [("ids", "dump_ids"), ("noid", "dump_noid"), ("sparse", "dump_sparse_ids")])
+@pytest.mark.parametrize("tag,name", [("ids", "dump_ids"), ("noid", "dump_noid"), ("sparse", "dump_sparse_ids"),
+                                      ("triclinic", "dump_triclinic")])
 def test_dump_reader_oracle_matches_the_reference_reader(tag, name):
     """oracle.read_lammps_dump against what the reference's own LAMMPSDumpTrajectoryReader read from the same
     files (tests/golden/make_golden.py dumps): positions bit for bit (NaN == NaN), boxes, steps, times, offsets."""
