@@ -9,6 +9,7 @@ properties and through oracle slices that the CPU finishes in seconds:
 """
 
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -118,6 +119,20 @@ def test_rdf_overflow_of_the_undecided_row_queue(ctx, n, n_bins, frac, tri):
     fast = _rdf_counts(ctx, pos, None, box, n_bins, window, exclusion=(1, 1))
     np.testing.assert_array_equal(fast, _rdf_counts(ctx, pos, None, box, n_bins, window, exclusion=(1, 1), exact=True))
     np.testing.assert_array_equal(fast, oracle.radial_histogram(pos, pos, n_bins, window, box, exclusion=(1, 1)))
+
+
+def test_rdf_random_configurations_filter_vs_exact_kernel(ctx, monkeypatch):
+    """tools/rdf_fuzz.py with a fixed seed: 40 random configurations (sizes around the tile and sort thresholds, one or
+    two groups, cubic / orthorhombic / triclinic cells, windows from zero or above and below or beyond half the cell
+    width, 1 - 4000 bins, exclusion blocks, unwrapped coordinates, lattice points on bin edges, changing boxes) through
+    the filter kernel and through the all-FP64 kernel: every histogram equal.  (1,500 more: profiles/rdf_fuzz_r02.txt.)"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("rdf_fuzz", os.path.join(os.path.dirname(__file__), "..", "tools", "rdf_fuzz.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(sys, "argv", ["rdf_fuzz.py", "40", "11"])
+    assert mod.main() == 0
 
 
 def test_c4_binary_electrolyte_partials(ctx):
