@@ -135,6 +135,20 @@ def test_rdf_random_configurations_filter_vs_exact_kernel(ctx, monkeypatch):
     assert mod.main() == 0
 
 
+def test_sq_random_configurations_every_kernel_family_vs_fp64(ctx, monkeypatch):
+    """tools/sq_fuzz.py with a fixed seed: 20 random S(q) configurations (50 - 40,000 particles, cubic and orthorhombic
+    cells, n_points 3 - 140, q_max cuts, total / partial / pair modes, coordinates far outside the cell): the NUFFT, the
+    factored and the direct kernel against the FP64 kernel on the same wavevectors, within the error model of DESIGN.md
+    3.10.  (340 more: profiles/sq_fuzz_r02.txt.)"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("sq_fuzz", os.path.join(os.path.dirname(__file__), "..", "tools", "sq_fuzz.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(sys, "argv", ["sq_fuzz.py", "20", "7"])
+    assert mod.main() == 0
+
+
 def test_c4_binary_electrolyte_partials(ctx):
     """C4: 100k cations + 100k anions: ++, +-, -- g(r) and the partial S(q) sum rule."""
     from mdcraft_b200 import _capi
