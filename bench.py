@@ -566,6 +566,11 @@ def run_native(args, rank, world, emit=print):
             "traffic_source": ncu_source(summary),
             "issue_active": kn.get("issue_active_pct") if kn else None,
             "slots_per_pair": kn.get("slots_per_algorithmic_pair") if kn else None,
+            # the hardware-side fraction, measured in THIS run: issue slots the kernel used per second (its executed
+            # warp instructions per algorithmic pair, from the committed capture, x the pairs/s of this run) over the
+            # issue slots the device has (SMs x 4 schedulers x SM clock)
+            "frac_issue_slots": (kn["slots_per_algorithmic_pair"] / 32.0 * pairs / (gr_ms * 1e-3)
+                                 / (sm * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6)) if kn and kn.get("slots_per_algorithmic_pair") else None,
             "peak_source": f"MODEL: {sm} SMs x 4 schedulers x 32 lanes x SM clock / {SLOTS:g} issue slots per pair "
                            "(SURVEY.md 8(d) algorithmic cost); `issue_active` and `slots_per_pair` (ncu) are the hardware-side pair",
             "algorithmic": "20 FP32/INT issue slots + 1 SFU op (sqrt) + 1 shared-memory atomic per pair-distance "
