@@ -2197,8 +2197,11 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
         const int64_t total = A.items_per_frame * F;
         A.ovf = nullptr;
         if (fast) {   // (before the timed region: the allocation blocks the host)
-            const size_t ovf_bytes = (size_t)p->ctx->sm_count * p->occ_fast * RF_TJ * RF_THREADS;
-            if (p->ovf.n < ovf_bytes) {   // first filtered push: the tables start (and are left) all zero
+            // one table per block of the grid this push launches (small systems: a few blocks, not 113 MB)
+            const int64_t max_blocks = std::min<int64_t>(total, (int64_t)p->ctx->sm_count * p->occ_fast);
+            const size_t ovf_bytes = (size_t)max_blocks * RF_TJ * RF_THREADS;
+            if (p->ovf.n < ovf_bytes) {   // first filtered push (or a larger one): the tables start, and are left, all zero
+                MDC_CUDA(cudaStreamSynchronize(sk));   // no kernel of this plan still reads the old tables
                 MDC_CHECK(p->ovf.alloc(ovf_bytes));
                 MDC_CUDA(cudaMemsetAsync(p->ovf.p, 0, ovf_bytes, sk));
             }
