@@ -770,7 +770,7 @@ __device__ __forceinline__ unsigned rows_rel(FastShared *S, const uint4 *ch, int
     const bool seam = (unsigned)abs(dx) + hf.x > 0x7fffffffu || (unsigned)abs(dy) + hf.y > 0x7fffffffu ||
                       (unsigned)abs(dz) + hf.z > 0x7fffffffu;
     __syncwarp();   // the previous chunk's rows have been read by every lane
-    S->rel[threadIdx.x >> 5][lane] = make_float4((float)dx, (float)dy, (float)dz, 0.f);
+    S->rel[threadIdx.x >> 5][lane] = make_float4((float)dx, (float)dy, (float)dz, __uint_as_float(pj.w));   // + exclusion block of j
     const unsigned m = __ballot_sync(0xffffffffu, seam);   // also orders the scratch writes before the reads below
     __syncwarp();
     return m;
@@ -1344,7 +1344,7 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
     // the same in the relative-coordinate form (rows_rel).  The group's particles then live in ux / uy / uz as MINUS their
     // FP32 differences to the centre of the group's box (the same twelve registers: the integer form is not used for
     // such a group), packed (0, 1) and (2, 3); groups whose box is wider than an eighth of the cell keep the integers.
-    constexpr bool REL = CULL && EXT && !HAS_OK;
+    constexpr bool REL = CULL && EXT;
     bool rel_ok = false;
     // shared address of the warp's scratch row 0, minus 16 c for the chunk in flight: a value the compiler must keep
     // (it otherwise rebuilds the address from the thread index for every row)
@@ -1383,6 +1383,31 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
         for (int u = 0; u < RF_IPT; ++u)
             if (adf[u] > thr) und |= 1u << u;
         if (und) park_row(S, j, und, group, true, 1u);
+    };
+    // one row with ok flags (tiles on the diagonal, ragged tiles, block exclusion): the row's exclusion block rides in
+    // the fourth component of its scratch entry
+    auto row_rel_ok = [&](int j, auto wrap) {
+        const float4 r = rel_row(j);
+        unsigned ok[RF_IPT];
+#pragma unroll
+        for (int u = 0; u < RF_IPT; ++u) {
+            ok[u] = 1u;
+            if (EXCL) ok[u] = bi[u] != (int)__float_as_uint(r.w);
+            if (CHECK) {
+                const int64_t ig = i0 + rf_il_of(group, u);
+                ok[u] = ok[u] && (ig < na) && (!diag || (j0 + j) > ig);
+            }
+        }
+        unsigned long long v[2];
+        vs_rel(r, wrap, v);
+        float adf[4];
+        if (bin_count4<true, false, SH>(v[0], v[1], magic, nmagic, neg1, thr, hbase, trash_addr, one, ok, adf)) {
+            unsigned und = 0;
+#pragma unroll
+            for (int u = 0; u < RF_IPT; ++u)
+                if (adf[u] > thr && ok[u]) und |= 1u << u;
+            if (und) park_row(S, j, und, group, true, 1u);
+        }
     };
     auto row_rel = [&](int j, int c, auto wrap) {
         float adf[4];
@@ -1511,6 +1536,19 @@ __device__ __forceinline__ void tile_pairs_fast(const TileCtx *Tp, FastShared *S
                     continue;
                 }
                 unsigned m = rows_in_reach(S, ib + 2, c, nj);
+                if (REL && rel_ok) {   // diagonal / edge tiles and block exclusion: the relative rows with their ok flags
+                    const unsigned seam = rows_rel(S, ib + 2, c, nj);
+                    asm volatile("mov.u32 %0, %1;" : "=r"(rel_at) : "r"((unsigned)__cvta_generic_to_shared(S->rel[threadIdx.x >> 5]) - 16u * (unsigned)c));
+                    if (seam == 0u && __popc(m) >= 29) {
+                        const int je = min(nj, c + 32);
+#pragma unroll RF_UNROLL
+                        for (int j = c; j < je; ++j) row_rel_ok(j, No());
+                        continue;
+                    }
+                    walk(m & ~seam, c, [&](int j) { row_rel_ok(j, No()); });
+                    walk(m & seam, c, [&](int j) { row_rel_ok(j, Yes()); });
+                    continue;
+                }
                 if (__popc(m) >= 29) {   // (nearly) all of them: the plain loop has less overhead per row than the bit walk
                     const int je = min(nj, c + 32);
 #pragma unroll RF_UNROLL
