@@ -125,7 +125,7 @@ def test_rdf_random_configurations_filter_vs_exact_kernel(ctx, monkeypatch):
     """tools/rdf_fuzz.py with a fixed seed: 40 random configurations (sizes around the tile and sort thresholds, one or
     two groups, cubic / orthorhombic / triclinic cells, windows from zero or above and below or beyond half the cell
     width, 1 - 4000 bins, exclusion blocks, unwrapped coordinates, lattice points on bin edges, changing boxes) through
-    the filter kernel and through the all-FP64 kernel: every histogram equal.  (1,500 more: profiles/rdf_fuzz_r02.txt.)"""
+    the filter kernel and through the all-FP64 kernel: every histogram equal.  (3,500 more: profiles/rdf_fuzz_r02.txt.)"""
     import importlib.util
 
     spec = importlib.util.spec_from_file_location("rdf_fuzz", os.path.join(os.path.dirname(__file__), "..", "tools", "rdf_fuzz.py"))
@@ -139,7 +139,7 @@ def test_sq_random_configurations_every_kernel_family_vs_fp64(ctx, monkeypatch):
     """tools/sq_fuzz.py with a fixed seed: 20 random S(q) configurations (50 - 40,000 particles, cubic and orthorhombic
     cells, n_points 3 - 140, q_max cuts, total / partial / pair modes, coordinates far outside the cell): the NUFFT, the
     factored and the direct kernel against the FP64 kernel on the same wavevectors, within the error model of DESIGN.md
-    3.10.  (340 more: profiles/sq_fuzz_r02.txt.)"""
+    3.10.  (540 more: profiles/sq_fuzz_r02.txt.)"""
     import importlib.util
 
     spec = importlib.util.spec_from_file_location("sq_fuzz", os.path.join(os.path.dirname(__file__), "..", "tools", "sq_fuzz.py"))
