@@ -383,6 +383,13 @@ int  mdc_elapsed_ms(mdc_ctx *ctx, float *ms);
 int  mdc_sq_last_push_stats(mdc_sq_plan *plan, float *kernel_ms, int *n_launches);
 int  mdc_rdf_last_push_stats(mdc_rdf_plan *plan, float *kernel_ms, int *n_launches);
 
+/* Which kernel path the LAST frame block of the last mdc_rdf_push took (diagnostics, tests, the verbose run log of the
+ * classes -- base.py:378-384 logs what the process farm does): info = {filter kernel (1) or FP64 kernel for every pair
+ * (0), frames in Hilbert order with culling, words per extended-histogram copy (0: range-tested update), words between
+ * consecutive bins of a copy (32: one copy per bank), relative-coordinate rows, a triclinic frame in the block,
+ * capacity of the undecided-row queue, frames in the block}. */
+int  mdc_rdf_plan_info(mdc_rdf_plan *plan, int info[8]);
+
 /* ---- on-box probes (recorded next to MEASURED_PEAKS.json by bench.py) ---- */
 
 /*

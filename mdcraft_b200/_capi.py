@@ -130,6 +130,7 @@ SIGNATURES = {
     "mdc_ncdf_read_var": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int]),
     "mdc_sq_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
     "mdc_rdf_last_push_stats": (c_int, [c_void_p, _fp, _ip]),
+    "mdc_rdf_plan_info": (c_int, [c_void_p, _ip]),
     "mdc_probe_rate": (c_int, [c_void_p, c_int, _dp]),
     "mdc_probe_sincos": (c_int, [c_void_p, c_int, _dp]),
 }
@@ -767,3 +768,10 @@ class RdfPlan:
         ms, nl = c_float(), c_int()
         _check(lib().mdc_rdf_last_push_stats(self._h, byref(ms), byref(nl)))
         return ms.value, nl.value
+
+    def info(self) -> dict:
+        """Kernel path of the last frame block pushed (``mdc_rdf_plan_info``)."""
+        a = (c_int * 8)()
+        _check(lib().mdc_rdf_plan_info(self._h, a))
+        return {"filter": bool(a[0]), "sorted": bool(a[1]), "ext_words": a[2], "copies_interleaved": a[3] == 32,
+                "relative_rows": bool(a[4]), "triclinic": bool(a[5]), "queue": a[6], "frames": a[7]}

@@ -156,7 +156,19 @@ class _RunLog:
         if plan is not None and hasattr(plan, "info"):
             try:
                 info = plan.info()
-                detail = f", algorithm {info['algo']}" + (f" (nf = {info['nf']}, w = {info['w']})" if info["algo"] == "nufft" else "")
+                if "algo" in info:          # S(q) plans
+                    detail = f", algorithm {info['algo']}" + (f" (nf = {info['nf']}, w = {info['w']})" if info["algo"] == "nufft" else "")
+                else:                       # g(r) plans: the kernel path of the last frame block
+                    parts = ["filter kernel" if info["filter"] else "FP64 kernel for every pair"]
+                    if info["triclinic"]:
+                        parts.append("triclinic cell")
+                    if info["sorted"]:
+                        parts.append("Hilbert-ordered frames")
+                    if info["relative_rows"]:
+                        parts.append("relative rows")
+                    if info["ext_words"]:
+                        parts.append("one histogram copy per bank" if info["copies_interleaved"] else "extended histograms")
+                    detail = ", " + ", ".join(parts)
             except Exception:  # pragma: no cover - diagnostics only
                 detail = ""
         logger.info("%s: %d frames in %.3f s (%.1f frames/s) on cuda:%s%s", type(a).__name__, a.n_frames, dt,

@@ -1816,6 +1816,7 @@ struct mdc_rdf_plan {
     size_t smem = 0, smem_fast = 0;
     int64_t n_frames = 0;
     int last_launches = 0;
+    int last_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // mdc_rdf_plan_info: the kernel path of the last frame block pushed
 };
 
 namespace {
@@ -2245,6 +2246,18 @@ extern "C" int mdc_rdf_push(mdc_rdf_plan *p, const float *pos_a, const float *po
             }
             A.ovf = p->ovf.p;
         }
+        {
+            bool any_tri = false;
+            for (int f = 0; f < F; ++f) any_tri = any_tri || ht[f0 + f].on != 0;
+            p->last_info[0] = fast ? 1 : 0;
+            p->last_info[1] = sorted ? 1 : 0;
+            p->last_info[2] = A.ext_k;
+            p->last_info[3] = A.hist_ks;
+            p->last_info[4] = (fast && sorted && A.rel) ? 1 : 0;
+            p->last_info[5] = any_tri ? 1 : 0;
+            p->last_info[6] = fast ? A.qcap : 0;
+            p->last_info[7] = F;
+        }
         const int ti = p->st.n_timed < 8 ? p->st.n_timed : -1;
         if (ti >= 0) MDC_CUDA(cudaEventRecord(p->st.k0[ti], sk));
         if (fast) {
@@ -2321,6 +2334,13 @@ extern "C" int mdc_rdf_last_push_stats(mdc_rdf_plan *p, float *kernel_ms, int *n
     MDC_CUDA(cudaSetDevice(p->ctx->device));
     if (kernel_ms) MDC_CHECK(p->st.kernel_ms(kernel_ms));
     if (n_launches) *n_launches = p->last_launches;
+    return MDC_OK;
+}
+
+extern "C" int mdc_rdf_plan_info(mdc_rdf_plan *p, int info[8])
+{
+    if (!p || !info) return fail(MDC_ERR_INVALID, "mdc_rdf_plan_info: NULL argument");
+    memcpy(info, p->last_info, sizeof(p->last_info));
     return MDC_OK;
 }
 

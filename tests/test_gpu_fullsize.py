@@ -60,6 +60,14 @@ def test_c2_rdf_full_size(ctx):
     np.testing.assert_array_equal(excl, fast - np.eye(1, 200, 0, dtype=np.int64)[0] * n)
     # ideal gas: the fraction of ordered pairs within L/2 is pi/6, to ~1/sqrt(pairs)
     assert abs(excl.sum() / (n * (n - 1.0)) - np.pi / 6) < 2e-4
+    # the path the headline runs: filter kernel, Hilbert-ordered frames, relative rows, one histogram copy per bank
+    from mdcraft_b200 import _capi
+
+    plan = _capi.RdfPlan(ctx, 200, rng, n, None, (1, 1))
+    plan.push(pos[None], None, box, n_frames=1)
+    info = plan.info()
+    plan.close()
+    assert info["filter"] and info["sorted"] and info["relative_rows"] and info["copies_interleaved"] and not info["triclinic"], info
     # a slab of i against all j, bit-exact against the CPU restatement of the reference
     slab = _rdf_counts(ctx, pos[:512], pos, box, 200, rng)
     np.testing.assert_array_equal(slab, oracle.radial_histogram(pos[:512], pos, 200, rng, box))

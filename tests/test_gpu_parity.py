@@ -250,6 +250,16 @@ def test_rdf_triclinic_filter_vs_oracle(box, n_a, n_b, excl, n_bins, frac):
     rcut = (0.0, frac * float(_cell_widths(m).min()))
     got = radial_histogram(a, b, n_bins=n_bins, range_=rcut, dimensions=box, exclusion=excl)
     np.testing.assert_array_equal(got, oracle.radial_histogram(a, b, n_bins, rcut, box, exclusion=excl))
+    # ... and it IS the filter kernel that ran (mdc_rdf_plan_info), the FP64 kernel beyond half the width
+    from mdcraft_b200 import _capi
+
+    ctx = _capi.context(0)
+    for r1, filt in ((rcut[1], True), (0.62 * float(_cell_widths(m).min()), False)):
+        plan = _capi.RdfPlan(ctx, 57, (0.0, r1), len(a), None if n_b is None else len(b), excl)
+        plan.push(a[None], None if n_b is None else b[None], box, n_frames=1)
+        info = plan.info()
+        plan.close()
+        assert info["triclinic"] and info["filter"] == filt and info["sorted"] == (filt and min(len(a), len(b)) >= 4096), info
     # a window that starts above zero, and one beyond half the width (exact kernel)
     for r0, r1 in ((0.3 * rcut[1], rcut[1]), (0.0, 0.62 * float(_cell_widths(m).min()))):
         got = radial_histogram(a[:3000], b[:3500], n_bins=57, range_=(r0, r1), dimensions=box, exclusion=excl)
