@@ -417,3 +417,39 @@ def test_run_together_steps_different_trajectories_in_lockstep(caplog):
     uc = synthetic.Universe(synthetic.MemoryTrajectory(rng.random((6, 5, 3)).astype(np.float32), dims))
     with pytest.raises(ValueError, match="same number of selected frames"):
         run_together([a, _CountingAnalysis(uc)])
+
+
+def test_run_log_names_the_kernel_path_of_each_plan(caplog):
+    """The finish line of the verbose run log (base.py:514-515 logs the farm's wall time; here: device, frames/s and what
+    the plan ran): S(q) plans report their algorithm, g(r) plans the kernel path of mdc_rdf_plan_info."""
+    import logging
+
+    from mdcraft_b200 import synthetic
+
+    rng = np.random.default_rng(4)
+    dims = np.array([5, 5, 5, 90, 90, 90], np.float32)
+    u = synthetic.Universe(synthetic.MemoryTrajectory(rng.random((3, 9, 3)).astype(np.float32), dims))
+
+    class FakePlan:
+        def __init__(self, info):
+            self._info = info
+
+        def info(self):
+            return self._info
+
+    cases = (({"algo": "nufft", "nf": 256, "w": 12}, "algorithm nufft (nf = 256, w = 12)"),
+             ({"algo": "factored", "nf": 0, "w": 0}, "algorithm factored"),
+             ({"filter": True, "sorted": True, "ext_words": 367, "copies_interleaved": True, "relative_rows": True,
+               "triclinic": False, "queue": 1024, "frames": 3},
+              "filter kernel, Hilbert-ordered frames, relative rows, one histogram copy per bank"),
+             ({"filter": True, "sorted": False, "ext_words": 640, "copies_interleaved": False, "relative_rows": False,
+               "triclinic": True, "queue": 4096, "frames": 3}, "filter kernel, triclinic cell, extended histograms"),
+             ({"filter": False, "sorted": False, "ext_words": 0, "copies_interleaved": False, "relative_rows": False,
+               "triclinic": True, "queue": 0, "frames": 3}, "FP64 kernel for every pair, triclinic cell"))
+    for info, want in cases:
+        a = _CountingAnalysis(u, verbose=True)
+        a._plan = FakePlan(info)
+        caplog.clear()
+        with caplog.at_level(logging.INFO, logger="mdcraft_b200.analysis"):
+            a.run()
+        assert caplog.records[-1].getMessage().endswith(want), caplog.records[-1].getMessage()
